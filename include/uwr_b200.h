@@ -1,0 +1,205 @@
+/*
+ * uwr_b200 — C ABI of the B200-native hot path for the restoration transformers of
+ * KarthikSundar2002/Underwater-Image-Restoration (AST / SpectralTransformer / NewBigFRFN
+ * forward + backward, their losses and the optimizer step).
+ *
+ * Conventions (SURVEY.md §8b "New C-ABI"):
+ *   - every pointer is a DEVICE pointer valid on `stream` unless it says "host";
+ *   - tensors are dense fp32 unless stated; "tokens" means (B, L=H*W, C) row-major, i.e. NHWC;
+ *   - no allocation, no synchronisation, no global state inside a call; scratch comes from the
+ *     caller (`*_workspace_bytes` tells how much);
+ *   - return 0 on success, negative on error; uwr_last_error() gives the message.
+ *
+ * The reference is pure PyTorch-eager (no FFI of its own); each entry cites the reference
+ * Python that it replaces (paths relative to the reference root).
+ */
+#ifndef UWR_B200_H
+#define UWR_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct CUstream_st* uwr_stream_t; /* == cudaStream_t */
+
+/* ---- library ---------------------------------------------------------------------------- */
+const char* uwr_last_error(void);
+int uwr_abi_version(void);
+int uwr_device_sm_count(void);
+
+/* ---- GEMM (nn.Linear fwd/bwd: AST.py:47-48,104,297,302,332,337; block.py:158-160) --------
+ * C[M,N] = epilogue( opA(A)[M,K] * opB(B)[K,N] ), TF32 tensor-core math (operands rounded to
+ * nearest tf32 in-kernel), fp32 accumulate.
+ *   a_km = 0: A stored [M][K] (lda = row stride)       a_km = 1: A stored [K][M]
+ *   b_nk = 1: B stored [N][K] (nn.Linear weight)       b_nk = 0: B stored [K][N]
+ *   B2/bias2/n_split: optional second weight segment: rows >= n_split of the STORED B come from
+ *                     B2 (to_q | to_kv fused projection, AST.py:59-60): output columns when
+ *                     b_nk = 1, contraction rows when b_nk = 0.
+ *   epilogue: v = acc + bias[n]; v *= rowscale[m / rows_per_group] (if rowscale);
+ *             UWR_EPI_RESID: v += R[m,n];  UWR_EPI_MUL_DGELU: v *= gelu'(R[m,n]).
+ *   a_km = 1 (weight gradient, contraction over tokens): rowscale indexes the K rows
+ *             (DropPath scale of the incoming gradient), colsum[M] = sum_k s_k A[k][m]
+ *             (bias gradient) is produced when non-NULL, and the contraction is split over
+ *             CTAs through `workspace` (uwr_gemm_workspace_bytes).
+ */
+enum { UWR_EPI_NONE = 0, UWR_EPI_RESID = 1, UWR_EPI_MUL_DGELU = 2 };
+
+typedef struct {
+    const float* A;
+    long long lda;
+    int a_km;
+    const float* B;
+    long long ldb;
+    int b_nk;
+    const float* B2;
+    int n_split;
+    float* C;
+    long long ldc;
+    int M, N, K;
+    const float* bias;
+    const float* bias2;
+    int epilogue;
+    const float* R;
+    long long ldr;
+    const float* rowscale;
+    int rows_per_group;
+    float* colsum;
+    float* workspace;
+    size_t workspace_bytes;
+} uwr_gemm_desc;
+
+size_t uwr_gemm_workspace_bytes(int M, int N, int K, int a_km);
+int uwr_gemm_tf32(const uwr_gemm_desc* d, uwr_stream_t stream);
+
+/* ---- LayerNorm over C (nn.LayerNorm eps 1e-5: AST.py:521,534,593,622) ------------------- */
+int uwr_layernorm_fwd(const float* x, const float* gamma, const float* beta, float* y,
+                      float* mean, float* rstd, long long rows, int C, float eps,
+                      uwr_stream_t stream);
+/* dx = dres (optional pass-through residual gradient) + LN backward; dgamma/dbeta reduced
+ * deterministically through `partials` (uwr_layernorm_bwd_workspace_bytes). */
+size_t uwr_layernorm_bwd_workspace_bytes(long long rows, int C);
+int uwr_layernorm_bwd(const float* dy, const float* x, const float* gamma, const float* mean,
+                      const float* rstd, const float* dres, float* dx, float* dgamma,
+                      float* dbeta, float* partials, long long rows, int C, uwr_stream_t stream);
+
+/* ---- adaptive sparse window attention (WindowAttention_sparse.forward, AST.py:187-219;
+ *      roll / window_partition / window_reverse, AST.py:377-402,596-618; shift mask 568-588) --
+ * qkv: tokens (B, H*W, ld_qkv) with q at column q_off + h*HD, k at k_off + h*HD, v at
+ * v_off + h*HD.  kv_ptr may differ from q_ptr (cross attention, block.py:185-188).
+ * out: tokens (B, H*W, ld_out) written at column h*HD in ORIGINAL token order (the cyclic
+ * shift and the 8x8 window partition are address arithmetic).  P = w0*softmax(S) + w1*relu(S)^2
+ * with (w0,w1) = softmax(w_param) evaluated on the device.  HD in {8,16,32,64,128}.
+ */
+typedef struct {
+    const float* q;
+    long long ld_q;
+    int q_off;
+    const float* kv;
+    long long ld_kv;
+    int k_off;
+    int v_off;
+    const float* bias_table; /* (225, heads) */
+    const float* w_param;    /* (2,) raw parameter; NULL => plain softmax attention */
+    int B, H, W, heads, head_dim, shift;
+    float scale;
+} uwr_attn_desc;
+
+int uwr_window_attn_fwd(const uwr_attn_desc* d, float* out, long long ld_out, uwr_stream_t stream);
+size_t uwr_window_attn_bwd_workspace_bytes(const uwr_attn_desc* d);
+/* dq/dk/dv are written with the same (ld, offset) addressing as q/k/v into dq_buf/dkv_buf.
+ * dbias_table (225,heads) and dw (2,) are overwritten. */
+int uwr_window_attn_bwd(const uwr_attn_desc* d, const float* dout, long long ld_dout,
+                        float* dq_buf, float* dkv_buf, float* dbias_table, float* dw,
+                        float* workspace, uwr_stream_t stream);
+
+/* ---- depthwise 3x3 conv on tokens with fused GELUs (LeFF / FRFN: AST.py:299-301,318,
+ *      334-336,365-367) ---------------------------------------------------------------------
+ * u: tokens (B,H,W,ld_u) pre-activation of linear1, channels [0,Ch) are convolved:
+ *   v  = dwconv3x3(gelu(u)) + bias        (saved for backward when v != NULL)
+ *   h2 = gelu(v)                          (mode 0, LeFF)
+ *   h2 = gelu(v) * gelu(u[:, Ch + c])     (mode 1, FRFN gate; u has 2*Ch channels)
+ */
+int uwr_dwconv_gelu_fwd(const float* u, long long ld_u, const float* weight /*(Ch,1,3,3)*/,
+                        const float* bias, float* v, float* h2, int B, int H, int W, int Ch,
+                        int mode, uwr_stream_t stream);
+size_t uwr_dwconv_gelu_bwd_workspace_bytes(int B, int H, int W, int Ch);
+/* dh2 -> du (ld_u wide, both halves in mode 1), dweight (Ch,1,3,3), dbias (Ch). */
+int uwr_dwconv_gelu_bwd(const float* dh2, const float* u, long long ld_u, const float* v,
+                        const float* weight, float* du, float* dweight, float* dbias,
+                        float* workspace, int B, int H, int W, int Ch, int mode,
+                        uwr_stream_t stream);
+
+/* ---- convolutions at the model boundary and between scales ---------------------------------
+ * InputProj  (AST.py:447-466): Conv3x3(3->Cout)+LeakyReLU(slope) NCHW image -> tokens.
+ * OutputProj (AST.py:470-493, 920-921): tokens -> Conv3x3(Cin->3) [+ image residual] -> NCHW.
+ * Downsample (AST.py:408-424): Conv4x4 s2 p1 as im2col (K order ky,kx,ci) + uwr_gemm_tf32.
+ * Upsample   (AST.py:428-443): ConvTranspose2x2 s2 as uwr_gemm_tf32 + pixel scatter.
+ */
+int uwr_input_proj_fwd(const float* img, const float* weight, const float* bias, float* tokens,
+                       int B, int H, int W, int Cin, int Cout, float slope, uwr_stream_t stream);
+size_t uwr_input_proj_bwd_workspace_bytes(int B, int H, int W, int Cin, int Cout);
+int uwr_input_proj_bwd(const float* dtokens, const float* tokens, const float* img,
+                       float* dweight, float* dbias, float* workspace, int B, int H, int W,
+                       int Cin, int Cout, float slope, uwr_stream_t stream);
+int uwr_output_proj_fwd(const float* tokens, long long ld, const float* weight, const float* bias,
+                        const float* residual_img, float* out_img, int B, int H, int W, int Cin,
+                        uwr_stream_t stream);
+size_t uwr_output_proj_bwd_workspace_bytes(int B, int H, int W, int Cin);
+int uwr_output_proj_bwd(const float* dout_img, const float* tokens, long long ld,
+                        const float* weight, float* dtokens, float* dweight, float* dbias,
+                        float* workspace, int B, int H, int W, int Cin, uwr_stream_t stream);
+int uwr_im2col_4x4s2(const float* tokens, long long ld, float* col, int B, int H, int W, int C,
+                     uwr_stream_t stream);
+int uwr_col2im_4x4s2(const float* dcol, float* dtokens, int B, int H, int W, int C,
+                     uwr_stream_t stream);
+/* g: (B*H*W, Cout*4) GEMM result with column (co,dy,dx); out tokens (B,2H,2W,ld_out). */
+int uwr_pixel_scatter_2x2(const float* g, const float* bias, float* out, long long ld_out, int B,
+                          int H, int W, int Cout, uwr_stream_t stream);
+int uwr_pixel_gather_2x2(const float* dout, long long ld_dout, float* dg, int B, int H, int W,
+                         int Cout, uwr_stream_t stream);
+/* strided 2-D copy / accumulate: dst[r, 0:cols] (op)= src[r, 0:cols]  (skip concat, AST.py:904) */
+int uwr_copy2d(const float* src, long long ld_src, float* dst, long long ld_dst, long long rows,
+               int cols, int accumulate, uwr_stream_t stream);
+/* column sums of a (rows, cols) matrix, deterministic two-pass; workspace >= 1024*cols floats */
+int uwr_colsum(const float* x, long long ld, float* out, float* workspace, long long rows,
+               int cols, uwr_stream_t stream);
+
+/* ---- losses (LossFunction.getloss, src/Losses/losses.py:54-160) ---------------------------
+ * kind: 0 "L1" (55-57), 1 "L1withColor" (58-66 + luminanceLoss.py:5-21), 2 "charbonnier"
+ * (80-81,189-193), 3 "L2" (76-78).  out[0] = loss, grad = dLoss/dpred (NULL to skip).
+ * `batch_divisor` is the B used in the reference's "/ (B*C)" (pass the GLOBAL batch under
+ * data parallelism).  workspace >= 4*1024 floats.
+ */
+int uwr_pixel_loss(const float* pred, const float* truth, float* out, float* grad,
+                   float* workspace, int kind, int B, int C, int H, int W, int batch_divisor,
+                   uwr_stream_t stream);
+/* focal frequency loss (third-party focal_frequency_loss 0.3.0, ctor losses.py:48):
+ * planes = B*C images of S x S (S power of two <= 1024). workspace: see *_workspace_bytes. */
+size_t uwr_ffl_workspace_bytes(int planes, int S);
+int uwr_ffl_loss(const float* pred, const float* truth, float* out, float* grad, float* workspace,
+                 int planes, int S, uwr_stream_t stream);
+
+/* ---- optimizer step (ModelTrainer.py:87-88,197-204): clip_grad_norm_(1.0) + Adam/AdamW -----
+ * tensor tables are device arrays of pointers; `offsets` (n_tensors+1 entries, offsets[0]=0) is
+ * the running element count of the virtual concatenation.
+ * norm_out[0] = total L2 norm, norm_out[1] = clip coefficient min(1, max_norm/(norm+1e-6)).
+ * step_dev (optional device int) overrides `step` so a captured CUDA graph can be replayed.
+ */
+int uwr_grad_norm(const float* const* grads, const long long* offsets, int n_tensors,
+                  long long total_elems, float max_norm, float grad_prescale, float* norm_out,
+                  float* workspace /* >= 4096 floats */, uwr_stream_t stream);
+int uwr_adam_step(float* const* params, const float* const* grads, float* const* exp_avg,
+                  float* const* exp_avg_sq, const long long* offsets, int n_tensors,
+                  long long total_elems, const float* clip_coef /* device, may be NULL */,
+                  float grad_prescale, float lr, float beta1, float beta2, float eps,
+                  float weight_decay, int decoupled, int step, const int* step_dev,
+                  uwr_stream_t stream);
+int uwr_increment_i32(int* counter, uwr_stream_t stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* UWR_B200_H */

@@ -1,0 +1,104 @@
+"""Module-level parity: uwr AST (CUDA kernels) vs the CPU oracle on identical weights and inputs.
+Tolerance (north star): outputs and gradients within 1e-3 relative (per-tensor relative L2;
+tiny-norm tensors are judged against the global gradient scale)."""
+import pytest
+import torch
+
+from conftest import rel_l2
+
+pytestmark = pytest.mark.gpu
+
+
+def _pair(B, S, seed=2024):
+    g = torch.Generator().manual_seed(seed)
+    raw = torch.rand(B, 3, S, S, generator=g) * 2 - 1
+    ref = torch.rand(B, 3, S, S, generator=g) * 2 - 1
+    return raw, ref
+
+
+def _run(B, S, img_size, train, report):
+    from oracle import ast_oracle, losses_oracle
+    from uwr.ast import AST, DropPath
+    torch.manual_seed(1234)
+    model = AST(img_size=img_size)
+    sd_cpu = {k: v.detach().clone() for k, v in model.state_dict().items()}
+    model = model.cuda()
+    raw, ref = _pair(B, S)
+
+    drop = {}
+    if train:
+        model.train()
+        g = torch.Generator().manual_seed(7)
+        for name, mod in model.named_modules():
+            if isinstance(mod, DropPath):
+                keep = 1.0 - mod.drop_prob
+                pre = name[: -len("drop_path")]
+                # the reference draws one mask for the attention residual and one for the MLP residual
+                ma = torch.bernoulli(torch.full((B,), keep), generator=g) / keep
+                mm = torch.bernoulli(torch.full((B,), keep), generator=g) / keep
+                drop[pre] = (ma, mm)
+        # inject: our DropPath.scale() is called once per residual, attention first
+        for name, mod in model.named_modules():
+            if isinstance(mod, DropPath):
+                pre = name[: -len("drop_path")]
+                seq = list(drop[pre]) if (pre + "attn.w") in sd_cpu else [drop[pre][1]]
+                mod._seq = seq
+
+                def scale(batch, device, _m=mod):
+                    return _m._seq.pop(0).to(device).float().contiguous()
+                mod.scale = scale
+    else:
+        model.eval()
+
+    out = model(raw.cuda())
+    loss = (out - ref.cuda()).abs().mean() / (B * 3)
+    loss.backward()
+
+    sd_o = {k: (v.clone().requires_grad_() if v.is_floating_point() else v) for k, v in sd_cpu.items()}
+    dsc = {k: (a if (k + "attn.w") in sd_cpu else None, m) for k, (a, m) in drop.items()}
+    out_o = ast_oracle.ast_forward(sd_o, raw, img_size=img_size, drop_scales=dsc)
+    loss_o = losses_oracle.l1(out_o, ref)
+    loss_o.backward()
+
+    e_out = rel_l2(out, out_o)
+    e_res = rel_l2(out - raw.cuda(), out_o - raw)   # the network's own contribution (harder)
+    gnorm = torch.sqrt(sum((v.grad.double() ** 2).sum() for v in sd_o.values() if v.is_floating_point())).item()
+    worst, tot = (0.0, ""), 0.0
+    for name, p in model.named_parameters():
+        go = sd_o[name].grad.double()
+        d = (p.grad.double().cpu() - go).norm().item()
+        tot += d * d
+        r = d / max(go.norm().item(), 1e-3 * gnorm)
+        if r > worst[0]:
+            worst = (r, name)
+    e_grad = tot ** 0.5 / gnorm
+    report.append((B, S, train, e_out, e_res, e_grad, worst))
+    print(f"AST parity B={B} S={S} train={train}: out {e_out:.2e} residual {e_res:.2e} "
+          f"grads(global) {e_grad:.2e} worst tensor {worst[1]} {worst[0]:.2e} "
+          f"loss {loss.item():.6e} vs {loss_o.item():.6e}")
+    assert abs(loss.item() - loss_o.item()) < 1e-3 * abs(loss_o.item())
+    assert e_out < 1e-3
+    assert e_res < 1e-3
+    assert e_grad < 1e-3
+    assert worst[0] < 5e-3, worst
+
+
+def test_ast_eval_128():
+    _run(2, 128, 128, False, [])
+
+
+def test_ast_train_droppath_128():
+    _run(2, 128, 128, True, [])
+
+
+def test_ast_eval_256():
+    _run(1, 256, 256, False, [])
+
+
+def test_registry_surface():
+    import uwr
+    assert uwr.get_names()[-1] == "AST"
+    with pytest.raises(KeyError):
+        uwr.init_model("nope")
+    m = uwr.init_model("AST", use_dwt="Fourier")
+    assert len(m.state_dict()) == 274

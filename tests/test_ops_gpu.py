@@ -1,0 +1,317 @@
+"""Op-level parity of every uwr CUDA kernel family against fp64 PyTorch math on the same GPU
+(the oracle's functions are device-agnostic torch code, so the attention check calls
+oracle.ast_oracle.window_attention directly).  Tolerance: TF32 operands, fp32 accumulate ->
+relative L2 <= 1e-3 (north star); pure fp32 kernels <= 2e-5."""
+import math
+
+import pytest
+import torch
+import torch.nn.functional as F
+
+from conftest import rel_l2
+
+pytestmark = pytest.mark.gpu
+TOL_TF32 = 1e-3
+TOL_FP32 = 2e-5
+
+
+@pytest.fixture(scope="module")
+def ops():
+    from uwr import ops as o
+    return o
+
+
+def _r(*shape, seed=0, scale=1.0):
+    g = torch.Generator(device="cpu").manual_seed(seed)
+    return (torch.randn(*shape, generator=g) * scale).cuda()
+
+
+# ------------------------------------------------------------------------------------------ GEMM
+@pytest.mark.parametrize("M,N,K", [(256, 128, 64), (200, 96, 72), (1024, 32, 128), (128, 2048, 512), (64, 64, 32),
+                                   (4096, 256, 64)])
+def test_gemm_nt_bias(ops, M, N, K):
+    x, w, b = _r(M, K, seed=1), _r(N, K, seed=2, scale=0.1), _r(N, seed=3)
+    y = ops.linear(x, w, b)
+    ref = x.double() @ w.double().t() + b.double()
+    assert rel_l2(y, ref) < TOL_TF32
+
+
+def test_gemm_segmented_and_strided(ops):
+    M, C = 512, 64
+    x = _r(M, 2 * C, seed=4)[:, :C]  # strided view, lda = 2C
+    wq, wkv = _r(C, C, seed=5, scale=0.1), _r(2 * C, C, seed=6, scale=0.1)
+    bq, bkv = _r(C, seed=7), _r(2 * C, seed=8)
+    y = ops.linear(x, wq, bq, weight2=wkv, bias2=bkv)
+    ref = torch.cat([x.double() @ wq.double().t() + bq.double(), x.double() @ wkv.double().t() + bkv.double()], 1)
+    assert rel_l2(y, ref) < TOL_TF32
+    dy = _r(M, 3 * C, seed=9)
+    dx = ops.linear_dgrad(dy, wq, weight2=wkv)
+    refdx = dy.double() @ torch.cat([wq, wkv], 0).double()
+    assert rel_l2(dx, refdx) < TOL_TF32
+
+
+def test_gemm_residual_rowscale(ops):
+    B, L, K, N = 4, 256, 128, 64
+    x, w, b, r = _r(B * L, K, seed=1), _r(N, K, seed=2, scale=0.1), _r(N, seed=3), _r(B * L, N, seed=4)
+    s = torch.tensor([0.0, 1.25, 1.25, 0.0]).cuda()
+    y = ops.linear(x, w, b, residual=r, rowscale=s, rows_per_group=L)
+    ref = r.double() + s.double().repeat_interleave(L)[:, None] * (x.double() @ w.double().t() + b.double())
+    assert rel_l2(y, ref) < TOL_TF32
+    dx = ops.linear_dgrad(r, w, rowscale=s, rows_per_group=L)
+    refdx = (s.double().repeat_interleave(L)[:, None] * r.double()) @ w.double()
+    assert rel_l2(dx, refdx) < TOL_TF32
+
+
+@pytest.mark.parametrize("M,N,K", [(8192, 128, 32), (65536, 256, 64), (1000, 96, 72), (512, 2048, 512)])
+def test_gemm_wgrad_splitk_colsum(ops, M, N, K):
+    dy, x = _r(M, N, seed=1), _r(M, K, seed=2)
+    dW, db = ops.linear_wgrad(dy, x)
+    assert rel_l2(dW, dy.double().t() @ x.double()) < TOL_TF32
+    assert rel_l2(db, dy.double().sum(0)) < TOL_FP32 * 10
+
+
+def test_gemm_wgrad_kscale(ops):
+    B, L, N, K = 4, 1024, 64, 32
+    dy, x = _r(B * L, N, seed=1), _r(B * L, K, seed=2)
+    s = torch.tensor([1.1, 0.0, 1.1, 1.1]).cuda()
+    dW, db = ops.linear_wgrad(dy, x, rowscale=s, rows_per_group=L)
+    sd = s.double().repeat_interleave(L)[:, None] * dy.double()
+    assert rel_l2(dW, sd.t() @ x.double()) < TOL_TF32
+    assert rel_l2(db, sd.sum(0)) < TOL_FP32 * 10
+
+
+def test_gemm_dgelu_epilogue(ops):
+    M, N, K = 512, 128, 64
+    x, w, v = _r(M, K, seed=1), _r(N, K, seed=2, scale=0.1), _r(M, N, seed=3)
+    out = torch.empty(M, N, device="cuda")
+    ops.gemm(x, w, out, M, N, K, lda=K, ldb=K, ldc=N, b_nk=True, epilogue=ops.EPI_MUL_DGELU, R=v, ldr=N)
+    vd = v.double().requires_grad_()
+    F.gelu(vd).sum().backward()
+    assert rel_l2(out, (x.double() @ w.double().t()) * vd.grad) < TOL_TF32
+
+
+# ------------------------------------------------------------------------------------- LayerNorm
+@pytest.mark.parametrize("rows,C", [(4096, 32), (1000, 64), (777, 128), (512, 256), (256, 512), (64, 48)])
+def test_layernorm(ops, rows, C):
+    x = _r(rows, C, seed=1) * 2 + 0.3
+    g, b = _r(C, seed=2) * 0.1 + 1, _r(C, seed=3) * 0.1
+    y, mean, rstd = ops.layernorm_fwd(x, g, b)
+    xd, gd, bd = (t.double().requires_grad_() for t in (x, g, b))
+    ref = F.layer_norm(xd, (C,), gd, bd, 1e-5)
+    assert rel_l2(y, ref) < TOL_FP32
+    dy, dres = _r(rows, C, seed=4), _r(rows, C, seed=5)
+    ref.backward(dy.double())
+    dx, dg, db = ops.layernorm_bwd(dy, x, g, mean, rstd, dres=dres)
+    assert rel_l2(dx, xd.grad + dres.double()) < TOL_FP32
+    assert rel_l2(dg, gd.grad) < TOL_FP32 * 5
+    assert rel_l2(db, bd.grad) < TOL_FP32 * 5
+
+
+# ------------------------------------------------------------------------------ window attention
+def _attn_ref(qkv, table, w, B, H, W, heads, shift, sparse=True):
+    """fp64 reference from the oracle's window_attention with identity projections."""
+    from oracle import ast_oracle as ao
+    C = qkv.shape[1] // 3
+    hd = C // heads
+    q, k, v = (qkv[:, i * C:(i + 1) * C].double().view(B, H, W, C) for i in range(3))
+
+    def win(t):
+        if shift:
+            t = torch.roll(t, (-shift, -shift), (1, 2))
+        return ao.to_windows(t, B, H, W, C)
+    qw, kw, vw = win(q), win(k), win(v)
+    N = 64
+    qh = qw.view(-1, N, heads, hd).transpose(1, 2) * hd ** -0.5
+    kh = kw.view(-1, N, heads, hd).transpose(1, 2)
+    vh = vw.view(-1, N, heads, hd).transpose(1, 2)
+    s = qh @ kh.transpose(-2, -1)
+    from uwr.ast import _relative_position_index
+    idx = _relative_position_index(8).view(-1).cuda()
+    s = s + table.double()[idx].view(N, N, heads).permute(2, 0, 1).unsqueeze(0)
+    if shift:
+        m = ao.shift_mask(H, W, shift, torch.float64).cuda()
+        nW = m.shape[0]
+        s = (s.view(B, nW, heads, N, N) + m[None, :, None]).view(-1, heads, N, N)
+    p = torch.softmax(s, -1)
+    if sparse:
+        e = torch.exp(w.double())
+        p = p * (e[0] / e.sum()) + torch.relu(s) ** 2 * (e[1] / e.sum())
+    o = (p @ vh).transpose(1, 2).reshape(-1, N, C)
+    o = ao.from_windows(o, B, H, W, C)
+    if shift:
+        o = torch.roll(o, (shift, shift), (1, 2))
+    return o.reshape(B * H * W, C)
+
+
+@pytest.mark.parametrize("B,H,heads,hd,shift", [(2, 16, 2, 32, 0), (2, 16, 2, 32, 4), (1, 32, 4, 32, 4),
+                                                 (1, 16, 4, 8, 4), (1, 16, 2, 16, 0), (1, 16, 2, 64, 4),
+                                                 (1, 16, 1, 128, 4), (3, 8, 1, 32, 4)])
+@pytest.mark.parametrize("sparse", [True, False])
+def test_window_attention_fwd_bwd(ops, B, H, heads, hd, shift, sparse):
+    W = H
+    C = heads * hd
+    qkv = _r(B * H * W, 3 * C, seed=1)
+    table = _r(225, heads, seed=2, scale=0.5)
+    w = torch.tensor([0.3, -0.2]).cuda()
+    scale = hd ** -0.5
+    o = ops.window_attn_fwd(qkv, 0, qkv, C, 2 * C, table, w if sparse else None, B, H, W, heads, hd, shift, scale)
+    qd, td, wd = qkv.double().requires_grad_(), table.double().requires_grad_(), w.double().requires_grad_()
+    ref = _attn_ref(qd, td, wd, B, H, W, heads, shift, sparse)
+    assert rel_l2(o, ref) < TOL_TF32
+    do = _r(B * H * W, C, seed=3)
+    ref.backward(do.double())
+    dqkv, _, dtable, dw = ops.window_attn_bwd(do, qkv, 0, qkv, C, 2 * C, table, w if sparse else None, B, H, W,
+                                              heads, hd, shift, scale)
+    assert rel_l2(dqkv, qd.grad) < 2 * TOL_TF32
+    assert rel_l2(dtable, td.grad) < 2 * TOL_TF32
+    if sparse:
+        assert rel_l2(dw, wd.grad) < 5 * TOL_TF32
+
+
+# ------------------------------------------------------------------------------------ dwconv+GELU
+@pytest.mark.parametrize("B,H,Ch,mode", [(2, 16, 64, 0), (1, 32, 128, 0), (2, 24, 48, 0), (1, 16, 64, 1),
+                                         (1, 40, 32, 1)])
+def test_dwconv_gelu(ops, B, H, Ch, mode):
+    W = H
+    width = Ch * (2 if mode else 1)
+    u = _r(B * H * W, width, seed=1)
+    wt, bs = _r(Ch, 1, 3, 3, seed=2, scale=0.3), _r(Ch, seed=3, scale=0.1)
+    v, h2 = ops.dwconv_gelu_fwd(u, wt, bs, B, H, W, Ch, mode=mode)
+    ud, wd, bd = u.double().requires_grad_(), wt.double().requires_grad_(), bs.double().requires_grad_()
+    h1 = F.gelu(ud[:, :Ch]).view(B, H, W, Ch).permute(0, 3, 1, 2)
+    vr = F.conv2d(h1, wd, bd, padding=1, groups=Ch).permute(0, 2, 3, 1).reshape(-1, Ch)
+    ref = F.gelu(vr)
+    if mode:
+        ref = ref * F.gelu(ud[:, Ch:])
+    assert rel_l2(v, vr) < TOL_FP32
+    assert rel_l2(h2, ref) < TOL_FP32
+    dh2 = _r(B * H * W, Ch, seed=4)
+    ref.backward(dh2.double())
+    du, dwt, dbs = ops.dwconv_gelu_bwd(dh2, u, v, wt, B, H, W, Ch, mode=mode)
+    assert rel_l2(du, ud.grad) < TOL_FP32 * 5
+    assert rel_l2(dwt, wd.grad) < TOL_FP32 * 10
+    assert rel_l2(dbs, bd.grad) < TOL_FP32 * 10
+
+
+# ------------------------------------------------------------------------------- boundary convs
+def test_input_proj():
+    from uwr.blocks import InputProjFn
+    B, H = 2, 48
+    img = _r(B, 3, H, H, seed=1)
+    w, b = _r(32, 3, 3, 3, seed=2, scale=0.2).requires_grad_(), _r(32, seed=3, scale=0.1).requires_grad_()
+    tok = InputProjFn.apply(img, w, b, 0.01)
+    wd, bd = w.detach().double().requires_grad_(), b.detach().double().requires_grad_()
+    ref = F.leaky_relu(F.conv2d(img.double(), wd, bd, padding=1), 0.01).flatten(2).transpose(1, 2)
+    assert rel_l2(tok, ref) < TOL_FP32
+    g = _r(B, H * H, 32, seed=4)
+    tok.backward(g)
+    ref.backward(g.double())
+    assert rel_l2(w.grad, wd.grad) < TOL_FP32 * 10
+    assert rel_l2(b.grad, bd.grad) < TOL_FP32 * 10
+
+
+@pytest.mark.parametrize("Cin", [64, 32])
+def test_output_proj(Cin):
+    from uwr.blocks import OutputProjFn
+    B, H = 2, 40
+    tok = _r(B, H * H, Cin, seed=1).requires_grad_()
+    img = _r(B, 3, H, H, seed=5)
+    w, b = _r(3, Cin, 3, 3, seed=2, scale=0.1).requires_grad_(), _r(3, seed=3, scale=0.1).requires_grad_()
+    out = OutputProjFn.apply(tok, w, b, img, H, H)
+    td, wd, bd = (t.detach().double().requires_grad_() for t in (tok, w, b))
+    ref = img.double() + F.conv2d(td.transpose(1, 2).reshape(B, Cin, H, H), wd, bd, padding=1)
+    assert rel_l2(out, ref) < TOL_FP32
+    g = _r(B, 3, H, H, seed=4)
+    out.backward(g)
+    ref.backward(g.double())
+    assert rel_l2(tok.grad, td.grad) < TOL_FP32 * 5
+    assert rel_l2(w.grad, wd.grad) < TOL_FP32 * 10
+    assert rel_l2(b.grad, bd.grad) < TOL_FP32 * 10
+
+
+def test_downsample():
+    from uwr.blocks import DownsampleFn
+    B, H, C = 2, 16, 32
+    x = _r(B, H * H, C, seed=1).requires_grad_()
+    w, b = _r(2 * C, C, 4, 4, seed=2, scale=0.1).requires_grad_(), _r(2 * C, seed=3, scale=0.1).requires_grad_()
+    y = DownsampleFn.apply(x, w, b, H, H)
+    xd, wd, bd = (t.detach().double().requires_grad_() for t in (x, w, b))
+    ref = F.conv2d(xd.transpose(1, 2).reshape(B, C, H, H), wd, bd, stride=2, padding=1).flatten(2).transpose(1, 2)
+    assert rel_l2(y, ref) < TOL_TF32
+    g = _r(B, H * H // 4, 2 * C, seed=4)
+    y.backward(g)
+    ref.backward(g.double())
+    assert rel_l2(x.grad, xd.grad) < TOL_TF32
+    assert rel_l2(w.grad, wd.grad) < TOL_TF32
+    assert rel_l2(b.grad, bd.grad) < TOL_FP32 * 10
+
+
+def test_upsample_cat():
+    from uwr.blocks import UpsampleCatFn
+    B, H, Cin, Cout = 2, 8, 64, 32
+    x = _r(B, H * H, Cin, seed=1).requires_grad_()
+    skip = _r(B, 4 * H * H, Cout, seed=5).requires_grad_()
+    w, b = _r(Cin, Cout, 2, 2, seed=2, scale=0.1).requires_grad_(), _r(Cout, seed=3, scale=0.1).requires_grad_()
+    y = UpsampleCatFn.apply(x, w, b, skip, H, H)
+    xd, sd_, wd, bd = (t.detach().double().requires_grad_() for t in (x, skip, w, b))
+    up = F.conv_transpose2d(xd.transpose(1, 2).reshape(B, Cin, H, H), wd, bd, stride=2).flatten(2).transpose(1, 2)
+    ref = torch.cat([up, sd_], -1)
+    assert rel_l2(y, ref) < TOL_TF32
+    g = _r(B, 4 * H * H, 2 * Cout, seed=4)
+    y.backward(g)
+    ref.backward(g.double())
+    assert rel_l2(x.grad, xd.grad) < TOL_TF32
+    assert rel_l2(skip.grad, sd_.grad) < 1e-7
+    assert rel_l2(w.grad, wd.grad) < TOL_TF32
+    assert rel_l2(b.grad, bd.grad) < TOL_FP32 * 10
+
+
+# ------------------------------------------------------------------------------------- losses
+@pytest.mark.parametrize("kind", ["L1", "L2", "L1withColor", "charbonnier"])
+def test_pixel_losses(kind):
+    from oracle import losses_oracle as lo
+    from uwr.losses import LossFunction
+    torch.manual_seed(0)
+    p = torch.rand(2, 3, 256, 256).cuda().requires_grad_()
+    t = torch.rand(2, 3, 256, 256).cuda()
+    loss = LossFunction(kind, "cuda").getloss(p, t)
+    loss.backward()
+    pd = p.detach().double().cpu().requires_grad_()
+    fn = {"L1": lo.l1, "L2": lo.l2, "L1withColor": lo.l1_with_color, "charbonnier": lo.charbonnier}[kind]
+    ref = fn(pd, t.double().cpu())
+    ref.backward()
+    assert abs(loss.item() - ref.item()) <= 1e-6 * abs(ref.item()) + 1e-9
+    assert rel_l2(p.grad, pd.grad) < 1e-5
+
+
+def test_loss_known_answers():
+    """src/Loss.ipynb:45 known answer: Charbonnier(x, x) = eps = 0.0010; L1(x,x) = 0."""
+    from uwr.losses import LossFunction
+    x = torch.rand(1, 3, 256, 256).cuda()
+    assert abs(LossFunction("charbonnier", "cuda").getloss(x, x).item() - 1e-3) < 1e-7
+    assert LossFunction("L1", "cuda").getloss(x, x).item() == 0.0
+    with pytest.raises(ValueError):
+        LossFunction("nope", "cuda").getloss(x, x)
+
+
+# ----------------------------------------------------------------------------------- optimizer
+@pytest.mark.parametrize("decoupled,wd", [(False, 0.0), (True, 0.01)])
+def test_fused_clip_adam(decoupled, wd):
+    from uwr.optim import FusedClipAdam
+    torch.manual_seed(0)
+    shapes = [(64, 32), (7,), (3, 5, 3, 3), (2048, 512), (1,)]
+    ps = [torch.nn.Parameter(torch.randn(s).cuda()) for s in shapes]
+    qs = [torch.nn.Parameter(p.detach().clone()) for p in ps]
+    opt = FusedClipAdam(ps, lr=1e-3, weight_decay=wd, decoupled=decoupled, max_norm=1.0)
+    ref = (torch.optim.AdamW if decoupled else torch.optim.Adam)(qs, lr=1e-3, weight_decay=wd)
+    for it in range(3):
+        for p, q in zip(ps, qs):
+            g = torch.randn_like(p) * (0.001 if it == 1 else 1.0)
+            p.grad = g.clone()
+            q.grad = g.clone()
+        norm = opt.step()
+        rn = torch.nn.utils.clip_grad_norm_(qs, 1.0)
+        ref.step()
+        assert abs(norm[0].item() - rn.item()) < 1e-4 * rn.item()
+        for p, q in zip(ps, qs):
+            assert rel_l2(p, q) < 1e-6

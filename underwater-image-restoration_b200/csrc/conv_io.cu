@@ -1,0 +1,665 @@
+// Convolutions at the model boundary and between scales, all on token (NHWC) tensors:
+//   InputProj  Conv3x3(3->C)+LeakyReLU   (AST.py:447-466)      direct, lane <-> output channel
+//   OutputProj Conv3x3(C->3) + residual  (AST.py:470-493,921)  direct, lanes split input channels
+//   Downsample Conv4x4 s2 p1             (AST.py:408-424)      im2col (ky,kx,ci) + uwr_gemm_tf32
+//   Upsample   ConvTranspose2x2 s2       (AST.py:428-443)      uwr_gemm_tf32 + 2x2 pixel scatter
+// plus the strided copy used for the skip concatenation (AST.py:904-916) and a deterministic
+// column sum (bias gradients).  All of these are HBM-bound data movement around the GEMMs.
+#include "uwr_common.cuh"
+#include "../../include/uwr_b200.h"
+
+namespace {
+
+// ------------------------------------------------------------------------------------------
+// InputProj
+constexpr int IP_TS = 16;
+constexpr int IP_HS = IP_TS + 2;
+constexpr int IP_MAXCIN = 4;
+
+template <int NCO>  // output channels per lane (Cout = 32*NCO)
+__global__ void __launch_bounds__(256) input_proj_fwd_kernel(const float* __restrict__ img,
+                                                             const float* __restrict__ weight,
+                                                             const float* __restrict__ bias,
+                                                             float* __restrict__ tokens, int H, int W, int Cin,
+                                                             int Cout, float slope, int tiles_x) {
+    __shared__ float in_s[IP_MAXCIN][IP_HS][IP_HS];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int b = blockIdx.z;
+    const int ty0 = (blockIdx.x / tiles_x) * IP_TS, tx0 = (blockIdx.x % tiles_x) * IP_TS;
+    for (int idx = threadIdx.x; idx < Cin * IP_HS * IP_HS; idx += 256) {
+        const int ci = idx / (IP_HS * IP_HS), rem = idx % (IP_HS * IP_HS);
+        const int y = ty0 + rem / IP_HS - 1, x = tx0 + rem % IP_HS - 1;
+        float v = 0.f;
+        if (y >= 0 && y < H && x >= 0 && x < W) v = img[(((long long)b * Cin + ci) * H + y) * W + x];
+        in_s[ci][rem / IP_HS][rem % IP_HS] = v;
+    }
+    float w[NCO][IP_MAXCIN * 9], bv[NCO];
+#pragma unroll
+    for (int n = 0; n < NCO; ++n) {
+        const int co = lane + 32 * n;
+        bv[n] = bias[co];
+#pragma unroll
+        for (int k = 0; k < IP_MAXCIN * 9; ++k) w[n][k] = k < Cin * 9 ? weight[co * Cin * 9 + k] : 0.f;
+    }
+    __syncthreads();
+    for (int pp = 0; pp < 32; ++pp) {
+        const int pix = warp * 32 + pp;
+        const int ly = pix / IP_TS, lx = pix % IP_TS;
+        const int y = ty0 + ly, x = tx0 + lx;
+        if (y >= H || x >= W) continue;
+        float acc[NCO];
+#pragma unroll
+        for (int n = 0; n < NCO; ++n) acc[n] = bv[n];
+#pragma unroll
+        for (int ci = 0; ci < IP_MAXCIN; ++ci) {
+            if (ci >= Cin) break;
+#pragma unroll
+            for (int ky = 0; ky < 3; ++ky)
+#pragma unroll
+                for (int kx = 0; kx < 3; ++kx) {
+                    const float iv = in_s[ci][ly + ky][lx + kx];
+#pragma unroll
+                    for (int n = 0; n < NCO; ++n) acc[n] = fmaf(iv, w[n][ci * 9 + ky * 3 + kx], acc[n]);
+                }
+        }
+        const long long tok = ((long long)b * H + y) * W + x;
+#pragma unroll
+        for (int n = 0; n < NCO; ++n) {
+            const float a = acc[n];
+            tokens[tok * Cout + lane + 32 * n] = a > 0.f ? a : a * slope;
+        }
+    }
+}
+
+template <int NCO>
+__global__ void __launch_bounds__(256) input_proj_bwd_kernel(const float* __restrict__ dtokens,
+                                                             const float* __restrict__ tokens,
+                                                             const float* __restrict__ img,
+                                                             float* __restrict__ partials, int B, int H, int W,
+                                                             int Cin, int Cout, float slope, int tiles_x,
+                                                             int tiles_per_img) {
+    __shared__ float in_s[IP_MAXCIN][IP_HS][IP_HS];
+    __shared__ float red[8][32];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    float dw[NCO][IP_MAXCIN * 9 + 1];
+#pragma unroll
+    for (int n = 0; n < NCO; ++n)
+#pragma unroll
+        for (int k = 0; k < IP_MAXCIN * 9 + 1; ++k) dw[n][k] = 0.f;
+
+    const int total = B * tiles_per_img;
+    for (int tile = blockIdx.x; tile < total; tile += gridDim.x) {
+        const int b = tile / tiles_per_img, tl = tile % tiles_per_img;
+        const int ty0 = (tl / tiles_x) * IP_TS, tx0 = (tl % tiles_x) * IP_TS;
+        __syncthreads();
+        for (int idx = threadIdx.x; idx < Cin * IP_HS * IP_HS; idx += 256) {
+            const int ci = idx / (IP_HS * IP_HS), rem = idx % (IP_HS * IP_HS);
+            const int y = ty0 + rem / IP_HS - 1, x = tx0 + rem % IP_HS - 1;
+            float v = 0.f;
+            if (y >= 0 && y < H && x >= 0 && x < W) v = img[(((long long)b * Cin + ci) * H + y) * W + x];
+            in_s[ci][rem / IP_HS][rem % IP_HS] = v;
+        }
+        __syncthreads();
+        for (int pp = 0; pp < 32; ++pp) {
+            const int pix = warp * 32 + pp;
+            const int ly = pix / IP_TS, lx = pix % IP_TS;
+            const int y = ty0 + ly, x = tx0 + lx;
+            if (y >= H || x >= W) continue;
+            const long long tok = ((long long)b * H + y) * W + x;
+            float d[NCO];
+#pragma unroll
+            for (int n = 0; n < NCO; ++n) {
+                const float o = tokens[tok * Cout + lane + 32 * n];
+                d[n] = dtokens[tok * Cout + lane + 32 * n] * (o > 0.f ? 1.f : slope);
+                dw[n][IP_MAXCIN * 9] += d[n];
+            }
+#pragma unroll
+            for (int ci = 0; ci < IP_MAXCIN; ++ci) {
+                if (ci >= Cin) break;
+#pragma unroll
+                for (int ky = 0; ky < 3; ++ky)
+#pragma unroll
+                    for (int kx = 0; kx < 3; ++kx) {
+                        const float iv = in_s[ci][ly + ky][lx + kx];
+#pragma unroll
+                        for (int n = 0; n < NCO; ++n) dw[n][ci * 9 + ky * 3 + kx] = fmaf(iv, d[n], dw[n][ci * 9 + ky * 3 + kx]);
+                    }
+            }
+        }
+    }
+    // cross-warp reduction, one k at a time; partial layout [cta][k][Cout], k = Cin*9 -> bias
+    const int nk = Cin * 9 + 1;
+#pragma unroll
+    for (int n = 0; n < NCO; ++n)
+#pragma unroll
+        for (int k = 0; k < IP_MAXCIN * 9 + 1; ++k) {
+            const int kk = (k == IP_MAXCIN * 9) ? Cin * 9 : k;
+            if (k != IP_MAXCIN * 9 && k >= Cin * 9) continue;
+            __syncthreads();
+            red[warp][lane] = dw[n][k];
+            __syncthreads();
+            if (warp == 0) {
+                float s = 0.f;
+#pragma unroll
+                for (int ww = 0; ww < 8; ++ww) s += red[ww][lane];
+                partials[((long long)blockIdx.x * nk + kk) * Cout + lane + 32 * n] = s;
+            }
+        }
+}
+
+__global__ void input_proj_reduce_kernel(const float* __restrict__ partials, float* __restrict__ dweight,
+                                         float* __restrict__ dbias, int P, int Cin, int Cout) {
+    const int nk = Cin * 9 + 1;
+    const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= nk * Cout) return;
+    const int k = idx / Cout, co = idx % Cout;
+    float s = 0.f;
+    for (int p = 0; p < P; ++p) s += partials[((long long)p * nk + k) * Cout + co];
+    if (k < Cin * 9) dweight[co * Cin * 9 + k] = s;
+    else dbias[co] = s;
+}
+
+// ------------------------------------------------------------------------------------------
+// OutputProj
+constexpr int OP_TY = 8, OP_TX = 16;
+constexpr int OP_HY = OP_TY + 2, OP_HX = OP_TX + 2;
+
+template <int CPL>  // input channels per lane (Cin = 32*CPL)
+__global__ void __launch_bounds__(256) output_proj_fwd_kernel(const float* __restrict__ tokens, long long ld,
+                                                              const float* __restrict__ weight,
+                                                              const float* __restrict__ bias,
+                                                              const float* __restrict__ residual,
+                                                              float* __restrict__ out, int H, int W, int tiles_x) {
+    constexpr int Cin = 32 * CPL;
+    extern __shared__ __align__(16) float smem[];  // [OP_HY*OP_HX][Cin]
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int b = blockIdx.z;
+    const int ty0 = (blockIdx.x / tiles_x) * OP_TY, tx0 = (blockIdx.x % tiles_x) * OP_TX;
+    for (int idx = threadIdx.x; idx < OP_HY * OP_HX * (Cin / 4); idx += 256) {
+        const int pix = idx / (Cin / 4), c4 = (idx % (Cin / 4)) * 4;
+        const int y = ty0 + pix / OP_HX - 1, x = tx0 + pix % OP_HX - 1;
+        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (y >= 0 && y < H && x >= 0 && x < W)
+            v = *reinterpret_cast<const float4*>(tokens + (((long long)b * H + y) * W + x) * ld + c4);
+        *reinterpret_cast<float4*>(smem + pix * Cin + c4) = v;
+    }
+    float w[3][CPL][9];
+#pragma unroll
+    for (int co = 0; co < 3; ++co)
+#pragma unroll
+        for (int e = 0; e < CPL; ++e)
+#pragma unroll
+            for (int k = 0; k < 9; ++k) w[co][e][k] = weight[(co * Cin + lane * CPL + e) * 9 + k];
+    __syncthreads();
+    const int ly = warp;  // one tile row per warp
+    const int y = ty0 + ly;
+    float keep[3] = {0.f, 0.f, 0.f};
+    for (int lx = 0; lx < OP_TX; ++lx) {
+        float acc[3] = {0.f, 0.f, 0.f};
+#pragma unroll
+        for (int ky = 0; ky < 3; ++ky)
+#pragma unroll
+            for (int kx = 0; kx < 3; ++kx) {
+                const float* sp = smem + ((ly + ky) * OP_HX + lx + kx) * Cin + lane * CPL;
+#pragma unroll
+                for (int e = 0; e < CPL; ++e) {
+                    const float xv = sp[e];
+#pragma unroll
+                    for (int co = 0; co < 3; ++co) acc[co] = fmaf(xv, w[co][e][ky * 3 + kx], acc[co]);
+                }
+            }
+#pragma unroll
+        for (int co = 0; co < 3; ++co) {
+            const float s = warp_sum(acc[co]);
+            if (lane == lx) keep[co] = s;
+        }
+    }
+    const int x = tx0 + lane;
+    if (lane < OP_TX && y < H && x < W) {
+#pragma unroll
+        for (int co = 0; co < 3; ++co) {
+            const long long o = (((long long)b * 3 + co) * H + y) * W + x;
+            float v = keep[co] + bias[co];
+            if (residual) v += residual[o];
+            out[o] = v;
+        }
+    }
+}
+
+template <int CPL>
+__global__ void __launch_bounds__(256) output_proj_bwd_kernel(const float* __restrict__ dout,
+                                                              const float* __restrict__ tokens, long long ld,
+                                                              const float* __restrict__ weight,
+                                                              float* __restrict__ dtokens,
+                                                              float* __restrict__ partials, int B, int H, int W,
+                                                              int tiles_x, int tiles_per_img) {
+    constexpr int Cin = 32 * CPL;
+    extern __shared__ __align__(16) float smem[];
+    float* xs = smem;                           // [OP_HY*OP_HX][Cin]
+    float* dys = smem + OP_HY * OP_HX * Cin;    // [3][OP_HY][OP_HX]
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    float w[3][CPL][9], dw[3][CPL][9], db[3] = {0.f, 0.f, 0.f};
+#pragma unroll
+    for (int co = 0; co < 3; ++co)
+#pragma unroll
+        for (int e = 0; e < CPL; ++e)
+#pragma unroll
+            for (int k = 0; k < 9; ++k) {
+                w[co][e][k] = weight[(co * Cin + lane * CPL + e) * 9 + k];
+                dw[co][e][k] = 0.f;
+            }
+    const int total = B * tiles_per_img;
+    for (int tile = blockIdx.x; tile < total; tile += gridDim.x) {
+        const int b = tile / tiles_per_img, tl = tile % tiles_per_img;
+        const int ty0 = (tl / tiles_x) * OP_TY, tx0 = (tl % tiles_x) * OP_TX;
+        __syncthreads();
+        for (int idx = threadIdx.x; idx < OP_HY * OP_HX * (Cin / 4); idx += 256) {
+            const int pix = idx / (Cin / 4), c4 = (idx % (Cin / 4)) * 4;
+            const int y = ty0 + pix / OP_HX - 1, x = tx0 + pix % OP_HX - 1;
+            float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (y >= 0 && y < H && x >= 0 && x < W)
+                v = *reinterpret_cast<const float4*>(tokens + (((long long)b * H + y) * W + x) * ld + c4);
+            *reinterpret_cast<float4*>(xs + pix * Cin + c4) = v;
+        }
+        for (int idx = threadIdx.x; idx < 3 * OP_HY * OP_HX; idx += 256) {
+            const int co = idx / (OP_HY * OP_HX), rem = idx % (OP_HY * OP_HX);
+            const int y = ty0 + rem / OP_HX - 1, x = tx0 + rem % OP_HX - 1;
+            float v = 0.f;
+            if (y >= 0 && y < H && x >= 0 && x < W) v = dout[(((long long)b * 3 + co) * H + y) * W + x];
+            dys[idx] = v;
+        }
+        __syncthreads();
+        const int ly = warp;
+        const int y = ty0 + ly;
+        if (y < H) {
+            for (int lx = 0; lx < OP_TX; ++lx) {
+                const int x = tx0 + lx;
+                if (x >= W) break;
+                float dx[CPL];
+#pragma unroll
+                for (int e = 0; e < CPL; ++e) dx[e] = 0.f;
+                float dyc[3];
+#pragma unroll
+                for (int co = 0; co < 3; ++co) {
+                    dyc[co] = dys[(co * OP_HY + ly + 1) * OP_HX + lx + 1];
+                    db[co] += dyc[co];
+                }
+#pragma unroll
+                for (int ky = 0; ky < 3; ++ky)
+#pragma unroll
+                    for (int kx = 0; kx < 3; ++kx) {
+                        const float* sp = xs + ((ly + ky) * OP_HX + lx + kx) * Cin + lane * CPL;
+#pragma unroll
+                        for (int co = 0; co < 3; ++co) {
+                            // dX[y,x] += dY[co][y+1-ky][x+1-kx] * W[co][ci][ky][kx]
+                            const float dyv = dys[(co * OP_HY + ly + 2 - ky) * OP_HX + lx + 2 - kx];
+#pragma unroll
+                            for (int e = 0; e < CPL; ++e) {
+                                dx[e] = fmaf(dyv, w[co][e][ky * 3 + kx], dx[e]);
+                                dw[co][e][ky * 3 + kx] = fmaf(dyc[co], sp[e], dw[co][e][ky * 3 + kx]);
+                            }
+                        }
+                    }
+                float* dp = dtokens + (((long long)b * H + y) * W + x) * Cin + lane * CPL;
+#pragma unroll
+                for (int e = 0; e < CPL; ++e) dp[e] = dx[e];
+            }
+        }
+    }
+    // cross-warp reduction through shared memory: partial layout [cta][27*Cin + 3]
+    __syncthreads();
+    float* red = smem;  // [8][27*Cin]  (27*64*8*4 = 55 KB <= tile bytes? no -> reduce per co)
+    for (int co = 0; co < 3; ++co) {
+        __syncthreads();
+#pragma unroll
+        for (int e = 0; e < CPL; ++e)
+#pragma unroll
+            for (int k = 0; k < 9; ++k) red[(warp * Cin + lane * CPL + e) * 9 + k] = dw[co][e][k];
+        __syncthreads();
+        for (int idx = threadIdx.x; idx < Cin * 9; idx += 256) {
+            float s = 0.f;
+#pragma unroll
+            for (int ww = 0; ww < 8; ++ww) s += red[ww * Cin * 9 + idx];
+            partials[(long long)blockIdx.x * (27 * Cin + 3) + co * Cin * 9 + idx] = s;
+        }
+    }
+    __syncthreads();
+    if (lane == 0) red[warp * 3 + 0] = db[0], red[warp * 3 + 1] = db[1], red[warp * 3 + 2] = db[2];
+    __syncthreads();
+    if (threadIdx.x < 3) {
+        float s = 0.f;
+        for (int ww = 0; ww < 8; ++ww) s += red[ww * 3 + threadIdx.x];
+        partials[(long long)blockIdx.x * (27 * Cin + 3) + 27 * Cin + threadIdx.x] = s;
+    }
+}
+
+__global__ void output_proj_reduce_kernel(const float* __restrict__ partials, float* __restrict__ dweight,
+                                          float* __restrict__ dbias, int P, int Cin) {
+    const int n = 27 * Cin + 3;
+    const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= n) return;
+    float s = 0.f;
+    for (int p = 0; p < P; ++p) s += partials[(long long)p * n + idx];
+    if (idx < 27 * Cin) dweight[idx] = s;
+    else dbias[idx - 27 * Cin] = s;
+}
+
+// ------------------------------------------------------------------------------------------
+__global__ void im2col_4x4s2_kernel(const float* __restrict__ x, long long ld, float* __restrict__ col, int B, int H,
+                                    int W, int C) {
+    const int Ho = H / 2, Wo = W / 2, C4 = C / 4;
+    const long long total = (long long)B * Ho * Wo * 16 * C4;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total;
+         i += (long long)gridDim.x * blockDim.x) {
+        const int c4 = (int)(i % C4);
+        long long r = i / C4;
+        const int tap = (int)(r % 16);
+        r /= 16;
+        const int ox = (int)(r % Wo);
+        r /= Wo;
+        const int oy = (int)(r % Ho);
+        const int b = (int)(r / Ho);
+        const int y = 2 * oy - 1 + (tap >> 2), xx = 2 * ox - 1 + (tap & 3);
+        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (y >= 0 && y < H && xx >= 0 && xx < W)
+            v = *reinterpret_cast<const float4*>(x + (((long long)b * H + y) * W + xx) * ld + c4 * 4);
+        reinterpret_cast<float4*>(col)[i] = v;
+    }
+}
+
+__global__ void col2im_4x4s2_kernel(const float* __restrict__ dcol, float* __restrict__ dx, int B, int H, int W,
+                                    int C) {
+    const int Ho = H / 2, Wo = W / 2, C4 = C / 4;
+    const long long total = (long long)B * H * W * C4;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total;
+         i += (long long)gridDim.x * blockDim.x) {
+        const int c4 = (int)(i % C4);
+        long long r = i / C4;
+        const int xx = (int)(r % W);
+        r /= W;
+        const int y = (int)(r % H);
+        const int b = (int)(r / H);
+        float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+        for (int a = 0; a < 2; ++a) {
+            const int ky = ((y + 1) & 1) + 2 * a;
+            const int oy = (y + 1 - ky) / 2;
+            if (y + 1 - ky < 0 || oy >= Ho) continue;
+#pragma unroll
+            for (int bb = 0; bb < 2; ++bb) {
+                const int kx = ((xx + 1) & 1) + 2 * bb;
+                const int ox = (xx + 1 - kx) / 2;
+                if (xx + 1 - kx < 0 || ox >= Wo) continue;
+                const float4 v = *reinterpret_cast<const float4*>(
+                    dcol + ((((long long)b * Ho + oy) * Wo + ox) * 16 + ky * 4 + kx) * C + c4 * 4);
+                acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
+            }
+        }
+        reinterpret_cast<float4*>(dx)[i] = acc;
+    }
+}
+
+__global__ void pixel_scatter_2x2_kernel(const float* __restrict__ g, const float* __restrict__ bias,
+                                         float* __restrict__ out, long long ld_out, int B, int H, int W, int Cout) {
+    const long long total = (long long)B * H * W * Cout;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total;
+         i += (long long)gridDim.x * blockDim.x) {
+        const int co = (int)(i % Cout);
+        long long r = i / Cout;
+        const int x = (int)(r % W);
+        r /= W;
+        const int y = (int)(r % H);
+        const int b = (int)(r / H);
+        const float4 v = reinterpret_cast<const float4*>(g)[i];
+        const float bv = bias ? bias[co] : 0.f;
+        const long long o00 = (((long long)b * 2 * H + 2 * y) * 2 * W + 2 * x) * ld_out + co;
+        out[o00] = v.x + bv;
+        out[o00 + ld_out] = v.y + bv;
+        out[o00 + 2 * W * ld_out] = v.z + bv;
+        out[o00 + 2 * W * ld_out + ld_out] = v.w + bv;
+    }
+}
+
+__global__ void pixel_gather_2x2_kernel(const float* __restrict__ dout, long long ld_dout, float* __restrict__ dg,
+                                        int B, int H, int W, int Cout) {
+    const long long total = (long long)B * H * W * Cout;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total;
+         i += (long long)gridDim.x * blockDim.x) {
+        const int co = (int)(i % Cout);
+        long long r = i / Cout;
+        const int x = (int)(r % W);
+        r /= W;
+        const int y = (int)(r % H);
+        const int b = (int)(r / H);
+        const long long o00 = (((long long)b * 2 * H + 2 * y) * 2 * W + 2 * x) * ld_dout + co;
+        float4 v;
+        v.x = dout[o00];
+        v.y = dout[o00 + ld_dout];
+        v.z = dout[o00 + 2 * W * ld_dout];
+        v.w = dout[o00 + 2 * W * ld_dout + ld_dout];
+        reinterpret_cast<float4*>(dg)[i] = v;
+    }
+}
+
+__global__ void copy2d_kernel(const float* __restrict__ src, long long ld_src, float* __restrict__ dst,
+                              long long ld_dst, long long rows, int cols4, int accumulate) {
+    const long long total = rows * cols4;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total;
+         i += (long long)gridDim.x * blockDim.x) {
+        const long long r = i / cols4;
+        const int c = (int)(i % cols4) * 4;
+        float4 v = *reinterpret_cast<const float4*>(src + r * ld_src + c);
+        float4* d = reinterpret_cast<float4*>(dst + r * ld_dst + c);
+        if (accumulate) {
+            const float4 o = *d;
+            v.x += o.x; v.y += o.y; v.z += o.z; v.w += o.w;
+        }
+        *d = v;
+    }
+}
+
+// column sums: grid (P, ceil(cols/32)), block (32, 8)
+__global__ void colsum_partial_kernel(const float* __restrict__ x, long long ld, float* __restrict__ partials,
+                                      long long rows, int cols) {
+    __shared__ float sh[8][33];
+    const int c = blockIdx.y * 32 + threadIdx.x;
+    float s = 0.f;
+    if (c < cols)
+        for (long long r = (long long)blockIdx.x * 8 + threadIdx.y; r < rows; r += (long long)gridDim.x * 8)
+            s += x[r * ld + c];
+    sh[threadIdx.y][threadIdx.x] = s;
+    __syncthreads();
+    if (threadIdx.y == 0 && c < cols) {
+        float t = 0.f;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) t += sh[i][threadIdx.x];
+        partials[(long long)blockIdx.x * cols + c] = t;
+    }
+}
+__global__ void colsum_final_kernel(const float* __restrict__ partials, float* __restrict__ out, int P, int cols) {
+    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= cols) return;
+    float s = 0.f;
+    for (int p = 0; p < P; ++p) s += partials[(long long)p * cols + c];
+    out[c] = s;
+}
+
+int ew_blocks(long long n, int threads) {
+    long long b = (n + threads - 1) / threads;
+    const long long cap = (long long)uwr_sm_count() * 16;
+    if (b > cap) b = cap;
+    return (int)(b < 1 ? 1 : b);
+}
+
+int persistent_ctas(int tiles) {
+    int p = 2 * uwr_sm_count();
+    if (p > tiles) p = tiles;
+    return p < 1 ? 1 : p;
+}
+
+}  // namespace
+
+extern "C" int uwr_input_proj_fwd(const float* img, const float* weight, const float* bias, float* tokens, int B,
+                                  int H, int W, int Cin, int Cout, float slope, uwr_stream_t stream_) {
+    cudaStream_t stream = (cudaStream_t)stream_;
+    UWR_REQUIRE(img && weight && bias && tokens, "uwr_input_proj_fwd: null pointer");
+    UWR_REQUIRE(Cin >= 1 && Cin <= IP_MAXCIN && (Cout == 32 || Cout == 64), "uwr_input_proj_fwd: Cin<=4, Cout in {32,64}");
+    UWR_REQUIRE(B > 0 && B <= 65535, "uwr_input_proj_fwd: bad batch");
+    const int tx = uwr_cdiv(W, IP_TS), ty = uwr_cdiv(H, IP_TS);
+    dim3 grid(tx * ty, 1, B);
+    if (Cout == 32) input_proj_fwd_kernel<1><<<grid, 256, 0, stream>>>(img, weight, bias, tokens, H, W, Cin, Cout, slope, tx);
+    else input_proj_fwd_kernel<2><<<grid, 256, 0, stream>>>(img, weight, bias, tokens, H, W, Cin, Cout, slope, tx);
+    UWR_CHECK_LAUNCH("input_proj_fwd_kernel");
+    return 0;
+}
+
+extern "C" size_t uwr_input_proj_bwd_workspace_bytes(int B, int H, int W, int Cin, int Cout) {
+    const int tiles = B * uwr_cdiv(W, IP_TS) * uwr_cdiv(H, IP_TS);
+    return (size_t)persistent_ctas(tiles) * (Cin * 9 + 1) * Cout * sizeof(float);
+}
+
+extern "C" int uwr_input_proj_bwd(const float* dtokens, const float* tokens, const float* img, float* dweight,
+                                  float* dbias, float* workspace, int B, int H, int W, int Cin, int Cout, float slope,
+                                  uwr_stream_t stream_) {
+    cudaStream_t stream = (cudaStream_t)stream_;
+    UWR_REQUIRE(dtokens && tokens && img && dweight && dbias && workspace, "uwr_input_proj_bwd: null pointer");
+    UWR_REQUIRE(Cin >= 1 && Cin <= IP_MAXCIN && (Cout == 32 || Cout == 64), "uwr_input_proj_bwd: Cin<=4, Cout in {32,64}");
+    const int tx = uwr_cdiv(W, IP_TS), ty = uwr_cdiv(H, IP_TS);
+    const int P = persistent_ctas(B * tx * ty);
+    if (Cout == 32)
+        input_proj_bwd_kernel<1><<<P, 256, 0, stream>>>(dtokens, tokens, img, workspace, B, H, W, Cin, Cout, slope, tx, tx * ty);
+    else
+        input_proj_bwd_kernel<2><<<P, 256, 0, stream>>>(dtokens, tokens, img, workspace, B, H, W, Cin, Cout, slope, tx, tx * ty);
+    UWR_CHECK_LAUNCH("input_proj_bwd_kernel");
+    input_proj_reduce_kernel<<<uwr_cdiv((Cin * 9 + 1) * Cout, 128), 128, 0, stream>>>(workspace, dweight, dbias, P, Cin, Cout);
+    UWR_CHECK_LAUNCH("input_proj_reduce_kernel");
+    return 0;
+}
+
+extern "C" int uwr_output_proj_fwd(const float* tokens, long long ld, const float* weight, const float* bias,
+                                   const float* residual_img, float* out_img, int B, int H, int W, int Cin,
+                                   uwr_stream_t stream_) {
+    cudaStream_t stream = (cudaStream_t)stream_;
+    UWR_REQUIRE(tokens && weight && bias && out_img, "uwr_output_proj_fwd: null pointer");
+    UWR_REQUIRE((Cin == 32 || Cin == 64) && ld % 4 == 0, "uwr_output_proj_fwd: Cin in {32,64}, ld %% 4 == 0");
+    UWR_REQUIRE(B > 0 && B <= 65535, "uwr_output_proj_fwd: bad batch");
+    const int tx = uwr_cdiv(W, OP_TX), ty = uwr_cdiv(H, OP_TY);
+    dim3 grid(tx * ty, 1, B);
+    const int smem = OP_HY * OP_HX * Cin * (int)sizeof(float);
+    if (Cin == 32) {
+        output_proj_fwd_kernel<1><<<grid, 256, smem, stream>>>(tokens, ld, weight, bias, residual_img, out_img, H, W, tx);
+    } else {
+        static bool configured = false;
+        if (!configured) {
+            UWR_CUDA(cudaFuncSetAttribute(output_proj_fwd_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+            configured = true;
+        }
+        output_proj_fwd_kernel<2><<<grid, 256, smem, stream>>>(tokens, ld, weight, bias, residual_img, out_img, H, W, tx);
+    }
+    UWR_CHECK_LAUNCH("output_proj_fwd_kernel");
+    return 0;
+}
+
+extern "C" size_t uwr_output_proj_bwd_workspace_bytes(int B, int H, int W, int Cin) {
+    const int tiles = B * uwr_cdiv(W, OP_TX) * uwr_cdiv(H, OP_TY);
+    return (size_t)persistent_ctas(tiles) * (27 * Cin + 3) * sizeof(float);
+}
+
+extern "C" int uwr_output_proj_bwd(const float* dout_img, const float* tokens, long long ld, const float* weight,
+                                   float* dtokens, float* dweight, float* dbias, float* workspace, int B, int H, int W,
+                                   int Cin, uwr_stream_t stream_) {
+    cudaStream_t stream = (cudaStream_t)stream_;
+    UWR_REQUIRE(dout_img && tokens && weight && dtokens && dweight && dbias && workspace, "uwr_output_proj_bwd: null pointer");
+    UWR_REQUIRE((Cin == 32 || Cin == 64) && ld % 4 == 0, "uwr_output_proj_bwd: Cin in {32,64}, ld %% 4 == 0");
+    const int tx = uwr_cdiv(W, OP_TX), ty = uwr_cdiv(H, OP_TY);
+    const int P = persistent_ctas(B * tx * ty);
+    // tile + dY halo; the cross-warp reduction reuses the same buffer (8 * 9 * Cin floats)
+    int smem = (OP_HY * OP_HX * Cin + 3 * OP_HY * OP_HX) * (int)sizeof(float);
+    const int red = 8 * 9 * Cin * (int)sizeof(float);
+    if (red > smem) smem = red;
+    if (Cin == 32) {
+        static bool configured = false;
+        if (!configured) {
+            UWR_CUDA(cudaFuncSetAttribute(output_proj_bwd_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+            configured = true;
+        }
+        output_proj_bwd_kernel<1><<<P, 256, smem, stream>>>(dout_img, tokens, ld, weight, dtokens, workspace, B, H, W, tx, tx * ty);
+    } else {
+        static bool configured = false;
+        if (!configured) {
+            UWR_CUDA(cudaFuncSetAttribute(output_proj_bwd_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+            configured = true;
+        }
+        output_proj_bwd_kernel<2><<<P, 256, smem, stream>>>(dout_img, tokens, ld, weight, dtokens, workspace, B, H, W, tx, tx * ty);
+    }
+    UWR_CHECK_LAUNCH("output_proj_bwd_kernel");
+    output_proj_reduce_kernel<<<uwr_cdiv(27 * Cin + 3, 128), 128, 0, stream>>>(workspace, dweight, dbias, P, Cin);
+    UWR_CHECK_LAUNCH("output_proj_reduce_kernel");
+    return 0;
+}
+
+extern "C" int uwr_im2col_4x4s2(const float* tokens, long long ld, float* col, int B, int H, int W, int C,
+                                uwr_stream_t stream_) {
+    cudaStream_t stream = (cudaStream_t)stream_;
+    UWR_REQUIRE(tokens && col && C % 4 == 0 && ld % 4 == 0 && H % 2 == 0 && W % 2 == 0, "uwr_im2col_4x4s2: bad args");
+    const long long total = (long long)B * (H / 2) * (W / 2) * 16 * (C / 4);
+    im2col_4x4s2_kernel<<<ew_blocks(total, 256), 256, 0, stream>>>(tokens, ld, col, B, H, W, C);
+    UWR_CHECK_LAUNCH("im2col_4x4s2_kernel");
+    return 0;
+}
+
+extern "C" int uwr_col2im_4x4s2(const float* dcol, float* dtokens, int B, int H, int W, int C, uwr_stream_t stream_) {
+    cudaStream_t stream = (cudaStream_t)stream_;
+    UWR_REQUIRE(dcol && dtokens && C % 4 == 0 && H % 2 == 0 && W % 2 == 0, "uwr_col2im_4x4s2: bad args");
+    const long long total = (long long)B * H * W * (C / 4);
+    col2im_4x4s2_kernel<<<ew_blocks(total, 256), 256, 0, stream>>>(dcol, dtokens, B, H, W, C);
+    UWR_CHECK_LAUNCH("col2im_4x4s2_kernel");
+    return 0;
+}
+
+extern "C" int uwr_pixel_scatter_2x2(const float* g, const float* bias, float* out, long long ld_out, int B, int H,
+                                     int W, int Cout, uwr_stream_t stream_) {
+    cudaStream_t stream = (cudaStream_t)stream_;
+    UWR_REQUIRE(g && out, "uwr_pixel_scatter_2x2: null pointer");
+    const long long total = (long long)B * H * W * Cout;
+    pixel_scatter_2x2_kernel<<<ew_blocks(total, 256), 256, 0, stream>>>(g, bias, out, ld_out, B, H, W, Cout);
+    UWR_CHECK_LAUNCH("pixel_scatter_2x2_kernel");
+    return 0;
+}
+
+extern "C" int uwr_pixel_gather_2x2(const float* dout, long long ld_dout, float* dg, int B, int H, int W, int Cout,
+                                    uwr_stream_t stream_) {
+    cudaStream_t stream = (cudaStream_t)stream_;
+    UWR_REQUIRE(dout && dg, "uwr_pixel_gather_2x2: null pointer");
+    const long long total = (long long)B * H * W * Cout;
+    pixel_gather_2x2_kernel<<<ew_blocks(total, 256), 256, 0, stream>>>(dout, ld_dout, dg, B, H, W, Cout);
+    UWR_CHECK_LAUNCH("pixel_gather_2x2_kernel");
+    return 0;
+}
+
+extern "C" int uwr_copy2d(const float* src, long long ld_src, float* dst, long long ld_dst, long long rows, int cols,
+                          int accumulate, uwr_stream_t stream_) {
+    cudaStream_t stream = (cudaStream_t)stream_;
+    UWR_REQUIRE(src && dst && cols % 4 == 0 && ld_src % 4 == 0 && ld_dst % 4 == 0, "uwr_copy2d: cols/ld must be multiples of 4");
+    if (rows == 0 || cols == 0) return 0;
+    copy2d_kernel<<<ew_blocks(rows * (cols / 4), 256), 256, 0, stream>>>(src, ld_src, dst, ld_dst, rows, cols / 4, accumulate);
+    UWR_CHECK_LAUNCH("copy2d_kernel");
+    return 0;
+}
+
+extern "C" int uwr_colsum(const float* x, long long ld, float* out, float* workspace, long long rows, int cols,
+                          uwr_stream_t stream_) {
+    cudaStream_t stream = (cudaStream_t)stream_;
+    UWR_REQUIRE(x && out && workspace && cols > 0 && rows > 0, "uwr_colsum: bad args");
+    long long P = (rows + 63) / 64;
+    const int cgroups = uwr_cdiv(cols, 32);
+    long long cap = (4LL * uwr_sm_count() + cgroups - 1) / cgroups;
+    if (cap > 1024) cap = 1024;
+    if (P > cap) P = cap;
+    if (P < 1) P = 1;
+    colsum_partial_kernel<<<dim3((unsigned)P, cgroups), dim3(32, 8), 0, stream>>>(x, ld, workspace, rows, cols);
+    UWR_CHECK_LAUNCH("colsum_partial_kernel");
+    colsum_final_kernel<<<uwr_cdiv(cols, 128), 128, 0, stream>>>(workspace, out, (int)P, cols);
+    UWR_CHECK_LAUNCH("colsum_final_kernel");
+    return 0;
+}

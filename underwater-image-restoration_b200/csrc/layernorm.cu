@@ -1,0 +1,196 @@
+// LayerNorm over the channel axis of token tensors (nn.LayerNorm, eps 1e-5, biased variance:
+// AST.py:521,534,593,622).  One warp per row, rows kept in registers; HBM-bound:
+// fwd 2*rows*C*4 B, bwd 3*rows*C*4 B (+ pass-through residual gradient).
+#include "uwr_common.cuh"
+#include "../../include/uwr_b200.h"
+
+namespace {
+
+constexpr int LN_WARPS = 8;
+constexpr int LN_MAX_PARTIAL_BLOCKS = 1024;
+
+// VPL = values per lane (C = 32 * VPL when exact; general C handled by the bounds check)
+template <int VPL>
+__global__ void __launch_bounds__(LN_WARPS * 32) ln_fwd_kernel(const float* __restrict__ x,
+                                                               const float* __restrict__ gamma,
+                                                               const float* __restrict__ beta,
+                                                               float* __restrict__ y, float* __restrict__ mean,
+                                                               float* __restrict__ rstd, long long rows, int C,
+                                                               float eps) {
+    const int lane = threadIdx.x & 31;
+    const int warp = threadIdx.x >> 5;
+    float gm[VPL], bt[VPL];
+#pragma unroll
+    for (int i = 0; i < VPL; ++i) {
+        const int c = lane + 32 * i;
+        gm[i] = c < C ? gamma[c] : 0.f;
+        bt[i] = c < C ? beta[c] : 0.f;
+    }
+    const float invC = 1.0f / (float)C;
+    for (long long r = (long long)blockIdx.x * LN_WARPS + warp; r < rows; r += (long long)gridDim.x * LN_WARPS) {
+        const float* xr = x + r * C;
+        float v[VPL];
+        float s = 0.f;
+#pragma unroll
+        for (int i = 0; i < VPL; ++i) {
+            const int c = lane + 32 * i;
+            v[i] = c < C ? xr[c] : 0.f;
+            s += v[i];
+        }
+        const float mu = warp_sum(s) * invC;
+        float q = 0.f;
+#pragma unroll
+        for (int i = 0; i < VPL; ++i) {
+            const int c = lane + 32 * i;
+            const float d = c < C ? v[i] - mu : 0.f;
+            q += d * d;
+        }
+        const float rs = rsqrtf(warp_sum(q) * invC + eps);
+        float* yr = y + r * C;
+#pragma unroll
+        for (int i = 0; i < VPL; ++i) {
+            const int c = lane + 32 * i;
+            if (c < C) yr[c] = (v[i] - mu) * rs * gm[i] + bt[i];
+        }
+        if (lane == 0) {
+            if (mean) mean[r] = mu;
+            if (rstd) rstd[r] = rs;
+        }
+    }
+}
+
+template <int VPL>
+__global__ void __launch_bounds__(LN_WARPS * 32) ln_bwd_kernel(const float* __restrict__ dy,
+                                                               const float* __restrict__ x,
+                                                               const float* __restrict__ gamma,
+                                                               const float* __restrict__ mean,
+                                                               const float* __restrict__ rstd,
+                                                               const float* __restrict__ dres,
+                                                               float* __restrict__ dx, float* __restrict__ partials,
+                                                               long long rows, int C) {
+    __shared__ float sh[LN_WARPS][32 * VPL];
+    const int lane = threadIdx.x & 31;
+    const int warp = threadIdx.x >> 5;
+    float gm[VPL], dg[VPL], db[VPL];
+#pragma unroll
+    for (int i = 0; i < VPL; ++i) {
+        const int c = lane + 32 * i;
+        gm[i] = c < C ? gamma[c] : 0.f;
+        dg[i] = 0.f;
+        db[i] = 0.f;
+    }
+    const float invC = 1.0f / (float)C;
+    for (long long r = (long long)blockIdx.x * LN_WARPS + warp; r < rows; r += (long long)gridDim.x * LN_WARPS) {
+        const float mu = mean[r], rs = rstd[r];
+        float xh[VPL], g[VPL];
+        float s1 = 0.f, s2 = 0.f;
+#pragma unroll
+        for (int i = 0; i < VPL; ++i) {
+            const int c = lane + 32 * i;
+            const float xv = c < C ? x[r * C + c] : 0.f;
+            const float d = c < C ? dy[r * C + c] : 0.f;
+            xh[i] = c < C ? (xv - mu) * rs : 0.f;
+            g[i] = d * gm[i];
+            s1 += g[i];
+            s2 += g[i] * xh[i];
+            dg[i] += d * xh[i];
+            db[i] += d;
+        }
+        s1 = warp_sum(s1) * invC;
+        s2 = warp_sum(s2) * invC;
+#pragma unroll
+        for (int i = 0; i < VPL; ++i) {
+            const int c = lane + 32 * i;
+            if (c < C) {
+                float o = rs * (g[i] - s1 - xh[i] * s2);
+                if (dres) o += dres[r * C + c];
+                dx[r * C + c] = o;
+            }
+        }
+    }
+    // block-level reduction of dgamma/dbeta, then one partial row per block
+#pragma unroll
+    for (int pass = 0; pass < 2; ++pass) {
+#pragma unroll
+        for (int i = 0; i < VPL; ++i) sh[warp][lane + 32 * i] = pass == 0 ? dg[i] : db[i];
+        __syncthreads();
+        for (int c = threadIdx.x; c < C; c += blockDim.x) {
+            float s = 0.f;
+#pragma unroll
+            for (int w = 0; w < LN_WARPS; ++w) s += sh[w][c];
+            partials[((long long)blockIdx.x * 2 + pass) * C + c] = s;
+        }
+        __syncthreads();
+    }
+}
+
+__global__ void ln_param_reduce_kernel(const float* __restrict__ partials, float* __restrict__ dgamma,
+                                       float* __restrict__ dbeta, int nblocks, int C) {
+    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= C) return;
+    float a = 0.f, b = 0.f;
+    for (int i = 0; i < nblocks; ++i) {
+        a += partials[((long long)i * 2 + 0) * C + c];
+        b += partials[((long long)i * 2 + 1) * C + c];
+    }
+    dgamma[c] = a;
+    dbeta[c] = b;
+}
+
+int ln_blocks(long long rows) {
+    long long b = (rows + LN_WARPS - 1) / LN_WARPS;
+    const long long cap = (long long)uwr_sm_count() * 6;
+    if (b > cap) b = cap;
+    if (b > LN_MAX_PARTIAL_BLOCKS) b = LN_MAX_PARTIAL_BLOCKS;
+    return (int)(b < 1 ? 1 : b);
+}
+
+}  // namespace
+
+extern "C" int uwr_layernorm_fwd(const float* x, const float* gamma, const float* beta, float* y, float* mean,
+                                 float* rstd, long long rows, int C, float eps, uwr_stream_t stream_) {
+    cudaStream_t stream = (cudaStream_t)stream_;
+    UWR_REQUIRE(x && gamma && beta && y, "uwr_layernorm_fwd: null pointer");
+    UWR_REQUIRE(C > 0 && C <= 1024, "uwr_layernorm_fwd: C=%d unsupported (1..1024)", C);
+    if (rows == 0) return 0;
+    const int blocks = ln_blocks(rows);
+    const int vpl = (C + 31) / 32;
+#define LN_FWD(V) ln_fwd_kernel<V><<<blocks, LN_WARPS * 32, 0, stream>>>(x, gamma, beta, y, mean, rstd, rows, C, eps)
+    if (vpl <= 1) LN_FWD(1);
+    else if (vpl <= 2) LN_FWD(2);
+    else if (vpl <= 4) LN_FWD(4);
+    else if (vpl <= 8) LN_FWD(8);
+    else if (vpl <= 16) LN_FWD(16);
+    else LN_FWD(32);
+#undef LN_FWD
+    UWR_CHECK_LAUNCH("ln_fwd_kernel");
+    return 0;
+}
+
+extern "C" size_t uwr_layernorm_bwd_workspace_bytes(long long rows, int C) {
+    return (size_t)ln_blocks(rows) * 2 * (size_t)C * sizeof(float);
+}
+
+extern "C" int uwr_layernorm_bwd(const float* dy, const float* x, const float* gamma, const float* mean,
+                                 const float* rstd, const float* dres, float* dx, float* dgamma, float* dbeta,
+                                 float* partials, long long rows, int C, uwr_stream_t stream_) {
+    cudaStream_t stream = (cudaStream_t)stream_;
+    UWR_REQUIRE(dy && x && gamma && mean && rstd && dx && dgamma && dbeta && partials, "uwr_layernorm_bwd: null pointer");
+    UWR_REQUIRE(C > 0 && C <= 1024, "uwr_layernorm_bwd: C=%d unsupported (1..1024)", C);
+    UWR_REQUIRE(rows > 0, "uwr_layernorm_bwd: rows must be positive");
+    const int blocks = ln_blocks(rows);
+    const int vpl = (C + 31) / 32;
+#define LN_BWD(V) \
+    ln_bwd_kernel<V><<<blocks, LN_WARPS * 32, 0, stream>>>(dy, x, gamma, mean, rstd, dres, dx, partials, rows, C)
+    if (vpl <= 1) LN_BWD(1);
+    else if (vpl <= 2) LN_BWD(2);
+    else if (vpl <= 4) LN_BWD(4);
+    else if (vpl <= 8) LN_BWD(8);
+    else if (vpl <= 16) LN_BWD(16);
+    else LN_BWD(32);
+#undef LN_BWD
+    UWR_CHECK_LAUNCH("ln_bwd_kernel");
+    ln_param_reduce_kernel<<<uwr_cdiv(C, 128), 128, 0, stream>>>(partials, dgamma, dbeta, blocks, C);
+    UWR_CHECK_LAUNCH("ln_param_reduce_kernel");
+    return 0;
+}

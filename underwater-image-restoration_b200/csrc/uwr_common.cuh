@@ -1,0 +1,92 @@
+// Shared device helpers for the uwr_b200 kernels (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <math.h>
+
+// Error plumbing (uwr_abi.cu): every C-ABI entry returns 0 or a negative code and leaves a
+// message retrievable through uwr_last_error().
+extern "C" const char* uwr_last_error(void);
+void uwr_set_error(const char* fmt, ...);
+
+#define UWR_REQUIRE(cond, ...)                 \
+    do {                                       \
+        if (!(cond)) {                         \
+            uwr_set_error(__VA_ARGS__);        \
+            return -1;                         \
+        }                                      \
+    } while (0)
+
+#define UWR_CHECK_LAUNCH(name)                                               \
+    do {                                                                     \
+        cudaError_t e__ = cudaGetLastError();                                \
+        if (e__ != cudaSuccess) {                                            \
+            uwr_set_error("%s: %s", name, cudaGetErrorString(e__));          \
+            return -2;                                                       \
+        }                                                                    \
+    } while (0)
+
+#define UWR_CUDA(call)                                                        \
+    do {                                                                      \
+        cudaError_t e__ = (call);                                             \
+        if (e__ != cudaSuccess) {                                             \
+            uwr_set_error("%s: %s", #call, cudaGetErrorString(e__));          \
+            return -2;                                                        \
+        }                                                                     \
+    } while (0)
+
+static inline int uwr_cdiv(long long a, long long b) { return (int)((a + b - 1) / b); }
+int uwr_sm_count();
+
+// ---- numerics ---------------------------------------------------------------------------
+// fp32 -> tf32 with round-to-nearest (ties away); the tensor core would otherwise truncate,
+// which biases every product by ~-1e-3 relative.
+__device__ __forceinline__ uint32_t f2tf32(float x) {
+    uint32_t r;
+    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
+    return r;
+}
+__device__ __forceinline__ float tf32_round(float x) { return __uint_as_float(f2tf32(x)); }
+
+// exact (erf) GELU, as nn.GELU() in the reference (AST.py:295-301)
+__device__ __forceinline__ float gelu_f(float x) {
+    return 0.5f * x * (1.0f + erff(x * 0.70710678118654752440f));
+}
+__device__ __forceinline__ float gelu_grad_f(float x) {
+    const float cdf = 0.5f * (1.0f + erff(x * 0.70710678118654752440f));
+    const float pdf = 0.39894228040143267794f * __expf(-0.5f * x * x);
+    return cdf + x * pdf;
+}
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+__device__ __forceinline__ float warp_max(float v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
+    return v;
+}
+
+// m16n8k8 TF32 tensor-core MMA, fp32 accumulate (legacy warp-level path; used where the tile
+// shape is far below a tcgen05 atom, e.g. 64x64x32 attention windows).
+__device__ __forceinline__ void mma_tf32_16x8x8(float (&d)[4], const uint32_t (&a)[4],
+                                                const uint32_t (&b)[2]) {
+    asm volatile(
+        "mma.sync.aligned.m16n8k8.row.col.f32.tf32.tf32.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, "
+        "{%8,%9}, {%0,%1,%2,%3};"
+        : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
+        : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b[0]), "r"(b[1]));
+}
+
+__device__ __forceinline__ void cp_async16(void* smem, const void* gmem, bool pred) {
+    const uint32_t s = (uint32_t)__cvta_generic_to_shared(smem);
+    const int bytes = pred ? 16 : 0;  // src-size 0 => zero fill
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(s), "l"(gmem), "r"(bytes));
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() {
+    asm volatile("cp.async.wait_group %0;" ::"n"(N));
+}

@@ -1,0 +1,545 @@
+// Adaptive sparse 8x8 window attention (WindowAttention_sparse.forward, AST.py:187-219) with the
+// cyclic shift, window partition/reverse (AST.py:377-402,596-618) and the shift mask
+// (AST.py:568-588) folded into address arithmetic.
+//
+//   S = scale*q k^T + table[idx(i,j),h] + mask ;  P = w0*softmax(S) + w1*relu(S)^2 ;  O = P v
+//
+// One (batch, window, head) tile = 64 tokens x HD.  QK^T / PV / the five backward products run
+// on TF32 tensor cores (m16n8k8, fp32 accumulate); S, P, dS never leave registers / shared
+// memory.  Algorithmic HBM bytes per tile: fwd 4*64*HD*4 (q,k,v in, o out),
+// bwd 7*64*HD*4 (q,k,v,do in; dq,dk,dv out).
+#include "uwr_common.cuh"
+#include "../../include/uwr_b200.h"
+
+namespace {
+
+constexpr int WIN = 8;
+constexpr int NTOK = 64;
+constexpr int ATT_THREADS = 128;  // 4 warps x 16 query rows
+constexpr int PS_STRIDE = 72;     // P / dS staging, conflict-free for transposed A fragments
+constexpr int NBINS = 225;
+
+struct AttnParams {
+    const float* q;
+    long long ld_q;
+    int q_off;
+    const float* kv;
+    long long ld_kv;
+    int k_off, v_off;
+    const float* table;
+    const float* w_param;
+    int B, H, W, heads, shift;
+    float scale;
+    int nWx, nW;  // windows per row / per image
+};
+
+__device__ __forceinline__ long long token_row(const AttnParams& p, int b, int wy, int wx, int n) {
+    const int i = n >> 3, j = n & 7;
+    int y = wy * WIN + i + p.shift;
+    int x = wx * WIN + j + p.shift;
+    if (y >= p.H) y -= p.H;
+    if (x >= p.W) x -= p.W;
+    return ((long long)b * p.H + y) * p.W + x;
+}
+
+__device__ __forceinline__ int region_code(const AttnParams& p, int wy, int wx, int n) {
+    // region id of the token on the SHIFTED grid (AST.py:570-581)
+    const int sy = wy * WIN + (n >> 3), sx = wx * WIN + (n & 7);
+    const int ry = (sy >= p.H - WIN) + (sy >= p.H - p.shift);
+    const int rx = (sx >= p.W - WIN) + (sx >= p.W - p.shift);
+    return ry * 3 + rx;
+}
+
+__device__ __forceinline__ int bias_index(int i, int j) {
+    return ((i >> 3) - (j >> 3) + WIN - 1) * (2 * WIN - 1) + ((i & 7) - (j & 7) + WIN - 1);
+}
+
+// stage a 64 x HD tile (tf32-rounded) into shared memory [64][HD+4]
+template <int HD>
+__device__ __forceinline__ void stage_tile(float* dst, const float* src, long long ld, int col_off,
+                                           const long long* rows, float mul) {
+    constexpr int ST = HD + 4;
+    constexpr int V4 = HD / 4;
+    for (int idx = threadIdx.x; idx < NTOK * V4; idx += ATT_THREADS) {
+        const int r = idx / V4, c4 = (idx % V4) * 4;
+        const float4 v = *reinterpret_cast<const float4*>(src + rows[r] * ld + col_off + c4);
+        float4 o;
+        o.x = tf32_round(v.x * mul);
+        o.y = tf32_round(v.y * mul);
+        o.z = tf32_round(v.z * mul);
+        o.w = tf32_round(v.w * mul);
+        *reinterpret_cast<float4*>(dst + r * ST + c4) = o;
+    }
+}
+
+// acc[nt][4] (16 rows x 64 cols) = A[r0.., :HD] * Bm[:, :HD]^T   (both row-major [64][HD+4])
+template <int HD>
+__device__ __forceinline__ void mma_rows_x_rowsT(float (&acc)[8][4], const float* A, const float* Bm, int r0,
+                                                 int g, int t) {
+    constexpr int ST = HD + 4;
+#pragma unroll
+    for (int nt = 0; nt < 8; ++nt)
+#pragma unroll
+        for (int c = 0; c < 4; ++c) acc[nt][c] = 0.f;
+#pragma unroll
+    for (int ks = 0; ks < HD / 8; ++ks) {
+        uint32_t a[4];
+        a[0] = __float_as_uint(A[(r0 + g) * ST + ks * 8 + t]);
+        a[1] = __float_as_uint(A[(r0 + g + 8) * ST + ks * 8 + t]);
+        a[2] = __float_as_uint(A[(r0 + g) * ST + ks * 8 + t + 4]);
+        a[3] = __float_as_uint(A[(r0 + g + 8) * ST + ks * 8 + t + 4]);
+#pragma unroll
+        for (int nt = 0; nt < 8; ++nt) {
+            uint32_t b[2];
+            b[0] = __float_as_uint(Bm[(nt * 8 + g) * ST + ks * 8 + t]);
+            b[1] = __float_as_uint(Bm[(nt * 8 + g) * ST + ks * 8 + t + 4]);
+            mma_tf32_16x8x8(acc[nt], a, b);
+        }
+    }
+}
+
+// out[nt2][4] (16 rows x HD) = P(regs, 16 x 64 in C-fragment layout) * Bm[64][HD+4]
+// key permutation inside each k8 block: slot t <-> key 2t, slot t+4 <-> key 2t+1.
+template <int HD>
+__device__ __forceinline__ void mma_regs_x_rows(float (&out)[HD / 8][4], const float (&P)[8][4], const float* Bm,
+                                                int g, int t) {
+    constexpr int ST = HD + 4;
+#pragma unroll
+    for (int n = 0; n < HD / 8; ++n)
+#pragma unroll
+        for (int c = 0; c < 4; ++c) out[n][c] = 0.f;
+#pragma unroll
+    for (int kb = 0; kb < 8; ++kb) {
+        uint32_t a[4];
+        a[0] = f2tf32(P[kb][0]);
+        a[1] = f2tf32(P[kb][2]);
+        a[2] = f2tf32(P[kb][1]);
+        a[3] = f2tf32(P[kb][3]);
+#pragma unroll
+        for (int n = 0; n < HD / 8; ++n) {
+            uint32_t b[2];
+            b[0] = __float_as_uint(Bm[(kb * 8 + 2 * t) * ST + n * 8 + g]);
+            b[1] = __float_as_uint(Bm[(kb * 8 + 2 * t + 1) * ST + n * 8 + g]);
+            mma_tf32_16x8x8(out[n], a, b);
+        }
+    }
+}
+
+// S -> S*1 + bias + mask (q pre-scaled at staging), then row softmax statistics
+__device__ __forceinline__ void add_bias_mask(float (&s)[8][4], const float* tab, const int* reg, int r0, int g,
+                                              int t, bool masked) {
+#pragma unroll
+    for (int nt = 0; nt < 8; ++nt)
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+            const int i = r0 + g + (c >> 1) * 8;
+            const int j = nt * 8 + 2 * t + (c & 1);
+            float v = s[nt][c] + tab[bias_index(i, j)];
+            if (masked && reg[i] != reg[j]) v += -100.0f;
+            s[nt][c] = v;
+        }
+}
+
+__device__ __forceinline__ void row_softmax(const float (&s)[8][4], float (&p0)[8][4]) {
+#pragma unroll
+    for (int half = 0; half < 2; ++half) {
+        float m = -INFINITY;
+#pragma unroll
+        for (int nt = 0; nt < 8; ++nt) m = fmaxf(m, fmaxf(s[nt][half * 2], s[nt][half * 2 + 1]));
+        m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, 1));
+        m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, 2));
+        float sum = 0.f;
+#pragma unroll
+        for (int nt = 0; nt < 8; ++nt) {
+            const float e0 = __expf(s[nt][half * 2] - m), e1 = __expf(s[nt][half * 2 + 1] - m);
+            p0[nt][half * 2] = e0;
+            p0[nt][half * 2 + 1] = e1;
+            sum += e0 + e1;
+        }
+        sum += __shfl_xor_sync(0xffffffffu, sum, 1);
+        sum += __shfl_xor_sync(0xffffffffu, sum, 2);
+        const float inv = 1.0f / sum;
+#pragma unroll
+        for (int nt = 0; nt < 8; ++nt) {
+            p0[nt][half * 2] *= inv;
+            p0[nt][half * 2 + 1] *= inv;
+        }
+    }
+}
+
+__device__ __forceinline__ void fusion_weights(const float* w_param, float& w0, float& w1) {
+    if (w_param == nullptr) {
+        w0 = 1.f;
+        w1 = 0.f;
+        return;
+    }
+    const float e0 = expf(w_param[0]), e1 = expf(w_param[1]);
+    w0 = e0 / (e0 + e1);
+    w1 = e1 / (e0 + e1);
+}
+
+// ------------------------------------------------------------------------------------------
+template <int HD>
+__global__ void __launch_bounds__(ATT_THREADS) attn_fwd_kernel(const AttnParams p, float* __restrict__ out,
+                                                               long long ld_out) {
+    constexpr int ST = HD + 4;
+    extern __shared__ __align__(16) float smem[];
+    float* Qs = smem;
+    float* Ks = Qs + NTOK * ST;
+    float* Vs = Ks + NTOK * ST;
+    float* tab = Vs + NTOK * ST;                             // 225 (+pad to 228)
+    int* reg = reinterpret_cast<int*>(tab + 228);            // 64
+    long long* rows = reinterpret_cast<long long*>(reg + NTOK);  // 64
+
+    const int tile = blockIdx.x;
+    const int h = tile % p.heads;
+    const int wlin = (tile / p.heads) % p.nW;
+    const int b = tile / (p.heads * p.nW);
+    const int wy = wlin / p.nWx, wx = wlin % p.nWx;
+
+    for (int i = threadIdx.x; i < NBINS; i += ATT_THREADS) tab[i] = p.table[i * p.heads + h];
+    if (threadIdx.x < NTOK) {
+        rows[threadIdx.x] = token_row(p, b, wy, wx, threadIdx.x);
+        reg[threadIdx.x] = p.shift > 0 ? region_code(p, wy, wx, threadIdx.x) : 0;
+    }
+    __syncthreads();
+    stage_tile<HD>(Qs, p.q, p.ld_q, p.q_off + h * HD, rows, p.scale);
+    stage_tile<HD>(Ks, p.kv, p.ld_kv, p.k_off + h * HD, rows, 1.0f);
+    stage_tile<HD>(Vs, p.kv, p.ld_kv, p.v_off + h * HD, rows, 1.0f);
+    __syncthreads();
+
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int g = lane >> 2, t = lane & 3;
+    const int r0 = warp * 16;
+
+    float s[8][4], p0[8][4];
+    mma_rows_x_rowsT<HD>(s, Qs, Ks, r0, g, t);
+    add_bias_mask(s, tab, reg, r0, g, t, p.shift > 0);
+    row_softmax(s, p0);
+    float w0, w1;
+    fusion_weights(p.w_param, w0, w1);
+#pragma unroll
+    for (int nt = 0; nt < 8; ++nt)
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+            const float r = fmaxf(s[nt][c], 0.f);
+            p0[nt][c] = w0 * p0[nt][c] + w1 * r * r;
+        }
+    float o[HD / 8][4];
+    mma_regs_x_rows<HD>(o, p0, Vs, g, t);
+#pragma unroll
+    for (int half = 0; half < 2; ++half) {
+        float* orow = out + rows[r0 + g + half * 8] * ld_out + h * HD;
+#pragma unroll
+        for (int n = 0; n < HD / 8; ++n)
+            *reinterpret_cast<float2*>(orow + n * 8 + 2 * t) = make_float2(o[n][half * 2], o[n][half * 2 + 1]);
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// Backward.  grid = (ctas_per_head, heads); each CTA walks the (batch, window) tiles of one head
+// so that the relative-position-bias gradient accumulates in registers and is binned once.
+template <int HD>
+__global__ void __launch_bounds__(ATT_THREADS) attn_bwd_kernel(const AttnParams p, const float* __restrict__ dout,
+                                                               long long ld_dout, float* __restrict__ dq_buf,
+                                                               float* __restrict__ dkv_buf,
+                                                               float* __restrict__ partials) {
+    constexpr int ST = HD + 4;
+    extern __shared__ __align__(16) float smem[];
+    float* Qs = smem;
+    float* Ks = Qs + NTOK * ST;
+    float* Vs = Ks + NTOK * ST;
+    float* dOs = Vs + NTOK * ST;
+    float* Ps = dOs + NTOK * ST;
+    float* dSs = Ps + NTOK * PS_STRIDE;
+    float* tab = dSs + NTOK * PS_STRIDE;
+    int* reg = reinterpret_cast<int*>(tab + 228);
+    long long* rows = reinterpret_cast<long long*>(reg + NTOK);
+    __shared__ float red[2][ATT_THREADS / 32];
+
+    const int h = blockIdx.y;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int g = lane >> 2, t = lane & 3;
+    const int r0 = warp * 16;
+
+    for (int i = threadIdx.x; i < NBINS; i += ATT_THREADS) tab[i] = p.table[i * p.heads + h];
+    float w0, w1;
+    fusion_weights(p.w_param, w0, w1);
+
+    float dsacc[8][4];
+#pragma unroll
+    for (int nt = 0; nt < 8; ++nt)
+#pragma unroll
+        for (int c = 0; c < 4; ++c) dsacc[nt][c] = 0.f;
+    float g1 = 0.f, g2 = 0.f;
+
+    const int ntiles = p.B * p.nW;
+    for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+        const int b = tile / p.nW, wlin = tile % p.nW;
+        const int wy = wlin / p.nWx, wx = wlin % p.nWx;
+        __syncthreads();  // previous iteration's consumers are done with smem
+        if (threadIdx.x < NTOK) {
+            rows[threadIdx.x] = token_row(p, b, wy, wx, threadIdx.x);
+            reg[threadIdx.x] = p.shift > 0 ? region_code(p, wy, wx, threadIdx.x) : 0;
+        }
+        __syncthreads();
+        stage_tile<HD>(Qs, p.q, p.ld_q, p.q_off + h * HD, rows, p.scale);
+        stage_tile<HD>(Ks, p.kv, p.ld_kv, p.k_off + h * HD, rows, 1.0f);
+        stage_tile<HD>(Vs, p.kv, p.ld_kv, p.v_off + h * HD, rows, 1.0f);
+        stage_tile<HD>(dOs, dout, ld_dout, h * HD, rows, 1.0f);
+        __syncthreads();
+
+        float s[8][4], p0[8][4], dp[8][4];
+        mma_rows_x_rowsT<HD>(s, Qs, Ks, r0, g, t);
+        add_bias_mask(s, tab, reg, r0, g, t, p.shift > 0);
+        row_softmax(s, p0);
+        mma_rows_x_rowsT<HD>(dp, dOs, Vs, r0, g, t);  // dP = dO V^T
+
+        // stage P (for dV) while S/P0/dP are live, then fold everything into dS
+#pragma unroll
+        for (int half = 0; half < 2; ++half) {
+            float rowdot = 0.f;
+#pragma unroll
+            for (int nt = 0; nt < 8; ++nt)
+#pragma unroll
+                for (int e = 0; e < 2; ++e) rowdot += dp[nt][half * 2 + e] * p0[nt][half * 2 + e];
+            rowdot += __shfl_xor_sync(0xffffffffu, rowdot, 1);
+            rowdot += __shfl_xor_sync(0xffffffffu, rowdot, 2);
+            const int i = r0 + g + half * 8;
+#pragma unroll
+            for (int nt = 0; nt < 8; ++nt) {
+                float pv[2], dv[2];
+#pragma unroll
+                for (int e = 0; e < 2; ++e) {
+                    const int c = half * 2 + e;
+                    const float r = fmaxf(s[nt][c], 0.f);
+                    const float P0 = p0[nt][c], dP = dp[nt][c];
+                    g1 += dP * P0;
+                    g2 += dP * r * r;
+                    pv[e] = tf32_round(w0 * P0 + w1 * r * r);
+                    const float ds = w0 * P0 * (dP - rowdot) + w1 * 2.f * r * dP;
+                    dsacc[nt][c] += ds;
+                    dp[nt][c] = ds;  // dp now holds dS
+                    dv[e] = tf32_round(ds);
+                }
+                const int j = nt * 8 + 2 * t;
+                *reinterpret_cast<float2*>(Ps + i * PS_STRIDE + j) = make_float2(pv[0], pv[1]);
+                *reinterpret_cast<float2*>(dSs + i * PS_STRIDE + j) = make_float2(dv[0], dv[1]);
+            }
+        }
+        // dQ = scale * dS K  (Qs holds scale*q, so the chain rule adds one more factor scale)
+        {
+            float dq[HD / 8][4];
+            mma_regs_x_rows<HD>(dq, dp, Ks, g, t);
+#pragma unroll
+            for (int half = 0; half < 2; ++half) {
+                float* drow = dq_buf + rows[r0 + g + half * 8] * p.ld_q + p.q_off + h * HD;
+#pragma unroll
+                for (int n = 0; n < HD / 8; ++n)
+                    *reinterpret_cast<float2*>(drow + n * 8 + 2 * t) =
+                        make_float2(dq[n][half * 2] * p.scale, dq[n][half * 2 + 1] * p.scale);
+            }
+        }
+        __syncthreads();  // Ps / dSs complete
+
+        // dV[j,:] = sum_i P[i,j] dO[i,:]   and   dK[j,:] = sum_i dS[i,j] (scale q)[i,:]
+#pragma unroll
+        for (int which = 0; which < 2; ++which) {
+            const float* Am = which == 0 ? Ps : dSs;
+            const float* Bm = which == 0 ? dOs : Qs;
+            float acc[HD / 8][4];
+#pragma unroll
+            for (int n = 0; n < HD / 8; ++n)
+#pragma unroll
+                for (int c = 0; c < 4; ++c) acc[n][c] = 0.f;
+#pragma unroll
+            for (int kb = 0; kb < 8; ++kb) {
+                uint32_t a[4];
+                a[0] = __float_as_uint(Am[(kb * 8 + t) * PS_STRIDE + r0 + g]);
+                a[1] = __float_as_uint(Am[(kb * 8 + t) * PS_STRIDE + r0 + g + 8]);
+                a[2] = __float_as_uint(Am[(kb * 8 + t + 4) * PS_STRIDE + r0 + g]);
+                a[3] = __float_as_uint(Am[(kb * 8 + t + 4) * PS_STRIDE + r0 + g + 8]);
+#pragma unroll
+                for (int n = 0; n < HD / 8; ++n) {
+                    uint32_t bb[2];
+                    bb[0] = __float_as_uint(Bm[(kb * 8 + t) * ST + n * 8 + g]);
+                    bb[1] = __float_as_uint(Bm[(kb * 8 + t + 4) * ST + n * 8 + g]);
+                    mma_tf32_16x8x8(acc[n], a, bb);
+                }
+            }
+            const int off = which == 0 ? p.v_off : p.k_off;
+#pragma unroll
+            for (int half = 0; half < 2; ++half) {
+                float* drow = dkv_buf + rows[r0 + g + half * 8] * p.ld_kv + off + h * HD;
+#pragma unroll
+                for (int n = 0; n < HD / 8; ++n)
+                    *reinterpret_cast<float2*>(drow + n * 8 + 2 * t) =
+                        make_float2(acc[n][half * 2], acc[n][half * 2 + 1]);
+            }
+        }
+    }
+
+    // ---- bin the accumulated dS into the 225 relative-position slots (deterministic) ----
+    __syncthreads();
+#pragma unroll
+    for (int half = 0; half < 2; ++half) {
+        const int i = r0 + g + half * 8;
+#pragma unroll
+        for (int nt = 0; nt < 8; ++nt)
+            *reinterpret_cast<float2*>(Ps + i * PS_STRIDE + nt * 8 + 2 * t) =
+                make_float2(dsacc[nt][half * 2], dsacc[nt][half * 2 + 1]);
+    }
+    g1 = warp_sum(g1);
+    g2 = warp_sum(g2);
+    if (lane == 0) {
+        red[0][warp] = g1;
+        red[1][warp] = g2;
+    }
+    __syncthreads();
+    float* part = partials + ((long long)h * gridDim.x + blockIdx.x) * (NBINS + 3);
+    for (int bin = threadIdx.x; bin < NBINS; bin += ATT_THREADS) {
+        const int dy = bin / 15 - 7, dx = bin % 15 - 7;
+        float sum = 0.f;
+        for (int yj = max(0, -dy); yj < min(8, 8 - dy); ++yj)
+            for (int xj = max(0, -dx); xj < min(8, 8 - dx); ++xj) {
+                const int j = yj * 8 + xj, i = (yj + dy) * 8 + (xj + dx);
+                sum += Ps[i * PS_STRIDE + j];
+            }
+        part[bin] = sum;
+    }
+    if (threadIdx.x == 0) {
+        part[NBINS] = red[0][0] + red[0][1] + red[0][2] + red[0][3];
+        part[NBINS + 1] = red[1][0] + red[1][1] + red[1][2] + red[1][3];
+    }
+}
+
+__global__ void attn_param_reduce_kernel(const float* __restrict__ partials, const float* __restrict__ w_param,
+                                         float* __restrict__ dtable, float* __restrict__ dw, int heads,
+                                         int ctas_per_head) {
+    const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx < NBINS * heads) {
+        const int bin = idx / heads, h = idx % heads;
+        float s = 0.f;
+        for (int c = 0; c < ctas_per_head; ++c) s += partials[((long long)h * ctas_per_head + c) * (NBINS + 3) + bin];
+        dtable[idx] = s;
+    }
+    if (idx == 0 && dw != nullptr) {
+        float g1 = 0.f, g2 = 0.f;
+        for (int i = 0; i < heads * ctas_per_head; ++i) {
+            g1 += partials[(long long)i * (NBINS + 3) + NBINS];
+            g2 += partials[(long long)i * (NBINS + 3) + NBINS + 1];
+        }
+        float w0 = 1.f, w1 = 0.f;
+        if (w_param) {
+            const float e0 = expf(w_param[0]), e1 = expf(w_param[1]);
+            w0 = e0 / (e0 + e1);
+            w1 = e1 / (e0 + e1);
+        }
+        const float mix = w0 * g1 + w1 * g2;
+        dw[0] = w0 * (g1 - mix);
+        dw[1] = w1 * (g2 - mix);
+    }
+}
+
+int bwd_ctas_per_head(const uwr_attn_desc* d) {
+    const int tiles = d->B * (d->H / WIN) * (d->W / WIN);
+    int c = (3 * uwr_sm_count() + d->heads - 1) / d->heads;
+    if (c > tiles) c = tiles;
+    if (c < 1) c = 1;
+    return c;
+}
+
+template <int HD>
+constexpr int fwd_smem() { return (3 * NTOK * (HD + 4) + 228 + NTOK) * 4 + NTOK * 8; }
+template <int HD>
+constexpr int bwd_smem() { return (4 * NTOK * (HD + 4) + 2 * NTOK * PS_STRIDE + 228 + NTOK) * 4 + NTOK * 8; }
+
+int fill_params(const uwr_attn_desc* d, AttnParams& p, const char* who) {
+    UWR_REQUIRE(d && d->q && d->kv && d->bias_table, "%s: null pointer", who);
+    UWR_REQUIRE(d->H % WIN == 0 && d->W % WIN == 0 && d->H >= WIN && d->W >= WIN, "%s: H,W must be multiples of 8", who);
+    UWR_REQUIRE(d->shift >= 0 && d->shift < WIN, "%s: shift must be in [0,8)", who);
+    UWR_REQUIRE(d->ld_q % 4 == 0 && d->ld_kv % 4 == 0 && d->q_off % 4 == 0 && d->k_off % 4 == 0 && d->v_off % 4 == 0,
+                "%s: leading dims / offsets must be multiples of 4", who);
+    p.q = d->q; p.ld_q = d->ld_q; p.q_off = d->q_off;
+    p.kv = d->kv; p.ld_kv = d->ld_kv; p.k_off = d->k_off; p.v_off = d->v_off;
+    p.table = d->bias_table; p.w_param = d->w_param;
+    p.B = d->B; p.H = d->H; p.W = d->W; p.heads = d->heads; p.shift = d->shift; p.scale = d->scale;
+    p.nWx = d->W / WIN; p.nW = (d->H / WIN) * (d->W / WIN);
+    return 0;
+}
+
+template <int HD>
+int launch_fwd(const AttnParams& p, float* out, long long ld_out, cudaStream_t stream) {
+    auto kern = attn_fwd_kernel<HD>;
+    static bool configured = false;
+    if (!configured) {
+        UWR_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, fwd_smem<HD>()));
+        configured = true;
+    }
+    const long long tiles = (long long)p.B * p.nW * p.heads;
+    kern<<<(unsigned)tiles, ATT_THREADS, fwd_smem<HD>(), stream>>>(p, out, ld_out);
+    UWR_CHECK_LAUNCH("attn_fwd_kernel");
+    return 0;
+}
+
+template <int HD>
+int launch_bwd(const AttnParams& p, const float* dout, long long ld_dout, float* dq, float* dkv, float* partials,
+               int cph, cudaStream_t stream) {
+    auto kern = attn_bwd_kernel<HD>;
+    static bool configured = false;
+    if (!configured) {
+        UWR_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, bwd_smem<HD>()));
+        configured = true;
+    }
+    kern<<<dim3(cph, p.heads), ATT_THREADS, bwd_smem<HD>(), stream>>>(p, dout, ld_dout, dq, dkv, partials);
+    UWR_CHECK_LAUNCH("attn_bwd_kernel");
+    return 0;
+}
+
+}  // namespace
+
+extern "C" int uwr_window_attn_fwd(const uwr_attn_desc* d, float* out, long long ld_out, uwr_stream_t stream_) {
+    cudaStream_t stream = (cudaStream_t)stream_;
+    AttnParams p;
+    if (int rc = fill_params(d, p, "uwr_window_attn_fwd")) return rc;
+    UWR_REQUIRE(out && ld_out % 2 == 0, "uwr_window_attn_fwd: bad output");
+    switch (d->head_dim) {
+        case 8: return launch_fwd<8>(p, out, ld_out, stream);
+        case 16: return launch_fwd<16>(p, out, ld_out, stream);
+        case 32: return launch_fwd<32>(p, out, ld_out, stream);
+        case 64: return launch_fwd<64>(p, out, ld_out, stream);
+        case 128: return launch_fwd<128>(p, out, ld_out, stream);
+    }
+    uwr_set_error("uwr_window_attn_fwd: head_dim %d unsupported (8,16,32,64,128)", d->head_dim);
+    return -1;
+}
+
+extern "C" size_t uwr_window_attn_bwd_workspace_bytes(const uwr_attn_desc* d) {
+    return (size_t)d->heads * bwd_ctas_per_head(d) * (NBINS + 3) * sizeof(float);
+}
+
+extern "C" int uwr_window_attn_bwd(const uwr_attn_desc* d, const float* dout, long long ld_dout, float* dq_buf,
+                                   float* dkv_buf, float* dbias_table, float* dw, float* workspace,
+                                   uwr_stream_t stream_) {
+    cudaStream_t stream = (cudaStream_t)stream_;
+    AttnParams p;
+    if (int rc = fill_params(d, p, "uwr_window_attn_bwd")) return rc;
+    UWR_REQUIRE(dout && dq_buf && dkv_buf && dbias_table && workspace && ld_dout % 4 == 0, "uwr_window_attn_bwd: bad args");
+    const int cph = bwd_ctas_per_head(d);
+    int rc;
+    switch (d->head_dim) {
+        case 8: rc = launch_bwd<8>(p, dout, ld_dout, dq_buf, dkv_buf, workspace, cph, stream); break;
+        case 16: rc = launch_bwd<16>(p, dout, ld_dout, dq_buf, dkv_buf, workspace, cph, stream); break;
+        case 32: rc = launch_bwd<32>(p, dout, ld_dout, dq_buf, dkv_buf, workspace, cph, stream); break;
+        case 64: rc = launch_bwd<64>(p, dout, ld_dout, dq_buf, dkv_buf, workspace, cph, stream); break;
+        case 128: rc = launch_bwd<128>(p, dout, ld_dout, dq_buf, dkv_buf, workspace, cph, stream); break;
+        default:
+            uwr_set_error("uwr_window_attn_bwd: head_dim %d unsupported (8,16,32,64,128)", d->head_dim);
+            return -1;
+    }
+    if (rc) return rc;
+    attn_param_reduce_kernel<<<uwr_cdiv(NBINS * d->heads, 128), 128, 0, stream>>>(workspace, d->w_param, dbias_table,
+                                                                                dw, d->heads, cph);
+    UWR_CHECK_LAUNCH("attn_param_reduce_kernel");
+    return 0;
+}

@@ -1,0 +1,107 @@
+"""ctypes binding of libuwr_b200.so (the C ABI declared in include/uwr_b200.h).
+
+There is deliberately NO fallback: if the CUDA library is missing the import fails loudly.
+"""
+import ctypes as C
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "..", "csrc", "libuwr_b200.so")
+LIB_PATH = os.path.normpath(LIB_PATH)
+
+if not os.path.exists(LIB_PATH):
+    raise ImportError(
+        f"uwr: native library {LIB_PATH} is missing. Build it with "
+        "`python underwater-image-restoration_b200/build.py` (nvcc, sm_100a). "
+        "There is no CPU/PyTorch fallback for the hot path.")
+
+lib = C.CDLL(LIB_PATH)
+
+c_fp = C.c_void_p      # device float*
+c_ll = C.c_longlong
+c_int = C.c_int
+c_f = C.c_float
+c_sz = C.c_size_t
+c_stream = C.c_void_p
+
+
+class GemmDesc(C.Structure):
+    _fields_ = [
+        ("A", c_fp), ("lda", c_ll), ("a_km", c_int),
+        ("B", c_fp), ("ldb", c_ll), ("b_nk", c_int),
+        ("B2", c_fp), ("n_split", c_int),
+        ("C", c_fp), ("ldc", c_ll),
+        ("M", c_int), ("N", c_int), ("K", c_int),
+        ("bias", c_fp), ("bias2", c_fp),
+        ("epilogue", c_int),
+        ("R", c_fp), ("ldr", c_ll),
+        ("rowscale", c_fp), ("rows_per_group", c_int),
+        ("colsum", c_fp),
+        ("workspace", c_fp), ("workspace_bytes", c_sz),
+    ]
+
+
+class AttnDesc(C.Structure):
+    _fields_ = [
+        ("q", c_fp), ("ld_q", c_ll), ("q_off", c_int),
+        ("kv", c_fp), ("ld_kv", c_ll), ("k_off", c_int), ("v_off", c_int),
+        ("bias_table", c_fp), ("w_param", c_fp),
+        ("B", c_int), ("H", c_int), ("W", c_int), ("heads", c_int), ("head_dim", c_int),
+        ("shift", c_int), ("scale", c_f),
+    ]
+
+
+def _sig(name, restype, argtypes):
+    fn = getattr(lib, name)
+    fn.restype = restype
+    fn.argtypes = argtypes
+    return fn
+
+
+SIGNATURES = {
+    "uwr_last_error": (C.c_char_p, []),
+    "uwr_abi_version": (c_int, []),
+    "uwr_device_sm_count": (c_int, []),
+    "uwr_gemm_workspace_bytes": (c_sz, [c_int, c_int, c_int, c_int]),
+    "uwr_gemm_tf32": (c_int, [C.POINTER(GemmDesc), c_stream]),
+    "uwr_layernorm_fwd": (c_int, [c_fp, c_fp, c_fp, c_fp, c_fp, c_fp, c_ll, c_int, c_f, c_stream]),
+    "uwr_layernorm_bwd_workspace_bytes": (c_sz, [c_ll, c_int]),
+    "uwr_layernorm_bwd": (c_int, [c_fp] * 10 + [c_ll, c_int, c_stream]),
+    "uwr_window_attn_fwd": (c_int, [C.POINTER(AttnDesc), c_fp, c_ll, c_stream]),
+    "uwr_window_attn_bwd_workspace_bytes": (c_sz, [C.POINTER(AttnDesc)]),
+    "uwr_window_attn_bwd": (c_int, [C.POINTER(AttnDesc), c_fp, c_ll, c_fp, c_fp, c_fp, c_fp, c_fp, c_stream]),
+    "uwr_dwconv_gelu_fwd": (c_int, [c_fp, c_ll, c_fp, c_fp, c_fp, c_fp, c_int, c_int, c_int, c_int, c_int, c_stream]),
+    "uwr_dwconv_gelu_bwd_workspace_bytes": (c_sz, [c_int, c_int, c_int, c_int]),
+    "uwr_dwconv_gelu_bwd": (c_int, [c_fp, c_fp, c_ll, c_fp, c_fp, c_fp, c_fp, c_fp, c_fp,
+                                    c_int, c_int, c_int, c_int, c_int, c_stream]),
+    "uwr_input_proj_fwd": (c_int, [c_fp, c_fp, c_fp, c_fp, c_int, c_int, c_int, c_int, c_int, c_f, c_stream]),
+    "uwr_input_proj_bwd_workspace_bytes": (c_sz, [c_int] * 5),
+    "uwr_input_proj_bwd": (c_int, [c_fp] * 6 + [c_int] * 5 + [c_f, c_stream]),
+    "uwr_output_proj_fwd": (c_int, [c_fp, c_ll, c_fp, c_fp, c_fp, c_fp, c_int, c_int, c_int, c_int, c_stream]),
+    "uwr_output_proj_bwd_workspace_bytes": (c_sz, [c_int] * 4),
+    "uwr_output_proj_bwd": (c_int, [c_fp, c_fp, c_ll, c_fp, c_fp, c_fp, c_fp, c_fp,
+                                    c_int, c_int, c_int, c_int, c_stream]),
+    "uwr_im2col_4x4s2": (c_int, [c_fp, c_ll, c_fp, c_int, c_int, c_int, c_int, c_stream]),
+    "uwr_col2im_4x4s2": (c_int, [c_fp, c_fp, c_int, c_int, c_int, c_int, c_stream]),
+    "uwr_pixel_scatter_2x2": (c_int, [c_fp, c_fp, c_fp, c_ll, c_int, c_int, c_int, c_int, c_stream]),
+    "uwr_pixel_gather_2x2": (c_int, [c_fp, c_ll, c_fp, c_int, c_int, c_int, c_int, c_stream]),
+    "uwr_copy2d": (c_int, [c_fp, c_ll, c_fp, c_ll, c_ll, c_int, c_int, c_stream]),
+    "uwr_colsum": (c_int, [c_fp, c_ll, c_fp, c_fp, c_ll, c_int, c_stream]),
+    "uwr_pixel_loss": (c_int, [c_fp, c_fp, c_fp, c_fp, c_fp, c_int, c_int, c_int, c_int, c_int, c_int, c_stream]),
+    "uwr_grad_norm": (c_int, [c_fp, c_fp, c_int, c_ll, c_f, c_f, c_fp, c_fp, c_stream]),
+    "uwr_adam_step": (c_int, [c_fp, c_fp, c_fp, c_fp, c_fp, c_int, c_ll, c_fp, c_f, c_f, c_f, c_f, c_f, c_f,
+                              c_int, c_int, c_fp, c_stream]),
+    "uwr_increment_i32": (c_int, [c_fp, c_stream]),
+}
+
+fn = {name: _sig(name, *sig) for name, sig in SIGNATURES.items()}
+
+
+class UwrError(RuntimeError):
+    pass
+
+
+def check(rc, who):
+    if rc != 0:
+        msg = fn["uwr_last_error"]()
+        raise UwrError(f"{who} failed ({rc}): {msg.decode() if msg else ''}")

@@ -1,0 +1,208 @@
+"""Hand-written forward/backward of the building blocks of the restoration transformers.
+
+Each autograd.Function below is one fused "block" of the reference with an explicit backward made
+of uwr kernels (no ATen autograd graph inside):
+
+  InputProjFn     AST.InputProj            (AST.py:447-466)
+  OutputProjFn    AST.OutputProj + x + y   (AST.py:470-493, 921)
+  DownsampleFn    AST.Downsample           (AST.py:408-424)
+  UpsampleCatFn   AST.Upsample + torch.cat (AST.py:428-443, 903-916)
+  AttnBlockFn     x + DropPath(W-MSA(LN1(x)))   (TransformerBlock.forward, AST.py:590-619)
+  LeFFBlockFn     x + DropPath(LeFF(LN2(x)))    (AST.py:307-326, 622)
+
+Token tensors are (B, L, C) fp32 contiguous; DropPath arrives as a per-sample scale vector
+(mask / keep_prob) or None.
+"""
+import torch
+from torch.autograd.function import once_differentiable
+
+from . import ops
+
+
+def _c(t):
+    return t if t.is_contiguous() else t.contiguous()
+
+
+class InputProjFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, img, weight, bias, slope):
+        img = _c(img)
+        tokens = ops.input_proj_fwd(img, weight, bias, slope)
+        ctx.save_for_backward(img, weight, tokens)
+        ctx.slope = slope
+        return tokens
+
+    @staticmethod
+    @once_differentiable
+    def backward(ctx, dtokens):
+        img, weight, tokens = ctx.saved_tensors
+        dweight, dbias = ops.input_proj_bwd(_c(dtokens), tokens, img, weight, ctx.slope)
+        # the image itself never needs a gradient on the training path
+        return None, dweight, dbias, None
+
+
+class OutputProjFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, tokens, weight, bias, residual_img, H, W):
+        tokens = _c(tokens)
+        B = tokens.shape[0]
+        out = ops.output_proj_fwd(tokens, weight, bias, residual_img, B, H, W)
+        ctx.save_for_backward(tokens, weight)
+        ctx.hw = (H, W)
+        return out
+
+    @staticmethod
+    @once_differentiable
+    def backward(ctx, dout):
+        tokens, weight = ctx.saved_tensors
+        H, W = ctx.hw
+        dtokens, dweight, dbias = ops.output_proj_bwd(_c(dout), tokens, weight, tokens.shape[0], H, W)
+        return dtokens, dweight, dbias, None, None, None
+
+
+class DownsampleFn(torch.autograd.Function):
+    """Conv4x4 stride 2 pad 1 on tokens = im2col (tap-major K) + TF32 GEMM."""
+
+    @staticmethod
+    def forward(ctx, x, weight, bias, H, W):
+        x = _c(x)
+        B, L, Cc = x.shape
+        Cout = weight.shape[0]
+        # (Cout, Cin, 4, 4) -> (Cout, 4, 4, Cin): K index = (ky, kx, ci) matches the im2col rows
+        wmat = weight.permute(0, 2, 3, 1).reshape(Cout, 16 * Cc)
+        col = ops.im2col_4x4s2(x.view(B * L, Cc), B, H, W, Cc)
+        y = ops.linear(col, wmat, bias)
+        ctx.save_for_backward(x, wmat)
+        ctx.dims = (B, H, W, Cc, Cout)
+        return y.view(B, L // 4, Cout)
+
+    @staticmethod
+    @once_differentiable
+    def backward(ctx, dy):
+        x, wmat = ctx.saved_tensors
+        B, H, W, Cc, Cout = ctx.dims
+        dy2 = _c(dy).view(-1, Cout)
+        col = ops.im2col_4x4s2(x.view(-1, Cc), B, H, W, Cc)  # recomputed, not saved (4x the input)
+        dwmat, dbias = ops.linear_wgrad(dy2, col)
+        del col
+        dcol = ops.linear_dgrad(dy2, wmat)
+        dx = ops.col2im_4x4s2(dcol, B, H, W, Cc)
+        dweight = dwmat.view(Cout, 4, 4, Cc).permute(0, 3, 1, 2).contiguous()
+        return dx.view(B, H * W, Cc), dweight, dbias, None, None
+
+
+class UpsampleCatFn(torch.autograd.Function):
+    """ConvTranspose2x2 stride 2 (GEMM + 2x2 pixel scatter) written straight into the left half of
+    the concatenated decoder input; the encoder skip is copied into the right half."""
+
+    @staticmethod
+    def forward(ctx, x, weight, bias, skip, H, W):
+        x = _c(x)
+        skip = _c(skip)
+        B, L, Cin = x.shape
+        Cout = weight.shape[1]
+        Cs = skip.shape[2]
+        wmat = weight.view(Cin, Cout * 4)  # stored [K=Cin][N=(co,dy,dx)]
+        g = ops._empty((B * L, Cout * 4), x)
+        ops.gemm(x.view(B * L, Cin), wmat, g, B * L, Cout * 4, Cin, lda=Cin, ldb=Cout * 4, ldc=Cout * 4,
+                 b_nk=False)
+        out = ops._empty((B, 4 * L, Cout + Cs), x)
+        out2 = out.view(B * 4 * L, Cout + Cs)
+        ops.pixel_scatter_2x2(g, bias, out2, B, H, W, Cout)
+        ops.copy2d(skip.view(B * 4 * L, Cs), out2[:, Cout:], Cs)
+        ctx.save_for_backward(x, weight)
+        ctx.dims = (B, H, W, Cin, Cout, Cs)
+        return out
+
+    @staticmethod
+    @once_differentiable
+    def backward(ctx, dout):
+        x, weight = ctx.saved_tensors
+        B, H, W, Cin, Cout, Cs = ctx.dims
+        L = H * W
+        d2 = _c(dout).view(B * 4 * L, Cout + Cs)
+        dskip = ops._empty((B, 4 * L, Cs), x)
+        ops.copy2d(d2[:, Cout:], dskip.view(B * 4 * L, Cs), Cs)
+        dbias = ops.colsum(d2, Cout)
+        dg = ops.pixel_gather_2x2(d2, B, H, W, Cout)
+        wmat = weight.view(Cin, Cout * 4)
+        # dx[M,Cin] = dg[M,4Cout] wmat^T : B stored [N=Cin][K=4Cout]
+        dx = ops._empty((B * L, Cin), x)
+        ops.gemm(dg, wmat, dx, B * L, Cin, Cout * 4, lda=Cout * 4, ldb=Cout * 4, ldc=Cin, b_nk=True)
+        # dW[Cin,4Cout] = x^T dg
+        dwmat = ops._empty((Cin, Cout * 4), x)
+        ops.gemm(x.view(B * L, Cin), dg, dwmat, Cin, Cout * 4, B * L, lda=Cin, ldb=Cout * 4, ldc=Cout * 4,
+                 a_km=True, b_nk=False)
+        return dx.view(B, L, Cin), dwmat.view_as(weight), dbias, dskip, None, None
+
+
+class AttnBlockFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, n1w, n1b, wq, bq, wkv, bkv, table, wparam, wp, bp, dp_scale, H, W, heads, shift, scale):
+        x = _c(x)
+        B, L, Cc = x.shape
+        M = B * L
+        x2 = x.view(M, Cc)
+        hd = Cc // heads
+        y1, mean, rstd = ops.layernorm_fwd(x2, n1w, n1b)
+        qkv = ops.linear(y1, wq, bq, weight2=wkv, bias2=bkv)
+        o = ops.window_attn_fwd(qkv, 0, qkv, Cc, 2 * Cc, table, wparam, B, H, W, heads, hd, shift, scale)
+        x1 = ops.linear(o, wp, bp, residual=x2, rowscale=dp_scale, rows_per_group=L)
+        ctx.save_for_backward(x2, n1w, mean, rstd, y1, qkv, o, wq, wkv, table, wparam, wp, dp_scale)
+        ctx.meta = (B, L, Cc, H, W, heads, hd, shift, scale, bq is not None)
+        return x1.view(B, L, Cc)
+
+    @staticmethod
+    @once_differentiable
+    def backward(ctx, dx1):
+        x2, n1w, mean, rstd, y1, qkv, o, wq, wkv, table, wparam, wp, dp = ctx.saved_tensors
+        B, L, Cc, H, W, heads, hd, shift, scale, has_qkv_bias = ctx.meta
+        d = _c(dx1).view(B * L, Cc)
+        d_o = ops.linear_dgrad(d, wp, rowscale=dp, rows_per_group=L)
+        dwp, dbp = ops.linear_wgrad(d, o, rowscale=dp, rows_per_group=L)
+        dqkv, _, dtable, dw = ops.window_attn_bwd(d_o, qkv, 0, qkv, Cc, 2 * Cc, table, wparam, B, H, W, heads, hd,
+                                                  shift, scale)
+        del d_o
+        dy1 = ops.linear_dgrad(dqkv, wq, weight2=wkv)
+        dwqkv, dbqkv = ops.linear_wgrad(dqkv, y1, want_bias=has_qkv_bias)
+        del dqkv
+        dx, dg, db = ops.layernorm_bwd(dy1, x2, n1w, mean, rstd, dres=d)
+        dbq = dbqkv[:Cc] if has_qkv_bias else None
+        dbkv = dbqkv[Cc:] if has_qkv_bias else None
+        return (dx.view(B, L, Cc), dg, db, dwqkv[:Cc], dbq, dwqkv[Cc:], dbkv, dtable,
+                dw if wparam is not None else None, dwp, dbp, None, None, None, None, None, None)
+
+
+class LeFFBlockFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, n2w, n2b, w1, b1, dww, dwb, w2, b2, dp_scale, H, W):
+        x = _c(x)
+        B, L, Cc = x.shape
+        M = B * L
+        Ch = w1.shape[0]
+        x2 = x.view(M, Cc)
+        y2, mean, rstd = ops.layernorm_fwd(x2, n2w, n2b)
+        u = ops.linear(y2, w1, b1)
+        need_bwd = any(ctx.needs_input_grad)
+        v, h2 = ops.dwconv_gelu_fwd(u, dww, dwb, B, H, W, Ch, mode=0, save_v=need_bwd)
+        out = ops.linear(h2, w2, b2, residual=x2, rowscale=dp_scale, rows_per_group=L)
+        if need_bwd:
+            ctx.save_for_backward(x2, n2w, mean, rstd, y2, u, v, h2, w1, dww, w2, dp_scale)
+        ctx.meta = (B, L, Cc, Ch, H, W)
+        return out.view(B, L, Cc)
+
+    @staticmethod
+    @once_differentiable
+    def backward(ctx, dout):
+        x2, n2w, mean, rstd, y2, u, v, h2, w1, dww, w2, dp = ctx.saved_tensors
+        B, L, Cc, Ch, H, W = ctx.meta
+        d = _c(dout).view(B * L, Cc)
+        dh2 = ops.linear_dgrad(d, w2, rowscale=dp, rows_per_group=L)
+        dw2, db2 = ops.linear_wgrad(d, h2, rowscale=dp, rows_per_group=L)
+        du, ddww, ddwb = ops.dwconv_gelu_bwd(dh2, u, v, dww, B, H, W, Ch, mode=0)
+        del dh2
+        dy2 = ops.linear_dgrad(du, w1)
+        dw1, db1 = ops.linear_wgrad(du, y2)
+        del du
+        dx, dg, db = ops.layernorm_bwd(dy2, x2, n2w, mean, rstd, dres=d)
+        return dx.view(B, L, Cc), dg, db, dw1, db1, ddww, ddwb, dw2, db2, None, None, None
