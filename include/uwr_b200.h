@@ -29,6 +29,7 @@ typedef struct CUstream_st* uwr_stream_t; /* == cudaStream_t */
 const char* uwr_last_error(void);
 int uwr_abi_version(void);
 int uwr_device_sm_count(void);
+unsigned long long uwr_launch_count(void); /* kernels launched by this library so far */
 
 /* ---- GEMM (nn.Linear fwd/bwd: AST.py:47-48,104,297,302,332,337; block.py:158-160) --------
  * C[M,N] = epilogue( opA(A)[M,K] * opB(B)[K,N] ), TF32 tensor-core math (operands rounded to
@@ -72,6 +73,10 @@ typedef struct {
 } uwr_gemm_desc;
 
 size_t uwr_gemm_workspace_bytes(int M, int N, int K, int a_km);
+/* passes = 1: single TF32 product (default, ~4e-4 relative per GEMM);
+ * passes = 3: error-compensated 3xTF32 (a_lo*b_hi + a_hi*b_lo + a_hi*b_hi), fp32-level accuracy. */
+int uwr_set_gemm_precision(int passes);
+int uwr_get_gemm_precision(void);
 int uwr_gemm_tf32(const uwr_gemm_desc* d, uwr_stream_t stream);
 
 /* ---- LayerNorm over C (nn.LayerNorm eps 1e-5: AST.py:521,534,593,622) ------------------- */

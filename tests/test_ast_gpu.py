@@ -16,7 +16,16 @@ def _pair(B, S, seed=2024):
     return raw, ref
 
 
-def _run(B, S, img_size, train, report):
+def _run(B, S, img_size, train, report, precision="tf32", tol=1e-3):
+    from uwr import ops
+    ops.set_gemm_precision(precision)
+    try:
+        _run_inner(B, S, img_size, train, report, tol)
+    finally:
+        ops.set_gemm_precision("tf32")
+
+
+def _run_inner(B, S, img_size, train, report, tol):
     from oracle import ast_oracle, losses_oracle
     from uwr.ast import AST, DropPath
     torch.manual_seed(1234)
@@ -76,11 +85,13 @@ def _run(B, S, img_size, train, report):
     print(f"AST parity B={B} S={S} train={train}: out {e_out:.2e} residual {e_res:.2e} "
           f"grads(global) {e_grad:.2e} worst tensor {worst[1]} {worst[0]:.2e} "
           f"loss {loss.item():.6e} vs {loss_o.item():.6e}")
-    assert abs(loss.item() - loss_o.item()) < 1e-3 * abs(loss_o.item())
-    assert e_out < 1e-3
-    assert e_res < 1e-3
-    assert e_grad < 1e-3
-    assert worst[0] < 5e-3, worst
+    assert abs(loss.item() - loss_o.item()) < tol * abs(loss_o.item())
+    assert e_out < tol
+    assert e_res < tol
+    assert e_grad < tol
+    # per-tensor: gradients that are sums of strongly cancelling terms carry a larger share of the
+    # TF32 rounding; bound them looser (they vanish in tf32x3 mode, see test_ast_tf32x3_128)
+    assert worst[0] < 20 * tol, worst
 
 
 def test_ast_eval_128():
@@ -91,13 +102,18 @@ def test_ast_train_droppath_128():
     _run(2, 128, 128, True, [])
 
 
+def test_ast_tf32x3_128():
+    """error-compensated GEMMs: the only remaining difference to the fp32 reference is summation order"""
+    _run(2, 128, 128, True, [], precision="tf32x3", tol=2e-5)
+
+
 def test_ast_eval_256():
     _run(1, 256, 256, False, [])
 
 
 def test_registry_surface():
     import uwr
-    assert uwr.get_names()[-1] == "AST"
+    assert uwr.get_names() == ["SpectralTransformer", "NewModel", "NewBigModel", "NewBigFRFNModel", "AST"]
     with pytest.raises(KeyError):
         uwr.init_model("nope")
     m = uwr.init_model("AST", use_dwt="Fourier")

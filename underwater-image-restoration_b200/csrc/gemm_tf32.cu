@@ -46,8 +46,8 @@ struct TileCfg {
     static constexpr int SMEM_BYTES = STAGES * (A_TILE + B_TILE) * (int)sizeof(float);
 };
 
-template <int BN, bool A_KM, bool B_NK, int EPI, bool KSCALE>
-__global__ void __launch_bounds__(NTHREADS, 2) gemm_tf32_kernel(const GemmParams p) {
+template <int BN, bool A_KM, bool B_NK, int EPI, bool KSCALE, bool X3>
+__global__ void __launch_bounds__(NTHREADS, X3 ? 1 : 2) gemm_tf32_kernel(const GemmParams p) {
     using Cfg = TileCfg<BN, A_KM, B_NK>;
     extern __shared__ __align__(16) float smem[];
     float* As = smem;
@@ -147,6 +147,7 @@ __global__ void __launch_bounds__(NTHREADS, 2) gemm_tf32_kernel(const GemmParams
 #pragma unroll
         for (int kk = 0; kk < BK; kk += 8) {
             uint32_t af[MT][4];
+            uint32_t al[X3 ? MT : 1][4];  // low parts (3xTF32 mode)
             float ks0 = 1.f, ks1 = 1.f;
             if (KSCALE) {
                 // DropPath scale of the incoming gradient rows (contraction index)
@@ -185,17 +186,36 @@ __global__ void __launch_bounds__(NTHREADS, 2) gemm_tf32_kernel(const GemmParams
                 af[mt][1] = f2tf32(a1);
                 af[mt][2] = f2tf32(a2);
                 af[mt][3] = f2tf32(a3);
+                if (X3) {
+                    al[X3 ? mt : 0][0] = f2tf32(a0 - __uint_as_float(af[mt][0]));
+                    al[X3 ? mt : 0][1] = f2tf32(a1 - __uint_as_float(af[mt][1]));
+                    al[X3 ? mt : 0][2] = f2tf32(a2 - __uint_as_float(af[mt][2]));
+                    al[X3 ? mt : 0][3] = f2tf32(a3 - __uint_as_float(af[mt][3]));
+                }
             }
 #pragma unroll
             for (int nt = 0; nt < NT; ++nt) {
                 const int c0 = wn * WN_TILE + nt * 8;
                 uint32_t bf[2];
+                float b0, b1;
                 if (B_NK) {
-                    bf[0] = f2tf32(bs[(c0 + g) * Cfg::B_STRIDE + kk + t]);
-                    bf[1] = f2tf32(bs[(c0 + g) * Cfg::B_STRIDE + kk + t + 4]);
+                    b0 = bs[(c0 + g) * Cfg::B_STRIDE + kk + t];
+                    b1 = bs[(c0 + g) * Cfg::B_STRIDE + kk + t + 4];
                 } else {
-                    bf[0] = f2tf32(bs[(kk + t) * Cfg::B_STRIDE + c0 + g]);
-                    bf[1] = f2tf32(bs[(kk + t + 4) * Cfg::B_STRIDE + c0 + g]);
+                    b0 = bs[(kk + t) * Cfg::B_STRIDE + c0 + g];
+                    b1 = bs[(kk + t + 4) * Cfg::B_STRIDE + c0 + g];
+                }
+                bf[0] = f2tf32(b0);
+                bf[1] = f2tf32(b1);
+                if (X3) {
+                    uint32_t bl[2];
+                    bl[0] = f2tf32(b0 - __uint_as_float(bf[0]));
+                    bl[1] = f2tf32(b1 - __uint_as_float(bf[1]));
+#pragma unroll
+                    for (int mt = 0; mt < MT; ++mt) {
+                        mma_tf32_16x8x8(acc[mt][nt], al[X3 ? mt : 0], bf);
+                        mma_tf32_16x8x8(acc[mt][nt], af[mt], bl);
+                    }
                 }
 #pragma unroll
                 for (int mt = 0; mt < MT; ++mt) mma_tf32_16x8x8(acc[mt][nt], af[mt], bf);
@@ -299,10 +319,12 @@ int pick_bn(int N) {
     return 128;
 }
 
-template <int BN, bool A_KM, bool B_NK, int EPI, bool KSCALE>
-int launch(const GemmParams& p, int splits, cudaStream_t stream) {
+int g_passes = 1;  // 1: TF32 (default), 3: error-compensated 3xTF32 (fp32-level accuracy)
+
+template <int BN, bool A_KM, bool B_NK, int EPI, bool KSCALE, bool X3>
+int launch_x(const GemmParams& p, int splits, cudaStream_t stream) {
     using Cfg = TileCfg<BN, A_KM, B_NK>;
-    auto kern = gemm_tf32_kernel<BN, A_KM, B_NK, EPI, KSCALE>;
+    auto kern = gemm_tf32_kernel<BN, A_KM, B_NK, EPI, KSCALE, X3>;
     static bool configured = false;
     if (!configured) {
         UWR_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
@@ -312,6 +334,12 @@ int launch(const GemmParams& p, int splits, cudaStream_t stream) {
     kern<<<grid, NTHREADS, Cfg::SMEM_BYTES, stream>>>(p);
     UWR_CHECK_LAUNCH("gemm_tf32_kernel");
     return 0;
+}
+
+template <int BN, bool A_KM, bool B_NK, int EPI, bool KSCALE>
+int launch(const GemmParams& p, int splits, cudaStream_t stream) {
+    return g_passes == 3 ? launch_x<BN, A_KM, B_NK, EPI, KSCALE, true>(p, splits, stream)
+                         : launch_x<BN, A_KM, B_NK, EPI, KSCALE, false>(p, splits, stream);
 }
 
 template <int BN>
@@ -341,6 +369,13 @@ int dispatch_layout(const uwr_gemm_desc* d, const GemmParams& p, int splits, cud
 }
 
 }  // namespace
+
+extern "C" int uwr_set_gemm_precision(int passes) {
+    UWR_REQUIRE(passes == 1 || passes == 3, "uwr_set_gemm_precision: passes must be 1 (tf32) or 3 (tf32x3)");
+    g_passes = passes;
+    return 0;
+}
+extern "C" int uwr_get_gemm_precision(void) { return g_passes; }
 
 extern "C" size_t uwr_gemm_workspace_bytes(int M, int N, int K, int a_km) {
     if (!a_km) return 0;

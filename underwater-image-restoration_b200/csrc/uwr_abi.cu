@@ -5,6 +5,7 @@
 #include <stdio.h>
 
 static thread_local char g_err[512] = "";
+unsigned long long g_uwr_launches = 0;
 
 void uwr_set_error(const char* fmt, ...) {
     va_list ap;
@@ -27,3 +28,4 @@ int uwr_sm_count() {
 extern "C" const char* uwr_last_error(void) { return g_err; }
 extern "C" int uwr_abi_version(void) { return 1; }
 extern "C" int uwr_device_sm_count(void) { return uwr_sm_count(); }
+extern "C" unsigned long long uwr_launch_count(void) { return g_uwr_launches; }

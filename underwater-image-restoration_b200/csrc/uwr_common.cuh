@@ -17,8 +17,11 @@ void uwr_set_error(const char* fmt, ...);
         }                                      \
     } while (0)
 
+extern unsigned long long g_uwr_launches;  // kernels launched by this library (bench evidence)
+
 #define UWR_CHECK_LAUNCH(name)                                               \
     do {                                                                     \
+        ++g_uwr_launches;                                                    \
         cudaError_t e__ = cudaGetLastError();                                \
         if (e__ != cudaSuccess) {                                            \
             uwr_set_error("%s: %s", name, cudaGetErrorString(e__));          \

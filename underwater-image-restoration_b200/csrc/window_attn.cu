@@ -54,7 +54,7 @@ __device__ __forceinline__ int bias_index(int i, int j) {
     return ((i >> 3) - (j >> 3) + WIN - 1) * (2 * WIN - 1) + ((i & 7) - (j & 7) + WIN - 1);
 }
 
-// stage a 64 x HD tile (tf32-rounded) into shared memory [64][HD+4]
+// stage a 64 x HD tile (fp32) into shared memory [64][HD+4]
 template <int HD>
 __device__ __forceinline__ void stage_tile(float* dst, const float* src, long long ld, int col_off,
                                            const long long* rows, float mul) {
@@ -63,16 +63,19 @@ __device__ __forceinline__ void stage_tile(float* dst, const float* src, long lo
     for (int idx = threadIdx.x; idx < NTOK * V4; idx += ATT_THREADS) {
         const int r = idx / V4, c4 = (idx % V4) * 4;
         const float4 v = *reinterpret_cast<const float4*>(src + rows[r] * ld + col_off + c4);
-        float4 o;
-        o.x = tf32_round(v.x * mul);
-        o.y = tf32_round(v.y * mul);
-        o.z = tf32_round(v.z * mul);
-        o.w = tf32_round(v.w * mul);
-        *reinterpret_cast<float4*>(dst + r * ST + c4) = o;
+        // full fp32 is kept in shared memory: S and dP use error-compensated 3xTF32 (hi/lo split at
+        // fragment load) because softmax' and the (dP - rowdot) cancellation amplify operand rounding
+        *reinterpret_cast<float4*>(dst + r * ST + c4) = make_float4(v.x * mul, v.y * mul, v.z * mul, v.w * mul);
     }
 }
 
-// acc[nt][4] (16 rows x 64 cols) = A[r0.., :HD] * Bm[:, :HD]^T   (both row-major [64][HD+4])
+__device__ __forceinline__ void split_tf32(float x, uint32_t& hi, uint32_t& lo) {
+    hi = f2tf32(x);
+    lo = f2tf32(x - __uint_as_float(hi));
+}
+
+// acc[nt][4] (16 rows x 64 cols) = A[r0.., :HD] * Bm[:, :HD]^T   (both row-major fp32 [64][HD+4]),
+// 3xTF32: a*b ~= a_lo*b_hi + a_hi*b_lo + a_hi*b_hi  (fp32-level accuracy on the tensor cores)
 template <int HD>
 __device__ __forceinline__ void mma_rows_x_rowsT(float (&acc)[8][4], const float* A, const float* Bm, int r0,
                                                  int g, int t) {
@@ -83,17 +86,19 @@ __device__ __forceinline__ void mma_rows_x_rowsT(float (&acc)[8][4], const float
         for (int c = 0; c < 4; ++c) acc[nt][c] = 0.f;
 #pragma unroll
     for (int ks = 0; ks < HD / 8; ++ks) {
-        uint32_t a[4];
-        a[0] = __float_as_uint(A[(r0 + g) * ST + ks * 8 + t]);
-        a[1] = __float_as_uint(A[(r0 + g + 8) * ST + ks * 8 + t]);
-        a[2] = __float_as_uint(A[(r0 + g) * ST + ks * 8 + t + 4]);
-        a[3] = __float_as_uint(A[(r0 + g + 8) * ST + ks * 8 + t + 4]);
+        uint32_t ah[4], al[4];
+        split_tf32(A[(r0 + g) * ST + ks * 8 + t], ah[0], al[0]);
+        split_tf32(A[(r0 + g + 8) * ST + ks * 8 + t], ah[1], al[1]);
+        split_tf32(A[(r0 + g) * ST + ks * 8 + t + 4], ah[2], al[2]);
+        split_tf32(A[(r0 + g + 8) * ST + ks * 8 + t + 4], ah[3], al[3]);
 #pragma unroll
         for (int nt = 0; nt < 8; ++nt) {
-            uint32_t b[2];
-            b[0] = __float_as_uint(Bm[(nt * 8 + g) * ST + ks * 8 + t]);
-            b[1] = __float_as_uint(Bm[(nt * 8 + g) * ST + ks * 8 + t + 4]);
-            mma_tf32_16x8x8(acc[nt], a, b);
+            uint32_t bh[2], bl[2];
+            split_tf32(Bm[(nt * 8 + g) * ST + ks * 8 + t], bh[0], bl[0]);
+            split_tf32(Bm[(nt * 8 + g) * ST + ks * 8 + t + 4], bh[1], bl[1]);
+            mma_tf32_16x8x8(acc[nt], al, bh);
+            mma_tf32_16x8x8(acc[nt], ah, bl);
+            mma_tf32_16x8x8(acc[nt], ah, bh);
         }
     }
 }
@@ -118,8 +123,8 @@ __device__ __forceinline__ void mma_regs_x_rows(float (&out)[HD / 8][4], const f
 #pragma unroll
         for (int n = 0; n < HD / 8; ++n) {
             uint32_t b[2];
-            b[0] = __float_as_uint(Bm[(kb * 8 + 2 * t) * ST + n * 8 + g]);
-            b[1] = __float_as_uint(Bm[(kb * 8 + 2 * t + 1) * ST + n * 8 + g]);
+            b[0] = f2tf32(Bm[(kb * 8 + 2 * t) * ST + n * 8 + g]);
+            b[1] = f2tf32(Bm[(kb * 8 + 2 * t + 1) * ST + n * 8 + g]);
             mma_tf32_16x8x8(out[n], a, b);
         }
     }
@@ -362,8 +367,8 @@ __global__ void __launch_bounds__(ATT_THREADS) attn_bwd_kernel(const AttnParams 
 #pragma unroll
                 for (int n = 0; n < HD / 8; ++n) {
                     uint32_t bb[2];
-                    bb[0] = __float_as_uint(Bm[(kb * 8 + t) * ST + n * 8 + g]);
-                    bb[1] = __float_as_uint(Bm[(kb * 8 + t + 4) * ST + n * 8 + g]);
+                    bb[0] = f2tf32(Bm[(kb * 8 + t) * ST + n * 8 + g]);
+                    bb[1] = f2tf32(Bm[(kb * 8 + t + 4) * ST + n * 8 + g]);
                     mma_tf32_16x8x8(acc[n], a, bb);
                 }
             }

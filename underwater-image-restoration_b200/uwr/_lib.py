@@ -62,6 +62,9 @@ SIGNATURES = {
     "uwr_last_error": (C.c_char_p, []),
     "uwr_abi_version": (c_int, []),
     "uwr_device_sm_count": (c_int, []),
+    "uwr_launch_count": (C.c_ulonglong, []),
+    "uwr_set_gemm_precision": (c_int, [c_int]),
+    "uwr_get_gemm_precision": (c_int, []),
     "uwr_gemm_workspace_bytes": (c_sz, [c_int, c_int, c_int, c_int]),
     "uwr_gemm_tf32": (c_int, [C.POINTER(GemmDesc), c_stream]),
     "uwr_layernorm_fwd": (c_int, [c_fp, c_fp, c_fp, c_fp, c_fp, c_fp, c_ll, c_int, c_f, c_stream]),

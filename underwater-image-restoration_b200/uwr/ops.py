@@ -14,8 +14,66 @@ from ._lib import AttnDesc, GemmDesc, check, fn
 EPI_NONE, EPI_RESID, EPI_MUL_DGELU = 0, 1, 2
 
 
+def set_gemm_precision(mode):
+    """"tf32" (default: one TF32 product, fp32 accumulate) or "tf32x3" (error-compensated, fp32-level)."""
+    check(fn["uwr_set_gemm_precision"]({"tf32": 1, "tf32x3": 3}[mode]), "uwr_set_gemm_precision")
+
+
+def launch_count():
+    return int(fn["uwr_launch_count"]())
+
+
 def _stream():
     return torch.cuda.current_stream().cuda_stream
+
+
+class KernelProfile:
+    """Per-call CUDA-event timing of the C-ABI launches (used by bench.py for the roofline table;
+    never active inside a timed region).  Records (family, shape key, algorithmic bytes, flops)."""
+
+    def __init__(self):
+        self.records = []
+
+    def __enter__(self):
+        global _PROF
+        _PROF = self
+        return self
+
+    def __exit__(self, *exc):
+        global _PROF
+        _PROF = None
+        torch.cuda.synchronize()
+
+    def table(self):
+        agg = {}
+        for name, key, nbytes, flops, e0, e1 in self.records:
+            ms = e0.elapsed_time(e1)
+            a = agg.setdefault((name, key), [0, 0.0, 0.0, 0.0])
+            a[0] += 1
+            a[1] += ms
+            a[2] += nbytes
+            a[3] += flops
+        rows = [dict(kernel=k[0], shape=k[1], launches=v[0], ms_total=v[1], ms_avg=v[1] / v[0],
+                     bytes_per_launch=v[2] / v[0], flops_per_launch=v[3] / v[0],
+                     gbs=(v[2] / v[1] / 1e6) if v[1] > 0 else 0.0, tflops=(v[3] / v[1] / 1e9) if v[1] > 0 else 0.0)
+                for k, v in agg.items()]
+        rows.sort(key=lambda r: -r["ms_total"])
+        return rows
+
+
+_PROF = None
+
+
+def _run(name, key, nbytes, flops, *args):
+    """Launch one C-ABI entry on the current stream (optionally bracketed by CUDA events)."""
+    if _PROF is None:
+        check(fn[name](*args, _stream()), name)
+        return
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    check(fn[name](*args, _stream()), name)
+    e1.record()
+    _PROF.records.append((name, key, nbytes, flops, e0, e1))
 
 
 def _ptr(t):
@@ -57,7 +115,9 @@ def gemm(A, B, C_out, M, N, K, *, lda, ldb, ldc, a_km=False, b_nk=True, B2=None,
         if nbytes:
             ws = _ws(nbytes, A)
             d.workspace, d.workspace_bytes = ws.data_ptr(), nbytes
-    check(fn["uwr_gemm_tf32"](C.byref(d), _stream()), "uwr_gemm_tf32")
+    nbytes = 4 * (M * K + K * N + M * N + (M * N if R is not None else 0))
+    lay = ("TN" if a_km else ("NT" if b_nk else "NN"))
+    _run("uwr_gemm_tf32", f"{lay} M{M} N{N} K{K} epi{epilogue}", nbytes, 2.0 * M * N * K, C.byref(d))
     return C_out
 
 
@@ -106,8 +166,8 @@ def layernorm_fwd(x2d, gamma, beta, eps=1e-5, save_stats=True):
     y = torch.empty_like(x2d)
     mean = _empty((rows,), x2d) if save_stats else None
     rstd = _empty((rows,), x2d) if save_stats else None
-    check(fn["uwr_layernorm_fwd"](_ptr(x2d), _ptr(gamma), _ptr(beta), _ptr(y), _ptr(mean), _ptr(rstd),
-                                  rows, Cc, eps, _stream()), "uwr_layernorm_fwd")
+    _run("uwr_layernorm_fwd", f"rows{rows} C{Cc}", 8 * rows * Cc, 8.0 * rows * Cc,
+         _ptr(x2d), _ptr(gamma), _ptr(beta), _ptr(y), _ptr(mean), _ptr(rstd), rows, Cc, eps)
     return y, mean, rstd
 
 
@@ -117,9 +177,9 @@ def layernorm_bwd(dy2d, x2d, gamma, mean, rstd, dres=None):
     dgamma = torch.empty_like(gamma)
     dbeta = torch.empty_like(gamma)
     ws = _ws(fn["uwr_layernorm_bwd_workspace_bytes"](rows, Cc), x2d)
-    check(fn["uwr_layernorm_bwd"](_ptr(dy2d), _ptr(x2d), _ptr(gamma), _ptr(mean), _ptr(rstd), _ptr(dres),
-                                  _ptr(dx), _ptr(dgamma), _ptr(dbeta), _ptr(ws), rows, Cc, _stream()),
-          "uwr_layernorm_bwd")
+    _run("uwr_layernorm_bwd", f"rows{rows} C{Cc}", (12 + (4 if dres is not None else 0)) * rows * Cc,
+         16.0 * rows * Cc, _ptr(dy2d), _ptr(x2d), _ptr(gamma), _ptr(mean), _ptr(rstd), _ptr(dres), _ptr(dx),
+         _ptr(dgamma), _ptr(dbeta), _ptr(ws), rows, Cc)
     return dx, dgamma, dbeta
 
 
@@ -137,7 +197,9 @@ def window_attn_fwd(q_buf, q_off, kv_buf, k_off, v_off, table, w_param, B, H, W,
     """q_buf/kv_buf: 2-D token matrices (B*H*W, ld). Returns O (B*H*W, heads*head_dim)."""
     d = _attn_desc(q_buf, q_off, kv_buf, k_off, v_off, table, w_param, B, H, W, heads, head_dim, shift, scale)
     out = _empty((B * H * W, heads * head_dim), q_buf)
-    check(fn["uwr_window_attn_fwd"](C.byref(d), _ptr(out), out.stride(0), _stream()), "uwr_window_attn_fwd")
+    tiles = B * (H // 8) * (W // 8) * heads
+    _run("uwr_window_attn_fwd", f"tiles{tiles} hd{head_dim} shift{shift}", tiles * 4 * 64 * head_dim * 4,
+         tiles * 4.0 * 64 * 64 * head_dim, C.byref(d), _ptr(out), out.stride(0))
     return out
 
 
@@ -151,8 +213,10 @@ def window_attn_bwd(dout, q_buf, q_off, kv_buf, k_off, v_off, table, w_param, B,
     dtable = torch.empty_like(table)
     dw = _empty((2,), q_buf)
     ws = _ws(fn["uwr_window_attn_bwd_workspace_bytes"](C.byref(d)), q_buf)
-    check(fn["uwr_window_attn_bwd"](C.byref(d), _ptr(dout), dout.stride(0), _ptr(dq_buf), _ptr(dkv_buf),
-                                    _ptr(dtable), _ptr(dw), _ptr(ws), _stream()), "uwr_window_attn_bwd")
+    tiles = B * (H // 8) * (W // 8) * heads
+    _run("uwr_window_attn_bwd", f"tiles{tiles} hd{head_dim} shift{shift}", tiles * 7 * 64 * head_dim * 4,
+         tiles * 10.0 * 64 * 64 * head_dim, C.byref(d), _ptr(dout), dout.stride(0), _ptr(dq_buf), _ptr(dkv_buf),
+         _ptr(dtable), _ptr(dw), _ptr(ws))
     return dq_buf, dkv_buf, dtable, dw
 
 
@@ -160,8 +224,9 @@ def window_attn_bwd(dout, q_buf, q_off, kv_buf, k_off, v_off, table, w_param, B,
 def dwconv_gelu_fwd(u2d, weight, bias, B, H, W, Ch, mode=0, save_v=True):
     v = _empty((B * H * W, Ch), u2d) if save_v else None
     h2 = _empty((B * H * W, Ch), u2d)
-    check(fn["uwr_dwconv_gelu_fwd"](_ptr(u2d), u2d.stride(0), _ptr(weight), _ptr(bias), _ptr(v), _ptr(h2),
-                                    B, H, W, Ch, mode, _stream()), "uwr_dwconv_gelu_fwd")
+    n = B * H * W * Ch
+    _run("uwr_dwconv_gelu_fwd", f"B{B} H{H} Ch{Ch} mode{mode}", 4 * n * ((2 if mode else 1) + (2 if save_v else 1)),
+         18.0 * n, _ptr(u2d), u2d.stride(0), _ptr(weight), _ptr(bias), _ptr(v), _ptr(h2), B, H, W, Ch, mode)
     return v, h2
 
 
@@ -170,9 +235,10 @@ def dwconv_gelu_bwd(dh2, u2d, v, weight, B, H, W, Ch, mode=0):
     dweight = torch.empty_like(weight)
     dbias = _empty((Ch,), u2d)
     ws = _ws(fn["uwr_dwconv_gelu_bwd_workspace_bytes"](B, H, W, Ch), u2d)
-    check(fn["uwr_dwconv_gelu_bwd"](_ptr(dh2), _ptr(u2d), u2d.stride(0), _ptr(v), _ptr(weight), _ptr(du),
-                                    _ptr(dweight), _ptr(dbias), _ptr(ws), B, H, W, Ch, mode, _stream()),
-          "uwr_dwconv_gelu_bwd")
+    n = B * H * W * Ch
+    _run("uwr_dwconv_gelu_bwd", f"B{B} H{H} Ch{Ch} mode{mode}", 4 * n * (4 + (2 if mode else 0)), 36.0 * n,
+         _ptr(dh2), _ptr(u2d), u2d.stride(0), _ptr(v), _ptr(weight), _ptr(du), _ptr(dweight), _ptr(dbias), _ptr(ws),
+         B, H, W, Ch, mode)
     return du, dweight, dbias
 
 
@@ -181,8 +247,8 @@ def input_proj_fwd(img, weight, bias, slope=0.01):
     B, Cin, H, W = img.shape
     Cout = weight.shape[0]
     tokens = _empty((B, H * W, Cout), img)
-    check(fn["uwr_input_proj_fwd"](_ptr(img), _ptr(weight), _ptr(bias), _ptr(tokens), B, H, W, Cin, Cout,
-                                   slope, _stream()), "uwr_input_proj_fwd")
+    _run("uwr_input_proj_fwd", "", 0, 0.0, _ptr(img), _ptr(weight), _ptr(bias), _ptr(tokens), B, H, W, Cin, Cout,
+                                   slope)
     return tokens
 
 
@@ -192,17 +258,16 @@ def input_proj_bwd(dtokens, tokens, img, weight, slope=0.01):
     dweight = torch.empty_like(weight)
     dbias = _empty((Cout,), img)
     ws = _ws(fn["uwr_input_proj_bwd_workspace_bytes"](B, H, W, Cin, Cout), img)
-    check(fn["uwr_input_proj_bwd"](_ptr(dtokens), _ptr(tokens), _ptr(img), _ptr(dweight), _ptr(dbias), _ptr(ws),
-                                   B, H, W, Cin, Cout, slope, _stream()), "uwr_input_proj_bwd")
+    _run("uwr_input_proj_bwd", "", 0, 0.0, _ptr(dtokens), _ptr(tokens), _ptr(img), _ptr(dweight), _ptr(dbias), _ptr(ws),
+                                   B, H, W, Cin, Cout, slope)
     return dweight, dbias
 
 
 def output_proj_fwd(tokens, weight, bias, residual_img, B, H, W):
     Cin = weight.shape[1]
     out = _empty((B, 3, H, W), tokens)
-    check(fn["uwr_output_proj_fwd"](_ptr(tokens), tokens.stride(-2), _ptr(weight), _ptr(bias),
-                                    _ptr(residual_img), _ptr(out), B, H, W, Cin, _stream()),
-          "uwr_output_proj_fwd")
+    _run("uwr_output_proj_fwd", "", 0, 0.0, _ptr(tokens), tokens.stride(-2), _ptr(weight), _ptr(bias),
+                                    _ptr(residual_img), _ptr(out), B, H, W, Cin)
     return out
 
 
@@ -212,48 +277,44 @@ def output_proj_bwd(dout_img, tokens, weight, B, H, W):
     dweight = torch.empty_like(weight)
     dbias = _empty((3,), tokens)
     ws = _ws(fn["uwr_output_proj_bwd_workspace_bytes"](B, H, W, Cin), tokens)
-    check(fn["uwr_output_proj_bwd"](_ptr(dout_img), _ptr(tokens), tokens.stride(-2), _ptr(weight), _ptr(dtokens),
-                                    _ptr(dweight), _ptr(dbias), _ptr(ws), B, H, W, Cin, _stream()),
-          "uwr_output_proj_bwd")
+    _run("uwr_output_proj_bwd", "", 0, 0.0, _ptr(dout_img), _ptr(tokens), tokens.stride(-2), _ptr(weight), _ptr(dtokens),
+                                    _ptr(dweight), _ptr(dbias), _ptr(ws), B, H, W, Cin)
     return dtokens, dweight, dbias
 
 
 def im2col_4x4s2(tokens2d, B, H, W, Cc):
     col = _empty((B * (H // 2) * (W // 2), 16 * Cc), tokens2d)
-    check(fn["uwr_im2col_4x4s2"](_ptr(tokens2d), tokens2d.stride(0), _ptr(col), B, H, W, Cc, _stream()),
-          "uwr_im2col_4x4s2")
+    _run("uwr_im2col_4x4s2", "", 0, 0.0, _ptr(tokens2d), tokens2d.stride(0), _ptr(col), B, H, W, Cc)
     return col
 
 
 def col2im_4x4s2(dcol, B, H, W, Cc):
     dx = _empty((B * H * W, Cc), dcol)
-    check(fn["uwr_col2im_4x4s2"](_ptr(dcol), _ptr(dx), B, H, W, Cc, _stream()), "uwr_col2im_4x4s2")
+    _run("uwr_col2im_4x4s2", "", 0, 0.0, _ptr(dcol), _ptr(dx), B, H, W, Cc)
     return dx
 
 
 def pixel_scatter_2x2(g, bias, out2d, B, H, W, Cout):
-    check(fn["uwr_pixel_scatter_2x2"](_ptr(g), _ptr(bias), _ptr(out2d), out2d.stride(0), B, H, W, Cout,
-                                      _stream()), "uwr_pixel_scatter_2x2")
+    _run("uwr_pixel_scatter_2x2", "", 0, 0.0, _ptr(g), _ptr(bias), _ptr(out2d), out2d.stride(0), B, H, W, Cout)
 
 
 def pixel_gather_2x2(dout2d, B, H, W, Cout):
     dg = _empty((B * H * W, 4 * Cout), dout2d)
-    check(fn["uwr_pixel_gather_2x2"](_ptr(dout2d), dout2d.stride(0), _ptr(dg), B, H, W, Cout, _stream()),
-          "uwr_pixel_gather_2x2")
+    _run("uwr_pixel_gather_2x2", "", 0, 0.0, _ptr(dout2d), dout2d.stride(0), _ptr(dg), B, H, W, Cout)
     return dg
 
 
 def copy2d(src2d, dst2d, cols, accumulate=False):
     rows = src2d.shape[0]
-    check(fn["uwr_copy2d"](_ptr(src2d), src2d.stride(0), _ptr(dst2d), dst2d.stride(0), rows, cols,
-                           int(accumulate), _stream()), "uwr_copy2d")
+    _run("uwr_copy2d", "", 0, 0.0, _ptr(src2d), src2d.stride(0), _ptr(dst2d), dst2d.stride(0), rows, cols,
+                           int(accumulate))
 
 
 def colsum(x2d, cols):
     rows = x2d.shape[0]
     out = _empty((cols,), x2d)
     ws = _ws(1024 * cols * 4, x2d)
-    check(fn["uwr_colsum"](_ptr(x2d), x2d.stride(0), _ptr(out), _ptr(ws), rows, cols, _stream()), "uwr_colsum")
+    _run("uwr_colsum", "", 0, 0.0, _ptr(x2d), x2d.stride(0), _ptr(out), _ptr(ws), rows, cols)
     return out
 
 
@@ -266,6 +327,6 @@ def pixel_loss(pred, truth, kind, batch_divisor=None, want_grad=True):
     out = _empty((1,), pred)
     grad = torch.empty_like(pred) if want_grad else None
     ws = _ws(4 * 1024 * 4, pred)
-    check(fn["uwr_pixel_loss"](_ptr(pred), _ptr(truth), _ptr(out), _ptr(grad), _ptr(ws), LOSS_KINDS[kind],
-                               B, Cc, H, W, batch_divisor or B, _stream()), "uwr_pixel_loss")
+    _run("uwr_pixel_loss", "", 0, 0.0, _ptr(pred), _ptr(truth), _ptr(out), _ptr(grad), _ptr(ws), LOSS_KINDS[kind],
+                               B, Cc, H, W, batch_divisor or B)
     return out, grad

@@ -2,41 +2,34 @@
 
 Behaviour kept verbatim: prints "modelCreated", KeyError for unknown names, `use_dwt` dropped for
 every arch reachable from argv, constructor defaults are the contract.
+Architectures are imported lazily (module, class) so that `import uwr` stays light.
 """
-from .ast import AST
+import importlib
 
-_FACTORY = {}
-
-
-def _register_defaults():
-    from . import spectral, newbig  # noqa: F401  (populate lazily; heavy imports)
-
-
-def _factory():
-    if not _FACTORY:
-        from .spectral import SpectralTransformer
-        from .newbig import NewModel, NewBigModel, NewBigFRFNModel
-        _FACTORY.update({
-            "SpectralTransformer": SpectralTransformer,
-            "NewModel": NewModel,
-            "NewBigModel": NewBigModel,
-            "NewBigFRFNModel": NewBigFRFNModel,
-            "AST": AST,
-        })
-    return _FACTORY
+_FACTORY = {
+    "SpectralTransformer": ("uwr.spectral", "SpectralTransformer"),
+    "NewModel": ("uwr.newbig", "MyModel"),
+    "NewBigModel": ("uwr.newbig", "MyBigModel"),
+    "NewBigFRFNModel": ("uwr.newbig", "MyBigFRFNModel"),
+    "AST": ("uwr.ast", "AST"),
+}
 
 
 def get_names():
-    return list(_factory().keys())
+    return list(_FACTORY.keys())
+
+
+def _resolve(name):
+    mod, cls = _FACTORY[name]
+    return getattr(importlib.import_module(mod), cls)
 
 
 def init_model(name, *args, **kwargs):
     print("modelCreated")
-    fac = _factory()
-    if name not in fac:
+    if name not in _FACTORY:
         raise KeyError(f"Unknown model: {name}")
     if "use_dwt" in kwargs:
         # the reference's `name is "NewModel"` identity test is False for argv strings, so the flag
         # is dropped for every architecture (src/Models/__init__.py:25-29, SURVEY.md §0)
         kwargs.pop("use_dwt")
-    return fac[name](*args, **kwargs)
+    return _resolve(name)(*args, **kwargs)

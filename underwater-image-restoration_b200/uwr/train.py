@@ -1,0 +1,94 @@
+"""Training step of the reference loop (src/ModelTrainer.py:78-88) on the uwr kernels:
+
+    zero_grad -> model(raw) -> LossFunction.getloss -> backward -> [grad all-reduce] ->
+    clip_grad_norm_(1.0) + Adam   (fused, no host sync; the reference's per-step .item()/print
+    calls at ModelTrainer.py:90-126 are left to the caller)
+
+Gradients live in a few flat buckets (views handed to autograd as .grad) so that
+  * the optimizer's pointer tables are built once,
+  * data parallelism is one NCCL all-reduce per bucket, launched from post-accumulate hooks as
+    soon as a bucket is complete, i.e. overlapped with the rest of backward.
+The loss divisor uses the GLOBAL batch so N-rank training reproduces the single-GPU global-batch
+gradients (losses.py:57 divides by the local B).
+"""
+import torch
+import torch.distributed as dist
+
+from .losses import LossFunction
+from .optim import FusedClipAdam
+
+
+class GradBuckets:
+    def __init__(self, params, bucket_bytes=32 << 20, group=None, world_size=1):
+        self.params = [p for p in params if p.requires_grad]
+        self.group, self.world = group, world_size
+        order = list(reversed(self.params))  # roughly the order gradients are produced in backward
+        self.buckets, cur, cur_n = [], [], 0
+        for p in order:
+            cur.append(p)
+            cur_n += p.numel()
+            if cur_n * 4 >= bucket_bytes:
+                self.buckets.append(cur)
+                cur, cur_n = [], 0
+        if cur:
+            self.buckets.append(cur)
+        self.flat, self._bucket_of, self._pending, self._handles = [], {}, [], []
+        for bi, ps in enumerate(self.buckets):
+            n = sum(-(-p.numel() // 4) * 4 for p in ps)  # 16-byte aligned slots
+            flat = torch.zeros(n, device=ps[0].device, dtype=torch.float32)
+            off = 0
+            for p in ps:
+                p.grad = flat[off:off + p.numel()].view_as(p)
+                off += -(-p.numel() // 4) * 4
+                self._bucket_of[id(p)] = bi
+            self.flat.append(flat)
+        self._count = [0] * len(self.buckets)
+        if self.world > 1:
+            for p in self.params:
+                p.register_post_accumulate_grad_hook(self._hook)
+
+    def _hook(self, p):
+        bi = self._bucket_of[id(p)]
+        self._count[bi] += 1
+        if self._count[bi] == len(self.buckets[bi]):
+            self._handles.append(dist.all_reduce(self.flat[bi], op=dist.ReduceOp.SUM, group=self.group,
+                                                 async_op=True))
+
+    def zero(self):
+        for f in self.flat:
+            f.zero_()
+        self._count = [0] * len(self.buckets)
+
+    def finish(self):
+        """Wait for the in-flight all-reduces; buckets whose parameters never received a gradient
+        (dead parameters) are reduced here so every rank stays in lock-step."""
+        if self.world > 1:
+            for bi, c in enumerate(self._count):
+                if c != len(self.buckets[bi]):
+                    self._handles.append(dist.all_reduce(self.flat[bi], op=dist.ReduceOp.SUM, group=self.group,
+                                                         async_op=True))
+            for h in self._handles:
+                h.wait()
+            self._handles = []
+
+
+class TrainStep:
+    def __init__(self, model, loss_name="L1", lr=1e-3, optim="adam", world_size=1, group=None,
+                 local_batch=None, bucket_bytes=32 << 20):
+        self.model = model
+        self.world = world_size
+        self.lossf = LossFunction(loss_name, "cuda", batch_divisor=(local_batch * world_size) if local_batch else None)
+        self.buckets = GradBuckets(model.parameters(), bucket_bytes, group, world_size)
+        self.opt = FusedClipAdam(model.parameters(), lr=lr, weight_decay=0.01 if optim == "adamw" else 0.0,
+                                 decoupled=(optim == "adamw"), max_norm=1.0, grad_prescale=1.0 / world_size)
+
+    def __call__(self, raw, ref):
+        self.buckets.zero()
+        out = self.model(raw)
+        loss = self.lossf.getloss(out, ref)
+        if isinstance(loss, tuple):
+            loss = loss[0]
+        loss.backward()
+        self.buckets.finish()
+        norm = self.opt.step()
+        return loss.detach(), norm
