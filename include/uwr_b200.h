@@ -130,12 +130,16 @@ int uwr_window_attn_bwd(const uwr_attn_desc* d, const float* dout, long long ld_
 int uwr_dwconv_gelu_fwd(const float* u, long long ld_u, const float* weight /*(Ch,1,3,3)*/,
                         const float* bias, float* v, float* h2, int B, int H, int W, int Ch,
                         int mode, uwr_stream_t stream);
+/* dv = dh2 * gelu'(v) [* gelu(u2)] for callers that do not fuse it into the producing GEMM
+ * (UWR_EPI_MUL_DGELU); mode 1 (FRFN) also writes du[:, Ch:2Ch] = dh2 * gelu(v) * gelu'(u2). */
+int uwr_gelu_gate_bwd(const float* dh2, const float* u, long long ld_u, const float* v, float* dv,
+                      float* du, long long rows, int Ch, int mode, uwr_stream_t stream);
 size_t uwr_dwconv_gelu_bwd_workspace_bytes(int B, int H, int W, int Ch);
-/* dh2 -> du (ld_u wide, both halves in mode 1), dweight (Ch,1,3,3), dbias (Ch). */
-int uwr_dwconv_gelu_bwd(const float* dh2, const float* u, long long ld_u, const float* v,
-                        const float* weight, float* du, float* dweight, float* dbias,
-                        float* workspace, int B, int H, int W, int Ch, int mode,
-                        uwr_stream_t stream);
+/* dv (gradient w.r.t. the conv output v) -> du[:, :Ch] (row stride ld_u), dweight (Ch,1,3,3),
+ * dbias (Ch); only dv needs a halo. */
+int uwr_dwconv_gelu_bwd(const float* dv, const float* u, long long ld_u, const float* weight,
+                        float* du, float* dweight, float* dbias, float* workspace, int B, int H,
+                        int W, int Ch, uwr_stream_t stream);
 
 /* ---- convolutions at the model boundary and between scales ---------------------------------
  * InputProj  (AST.py:447-466): Conv3x3(3->Cout)+LeakyReLU(slope) NCHW image -> tokens.

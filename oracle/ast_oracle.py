@@ -12,10 +12,10 @@ import torch.nn.functional as F
 WIN = 8
 
 
-def shift_mask(H, W, shift, dtype=torch.float32):
+def shift_mask(H, W, shift, dtype=torch.float32, device=None):
     """(nW, 64, 64) additive mask of {0, -100}: AST.py:568-588 (region ids on the rolled grid)."""
-    ys = torch.arange(H)
-    xs = torch.arange(W)
+    ys = torch.arange(H, device=device)
+    xs = torch.arange(W, device=device)
     ry = (ys >= H - WIN).long() + (ys >= H - shift).long()
     rx = (xs >= W - WIN).long() + (xs >= W - shift).long()
     reg = (ry[:, None] * 3 + rx[None, :]).to(dtype)                     # (H, W)
@@ -98,7 +98,7 @@ def transformer_block(sd, pre, x, heads, shift, att, token_mlp, dp_attn=None, dp
         mask = None
         if shift > 0:
             y = torch.roll(y, shifts=(-shift, -shift), dims=(1, 2))
-            mask = shift_mask(H, W, shift, x.dtype)
+            mask = shift_mask(H, W, shift, x.dtype, x.device)
         yw = window_attention(sd, pre + "attn.", to_windows(y, B, H, W, C), heads, mask,
                               sparse=(pre + "attn.w") in sd)
         y = from_windows(yw, B, H, W, C)

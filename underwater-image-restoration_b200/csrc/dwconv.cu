@@ -3,9 +3,14 @@
 //
 //   h1 = gelu(u[..., :Ch]) ; v = dwconv3x3(h1) + bias ; h2 = gelu(v) [* gelu(u[..., Ch:2Ch])]
 //
-// CTA = 16x16 pixels x 32 channels, lane <-> channel (128 B coalesced per pixel), halo tile staged
-// once in shared memory after the GELU so erf is evaluated once per element.  HBM-bound:
-// fwd reads u (x1.27 halo, mostly L2 hits) and writes v,h2; bwd reads dh2,v,u and writes du.
+// CTA = 16x16 pixels x 32 channels, lane <-> channel (128 B coalesced per pixel).  The halo tile is
+// staged once in shared memory (after the GELU in the forward, so erf is evaluated once per
+// element); global loads are issued in batches of 8 per warp to keep enough bytes in flight.
+// Backward consumes dv = dL/dv (produced by the linear2 data-gradient GEMM epilogue,
+// UWR_EPI_MUL_DGELU, or by uwr_gelu_gate_bwd) so only ONE tensor needs a halo:
+//   dh1[p] = sum_k dv[p+1-k] w[k] ; du = dh1 * gelu'(u) ; dw[k] = sum_p gelu(u[p]) dv[p+1-k]
+// HBM-bound: fwd reads u (x1.27 halo, mostly L2 hits) and writes v,h2; bwd reads dv (x1.27), u and
+// writes du.
 #include "uwr_common.cuh"
 #include "../../include/uwr_b200.h"
 
@@ -15,6 +20,8 @@ constexpr int TS = 16;          // tile side
 constexpr int HS = TS + 2;      // halo side
 constexpr int CG = 32;          // channels per CTA
 constexpr int DW_THREADS = 256; // 8 warps, 2 tile rows each
+constexpr int NWARP = DW_THREADS / 32;
+constexpr int BATCH = 8;        // global loads in flight per warp while staging
 
 __global__ void __launch_bounds__(DW_THREADS) dwconv_fwd_kernel(const float* __restrict__ u, long long ld_u,
                                                                 const float* __restrict__ weight,
@@ -29,11 +36,21 @@ __global__ void __launch_bounds__(DW_THREADS) dwconv_fwd_kernel(const float* __r
     const int ty0 = (blockIdx.x / tiles_x) * TS, tx0 = (blockIdx.x % tiles_x) * TS;
     const float* ub = u + (long long)b * H * W * ld_u;
 
-    for (int pix = warp; pix < HS * HS; pix += DW_THREADS / 32) {
-        const int y = ty0 + pix / HS - 1, x = tx0 + pix % HS - 1;
-        float val = 0.f;
-        if (cok && y >= 0 && y < H && x >= 0 && x < W) val = gelu_f(ub[((long long)y * W + x) * ld_u + c]);
-        h1s[pix][lane] = val;
+    for (int p0 = warp; p0 < HS * HS; p0 += NWARP * BATCH) {
+        float val[BATCH];
+#pragma unroll
+        for (int i = 0; i < BATCH; ++i) {
+            const int pix = p0 + i * NWARP;
+            const int y = ty0 + pix / HS - 1, x = tx0 + pix % HS - 1;
+            val[i] = 0.f;
+            if (pix < HS * HS && cok && y >= 0 && y < H && x >= 0 && x < W)
+                val[i] = __ldg(ub + ((long long)y * W + x) * ld_u + c);
+        }
+#pragma unroll
+        for (int i = 0; i < BATCH; ++i) {
+            const int pix = p0 + i * NWARP;
+            if (pix < HS * HS) h1s[pix][lane] = gelu_f(val[i]);  // gelu(0) = 0 keeps the zero padding
+        }
     }
     float wgt[9];
 #pragma unroll
@@ -47,6 +64,12 @@ __global__ void __launch_bounds__(DW_THREADS) dwconv_fwd_kernel(const float* __r
         const int ly = warp * 2 + rr;  // local row 0..15
         const int y = ty0 + ly;
         if (y >= H) break;
+        const long long tok0 = ((long long)b * H + y) * W + tx0;
+        float gate[TS];
+        if (mode == 1) {
+#pragma unroll
+            for (int lx = 0; lx < TS; ++lx) gate[lx] = (tx0 + lx < W) ? __ldg(u + (tok0 + lx) * ld_u + Ch + c) : 0.f;
+        }
         float win[3][3];
 #pragma unroll
         for (int ky = 0; ky < 3; ++ky) {
@@ -61,34 +84,50 @@ __global__ void __launch_bounds__(DW_THREADS) dwconv_fwd_kernel(const float* __r
                 win[ky][1] = win[ky][2];
                 win[ky][2] = h1s[(ly + ky) * HS + lx + 2][lane];
             }
-            const int x = tx0 + lx;
-            if (x < W) {
+            if (tx0 + lx < W) {
                 float acc = bv;
 #pragma unroll
                 for (int ky = 0; ky < 3; ++ky)
 #pragma unroll
                     for (int kx = 0; kx < 3; ++kx) acc = fmaf(win[ky][kx], wgt[ky * 3 + kx], acc);
-                const long long tok = ((long long)b * H + y) * W + x;
-                if (v) v[tok * Ch + c] = acc;
+                if (v) v[(tok0 + lx) * Ch + c] = acc;
                 float o = gelu_f(acc);
-                if (mode == 1) o *= gelu_f(u[tok * ld_u + Ch + c]);
-                h2[tok * Ch + c] = o;
+                if (mode == 1) o *= gelu_f(gate[lx]);
+                h2[(tok0 + lx) * Ch + c] = o;
             }
         }
     }
 }
 
+// dv = dh2 * gelu'(v) [* gelu(u2)] ; FRFN additionally du[:, Ch:] = dh2 * gelu(v) * gelu'(u2)
+__global__ void __launch_bounds__(256) gelu_gate_bwd_kernel(const float* __restrict__ dh2,
+                                                            const float* __restrict__ u, long long ld_u,
+                                                            const float* __restrict__ v, float* __restrict__ dv,
+                                                            float* __restrict__ du, long long rows, int Ch, int mode) {
+    const long long total = rows * Ch;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total;
+         i += (long long)gridDim.x * blockDim.x) {
+        const long long r = i / Ch;
+        const int c = (int)(i % Ch);
+        const float d = dh2[i], vv = v[i];
+        float g = d * gelu_grad_f(vv);
+        if (mode == 1) {
+            const float u2 = u[r * ld_u + Ch + c];
+            g *= gelu_f(u2);
+            du[r * ld_u + Ch + c] = d * gelu_f(vv) * gelu_grad_f(u2);
+        }
+        dv[i] = g;
+    }
+}
+
 // persistent over tiles: grid = (P, Ch/32); each CTA accumulates dweight/dbias partials in registers
-__global__ void __launch_bounds__(DW_THREADS) dwconv_bwd_kernel(const float* __restrict__ dh2,
+__global__ void __launch_bounds__(DW_THREADS) dwconv_bwd_kernel(const float* __restrict__ dv,
                                                                 const float* __restrict__ u, long long ld_u,
-                                                                const float* __restrict__ v,
                                                                 const float* __restrict__ weight,
                                                                 float* __restrict__ du, float* __restrict__ partials,
-                                                                int B, int H, int W, int Ch, int mode, int tiles_x,
+                                                                int B, int H, int W, int Ch, int tiles_x,
                                                                 int tiles_per_img) {
-    extern __shared__ __align__(16) float smem[];
-    float(*dvs)[CG] = reinterpret_cast<float(*)[CG]>(smem);
-    float(*h1s)[CG] = reinterpret_cast<float(*)[CG]>(smem + HS * HS * CG);
+    __shared__ float dvs[HS * HS][CG];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int c = blockIdx.y * CG + lane;
     const bool cok = c < Ch;
@@ -107,19 +146,21 @@ __global__ void __launch_bounds__(DW_THREADS) dwconv_bwd_kernel(const float* __r
         const int ty0 = (tl / tiles_x) * TS, tx0 = (tl % tiles_x) * TS;
         const long long base = (long long)b * H * W;
         __syncthreads();
-        for (int pix = warp; pix < HS * HS; pix += DW_THREADS / 32) {
-            const int y = ty0 + pix / HS - 1, x = tx0 + pix % HS - 1;
-            float dvv = 0.f, h1 = 0.f;
-            if (cok && y >= 0 && y < H && x >= 0 && x < W) {
-                const long long tok = base + (long long)y * W + x;
-                const float vv = v[tok * Ch + c];
-                float d = dh2[tok * Ch + c] * gelu_grad_f(vv);
-                if (mode == 1) d *= gelu_f(u[tok * ld_u + Ch + c]);
-                dvv = d;
-                h1 = gelu_f(u[tok * ld_u + c]);
+        for (int p0 = warp; p0 < HS * HS; p0 += NWARP * BATCH) {
+            float val[BATCH];
+#pragma unroll
+            for (int i = 0; i < BATCH; ++i) {
+                const int pix = p0 + i * NWARP;
+                const int y = ty0 + pix / HS - 1, x = tx0 + pix % HS - 1;
+                val[i] = 0.f;
+                if (pix < HS * HS && cok && y >= 0 && y < H && x >= 0 && x < W)
+                    val[i] = __ldg(dv + (base + (long long)y * W + x) * Ch + c);
             }
-            dvs[pix][lane] = dvv;
-            h1s[pix][lane] = h1;
+#pragma unroll
+            for (int i = 0; i < BATCH; ++i) {
+                const int pix = p0 + i * NWARP;
+                if (pix < HS * HS) dvs[pix][lane] = val[i];
+            }
         }
         __syncthreads();
         if (cok) {
@@ -128,43 +169,59 @@ __global__ void __launch_bounds__(DW_THREADS) dwconv_bwd_kernel(const float* __r
                 const int ly = warp * 2 + rr;
                 const int y = ty0 + ly;
                 if (y >= H) break;
+                const long long tok0 = base + (long long)y * W + tx0;
+                float uc[TS];
+#pragma unroll
+                for (int lx = 0; lx < TS; ++lx) uc[lx] = (tx0 + lx < W) ? __ldg(u + (tok0 + lx) * ld_u + c) : 0.f;
+                // window of dv around the output pixel: win[a][b] = dv[y-1+a][x-1+b]
+                float win[3][3];
+#pragma unroll
+                for (int a = 0; a < 3; ++a) {
+                    win[a][1] = dvs[(ly + a) * HS + 0][lane];
+                    win[a][2] = dvs[(ly + a) * HS + 1][lane];
+                }
+#pragma unroll
                 for (int lx = 0; lx < TS; ++lx) {
-                    const int x = tx0 + lx;
-                    if (x >= W) break;
-                    // dh1[y,x] = sum_k dv[y+1-ky, x+1-kx] w[ky,kx]; local halo index of (y,x) is (ly+1, lx+1)
-                    float dh1 = 0.f;
-                    const float dvc = dvs[(ly + 1) * HS + lx + 1][lane];
 #pragma unroll
-                    for (int ky = 0; ky < 3; ++ky)
+                    for (int a = 0; a < 3; ++a) {
+                        win[a][0] = win[a][1];
+                        win[a][1] = win[a][2];
+                        win[a][2] = dvs[(ly + a) * HS + lx + 2][lane];
+                    }
+                    if (tx0 + lx < W) {
+                        const float x = uc[lx];
+                        const float cdf = 0.5f * (1.0f + erff(x * 0.70710678118654752440f));
+                        const float pdf = 0.39894228040143267794f * __expf(-0.5f * x * x);
+                        const float h1 = x * cdf;
+                        float dh1 = 0.f;
+                        // v[q] = sum_k h1[q + k - 1] w[k]  =>  h1[p] meets dv[p + 1 - k] with weight w[k]
 #pragma unroll
-                        for (int kx = 0; kx < 3; ++kx) {
-                            dh1 = fmaf(dvs[(ly + 2 - ky) * HS + (lx + 2 - kx)][lane], wgt[ky * 3 + kx], dh1);
-                            dwt[ky * 3 + kx] = fmaf(dvc, h1s[(ly + ky) * HS + lx + kx][lane], dwt[ky * 3 + kx]);
-                        }
-                    dbs += dvc;
-                    const long long tok = base + (long long)y * W + x;
-                    const float uc = u[tok * ld_u + c];
-                    du[tok * ld_u + c] = dh1 * gelu_grad_f(uc);
-                    if (mode == 1) {
-                        const float u2 = u[tok * ld_u + Ch + c];
-                        du[tok * ld_u + Ch + c] = dh2[tok * Ch + c] * gelu_f(v[tok * Ch + c]) * gelu_grad_f(u2);
+                        for (int ky = 0; ky < 3; ++ky)
+#pragma unroll
+                            for (int kx = 0; kx < 3; ++kx) {
+                                const float d = win[2 - ky][2 - kx];
+                                dh1 = fmaf(d, wgt[ky * 3 + kx], dh1);
+                                dwt[ky * 3 + kx] = fmaf(h1, d, dwt[ky * 3 + kx]);
+                            }
+                        dbs += win[1][1];
+                        du[(tok0 + lx) * ld_u + c] = dh1 * (cdf + x * pdf);
                     }
                 }
             }
         }
     }
-    // reduce the 10 per-channel partial sums across the 8 warps
+    // reduce the 10 per-channel partial sums across the 8 warps (the tile buffer is reused)
     __syncthreads();
-    float* red = smem;  // [8][10][32]
+    float(*red)[10][CG] = reinterpret_cast<float(*)[10][CG]>(&dvs[0][0]);
 #pragma unroll
-    for (int k = 0; k < 9; ++k) red[(warp * 10 + k) * CG + lane] = dwt[k];
-    red[(warp * 10 + 9) * CG + lane] = dbs;
+    for (int k = 0; k < 9; ++k) red[warp][k][lane] = dwt[k];
+    red[warp][9][lane] = dbs;
     __syncthreads();
     for (int idx = threadIdx.x; idx < 10 * CG; idx += DW_THREADS) {
         const int k = idx / CG, l = idx % CG;
         float s = 0.f;
 #pragma unroll
-        for (int w = 0; w < DW_THREADS / 32; ++w) s += red[(w * 10 + k) * CG + l];
+        for (int w = 0; w < NWARP; ++w) s += red[w][k][l];
         const int cc = blockIdx.y * CG + l;
         if (cc < Ch) partials[((long long)blockIdx.x * 10 + k) * Ch + cc] = s;
     }
@@ -184,7 +241,7 @@ __global__ void dwconv_param_reduce_kernel(const float* __restrict__ partials, f
 int bwd_ctas(int B, int H, int W, int Ch) {
     const int tiles = B * uwr_cdiv(H, TS) * uwr_cdiv(W, TS);
     const int groups = uwr_cdiv(Ch, CG);
-    int p = uwr_cdiv(2 * uwr_sm_count(), groups);
+    int p = uwr_cdiv(4 * uwr_sm_count(), groups);
     if (p > tiles) p = tiles;
     return p < 1 ? 1 : p;
 }
@@ -205,27 +262,31 @@ extern "C" int uwr_dwconv_gelu_fwd(const float* u, long long ld_u, const float* 
     return 0;
 }
 
+extern "C" int uwr_gelu_gate_bwd(const float* dh2, const float* u, long long ld_u, const float* v, float* dv,
+                                 float* du, long long rows, int Ch, int mode, uwr_stream_t stream_) {
+    cudaStream_t stream = (cudaStream_t)stream_;
+    UWR_REQUIRE(dh2 && v && dv && (mode == 0 || (u && du)), "uwr_gelu_gate_bwd: null pointer");
+    const long long total = rows * Ch;
+    long long blocks = (total + 255) / 256;
+    if (blocks > 16LL * uwr_sm_count()) blocks = 16LL * uwr_sm_count();
+    gelu_gate_bwd_kernel<<<(unsigned)blocks, 256, 0, stream>>>(dh2, u, ld_u, v, dv, du, rows, Ch, mode);
+    UWR_CHECK_LAUNCH("gelu_gate_bwd_kernel");
+    return 0;
+}
+
 extern "C" size_t uwr_dwconv_gelu_bwd_workspace_bytes(int B, int H, int W, int Ch) {
     return (size_t)bwd_ctas(B, H, W, Ch) * 10 * (size_t)Ch * sizeof(float);
 }
 
-extern "C" int uwr_dwconv_gelu_bwd(const float* dh2, const float* u, long long ld_u, const float* v,
-                                   const float* weight, float* du, float* dweight, float* dbias, float* workspace,
-                                   int B, int H, int W, int Ch, int mode, uwr_stream_t stream_) {
+extern "C" int uwr_dwconv_gelu_bwd(const float* dv, const float* u, long long ld_u, const float* weight, float* du,
+                                   float* dweight, float* dbias, float* workspace, int B, int H, int W, int Ch,
+                                   uwr_stream_t stream_) {
     cudaStream_t stream = (cudaStream_t)stream_;
-    UWR_REQUIRE(dh2 && u && v && weight && du && dweight && dbias && workspace, "uwr_dwconv_gelu_bwd: null pointer");
-    UWR_REQUIRE(mode == 0 || mode == 1, "uwr_dwconv_gelu_bwd: mode must be 0 or 1");
+    UWR_REQUIRE(dv && u && weight && du && dweight && dbias && workspace, "uwr_dwconv_gelu_bwd: null pointer");
     const int tx = uwr_cdiv(W, TS), ty = uwr_cdiv(H, TS);
     const int P = bwd_ctas(B, H, W, Ch);
-    constexpr int smem_bytes = 2 * HS * HS * CG * (int)sizeof(float);
-    static bool configured = false;
-    if (!configured) {
-        UWR_CUDA(cudaFuncSetAttribute(dwconv_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes));
-        configured = true;
-    }
     dim3 grid(P, uwr_cdiv(Ch, CG));
-    dwconv_bwd_kernel<<<grid, DW_THREADS, smem_bytes, stream>>>(dh2, u, ld_u, v, weight, du, workspace, B, H, W, Ch,
-                                                               mode, tx, tx * ty);
+    dwconv_bwd_kernel<<<grid, DW_THREADS, 0, stream>>>(dv, u, ld_u, weight, du, workspace, B, H, W, Ch, tx, tx * ty);
     UWR_CHECK_LAUNCH("dwconv_bwd_kernel");
     dwconv_param_reduce_kernel<<<uwr_cdiv(10 * Ch, 128), 128, 0, stream>>>(workspace, dweight, dbias, P, Ch);
     UWR_CHECK_LAUNCH("dwconv_param_reduce_kernel");

@@ -105,7 +105,7 @@ __device__ __forceinline__ void mma_rows_x_rowsT(float (&acc)[8][4], const float
 
 // out[nt2][4] (16 rows x HD) = P(regs, 16 x 64 in C-fragment layout) * Bm[64][HD+4]
 // key permutation inside each k8 block: slot t <-> key 2t, slot t+4 <-> key 2t+1.
-template <int HD>
+template <int HD, bool X3>
 __device__ __forceinline__ void mma_regs_x_rows(float (&out)[HD / 8][4], const float (&P)[8][4], const float* Bm,
                                                 int g, int t) {
     constexpr int ST = HD + 4;
@@ -115,16 +115,20 @@ __device__ __forceinline__ void mma_regs_x_rows(float (&out)[HD / 8][4], const f
         for (int c = 0; c < 4; ++c) out[n][c] = 0.f;
 #pragma unroll
     for (int kb = 0; kb < 8; ++kb) {
-        uint32_t a[4];
-        a[0] = f2tf32(P[kb][0]);
-        a[1] = f2tf32(P[kb][2]);
-        a[2] = f2tf32(P[kb][1]);
-        a[3] = f2tf32(P[kb][3]);
+        uint32_t a[4], al[4];
+        split_tf32(P[kb][0], a[0], al[0]);
+        split_tf32(P[kb][2], a[1], al[1]);
+        split_tf32(P[kb][1], a[2], al[2]);
+        split_tf32(P[kb][3], a[3], al[3]);
 #pragma unroll
         for (int n = 0; n < HD / 8; ++n) {
-            uint32_t b[2];
-            b[0] = f2tf32(Bm[(kb * 8 + 2 * t) * ST + n * 8 + g]);
-            b[1] = f2tf32(Bm[(kb * 8 + 2 * t + 1) * ST + n * 8 + g]);
+            uint32_t b[2], bl[2];
+            split_tf32(Bm[(kb * 8 + 2 * t) * ST + n * 8 + g], b[0], bl[0]);
+            split_tf32(Bm[(kb * 8 + 2 * t + 1) * ST + n * 8 + g], b[1], bl[1]);
+            if (X3) {
+                mma_tf32_16x8x8(out[n], al, b);
+                mma_tf32_16x8x8(out[n], a, bl);
+            }
             mma_tf32_16x8x8(out[n], a, b);
         }
     }
@@ -231,7 +235,7 @@ __global__ void __launch_bounds__(ATT_THREADS) attn_fwd_kernel(const AttnParams 
             p0[nt][c] = w0 * p0[nt][c] + w1 * r * r;
         }
     float o[HD / 8][4];
-    mma_regs_x_rows<HD>(o, p0, Vs, g, t);
+    mma_regs_x_rows<HD, false>(o, p0, Vs, g, t);
 #pragma unroll
     for (int half = 0; half < 2; ++half) {
         float* orow = out + rows[r0 + g + half * 8] * ld_out + h * HD;
@@ -325,7 +329,7 @@ __global__ void __launch_bounds__(ATT_THREADS) attn_bwd_kernel(const AttnParams 
                     const float ds = w0 * P0 * (dP - rowdot) + w1 * 2.f * r * dP;
                     dsacc[nt][c] += ds;
                     dp[nt][c] = ds;  // dp now holds dS
-                    dv[e] = tf32_round(ds);
+                    dv[e] = ds;  // full fp32: dK = dS^T q cancels the common part of q (3xTF32 below)
                 }
                 const int j = nt * 8 + 2 * t;
                 *reinterpret_cast<float2*>(Ps + i * PS_STRIDE + j) = make_float2(pv[0], pv[1]);
@@ -335,7 +339,7 @@ __global__ void __launch_bounds__(ATT_THREADS) attn_bwd_kernel(const AttnParams 
         // dQ = scale * dS K  (Qs holds scale*q, so the chain rule adds one more factor scale)
         {
             float dq[HD / 8][4];
-            mma_regs_x_rows<HD>(dq, dp, Ks, g, t);
+            mma_regs_x_rows<HD, true>(dq, dp, Ks, g, t);  // dS rows sum to ~0: needs 3xTF32
 #pragma unroll
             for (int half = 0; half < 2; ++half) {
                 float* drow = dq_buf + rows[r0 + g + half * 8] * p.ld_q + p.q_off + h * HD;
@@ -359,16 +363,20 @@ __global__ void __launch_bounds__(ATT_THREADS) attn_bwd_kernel(const AttnParams 
                 for (int c = 0; c < 4; ++c) acc[n][c] = 0.f;
 #pragma unroll
             for (int kb = 0; kb < 8; ++kb) {
-                uint32_t a[4];
-                a[0] = __float_as_uint(Am[(kb * 8 + t) * PS_STRIDE + r0 + g]);
-                a[1] = __float_as_uint(Am[(kb * 8 + t) * PS_STRIDE + r0 + g + 8]);
-                a[2] = __float_as_uint(Am[(kb * 8 + t + 4) * PS_STRIDE + r0 + g]);
-                a[3] = __float_as_uint(Am[(kb * 8 + t + 4) * PS_STRIDE + r0 + g + 8]);
+                uint32_t a[4], al[4];
+                split_tf32(Am[(kb * 8 + t) * PS_STRIDE + r0 + g], a[0], al[0]);
+                split_tf32(Am[(kb * 8 + t) * PS_STRIDE + r0 + g + 8], a[1], al[1]);
+                split_tf32(Am[(kb * 8 + t + 4) * PS_STRIDE + r0 + g], a[2], al[2]);
+                split_tf32(Am[(kb * 8 + t + 4) * PS_STRIDE + r0 + g + 8], a[3], al[3]);
 #pragma unroll
                 for (int n = 0; n < HD / 8; ++n) {
-                    uint32_t bb[2];
-                    bb[0] = f2tf32(Bm[(kb * 8 + t) * ST + n * 8 + g]);
-                    bb[1] = f2tf32(Bm[(kb * 8 + t + 4) * ST + n * 8 + g]);
+                    uint32_t bb[2], bl[2];
+                    split_tf32(Bm[(kb * 8 + t) * ST + n * 8 + g], bb[0], bl[0]);
+                    split_tf32(Bm[(kb * 8 + t + 4) * ST + n * 8 + g], bb[1], bl[1]);
+                    if (which == 1) {  // dK: error-compensated
+                        mma_tf32_16x8x8(acc[n], al, bb);
+                        mma_tf32_16x8x8(acc[n], a, bl);
+                    }
                     mma_tf32_16x8x8(acc[n], a, bb);
                 }
             }

@@ -75,8 +75,9 @@ SIGNATURES = {
     "uwr_window_attn_bwd": (c_int, [C.POINTER(AttnDesc), c_fp, c_ll, c_fp, c_fp, c_fp, c_fp, c_fp, c_stream]),
     "uwr_dwconv_gelu_fwd": (c_int, [c_fp, c_ll, c_fp, c_fp, c_fp, c_fp, c_int, c_int, c_int, c_int, c_int, c_stream]),
     "uwr_dwconv_gelu_bwd_workspace_bytes": (c_sz, [c_int, c_int, c_int, c_int]),
-    "uwr_dwconv_gelu_bwd": (c_int, [c_fp, c_fp, c_ll, c_fp, c_fp, c_fp, c_fp, c_fp, c_fp,
-                                    c_int, c_int, c_int, c_int, c_int, c_stream]),
+    "uwr_dwconv_gelu_bwd": (c_int, [c_fp, c_fp, c_ll, c_fp, c_fp, c_fp, c_fp, c_fp,
+                                    c_int, c_int, c_int, c_int, c_stream]),
+    "uwr_gelu_gate_bwd": (c_int, [c_fp, c_fp, c_ll, c_fp, c_fp, c_fp, c_ll, c_int, c_int, c_stream]),
     "uwr_input_proj_fwd": (c_int, [c_fp, c_fp, c_fp, c_fp, c_int, c_int, c_int, c_int, c_int, c_f, c_stream]),
     "uwr_input_proj_bwd_workspace_bytes": (c_sz, [c_int] * 5),
     "uwr_input_proj_bwd": (c_int, [c_fp] * 6 + [c_int] * 5 + [c_f, c_stream]),

@@ -197,10 +197,11 @@ class LeFFBlockFn(torch.autograd.Function):
         x2, n2w, mean, rstd, y2, u, v, h2, w1, dww, w2, dp = ctx.saved_tensors
         B, L, Cc, Ch, H, W = ctx.meta
         d = _c(dout).view(B * L, Cc)
-        dh2 = ops.linear_dgrad(d, w2, rowscale=dp, rows_per_group=L)
+        # dv = (s*d W2) * gelu'(v): the second GELU's derivative rides in the GEMM epilogue
+        dv = ops.linear_dgrad(d, w2, rowscale=dp, rows_per_group=L, dgelu_of=v)
         dw2, db2 = ops.linear_wgrad(d, h2, rowscale=dp, rows_per_group=L)
-        du, ddww, ddwb = ops.dwconv_gelu_bwd(dh2, u, v, dww, B, H, W, Ch, mode=0)
-        del dh2
+        du, ddww, ddwb = ops.dwconv_gelu_bwd(dv, u, dww, B, H, W, Ch)
+        del dv
         dy2 = ops.linear_dgrad(du, w1)
         dw1, db1 = ops.linear_wgrad(du, y2)
         del du

@@ -137,15 +137,17 @@ def linear(x2d, weight, bias=None, *, weight2=None, bias2=None, residual=None, r
     return out
 
 
-def linear_dgrad(dy2d, weight, *, weight2=None, rowscale=None, rows_per_group=0, out=None):
-    """dx = (s*dy) [W;W2]   (dy: (M,N), W: (N1,K), W2: (N2,K))."""
+def linear_dgrad(dy2d, weight, *, weight2=None, rowscale=None, rows_per_group=0, out=None, dgelu_of=None):
+    """dx = (s*dy) [W;W2]   (dy: (M,N), W: (N1,K), W2: (N2,K)); dgelu_of=v multiplies by gelu'(v)."""
     M, N = dy2d.shape
     K = weight.shape[1]
     if out is None:
         out = _empty((M, K), dy2d)
     gemm(dy2d, weight, out, M, K, N, lda=dy2d.stride(0), ldb=weight.stride(0), ldc=out.stride(0),
          b_nk=False, B2=weight2, n_split=weight.shape[0] if weight2 is not None else 0,
-         rowscale=rowscale, rows_per_group=rows_per_group)
+         rowscale=rowscale, rows_per_group=rows_per_group,
+         epilogue=EPI_MUL_DGELU if dgelu_of is not None else EPI_NONE, R=dgelu_of,
+         ldr=dgelu_of.stride(0) if dgelu_of is not None else 0)
     return out
 
 
@@ -230,15 +232,26 @@ def dwconv_gelu_fwd(u2d, weight, bias, B, H, W, Ch, mode=0, save_v=True):
     return v, h2
 
 
-def dwconv_gelu_bwd(dh2, u2d, v, weight, B, H, W, Ch, mode=0):
-    du = torch.empty_like(u2d)
+def gelu_gate_bwd(dh2, u2d, v, Ch, mode, du=None):
+    """dv = dh2 * gelu'(v) [* gelu(u2)]; FRFN (mode 1) also fills du[:, Ch:]."""
+    rows = dh2.shape[0]
+    dv = torch.empty_like(dh2)
+    _run("uwr_gelu_gate_bwd", f"rows{rows} Ch{Ch} mode{mode}", 4 * rows * Ch * (3 + 2 * mode), 0.0,
+         _ptr(dh2), _ptr(u2d), u2d.stride(0), _ptr(v), _ptr(dv), _ptr(du), rows, Ch, mode)
+    return dv
+
+
+def dwconv_gelu_bwd(dv, u2d, weight, B, H, W, Ch, du=None):
+    """dv = dL/d(conv output).  Returns du (same row stride as u; only [:, :Ch] is written), dweight, dbias."""
+    if du is None:
+        du = torch.empty_like(u2d)
     dweight = torch.empty_like(weight)
     dbias = _empty((Ch,), u2d)
     ws = _ws(fn["uwr_dwconv_gelu_bwd_workspace_bytes"](B, H, W, Ch), u2d)
     n = B * H * W * Ch
-    _run("uwr_dwconv_gelu_bwd", f"B{B} H{H} Ch{Ch} mode{mode}", 4 * n * (4 + (2 if mode else 0)), 36.0 * n,
-         _ptr(dh2), _ptr(u2d), u2d.stride(0), _ptr(v), _ptr(weight), _ptr(du), _ptr(dweight), _ptr(dbias), _ptr(ws),
-         B, H, W, Ch, mode)
+    _run("uwr_dwconv_gelu_bwd", f"B{B} H{H} Ch{Ch}", 4 * n * 3, 36.0 * n,
+         _ptr(dv), _ptr(u2d), u2d.stride(0), _ptr(weight), _ptr(du), _ptr(dweight), _ptr(dbias), _ptr(ws),
+         B, H, W, Ch)
     return du, dweight, dbias
 
 
