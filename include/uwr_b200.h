@@ -40,13 +40,13 @@ unsigned long long uwr_launch_count(void); /* kernels launched by this library s
  *                     B2 (to_q | to_kv fused projection, AST.py:59-60): output columns when
  *                     b_nk = 1, contraction rows when b_nk = 0.
  *   epilogue: v = acc + bias[n]; v *= rowscale[m / rows_per_group] (if rowscale);
- *             UWR_EPI_RESID: v += R[m,n];  UWR_EPI_MUL_DGELU: v *= gelu'(R[m,n]).
+ *             UWR_EPI_RESID: v += R[m,n];  UWR_EPI_MUL_DGELU: v *= gelu'(R[m,n]);  UWR_EPI_MUL: v *= R[m,n].
  *   a_km = 1 (weight gradient, contraction over tokens): rowscale indexes the K rows
  *             (DropPath scale of the incoming gradient), colsum[M] = sum_k s_k A[k][m]
  *             (bias gradient) is produced when non-NULL, and the contraction is split over
  *             CTAs through `workspace` (uwr_gemm_workspace_bytes).
  */
-enum { UWR_EPI_NONE = 0, UWR_EPI_RESID = 1, UWR_EPI_MUL_DGELU = 2 };
+enum { UWR_EPI_NONE = 0, UWR_EPI_RESID = 1, UWR_EPI_MUL_DGELU = 2, UWR_EPI_MUL = 3 };
 
 typedef struct {
     const float* A;
@@ -78,6 +78,25 @@ size_t uwr_gemm_workspace_bytes(int M, int N, int K, int a_km);
 int uwr_set_gemm_precision(int passes);
 int uwr_get_gemm_precision(void);
 int uwr_gemm_tf32(const uwr_gemm_desc* d, uwr_stream_t stream);
+
+/* Blackwell-native path for the same descriptor: TMA (128B swizzle) -> smem ring -> tcgen05.mma
+ * kind::tf32 with TMEM accumulators -> tcgen05.ld epilogue, persistent warp-specialised CTAs.
+ * Operands must already be TF32-rounded (the tensor core truncates): producers round at store,
+ * weights via uwr_round_tf32_tensors.  `_supported` tells whether a descriptor is served here
+ * (no segmented weights / colsum / k-scale; MN-major widths in multiples of 32). */
+int uwr_gemm_tcgen05_supported(const uwr_gemm_desc* d);
+size_t uwr_gemm_tcgen05_workspace_bytes(int M, int N, int K, int a_km);
+int uwr_gemm_tcgen05(const uwr_gemm_desc* d, uwr_stream_t stream);
+
+/* TF32 operand preparation (tcgen05 truncates; operands are rounded to nearest where produced).
+ * In single-pass mode (uwr_set_gemm_precision(1)) the producers of GEMM operands — layernorm_fwd,
+ * window_attn_fwd/bwd, dwconv_gelu_fwd (h2) / _bwd (du), im2col — round at their stores.
+ * uwr_round_tf32_tensors: multi-tensor copy (+rounding when do_round) over device pointer tables
+ * (offsets has n_tensors+1 entries); uwr_scale_round: dst[rows][cols] = tf32(rowscale[r/rpg]*src). */
+int uwr_round_tf32_tensors(const float* const* src, float* const* dst, const long long* offsets,
+                           int n_tensors, long long total_elems, int do_round, uwr_stream_t stream);
+int uwr_scale_round(const float* src, long long ld_src, float* dst, long long rows, int cols,
+                    const float* rowscale, int rows_per_group, int do_round, uwr_stream_t stream);
 
 /* ---- LayerNorm over C (nn.LayerNorm eps 1e-5: AST.py:521,534,593,622) ------------------- */
 int uwr_layernorm_fwd(const float* x, const float* gamma, const float* beta, float* y,
@@ -123,13 +142,15 @@ int uwr_window_attn_bwd(const uwr_attn_desc* d, const float* dout, long long ld_
 /* ---- depthwise 3x3 conv on tokens with fused GELUs (LeFF / FRFN: AST.py:299-301,318,
  *      334-336,365-367) ---------------------------------------------------------------------
  * u: tokens (B,H,W,ld_u) pre-activation of linear1, channels [0,Ch) are convolved:
- *   v  = dwconv3x3(gelu(u)) + bias        (saved for backward when v != NULL)
+ *   v  = dwconv3x3(gelu(u)) + bias        (saved for backward when v != NULL; with v_is_dgelu the
+ *                                          buffer receives gelu'(v) instead, which is all the LeFF
+ *                                          backward needs: the GEMM epilogue UWR_EPI_MUL consumes it)
  *   h2 = gelu(v)                          (mode 0, LeFF)
  *   h2 = gelu(v) * gelu(u[:, Ch + c])     (mode 1, FRFN gate; u has 2*Ch channels)
  */
 int uwr_dwconv_gelu_fwd(const float* u, long long ld_u, const float* weight /*(Ch,1,3,3)*/,
                         const float* bias, float* v, float* h2, int B, int H, int W, int Ch,
-                        int mode, uwr_stream_t stream);
+                        int mode, int v_is_dgelu, uwr_stream_t stream);
 /* dv = dh2 * gelu'(v) [* gelu(u2)] for callers that do not fuse it into the producing GEMM
  * (UWR_EPI_MUL_DGELU); mode 1 (FRFN) also writes du[:, Ch:2Ch] = dh2 * gelu(v) * gelu'(u2). */
 int uwr_gelu_gate_bwd(const float* dh2, const float* u, long long ld_u, const float* v, float* dv,

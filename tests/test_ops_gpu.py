@@ -21,6 +21,14 @@ def ops():
     return o
 
 
+@pytest.fixture
+def exact(ops):
+    """tf32x3 mode: producers keep full fp32 outputs (no TF32 rounding at the stores)."""
+    ops.set_gemm_precision("tf32x3")
+    yield ops
+    ops.set_gemm_precision("tf32")
+
+
 def _r(*shape, seed=0, scale=1.0):
     g = torch.Generator(device="cpu").manual_seed(seed)
     return (torch.randn(*shape, generator=g) * scale).cuda()
@@ -92,7 +100,8 @@ def test_gemm_dgelu_epilogue(ops):
 
 # ------------------------------------------------------------------------------------- LayerNorm
 @pytest.mark.parametrize("rows,C", [(4096, 32), (1000, 64), (777, 128), (512, 256), (256, 512), (64, 48)])
-def test_layernorm(ops, rows, C):
+def test_layernorm(exact, rows, C):
+    ops = exact
     x = _r(rows, C, seed=1) * 2 + 0.3
     g, b = _r(C, seed=2) * 0.1 + 1, _r(C, seed=3) * 0.1
     y, mean, rstd = ops.layernorm_fwd(x, g, b)
@@ -171,7 +180,8 @@ def test_window_attention_fwd_bwd(ops, B, H, heads, hd, shift, sparse):
 # ------------------------------------------------------------------------------------ dwconv+GELU
 @pytest.mark.parametrize("B,H,Ch,mode", [(2, 16, 64, 0), (1, 32, 128, 0), (2, 24, 48, 0), (1, 16, 64, 1),
                                          (1, 40, 32, 1)])
-def test_dwconv_gelu(ops, B, H, Ch, mode):
+def test_dwconv_gelu(exact, B, H, Ch, mode):
+    ops = exact
     W = H
     width = Ch * (2 if mode else 1)
     u = _r(B * H * W, width, seed=1)
@@ -361,3 +371,19 @@ def test_transformer_block_vs_oracle(att, shift, scales):
     # P V and dV stay single-pass TF32 inside the attention kernel (P >= 0: no cancellation)
     assert errs.pop("out") < (3e-4 if att else 2e-5)
     assert max(errs.values()) < (2e-3 if att else 5e-4), errs
+
+
+def test_producers_round_to_tf32_in_fast_mode(ops):
+    """tf32 mode: LayerNorm output is exactly the TF32 rounding (cvt.rna) of the fp32 result."""
+    x = _r(512, 64, seed=1)
+    g, b = _r(64, seed=2) * 0.1 + 1, _r(64, seed=3) * 0.1
+    y_fast, _, _ = ops.layernorm_fwd(x, g, b)
+    ops.set_gemm_precision("tf32x3")
+    try:
+        y_full, _, _ = ops.layernorm_fwd(x, g, b)
+    finally:
+        ops.set_gemm_precision("tf32")
+    i = y_full.view(torch.int32)
+    expect = ((i + 0x1000) & ~0x1FFF).view(torch.float32)
+    assert torch.equal(y_fast, expect)
+    assert (y_fast.view(torch.int32) & 0x1FFF).abs().max().item() == 0

@@ -1,0 +1,89 @@
+"""tcgen05/TMA GEMM (uwr_gemm_tcgen05) vs fp64 on TF32-pre-rounded operands: all three layouts,
+tile edges, epilogues, split contraction."""
+import ctypes as C
+
+import pytest
+import torch
+import torch.nn.functional as F
+
+from conftest import rel_l2
+
+pytestmark = pytest.mark.gpu
+
+
+def tf32_round(x):
+    """round-to-nearest (ties away) to 10 mantissa bits, like cvt.rna.tf32.f32"""
+    i = x.contiguous().view(torch.int32)
+    return ((i + 0x1000) & ~0x1FFF).view(torch.float32)
+
+
+def _r(*shape, seed=0, scale=1.0):
+    g = torch.Generator(device="cpu").manual_seed(seed)
+    return tf32_round((torch.randn(*shape, generator=g) * scale).cuda())
+
+
+def _t5(A, B, Cout, M, N, K, lda, ldb, ldc, a_km=False, b_nk=True, bias=None, epilogue=0, R=None, ldr=0,
+        rowscale=None, rpg=0):
+    from uwr._lib import GemmDesc, check, fn
+    d = GemmDesc()
+    d.A, d.lda, d.a_km = A.data_ptr(), lda, int(a_km)
+    d.B, d.ldb, d.b_nk = B.data_ptr(), ldb, int(b_nk)
+    d.C, d.ldc, d.M, d.N, d.K = Cout.data_ptr(), ldc, M, N, K
+    d.bias = bias.data_ptr() if bias is not None else None
+    d.epilogue = epilogue
+    d.R, d.ldr = (R.data_ptr() if R is not None else None), ldr
+    d.rowscale, d.rows_per_group = (rowscale.data_ptr() if rowscale is not None else None), rpg
+    ws = None
+    nbytes = fn["uwr_gemm_tcgen05_workspace_bytes"](M, N, K, int(a_km))
+    if nbytes:
+        ws = torch.empty(nbytes // 4, device="cuda")
+        d.workspace, d.workspace_bytes = ws.data_ptr(), nbytes
+    assert fn["uwr_gemm_tcgen05_supported"](C.byref(d)) == 1
+    check(fn["uwr_gemm_tcgen05"](C.byref(d), torch.cuda.current_stream().cuda_stream), "uwr_gemm_tcgen05")
+    torch.cuda.synchronize()
+    return Cout
+
+
+@pytest.mark.parametrize("M,N,K", [(128, 32, 32), (256, 64, 64), (1000, 256, 64), (4096, 192, 64), (512, 512, 128),
+                                   (300, 2048, 512), (65536, 256, 64), (2048, 64, 256), (128, 128, 72)])
+def test_t5_nt(M, N, K):
+    x, w, b = _r(M, K, seed=1), _r(N, K, seed=2, scale=0.1), _r(N, seed=3)
+    out = torch.full((M, N), float("nan"), device="cuda")
+    _t5(x, w, out, M, N, K, K, K, N, bias=b)
+    assert rel_l2(out, x.double() @ w.double().t() + b.double()) < 1e-5
+
+
+def test_t5_nt_epilogues():
+    B, L, K, N = 4, 256, 128, 64
+    x, w, b, r = _r(B * L, K, seed=1), _r(N, K, seed=2, scale=0.1), _r(N, seed=3), _r(B * L, N, seed=4)
+    s = torch.tensor([0.0, 1.25, 1.25, 0.0]).cuda()
+    out = torch.empty(B * L, N, device="cuda")
+    _t5(x, w, out, B * L, N, K, K, K, N, bias=b, epilogue=1, R=r, ldr=N, rowscale=s, rpg=L)
+    ref = r.double() + s.double().repeat_interleave(L)[:, None] * (x.double() @ w.double().t() + b.double())
+    assert rel_l2(out, ref) < 2e-6
+    _t5(x, w, out, B * L, N, K, K, K, N, epilogue=2, R=r, ldr=N)
+    vd = r.double().requires_grad_()
+    F.gelu(vd).sum().backward()
+    assert rel_l2(out, (x.double() @ w.double().t()) * vd.grad) < 2e-6
+    _t5(x, w, out, B * L, N, K, K, K, N, epilogue=3, R=r, ldr=N, rowscale=s, rpg=L)
+    assert rel_l2(out, s.double().repeat_interleave(L)[:, None] * (x.double() @ w.double().t()) * r.double()) < 2e-6
+
+
+@pytest.mark.parametrize("M,N,K", [(256, 64, 256), (1000, 32, 128), (4096, 64, 256), (512, 128, 512),
+                                   (300, 512, 2048), (65536, 64, 256)])
+def test_t5_nn(M, N, K):
+    """dx[M,N] = dy[M,K] W[K,N]  (W stored [K][N]: MN-major B operand)"""
+    dy, w = _r(M, K, seed=1), _r(K, N, seed=2, scale=0.1)
+    out = torch.full((M, N), float("nan"), device="cuda")
+    _t5(dy, w, out, M, N, K, K, N, N, b_nk=False)
+    assert rel_l2(out, dy.double() @ w.double()) < 1e-5
+
+
+@pytest.mark.parametrize("M,N,K", [(128, 32, 512), (256, 64, 8192), (64, 256, 65536), (2048, 512, 4096),
+                                   (192, 64, 1000), (32, 128, 100000)])
+def test_t5_tn(M, N, K):
+    """dW[M,N] = dy[K,M]^T x[K,N]  (both MN-major, contraction split across CTAs)"""
+    dy, x = _r(K, M, seed=1), _r(K, N, seed=2)
+    out = torch.full((M, N), float("nan"), device="cuda")
+    _t5(dy, x, out, M, N, K, M, N, N, a_km=True, b_nk=False)
+    assert rel_l2(out, dy.double().t() @ x.double()) < 5e-6

@@ -1,0 +1,100 @@
+"""Per-kernel timing at the AST B=16 hot shapes (CUDA events, inputs >> L2). Used under ncu too.
+usage: python tools/kernel_bench.py [which ...]   which in {t5nt,t5nn,t5tn,legacy,dwf,dwb,attnb,attnf,lnb,colsum}"""
+import os, sys
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "underwater-image-restoration_b200"))
+import torch
+from uwr import ops
+
+which = sys.argv[1:] or ["t5nt", "t5nn", "t5tn", "legacy", "dwf", "dwb", "attnb", "attnf", "lnb", "colsum"]
+dev = "cuda"
+M = 16 * 65536
+
+
+def rnd(*s):
+    x = torch.randn(*s, device=dev)
+    return ((x.view(torch.int32) + 0x1000) & ~0x1FFF).view(torch.float32)
+
+
+def timeit(name, fn, nbytes, flops, reps=5):
+    for _ in range(2):
+        fn()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(reps):
+        fn()
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / reps
+    print(f"{name:34s} {ms:8.3f} ms  {nbytes / ms / 1e6:8.0f} GB/s  {flops / ms / 1e9:8.1f} TFLOP/s", flush=True)
+
+
+if "t5nt" in which or "legacy" in which:
+    x, w, b = rnd(M, 64), rnd(256, 64), rnd(256)
+    out = torch.empty(M, 256, device=dev)
+    nb, fl = 4 * (M * 64 + 256 * 64 + M * 256), 2.0 * M * 256 * 64
+    if "t5nt" in which:
+        timeit("t5 NT M1M N256 K64 bias", lambda: ops.linear(x, w, b, out=out, t5=True), nb, fl)
+    if "legacy" in which:
+        timeit("legacy NT M1M N256 K64 bias", lambda: ops.linear(x, w, b, out=out, t5=False), nb, fl)
+    h2, w2, r = rnd(M, 256), rnd(64, 256), rnd(M, 64)
+    out2 = torch.empty(M, 64, device=dev)
+    nb2, fl2 = 4 * (M * 256 + 2 * M * 64), 2.0 * M * 256 * 64
+    if "t5nt" in which:
+        timeit("t5 NT M1M N64 K256 resid", lambda: ops.linear(h2, w2, None, residual=r, out=out2, t5=True), nb2, fl2)
+    if "legacy" in which:
+        timeit("legacy NT M1M N64 K256 resid", lambda: ops.linear(h2, w2, None, residual=r, out=out2, t5=False), nb2, fl2)
+    del x, out, h2, r, out2
+if "t5nn" in which:
+    d, w2, v = rnd(M, 64), rnd(64, 256), rnd(M, 256)
+    out = torch.empty(M, 256, device=dev)
+    timeit("t5 NN M1M N256 K64 mul", lambda: ops.linear_dgrad(d, w2, mul_by=v, out=out, t5=True),
+           4 * (M * 64 + 2 * M * 256), 2.0 * M * 256 * 64)
+    timeit("t5 NN M1M N256 K64 plain", lambda: ops.linear_dgrad(d, w2, out=out, t5=True),
+           4 * (M * 64 + M * 256), 2.0 * M * 256 * 64)
+    del d, v, out
+if "t5tn" in which:
+    du, y = rnd(M, 256), rnd(M, 64)
+    timeit("t5 TN M256 N64 K1M", lambda: ops.linear_wgrad(du, y, want_bias=False, t5=True), 4 * (M * 320), 2.0 * M * 256 * 64)
+    timeit("legacy TN M256 N64 K1M", lambda: ops.linear_wgrad(du, y, want_bias=False, t5=False), 4 * (M * 320), 2.0 * M * 256 * 64)
+    del du, y
+if "dwf" in which or "dwb" in which:
+    B, H, Ch = 16, 256, 256
+    u = torch.randn(B * H * H, Ch, device=dev)
+    wt, bs = torch.randn(Ch, 1, 3, 3, device=dev) * 0.3, torch.randn(Ch, device=dev)
+    n = B * H * H * Ch
+    if "dwf" in which:
+        timeit("dwconv fwd B16 H256 Ch256", lambda: ops.dwconv_gelu_fwd(u, wt, bs, B, H, H, Ch), 4 * n * 3, 18.0 * n)
+    if "dwb" in which:
+        dv = torch.randn(B * H * H, Ch, device=dev)
+        du = torch.empty_like(u)
+        timeit("dwconv bwd B16 H256 Ch256", lambda: ops.dwconv_gelu_bwd(dv, u, wt, B, H, H, Ch, du=du), 4 * n * 3, 36.0 * n)
+        del dv, du
+    del u
+if "attnb" in which or "attnf" in which:
+    B, H, heads, hd = 16, 256, 2, 32
+    C = heads * hd
+    qkv = torch.randn(B * H * H, 3 * C, device=dev)
+    table = torch.randn(225, heads, device=dev) * 0.02
+    w = torch.ones(2, device=dev)
+    tiles = B * (H // 8) ** 2 * heads
+    if "attnf" in which:
+        timeit("attn fwd tiles32768 hd32", lambda: ops.window_attn_fwd(qkv, 0, qkv, C, 2 * C, table, w, B, H, H, heads, hd, 4, hd ** -0.5),
+               tiles * 4 * 64 * hd * 4, tiles * 4.0 * 64 * 64 * hd)
+    if "attnb" in which:
+        do = torch.randn(B * H * H, C, device=dev)
+        dq = torch.empty_like(qkv)
+        timeit("attn bwd tiles32768 hd32", lambda: ops.window_attn_bwd(do, qkv, 0, qkv, C, 2 * C, table, w, B, H, H, heads, hd, 4, hd ** -0.5, dq_buf=dq, dkv_buf=dq),
+               tiles * 7 * 64 * hd * 4, tiles * 10.0 * 64 * 64 * hd)
+        del do, dq
+    del qkv
+if "lnb" in which:
+    x, dy, dres = torch.randn(M, 64, device=dev), torch.randn(M, 64, device=dev), torch.randn(M, 64, device=dev)
+    g, b = torch.ones(64, device=dev), torch.zeros(64, device=dev)
+    y, mean, rstd = ops.layernorm_fwd(x, g, b)
+    timeit("LN fwd rows1M C64", lambda: ops.layernorm_fwd(x, g, b), 8 * M * 64, 0.0)
+    timeit("LN bwd rows1M C64 (+dres)", lambda: ops.layernorm_bwd(dy, x, g, mean, rstd, dres=dres), 16 * M * 64, 0.0)
+if "colsum" in which:
+    x = torch.randn(M, 256, device=dev)
+    timeit("colsum rows1M C256", lambda: ops.colsum(x, 256), 4 * M * 256, 0.0)

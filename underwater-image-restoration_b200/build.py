@@ -58,7 +58,7 @@ def build(force=False, verbose=False):
                     print("   ", l.strip())
     objs = [os.path.join(OBJ, s[:-3] + ".o") for s in srcs]
     if rebuilt or not os.path.exists(LIB) or any(os.path.getmtime(o) > os.path.getmtime(LIB) for o in objs):
-        cmd = [NVCC, "-shared", "-o", LIB] + objs + ["-lcuda"]
+        cmd = [NVCC, "-shared", "-o", LIB] + objs
         r = subprocess.run(cmd, capture_output=True, text=True)
         if r.returncode != 0:
             raise RuntimeError(f"link failed:\n{r.stdout}\n{r.stderr}")

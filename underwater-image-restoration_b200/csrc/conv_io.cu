@@ -346,7 +346,7 @@ __global__ void output_proj_reduce_kernel(const float* __restrict__ partials, fl
 
 // ------------------------------------------------------------------------------------------
 __global__ void im2col_4x4s2_kernel(const float* __restrict__ x, long long ld, float* __restrict__ col, int B, int H,
-                                    int W, int C) {
+                                    int W, int C, int rnd) {
     const int Ho = H / 2, Wo = W / 2, C4 = C / 4;
     const long long total = (long long)B * Ho * Wo * 16 * C4;
     for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total;
@@ -363,6 +363,7 @@ __global__ void im2col_4x4s2_kernel(const float* __restrict__ x, long long ld, f
         float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
         if (y >= 0 && y < H && xx >= 0 && xx < W)
             v = *reinterpret_cast<const float4*>(x + (((long long)b * H + y) * W + xx) * ld + c4 * 4);
+        if (rnd) v = make_float4(tf32_round(v.x), tf32_round(v.y), tf32_round(v.z), tf32_round(v.w));
         reinterpret_cast<float4*>(col)[i] = v;
     }
 }
@@ -464,9 +465,18 @@ __global__ void colsum_partial_kernel(const float* __restrict__ x, long long ld,
     __shared__ float sh[8][33];
     const int c = blockIdx.y * 32 + threadIdx.x;
     float s = 0.f;
-    if (c < cols)
-        for (long long r = (long long)blockIdx.x * 8 + threadIdx.y; r < rows; r += (long long)gridDim.x * 8)
-            s += x[r * ld + c];
+    if (c < cols) {
+        const long long step = (long long)gridDim.x * 8;
+        long long r = (long long)blockIdx.x * 8 + threadIdx.y;
+        for (; r + 7 * step < rows; r += 8 * step) {  // 8 independent loads in flight per thread
+            float v[8];
+#pragma unroll
+            for (int i = 0; i < 8; ++i) v[i] = __ldg(x + (r + i * step) * ld + c);
+#pragma unroll
+            for (int i = 0; i < 8; ++i) s += v[i];
+        }
+        for (; r < rows; r += step) s += __ldg(x + r * ld + c);
+    }
     sh[threadIdx.y][threadIdx.x] = s;
     __syncthreads();
     if (threadIdx.y == 0 && c < cols) {
@@ -603,7 +613,7 @@ extern "C" int uwr_im2col_4x4s2(const float* tokens, long long ld, float* col, i
     cudaStream_t stream = (cudaStream_t)stream_;
     UWR_REQUIRE(tokens && col && C % 4 == 0 && ld % 4 == 0 && H % 2 == 0 && W % 2 == 0, "uwr_im2col_4x4s2: bad args");
     const long long total = (long long)B * (H / 2) * (W / 2) * 16 * (C / 4);
-    im2col_4x4s2_kernel<<<ew_blocks(total, 256), 256, 0, stream>>>(tokens, ld, col, B, H, W, C);
+    im2col_4x4s2_kernel<<<ew_blocks(total, 256), 256, 0, stream>>>(tokens, ld, col, B, H, W, C, uwr_round_outputs());
     UWR_CHECK_LAUNCH("im2col_4x4s2_kernel");
     return 0;
 }

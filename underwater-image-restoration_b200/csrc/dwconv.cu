@@ -27,7 +27,8 @@ __global__ void __launch_bounds__(DW_THREADS) dwconv_fwd_kernel(const float* __r
                                                                 const float* __restrict__ weight,
                                                                 const float* __restrict__ bias,
                                                                 float* __restrict__ v, float* __restrict__ h2,
-                                                                int H, int W, int Ch, int mode, int tiles_x) {
+                                                                int H, int W, int Ch, int mode, int tiles_x, int rnd,
+                                                                int v_is_dgelu) {
     __shared__ float h1s[HS * HS][CG];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int c = blockIdx.y * CG + lane;
@@ -90,10 +91,12 @@ __global__ void __launch_bounds__(DW_THREADS) dwconv_fwd_kernel(const float* __r
                 for (int ky = 0; ky < 3; ++ky)
 #pragma unroll
                     for (int kx = 0; kx < 3; ++kx) acc = fmaf(win[ky][kx], wgt[ky * 3 + kx], acc);
-                if (v) v[(tok0 + lx) * Ch + c] = acc;
-                float o = gelu_f(acc);
+                const float cdf = 0.5f * (1.0f + erff(acc * 0.70710678118654752440f));
+                if (v) v[(tok0 + lx) * Ch + c] =
+                           v_is_dgelu ? cdf + acc * 0.39894228040143267794f * __expf(-0.5f * acc * acc) : acc;
+                float o = acc * cdf;
                 if (mode == 1) o *= gelu_f(gate[lx]);
-                h2[(tok0 + lx) * Ch + c] = o;
+                h2[(tok0 + lx) * Ch + c] = rnd ? tf32_round(o) : o;
             }
         }
     }
@@ -126,7 +129,7 @@ __global__ void __launch_bounds__(DW_THREADS) dwconv_bwd_kernel(const float* __r
                                                                 const float* __restrict__ weight,
                                                                 float* __restrict__ du, float* __restrict__ partials,
                                                                 int B, int H, int W, int Ch, int tiles_x,
-                                                                int tiles_per_img) {
+                                                                int tiles_per_img, int rnd) {
     __shared__ float dvs[HS * HS][CG];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int c = blockIdx.y * CG + lane;
@@ -204,7 +207,8 @@ __global__ void __launch_bounds__(DW_THREADS) dwconv_bwd_kernel(const float* __r
                                 dwt[ky * 3 + kx] = fmaf(h1, d, dwt[ky * 3 + kx]);
                             }
                         dbs += win[1][1];
-                        du[(tok0 + lx) * ld_u + c] = dh1 * (cdf + x * pdf);
+                        const float dval = dh1 * (cdf + x * pdf);
+                        du[(tok0 + lx) * ld_u + c] = rnd ? tf32_round(dval) : dval;
                     }
                 }
             }
@@ -249,7 +253,8 @@ int bwd_ctas(int B, int H, int W, int Ch) {
 }  // namespace
 
 extern "C" int uwr_dwconv_gelu_fwd(const float* u, long long ld_u, const float* weight, const float* bias, float* v,
-                                   float* h2, int B, int H, int W, int Ch, int mode, uwr_stream_t stream_) {
+                                   float* h2, int B, int H, int W, int Ch, int mode, int v_is_dgelu,
+                                   uwr_stream_t stream_) {
     cudaStream_t stream = (cudaStream_t)stream_;
     UWR_REQUIRE(u && weight && bias && h2, "uwr_dwconv_gelu_fwd: null pointer");
     UWR_REQUIRE(mode == 0 || mode == 1, "uwr_dwconv_gelu_fwd: mode must be 0 (LeFF) or 1 (FRFN gate)");
@@ -257,7 +262,8 @@ extern "C" int uwr_dwconv_gelu_fwd(const float* u, long long ld_u, const float* 
     UWR_REQUIRE(B > 0 && B <= 65535, "uwr_dwconv_gelu_fwd: bad batch %d", B);
     const int tx = uwr_cdiv(W, TS), ty = uwr_cdiv(H, TS);
     dim3 grid(tx * ty, uwr_cdiv(Ch, CG), B);
-    dwconv_fwd_kernel<<<grid, DW_THREADS, 0, stream>>>(u, ld_u, weight, bias, v, h2, H, W, Ch, mode, tx);
+    dwconv_fwd_kernel<<<grid, DW_THREADS, 0, stream>>>(u, ld_u, weight, bias, v, h2, H, W, Ch, mode, tx, uwr_round_outputs(),
+                                                      v_is_dgelu);
     UWR_CHECK_LAUNCH("dwconv_fwd_kernel");
     return 0;
 }
@@ -286,7 +292,8 @@ extern "C" int uwr_dwconv_gelu_bwd(const float* dv, const float* u, long long ld
     const int tx = uwr_cdiv(W, TS), ty = uwr_cdiv(H, TS);
     const int P = bwd_ctas(B, H, W, Ch);
     dim3 grid(P, uwr_cdiv(Ch, CG));
-    dwconv_bwd_kernel<<<grid, DW_THREADS, 0, stream>>>(dv, u, ld_u, weight, du, workspace, B, H, W, Ch, tx, tx * ty);
+    dwconv_bwd_kernel<<<grid, DW_THREADS, 0, stream>>>(dv, u, ld_u, weight, du, workspace, B, H, W, Ch, tx, tx * ty,
+                                                      uwr_round_outputs());
     UWR_CHECK_LAUNCH("dwconv_bwd_kernel");
     dwconv_param_reduce_kernel<<<uwr_cdiv(10 * Ch, 128), 128, 0, stream>>>(workspace, dweight, dbias, P, Ch);
     UWR_CHECK_LAUNCH("dwconv_param_reduce_kernel");

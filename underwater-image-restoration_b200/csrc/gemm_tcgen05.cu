@@ -1,0 +1,539 @@
+// Blackwell-native streaming GEMM for the Linear layers (AST.py:47-48,104,297,302,332,337):
+// TMA (cp.async.bulk.tensor, 128B swizzle) -> shared memory ring -> tcgen05.mma kind::tf32 issued by
+// one thread, fp32 accumulators in TMEM (two buffers) -> tcgen05.ld epilogue warps -> global.
+//
+//   persistent CTAs (one per SM), 320 threads:
+//     warp 0   : TMA producer          (one elected lane)
+//     warp 1   : TMEM allocator + MMA issuer (one elected lane)
+//     warp 2-9 : epilogue, warp w owns TMEM lanes 32*(w%4) .. +31 of the 128-row accumulator and
+//                every second 32-column chunk; bias staged in smem, R prefetched, TMEM loads pipelined
+//
+//   CTA tile 128 x BN (BN <= 256), contraction streamed in chunks of 32 fp32 (128 B rows).
+//   Layouts (same meaning as uwr_gemm_tf32):  NT: A[M][K], B[N][K]   (forward,   both K-major)
+//                                              NN: A[M][K], B[K][N]   (data grad, B MN-major)
+//                                              TN: A[K][M], B[K][N]   (weight grad, both MN-major,
+//                                                                      split over the contraction)
+// Operand contract: kind::tf32 reads the upper 19 bits of each fp32 (truncation), so callers pass
+// operands already rounded to TF32 (the producing kernels round at their stores, weights through
+// uwr_round_tf32_tensors); the GEMM itself adds no rounding bias.
+#include <cuda.h>
+
+#include "uwr_common.cuh"
+#include "../../include/uwr_b200.h"
+
+namespace {
+
+constexpr int TM = 128;      // CTA tile rows (UMMA M)
+constexpr int KC = 32;       // contraction chunk: 32 fp32 = one 128-byte swizzle row
+constexpr int STAGES = 4;
+constexpr int EPI_WARPS = 8;   // two warps per TMEM lane quadrant, interleaved over 32-column chunks
+constexpr int T5_THREADS = 64 + EPI_WARPS * 32;
+constexpr uint32_t SPIN_LIMIT = 1u << 24;
+
+enum { LAY_NT = 0, LAY_NN = 1, LAY_TN = 2 };
+
+struct T5Params {
+    float* C;
+    long long ldc;
+    int M, N;            // output extent
+    int chunks;          // contraction chunks (of 32) in total
+    int chunks_per_split;
+    int splits;
+    long long split_stride;  // elements between split partials (TN)
+    int tiles_m, tiles_n;
+    const float* bias;
+    const float* R;
+    long long ldr;
+    const float* rowscale;
+    int rows_per_group;
+    int epilogue;
+};
+
+// ---------------------------------------------------------------------------------- PTX wrappers
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
+    uint32_t ok;
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+        "selp.u32 %0, 1, 0, p;\n"
+        "}"
+        : "=r"(ok)
+        : "r"(smem_u32(bar)), "r"(parity)
+        : "memory");
+    return ok != 0;
+}
+// bounded spin: a protocol bug traps (launch error) instead of hanging the GPU
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+    uint32_t spins = 0;
+    while (!mbar_try_wait(bar, parity)) {
+        if (++spins > SPIN_LIMIT) __trap();
+    }
+}
+__device__ __forceinline__ void tma_load_2d(void* dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+        ::"r"(smem_u32(dst)), "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
+        : "memory");
+}
+__device__ __forceinline__ void tma_load_3d(void* dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1, int c2) {
+    asm volatile(
+        "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
+        ::"r"(smem_u32(dst)), "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2)
+        : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+
+// shared-memory matrix descriptor (cute::UMMA::SmemDescriptor): SWIZZLE_128B, version 1
+// layout: 2 = SWIZZLE_128B (K-major operands), 1 = SWIZZLE_128B_BASE32B (the only layout the tensor
+// core accepts for MN-major 32-bit operands: 32 B chunks permuted inside 128 B rows, 4-row atoms)
+__device__ __forceinline__ uint64_t make_smem_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes,
+                                                   uint32_t layout) {
+    uint64_t d = 0;
+    d |= (uint64_t)((saddr & 0x3FFFFu) >> 4);
+    d |= (uint64_t)((lbo_bytes >> 4) & 0x3FFFu) << 16;
+    d |= (uint64_t)((sbo_bytes >> 4) & 0x3FFFu) << 32;
+    d |= (uint64_t)1 << 46;  // descriptor version (Blackwell)
+    d |= (uint64_t)layout << 61;
+    return d;
+}
+__device__ __forceinline__ void umma_tf32(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
+                                          uint32_t accumulate) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "setp.ne.b32 p, %4, 0;\n"
+        "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n"
+        "}" ::"r"(d_tmem), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint64_t* bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar))
+                 : "memory");
+}
+__device__ __forceinline__ void tmem_ld32_issue(uint32_t taddr, uint32_t (&r)[32]) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+          "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
+          "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
+          "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+        : "r"(taddr));
+}
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
+// -------------------------------------------------------------------------------------- kernel
+template <int BN, int LAY>
+__global__ void __launch_bounds__(T5_THREADS, 1)
+gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapB,
+                    const T5Params p) {
+    constexpr bool A_MN = (LAY == LAY_TN);
+    constexpr bool B_MN = (LAY != LAY_NT);
+    constexpr int A_BYTES = TM * KC * 4;  // 16 KB
+    constexpr int B_BYTES = BN * KC * 4;
+    constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
+    constexpr int TMEM_COLS = (2 * BN < 32) ? 32 : 2 * BN;  // power of two: BN in {32,64,128,256}
+    // instruction descriptor (cute::UMMA::InstrDescriptor): D=f32, A=B=tf32, majors, N>>3, M>>4
+    constexpr uint32_t IDESC = (1u << 4) | (2u << 7) | (2u << 10) | ((A_MN ? 1u : 0u) << 15) |
+                               ((B_MN ? 1u : 0u) << 16) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(TM >> 4) << 24);
+
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);  // 1024 B: swizzle atoms
+    uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + STAGES * STAGE_BYTES);
+    uint64_t* empty_bar = full_bar + STAGES;
+    uint64_t* tfull_bar = empty_bar + STAGES;  // [2] accumulator ready
+    uint64_t* tempty_bar = tfull_bar + 2;      // [2] accumulator drained
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty_bar + 2);
+    float* sbias = reinterpret_cast<float*>(smem + STAGES * STAGE_BYTES + 256);  // [BN]
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int items = p.tiles_m * p.tiles_n * p.splits;
+
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < STAGES; ++s) {
+            mbar_init(&full_bar[s], 1);
+            mbar_init(&empty_bar[s], 1);
+        }
+        for (int b = 0; b < 2; ++b) {
+            mbar_init(&tfull_bar[b], 1);
+            mbar_init(&tempty_bar[b], EPI_WARPS);  // one arrival per epilogue warp
+        }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 1) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)),
+                     "n"(TMEM_COLS)
+                     : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp == 0) {
+        // ================================ TMA producer ================================
+        if (lane == 0) {
+            asm volatile("prefetch.tensormap [%0];" ::"l"(&mapA) : "memory");
+            asm volatile("prefetch.tensormap [%0];" ::"l"(&mapB) : "memory");
+            int stage = 0;
+            uint32_t phase = 0;
+            for (int item = blockIdx.x; item < items; item += gridDim.x) {
+                const int tm = item % p.tiles_m;
+                const int tn = (item / p.tiles_m) % p.tiles_n;
+                const int z = item / (p.tiles_m * p.tiles_n);
+                const int c_begin = z * p.chunks_per_split;
+                const int c_end = min(p.chunks, c_begin + p.chunks_per_split);
+                for (int c = c_begin; c < c_end; ++c) {
+                    mbar_wait(&empty_bar[stage], phase ^ 1);
+                    uint8_t* sa = smem + stage * STAGE_BYTES;
+                    uint8_t* sb = sa + A_BYTES;
+                    mbar_expect_tx(&full_bar[stage], STAGE_BYTES);
+                    if (!A_MN) {
+                        tma_load_2d(sa, &mapA, &full_bar[stage], c * KC, tm * TM);
+                    } else {
+                        // MN-major: one 32(mn) x 32(k) box per 32-wide group -> [group][k][128 B]
+#pragma unroll
+                        for (int g = 0; g < TM / 32; ++g)
+                            tma_load_2d(sa + g * 4096, &mapA, &full_bar[stage], tm * TM + g * 32, c * KC);
+                    }
+                    if (!B_MN) {
+                        tma_load_2d(sb, &mapB, &full_bar[stage], c * KC, tn * BN);
+                    } else {
+#pragma unroll
+                        for (int g = 0; g < BN / 32; ++g)
+                            tma_load_2d(sb + g * 4096, &mapB, &full_bar[stage], tn * BN + g * 32, c * KC);
+                    }
+                    if (++stage == STAGES) {
+                        stage = 0;
+                        phase ^= 1;
+                    }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ================================ MMA issuer ==================================
+        if (lane == 0) {
+            int stage = 0;
+            uint32_t phase = 0;
+            int local = 0;
+            for (int item = blockIdx.x; item < items; item += gridDim.x, ++local) {
+                const int z = item / (p.tiles_m * p.tiles_n);
+                const int c_begin = z * p.chunks_per_split;
+                const int c_end = min(p.chunks, c_begin + p.chunks_per_split);
+                const int buf = local & 1;
+                const uint32_t use = (uint32_t)(local >> 1);  // how often this buffer was used before
+                mbar_wait(&tempty_bar[buf], (use & 1) ^ 1);
+                tc_fence_after();
+                const uint32_t d_tmem = tmem_base + (uint32_t)(buf * BN);
+                for (int c = c_begin; c < c_end; ++c) {
+                    mbar_wait(&full_bar[stage], phase);
+                    tc_fence_after();
+                    const uint32_t sa = smem_u32(smem + stage * STAGE_BYTES);
+                    const uint32_t sb = sa + A_BYTES;
+#pragma unroll
+                    for (int k8 = 0; k8 < KC / 8; ++k8) {
+                        // K-major: rows of 128 B, 8-row groups 1024 B apart, step 32 B inside the row.
+                        // MN-major: [mn/32][k][32 floats]; 4-k atoms 512 B apart (SBO), mn groups 4096 B
+                        // apart (LBO); one MMA consumes 8 k rows = 1024 B.
+                        const uint64_t ad = A_MN ? make_smem_desc(sa + k8 * 1024, 4096, 512, 1)
+                                                 : make_smem_desc(sa + k8 * 32, 16, 1024, 2);
+                        const uint64_t bd = B_MN ? make_smem_desc(sb + k8 * 1024, 4096, 512, 1)
+                                                 : make_smem_desc(sb + k8 * 32, 16, 1024, 2);
+                        umma_tf32(d_tmem, ad, bd, IDESC, (c > c_begin || k8 > 0) ? 1u : 0u);
+                    }
+                    umma_commit(&empty_bar[stage]);  // frees the smem slot once these MMAs retire
+                    if (++stage == STAGES) {
+                        stage = 0;
+                        phase ^= 1;
+                    }
+                }
+                umma_commit(&tfull_bar[buf]);  // accumulator complete
+            }
+        }
+    } else {
+        // ================================ epilogue ====================================
+        const int q = warp & 3;              // TMEM lane quadrant owned by this warp
+        const int half = (warp - 2) >> 2;    // 0/1: which 32-column chunks (even/odd)
+        const int etid = threadIdx.x - 64;   // 0..255 inside the epilogue group
+        int local = 0, cur_tn = -1;
+        for (int item = blockIdx.x; item < items; item += gridDim.x, ++local) {
+            const int tm = item % p.tiles_m;
+            const int tn = (item / p.tiles_m) % p.tiles_n;
+            const int z = item / (p.tiles_m * p.tiles_n);
+            const int buf = local & 1;
+            const uint32_t use = (uint32_t)(local >> 1);
+            if (p.bias != nullptr && tn != cur_tn) {  // uniform across the epilogue warps
+                asm volatile("bar.sync 1, %0;" ::"n"(EPI_WARPS * 32) : "memory");
+                for (int i = etid; i < BN; i += EPI_WARPS * 32) {
+                    const int col = tn * BN + i;
+                    sbias[i] = col < p.N ? __ldg(p.bias + col) : 0.f;
+                }
+                asm volatile("bar.sync 1, %0;" ::"n"(EPI_WARPS * 32) : "memory");
+            }
+            cur_tn = tn;
+            const int row = tm * TM + q * 32 + lane;
+            const bool row_ok = row < p.M;
+            float* crow = p.C + (long long)z * p.split_stride + (long long)row * p.ldc;
+            const float* rrow = p.R + (long long)row * p.ldr;
+            float s = 1.f;
+            if (p.rowscale != nullptr && row_ok) s = __ldg(p.rowscale + row / p.rows_per_group);
+            mbar_wait(&tfull_bar[buf], use & 1);
+            tc_fence_after();
+            const uint32_t tbase = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(buf * BN);
+            constexpr int NCH = (BN / 32 + 1) / 2;  // chunks per warp (BN = 32: only half 0 works)
+            uint32_t acc[2][32];
+            if (half * 32 < BN) tmem_ld32_issue(tbase + half * 32, acc[0]);
+#pragma unroll
+            for (int ci = 0; ci < NCH; ++ci) {
+                const int c0 = (2 * ci + half) * 32;
+                if (c0 >= BN) break;
+                const int col0 = tn * BN + c0;
+                const bool live = row_ok && col0 < p.N;
+                // operand of the epilogue (residual / multiplier): issue the loads before waiting on TMEM
+                float4 rv[8];
+                if (p.epilogue != UWR_EPI_NONE && live) {
+#pragma unroll
+                    for (int j = 0; j < 8; ++j)
+                        rv[j] = (col0 + 4 * j < p.N) ? *reinterpret_cast<const float4*>(rrow + col0 + 4 * j)
+                                                     : make_float4(0.f, 0.f, 0.f, 0.f);
+                }
+                tmem_ld_wait();
+                const int cn = c0 + 64;
+                if (ci + 1 < NCH && cn < BN) tmem_ld32_issue(tbase + cn, acc[(ci + 1) & 1]);  // next chunk in flight
+                if (live) {
+                    const uint32_t* a = acc[ci & 1];
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) {
+                        const int col = col0 + 4 * j;
+                        if (col >= p.N) break;  // N is a multiple of 4
+                        float4 o = make_float4(__uint_as_float(a[4 * j]), __uint_as_float(a[4 * j + 1]),
+                                               __uint_as_float(a[4 * j + 2]), __uint_as_float(a[4 * j + 3]));
+                        if (p.bias != nullptr) {
+                            const float4 b = *reinterpret_cast<const float4*>(sbias + c0 + 4 * j);
+                            o.x += b.x; o.y += b.y; o.z += b.z; o.w += b.w;
+                        }
+                        o.x *= s; o.y *= s; o.z *= s; o.w *= s;
+                        if (p.epilogue == UWR_EPI_RESID) {
+                            o.x += rv[j].x; o.y += rv[j].y; o.z += rv[j].z; o.w += rv[j].w;
+                        } else if (p.epilogue == UWR_EPI_MUL) {
+                            o.x *= rv[j].x; o.y *= rv[j].y; o.z *= rv[j].z; o.w *= rv[j].w;
+                        } else if (p.epilogue == UWR_EPI_MUL_DGELU) {
+                            o.x *= gelu_grad_f(rv[j].x); o.y *= gelu_grad_f(rv[j].y);
+                            o.z *= gelu_grad_f(rv[j].z); o.w *= gelu_grad_f(rv[j].w);
+                        }
+                        *reinterpret_cast<float4*>(crow + col) = o;
+                    }
+                }
+            }
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&tempty_bar[buf]);
+        }
+    }
+
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) {
+        tc_fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(TMEM_COLS) : "memory");
+    }
+}
+
+__global__ void t5_splitk_reduce_kernel(const float* __restrict__ ws, float* __restrict__ out, long long n,
+                                        long long stride, int splits) {
+    long long i = ((long long)blockIdx.x * blockDim.x + threadIdx.x) * 4;
+    const long long step = (long long)gridDim.x * blockDim.x * 4;
+    for (; i < n; i += step) {
+        float4 s = make_float4(0.f, 0.f, 0.f, 0.f);
+        for (int z = 0; z < splits; ++z) {
+            const float4 v = *reinterpret_cast<const float4*>(ws + z * stride + i);
+            s.x += v.x; s.y += v.y; s.z += v.z; s.w += v.w;
+        }
+        *reinterpret_cast<float4*>(out + i) = s;
+    }
+}
+
+// ------------------------------------------------------------------------------------ host side
+// cuTensorMapEncodeTiled is resolved through the runtime (no link-time dependency on libcuda.so, so
+// the library also loads on a machine without a driver, e.g. for the CPU-side symbol checks).
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+EncodeTiledFn encode_tiled_fn() {
+    static EncodeTiledFn fn = nullptr;
+    if (!fn) {
+        void* p = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
+            q == cudaDriverEntryPointSuccess)
+            fn = (EncodeTiledFn)p;
+    }
+    return fn;
+}
+
+int encode_2d(CUtensorMap* m, const float* base, long long inner, long long rows, long long ld, int box_rows,
+              CUtensorMapSwizzle swz = CU_TENSOR_MAP_SWIZZLE_128B) {
+    cuuint64_t dims[2] = {(cuuint64_t)inner, (cuuint64_t)rows};
+    cuuint64_t strides[1] = {(cuuint64_t)ld * 4};
+    cuuint32_t box[2] = {KC, (cuuint32_t)box_rows};
+    cuuint32_t es[2] = {1, 1};
+    EncodeTiledFn enc = encode_tiled_fn();
+    if (!enc) {
+        uwr_set_error("cuTensorMapEncodeTiled is not available from the driver");
+        return -3;
+    }
+    CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, (void*)base, dims, strides, box, es,
+                     CU_TENSOR_MAP_INTERLEAVE_NONE, swz, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) {
+        uwr_set_error("cuTensorMapEncodeTiled(2d) failed: %d (inner %lld rows %lld ld %lld)", (int)r, inner, rows, ld);
+        return -3;
+    }
+    return 0;
+}
+// MN-major operand stored [k][width]: plain 2-D map, box = 32 (width) x 32 (k rows)
+int encode_mn(CUtensorMap* m, const float* base, long long width, long long krows, long long ld) {
+    return encode_2d(m, base, width, krows, ld, KC, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B);
+}
+
+int t5_pick_bn(int N) {
+    if (N <= 32) return 32;
+    if (N <= 64) return 64;
+    if (N <= 128) return 128;
+    return 256;
+}
+
+struct T5Split {
+    int splits, chunks_per_split;
+};
+T5Split t5_plan(int M, int N, int Kc, int lay, int bn) {
+    const int chunks = uwr_cdiv(Kc, KC);
+    T5Split sp{1, chunks};
+    if (lay != LAY_TN) return sp;
+    const long long tiles = (long long)uwr_cdiv(M, TM) * uwr_cdiv(N, bn);
+    int splits = (int)((uwr_sm_count() + tiles - 1) / tiles);
+    const int max_splits = chunks / 8 > 0 ? chunks / 8 : 1;  // >= 256 contraction rows per split
+    if (splits > max_splits) splits = max_splits;
+    if (splits < 1) splits = 1;
+    sp.chunks_per_split = uwr_cdiv(chunks, splits);
+    sp.splits = uwr_cdiv(chunks, sp.chunks_per_split);
+    return sp;
+}
+
+template <int BN, int LAY>
+int t5_launch(const CUtensorMap& ma, const CUtensorMap& mb, const T5Params& p, cudaStream_t stream) {
+    constexpr int smem = STAGES * (TM * KC * 4 + BN * KC * 4) + 1024 + 256 + BN * 4;
+    auto kern = gemm_tcgen05_kernel<BN, LAY>;
+    static bool configured = false;
+    if (!configured) {
+        UWR_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+        configured = true;
+    }
+    const int items = p.tiles_m * p.tiles_n * p.splits;
+    int grid = uwr_sm_count();
+    if (grid > items) grid = items;
+    kern<<<grid, T5_THREADS, smem, stream>>>(ma, mb, p);
+    UWR_CHECK_LAUNCH("gemm_tcgen05_kernel");
+    return 0;
+}
+
+template <int BN>
+int t5_dispatch(int lay, const CUtensorMap& ma, const CUtensorMap& mb, const T5Params& p, cudaStream_t stream) {
+    switch (lay) {
+        case LAY_NT: return t5_launch<BN, LAY_NT>(ma, mb, p, stream);
+        case LAY_NN: return t5_launch<BN, LAY_NN>(ma, mb, p, stream);
+        default: return t5_launch<BN, LAY_TN>(ma, mb, p, stream);
+    }
+}
+
+}  // namespace
+
+extern "C" size_t uwr_gemm_tcgen05_workspace_bytes(int M, int N, int K, int a_km) {
+    if (!a_km) return 0;
+    const T5Split sp = t5_plan(M, N, K, LAY_TN, t5_pick_bn(N));
+    return sp.splits > 1 ? (size_t)sp.splits * M * N * sizeof(float) : 0;
+}
+
+// 1 if the shape/layout/alignment of `d` is served by the tcgen05 path (the caller falls back to
+// uwr_gemm_tf32 otherwise, e.g. segmented weights, odd widths, colsum / k-scale requests).
+extern "C" int uwr_gemm_tcgen05_supported(const uwr_gemm_desc* d) {
+    if (!d || d->B2 || d->colsum) return 0;
+    if (d->a_km && (d->b_nk || d->rowscale || d->epilogue != UWR_EPI_NONE || d->bias)) return 0;
+    if (d->K % 4 || d->N % 4 || d->lda % 4 || d->ldb % 4 || d->ldc % 4) return 0;
+    if (((uintptr_t)d->A | (uintptr_t)d->B | (uintptr_t)d->C) % 16) return 0;
+    if (d->epilogue != UWR_EPI_NONE && (!d->R || d->ldr % 4 || (uintptr_t)d->R % 16)) return 0;
+    if (d->bias && (uintptr_t)d->bias % 16) return 0;
+    if (d->a_km && (d->M % 32 || d->N % 32)) return 0;   // MN-major operands: widths in 32-float groups
+    if (!d->a_km && !d->b_nk && d->N % 32) return 0;
+    if (d->M < 1 || d->N < 8 || d->K < 8) return 0;
+    return 1;
+}
+
+extern "C" int uwr_gemm_tcgen05(const uwr_gemm_desc* d, uwr_stream_t stream_) {
+    cudaStream_t stream = (cudaStream_t)stream_;
+    UWR_REQUIRE(uwr_gemm_tcgen05_supported(d), "uwr_gemm_tcgen05: unsupported shape/layout (use uwr_gemm_tf32)");
+    const int lay = d->a_km ? LAY_TN : (d->b_nk ? LAY_NT : LAY_NN);
+    const int bn = t5_pick_bn(d->N);
+    const T5Split sp = t5_plan(d->M, d->N, d->K, lay, bn);
+
+    CUtensorMap ma, mb;
+    int rc;
+    if (lay == LAY_TN) {
+        // A stored [K][M] (width M), B stored [K][N] (width N)
+        if ((rc = encode_mn(&ma, d->A, d->M, d->K, d->lda))) return rc;
+        if ((rc = encode_mn(&mb, d->B, d->N, d->K, d->ldb))) return rc;
+    } else {
+        if ((rc = encode_2d(&ma, d->A, d->K, d->M, d->lda, TM))) return rc;
+        if (lay == LAY_NT) {
+            if ((rc = encode_2d(&mb, d->B, d->K, d->N, d->ldb, bn))) return rc;
+        } else {
+            if ((rc = encode_mn(&mb, d->B, d->N, d->K, d->ldb))) return rc;
+        }
+    }
+
+    T5Params p;
+    p.C = d->C; p.ldc = d->ldc; p.M = d->M; p.N = d->N;
+    p.chunks = uwr_cdiv(d->K, KC);
+    p.chunks_per_split = sp.chunks_per_split; p.splits = sp.splits; p.split_stride = 0;
+    p.tiles_m = uwr_cdiv(d->M, TM); p.tiles_n = uwr_cdiv(d->N, bn);
+    p.bias = d->bias; p.R = d->R; p.ldr = d->ldr;
+    p.rowscale = d->rowscale; p.rows_per_group = d->rows_per_group > 0 ? d->rows_per_group : 1;
+    p.epilogue = d->epilogue;
+    if (sp.splits > 1) {
+        const size_t need = (size_t)sp.splits * d->M * d->N * sizeof(float);
+        UWR_REQUIRE(d->workspace && d->workspace_bytes >= need, "uwr_gemm_tcgen05: workspace too small (%zu < %zu)",
+                    d->workspace_bytes, need);
+        UWR_REQUIRE(d->ldc == d->N, "uwr_gemm_tcgen05: split contraction needs a dense C");
+        p.C = d->workspace; p.ldc = d->N; p.split_stride = (long long)d->M * d->N;
+    }
+    switch (bn) {
+        case 32: rc = t5_dispatch<32>(lay, ma, mb, p, stream); break;
+        case 64: rc = t5_dispatch<64>(lay, ma, mb, p, stream); break;
+        case 128: rc = t5_dispatch<128>(lay, ma, mb, p, stream); break;
+        default: rc = t5_dispatch<256>(lay, ma, mb, p, stream); break;
+    }
+    if (rc) return rc;
+    if (sp.splits > 1) {
+        const long long n = (long long)d->M * d->N;
+        int blocks = (int)((n / 4 + 255) / 256);
+        if (blocks > 4 * uwr_sm_count()) blocks = 4 * uwr_sm_count();
+        t5_splitk_reduce_kernel<<<blocks, 256, 0, stream>>>(d->workspace, d->C, n, n, sp.splits);
+        UWR_CHECK_LAUNCH("t5_splitk_reduce_kernel");
+    }
+    return 0;
+}

@@ -255,6 +255,10 @@ __global__ void __launch_bounds__(NTHREADS, X3 ? 1 : 2) gemm_tf32_kernel(const G
                     const float2 r = *reinterpret_cast<const float2*>(p.R + (long long)row * p.ldr + col);
                     v0 *= gelu_grad_f(r.x);
                     v1 *= gelu_grad_f(r.y);
+                } else if (EPI == UWR_EPI_MUL) {
+                    const float2 r = *reinterpret_cast<const float2*>(p.R + (long long)row * p.ldr + col);
+                    v0 *= r.x;
+                    v1 *= r.y;
                 }
                 *reinterpret_cast<float2*>(Cout + (long long)row * p.ldc + col) = make_float2(v0, v1);
             }
@@ -319,7 +323,6 @@ int pick_bn(int N) {
     return 128;
 }
 
-int g_passes = 1;  // 1: TF32 (default), 3: error-compensated 3xTF32 (fp32-level accuracy)
 
 template <int BN, bool A_KM, bool B_NK, int EPI, bool KSCALE, bool X3>
 int launch_x(const GemmParams& p, int splits, cudaStream_t stream) {
@@ -338,7 +341,7 @@ int launch_x(const GemmParams& p, int splits, cudaStream_t stream) {
 
 template <int BN, bool A_KM, bool B_NK, int EPI, bool KSCALE>
 int launch(const GemmParams& p, int splits, cudaStream_t stream) {
-    return g_passes == 3 ? launch_x<BN, A_KM, B_NK, EPI, KSCALE, true>(p, splits, stream)
+    return g_uwr_gemm_passes == 3 ? launch_x<BN, A_KM, B_NK, EPI, KSCALE, true>(p, splits, stream)
                          : launch_x<BN, A_KM, B_NK, EPI, KSCALE, false>(p, splits, stream);
 }
 
@@ -356,12 +359,14 @@ int dispatch_layout(const uwr_gemm_desc* d, const GemmParams& p, int splits, cud
             case UWR_EPI_NONE: return launch<BN, false, true, UWR_EPI_NONE, false>(p, splits, stream);
             case UWR_EPI_RESID: return launch<BN, false, true, UWR_EPI_RESID, false>(p, splits, stream);
             case UWR_EPI_MUL_DGELU: return launch<BN, false, true, UWR_EPI_MUL_DGELU, false>(p, splits, stream);
+            case UWR_EPI_MUL: return launch<BN, false, true, UWR_EPI_MUL, false>(p, splits, stream);
         }
     } else {
         switch (d->epilogue) {
             case UWR_EPI_NONE: return launch<BN, false, false, UWR_EPI_NONE, false>(p, splits, stream);
             case UWR_EPI_RESID: return launch<BN, false, false, UWR_EPI_RESID, false>(p, splits, stream);
             case UWR_EPI_MUL_DGELU: return launch<BN, false, false, UWR_EPI_MUL_DGELU, false>(p, splits, stream);
+            case UWR_EPI_MUL: return launch<BN, false, false, UWR_EPI_MUL, false>(p, splits, stream);
         }
     }
     uwr_set_error("uwr_gemm_tf32: bad epilogue %d", d->epilogue);
@@ -369,13 +374,6 @@ int dispatch_layout(const uwr_gemm_desc* d, const GemmParams& p, int splits, cud
 }
 
 }  // namespace
-
-extern "C" int uwr_set_gemm_precision(int passes) {
-    UWR_REQUIRE(passes == 1 || passes == 3, "uwr_set_gemm_precision: passes must be 1 (tf32) or 3 (tf32x3)");
-    g_passes = passes;
-    return 0;
-}
-extern "C" int uwr_get_gemm_precision(void) { return g_passes; }
 
 extern "C" size_t uwr_gemm_workspace_bytes(int M, int N, int K, int a_km) {
     if (!a_km) return 0;

@@ -16,7 +16,7 @@ __global__ void __launch_bounds__(LN_WARPS * 32) ln_fwd_kernel(const float* __re
                                                                const float* __restrict__ beta,
                                                                float* __restrict__ y, float* __restrict__ mean,
                                                                float* __restrict__ rstd, long long rows, int C,
-                                                               float eps) {
+                                                               float eps, int rnd) {
     const int lane = threadIdx.x & 31;
     const int warp = threadIdx.x >> 5;
     float gm[VPL], bt[VPL];
@@ -50,7 +50,10 @@ __global__ void __launch_bounds__(LN_WARPS * 32) ln_fwd_kernel(const float* __re
 #pragma unroll
         for (int i = 0; i < VPL; ++i) {
             const int c = lane + 32 * i;
-            if (c < C) yr[c] = (v[i] - mu) * rs * gm[i] + bt[i];
+            if (c < C) {
+                const float o = (v[i] - mu) * rs * gm[i] + bt[i];
+                yr[c] = rnd ? tf32_round(o) : o;
+            }
         }
         if (lane == 0) {
             if (mean) mean[r] = mu;
@@ -155,7 +158,7 @@ extern "C" int uwr_layernorm_fwd(const float* x, const float* gamma, const float
     if (rows == 0) return 0;
     const int blocks = ln_blocks(rows);
     const int vpl = (C + 31) / 32;
-#define LN_FWD(V) ln_fwd_kernel<V><<<blocks, LN_WARPS * 32, 0, stream>>>(x, gamma, beta, y, mean, rstd, rows, C, eps)
+#define LN_FWD(V) ln_fwd_kernel<V><<<blocks, LN_WARPS * 32, 0, stream>>>(x, gamma, beta, y, mean, rstd, rows, C, eps, uwr_round_outputs())
     if (vpl <= 1) LN_FWD(1);
     else if (vpl <= 2) LN_FWD(2);
     else if (vpl <= 4) LN_FWD(4);

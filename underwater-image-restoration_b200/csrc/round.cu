@@ -1,0 +1,85 @@
+// TF32 operand preparation for the tcgen05 GEMM path (kind::tf32 truncates, so operands are
+// rounded to nearest once, where they are produced):
+//   uwr_round_tf32_tensors : multi-tensor copy (+ optional rounding) -> rounded weight copies,
+//                            also used to pack to_q|to_kv weights / biases contiguously
+//   uwr_scale_round        : d_s = tf32(rowscale * d)  (DropPath-scaled residual-stream gradient,
+//                            the A operand of the proj / linear2 data- and weight-gradient GEMMs)
+#include "uwr_common.cuh"
+#include "../../include/uwr_b200.h"
+
+namespace {
+
+__device__ __forceinline__ int rt_find(const long long* __restrict__ offsets, int n, long long i) {
+    int lo = 0, hi = n;
+    while (hi - lo > 1) {
+        const int mid = (lo + hi) >> 1;
+        if (offsets[mid] <= i) lo = mid;
+        else hi = mid;
+    }
+    return lo;
+}
+
+__global__ void __launch_bounds__(256) round_tensors_kernel(const float* const* __restrict__ src,
+                                                            float* const* __restrict__ dst,
+                                                            const long long* __restrict__ offsets, int n,
+                                                            long long total, int do_round) {
+    constexpr int CHUNK = 4096;
+    for (long long c0 = (long long)blockIdx.x * CHUNK; c0 < total; c0 += (long long)gridDim.x * CHUNK) {
+        const long long c1 = min(total, c0 + CHUNK);
+        long long i = c0 + threadIdx.x;
+        if (i >= c1) continue;
+        int t = rt_find(offsets, n, i);
+        for (; i < c1; i += 256) {
+            while (i >= offsets[t + 1]) ++t;
+            const float v = src[t][i - offsets[t]];
+            dst[t][i - offsets[t]] = do_round ? tf32_round(v) : v;
+        }
+    }
+}
+
+__global__ void __launch_bounds__(256) scale_round_kernel(const float* __restrict__ src, long long ld_src,
+                                                          float* __restrict__ dst, long long rows, int cols4,
+                                                          const float* __restrict__ rowscale, int rpg,
+                                                          int do_round) {
+    const long long total = rows * cols4;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total;
+         i += (long long)gridDim.x * blockDim.x) {
+        const long long r = i / cols4;
+        const int c = (int)(i % cols4) * 4;
+        float4 v = *reinterpret_cast<const float4*>(src + r * ld_src + c);
+        const float s = rowscale ? __ldg(rowscale + r / rpg) : 1.f;
+        v.x *= s; v.y *= s; v.z *= s; v.w *= s;
+        if (do_round) {
+            v.x = tf32_round(v.x); v.y = tf32_round(v.y); v.z = tf32_round(v.z); v.w = tf32_round(v.w);
+        }
+        reinterpret_cast<float4*>(dst)[i] = v;
+    }
+}
+
+}  // namespace
+
+extern "C" int uwr_round_tf32_tensors(const float* const* src, float* const* dst, const long long* offsets,
+                                      int n_tensors, long long total_elems, int do_round, uwr_stream_t stream_) {
+    cudaStream_t stream = (cudaStream_t)stream_;
+    UWR_REQUIRE(src && dst && offsets && n_tensors > 0, "uwr_round_tf32_tensors: bad args");
+    long long blocks = (total_elems + 4095) / 4096;
+    if (blocks > 8LL * uwr_sm_count()) blocks = 8LL * uwr_sm_count();
+    if (blocks < 1) blocks = 1;
+    round_tensors_kernel<<<(unsigned)blocks, 256, 0, stream>>>(src, dst, offsets, n_tensors, total_elems, do_round);
+    UWR_CHECK_LAUNCH("round_tensors_kernel");
+    return 0;
+}
+
+extern "C" int uwr_scale_round(const float* src, long long ld_src, float* dst, long long rows, int cols,
+                               const float* rowscale, int rows_per_group, int do_round, uwr_stream_t stream_) {
+    cudaStream_t stream = (cudaStream_t)stream_;
+    UWR_REQUIRE(src && dst && cols % 4 == 0 && ld_src % 4 == 0, "uwr_scale_round: cols/ld must be multiples of 4");
+    UWR_REQUIRE(!rowscale || rows_per_group > 0, "uwr_scale_round: rowscale needs rows_per_group");
+    if (rows == 0) return 0;
+    long long blocks = (rows * (cols / 4) + 255) / 256;
+    if (blocks > 16LL * uwr_sm_count()) blocks = 16LL * uwr_sm_count();
+    scale_round_kernel<<<(unsigned)blocks, 256, 0, stream>>>(src, ld_src, dst, rows, cols / 4, rowscale,
+                                                            rows_per_group > 0 ? rows_per_group : 1, do_round);
+    UWR_CHECK_LAUNCH("scale_round_kernel");
+    return 0;
+}

@@ -6,6 +6,7 @@
 
 static thread_local char g_err[512] = "";
 unsigned long long g_uwr_launches = 0;
+int g_uwr_gemm_passes = 1;  // 1: TF32 (operands rounded where produced), 3: 3xTF32 (fp32 operands)
 
 void uwr_set_error(const char* fmt, ...) {
     va_list ap;
@@ -29,3 +30,12 @@ extern "C" const char* uwr_last_error(void) { return g_err; }
 extern "C" int uwr_abi_version(void) { return 1; }
 extern "C" int uwr_device_sm_count(void) { return uwr_sm_count(); }
 extern "C" unsigned long long uwr_launch_count(void) { return g_uwr_launches; }
+extern "C" int uwr_set_gemm_precision(int passes) {
+    if (passes != 1 && passes != 3) {
+        uwr_set_error("uwr_set_gemm_precision: passes must be 1 (tf32) or 3 (tf32x3)");
+        return -1;
+    }
+    g_uwr_gemm_passes = passes;
+    return 0;
+}
+extern "C" int uwr_get_gemm_precision(void) { return g_uwr_gemm_passes; }

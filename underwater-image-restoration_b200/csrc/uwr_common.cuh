@@ -17,6 +17,9 @@ void uwr_set_error(const char* fmt, ...);
         }                                      \
     } while (0)
 
+extern int g_uwr_gemm_passes;
+// producers round GEMM-operand outputs to TF32 at their stores in single-pass mode
+static inline int uwr_round_outputs() { return g_uwr_gemm_passes == 1; }
 extern unsigned long long g_uwr_launches;  // kernels launched by this library (bench evidence)
 
 #define UWR_CHECK_LAUNCH(name)                                               \

@@ -31,6 +31,7 @@ struct AttnParams {
     int B, H, W, heads, shift;
     float scale;
     int nWx, nW;  // windows per row / per image
+    int rnd;      // round outputs to TF32 (they are GEMM operands)
 };
 
 __device__ __forceinline__ long long token_row(const AttnParams& p, int b, int wy, int wx, int n) {
@@ -241,7 +242,9 @@ __global__ void __launch_bounds__(ATT_THREADS) attn_fwd_kernel(const AttnParams 
         float* orow = out + rows[r0 + g + half * 8] * ld_out + h * HD;
 #pragma unroll
         for (int n = 0; n < HD / 8; ++n)
-            *reinterpret_cast<float2*>(orow + n * 8 + 2 * t) = make_float2(o[n][half * 2], o[n][half * 2 + 1]);
+            *reinterpret_cast<float2*>(orow + n * 8 + 2 * t) =
+                p.rnd ? make_float2(tf32_round(o[n][half * 2]), tf32_round(o[n][half * 2 + 1]))
+                      : make_float2(o[n][half * 2], o[n][half * 2 + 1]);
     }
 }
 
@@ -345,8 +348,11 @@ __global__ void __launch_bounds__(ATT_THREADS) attn_bwd_kernel(const AttnParams 
                 float* drow = dq_buf + rows[r0 + g + half * 8] * p.ld_q + p.q_off + h * HD;
 #pragma unroll
                 for (int n = 0; n < HD / 8; ++n)
+                {
+                    const float a = dq[n][half * 2] * p.scale, b = dq[n][half * 2 + 1] * p.scale;
                     *reinterpret_cast<float2*>(drow + n * 8 + 2 * t) =
-                        make_float2(dq[n][half * 2] * p.scale, dq[n][half * 2 + 1] * p.scale);
+                        p.rnd ? make_float2(tf32_round(a), tf32_round(b)) : make_float2(a, b);
+                }
             }
         }
         __syncthreads();  // Ps / dSs complete
@@ -387,7 +393,8 @@ __global__ void __launch_bounds__(ATT_THREADS) attn_bwd_kernel(const AttnParams 
 #pragma unroll
                 for (int n = 0; n < HD / 8; ++n)
                     *reinterpret_cast<float2*>(drow + n * 8 + 2 * t) =
-                        make_float2(acc[n][half * 2], acc[n][half * 2 + 1]);
+                        p.rnd ? make_float2(tf32_round(acc[n][half * 2]), tf32_round(acc[n][half * 2 + 1]))
+                              : make_float2(acc[n][half * 2], acc[n][half * 2 + 1]);
             }
         }
     }
@@ -478,6 +485,7 @@ int fill_params(const uwr_attn_desc* d, AttnParams& p, const char* who) {
     p.table = d->bias_table; p.w_param = d->w_param;
     p.B = d->B; p.H = d->H; p.W = d->W; p.heads = d->heads; p.shift = d->shift; p.scale = d->scale;
     p.nWx = d->W / WIN; p.nW = (d->H / WIN) * (d->W / WIN);
+    p.rnd = uwr_round_outputs();
     return 0;
 }
 

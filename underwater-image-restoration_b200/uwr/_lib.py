@@ -67,13 +67,19 @@ SIGNATURES = {
     "uwr_get_gemm_precision": (c_int, []),
     "uwr_gemm_workspace_bytes": (c_sz, [c_int, c_int, c_int, c_int]),
     "uwr_gemm_tf32": (c_int, [C.POINTER(GemmDesc), c_stream]),
+    "uwr_gemm_tcgen05": (c_int, [C.POINTER(GemmDesc), c_stream]),
+    "uwr_gemm_tcgen05_supported": (c_int, [C.POINTER(GemmDesc)]),
+    "uwr_gemm_tcgen05_workspace_bytes": (c_sz, [c_int, c_int, c_int, c_int]),
+    "uwr_round_tf32_tensors": (c_int, [c_fp, c_fp, c_fp, c_int, c_ll, c_int, c_stream]),
+    "uwr_scale_round": (c_int, [c_fp, c_ll, c_fp, c_ll, c_int, c_fp, c_int, c_int, c_stream]),
     "uwr_layernorm_fwd": (c_int, [c_fp, c_fp, c_fp, c_fp, c_fp, c_fp, c_ll, c_int, c_f, c_stream]),
     "uwr_layernorm_bwd_workspace_bytes": (c_sz, [c_ll, c_int]),
     "uwr_layernorm_bwd": (c_int, [c_fp] * 10 + [c_ll, c_int, c_stream]),
     "uwr_window_attn_fwd": (c_int, [C.POINTER(AttnDesc), c_fp, c_ll, c_stream]),
     "uwr_window_attn_bwd_workspace_bytes": (c_sz, [C.POINTER(AttnDesc)]),
     "uwr_window_attn_bwd": (c_int, [C.POINTER(AttnDesc), c_fp, c_ll, c_fp, c_fp, c_fp, c_fp, c_fp, c_stream]),
-    "uwr_dwconv_gelu_fwd": (c_int, [c_fp, c_ll, c_fp, c_fp, c_fp, c_fp, c_int, c_int, c_int, c_int, c_int, c_stream]),
+    "uwr_dwconv_gelu_fwd": (c_int, [c_fp, c_ll, c_fp, c_fp, c_fp, c_fp, c_int, c_int, c_int, c_int, c_int, c_int,
+                                    c_stream]),
     "uwr_dwconv_gelu_bwd_workspace_bytes": (c_sz, [c_int, c_int, c_int, c_int]),
     "uwr_dwconv_gelu_bwd": (c_int, [c_fp, c_fp, c_ll, c_fp, c_fp, c_fp, c_fp, c_fp,
                                     c_int, c_int, c_int, c_int, c_stream]),

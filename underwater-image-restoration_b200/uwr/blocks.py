@@ -70,8 +70,8 @@ class DownsampleFn(torch.autograd.Function):
         Cout = weight.shape[0]
         # (Cout, Cin, 4, 4) -> (Cout, 4, 4, Cin): K index = (ky, kx, ci) matches the im2col rows
         wmat = weight.permute(0, 2, 3, 1).reshape(Cout, 16 * Cc)
-        col = ops.im2col_4x4s2(x.view(B * L, Cc), B, H, W, Cc)
-        y = ops.linear(col, wmat, bias)
+        col = ops.im2col_4x4s2(x.view(B * L, Cc), B, H, W, Cc)  # TF32-rounded at the store in tf32 mode
+        y = ops.linear(col, ops.scale_round(wmat, 16 * Cc), bias, t5=True)
         ctx.save_for_backward(x, wmat)
         ctx.dims = (B, H, W, Cc, Cout)
         return y.view(B, L // 4, Cout)
@@ -136,6 +136,20 @@ class UpsampleCatFn(torch.autograd.Function):
         return dx.view(B, L, Cin), dwmat.view_as(weight), dbias, dskip, None, None
 
 
+def _qkv_forward(y1, wq, bq, wkv, bkv):
+    if ops.fast_path():
+        w, b = ops.packed_qkv(wq, bq, wkv, bkv)
+        return ops.linear(y1, w, b, t5=True)
+    return ops.linear(y1, wq, bq, weight2=wkv, bias2=bkv)
+
+
+def _qkv_dgrad(dqkv, wq, bq, wkv, bkv):
+    if ops.fast_path():
+        w, _ = ops.packed_qkv(wq, bq, wkv, bkv)
+        return ops.linear_dgrad(dqkv, w, t5=True)
+    return ops.linear_dgrad(dqkv, wq, weight2=wkv)
+
+
 class AttnBlockFn(torch.autograd.Function):
     @staticmethod
     def forward(ctx, x, n1w, n1b, wq, bq, wkv, bkv, table, wparam, wp, bp, dp_scale, H, W, heads, shift, scale):
@@ -145,30 +159,35 @@ class AttnBlockFn(torch.autograd.Function):
         x2 = x.view(M, Cc)
         hd = Cc // heads
         y1, mean, rstd = ops.layernorm_fwd(x2, n1w, n1b)
-        qkv = ops.linear(y1, wq, bq, weight2=wkv, bias2=bkv)
+        qkv = _qkv_forward(y1, wq, bq, wkv, bkv)
         o = ops.window_attn_fwd(qkv, 0, qkv, Cc, 2 * Cc, table, wparam, B, H, W, heads, hd, shift, scale)
-        x1 = ops.linear(o, wp, bp, residual=x2, rowscale=dp_scale, rows_per_group=L)
-        ctx.save_for_backward(x2, n1w, mean, rstd, y1, qkv, o, wq, wkv, table, wparam, wp, dp_scale)
-        ctx.meta = (B, L, Cc, H, W, heads, hd, shift, scale, bq is not None)
+        x1 = ops.linear(o, ops.rounded_weight(wp), bp, residual=x2, rowscale=dp_scale, rows_per_group=L, t5=True)
+        ctx.save_for_backward(x2, n1w, mean, rstd, y1, qkv, o, wq, bq, wkv, bkv, table, wparam, wp, dp_scale)
+        ctx.meta = (B, L, Cc, H, W, heads, hd, shift, scale)
         return x1.view(B, L, Cc)
 
     @staticmethod
     @once_differentiable
     def backward(ctx, dx1):
-        x2, n1w, mean, rstd, y1, qkv, o, wq, wkv, table, wparam, wp, dp = ctx.saved_tensors
-        B, L, Cc, H, W, heads, hd, shift, scale, has_qkv_bias = ctx.meta
+        x2, n1w, mean, rstd, y1, qkv, o, wq, bq, wkv, bkv, table, wparam, wp, dp = ctx.saved_tensors
+        B, L, Cc, H, W, heads, hd, shift, scale = ctx.meta
         d = _c(dx1).view(B * L, Cc)
-        d_o = ops.linear_dgrad(d, wp, rowscale=dp, rows_per_group=L)
-        dwp, dbp = ops.linear_wgrad(d, o, rowscale=dp, rows_per_group=L)
+        # DropPath-scaled (and, in tf32 mode, TF32-rounded) branch gradient: operand of three GEMMs
+        d_s = ops.scale_round(d, Cc, dp, L)
+        d_o = ops.linear_dgrad(d_s, ops.rounded_weight(wp), t5=True)
+        dwp, _ = ops.linear_wgrad(d_s, o, want_bias=False, t5=True)
+        dbp = ops.colsum(d_s, Cc)
+        del d_s
         dqkv, _, dtable, dw = ops.window_attn_bwd(d_o, qkv, 0, qkv, Cc, 2 * Cc, table, wparam, B, H, W, heads, hd,
                                                   shift, scale)
         del d_o
-        dy1 = ops.linear_dgrad(dqkv, wq, weight2=wkv)
-        dwqkv, dbqkv = ops.linear_wgrad(dqkv, y1, want_bias=has_qkv_bias)
+        dy1 = _qkv_dgrad(dqkv, wq, bq, wkv, bkv)
+        dwqkv, _ = ops.linear_wgrad(dqkv, y1, want_bias=False, t5=True)
+        dbqkv = ops.colsum(dqkv, 3 * Cc) if bq is not None else None
         del dqkv
         dx, dg, db = ops.layernorm_bwd(dy1, x2, n1w, mean, rstd, dres=d)
-        dbq = dbqkv[:Cc] if has_qkv_bias else None
-        dbkv = dbqkv[Cc:] if has_qkv_bias else None
+        dbq = dbqkv[:Cc] if bq is not None else None
+        dbkv = dbqkv[Cc:] if bq is not None else None
         return (dx.view(B, L, Cc), dg, db, dwqkv[:Cc], dbq, dwqkv[Cc:], dbkv, dtable,
                 dw if wparam is not None else None, dwp, dbp, None, None, None, None, None, None)
 
@@ -182,10 +201,11 @@ class LeFFBlockFn(torch.autograd.Function):
         Ch = w1.shape[0]
         x2 = x.view(M, Cc)
         y2, mean, rstd = ops.layernorm_fwd(x2, n2w, n2b)
-        u = ops.linear(y2, w1, b1)
+        u = ops.linear(y2, ops.rounded_weight(w1), b1, t5=True)
         need_bwd = any(ctx.needs_input_grad)
-        v, h2 = ops.dwconv_gelu_fwd(u, dww, dwb, B, H, W, Ch, mode=0, save_v=need_bwd)
-        out = ops.linear(h2, w2, b2, residual=x2, rowscale=dp_scale, rows_per_group=L)
+        # the conv pre-activation v is only ever needed as gelu'(v): store that instead
+        v, h2 = ops.dwconv_gelu_fwd(u, dww, dwb, B, H, W, Ch, mode=0, save_v=need_bwd, v_is_dgelu=True)
+        out = ops.linear(h2, ops.rounded_weight(w2), b2, residual=x2, rowscale=dp_scale, rows_per_group=L, t5=True)
         if need_bwd:
             ctx.save_for_backward(x2, n2w, mean, rstd, y2, u, v, h2, w1, dww, w2, dp_scale)
         ctx.meta = (B, L, Cc, Ch, H, W)
@@ -197,13 +217,18 @@ class LeFFBlockFn(torch.autograd.Function):
         x2, n2w, mean, rstd, y2, u, v, h2, w1, dww, w2, dp = ctx.saved_tensors
         B, L, Cc, Ch, H, W = ctx.meta
         d = _c(dout).view(B * L, Cc)
-        # dv = (s*d W2) * gelu'(v): the second GELU's derivative rides in the GEMM epilogue
-        dv = ops.linear_dgrad(d, w2, rowscale=dp, rows_per_group=L, dgelu_of=v)
-        dw2, db2 = ops.linear_wgrad(d, h2, rowscale=dp, rows_per_group=L)
+        d_s = ops.scale_round(d, Cc, dp, L)
+        # dv = (d_s W2) * gelu'(v): the second GELU's derivative (saved by the forward) rides in the
+        # GEMM epilogue
+        dv = ops.linear_dgrad(d_s, ops.rounded_weight(w2), mul_by=v, t5=True)
+        dw2, _ = ops.linear_wgrad(d_s, h2, want_bias=False, t5=True)
+        db2 = ops.colsum(d_s, Cc)
+        del d_s
         du, ddww, ddwb = ops.dwconv_gelu_bwd(dv, u, dww, B, H, W, Ch)
         del dv
-        dy2 = ops.linear_dgrad(du, w1)
-        dw1, db1 = ops.linear_wgrad(du, y2)
+        dy2 = ops.linear_dgrad(du, ops.rounded_weight(w1), t5=True)
+        dw1, _ = ops.linear_wgrad(du, y2, want_bias=False, t5=True)
+        db1 = ops.colsum(du, Ch)
         del du
         dx, dg, db = ops.layernorm_bwd(dy2, x2, n2w, mean, rstd, dres=d)
         return dx.view(B, L, Cc), dg, db, dw1, db1, ddww, ddwb, dw2, db2, None, None, None

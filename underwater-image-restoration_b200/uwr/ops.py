@@ -11,12 +11,29 @@ import torch
 from . import _lib
 from ._lib import AttnDesc, GemmDesc, check, fn
 
-EPI_NONE, EPI_RESID, EPI_MUL_DGELU = 0, 1, 2
+EPI_NONE, EPI_RESID, EPI_MUL_DGELU, EPI_MUL = 0, 1, 2, 3
+
+
+_PASSES = 1
+WEIGHT_EPOCH = 0  # bumped by optimizers that update parameters behind torch's version counter
 
 
 def set_gemm_precision(mode):
-    """"tf32" (default: one TF32 product, fp32 accumulate) or "tf32x3" (error-compensated, fp32-level)."""
-    check(fn["uwr_set_gemm_precision"]({"tf32": 1, "tf32x3": 3}[mode]), "uwr_set_gemm_precision")
+    """"tf32" (default: one TF32 product, fp32 accumulate; GEMM operands are rounded where they are
+    produced and the Linear layers run on the tcgen05 path) or "tf32x3" (error-compensated 3xTF32 on
+    full fp32 operands, fp32-level accuracy, legacy mma.sync kernel)."""
+    global _PASSES
+    _PASSES = {"tf32": 1, "tf32x3": 3}[mode]
+    check(fn["uwr_set_gemm_precision"](_PASSES), "uwr_set_gemm_precision")
+
+
+def fast_path():
+    return _PASSES == 1
+
+
+def bump_weight_epoch():
+    global WEIGHT_EPOCH
+    WEIGHT_EPOCH += 1
 
 
 def launch_count():
@@ -96,8 +113,9 @@ def _ws(nbytes, like):
 # --------------------------------------------------------------------------------------------
 def gemm(A, B, C_out, M, N, K, *, lda, ldb, ldc, a_km=False, b_nk=True, B2=None, n_split=0,
          bias=None, bias2=None, epilogue=EPI_NONE, R=None, ldr=0, rowscale=None, rows_per_group=0,
-         colsum=None):
-    """C[M,N] = epi(opA(A) opB(B)); see uwr_gemm_tf32 in include/uwr_b200.h."""
+         colsum=None, t5=False):
+    """C[M,N] = epi(opA(A) opB(B)); see uwr_gemm_tf32 in include/uwr_b200.h.  t5=True: the operands are
+    TF32-rounded already, use the tcgen05/TMA kernel when the descriptor is supported."""
     d = GemmDesc()
     d.A, d.lda, d.a_km = _ptr(A), lda, int(a_km)
     d.B, d.ldb, d.b_nk = _ptr(B), ldb, int(b_nk)
@@ -109,20 +127,27 @@ def gemm(A, B, C_out, M, N, K, *, lda, ldb, ldc, a_km=False, b_nk=True, B2=None,
     d.R, d.ldr = _ptr(R), ldr
     d.rowscale, d.rows_per_group = _ptr(rowscale), rows_per_group
     d.colsum = _ptr(colsum)
-    ws = None
-    if a_km:
-        nbytes = fn["uwr_gemm_workspace_bytes"](M, N, K, 1)
-        if nbytes:
-            ws = _ws(nbytes, A)
-            d.workspace, d.workspace_bytes = ws.data_ptr(), nbytes
     nbytes = 4 * (M * K + K * N + M * N + (M * N if R is not None else 0))
     lay = ("TN" if a_km else ("NT" if b_nk else "NN"))
+    ws = None
+    if t5 and _PASSES == 1 and fn["uwr_gemm_tcgen05_supported"](C.byref(d)):
+        wbytes = fn["uwr_gemm_tcgen05_workspace_bytes"](M, N, K, int(a_km))
+        if wbytes:
+            ws = _ws(wbytes, A)
+            d.workspace, d.workspace_bytes = ws.data_ptr(), wbytes
+        _run("uwr_gemm_tcgen05", f"{lay} M{M} N{N} K{K} epi{epilogue}", nbytes, 2.0 * M * N * K, C.byref(d))
+        return C_out
+    if a_km:
+        wbytes = fn["uwr_gemm_workspace_bytes"](M, N, K, 1)
+        if wbytes:
+            ws = _ws(wbytes, A)
+            d.workspace, d.workspace_bytes = ws.data_ptr(), wbytes
     _run("uwr_gemm_tf32", f"{lay} M{M} N{N} K{K} epi{epilogue}", nbytes, 2.0 * M * N * K, C.byref(d))
     return C_out
 
 
 def linear(x2d, weight, bias=None, *, weight2=None, bias2=None, residual=None, rowscale=None,
-           rows_per_group=0, out=None):
+           rows_per_group=0, out=None, t5=False):
     """y = x W^T + b  (optionally [W;W2], optionally residual + s*(.)). x2d: (M,K) view, row stride lda."""
     M, K = x2d.shape
     lda = x2d.stride(0)
@@ -133,12 +158,14 @@ def linear(x2d, weight, bias=None, *, weight2=None, bias2=None, residual=None, r
     gemm(x2d, weight, out, M, N, K, lda=lda, ldb=weight.stride(0), ldc=out.stride(0), b_nk=True,
          B2=weight2, n_split=weight.shape[0] if weight2 is not None else 0, bias=bias, bias2=bias2,
          epilogue=epi, R=residual, ldr=residual.stride(0) if residual is not None else 0,
-         rowscale=rowscale, rows_per_group=rows_per_group)
+         rowscale=rowscale, rows_per_group=rows_per_group, t5=t5)
     return out
 
 
-def linear_dgrad(dy2d, weight, *, weight2=None, rowscale=None, rows_per_group=0, out=None, dgelu_of=None):
-    """dx = (s*dy) [W;W2]   (dy: (M,N), W: (N1,K), W2: (N2,K)); dgelu_of=v multiplies by gelu'(v)."""
+def linear_dgrad(dy2d, weight, *, weight2=None, rowscale=None, rows_per_group=0, out=None, dgelu_of=None,
+                 mul_by=None, t5=False):
+    """dx = (s*dy) [W;W2]   (dy: (M,N), W: (N1,K), W2: (N2,K)); dgelu_of=v multiplies by gelu'(v),
+    mul_by=g multiplies elementwise by g (a stored gelu'(v))."""
     M, N = dy2d.shape
     K = weight.shape[1]
     if out is None:
@@ -146,20 +173,72 @@ def linear_dgrad(dy2d, weight, *, weight2=None, rowscale=None, rows_per_group=0,
     gemm(dy2d, weight, out, M, K, N, lda=dy2d.stride(0), ldb=weight.stride(0), ldc=out.stride(0),
          b_nk=False, B2=weight2, n_split=weight.shape[0] if weight2 is not None else 0,
          rowscale=rowscale, rows_per_group=rows_per_group,
-         epilogue=EPI_MUL_DGELU if dgelu_of is not None else EPI_NONE, R=dgelu_of,
-         ldr=dgelu_of.stride(0) if dgelu_of is not None else 0)
+         epilogue=EPI_MUL_DGELU if dgelu_of is not None else (EPI_MUL if mul_by is not None else EPI_NONE),
+         R=dgelu_of if dgelu_of is not None else mul_by,
+         ldr=(dgelu_of if dgelu_of is not None else mul_by).stride(0) if (dgelu_of is not None or mul_by is not None) else 0,
+         t5=t5)
     return out
 
 
-def linear_wgrad(dy2d, x2d, *, want_bias=True, rowscale=None, rows_per_group=0):
+def linear_wgrad(dy2d, x2d, *, want_bias=True, rowscale=None, rows_per_group=0, t5=False):
     """dW[N,K] = (s*dy)^T x ; db[N] = colsum(s*dy).  dy: (M,N) view, x: (M,K) view."""
     M, N = dy2d.shape
     K = x2d.shape[1]
     dW = _empty((N, K), dy2d)
     db = _empty((N,), dy2d) if want_bias else None
     gemm(dy2d, x2d, dW, N, K, M, lda=dy2d.stride(0), ldb=x2d.stride(0), ldc=K, a_km=True, b_nk=False,
-         rowscale=rowscale, rows_per_group=rows_per_group, colsum=db)
+         rowscale=rowscale, rows_per_group=rows_per_group, colsum=db, t5=t5)
     return dW, db
+
+
+# --------------------------------------------------------------------------------------------
+def scale_round(src2d, cols, rowscale=None, rows_per_group=0, out=None):
+    """dense (rows, cols) copy of src2d[:, :cols] scaled per sample and, in tf32 mode, rounded to TF32."""
+    rows = src2d.shape[0]
+    if out is None:
+        out = _empty((rows, cols), src2d)
+    _run("uwr_scale_round", f"rows{rows} C{cols}", 8 * rows * cols, 0.0, _ptr(src2d), src2d.stride(0), _ptr(out),
+         rows, cols, _ptr(rowscale), rows_per_group, int(_PASSES == 1))
+    return out
+
+
+def _fresh(w, tag):
+    ent = getattr(w, tag, None)
+    ver = (w.data_ptr(), w._version, WEIGHT_EPOCH, _PASSES)
+    return ent, ver
+
+
+def rounded_weight(w):
+    """TF32-rounded copy of a weight matrix (cached on the tensor object, refreshed when the parameter
+    changes); the weight itself in tf32x3 mode."""
+    if _PASSES != 1:
+        return w
+    ent, ver = _fresh(w, "_uwr_rounded")
+    if ent is None or ent[0] != ver:
+        buf = ent[1] if ent is not None and ent[1].shape == w.shape and ent[1].device == w.device else torch.empty_like(w)
+        wd = w.detach()
+        scale_round(wd.reshape(-1, wd.shape[-1]) if wd.dim() > 1 else wd.reshape(1, -1), wd.shape[-1],
+                    out=buf.view(-1, wd.shape[-1]) if wd.dim() > 1 else buf.view(1, -1))
+        w._uwr_rounded = ent = (ver, buf)
+    return ent[1]
+
+
+def packed_qkv(wq, bq, wkv, bkv):
+    """[to_q; to_kv] as one (3C, C) TF32-rounded matrix + packed bias (AST.py:47-48,59-60), cached."""
+    ent, ver = _fresh(wq, "_uwr_qkv")
+    ver = ver + (wkv.data_ptr(), wkv._version, None if bq is None else (bq._version, bkv._version))
+    if ent is None or ent[0] != ver:
+        Cq, K = wq.shape
+        buf = ent[1] if ent is not None else _empty((3 * Cq, K), wq)
+        scale_round(wq.detach(), K, out=buf[:Cq])
+        scale_round(wkv.detach(), K, out=buf[Cq:])
+        bias = None
+        if bq is not None:
+            bias = ent[2] if ent is not None and ent[2] is not None else _empty((3 * Cq,), wq)
+            _run("uwr_scale_round", "bias", 0, 0.0, _ptr(bq.detach()), Cq, _ptr(bias), 1, Cq, None, 0, 0)
+            _run("uwr_scale_round", "bias", 0, 0.0, _ptr(bkv.detach()), 2 * Cq, _ptr(bias[Cq:]), 1, 2 * Cq, None, 0, 0)
+        wq._uwr_qkv = ent = (ver, buf, bias)
+    return ent[1], ent[2]
 
 
 # --------------------------------------------------------------------------------------------
@@ -223,12 +302,13 @@ def window_attn_bwd(dout, q_buf, q_off, kv_buf, k_off, v_off, table, w_param, B,
 
 
 # --------------------------------------------------------------------------------------------
-def dwconv_gelu_fwd(u2d, weight, bias, B, H, W, Ch, mode=0, save_v=True):
+def dwconv_gelu_fwd(u2d, weight, bias, B, H, W, Ch, mode=0, save_v=True, v_is_dgelu=False):
+    """Returns (v or gelu'(v), h2)."""
     v = _empty((B * H * W, Ch), u2d) if save_v else None
     h2 = _empty((B * H * W, Ch), u2d)
     n = B * H * W * Ch
     _run("uwr_dwconv_gelu_fwd", f"B{B} H{H} Ch{Ch} mode{mode}", 4 * n * ((2 if mode else 1) + (2 if save_v else 1)),
-         18.0 * n, _ptr(u2d), u2d.stride(0), _ptr(weight), _ptr(bias), _ptr(v), _ptr(h2), B, H, W, Ch, mode)
+         18.0 * n, _ptr(u2d), u2d.stride(0), _ptr(weight), _ptr(bias), _ptr(v), _ptr(h2), B, H, W, Ch, mode, int(v_is_dgelu))
     return v, h2
 
 

@@ -68,4 +68,6 @@ class FusedClipAdam:
                                   float(self.grad_prescale), float(self.lr), float(self.betas[0]),
                                   float(self.betas[1]), float(self.eps), float(self.weight_decay),
                                   int(self.decoupled), 0, self._step_dev.data_ptr(), stream), "uwr_adam_step")
+        from . import ops
+        ops.bump_weight_epoch()  # parameters changed behind torch's version counter: refresh rounded copies
         return self._norm
