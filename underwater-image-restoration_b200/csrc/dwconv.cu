@@ -91,9 +91,9 @@ __global__ void __launch_bounds__(DW_THREADS) dwconv_fwd_kernel(const float* __r
                 for (int ky = 0; ky < 3; ++ky)
 #pragma unroll
                     for (int kx = 0; kx < 3; ++kx) acc = fmaf(win[ky][kx], wgt[ky * 3 + kx], acc);
-                const float cdf = 0.5f * (1.0f + erff(acc * 0.70710678118654752440f));
-                if (v) v[(tok0 + lx) * Ch + c] =
-                           v_is_dgelu ? cdf + acc * 0.39894228040143267794f * __expf(-0.5f * acc * acc) : acc;
+                float cdf, pdf;
+                gelu_parts(acc, cdf, pdf);
+                if (v) v[(tok0 + lx) * Ch + c] = v_is_dgelu ? fmaf(acc, pdf, cdf) : acc;
                 float o = acc * cdf;
                 if (mode == 1) o *= gelu_f(gate[lx]);
                 h2[(tok0 + lx) * Ch + c] = rnd ? tf32_round(o) : o;
@@ -193,8 +193,8 @@ __global__ void __launch_bounds__(DW_THREADS) dwconv_bwd_kernel(const float* __r
                     }
                     if (tx0 + lx < W) {
                         const float x = uc[lx];
-                        const float cdf = 0.5f * (1.0f + erff(x * 0.70710678118654752440f));
-                        const float pdf = 0.39894228040143267794f * __expf(-0.5f * x * x);
+                        float cdf, pdf;
+                        gelu_parts(x, cdf, pdf);
                         const float h1 = x * cdf;
                         float dh1 = 0.f;
                         // v[q] = sum_k h1[q + k - 1] w[k]  =>  h1[p] meets dv[p + 1 - k] with weight w[k]

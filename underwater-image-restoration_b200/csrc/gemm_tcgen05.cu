@@ -25,7 +25,7 @@ namespace {
 
 constexpr int TM = 128;      // CTA tile rows (UMMA M)
 constexpr int KC = 32;       // contraction chunk: 32 fp32 = one 128-byte swizzle row
-constexpr int STAGES = 4;
+constexpr int EP_STRIDE = 36;  // fp32 words per staged epilogue row (32 + 4: conflict-free float4 access)
 constexpr int EPI_WARPS = 8;   // two warps per TMEM lane quadrant, interleaved over 32-column chunks
 constexpr int T5_THREADS = 64 + EPI_WARPS * 32;
 constexpr uint32_t SPIN_LIMIT = 1u << 24;
@@ -137,10 +137,18 @@ __device__ __forceinline__ void tmem_ld32_issue(uint32_t taddr, uint32_t (&r)[32
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
 // -------------------------------------------------------------------------------------- kernel
+template <int BN>
+__host__ __device__ constexpr int t5_stages() { return BN >= 256 ? 3 : 4; }
+template <int BN>
+__host__ __device__ constexpr int t5_smem_bytes() {
+    return t5_stages<BN>() * (TM * KC * 4 + BN * KC * 4) + 256 + BN * 4 + EPI_WARPS * 32 * EP_STRIDE * 4 + 1024;
+}
+
 template <int BN, int LAY>
 __global__ void __launch_bounds__(T5_THREADS, 1)
 gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapB,
                     const T5Params p) {
+    constexpr int STAGES = t5_stages<BN>();
     constexpr bool A_MN = (LAY == LAY_TN);
     constexpr bool B_MN = (LAY != LAY_NT);
     constexpr int A_BYTES = TM * KC * 4;  // 16 KB
@@ -159,6 +167,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_const
     uint64_t* tempty_bar = tfull_bar + 2;      // [2] accumulator drained
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty_bar + 2);
     float* sbias = reinterpret_cast<float*>(smem + STAGES * STAGE_BYTES + 256);  // [BN]
+    float* sstage = sbias + BN;  // [EPI_WARPS][32][EP_STRIDE] accumulator transposition buffers
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int items = p.tiles_m * p.tiles_n * p.splits;
@@ -286,12 +295,20 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_const
                 asm volatile("bar.sync 1, %0;" ::"n"(EPI_WARPS * 32) : "memory");
             }
             cur_tn = tn;
-            const int row = tm * TM + q * 32 + lane;
-            const bool row_ok = row < p.M;
-            float* crow = p.C + (long long)z * p.split_stride + (long long)row * p.ldc;
-            const float* rrow = p.R + (long long)row * p.ldr;
-            float s = 1.f;
-            if (p.rowscale != nullptr && row_ok) s = __ldg(p.rowscale + row / p.rows_per_group);
+            // Accumulator rows arrive one per lane (TMEM lane = tile row).  They are transposed through
+            // a per-warp smem buffer so that every global access of the epilogue (C stores, R loads)
+            // covers 4 rows x 128 contiguous bytes per warp instruction instead of 32 rows x 16 bytes.
+            float* st = sstage + (warp - 2) * (32 * EP_STRIDE);
+            const int rsub = lane >> 3;        // row within a group of 4
+            const int cc = (lane & 7) * 4;     // column offset of this lane's float4
+            const int row0 = tm * TM + q * 32;
+            float sc[8];
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+                const int row = row0 + i * 4 + rsub;
+                sc[i] = (p.rowscale != nullptr && row < p.M) ? __ldg(p.rowscale + row / p.rows_per_group) : 1.f;
+            }
+            float* cbase = p.C + (long long)z * p.split_stride;
             mbar_wait(&tfull_bar[buf], use & 1);
             tc_fence_after();
             const uint32_t tbase = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(buf * BN);
@@ -302,43 +319,49 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_const
             for (int ci = 0; ci < NCH; ++ci) {
                 const int c0 = (2 * ci + half) * 32;
                 if (c0 >= BN) break;
-                const int col0 = tn * BN + c0;
-                const bool live = row_ok && col0 < p.N;
+                const int col = tn * BN + c0 + cc;
+                const bool col_ok = col < p.N;  // N is a multiple of 4
                 // operand of the epilogue (residual / multiplier): issue the loads before waiting on TMEM
                 float4 rv[8];
-                if (p.epilogue != UWR_EPI_NONE && live) {
+                if (p.epilogue != UWR_EPI_NONE) {
 #pragma unroll
-                    for (int j = 0; j < 8; ++j)
-                        rv[j] = (col0 + 4 * j < p.N) ? *reinterpret_cast<const float4*>(rrow + col0 + 4 * j)
-                                                     : make_float4(0.f, 0.f, 0.f, 0.f);
-                }
-                tmem_ld_wait();
-                const int cn = c0 + 64;
-                if (ci + 1 < NCH && cn < BN) tmem_ld32_issue(tbase + cn, acc[(ci + 1) & 1]);  // next chunk in flight
-                if (live) {
-                    const uint32_t* a = acc[ci & 1];
-#pragma unroll
-                    for (int j = 0; j < 8; ++j) {
-                        const int col = col0 + 4 * j;
-                        if (col >= p.N) break;  // N is a multiple of 4
-                        float4 o = make_float4(__uint_as_float(a[4 * j]), __uint_as_float(a[4 * j + 1]),
-                                               __uint_as_float(a[4 * j + 2]), __uint_as_float(a[4 * j + 3]));
-                        if (p.bias != nullptr) {
-                            const float4 b = *reinterpret_cast<const float4*>(sbias + c0 + 4 * j);
-                            o.x += b.x; o.y += b.y; o.z += b.z; o.w += b.w;
-                        }
-                        o.x *= s; o.y *= s; o.z *= s; o.w *= s;
-                        if (p.epilogue == UWR_EPI_RESID) {
-                            o.x += rv[j].x; o.y += rv[j].y; o.z += rv[j].z; o.w += rv[j].w;
-                        } else if (p.epilogue == UWR_EPI_MUL) {
-                            o.x *= rv[j].x; o.y *= rv[j].y; o.z *= rv[j].z; o.w *= rv[j].w;
-                        } else if (p.epilogue == UWR_EPI_MUL_DGELU) {
-                            o.x *= gelu_grad_f(rv[j].x); o.y *= gelu_grad_f(rv[j].y);
-                            o.z *= gelu_grad_f(rv[j].z); o.w *= gelu_grad_f(rv[j].w);
-                        }
-                        *reinterpret_cast<float4*>(crow + col) = o;
+                    for (int i = 0; i < 8; ++i) {
+                        const int row = row0 + i * 4 + rsub;
+                        rv[i] = (col_ok && row < p.M) ? *reinterpret_cast<const float4*>(p.R + (long long)row * p.ldr + col)
+                                                      : make_float4(0.f, 0.f, 0.f, 0.f);
                     }
                 }
+                float4 b4 = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (p.bias != nullptr) b4 = *reinterpret_cast<const float4*>(sbias + c0 + cc);
+                tmem_ld_wait();
+                {
+                    const uint32_t* a = acc[ci & 1];
+#pragma unroll
+                    for (int j = 0; j < 8; ++j)
+                        *reinterpret_cast<uint4*>(st + lane * EP_STRIDE + 4 * j) =
+                            make_uint4(a[4 * j], a[4 * j + 1], a[4 * j + 2], a[4 * j + 3]);
+                }
+                const int cn = c0 + 64;
+                if (ci + 1 < NCH && cn < BN) tmem_ld32_issue(tbase + cn, acc[(ci + 1) & 1]);  // next chunk in flight
+                __syncwarp();
+#pragma unroll
+                for (int i = 0; i < 8; ++i) {
+                    const int rr = i * 4 + rsub;
+                    const int row = row0 + rr;
+                    float4 o = *reinterpret_cast<const float4*>(st + rr * EP_STRIDE + cc);
+                    o.x = (o.x + b4.x) * sc[i]; o.y = (o.y + b4.y) * sc[i];
+                    o.z = (o.z + b4.z) * sc[i]; o.w = (o.w + b4.w) * sc[i];
+                    if (p.epilogue == UWR_EPI_RESID) {
+                        o.x += rv[i].x; o.y += rv[i].y; o.z += rv[i].z; o.w += rv[i].w;
+                    } else if (p.epilogue == UWR_EPI_MUL) {
+                        o.x *= rv[i].x; o.y *= rv[i].y; o.z *= rv[i].z; o.w *= rv[i].w;
+                    } else if (p.epilogue == UWR_EPI_MUL_DGELU) {
+                        o.x *= gelu_grad_f(rv[i].x); o.y *= gelu_grad_f(rv[i].y);
+                        o.z *= gelu_grad_f(rv[i].z); o.w *= gelu_grad_f(rv[i].w);
+                    }
+                    if (col_ok && row < p.M) *reinterpret_cast<float4*>(cbase + (long long)row * p.ldc + col) = o;
+                }
+                __syncwarp();  // the staging buffer is reused by the next chunk
             }
             tc_fence_before();
             __syncwarp();
@@ -437,7 +460,7 @@ T5Split t5_plan(int M, int N, int Kc, int lay, int bn) {
 
 template <int BN, int LAY>
 int t5_launch(const CUtensorMap& ma, const CUtensorMap& mb, const T5Params& p, cudaStream_t stream) {
-    constexpr int smem = STAGES * (TM * KC * 4 + BN * KC * 4) + 1024 + 256 + BN * 4;
+    constexpr int smem = t5_smem_bytes<BN>();
     auto kern = gemm_tcgen05_kernel<BN, LAY>;
     static bool configured = false;
     if (!configured) {

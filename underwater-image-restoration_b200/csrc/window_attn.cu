@@ -252,7 +252,7 @@ __global__ void __launch_bounds__(ATT_THREADS) attn_fwd_kernel(const AttnParams 
 // Backward.  grid = (ctas_per_head, heads); each CTA walks the (batch, window) tiles of one head
 // so that the relative-position-bias gradient accumulates in registers and is binned once.
 template <int HD>
-__global__ void __launch_bounds__(ATT_THREADS) attn_bwd_kernel(const AttnParams p, const float* __restrict__ dout,
+__global__ void __launch_bounds__(ATT_THREADS, HD <= 32 ? 2 : 1) attn_bwd_kernel(const AttnParams p, const float* __restrict__ dout,
                                                                long long ld_dout, float* __restrict__ dq_buf,
                                                                float* __restrict__ dkv_buf,
                                                                float* __restrict__ partials) {
@@ -264,7 +264,8 @@ __global__ void __launch_bounds__(ATT_THREADS) attn_bwd_kernel(const AttnParams 
     float* dOs = Vs + NTOK * ST;
     float* Ps = dOs + NTOK * ST;
     float* dSs = Ps + NTOK * PS_STRIDE;
-    float* tab = dSs + NTOK * PS_STRIDE;
+    float* dSacc = dSs + NTOK * PS_STRIDE;  // running sum of dS over this CTA's tiles (bias-table gradient)
+    float* tab = dSacc + NTOK * PS_STRIDE;
     int* reg = reinterpret_cast<int*>(tab + 228);
     long long* rows = reinterpret_cast<long long*>(reg + NTOK);
     __shared__ float red[2][ATT_THREADS / 32];
@@ -278,11 +279,12 @@ __global__ void __launch_bounds__(ATT_THREADS) attn_bwd_kernel(const AttnParams 
     float w0, w1;
     fusion_weights(p.w_param, w0, w1);
 
-    float dsacc[8][4];
+    // each thread owns fixed (i, j) slots of the dS accumulator, so plain read-modify-write is safe
 #pragma unroll
-    for (int nt = 0; nt < 8; ++nt)
+    for (int half = 0; half < 2; ++half)
 #pragma unroll
-        for (int c = 0; c < 4; ++c) dsacc[nt][c] = 0.f;
+        for (int nt = 0; nt < 8; ++nt)
+            *reinterpret_cast<float2*>(dSacc + (r0 + g + half * 8) * PS_STRIDE + nt * 8 + 2 * t) = make_float2(0.f, 0.f);
     float g1 = 0.f, g2 = 0.f;
 
     const int ntiles = p.B * p.nW;
@@ -330,13 +332,15 @@ __global__ void __launch_bounds__(ATT_THREADS) attn_bwd_kernel(const AttnParams 
                     g2 += dP * r * r;
                     pv[e] = tf32_round(w0 * P0 + w1 * r * r);
                     const float ds = w0 * P0 * (dP - rowdot) + w1 * 2.f * r * dP;
-                    dsacc[nt][c] += ds;
                     dp[nt][c] = ds;  // dp now holds dS
                     dv[e] = ds;  // full fp32: dK = dS^T q cancels the common part of q (3xTF32 below)
                 }
                 const int j = nt * 8 + 2 * t;
                 *reinterpret_cast<float2*>(Ps + i * PS_STRIDE + j) = make_float2(pv[0], pv[1]);
                 *reinterpret_cast<float2*>(dSs + i * PS_STRIDE + j) = make_float2(dv[0], dv[1]);
+                float2* accp = reinterpret_cast<float2*>(dSacc + i * PS_STRIDE + j);
+                const float2 old = *accp;
+                *accp = make_float2(old.x + dv[0], old.y + dv[1]);
             }
         }
         // dQ = scale * dS K  (Qs holds scale*q, so the chain rule adds one more factor scale)
@@ -401,14 +405,6 @@ __global__ void __launch_bounds__(ATT_THREADS) attn_bwd_kernel(const AttnParams 
 
     // ---- bin the accumulated dS into the 225 relative-position slots (deterministic) ----
     __syncthreads();
-#pragma unroll
-    for (int half = 0; half < 2; ++half) {
-        const int i = r0 + g + half * 8;
-#pragma unroll
-        for (int nt = 0; nt < 8; ++nt)
-            *reinterpret_cast<float2*>(Ps + i * PS_STRIDE + nt * 8 + 2 * t) =
-                make_float2(dsacc[nt][half * 2], dsacc[nt][half * 2 + 1]);
-    }
     g1 = warp_sum(g1);
     g2 = warp_sum(g2);
     if (lane == 0) {
@@ -423,7 +419,7 @@ __global__ void __launch_bounds__(ATT_THREADS) attn_bwd_kernel(const AttnParams 
         for (int yj = max(0, -dy); yj < min(8, 8 - dy); ++yj)
             for (int xj = max(0, -dx); xj < min(8, 8 - dx); ++xj) {
                 const int j = yj * 8 + xj, i = (yj + dy) * 8 + (xj + dx);
-                sum += Ps[i * PS_STRIDE + j];
+                sum += dSacc[i * PS_STRIDE + j];
             }
         part[bin] = sum;
     }
@@ -472,7 +468,7 @@ int bwd_ctas_per_head(const uwr_attn_desc* d) {
 template <int HD>
 constexpr int fwd_smem() { return (3 * NTOK * (HD + 4) + 228 + NTOK) * 4 + NTOK * 8; }
 template <int HD>
-constexpr int bwd_smem() { return (4 * NTOK * (HD + 4) + 2 * NTOK * PS_STRIDE + 228 + NTOK) * 4 + NTOK * 8; }
+constexpr int bwd_smem() { return (4 * NTOK * (HD + 4) + 3 * NTOK * PS_STRIDE + 228 + NTOK) * 4 + NTOK * 8; }
 
 int fill_params(const uwr_attn_desc* d, AttnParams& p, const char* who) {
     UWR_REQUIRE(d && d->q && d->kv && d->bias_table, "%s: null pointer", who);
