@@ -1,0 +1,95 @@
+"""Generate tests/golden/*.pt from the UNMODIFIED reference (TEST INFRASTRUCTURE).
+
+Run in the authoring container only (needs /root/reference; the stand-ins under oracle/shims/ supply
+the third-party packages that are absent from the image):
+
+    python oracle/make_golden.py
+
+The vectors pin the oracle (oracle/*.py) and, through it, the CUDA path.  Documented reference
+patches used here: P2 = LuminanceLoss attached for "L1withColor".
+"""
+import hashlib
+import os
+import sys
+
+import numpy as np
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+REF = "/root/reference"
+sys.path[:0] = [os.path.join(ROOT, "oracle", "shims"), REF]
+OUT = os.path.join(ROOT, "tests", "golden")
+
+
+def sha(t):
+    return hashlib.sha1(t.detach().cpu().contiguous().numpy().tobytes()).hexdigest()
+
+
+def main():
+    os.makedirs(OUT, exist_ok=True)
+    from src.Models.AST import AST, TransformerBlock, WindowAttention_sparse
+    from src.Losses.losses import LossFunction
+    from src.Losses.luminanceLoss import LuminanceLoss
+    from src.ModelTrainer import torchPSNR
+    import uqim_utils
+
+    # ---- AST: seeded weights, seeded input, output + loss + per-tensor gradient norms/projections
+    torch.manual_seed(1234)
+    model = AST(img_size=128)
+    keys = [(k, list(v.shape), str(v.dtype), sha(v)) for k, v in model.state_dict().items()]
+    model.eval()
+    g = torch.Generator().manual_seed(2024)
+    raw = torch.rand(1, 3, 128, 128, generator=g) * 2 - 1
+    ref = torch.rand(1, 3, 128, 128, generator=g) * 2 - 1
+    out = model(raw)
+    lf = LossFunction("L1", "cpu")
+    loss = lf.getloss(out, ref)
+    loss.backward()
+    pg = torch.Generator().manual_seed(99)
+    grads = {}
+    for n, p in model.named_parameters():
+        r = torch.randn(p.shape, generator=pg)
+        grads[n] = (p.grad.norm().item(), (p.grad * r).sum().item())
+    torch.save({"state_dict_sha1": keys, "out": out.detach(), "loss_l1": loss.item(), "grad_norm_proj": grads,
+                "seed_weights": 1234, "seed_data": 2024, "proj_seed": 99}, os.path.join(OUT, "ast_128.pt"))
+
+    # full-size default model: only the hashes (weights are regenerated from the seed on the GPU box)
+    torch.manual_seed(1234)
+    m256 = AST()
+    torch.save({"state_dict_sha1": [(k, list(v.shape), str(v.dtype), sha(v)) for k, v in m256.state_dict().items()]},
+               os.path.join(OUT, "ast_256_state_sha1.pt"))
+
+    # ---- building blocks: one shifted sparse-attention block and its mask / index buffers
+    torch.manual_seed(5)
+    blk = TransformerBlock(64, (16, 16), 2, win_size=8, shift_size=4, att=True, sparseAtt=True)
+    for p in blk.parameters():
+        torch.nn.init.normal_(p, std=0.1)
+    blk.eval()
+    x = torch.randn(2, 256, 64)
+    y = blk(x)
+    torch.save({"state": {k: v.clone() for k, v in blk.state_dict().items()}, "x": x, "y": y.detach(),
+                "rel_index": blk.attn.relative_position_index.clone()}, os.path.join(OUT, "block_shift.pt"))
+
+    # ---- losses / metrics known answers
+    torch.manual_seed(0)
+    p = torch.rand(2, 3, 256, 256)
+    t = torch.rand(2, 3, 256, 256)
+    vals = {}
+    for name in ("L1", "L2", "charbonnier", "fflCharbonnier"):
+        vals[name] = LossFunction(name, "cpu").getloss(p, t).item()
+    lfc = LossFunction("L1withColor", "cpu")
+    lfc.luminanceLoss = LuminanceLoss()  # patch P2
+    import io, contextlib
+    with contextlib.redirect_stdout(io.StringIO()):
+        vals["L1withColor"] = lfc.getloss(p, t).item()
+    vals["Luminance"] = LuminanceLoss()(p, t).item()
+    vals["charbonnier_identical"] = LossFunction("charbonnier", "cpu").getloss(p, p).item()  # Loss.ipynb:45
+    vals["psnr"] = torchPSNR(t, p).item()
+    img = (np.random.default_rng(0).random((256, 256, 3)) * 255).astype(np.uint8)
+    vals["uiqm"] = [float(v) for v in uqim_utils.getUIQM(img)]
+    torch.save(vals, os.path.join(OUT, "losses_metrics.pt"))
+    print({k: v for k, v in vals.items()})
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,54 @@
+"""CPU, world_size 2 over gloo: the gradient buckets of uwr.train (views handed to autograd,
+all-reduce launched from post-accumulate hooks, dead-parameter buckets flushed in finish())
+reproduce the single-process global-batch gradients."""
+import os
+import sys
+
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+from conftest import ROOT, PKG
+
+
+def _worker(rank, world, port, out):
+    for p in (ROOT, PKG):
+        sys.path.insert(0, p)
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from uwr.train import GradBuckets
+    torch.manual_seed(0)
+    net = torch.nn.Sequential(torch.nn.Linear(16, 32), torch.nn.GELU(), torch.nn.Linear(32, 8))
+    dead = torch.nn.Parameter(torch.ones(5))          # never receives a gradient
+    params = list(net.parameters()) + [dead]
+    buckets = GradBuckets(params, bucket_bytes=1024, world_size=world)
+    g = torch.Generator().manual_seed(1)
+    x = torch.randn(8, 16, generator=g)
+    y = torch.randn(8, 8, generator=g)
+    xs, ys = x[rank * 4:(rank + 1) * 4], y[rank * 4:(rank + 1) * 4]
+    for _ in range(2):                                  # second pass checks zero()/re-arming
+        buckets.zero()
+        loss = ((net(xs) - ys) ** 2).sum() / 8          # divisor = GLOBAL batch
+        loss.backward()
+        buckets.finish()
+    if rank == 0:
+        torch.save([p.grad.clone() for p in params], out)
+    dist.destroy_process_group()
+
+
+@pytest.mark.timeout(120)
+def test_grad_buckets_match_global_batch(tmp_path):
+    out = str(tmp_path / "grads.pt")
+    port = 29500 + os.getpid() % 1000
+    mp.spawn(_worker, args=(2, port, out), nprocs=2, join=True)
+    got = torch.load(out)
+    torch.manual_seed(0)
+    net = torch.nn.Sequential(torch.nn.Linear(16, 32), torch.nn.GELU(), torch.nn.Linear(32, 8))
+    g = torch.Generator().manual_seed(1)
+    x = torch.randn(8, 16, generator=g)
+    y = torch.randn(8, 8, generator=g)
+    (((net(x) - y) ** 2).sum() / 8).backward()
+    for a, p in zip(got, net.parameters()):
+        assert torch.allclose(a, p.grad, rtol=1e-5, atol=1e-7)   # SUM over ranks of local/global-divisor grads
+    assert torch.count_nonzero(got[-1]) == 0

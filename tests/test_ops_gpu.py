@@ -387,3 +387,24 @@ def test_producers_round_to_tf32_in_fast_mode(ops):
     expect = ((i + 0x1000) & ~0x1FFF).view(torch.float32)
     assert torch.equal(y_fast, expect)
     assert (y_fast.view(torch.int32) & 0x1FFF).abs().max().item() == 0
+
+
+@pytest.mark.parametrize("B,S", [(2, 256), (1, 128), (3, 64)])
+def test_focal_frequency_loss(B, S):
+    """uwr_ffl_loss (smem FFT) vs the oracle restatement of focal_frequency_loss; FFL(x, x) = 0
+    (src/Loss.ipynb:49)."""
+    from oracle import losses_oracle as lo
+    from uwr.losses import LossFunction
+    torch.manual_seed(0)
+    p = torch.rand(B, 3, S, S).cuda().requires_grad_()
+    t = torch.rand(B, 3, S, S).cuda()
+    loss = LossFunction("ffl", "cuda").getloss(p, t)
+    loss.backward()
+    pd = p.detach().double().cpu().requires_grad_()
+    ref = lo.focal_frequency(pd, t.double().cpu())
+    ref.backward()
+    assert abs(loss.item() - ref.item()) <= 2e-5 * abs(ref.item())
+    assert rel_l2(p.grad, pd.grad) < 2e-5
+    assert LossFunction("ffl", "cuda").getloss(t, t).item() == 0.0
+    both = LossFunction("fflCharbonnier", "cuda").getloss(p.detach(), t).item()
+    assert abs(both - (ref.item() + lo.charbonnier(pd.detach(), t.double().cpu()).item())) < 1e-5

@@ -1,0 +1,111 @@
+"""CPU: the drop-in surface (registry, module tree, loss registry) and the C ABI (library loads,
+exports every symbol that include/uwr_b200.h declares).  No kernel is launched here."""
+import ctypes
+import os
+import re
+
+import pytest
+import torch
+
+from conftest import ROOT, PKG
+
+
+def _declared_symbols():
+    src = open(os.path.join(ROOT, "include", "uwr_b200.h")).read()
+    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+    return sorted(set(re.findall(r"\b(uwr_[a-z0-9_]+)\s*\(", src)))
+
+
+def test_library_exports_every_declared_symbol(build_lib):
+    lib = ctypes.CDLL(build_lib)
+    names = _declared_symbols()
+    assert len(names) >= 35
+    missing = [n for n in names if not hasattr(lib, n)]
+    assert not missing, missing
+    lib.uwr_abi_version.restype = ctypes.c_int
+    assert lib.uwr_abi_version() == 1
+    lib.uwr_last_error.restype = ctypes.c_char_p
+    assert lib.uwr_last_error() is not None
+
+
+def test_ctypes_table_matches_header(build_lib):
+    from uwr import _lib
+    declared = set(_declared_symbols())
+    bound = set(_lib.SIGNATURES)
+    assert bound <= declared, bound - declared
+    # descriptor structs mirror the C layout: ask the C compiler (the header is plain C)
+    import subprocess, tempfile
+    with tempfile.TemporaryDirectory() as td:
+        src = os.path.join(td, "sz.c")
+        open(src, "w").write('#include <stdio.h>\n#include "uwr_b200.h"\nint main(void){printf("%zu %zu %zu %zu", '
+                             'sizeof(uwr_gemm_desc), sizeof(uwr_attn_desc), '
+                             '__builtin_offsetof(uwr_gemm_desc, workspace_bytes), '
+                             '__builtin_offsetof(uwr_attn_desc, scale));return 0;}\n')
+        exe = os.path.join(td, "sz")
+        subprocess.check_call(["gcc", "-I", os.path.join(ROOT, "include"), src, "-o", exe])
+        g, a, go, ao = map(int, subprocess.check_output([exe]).split())
+    assert ctypes.sizeof(_lib.GemmDesc) == g and _lib.GemmDesc.workspace_bytes.offset == go
+    assert ctypes.sizeof(_lib.AttnDesc) == a and _lib.AttnDesc.scale.offset == ao
+
+
+def test_error_paths_return_codes_not_crashes(build_lib):
+    """argument validation happens before any launch, so it is testable without a GPU"""
+    from uwr import _lib
+    d = _lib.GemmDesc()
+    rc = _lib.fn["uwr_gemm_tf32"](ctypes.byref(d), None)
+    assert rc == -1 and b"null operand" in _lib.fn["uwr_last_error"]()
+    assert _lib.fn["uwr_set_gemm_precision"](2) == -1
+    assert _lib.fn["uwr_gemm_tcgen05_supported"](ctypes.byref(d)) == 0
+    with pytest.raises(_lib.UwrError):
+        _lib.check(_lib.fn["uwr_pixel_loss"](None, None, None, None, None, 0, 1, 3, 8, 8, 1, None), "uwr_pixel_loss")
+
+
+def test_registry_surface():
+    import uwr
+    assert uwr.get_names() == ["SpectralTransformer", "NewModel", "NewBigModel", "NewBigFRFNModel", "AST"]
+    with pytest.raises(KeyError, match="Unknown model: nope"):
+        uwr.init_model("nope")
+    m = uwr.init_model("AST", use_dwt="Fourier")   # use_dwt is dropped (src/Models/__init__.py:25-29)
+    sd = m.state_dict()
+    assert len(sd) == 274
+    assert sd["conv.blocks.0.attn.qkv.to_kv.weight"].shape == (1024, 512)
+    assert sd["encoderlayer_0.blocks.0.mlp.dwconv.0.weight"].shape == (128, 1, 3, 3)
+    assert sd["dowsample_0.conv.0.weight"].shape == (64, 32, 4, 4)
+    assert sd["upsample_0.deconv.0.weight"].shape == (512, 256, 2, 2)
+    assert sd["decoderlayer_3.blocks.1.attn.relative_position_index"].dtype == torch.int64
+    assert "encoderlayer_0.blocks.0.norm1.weight" not in sd     # encoder stages have no attention
+    assert sd["conv.blocks.0.attn.w"].tolist() == [1.0, 1.0]
+
+
+def test_no_cpu_fallback():
+    import uwr
+    m = uwr.AST(img_size=128)
+    with pytest.raises(RuntimeError, match="CUDA"):
+        m(torch.zeros(1, 3, 128, 128))
+    with pytest.raises(ValueError, match="Unsupported loss"):
+        uwr.LossFunction("nope", "cpu").getloss(torch.zeros(1, 3, 8, 8), torch.zeros(1, 3, 8, 8))
+    with pytest.raises(TypeError):
+        from uwr import ops
+        ops.layernorm_fwd(torch.zeros(4, 32), torch.ones(32), torch.zeros(32))
+
+
+def test_product_does_not_import_oracle():
+    """the oracle is test infrastructure: nothing under uwr/ may reference it"""
+    for dirpath, _, files in os.walk(os.path.join(PKG, "uwr")):
+        for f in files:
+            if f.endswith(".py"):
+                txt = open(os.path.join(dirpath, f)).read()
+                assert "oracle" not in txt.replace("oracle's", ""), os.path.join(dirpath, f)
+
+
+def test_droppath_semantics():
+    from uwr.ast import DropPath
+    dp = DropPath(0.25)
+    dp.eval()
+    assert dp.scale(8, "cpu") is None
+    dp.train()
+    torch.manual_seed(0)
+    s = dp.scale(4096, "cpu")
+    assert set(s.unique().tolist()) <= {0.0, 1.0 / 0.75}
+    assert abs((s > 0).float().mean().item() - 0.75) < 0.03
+    assert DropPath(0.0).train().scale(4, "cpu") is None

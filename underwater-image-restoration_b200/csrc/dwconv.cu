@@ -20,8 +20,12 @@ constexpr int TS = 16;          // tile side
 constexpr int HS = TS + 2;      // halo side
 constexpr int CG = 32;          // channels per CTA
 constexpr int DW_THREADS = 256; // 8 warps, 2 tile rows each
-constexpr int NWARP = DW_THREADS / 32;
-constexpr int BATCH = 8;        // global loads in flight per warp while staging
+
+// thread -> (tile row r, x half xh, 4-channel group c4): 8 outputs x 4 channels, 128-bit accesses only
+__device__ __forceinline__ float4 ld4(const float* p) { return *reinterpret_cast<const float4*>(p); }
+__device__ __forceinline__ void fma4(float4& a, const float4& x, const float4& w) {
+    a.x = fmaf(x.x, w.x, a.x); a.y = fmaf(x.y, w.y, a.y); a.z = fmaf(x.z, w.z, a.z); a.w = fmaf(x.w, w.w, a.w);
+}
 
 __global__ void __launch_bounds__(DW_THREADS) dwconv_fwd_kernel(const float* __restrict__ u, long long ld_u,
                                                                 const float* __restrict__ weight,
@@ -29,75 +33,85 @@ __global__ void __launch_bounds__(DW_THREADS) dwconv_fwd_kernel(const float* __r
                                                                 float* __restrict__ v, float* __restrict__ h2,
                                                                 int H, int W, int Ch, int mode, int tiles_x, int rnd,
                                                                 int v_is_dgelu) {
-    __shared__ float h1s[HS * HS][CG];
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const int c = blockIdx.y * CG + lane;
-    const bool cok = c < Ch;
+    __shared__ __align__(16) float h1s[HS * HS][CG];
+    const int tid = threadIdx.x;
+    const int c4 = (tid & 7) * 4;
+    const int c = blockIdx.y * CG + c4;
+    const bool cok = c < Ch;  // Ch is a multiple of 4
     const int b = blockIdx.z;
     const int ty0 = (blockIdx.x / tiles_x) * TS, tx0 = (blockIdx.x % tiles_x) * TS;
     const float* ub = u + (long long)b * H * W * ld_u;
 
-    for (int p0 = warp; p0 < HS * HS; p0 += NWARP * BATCH) {
-        float val[BATCH];
+    // ---- stage gelu(u) with halo: 324 pixels x 8 float4, all loads of a batch in flight together
+    constexpr int NV = (HS * HS * (CG / 4) + DW_THREADS - 1) / DW_THREADS;  // 11
+    float4 val[NV];
 #pragma unroll
-        for (int i = 0; i < BATCH; ++i) {
-            const int pix = p0 + i * NWARP;
-            const int y = ty0 + pix / HS - 1, x = tx0 + pix % HS - 1;
-            val[i] = 0.f;
-            if (pix < HS * HS && cok && y >= 0 && y < H && x >= 0 && x < W)
-                val[i] = __ldg(ub + ((long long)y * W + x) * ld_u + c);
-        }
-#pragma unroll
-        for (int i = 0; i < BATCH; ++i) {
-            const int pix = p0 + i * NWARP;
-            if (pix < HS * HS) h1s[pix][lane] = gelu_f(val[i]);  // gelu(0) = 0 keeps the zero padding
-        }
+    for (int i = 0; i < NV; ++i) {
+        const int idx = tid + i * DW_THREADS;
+        const int pix = idx >> 3;
+        const int y = ty0 + pix / HS - 1, x = tx0 + pix % HS - 1;
+        val[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (pix < HS * HS && cok && y >= 0 && y < H && x >= 0 && x < W)
+            val[i] = ld4(ub + ((long long)y * W + x) * ld_u + c);
     }
-    float wgt[9];
 #pragma unroll
-    for (int k = 0; k < 9; ++k) wgt[k] = cok ? weight[c * 9 + k] : 0.f;
-    const float bv = cok ? bias[c] : 0.f;
+    for (int i = 0; i < NV; ++i) {
+        const int idx = tid + i * DW_THREADS;
+        const int pix = idx >> 3;
+        if (pix < HS * HS)  // gelu(0) = 0 keeps the zero padding
+            *reinterpret_cast<float4*>(&h1s[pix][c4]) =
+                make_float4(gelu_f(val[i].x), gelu_f(val[i].y), gelu_f(val[i].z), gelu_f(val[i].w));
+    }
+    float4 wgt[9];
+#pragma unroll
+    for (int k = 0; k < 9; ++k)
+        wgt[k] = cok ? make_float4(weight[c * 9 + k], weight[(c + 1) * 9 + k], weight[(c + 2) * 9 + k],
+                                   weight[(c + 3) * 9 + k])
+                     : make_float4(0.f, 0.f, 0.f, 0.f);
+    const float4 bv = cok ? ld4(bias + c) : make_float4(0.f, 0.f, 0.f, 0.f);
     __syncthreads();
-    if (!cok) return;
 
+    const int ly = tid >> 4;            // tile row 0..15
+    const int lx0 = ((tid >> 3) & 1) * 8;  // first of 8 columns
+    const int y = ty0 + ly;
+    if (!cok || y >= H) return;
+    const long long tok0 = ((long long)b * H + y) * W + tx0;
+    float4 win[3][3];
 #pragma unroll
-    for (int rr = 0; rr < 2; ++rr) {
-        const int ly = warp * 2 + rr;  // local row 0..15
-        const int y = ty0 + ly;
-        if (y >= H) break;
-        const long long tok0 = ((long long)b * H + y) * W + tx0;
-        float gate[TS];
-        if (mode == 1) {
+    for (int ky = 0; ky < 3; ++ky) {
+        win[ky][1] = ld4(&h1s[(ly + ky) * HS + lx0][c4]);
+        win[ky][2] = ld4(&h1s[(ly + ky) * HS + lx0 + 1][c4]);
+    }
 #pragma unroll
-            for (int lx = 0; lx < TS; ++lx) gate[lx] = (tx0 + lx < W) ? __ldg(u + (tok0 + lx) * ld_u + Ch + c) : 0.f;
-        }
-        float win[3][3];
+    for (int i = 0; i < 8; ++i) {
+        const int lx = lx0 + i;
 #pragma unroll
         for (int ky = 0; ky < 3; ++ky) {
-            win[ky][1] = h1s[(ly + ky) * HS + 0][lane];
-            win[ky][2] = h1s[(ly + ky) * HS + 1][lane];
+            win[ky][0] = win[ky][1];
+            win[ky][1] = win[ky][2];
+            win[ky][2] = ld4(&h1s[(ly + ky) * HS + lx + 2][c4]);
         }
+        if (tx0 + lx < W) {
+            float4 acc = bv;
 #pragma unroll
-        for (int lx = 0; lx < TS; ++lx) {
+            for (int ky = 0; ky < 3; ++ky)
 #pragma unroll
-            for (int ky = 0; ky < 3; ++ky) {
-                win[ky][0] = win[ky][1];
-                win[ky][1] = win[ky][2];
-                win[ky][2] = h1s[(ly + ky) * HS + lx + 2][lane];
-            }
-            if (tx0 + lx < W) {
-                float acc = bv;
+                for (int kx = 0; kx < 3; ++kx) fma4(acc, win[ky][kx], wgt[ky * 3 + kx]);
+            float a[4] = {acc.x, acc.y, acc.z, acc.w}, o[4], sv[4];
+            float4 gate = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (mode == 1) gate = ld4(u + (tok0 + lx) * ld_u + Ch + c);
+            const float gt[4] = {gate.x, gate.y, gate.z, gate.w};
 #pragma unroll
-                for (int ky = 0; ky < 3; ++ky)
-#pragma unroll
-                    for (int kx = 0; kx < 3; ++kx) acc = fmaf(win[ky][kx], wgt[ky * 3 + kx], acc);
+            for (int e = 0; e < 4; ++e) {
                 float cdf, pdf;
-                gelu_parts(acc, cdf, pdf);
-                if (v) v[(tok0 + lx) * Ch + c] = v_is_dgelu ? fmaf(acc, pdf, cdf) : acc;
-                float o = acc * cdf;
-                if (mode == 1) o *= gelu_f(gate[lx]);
-                h2[(tok0 + lx) * Ch + c] = rnd ? tf32_round(o) : o;
+                gelu_parts(a[e], cdf, pdf);
+                sv[e] = v_is_dgelu ? fmaf(a[e], pdf, cdf) : a[e];
+                o[e] = a[e] * cdf;
+                if (mode == 1) o[e] *= gelu_f(gt[e]);
+                if (rnd) o[e] = tf32_round(o[e]);
             }
+            if (v) *reinterpret_cast<float4*>(v + (tok0 + lx) * Ch + c) = make_float4(sv[0], sv[1], sv[2], sv[3]);
+            *reinterpret_cast<float4*>(h2 + (tok0 + lx) * Ch + c) = make_float4(o[0], o[1], o[2], o[3]);
         }
     }
 }
@@ -123,25 +137,37 @@ __global__ void __launch_bounds__(256) gelu_gate_bwd_kernel(const float* __restr
     }
 }
 
-// persistent over tiles: grid = (P, Ch/32); each CTA accumulates dweight/dbias partials in registers
-__global__ void __launch_bounds__(DW_THREADS) dwconv_bwd_kernel(const float* __restrict__ dv,
-                                                                const float* __restrict__ u, long long ld_u,
-                                                                const float* __restrict__ weight,
-                                                                float* __restrict__ du, float* __restrict__ partials,
-                                                                int B, int H, int W, int Ch, int tiles_x,
-                                                                int tiles_per_img, int rnd) {
-    __shared__ float dvs[HS * HS][CG];
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const int c = blockIdx.y * CG + lane;
-    const bool cok = c < Ch;
+// persistent over tiles: grid = (P, Ch/32).  thread -> (tile row, 2-channel group): 16 outputs x 2
+// channels with 64-bit accesses (the 4-channel variant needs > 128 registers for the nine dweight
+// accumulators and would leave one CTA per SM).  dweight/dbias partials accumulate in registers and
+// are reduced across the CTA once, at the end.
+__device__ __forceinline__ float2 ld2(const float* p) { return *reinterpret_cast<const float2*>(p); }
+__device__ __forceinline__ void fma2(float2& a, const float2& x, const float2& w) {
+    a.x = fmaf(x.x, w.x, a.x); a.y = fmaf(x.y, w.y, a.y);
+}
 
-    float wgt[9], dwt[9];
+__global__ void __launch_bounds__(DW_THREADS, 2) dwconv_bwd_kernel(const float* __restrict__ dv,
+                                                                   const float* __restrict__ u, long long ld_u,
+                                                                   const float* __restrict__ weight,
+                                                                   float* __restrict__ du,
+                                                                   float* __restrict__ partials, int B, int H, int W,
+                                                                   int Ch, int tiles_x, int tiles_per_img, int rnd) {
+    __shared__ __align__(16) float dvs[HS * HS][CG];
+    const int tid = threadIdx.x;
+    const int c2 = (tid & 15) * 2;
+    const int c = blockIdx.y * CG + c2;
+    const bool cok = c < Ch;  // Ch is a multiple of 4
+    const int ly = tid >> 4;
+    const int s4 = (tid & 7) * 4;  // staging uses 128-bit pieces
+
+    float2 wgt[9], dwt[9];
 #pragma unroll
     for (int k = 0; k < 9; ++k) {
-        wgt[k] = cok ? weight[c * 9 + k] : 0.f;
-        dwt[k] = 0.f;
+        wgt[k] = cok ? make_float2(weight[c * 9 + k], weight[(c + 1) * 9 + k]) : make_float2(0.f, 0.f);
+        dwt[k] = make_float2(0.f, 0.f);
     }
-    float dbs = 0.f;
+    float2 dbs = make_float2(0.f, 0.f);
+    const bool sok = blockIdx.y * CG + s4 < Ch;
 
     const int total = B * tiles_per_img;
     for (int tile = blockIdx.x; tile < total; tile += gridDim.x) {
@@ -149,85 +175,99 @@ __global__ void __launch_bounds__(DW_THREADS) dwconv_bwd_kernel(const float* __r
         const int ty0 = (tl / tiles_x) * TS, tx0 = (tl % tiles_x) * TS;
         const long long base = (long long)b * H * W;
         __syncthreads();
-        for (int p0 = warp; p0 < HS * HS; p0 += NWARP * BATCH) {
-            float val[BATCH];
+        constexpr int NV = (HS * HS * (CG / 4) + DW_THREADS - 1) / DW_THREADS;  // 11 float4 per thread
 #pragma unroll
-            for (int i = 0; i < BATCH; ++i) {
-                const int pix = p0 + i * NWARP;
+        for (int h = 0; h < 2; ++h) {  // two batches keep the register footprint down
+            float4 val[(NV + 1) / 2];
+#pragma unroll
+            for (int i = 0; i < (NV + 1) / 2; ++i) {
+                const int idx = tid + (h * ((NV + 1) / 2) + i) * DW_THREADS;
+                const int pix = idx >> 3;
                 const int y = ty0 + pix / HS - 1, x = tx0 + pix % HS - 1;
-                val[i] = 0.f;
-                if (pix < HS * HS && cok && y >= 0 && y < H && x >= 0 && x < W)
-                    val[i] = __ldg(dv + (base + (long long)y * W + x) * Ch + c);
+                val[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (pix < HS * HS && sok && y >= 0 && y < H && x >= 0 && x < W)
+                    val[i] = ld4(dv + (base + (long long)y * W + x) * Ch + blockIdx.y * CG + s4);
             }
 #pragma unroll
-            for (int i = 0; i < BATCH; ++i) {
-                const int pix = p0 + i * NWARP;
-                if (pix < HS * HS) dvs[pix][lane] = val[i];
+            for (int i = 0; i < (NV + 1) / 2; ++i) {
+                const int idx = tid + (h * ((NV + 1) / 2) + i) * DW_THREADS;
+                const int pix = idx >> 3;
+                if (pix < HS * HS) *reinterpret_cast<float4*>(&dvs[pix][s4]) = val[i];
             }
         }
+        const int y = ty0 + ly;
+        const bool rok = cok && y < H;
+        const long long tok0 = base + (long long)y * W + tx0;
         __syncthreads();
-        if (cok) {
+        if (rok) {
 #pragma unroll
-            for (int rr = 0; rr < 2; ++rr) {
-                const int ly = warp * 2 + rr;
-                const int y = ty0 + ly;
-                if (y >= H) break;
-                const long long tok0 = base + (long long)y * W + tx0;
-                float uc[TS];
+            for (int hx = 0; hx < 2; ++hx) {  // two strips of 8 columns
+                const int lx0 = hx * 8;
+                float2 uc[8];
 #pragma unroll
-                for (int lx = 0; lx < TS; ++lx) uc[lx] = (tx0 + lx < W) ? __ldg(u + (tok0 + lx) * ld_u + c) : 0.f;
+                for (int i = 0; i < 8; ++i)
+                    uc[i] = (tx0 + lx0 + i < W) ? ld2(u + (tok0 + lx0 + i) * ld_u + c) : make_float2(0.f, 0.f);
                 // window of dv around the output pixel: win[a][b] = dv[y-1+a][x-1+b]
-                float win[3][3];
+                float2 win[3][3];
 #pragma unroll
                 for (int a = 0; a < 3; ++a) {
-                    win[a][1] = dvs[(ly + a) * HS + 0][lane];
-                    win[a][2] = dvs[(ly + a) * HS + 1][lane];
+                    win[a][1] = ld2(&dvs[(ly + a) * HS + lx0][c2]);
+                    win[a][2] = ld2(&dvs[(ly + a) * HS + lx0 + 1][c2]);
                 }
 #pragma unroll
-                for (int lx = 0; lx < TS; ++lx) {
+                for (int i = 0; i < 8; ++i) {
+                    const int lx = lx0 + i;
 #pragma unroll
                     for (int a = 0; a < 3; ++a) {
                         win[a][0] = win[a][1];
                         win[a][1] = win[a][2];
-                        win[a][2] = dvs[(ly + a) * HS + lx + 2][lane];
+                        win[a][2] = ld2(&dvs[(ly + a) * HS + lx + 2][c2]);
                     }
                     if (tx0 + lx < W) {
-                        const float x = uc[lx];
-                        float cdf, pdf;
-                        gelu_parts(x, cdf, pdf);
-                        const float h1 = x * cdf;
-                        float dh1 = 0.f;
+                        float cdf0, pdf0, cdf1, pdf1;
+                        gelu_parts(uc[i].x, cdf0, pdf0);
+                        gelu_parts(uc[i].y, cdf1, pdf1);
+                        const float2 h1 = make_float2(uc[i].x * cdf0, uc[i].y * cdf1);
+                        float2 dh1 = make_float2(0.f, 0.f);
                         // v[q] = sum_k h1[q + k - 1] w[k]  =>  h1[p] meets dv[p + 1 - k] with weight w[k]
 #pragma unroll
                         for (int ky = 0; ky < 3; ++ky)
 #pragma unroll
                             for (int kx = 0; kx < 3; ++kx) {
-                                const float d = win[2 - ky][2 - kx];
-                                dh1 = fmaf(d, wgt[ky * 3 + kx], dh1);
-                                dwt[ky * 3 + kx] = fmaf(h1, d, dwt[ky * 3 + kx]);
+                                const float2 d = win[2 - ky][2 - kx];
+                                fma2(dh1, d, wgt[ky * 3 + kx]);
+                                fma2(dwt[ky * 3 + kx], h1, d);
                             }
-                        dbs += win[1][1];
-                        const float dval = dh1 * (cdf + x * pdf);
-                        du[(tok0 + lx) * ld_u + c] = rnd ? tf32_round(dval) : dval;
+                        dbs.x += win[1][1].x;
+                        dbs.y += win[1][1].y;
+                        float2 o = make_float2(dh1.x * fmaf(uc[i].x, pdf0, cdf0), dh1.y * fmaf(uc[i].y, pdf1, cdf1));
+                        if (rnd) o = make_float2(tf32_round(o.x), tf32_round(o.y));
+                        *reinterpret_cast<float2*>(du + (tok0 + lx) * ld_u + c) = o;
                     }
                 }
             }
         }
     }
-    // reduce the 10 per-channel partial sums across the 8 warps (the tile buffer is reused)
+    // cross-thread reduction: 20 partial sums per thread (10 taps x 2 channels), 16 threads per channel
+    // pair; the tile buffer is reused as red[slot][tid]
     __syncthreads();
-    float(*red)[10][CG] = reinterpret_cast<float(*)[10][CG]>(&dvs[0][0]);
+    float* red = &dvs[0][0];
 #pragma unroll
-    for (int k = 0; k < 9; ++k) red[warp][k][lane] = dwt[k];
-    red[warp][9][lane] = dbs;
+    for (int k = 0; k < 9; ++k) {
+        red[(k * 2 + 0) * DW_THREADS + tid] = dwt[k].x;
+        red[(k * 2 + 1) * DW_THREADS + tid] = dwt[k].y;
+    }
+    red[18 * DW_THREADS + tid] = dbs.x;
+    red[19 * DW_THREADS + tid] = dbs.y;
     __syncthreads();
-    for (int idx = threadIdx.x; idx < 10 * CG; idx += DW_THREADS) {
-        const int k = idx / CG, l = idx % CG;
-        float s = 0.f;
-#pragma unroll
-        for (int w = 0; w < NWARP; ++w) s += red[w][k][l];
+    for (int idx = tid; idx < 10 * CG; idx += DW_THREADS) {
+        const int k = idx / CG, l = idx % CG;  // tap (9 = bias), local channel
+        const int grp = l >> 1, e = l & 1;
+        float sum = 0.f;
+#pragma unroll 8
+        for (int j = 0; j < DW_THREADS / 16; ++j) sum += red[(k * 2 + e) * DW_THREADS + j * 16 + grp];
         const int cc = blockIdx.y * CG + l;
-        if (cc < Ch) partials[((long long)blockIdx.x * 10 + k) * Ch + cc] = s;
+        if (cc < Ch) partials[((long long)blockIdx.x * 10 + k) * Ch + cc] = sum;
     }
 }
 
@@ -260,6 +300,7 @@ extern "C" int uwr_dwconv_gelu_fwd(const float* u, long long ld_u, const float* 
     UWR_REQUIRE(mode == 0 || mode == 1, "uwr_dwconv_gelu_fwd: mode must be 0 (LeFF) or 1 (FRFN gate)");
     UWR_REQUIRE(ld_u >= (mode == 1 ? 2 * Ch : Ch), "uwr_dwconv_gelu_fwd: ld_u too small");
     UWR_REQUIRE(B > 0 && B <= 65535, "uwr_dwconv_gelu_fwd: bad batch %d", B);
+    UWR_REQUIRE(Ch % 4 == 0 && ld_u % 4 == 0, "uwr_dwconv_gelu_fwd: Ch and ld_u must be multiples of 4");
     const int tx = uwr_cdiv(W, TS), ty = uwr_cdiv(H, TS);
     dim3 grid(tx * ty, uwr_cdiv(Ch, CG), B);
     dwconv_fwd_kernel<<<grid, DW_THREADS, 0, stream>>>(u, ld_u, weight, bias, v, h2, H, W, Ch, mode, tx, uwr_round_outputs(),
@@ -289,6 +330,7 @@ extern "C" int uwr_dwconv_gelu_bwd(const float* dv, const float* u, long long ld
                                    uwr_stream_t stream_) {
     cudaStream_t stream = (cudaStream_t)stream_;
     UWR_REQUIRE(dv && u && weight && du && dweight && dbias && workspace, "uwr_dwconv_gelu_bwd: null pointer");
+    UWR_REQUIRE(Ch % 4 == 0 && ld_u % 4 == 0, "uwr_dwconv_gelu_bwd: Ch and ld_u must be multiples of 4");
     const int tx = uwr_cdiv(W, TS), ty = uwr_cdiv(H, TS);
     const int P = bwd_ctas(B, H, W, Ch);
     dim3 grid(P, uwr_cdiv(Ch, CG));

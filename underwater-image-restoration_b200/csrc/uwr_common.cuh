@@ -61,7 +61,7 @@ __device__ __forceinline__ float tf32_round(float x) { return __uint_as_float(f2
 // ALU-bound on erff).
 __device__ __forceinline__ void gelu_parts(float x, float& cdf, float& pdf) {
     const float ax = fabsf(x);
-    const float t = __frcp_rn(fmaf(0.23164189f, ax, 1.0f));  // 1/(1 + p*z), p*z = 0.3275911*|x|/sqrt(2)
+    const float t = __fdividef(1.0f, fmaf(0.23164189f, ax, 1.0f));  // 1/(1 + p*z), p*z = 0.3275911*|x|/sqrt(2)
     const float e = __expf(-0.5f * x * x);
     float poly = fmaf(1.061405429f, t, -1.453152027f);
     poly = fmaf(poly, t, 1.421413741f);

@@ -98,6 +98,8 @@ SIGNATURES = {
     "uwr_copy2d": (c_int, [c_fp, c_ll, c_fp, c_ll, c_ll, c_int, c_int, c_stream]),
     "uwr_colsum": (c_int, [c_fp, c_ll, c_fp, c_fp, c_ll, c_int, c_stream]),
     "uwr_pixel_loss": (c_int, [c_fp, c_fp, c_fp, c_fp, c_fp, c_int, c_int, c_int, c_int, c_int, c_int, c_stream]),
+    "uwr_ffl_workspace_bytes": (c_sz, [c_int, c_int]),
+    "uwr_ffl_loss": (c_int, [c_fp, c_fp, c_fp, c_fp, c_fp, c_int, c_int, c_stream]),
     "uwr_grad_norm": (c_int, [c_fp, c_fp, c_int, c_ll, c_f, c_f, c_fp, c_fp, c_stream]),
     "uwr_adam_step": (c_int, [c_fp, c_fp, c_fp, c_fp, c_fp, c_int, c_ll, c_fp, c_f, c_f, c_f, c_f, c_f, c_f,
                               c_int, c_int, c_fp, c_stream]),
