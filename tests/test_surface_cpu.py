@@ -106,6 +106,6 @@ def test_droppath_semantics():
     dp.train()
     torch.manual_seed(0)
     s = dp.scale(4096, "cpu")
-    assert set(s.unique().tolist()) <= {0.0, 1.0 / 0.75}
+    assert all(v == 0.0 or abs(v - 1.0 / 0.75) < 1e-6 for v in s.unique().tolist())
     assert abs((s > 0).float().mean().item() - 0.75) < 0.03
     assert DropPath(0.0).train().scale(4, "cpu") is None
