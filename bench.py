@@ -217,6 +217,8 @@ def run_ours(args):
 
     # ---- roofline of the dominant kernel: one extra instrumented step (CUDA events per launch) ----
     roofline, table = None, None
+    if rank != 0:
+        step_resident()  # every rank takes part in the instrumented step's all-reduces
     if rank == 0:
         with ops.KernelProfile() as prof:
             step_resident()

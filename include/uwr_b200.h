@@ -70,6 +70,7 @@ typedef struct {
     float* colsum;
     float* workspace;
     size_t workspace_bytes;
+    int round_out; /* store C rounded to TF32 (it feeds another tensor-core GEMM) */
 } uwr_gemm_desc;
 
 size_t uwr_gemm_workspace_bytes(int M, int N, int K, int a_km);
@@ -186,6 +187,11 @@ int uwr_im2col_4x4s2(const float* tokens, long long ld, float* col, int B, int H
 int uwr_col2im_4x4s2(const float* dcol, float* dtokens, int B, int H, int W, int C,
                      uwr_stream_t stream);
 /* g: (B*H*W, Cout*4) GEMM result with column (co,dy,dx); out tokens (B,2H,2W,ld_out). */
+/* dense 3x3 s1 p1 conv as GEMM: col (B*H*W, 9*C) with K order (ky,kx,ci); col2im gathers back */
+int uwr_im2col_3x3(const float* tokens, long long ld, float* col, int B, int H, int W, int C,
+                   uwr_stream_t stream);
+int uwr_col2im_3x3(const float* dcol, float* dtokens, long long ld, int B, int H, int W, int C,
+                   int accumulate, uwr_stream_t stream);
 int uwr_pixel_scatter_2x2(const float* g, const float* bias, float* out, long long ld_out, int B,
                           int H, int W, int Cout, uwr_stream_t stream);
 int uwr_pixel_gather_2x2(const float* dout, long long ld_dout, float* dg, int B, int H, int W,

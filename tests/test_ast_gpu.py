@@ -16,11 +16,11 @@ def _pair(B, S, seed=2024):
     return raw, ref
 
 
-def _run(B, S, img_size, train, report, precision="tf32", tol=1e-3):
+def _run(B, S, img_size, train, report, precision="tf32", tol=1e-3, token_mlp="leff"):
     from uwr import ops
     ops.set_gemm_precision(precision)
     try:
-        _run_inner(B, S, img_size, train, report, tol)
+        _run_inner(B, S, img_size, train, report, tol, token_mlp)
     finally:
         ops.set_gemm_precision("tf32")
 
@@ -30,11 +30,11 @@ def uwr_l1(out, ref):
     return LossFunction("L1", "cuda").getloss(out.detach(), ref)
 
 
-def _run_inner(B, S, img_size, train, report, tol):
+def _run_inner(B, S, img_size, train, report, tol, token_mlp="leff"):
     from oracle import ast_oracle, losses_oracle
     from uwr.ast import AST, DropPath
     torch.manual_seed(1234)
-    model = AST(img_size=img_size)
+    model = AST(img_size=img_size, token_mlp=token_mlp)
     sd_cpu = {k: v.detach().clone() for k, v in model.state_dict().items()}
     model = model.cuda()
     raw, ref = _pair(B, S)
@@ -66,7 +66,7 @@ def _run_inner(B, S, img_size, train, report, tol):
 
     sd_o = {k: (v.clone().requires_grad_() if v.is_floating_point() else v) for k, v in sd_cpu.items()}
     dsc = {k: (a if (k + "attn.w") in sd_cpu else None, m) for k, (a, m) in drop.items()}
-    out_o = ast_oracle.ast_forward(sd_o, raw, img_size=img_size, drop_scales=dsc)
+    out_o = ast_oracle.ast_forward(sd_o, raw, img_size=img_size, drop_scales=dsc, token_mlp=token_mlp)
     loss_o = losses_oracle.l1(out_o, ref)
     # The L1 gradient sign(out - ref) is discontinuous: a single pixel with |out - ref| ~ 1e-6 that
     # flips sign changes dL/dout by 2/sqrt(n) ~ 6e-3 relative.  Parity of the backward pass is
@@ -115,6 +115,11 @@ def test_ast_train_droppath_128():
 def test_ast_tf32x3_128():
     """error-compensated GEMMs: the only remaining difference to the fp32 reference is summation order"""
     _run(2, 128, 128, True, [], precision="tf32x3", tol=5e-5)
+
+
+def test_ast_frfn_train_128():
+    """AST(token_mlp='frfn') (AST.py:540-541): FRFN feed-forward in every block"""
+    _run(2, 128, 128, True, [], token_mlp="frfn")
 
 
 def test_ast_eval_256():

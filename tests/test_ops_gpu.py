@@ -408,3 +408,41 @@ def test_focal_frequency_loss(B, S):
     assert LossFunction("ffl", "cuda").getloss(t, t).item() == 0.0
     both = LossFunction("fflCharbonnier", "cuda").getloss(p.detach(), t).item()
     assert abs(both - (ref.item() + lo.charbonnier(pd.detach(), t.double().cpu()).item())) < 1e-5
+
+
+@pytest.mark.parametrize("C,scales", [(64, (1.25, 0.0)), (32, None), (128, (1.0, 1.0))])
+def test_frfn_block_vs_oracle(C, scales):
+    """FRFN token MLP (AST.py:329-372): partial conv + gated dwconv block vs the oracle, tf32x3."""
+    from oracle import ast_oracle as ao
+    from uwr import ops
+    from uwr.ast import TransformerBlock
+    torch.manual_seed(4)
+    B, H = 2, 16
+    blk = TransformerBlock(C, (H, H), 2, win_size=8, shift_size=0, drop_path=0.1, att=False, token_mlp="frfn")
+    for p in blk.parameters():
+        torch.nn.init.normal_(p, std=0.08) if p.ndim > 1 else torch.nn.init.normal_(p, mean=0.5, std=0.2)
+    blk = blk.cuda().train()
+    sd = {k: v.detach().double().clone().requires_grad_() for k, v in blk.state_dict().items()}
+    x = _r(B, H * H, C, seed=5).requires_grad_()
+    sm = torch.tensor(scales).cuda() if scales is not None else None
+    blk.drop_path.scale = lambda batch, device: sm
+    ops.set_gemm_precision("tf32x3")
+    try:
+        y = blk(x)
+        g = _r(B, H * H, C, seed=6)
+        y.backward(g)
+    finally:
+        ops.set_gemm_precision("tf32")
+    xd = x.detach().double().requires_grad_()
+    yo = ao.transformer_block(sd, "", xd, 2, 0, False, "frfn", None, sm.double() if sm is not None else None)
+    yo.backward(g.double())
+    errs = {"out": rel_l2(y, yo), "dx": rel_l2(x.grad, xd.grad)}
+    for n, p in blk.named_parameters():
+        errs[n] = rel_l2(p.grad, sd[n].grad)
+    assert max(errs.values()) < 2e-4, errs
+    # default (tf32, tcgen05) mode within the north-star tolerance
+    x2 = x.detach().clone().requires_grad_()
+    blk.zero_grad()
+    y2 = blk(x2)
+    y2.backward(g)
+    assert rel_l2(y2, yo) < 1e-3 and rel_l2(x2.grad, xd.grad) < 2e-3

@@ -400,6 +400,61 @@ __global__ void col2im_4x4s2_kernel(const float* __restrict__ dcol, float* __res
     }
 }
 
+// dense 3x3 stride-1 pad-1 convolution as a GEMM: col[row][(ky*3+kx)*C + ci] = x[b][y+ky-1][x+kx-1][ci]
+__global__ void im2col_3x3_kernel(const float* __restrict__ x, long long ld, float* __restrict__ col, int B, int H,
+                                  int W, int C, int rnd) {
+    const int C4 = C / 4;
+    const long long total = (long long)B * H * W * 9 * C4;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total;
+         i += (long long)gridDim.x * blockDim.x) {
+        const int c4 = (int)(i % C4);
+        long long r = i / C4;
+        const int tap = (int)(r % 9);
+        r /= 9;
+        const int xx = (int)(r % W);
+        r /= W;
+        const int y = (int)(r % H);
+        const int b = (int)(r / H);
+        const int sy = y + tap / 3 - 1, sx = xx + tap % 3 - 1;
+        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (sy >= 0 && sy < H && sx >= 0 && sx < W)
+            v = *reinterpret_cast<const float4*>(x + (((long long)b * H + sy) * W + sx) * ld + c4 * 4);
+        if (rnd) v = make_float4(tf32_round(v.x), tf32_round(v.y), tf32_round(v.z), tf32_round(v.w));
+        reinterpret_cast<float4*>(col)[i] = v;
+    }
+}
+
+// dx[b][y][x][ci] (+)= sum_taps dcol[(b, y-ky+1, x-kx+1)][tap*C + ci]
+__global__ void col2im_3x3_kernel(const float* __restrict__ dcol, float* __restrict__ dx, long long ld_dx, int B, int H,
+                                  int W, int C, int accumulate) {
+    const int C4 = C / 4;
+    const long long total = (long long)B * H * W * C4;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total;
+         i += (long long)gridDim.x * blockDim.x) {
+        const int c4 = (int)(i % C4);
+        long long r = i / C4;
+        const int xx = (int)(r % W);
+        r /= W;
+        const int y = (int)(r % H);
+        const int b = (int)(r / H);
+        float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+        for (int tap = 0; tap < 9; ++tap) {
+            const int oy = y - (tap / 3) + 1, ox = xx - (tap % 3) + 1;
+            if (oy < 0 || oy >= H || ox < 0 || ox >= W) continue;
+            const float4 v = *reinterpret_cast<const float4*>(
+                dcol + ((((long long)b * H + oy) * W + ox) * 9 + tap) * C + c4 * 4);
+            acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
+        }
+        float4* d = reinterpret_cast<float4*>(dx + (((long long)b * H + y) * W + xx) * ld_dx + c4 * 4);
+        if (accumulate) {
+            const float4 o = *d;
+            acc.x += o.x; acc.y += o.y; acc.z += o.z; acc.w += o.w;
+        }
+        *d = acc;
+    }
+}
+
 __global__ void pixel_scatter_2x2_kernel(const float* __restrict__ g, const float* __restrict__ bias,
                                          float* __restrict__ out, long long ld_out, int B, int H, int W, int Cout) {
     const long long total = (long long)B * H * W * Cout;
@@ -624,6 +679,26 @@ extern "C" int uwr_col2im_4x4s2(const float* dcol, float* dtokens, int B, int H,
     const long long total = (long long)B * H * W * (C / 4);
     col2im_4x4s2_kernel<<<ew_blocks(total, 256), 256, 0, stream>>>(dcol, dtokens, B, H, W, C);
     UWR_CHECK_LAUNCH("col2im_4x4s2_kernel");
+    return 0;
+}
+
+extern "C" int uwr_im2col_3x3(const float* tokens, long long ld, float* col, int B, int H, int W, int C,
+                              uwr_stream_t stream_) {
+    cudaStream_t stream = (cudaStream_t)stream_;
+    UWR_REQUIRE(tokens && col && C % 4 == 0 && ld % 4 == 0, "uwr_im2col_3x3: bad args");
+    const long long total = (long long)B * H * W * 9 * (C / 4);
+    im2col_3x3_kernel<<<ew_blocks(total, 256), 256, 0, stream>>>(tokens, ld, col, B, H, W, C, uwr_round_outputs());
+    UWR_CHECK_LAUNCH("im2col_3x3_kernel");
+    return 0;
+}
+
+extern "C" int uwr_col2im_3x3(const float* dcol, float* dtokens, long long ld, int B, int H, int W, int C,
+                              int accumulate, uwr_stream_t stream_) {
+    cudaStream_t stream = (cudaStream_t)stream_;
+    UWR_REQUIRE(dcol && dtokens && C % 4 == 0 && ld % 4 == 0, "uwr_col2im_3x3: bad args");
+    const long long total = (long long)B * H * W * (C / 4);
+    col2im_3x3_kernel<<<ew_blocks(total, 256), 256, 0, stream>>>(dcol, dtokens, ld, B, H, W, C, accumulate);
+    UWR_CHECK_LAUNCH("col2im_3x3_kernel");
     return 0;
 }
 

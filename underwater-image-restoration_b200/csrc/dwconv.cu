@@ -120,7 +120,8 @@ __global__ void __launch_bounds__(DW_THREADS) dwconv_fwd_kernel(const float* __r
 __global__ void __launch_bounds__(256) gelu_gate_bwd_kernel(const float* __restrict__ dh2,
                                                             const float* __restrict__ u, long long ld_u,
                                                             const float* __restrict__ v, float* __restrict__ dv,
-                                                            float* __restrict__ du, long long rows, int Ch, int mode) {
+                                                            float* __restrict__ du, long long rows, int Ch, int mode,
+                                                            int rnd) {
     const long long total = rows * Ch;
     for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total;
          i += (long long)gridDim.x * blockDim.x) {
@@ -131,7 +132,8 @@ __global__ void __launch_bounds__(256) gelu_gate_bwd_kernel(const float* __restr
         if (mode == 1) {
             const float u2 = u[r * ld_u + Ch + c];
             g *= gelu_f(u2);
-            du[r * ld_u + Ch + c] = d * gelu_f(vv) * gelu_grad_f(u2);
+            const float g2 = d * gelu_f(vv) * gelu_grad_f(u2);
+            du[r * ld_u + Ch + c] = rnd ? tf32_round(g2) : g2;
         }
         dv[i] = g;
     }
@@ -316,7 +318,7 @@ extern "C" int uwr_gelu_gate_bwd(const float* dh2, const float* u, long long ld_
     const long long total = rows * Ch;
     long long blocks = (total + 255) / 256;
     if (blocks > 16LL * uwr_sm_count()) blocks = 16LL * uwr_sm_count();
-    gelu_gate_bwd_kernel<<<(unsigned)blocks, 256, 0, stream>>>(dh2, u, ld_u, v, dv, du, rows, Ch, mode);
+    gelu_gate_bwd_kernel<<<(unsigned)blocks, 256, 0, stream>>>(dh2, u, ld_u, v, dv, du, rows, Ch, mode, uwr_round_outputs());
     UWR_CHECK_LAUNCH("gelu_gate_bwd_kernel");
     return 0;
 }

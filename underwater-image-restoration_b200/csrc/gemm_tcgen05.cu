@@ -47,6 +47,7 @@ struct T5Params {
     const float* rowscale;
     int rows_per_group;
     int epilogue;
+    int round_out;
 };
 
 // ---------------------------------------------------------------------------------- PTX wrappers
@@ -359,6 +360,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_const
                         o.x *= gelu_grad_f(rv[i].x); o.y *= gelu_grad_f(rv[i].y);
                         o.z *= gelu_grad_f(rv[i].z); o.w *= gelu_grad_f(rv[i].w);
                     }
+                    if (p.round_out) o = make_float4(tf32_round(o.x), tf32_round(o.y), tf32_round(o.z), tf32_round(o.w));
                     if (col_ok && row < p.M) *reinterpret_cast<float4*>(cbase + (long long)row * p.ldc + col) = o;
                 }
                 __syncwarp();  // the staging buffer is reused by the next chunk
@@ -537,6 +539,7 @@ extern "C" int uwr_gemm_tcgen05(const uwr_gemm_desc* d, uwr_stream_t stream_) {
     p.bias = d->bias; p.R = d->R; p.ldr = d->ldr;
     p.rowscale = d->rowscale; p.rows_per_group = d->rows_per_group > 0 ? d->rows_per_group : 1;
     p.epilogue = d->epilogue;
+    p.round_out = d->round_out;
     if (sp.splits > 1) {
         const size_t need = (size_t)sp.splits * d->M * d->N * sizeof(float);
         UWR_REQUIRE(d->workspace && d->workspace_bytes >= need, "uwr_gemm_tcgen05: workspace too small (%zu < %zu)",

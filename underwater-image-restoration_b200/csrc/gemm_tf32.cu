@@ -35,6 +35,7 @@ struct GemmParams {
     int rows_per_group;
     float* colsum;  // TN only: per-split partial column sums live at colsum + z*M
     long long c_split_stride;
+    int round_out;
 };
 
 template <int BN, bool A_KM, bool B_NK>
@@ -260,6 +261,10 @@ __global__ void __launch_bounds__(NTHREADS, X3 ? 1 : 2) gemm_tf32_kernel(const G
                     v0 *= r.x;
                     v1 *= r.y;
                 }
+                if (p.round_out) {
+                    v0 = tf32_round(v0);
+                    v1 = tf32_round(v1);
+                }
                 *reinterpret_cast<float2*>(Cout + (long long)row * p.ldc + col) = make_float2(v0, v1);
             }
         }
@@ -412,6 +417,7 @@ extern "C" int uwr_gemm_tf32(const uwr_gemm_desc* d, uwr_stream_t stream_) {
     p.R = d->R; p.ldr = d->ldr;
     p.rowscale = d->rowscale; p.rows_per_group = d->rows_per_group > 0 ? d->rows_per_group : 1;
     p.colsum = d->colsum; p.c_split_stride = 0;
+    p.round_out = d->round_out;
 
     float* ws_c = nullptr;
     float* ws_cs = nullptr;

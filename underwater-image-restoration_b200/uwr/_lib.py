@@ -38,6 +38,7 @@ class GemmDesc(C.Structure):
         ("rowscale", c_fp), ("rows_per_group", c_int),
         ("colsum", c_fp),
         ("workspace", c_fp), ("workspace_bytes", c_sz),
+        ("round_out", c_int),
     ]
 
 
@@ -93,6 +94,8 @@ SIGNATURES = {
                                     c_int, c_int, c_int, c_int, c_stream]),
     "uwr_im2col_4x4s2": (c_int, [c_fp, c_ll, c_fp, c_int, c_int, c_int, c_int, c_stream]),
     "uwr_col2im_4x4s2": (c_int, [c_fp, c_fp, c_int, c_int, c_int, c_int, c_stream]),
+    "uwr_im2col_3x3": (c_int, [c_fp, c_ll, c_fp, c_int, c_int, c_int, c_int, c_stream]),
+    "uwr_col2im_3x3": (c_int, [c_fp, c_fp, c_ll, c_int, c_int, c_int, c_int, c_int, c_stream]),
     "uwr_pixel_scatter_2x2": (c_int, [c_fp, c_fp, c_fp, c_ll, c_int, c_int, c_int, c_int, c_stream]),
     "uwr_pixel_gather_2x2": (c_int, [c_fp, c_ll, c_fp, c_int, c_int, c_int, c_int, c_stream]),
     "uwr_copy2d": (c_int, [c_fp, c_ll, c_fp, c_ll, c_ll, c_int, c_int, c_stream]),

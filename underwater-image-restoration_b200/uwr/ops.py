@@ -113,7 +113,7 @@ def _ws(nbytes, like):
 # --------------------------------------------------------------------------------------------
 def gemm(A, B, C_out, M, N, K, *, lda, ldb, ldc, a_km=False, b_nk=True, B2=None, n_split=0,
          bias=None, bias2=None, epilogue=EPI_NONE, R=None, ldr=0, rowscale=None, rows_per_group=0,
-         colsum=None, t5=False):
+         colsum=None, t5=False, round_out=False):
     """C[M,N] = epi(opA(A) opB(B)); see uwr_gemm_tf32 in include/uwr_b200.h.  t5=True: the operands are
     TF32-rounded already, use the tcgen05/TMA kernel when the descriptor is supported."""
     d = GemmDesc()
@@ -127,6 +127,7 @@ def gemm(A, B, C_out, M, N, K, *, lda, ldb, ldc, a_km=False, b_nk=True, B2=None,
     d.R, d.ldr = _ptr(R), ldr
     d.rowscale, d.rows_per_group = _ptr(rowscale), rows_per_group
     d.colsum = _ptr(colsum)
+    d.round_out = int(round_out and _PASSES == 1)
     nbytes = 4 * (M * K + K * N + M * N + (M * N if R is not None else 0))
     lay = ("TN" if a_km else ("NT" if b_nk else "NN"))
     ws = None
@@ -147,7 +148,7 @@ def gemm(A, B, C_out, M, N, K, *, lda, ldb, ldc, a_km=False, b_nk=True, B2=None,
 
 
 def linear(x2d, weight, bias=None, *, weight2=None, bias2=None, residual=None, rowscale=None,
-           rows_per_group=0, out=None, t5=False):
+           rows_per_group=0, out=None, t5=False, round_out=False):
     """y = x W^T + b  (optionally [W;W2], optionally residual + s*(.)). x2d: (M,K) view, row stride lda."""
     M, K = x2d.shape
     lda = x2d.stride(0)
@@ -158,7 +159,7 @@ def linear(x2d, weight, bias=None, *, weight2=None, bias2=None, residual=None, r
     gemm(x2d, weight, out, M, N, K, lda=lda, ldb=weight.stride(0), ldc=out.stride(0), b_nk=True,
          B2=weight2, n_split=weight.shape[0] if weight2 is not None else 0, bias=bias, bias2=bias2,
          epilogue=epi, R=residual, ldr=residual.stride(0) if residual is not None else 0,
-         rowscale=rowscale, rows_per_group=rows_per_group, t5=t5)
+         rowscale=rowscale, rows_per_group=rows_per_group, t5=t5, round_out=round_out)
     return out
 
 
@@ -385,6 +386,21 @@ def col2im_4x4s2(dcol, B, H, W, Cc):
     dx = _empty((B * H * W, Cc), dcol)
     _run("uwr_col2im_4x4s2", "", 0, 0.0, _ptr(dcol), _ptr(dx), B, H, W, Cc)
     return dx
+
+
+def im2col_3x3(tokens2d, B, H, W, Cc):
+    """tokens2d: (B*H*W, >=Cc) view (row stride = ld); returns col (B*H*W, 9*Cc), K order (ky,kx,ci)."""
+    col = _empty((B * H * W, 9 * Cc), tokens2d)
+    _run("uwr_im2col_3x3", f"B{B} H{H} C{Cc}", 4 * B * H * W * Cc * 10, 0.0, _ptr(tokens2d), tokens2d.stride(0),
+         _ptr(col), B, H, W, Cc)
+    return col
+
+
+def col2im_3x3(dcol, out2d, B, H, W, Cc, accumulate=False):
+    """out2d[:, :Cc] (+)= gathered dcol; out2d is a (B*H*W, >=Cc) view."""
+    _run("uwr_col2im_3x3", f"B{B} H{H} C{Cc}", 4 * B * H * W * Cc * 10, 0.0, _ptr(dcol), _ptr(out2d),
+         out2d.stride(0), B, H, W, Cc, int(accumulate))
+    return out2d
 
 
 def pixel_scatter_2x2(g, bias, out2d, B, H, W, Cout):
