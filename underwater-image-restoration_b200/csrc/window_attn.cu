@@ -55,18 +55,47 @@ __device__ __forceinline__ int bias_index(int i, int j) {
     return ((i >> 3) - (j >> 3) + WIN - 1) * (2 * WIN - 1) + ((i & 7) - (j & 7) + WIN - 1);
 }
 
-// stage a 64 x HD tile (fp32) into shared memory [64][HD+4]
+// stage 64 x HD tiles (fp32) into shared memory [64][HD+4].  All global loads of a batch are issued
+// before the first shared-memory store (the one-load-at-a-time version left the kernel stalled on
+// long_scoreboard with ~12% of the warps active).
 template <int HD>
-__device__ __forceinline__ void stage_tile(float* dst, const float* src, long long ld, int col_off,
-                                           const long long* rows, float mul) {
+struct TileSrc {
+    const float* base;
+    long long ld;
+    int col;
+    float mul;
+    float* dst;
+};
+
+template <int HD, int NT>
+__device__ __forceinline__ void stage_tiles(const TileSrc<HD> (&t)[NT], const long long* rows) {
     constexpr int ST = HD + 4;
     constexpr int V4 = HD / 4;
-    for (int idx = threadIdx.x; idx < NTOK * V4; idx += ATT_THREADS) {
-        const int r = idx / V4, c4 = (idx % V4) * 4;
-        const float4 v = *reinterpret_cast<const float4*>(src + rows[r] * ld + col_off + c4);
-        // full fp32 is kept in shared memory: S and dP use error-compensated 3xTF32 (hi/lo split at
-        // fragment load) because softmax' and the (dP - rowdot) cancellation amplify operand rounding
-        *reinterpret_cast<float4*>(dst + r * ST + c4) = make_float4(v.x * mul, v.y * mul, v.z * mul, v.w * mul);
+    constexpr int PER = NTOK * V4 / ATT_THREADS;  // float4 per thread per tile
+    constexpr int GROUP = (PER * NT <= 16) ? NT : 1;  // tiles whose loads are in flight together
+#pragma unroll
+    for (int g0 = 0; g0 < NT; g0 += GROUP) {
+        float4 buf[GROUP][PER];
+#pragma unroll
+        for (int g = 0; g < GROUP; ++g)
+#pragma unroll
+            for (int i = 0; i < PER; ++i) {
+                const int idx = threadIdx.x + i * ATT_THREADS;
+                const int r = idx / V4, c4 = (idx % V4) * 4;
+                buf[g][i] = *reinterpret_cast<const float4*>(t[g0 + g].base + rows[r] * t[g0 + g].ld + t[g0 + g].col + c4);
+            }
+#pragma unroll
+        for (int g = 0; g < GROUP; ++g)
+#pragma unroll
+            for (int i = 0; i < PER; ++i) {
+                const int idx = threadIdx.x + i * ATT_THREADS;
+                const int r = idx / V4, c4 = (idx % V4) * 4;
+                const float m = t[g0 + g].mul;
+                // full fp32 is kept in shared memory: S, dP, dQ, dK use error-compensated 3xTF32 (hi/lo
+                // split at fragment load) because softmax' and the dS cancellations amplify rounding
+                *reinterpret_cast<float4*>(t[g0 + g].dst + r * ST + c4) =
+                    make_float4(buf[g][i].x * m, buf[g][i].y * m, buf[g][i].z * m, buf[g][i].w * m);
+            }
     }
 }
 
@@ -213,9 +242,12 @@ __global__ void __launch_bounds__(ATT_THREADS) attn_fwd_kernel(const AttnParams 
         reg[threadIdx.x] = p.shift > 0 ? region_code(p, wy, wx, threadIdx.x) : 0;
     }
     __syncthreads();
-    stage_tile<HD>(Qs, p.q, p.ld_q, p.q_off + h * HD, rows, p.scale);
-    stage_tile<HD>(Ks, p.kv, p.ld_kv, p.k_off + h * HD, rows, 1.0f);
-    stage_tile<HD>(Vs, p.kv, p.ld_kv, p.v_off + h * HD, rows, 1.0f);
+    {
+        const TileSrc<HD> src[3] = {{p.q, p.ld_q, p.q_off + h * HD, p.scale, Qs},
+                                    {p.kv, p.ld_kv, p.k_off + h * HD, 1.0f, Ks},
+                                    {p.kv, p.ld_kv, p.v_off + h * HD, 1.0f, Vs}};
+        stage_tiles<HD, 3>(src, rows);
+    }
     __syncthreads();
 
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -252,19 +284,23 @@ __global__ void __launch_bounds__(ATT_THREADS) attn_fwd_kernel(const AttnParams 
 // Backward.  grid = (ctas_per_head, heads); each CTA walks the (batch, window) tiles of one head
 // so that the relative-position-bias gradient accumulates in registers and is binned once.
 template <int HD>
-__global__ void __launch_bounds__(ATT_THREADS, HD <= 32 ? 2 : 1) attn_bwd_kernel(const AttnParams p, const float* __restrict__ dout,
-                                                               long long ld_dout, float* __restrict__ dq_buf,
-                                                               float* __restrict__ dkv_buf,
-                                                               float* __restrict__ partials) {
+__global__ void __launch_bounds__(ATT_THREADS, HD <= 32 ? 3 : 1) attn_bwd_kernel(const AttnParams p,
+                                                                              const float* __restrict__ dout,
+                                                                              long long ld_dout,
+                                                                              float* __restrict__ dq_buf,
+                                                                              float* __restrict__ dkv_buf,
+                                                                              float* __restrict__ partials) {
     constexpr int ST = HD + 4;
+    // the transposed products dV = P^T dO and dK = dS^T q need P / dS in shared memory; K and V are dead
+    // by then, so (for HD >= 32) the 64 x 72 staging buffer aliases their tiles
+    constexpr bool ALIAS = (2 * NTOK * ST >= NTOK * PS_STRIDE);
     extern __shared__ __align__(16) float smem[];
     float* Qs = smem;
-    float* Ks = Qs + NTOK * ST;
+    float* dOs = Qs + NTOK * ST;
+    float* Ks = dOs + NTOK * ST;
     float* Vs = Ks + NTOK * ST;
-    float* dOs = Vs + NTOK * ST;
-    float* Ps = dOs + NTOK * ST;
-    float* dSs = Ps + NTOK * PS_STRIDE;
-    float* dSacc = dSs + NTOK * PS_STRIDE;  // running sum of dS over this CTA's tiles (bias-table gradient)
+    float* PD = ALIAS ? Ks : Vs + NTOK * ST;
+    float* dSacc = (ALIAS ? Vs + NTOK * ST : PD + NTOK * PS_STRIDE);  // running sum of dS (bias-table gradient)
     float* tab = dSacc + NTOK * PS_STRIDE;
     int* reg = reinterpret_cast<int*>(tab + 228);
     long long* rows = reinterpret_cast<long long*>(reg + NTOK);
@@ -297,50 +333,51 @@ __global__ void __launch_bounds__(ATT_THREADS, HD <= 32 ? 2 : 1) attn_bwd_kernel
             reg[threadIdx.x] = p.shift > 0 ? region_code(p, wy, wx, threadIdx.x) : 0;
         }
         __syncthreads();
-        stage_tile<HD>(Qs, p.q, p.ld_q, p.q_off + h * HD, rows, p.scale);
-        stage_tile<HD>(Ks, p.kv, p.ld_kv, p.k_off + h * HD, rows, 1.0f);
-        stage_tile<HD>(Vs, p.kv, p.ld_kv, p.v_off + h * HD, rows, 1.0f);
-        stage_tile<HD>(dOs, dout, ld_dout, h * HD, rows, 1.0f);
+        {
+            const TileSrc<HD> src[4] = {{p.q, p.ld_q, p.q_off + h * HD, p.scale, Qs},
+                                        {p.kv, p.ld_kv, p.k_off + h * HD, 1.0f, Ks},
+                                        {p.kv, p.ld_kv, p.v_off + h * HD, 1.0f, Vs},
+                                        {dout, ld_dout, h * HD, 1.0f, dOs}};
+            stage_tiles<HD, 4>(src, rows);
+        }
         __syncthreads();
 
-        float s[8][4], p0[8][4], dp[8][4];
-        mma_rows_x_rowsT<HD>(s, Qs, Ks, r0, g, t);
-        add_bias_mask(s, tab, reg, r0, g, t, p.shift > 0);
-        row_softmax(s, p0);
-        mma_rows_x_rowsT<HD>(dp, dOs, Vs, r0, g, t);  // dP = dO V^T
-
-        // stage P (for dV) while S/P0/dP are live, then fold everything into dS
+        float pm[8][4], dp[8][4];  // final mixture P and dP -> dS
+        {
+            float s[8][4], p0[8][4];
+            mma_rows_x_rowsT<HD>(s, Qs, Ks, r0, g, t);
+            add_bias_mask(s, tab, reg, r0, g, t, p.shift > 0);
+            row_softmax(s, p0);
+            mma_rows_x_rowsT<HD>(dp, dOs, Vs, r0, g, t);  // dP = dO V^T
 #pragma unroll
-        for (int half = 0; half < 2; ++half) {
-            float rowdot = 0.f;
+            for (int half = 0; half < 2; ++half) {
+                float rowdot = 0.f;
 #pragma unroll
-            for (int nt = 0; nt < 8; ++nt)
+                for (int nt = 0; nt < 8; ++nt)
 #pragma unroll
-                for (int e = 0; e < 2; ++e) rowdot += dp[nt][half * 2 + e] * p0[nt][half * 2 + e];
-            rowdot += __shfl_xor_sync(0xffffffffu, rowdot, 1);
-            rowdot += __shfl_xor_sync(0xffffffffu, rowdot, 2);
-            const int i = r0 + g + half * 8;
+                    for (int e = 0; e < 2; ++e) rowdot += dp[nt][half * 2 + e] * p0[nt][half * 2 + e];
+                rowdot += __shfl_xor_sync(0xffffffffu, rowdot, 1);
+                rowdot += __shfl_xor_sync(0xffffffffu, rowdot, 2);
+                const int i = r0 + g + half * 8;
 #pragma unroll
-            for (int nt = 0; nt < 8; ++nt) {
-                float pv[2], dv[2];
+                for (int nt = 0; nt < 8; ++nt) {
+                    float dv[2];
 #pragma unroll
-                for (int e = 0; e < 2; ++e) {
-                    const int c = half * 2 + e;
-                    const float r = fmaxf(s[nt][c], 0.f);
-                    const float P0 = p0[nt][c], dP = dp[nt][c];
-                    g1 += dP * P0;
-                    g2 += dP * r * r;
-                    pv[e] = tf32_round(w0 * P0 + w1 * r * r);
-                    const float ds = w0 * P0 * (dP - rowdot) + w1 * 2.f * r * dP;
-                    dp[nt][c] = ds;  // dp now holds dS
-                    dv[e] = ds;  // full fp32: dK = dS^T q cancels the common part of q (3xTF32 below)
+                    for (int e = 0; e < 2; ++e) {
+                        const int c = half * 2 + e;
+                        const float r = fmaxf(s[nt][c], 0.f);
+                        const float P0 = p0[nt][c], dP = dp[nt][c];
+                        g1 += dP * P0;
+                        g2 += dP * r * r;
+                        pm[nt][c] = tf32_round(w0 * P0 + w1 * r * r);
+                        const float ds = w0 * P0 * (dP - rowdot) + w1 * 2.f * r * dP;
+                        dp[nt][c] = ds;  // dp now holds dS (full fp32: dQ / dK are error-compensated)
+                        dv[e] = ds;
+                    }
+                    float2* accp = reinterpret_cast<float2*>(dSacc + i * PS_STRIDE + nt * 8 + 2 * t);
+                    const float2 old = *accp;
+                    *accp = make_float2(old.x + dv[0], old.y + dv[1]);
                 }
-                const int j = nt * 8 + 2 * t;
-                *reinterpret_cast<float2*>(Ps + i * PS_STRIDE + j) = make_float2(pv[0], pv[1]);
-                *reinterpret_cast<float2*>(dSs + i * PS_STRIDE + j) = make_float2(dv[0], dv[1]);
-                float2* accp = reinterpret_cast<float2*>(dSacc + i * PS_STRIDE + j);
-                const float2 old = *accp;
-                *accp = make_float2(old.x + dv[0], old.y + dv[1]);
             }
         }
         // dQ = scale * dS K  (Qs holds scale*q, so the chain rule adds one more factor scale)
@@ -351,20 +388,29 @@ __global__ void __launch_bounds__(ATT_THREADS, HD <= 32 ? 2 : 1) attn_bwd_kernel
             for (int half = 0; half < 2; ++half) {
                 float* drow = dq_buf + rows[r0 + g + half * 8] * p.ld_q + p.q_off + h * HD;
 #pragma unroll
-                for (int n = 0; n < HD / 8; ++n)
-                {
-                    const float a = dq[n][half * 2] * p.scale, b = dq[n][half * 2 + 1] * p.scale;
+                for (int n = 0; n < HD / 8; ++n) {
+                    const float a = dq[n][half * 2] * p.scale, bq = dq[n][half * 2 + 1] * p.scale;
                     *reinterpret_cast<float2*>(drow + n * 8 + 2 * t) =
-                        p.rnd ? make_float2(tf32_round(a), tf32_round(b)) : make_float2(a, b);
+                        p.rnd ? make_float2(tf32_round(a), tf32_round(bq)) : make_float2(a, bq);
                 }
             }
         }
-        __syncthreads();  // Ps / dSs complete
+        if (ALIAS) __syncthreads();  // everyone is done with K and V before P overwrites them
 
-        // dV[j,:] = sum_i P[i,j] dO[i,:]   and   dK[j,:] = sum_i dS[i,j] (scale q)[i,:]
+        // dV[j,:] = sum_i P[i,j] dO[i,:]   then   dK[j,:] = sum_i dS[i,j] (scale q)[i,:]
 #pragma unroll
         for (int which = 0; which < 2; ++which) {
-            const float* Am = which == 0 ? Ps : dSs;
+            if (which == 1) __syncthreads();  // dV readers are done with the staging buffer
+#pragma unroll
+            for (int half = 0; half < 2; ++half) {
+                const int i = r0 + g + half * 8;
+#pragma unroll
+                for (int nt = 0; nt < 8; ++nt)
+                    *reinterpret_cast<float2*>(PD + i * PS_STRIDE + nt * 8 + 2 * t) =
+                        which == 0 ? make_float2(pm[nt][half * 2], pm[nt][half * 2 + 1])
+                                   : make_float2(dp[nt][half * 2], dp[nt][half * 2 + 1]);
+            }
+            __syncthreads();
             const float* Bm = which == 0 ? dOs : Qs;
             float acc[HD / 8][4];
 #pragma unroll
@@ -374,10 +420,10 @@ __global__ void __launch_bounds__(ATT_THREADS, HD <= 32 ? 2 : 1) attn_bwd_kernel
 #pragma unroll
             for (int kb = 0; kb < 8; ++kb) {
                 uint32_t a[4], al[4];
-                split_tf32(Am[(kb * 8 + t) * PS_STRIDE + r0 + g], a[0], al[0]);
-                split_tf32(Am[(kb * 8 + t) * PS_STRIDE + r0 + g + 8], a[1], al[1]);
-                split_tf32(Am[(kb * 8 + t + 4) * PS_STRIDE + r0 + g], a[2], al[2]);
-                split_tf32(Am[(kb * 8 + t + 4) * PS_STRIDE + r0 + g + 8], a[3], al[3]);
+                split_tf32(PD[(kb * 8 + t) * PS_STRIDE + r0 + g], a[0], al[0]);
+                split_tf32(PD[(kb * 8 + t) * PS_STRIDE + r0 + g + 8], a[1], al[1]);
+                split_tf32(PD[(kb * 8 + t + 4) * PS_STRIDE + r0 + g], a[2], al[2]);
+                split_tf32(PD[(kb * 8 + t + 4) * PS_STRIDE + r0 + g + 8], a[3], al[3]);
 #pragma unroll
                 for (int n = 0; n < HD / 8; ++n) {
                     uint32_t bb[2], bl[2];
@@ -468,7 +514,9 @@ int bwd_ctas_per_head(const uwr_attn_desc* d) {
 template <int HD>
 constexpr int fwd_smem() { return (3 * NTOK * (HD + 4) + 228 + NTOK) * 4 + NTOK * 8; }
 template <int HD>
-constexpr int bwd_smem() { return (4 * NTOK * (HD + 4) + 3 * NTOK * PS_STRIDE + 228 + NTOK) * 4 + NTOK * 8; }
+constexpr int bwd_smem() {
+    return (4 * NTOK * (HD + 4) + ((2 * (HD + 4) >= PS_STRIDE) ? 1 : 2) * NTOK * PS_STRIDE + 228 + NTOK) * 4 + NTOK * 8;
+}
 
 int fill_params(const uwr_attn_desc* d, AttnParams& p, const char* who) {
     UWR_REQUIRE(d && d->q && d->kv && d->bias_table, "%s: null pointer", who);
