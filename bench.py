@@ -229,19 +229,24 @@ def run_ours(args):
             f[0] += r["ms_total"]; f[1] += r["bytes_per_launch"] * r["launches"]
             f[2] += r["flops_per_launch"] * r["launches"]; f[3] += r["launches"]
         hbm, tf_bf16, src = _peaks()
-        top = table[0]
-        ai = top["flops_per_launch"] / max(top["bytes_per_launch"], 1.0)
+        # dominant kernel = the family with the largest share of the step; its roofline figure is the
+        # family aggregate (sum of algorithmic bytes or flops over its launches / sum of their durations)
+        fam_name, fv = max(((k, v) for k, v in fam.items() if v[1] > 0 or v[2] > 0), key=lambda kv: kv[1][0])
+        top = next(r for r in table if r["kernel"] == fam_name)
+        gbs, tfl = fv[1] / fv[0] / 1e6, fv[2] / fv[0] / 1e9
+        ai = fv[2] / max(fv[1], 1.0)
         tf32_peak = tf_bf16 / 2.0  # dense TF32 is half the bf16 rate
         tensor_bound = ai > (tf32_peak * 1e12) / (hbm * 1e9)
         if tensor_bound:
-            roofline = {"bound": "tensor", "achieved": top["tflops"], "peak": tf32_peak, "unit": "TFLOP/s",
-                        "frac": top["tflops"] / tf32_peak}
+            roofline = {"bound": "tensor", "achieved": tfl, "peak": tf32_peak, "unit": "TFLOP/s", "frac": tfl / tf32_peak}
         else:
-            roofline = {"bound": "hbm", "achieved": top["gbs"], "peak": hbm, "unit": "GB/s",
-                        "frac": top["gbs"] / hbm}
-        roofline.update({"traffic": None, "kernel": f"{top['kernel']} [{top['shape']}]",
-                         "ms_per_launch": top["ms_avg"], "launches_per_step": top["launches"],
-                         "share_of_step": top["ms_total"] / sum(r["ms_total"] for r in table),
+            roofline = {"bound": "hbm", "achieved": gbs, "peak": hbm, "unit": "GB/s", "frac": gbs / hbm}
+        total_ms = sum(r["ms_total"] for r in table)
+        roofline.update({"traffic": None, "kernel": fam_name, "launches_per_step": fv[3],
+                         "ms_per_launch": fv[0] / fv[3], "share_of_step": fv[0] / total_ms,
+                         "arithmetic_intensity": ai,
+                         "top_shape": {"shape": top["shape"], "ms_per_launch": top["ms_avg"], "gbs": top["gbs"],
+                                       "tflops": top["tflops"], "launches": top["launches"]},
                          "peak_source": f"MEASURED_PEAKS.json ({src}); tf32 peak = bf16 sustained / 2"})
         if args.profile_out:
             os.makedirs(os.path.dirname(os.path.abspath(args.profile_out)), exist_ok=True)

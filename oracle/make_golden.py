@@ -70,6 +70,27 @@ def main():
     torch.save({"state": {k: v.clone() for k, v in blk.state_dict().items()}, "x": x, "y": y.detach(),
                 "rel_index": blk.attn.relative_position_index.clone()}, os.path.join(OUT, "block_shift.pt"))
 
+    # ---- NewBigFRFNModel (patch P1: token->NCHW transpose before output_proj, model.py:435-437 vs 637)
+    from src.model.model import MyBigFRFNModel
+    torch.manual_seed(1234)
+    nb = MyBigFRFNModel()
+    nkeys = [(k, list(v.shape), str(v.dtype), sha(v)) for k, v in nb.state_dict().items()]
+    orig = nb.output_proj.forward
+
+    def patched(tk):
+        b, l, c = tk.shape
+        h = int(l ** 0.5)
+        return orig(tk.transpose(1, 2).reshape(b, c, h, h).contiguous())
+    nb.output_proj.forward = patched
+    nb.eval()
+    gg = torch.Generator().manual_seed(2024)
+    xr = torch.rand(1, 3, 128, 128, generator=gg) * 2 - 1
+    import io, contextlib
+    with torch.no_grad(), contextlib.redirect_stdout(io.StringIO()):
+        yr = nb(xr)
+    torch.save({"state_dict_sha1": nkeys, "out": yr, "seed_weights": 1234, "seed_data": 2024},
+               os.path.join(OUT, "newbigfrfn_128.pt"))
+
     # ---- losses / metrics known answers
     torch.manual_seed(0)
     p = torch.rand(2, 3, 256, 256)

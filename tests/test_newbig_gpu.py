@@ -1,0 +1,65 @@
+"""NewBigFRFNModel (BASELINE config 3's architecture) on the uwr kernels vs the CPU oracle (patch P1),
+same-cotangent protocol, eval and train mode (injected encoder DropPath masks)."""
+import pytest
+import torch
+
+from conftest import rel_l2
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.mark.parametrize("train", [False, True])
+def test_newbigfrfn_vs_oracle_128(train):
+    from oracle import newbig_oracle
+    from uwr.ast import DropPath
+    from uwr.newbig import MyBigFRFNModel
+    B, S = 1 if not train else 2, 128
+    torch.manual_seed(1234)
+    model = MyBigFRFNModel()
+    sd_cpu = {k: v.detach().clone() for k, v in model.state_dict().items()}
+    model = model.cuda()
+    g = torch.Generator().manual_seed(2024)
+    raw = torch.rand(B, 3, S, S, generator=g) * 2 - 1
+    cot = torch.randn(B, 3, S, S, generator=g) * 1e-3
+    drop = {}
+    if train:
+        model.train()
+        gm = torch.Generator().manual_seed(7)
+        for name, mod in model.named_modules():
+            if isinstance(mod, DropPath) and name.endswith("drop_path2"):
+                pre = name[: -len("drop_path2")]
+                keep = 1.0 - mod.drop_prob
+                mf = torch.bernoulli(torch.full((B,), keep), generator=gm) / keep
+                ms = torch.bernoulli(torch.full((B,), keep), generator=gm) / keep
+                drop[pre] = (mf, ms)
+                blk = dict(model.named_modules())[pre[:-1]]
+                blk.drop_path2.scale = (lambda batch, device, _m=mf: _m.to(device).float())
+                blk.drop_path.scale = (lambda batch, device, _m=ms: _m.to(device).float())
+    else:
+        model.eval()
+    out = model(raw.cuda())
+    out.backward(cot.cuda())
+    sd_o = {k: (v.clone().requires_grad_() if v.is_floating_point() and v.dim() > 0 and "dwt" not in k else v)
+            for k, v in sd_cpu.items()}
+    out_o = newbig_oracle.newbig_frfn_forward(sd_o, raw, drop_scales=drop)
+    out_o.backward(cot)
+    e_out = rel_l2(out, out_o)
+    e_res = rel_l2(out - raw.cuda(), out_o - raw)
+    named = dict(model.named_parameters())
+    live = [n for n, v in sd_o.items() if getattr(v, "grad", None) is not None]
+    gnorm = torch.sqrt(sum((sd_o[n].grad.double() ** 2).sum() for n in live)).item()
+    tot, worst = 0.0, (0.0, "")
+    for n in live:
+        assert named[n].grad is not None, n
+        d = (named[n].grad.double().cpu() - sd_o[n].grad.double()).norm().item()
+        tot += d * d
+        r = d / max(sd_o[n].grad.norm().item(), 1e-3 * gnorm)
+        worst = max(worst, (r, n))
+    dead = [n for n in named if n not in live]
+    print(f"NewBigFRFN parity train={train}: out {e_out:.2e} residual {e_res:.2e} grads {tot ** 0.5 / gnorm:.2e} "
+          f"worst {worst[1]} {worst[0]:.2e}; {len(dead)} dead tensors")
+    assert e_out < 1e-3 and e_res < 2e-3
+    assert tot ** 0.5 / gnorm < 2e-3
+    # dead parameters of the Fourier mode get no gradient, as in the reference
+    for n in dead:
+        assert named[n].grad is None or float(named[n].grad.abs().max()) == 0.0, n

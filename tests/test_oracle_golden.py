@@ -130,3 +130,29 @@ def test_oracle_vs_live_reference_train_mode_masks():
             dsc[pre] = (ms[0], ms[1]) if len(ms) == 2 else (None, ms[0])
     yo = ast_oracle.ast_forward(sd, x, img_size=128, drop_scales=dsc)
     assert rel_l2(yo, y) < 1e-6
+
+
+def test_newbigfrfn_state_dict_and_oracle_match_reference_golden():
+    """632-entry state_dict (incl. Haar buffers) is RNG-identical to the reference; the oracle
+    (with patch P1) reproduces the patched reference output."""
+    from oracle import newbig_oracle
+    from uwr.newbig import MyBigFRFNModel
+    g = _load("newbigfrfn_128.pt")
+    torch.manual_seed(g["seed_weights"])
+    model = MyBigFRFNModel()
+    got = [(k, list(v.shape), str(v.dtype), _sha(v)) for k, v in model.state_dict().items()]
+    assert len(got) == 632
+    assert got == g["state_dict_sha1"]
+    assert sum(p.numel() for p in model.parameters()) == 35949007  # SURVEY.md §8a row 21
+    gen = torch.Generator().manual_seed(g["seed_data"])
+    x = torch.rand(1, 3, 128, 128, generator=gen) * 2 - 1
+    with torch.no_grad():
+        y = newbig_oracle.newbig_frfn_forward(model.state_dict(), x)
+    assert rel_l2(y, g["out"]) < 1e-6
+
+
+def test_broken_reference_models_are_names_only():
+    import uwr
+    for name in ("NewModel", "NewBigModel"):
+        with pytest.raises(NotImplementedError, match="registry name only"):
+            uwr.init_model(name)

@@ -1,0 +1,147 @@
+"""Generic autograd functions over the uwr kernels (used by the NewBig/FRFN family, where blocks are
+composed with a few ATen pieces — FFTs, pixel shuffles — that are not hand-written yet):
+
+  LinearFn      y = x W^T + b on token matrices (tcgen05 path when `rounded` promises TF32 operands)
+  LayerNormFn   nn.LayerNorm over the channel axis
+  Conv3x3Fn     dense 3x3 s1 p1 convolution on tokens = im2col + GEMM
+  AttnFn        sparse window attention incl. q / kv / output projections (self or cross)
+"""
+import torch
+from torch.autograd.function import once_differentiable
+
+from . import ops
+
+
+def _c(t):
+    return t if t.is_contiguous() else t.contiguous()
+
+
+class LinearFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, w, b, rounded):
+        x = _c(x)
+        x2 = x.view(-1, x.shape[-1])
+        t5 = bool(rounded)
+        y = ops.linear(x2, ops.rounded_weight(w) if t5 else w, b, t5=t5)
+        ctx.save_for_backward(x2, w)
+        ctx.meta = (x.shape, b is not None)
+        return y.view(*x.shape[:-1], w.shape[0])
+
+    @staticmethod
+    @once_differentiable
+    def backward(ctx, dy):
+        x2, w = ctx.saved_tensors
+        shape, has_b = ctx.meta
+        d = _c(dy).view(-1, w.shape[0])
+        dx = ops.linear_dgrad(d, w)
+        dw, db = ops.linear_wgrad(d, x2, want_bias=has_b)
+        return dx.view(shape), dw, db, None
+
+
+def linear(x, w, b=None, rounded=False):
+    return LinearFn.apply(x, w, b, rounded)
+
+
+class LayerNormFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, g, b):
+        x = _c(x)
+        x2 = x.view(-1, x.shape[-1])
+        y, mean, rstd = ops.layernorm_fwd(x2, g, b)
+        ctx.save_for_backward(x2, g, mean, rstd)
+        ctx.shape = x.shape
+        return y.view(x.shape)
+
+    @staticmethod
+    @once_differentiable
+    def backward(ctx, dy):
+        x2, g, mean, rstd = ctx.saved_tensors
+        dx, dg, db = ops.layernorm_bwd(_c(dy).view(x2.shape), x2, g, mean, rstd)
+        return dx.view(ctx.shape), dg, db
+
+
+def layernorm(x, mod):
+    return LayerNormFn.apply(x, mod.weight, mod.bias)
+
+
+class Conv3x3Fn(torch.autograd.Function):
+    """tokens (B, H*W, Cin) -> (B, H*W, Cout); weight (Cout, Cin, 3, 3), Cin % 4 == 0."""
+
+    @staticmethod
+    def forward(ctx, x, weight, bias, H, W):
+        x = _c(x)
+        B, L, Cin = x.shape
+        Cout = weight.shape[0]
+        wmat = ops.scale_round(weight.permute(0, 2, 3, 1).reshape(Cout, 9 * Cin), 9 * Cin)
+        col = ops.im2col_3x3(x.view(B * L, Cin), B, H, W, Cin)
+        y = ops.linear(col, wmat, bias, t5=True)
+        ctx.save_for_backward(x, wmat)
+        ctx.meta = (B, H, W, Cin, Cout, bias is not None)
+        return y.view(B, L, Cout)
+
+    @staticmethod
+    @once_differentiable
+    def backward(ctx, dy):
+        x, wmat = ctx.saved_tensors
+        B, H, W, Cin, Cout, has_b = ctx.meta
+        d = _c(dy).view(-1, Cout)
+        col = ops.im2col_3x3(x.view(-1, Cin), B, H, W, Cin)  # recomputed (9x the input)
+        dwm, db = ops.linear_wgrad(d, col, want_bias=has_b)
+        del col
+        dcol = ops.linear_dgrad(d, wmat)
+        dx = ops._empty((B * H * W, Cin), x)
+        ops.col2im_3x3(dcol, dx, B, H, W, Cin)
+        dw = dwm.view(Cout, 3, 3, Cin).permute(0, 3, 1, 2).contiguous()
+        return dx.view(B, H * W, Cin), dw, db, None, None
+
+
+class AttnFn(torch.autograd.Function):
+    """WindowAttention_Sparse (block.py:325-370) on un-partitioned token matrices: q projection of xq,
+    kv projection of xkv (cross, block.py:185-188) or of xq (self), 8x8 window attention (windows and
+    shift are address arithmetic), output projection."""
+
+    @staticmethod
+    def forward(ctx, xq, xkv, wq, bq, wkv, bkv, table, wparam, wp, bp, B, H, W, heads, shift):
+        xq = _c(xq)
+        M, Cc = xq.shape
+        hd = Cc // heads
+        scale = hd ** -0.5
+        if xkv is None:
+            qkv = ops.linear(xq, wq, bq, weight2=wkv, bias2=bkv)
+            q_buf, q_off, kv_buf, k_off, v_off = qkv, 0, qkv, Cc, 2 * Cc
+        else:
+            xkv = _c(xkv)
+            q_buf = ops.linear(xq, wq, bq)
+            kv_buf = ops.linear(xkv, wkv, bkv)
+            q_off, k_off, v_off = 0, 0, Cc
+        o = ops.window_attn_fwd(q_buf, q_off, kv_buf, k_off, v_off, table, wparam, B, H, W, heads, hd, shift, scale)
+        y = ops.linear(o, ops.rounded_weight(wp), bp, t5=True)
+        ctx.save_for_backward(xq, xkv, wq, wkv, table, wparam, wp, q_buf, kv_buf, o)
+        ctx.meta = (B, H, W, heads, hd, shift, scale, Cc, bq is not None)
+        return y
+
+    @staticmethod
+    @once_differentiable
+    def backward(ctx, dy):
+        xq, xkv, wq, wkv, table, wparam, wp, q_buf, kv_buf, o = ctx.saved_tensors
+        B, H, W, heads, hd, shift, scale, Cc, has_b = ctx.meta
+        d = _c(dy)
+        d_o = ops.linear_dgrad(d, wp)
+        dwp, dbp = ops.linear_wgrad(d, o)
+        cross = xkv is not None
+        q_off, k_off, v_off = (0, 0, Cc) if cross else (0, Cc, 2 * Cc)
+        dq_buf, dkv_buf, dtable, dw = ops.window_attn_bwd(d_o, q_buf, q_off, kv_buf, k_off, v_off, table, wparam,
+                                                          B, H, W, heads, hd, shift, scale)
+        if cross:
+            dxq = ops.linear_dgrad(dq_buf, wq)
+            dwq, dbq = ops.linear_wgrad(dq_buf, xq, want_bias=has_b)
+            dxkv = ops.linear_dgrad(dkv_buf, wkv)
+            dwkv, dbkv = ops.linear_wgrad(dkv_buf, xkv, want_bias=has_b)
+        else:
+            dxq = ops.linear_dgrad(dq_buf, wq, weight2=wkv)
+            dwqkv, dbqkv = ops.linear_wgrad(dq_buf, xq, want_bias=has_b)
+            dwq, dwkv = dwqkv[:Cc], dwqkv[Cc:]
+            dbq, dbkv = (dbqkv[:Cc], dbqkv[Cc:]) if has_b else (None, None)
+            dxkv = None
+        return (dxq, dxkv, dwq, dbq, dwkv, dbkv, dtable, dw if wparam is not None else None, dwp, dbp,
+                None, None, None, None, None)

@@ -13,34 +13,39 @@ from . import ops
 
 
 class FRFNBlockFn(torch.autograd.Function):
-    """x + DropPath(FRFN(LN(x))) with a hand-written backward."""
+    """[x +] DropPath(FRFN([LN](x))) with a hand-written backward.  `nw is None` skips the LayerNorm,
+    `residual=False` returns the bare FRFN output (EncoderBlock of the NewBig family, model.py:57-72)."""
 
     @staticmethod
-    def forward(ctx, x, nw, nb, wpc, w1, b1, dww, dwb, w2, b2, dp_scale, H, W):
+    def forward(ctx, x, nw, nb, wpc, w1, b1, dww, dwb, w2, b2, dp_scale, H, W, residual):
         x = x if x.is_contiguous() else x.contiguous()
         B, L, Cc = x.shape
         M, Cq, Ch = B * L, Cc // 4, w2.shape[1]
         x2 = x.view(M, Cc)
-        y, mean, rstd = ops.layernorm_fwd(x2, nw, nb)
-        # partial conv on the first C/4 channels, written in place of them (y is a fresh LN output)
+        if nw is not None:
+            y, mean, rstd = ops.layernorm_fwd(x2, nw, nb)
+        else:
+            y, mean, rstd = ops.scale_round(x2, Cc), None, None   # private (TF32-rounded) copy
+        # partial conv on the first C/4 channels, written in place of them (y is a private buffer)
         wpm = ops.scale_round(wpc.permute(0, 2, 3, 1).reshape(Cq, 9 * Cq), 9 * Cq)
         col = ops.im2col_3x3(y, B, H, W, Cq)
-        xp = y.clone() if False else y  # noqa: the conv result overwrites y[:, :Cq] after col was gathered
+        xp = y  # the conv result overwrites y[:, :Cq] after col was gathered
         ops.linear(col, wpm, None, out=xp[:, :Cq], t5=True, round_out=True)
         u = ops.linear(xp, ops.rounded_weight(w1), b1, t5=True)
         need_bwd = any(ctx.needs_input_grad)
         v, h = ops.dwconv_gelu_fwd(u, dww, dwb, B, H, W, Ch, mode=1, save_v=need_bwd)
-        out = ops.linear(h, ops.rounded_weight(w2), b2, residual=x2, rowscale=dp_scale, rows_per_group=L, t5=True)
+        out = ops.linear(h, ops.rounded_weight(w2), b2, residual=x2 if residual else None, rowscale=dp_scale,
+                         rows_per_group=L, t5=True)
         if need_bwd:
             ctx.save_for_backward(x2, nw, mean, rstd, xp, col, wpm, u, v, h, w1, dww, w2, dp_scale)
-        ctx.meta = (B, L, Cc, Cq, Ch, H, W)
+        ctx.meta = (B, L, Cc, Cq, Ch, H, W, residual)
         return out.view(B, L, Cc)
 
     @staticmethod
     @once_differentiable
     def backward(ctx, dout):
         x2, nw, mean, rstd, xp, col, wpm, u, v, h, w1, dww, w2, dp = ctx.saved_tensors
-        B, L, Cc, Cq, Ch, H, W = ctx.meta
+        B, L, Cc, Cq, Ch, H, W, residual = ctx.meta
         M = B * L
         d = (dout if dout.is_contiguous() else dout.contiguous()).view(M, Cc)
         d_s = ops.scale_round(d, Cc, dp, L)
@@ -61,10 +66,16 @@ class FRFNBlockFn(torch.autograd.Function):
         g1 = dxp[:, :Cq]
         dwpm, _ = ops.linear_wgrad(g1, col, want_bias=False)
         dcol = ops.linear_dgrad(g1, wpm)
-        ops.col2im_3x3(dcol, dxp, B, H, W, Cq)                   # overwrites dxp[:, :Cq] with d/d(LN out)
-        dx, dg, db = ops.layernorm_bwd(dxp, x2, nw, mean, rstd, dres=d)
+        ops.col2im_3x3(dcol, dxp, B, H, W, Cq)                   # overwrites dxp[:, :Cq] with d/d(FRFN input)
+        dg = db = None
+        if nw is not None:
+            dx, dg, db = ops.layernorm_bwd(dxp, x2, nw, mean, rstd, dres=d if residual else None)
+        else:
+            dx = dxp
+            if residual:
+                ops.copy2d(d, dx, Cc, accumulate=True)
         dwpc = dwpm.view(Cq, 3, 3, Cq).permute(0, 3, 1, 2).contiguous()
-        return dx.view(B, L, Cc), dg, db, dwpc, dw1, db1, ddww, ddwb, dw2, db2, None, None, None
+        return dx.view(B, L, Cc), dg, db, dwpc, dw1, db1, ddww, ddwb, dw2, db2, None, None, None, None
 
 
 class FRFN(nn.Module):
@@ -80,8 +91,9 @@ class FRFN(nn.Module):
         self.dim_untouched = self.dim - self.dim_conv
         self.partial_conv3 = nn.Conv2d(self.dim_conv, self.dim_conv, 3, 1, 1, bias=False)
 
-    def block_forward(self, x, norm, dp_scale, H, W):
-        """x + DropPath(FRFN(norm(x))) — the LayerNorm is fused into the block function."""
-        return FRFNBlockFn.apply(x, norm.weight, norm.bias, self.partial_conv3.weight, self.linear1[0].weight,
-                                 self.linear1[0].bias, self.dwconv[0].weight, self.dwconv[0].bias,
-                                 self.linear2[0].weight, self.linear2[0].bias, dp_scale, H, W)
+    def block_forward(self, x, norm, dp_scale, H, W, residual=True):
+        """[x +] DropPath(FRFN([norm](x))) — LayerNorm and residual are fused into the block function."""
+        return FRFNBlockFn.apply(x, norm.weight if norm is not None else None, norm.bias if norm is not None else None,
+                                 self.partial_conv3.weight, self.linear1[0].weight, self.linear1[0].bias,
+                                 self.dwconv[0].weight, self.dwconv[0].bias, self.linear2[0].weight,
+                                 self.linear2[0].bias, dp_scale, H, W, residual)

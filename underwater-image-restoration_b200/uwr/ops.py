@@ -423,7 +423,8 @@ def colsum(x2d, cols):
     rows = x2d.shape[0]
     out = _empty((cols,), x2d)
     ws = _ws(1024 * cols * 4, x2d)
-    _run("uwr_colsum", "", 0, 0.0, _ptr(x2d), x2d.stride(0), _ptr(out), _ptr(ws), rows, cols)
+    _run("uwr_colsum", f"rows{rows} C{cols}", 4 * rows * cols, 0.0, _ptr(x2d), x2d.stride(0), _ptr(out), _ptr(ws),
+         rows, cols)
     return out
 
 
