@@ -148,6 +148,8 @@ int uwr_window_attn_bwd(const uwr_attn_desc* d, const float* dout, long long ld_
  *                                          backward needs: the GEMM epilogue UWR_EPI_MUL consumes it)
  *   h2 = gelu(v)                          (mode 0, LeFF)
  *   h2 = gelu(v) * gelu(u[:, Ch + c])     (mode 1, FRFN gate; u has 2*Ch channels)
+ *   h2 = dwconv3x3(u) [+ bias]            (mode 2, plain depthwise conv: MDTA/GDFN,
+ *                                          SpectralTransformer.py:82,89,123; bias may be NULL)
  */
 int uwr_dwconv_gelu_fwd(const float* u, long long ld_u, const float* weight /*(Ch,1,3,3)*/,
                         const float* bias, float* v, float* h2, int B, int H, int W, int Ch,
@@ -161,7 +163,8 @@ size_t uwr_dwconv_gelu_bwd_workspace_bytes(int B, int H, int W, int Ch);
  * dbias (Ch); only dv needs a halo. */
 int uwr_dwconv_gelu_bwd(const float* dv, const float* u, long long ld_u, const float* weight,
                         float* du, float* dweight, float* dbias, float* workspace, int B, int H,
-                        int W, int Ch, uwr_stream_t stream);
+                        int W, int Ch, int plain /* 1: no GELU around the conv (mode 2) */,
+                        uwr_stream_t stream);
 
 /* ---- convolutions at the model boundary and between scales ---------------------------------
  * InputProj  (AST.py:447-466): Conv3x3(3->Cout)+LeakyReLU(slope) NCHW image -> tokens.

@@ -91,6 +91,19 @@ def main():
     torch.save({"state_dict_sha1": nkeys, "out": yr, "seed_weights": 1234, "seed_data": 2024},
                os.path.join(OUT, "newbigfrfn_128.pt"))
 
+    # ---- SpectralTransformer (runs as shipped)
+    from src.Models.SpectralTransformer import SpectralTransformer
+    torch.manual_seed(1234)
+    sp = SpectralTransformer()
+    sp.eval()
+    skeys = [(k, list(v.shape), str(v.dtype), sha(v)) for k, v in sp.state_dict().items()]
+    gs = torch.Generator().manual_seed(2024)
+    xs = torch.rand(1, 3, 64, 96, generator=gs) * 2 - 1          # non-square is legal (H, W % 8 == 0)
+    with torch.no_grad():
+        ys = sp(xs)
+    torch.save({"state_dict_sha1": skeys, "out": ys, "seed_weights": 1234, "seed_data": 2024},
+               os.path.join(OUT, "spectral_64x96.pt"))
+
     # ---- losses / metrics known answers
     torch.manual_seed(0)
     p = torch.rand(2, 3, 256, 256)

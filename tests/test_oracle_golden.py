@@ -156,3 +156,19 @@ def test_broken_reference_models_are_names_only():
     for name in ("NewModel", "NewBigModel"):
         with pytest.raises(NotImplementedError, match="registry name only"):
             uwr.init_model(name)
+
+
+def test_spectral_state_dict_and_oracle_match_reference_golden():
+    from oracle import spectral_oracle
+    from uwr.spectral import SpectralTransformer
+    g = _load("spectral_64x96.pt")
+    torch.manual_seed(g["seed_weights"])
+    model = SpectralTransformer()
+    got = [(k, list(v.shape), str(v.dtype), _sha(v)) for k, v in model.state_dict().items()]
+    assert len(got) == 443 and got == g["state_dict_sha1"]
+    assert sum(p.numel() for p in model.parameters()) == 2430709
+    gen = torch.Generator().manual_seed(g["seed_data"])
+    x = torch.rand(1, 3, 64, 96, generator=gen) * 2 - 1
+    with torch.no_grad():
+        y = spectral_oracle.spectral_forward(model.state_dict(), x)
+    assert rel_l2(y, g["out"]) < 1e-5

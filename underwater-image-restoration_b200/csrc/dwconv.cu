@@ -58,9 +58,10 @@ __global__ void __launch_bounds__(DW_THREADS) dwconv_fwd_kernel(const float* __r
     for (int i = 0; i < NV; ++i) {
         const int idx = tid + i * DW_THREADS;
         const int pix = idx >> 3;
-        if (pix < HS * HS)  // gelu(0) = 0 keeps the zero padding
+        if (pix < HS * HS)  // gelu(0) = 0 keeps the zero padding; mode 2 = plain depthwise conv
             *reinterpret_cast<float4*>(&h1s[pix][c4]) =
-                make_float4(gelu_f(val[i].x), gelu_f(val[i].y), gelu_f(val[i].z), gelu_f(val[i].w));
+                mode == 2 ? val[i]
+                          : make_float4(gelu_f(val[i].x), gelu_f(val[i].y), gelu_f(val[i].z), gelu_f(val[i].w));
     }
     float4 wgt[9];
 #pragma unroll
@@ -68,7 +69,7 @@ __global__ void __launch_bounds__(DW_THREADS) dwconv_fwd_kernel(const float* __r
         wgt[k] = cok ? make_float4(weight[c * 9 + k], weight[(c + 1) * 9 + k], weight[(c + 2) * 9 + k],
                                    weight[(c + 3) * 9 + k])
                      : make_float4(0.f, 0.f, 0.f, 0.f);
-    const float4 bv = cok ? ld4(bias + c) : make_float4(0.f, 0.f, 0.f, 0.f);
+    const float4 bv = (cok && bias != nullptr) ? ld4(bias + c) : make_float4(0.f, 0.f, 0.f, 0.f);
     __syncthreads();
 
     const int ly = tid >> 4;            // tile row 0..15
@@ -106,7 +107,7 @@ __global__ void __launch_bounds__(DW_THREADS) dwconv_fwd_kernel(const float* __r
                 float cdf, pdf;
                 gelu_parts(a[e], cdf, pdf);
                 sv[e] = v_is_dgelu ? fmaf(a[e], pdf, cdf) : a[e];
-                o[e] = a[e] * cdf;
+                o[e] = mode == 2 ? a[e] : a[e] * cdf;
                 if (mode == 1) o[e] *= gelu_f(gt[e]);
                 if (rnd) o[e] = tf32_round(o[e]);
             }
@@ -153,7 +154,8 @@ __global__ void __launch_bounds__(DW_THREADS, 2) dwconv_bwd_kernel(const float* 
                                                                    const float* __restrict__ weight,
                                                                    float* __restrict__ du,
                                                                    float* __restrict__ partials, int B, int H, int W,
-                                                                   int Ch, int tiles_x, int tiles_per_img, int rnd) {
+                                                                   int Ch, int tiles_x, int tiles_per_img, int rnd,
+                                                                   int plain) {
     __shared__ __align__(16) float dvs[HS * HS][CG];
     const int tid = threadIdx.x;
     const int c2 = (tid & 15) * 2;
@@ -226,9 +228,11 @@ __global__ void __launch_bounds__(DW_THREADS, 2) dwconv_bwd_kernel(const float* 
                         win[a][2] = ld2(&dvs[(ly + a) * HS + lx + 2][c2]);
                     }
                     if (tx0 + lx < W) {
-                        float cdf0, pdf0, cdf1, pdf1;
-                        gelu_parts(uc[i].x, cdf0, pdf0);
-                        gelu_parts(uc[i].y, cdf1, pdf1);
+                        float cdf0 = 1.f, pdf0 = 0.f, cdf1 = 1.f, pdf1 = 0.f;  // plain conv: h1 = u, gelu' = 1
+                        if (!plain) {
+                            gelu_parts(uc[i].x, cdf0, pdf0);
+                            gelu_parts(uc[i].y, cdf1, pdf1);
+                        }
                         const float2 h1 = make_float2(uc[i].x * cdf0, uc[i].y * cdf1);
                         float2 dh1 = make_float2(0.f, 0.f);
                         // v[q] = sum_k h1[q + k - 1] w[k]  =>  h1[p] meets dv[p + 1 - k] with weight w[k]
@@ -298,8 +302,8 @@ extern "C" int uwr_dwconv_gelu_fwd(const float* u, long long ld_u, const float* 
                                    float* h2, int B, int H, int W, int Ch, int mode, int v_is_dgelu,
                                    uwr_stream_t stream_) {
     cudaStream_t stream = (cudaStream_t)stream_;
-    UWR_REQUIRE(u && weight && bias && h2, "uwr_dwconv_gelu_fwd: null pointer");
-    UWR_REQUIRE(mode == 0 || mode == 1, "uwr_dwconv_gelu_fwd: mode must be 0 (LeFF) or 1 (FRFN gate)");
+    UWR_REQUIRE(u && weight && h2 && (bias || mode == 2), "uwr_dwconv_gelu_fwd: null pointer");
+    UWR_REQUIRE(mode >= 0 && mode <= 2, "uwr_dwconv_gelu_fwd: mode must be 0 (LeFF), 1 (FRFN gate) or 2 (plain)");
     UWR_REQUIRE(ld_u >= (mode == 1 ? 2 * Ch : Ch), "uwr_dwconv_gelu_fwd: ld_u too small");
     UWR_REQUIRE(B > 0 && B <= 65535, "uwr_dwconv_gelu_fwd: bad batch %d", B);
     UWR_REQUIRE(Ch % 4 == 0 && ld_u % 4 == 0, "uwr_dwconv_gelu_fwd: Ch and ld_u must be multiples of 4");
@@ -329,7 +333,7 @@ extern "C" size_t uwr_dwconv_gelu_bwd_workspace_bytes(int B, int H, int W, int C
 
 extern "C" int uwr_dwconv_gelu_bwd(const float* dv, const float* u, long long ld_u, const float* weight, float* du,
                                    float* dweight, float* dbias, float* workspace, int B, int H, int W, int Ch,
-                                   uwr_stream_t stream_) {
+                                   int plain, uwr_stream_t stream_) {
     cudaStream_t stream = (cudaStream_t)stream_;
     UWR_REQUIRE(dv && u && weight && du && dweight && dbias && workspace, "uwr_dwconv_gelu_bwd: null pointer");
     UWR_REQUIRE(Ch % 4 == 0 && ld_u % 4 == 0, "uwr_dwconv_gelu_bwd: Ch and ld_u must be multiples of 4");
@@ -337,7 +341,7 @@ extern "C" int uwr_dwconv_gelu_bwd(const float* dv, const float* u, long long ld
     const int P = bwd_ctas(B, H, W, Ch);
     dim3 grid(P, uwr_cdiv(Ch, CG));
     dwconv_bwd_kernel<<<grid, DW_THREADS, 0, stream>>>(dv, u, ld_u, weight, du, workspace, B, H, W, Ch, tx, tx * ty,
-                                                      uwr_round_outputs());
+                                                      uwr_round_outputs(), plain);
     UWR_CHECK_LAUNCH("dwconv_bwd_kernel");
     dwconv_param_reduce_kernel<<<uwr_cdiv(10 * Ch, 128), 128, 0, stream>>>(workspace, dweight, dbias, P, Ch);
     UWR_CHECK_LAUNCH("dwconv_param_reduce_kernel");

@@ -83,7 +83,7 @@ SIGNATURES = {
                                     c_stream]),
     "uwr_dwconv_gelu_bwd_workspace_bytes": (c_sz, [c_int, c_int, c_int, c_int]),
     "uwr_dwconv_gelu_bwd": (c_int, [c_fp, c_fp, c_ll, c_fp, c_fp, c_fp, c_fp, c_fp,
-                                    c_int, c_int, c_int, c_int, c_stream]),
+                                    c_int, c_int, c_int, c_int, c_int, c_stream]),
     "uwr_gelu_gate_bwd": (c_int, [c_fp, c_fp, c_ll, c_fp, c_fp, c_fp, c_ll, c_int, c_int, c_stream]),
     "uwr_input_proj_fwd": (c_int, [c_fp, c_fp, c_fp, c_fp, c_int, c_int, c_int, c_int, c_int, c_f, c_stream]),
     "uwr_input_proj_bwd_workspace_bytes": (c_sz, [c_int] * 5),

@@ -16,11 +16,18 @@ def _c(t):
     return t if t.is_contiguous() else t.contiguous()
 
 
+def _rows(x):
+    """2-D row-major view (row stride may exceed the width: column slices of token matrices are fine)."""
+    if x.dim() == 2 and x.stride(1) == 1 and x.stride(0) % 4 == 0 and x.data_ptr() % 16 == 0:
+        return x
+    x = _c(x)
+    return x.view(-1, x.shape[-1])
+
+
 class LinearFn(torch.autograd.Function):
     @staticmethod
     def forward(ctx, x, w, b, rounded):
-        x = _c(x)
-        x2 = x.view(-1, x.shape[-1])
+        x2 = _rows(x)
         t5 = bool(rounded)
         y = ops.linear(x2, ops.rounded_weight(w) if t5 else w, b, t5=t5)
         ctx.save_for_backward(x2, w)
@@ -33,9 +40,9 @@ class LinearFn(torch.autograd.Function):
         x2, w = ctx.saved_tensors
         shape, has_b = ctx.meta
         d = _c(dy).view(-1, w.shape[0])
-        dx = ops.linear_dgrad(d, w)
+        dx = ops.linear_dgrad(d, w) if ctx.needs_input_grad[0] else None
         dw, db = ops.linear_wgrad(d, x2, want_bias=has_b)
-        return dx.view(shape), dw, db, None
+        return (dx.view(shape) if dx is not None else None), dw, db, None
 
 
 def linear(x, w, b=None, rounded=False):
@@ -145,3 +152,48 @@ class AttnFn(torch.autograd.Function):
             dxkv = None
         return (dxq, dxkv, dwq, dbq, dwkv, dbkv, dtable, dw if wparam is not None else None, dwp, dbp,
                 None, None, None, None, None)
+
+
+class PlainDWConvFn(torch.autograd.Function):
+    """depthwise 3x3 conv (pad 1, no bias, no activation) on tokens (B*H*W, C): MDTA qkv_conv / kv_conv and
+    GDFN conv of the SpectralTransformer (SpectralTransformer.py:82,89,123)."""
+
+    @staticmethod
+    def forward(ctx, u, weight, B, H, W):
+        u = _c(u)
+        Ch = u.shape[1]
+        _, y = ops.dwconv_gelu_fwd(u, weight, None, B, H, W, Ch, mode=2, save_v=False)
+        ctx.save_for_backward(u, weight)
+        ctx.dims = (B, H, W, Ch)
+        return y
+
+    @staticmethod
+    @once_differentiable
+    def backward(ctx, dy):
+        u, weight = ctx.saved_tensors
+        B, H, W, Ch = ctx.dims
+        du, dw, _ = ops.dwconv_gelu_bwd(_c(dy), u, weight, B, H, W, Ch, plain=True)
+        return du, dw, None, None, None
+
+
+class GramFn(torch.autograd.Function):
+    """G = X^T X for a token slab X (L, n) (row stride may be larger): one TN GEMM over the tokens.
+    Used for MDTA's channel attention, where q^T k and the L2 norms of q, k are blocks of G."""
+
+    @staticmethod
+    def forward(ctx, x):
+        L, n = x.shape
+        G = ops._empty((n, n), x)
+        ops.gemm(x, x, G, n, n, L, lda=x.stride(0), ldb=x.stride(0), ldc=n, a_km=True, b_nk=False)
+        ctx.save_for_backward(x)
+        return G
+
+    @staticmethod
+    @once_differentiable
+    def backward(ctx, dG):
+        (x,) = ctx.saved_tensors
+        L, n = x.shape
+        S = _c(dG + dG.t())
+        dx = ops._empty((L, n), x)
+        ops.gemm(x, S, dx, L, n, n, lda=x.stride(0), ldb=n, ldc=n, b_nk=False)
+        return dx

@@ -322,7 +322,7 @@ def gelu_gate_bwd(dh2, u2d, v, Ch, mode, du=None):
     return dv
 
 
-def dwconv_gelu_bwd(dv, u2d, weight, B, H, W, Ch, du=None):
+def dwconv_gelu_bwd(dv, u2d, weight, B, H, W, Ch, du=None, plain=False):
     """dv = dL/d(conv output).  Returns du (same row stride as u; only [:, :Ch] is written), dweight, dbias."""
     if du is None:
         du = torch.empty_like(u2d)
@@ -332,7 +332,7 @@ def dwconv_gelu_bwd(dv, u2d, weight, B, H, W, Ch, du=None):
     n = B * H * W * Ch
     _run("uwr_dwconv_gelu_bwd", f"B{B} H{H} Ch{Ch}", 4 * n * 3, 36.0 * n,
          _ptr(dv), _ptr(u2d), u2d.stride(0), _ptr(weight), _ptr(du), _ptr(dweight), _ptr(dbias), _ptr(ws),
-         B, H, W, Ch)
+         B, H, W, Ch, int(plain))
     return du, dweight, dbias
 
 

@@ -1,0 +1,219 @@
+"""SpectralTransformer (src/Models/SpectralTransformer.py:213-269) behind the reference's module tree
+(443 state_dict entries, RNG-identical default init), computed on NHWC token matrices.
+
+Native (uwr kernels): LayerNorm over channels (no NCHW<->NHWC round trips), every 1x1 convolution
+(tensor-core GEMM on tokens), the depthwise 3x3 convs of MDTA / GDFN (plain mode of the dwconv kernel),
+MDTA's channel attention as two GEMMs per image (Gram matrix of [q|k] over the tokens -> tiny softmax
+-> block-diagonal apply), the dense 3x3 convs with Cin % 4 == 0 (im2col + GEMM).
+Still ATen in this round: the FFT amplitude/phase up-sampler (torch.fft, abs/angle/
+cos/sin), PixelShuffle/Unshuffle, the GELU gate product of GDFN, the 3-channel first / last 3x3 conv.
+Only the live data path is executed: MDTA's FFT branch, `attnf`, q1X1_*, ups_4, ups1, ups2, output1
+are dead in value and gradient in the reference; their parameters are kept.
+"""
+import torch
+import torch.nn as nn
+import torch.nn.functional as F
+
+from . import fn
+
+
+def _w2(conv):
+    return conv.weight.flatten(1)
+
+
+class MDTA(nn.Module):
+    def __init__(self, channels, num_heads):
+        super().__init__()
+        self.num_heads = num_heads
+        self.temperature = nn.Parameter(torch.ones(1, num_heads, 1, 1))
+        self.qkv = nn.Conv2d(channels, channels * 3, kernel_size=1, bias=False)
+        self.qkv_conv = nn.Conv2d(channels * 3, channels * 3, kernel_size=3, padding=1, groups=channels * 3, bias=False)
+        self.project_out = nn.Conv2d(channels, channels, kernel_size=1, bias=False)
+        self.kv = nn.Conv2d(channels, channels * 2, kernel_size=1, bias=False)
+        self.q1X1_1 = nn.Conv2d(channels, channels, kernel_size=1, bias=False)   # dead
+        self.q1X1_2 = nn.Conv2d(channels, channels, kernel_size=1, bias=False)   # dead
+        self.kv_conv = nn.Conv2d(channels * 2, channels * 2, kernel_size=3, padding=1, groups=channels * 2, bias=False)
+        self.project_outf = nn.Conv2d(channels, channels, kernel_size=1, bias=False)
+
+    def _attention_matrices(self, qkv, B, L, C):
+        """per image: block-diagonal (C, C) matrix of softmax(normalize(q) normalize(k)^T * temperature)."""
+        h = self.num_heads
+        c = C // h
+        mats = []
+        for b in range(B):
+            G = fn.GramFn.apply(qkv[b * L:(b + 1) * L, :2 * C])          # [[q^T q, q^T k], [k^T q, k^T k]]
+            d = torch.diagonal(G)
+            nq = d[:C].clamp_min(0).sqrt().clamp_min(1e-12)              # F.normalize eps (line 99)
+            nk = d[C:].clamp_min(0).sqrt().clamp_min(1e-12)
+            S = G[:C, C:] / (nq[:, None] * nk[None, :])
+            blocks = torch.stack([S[i * c:(i + 1) * c, i * c:(i + 1) * c] for i in range(h)])   # (h, c, c)
+            A = torch.softmax(blocks * self.temperature.view(h, 1, 1), dim=-1)
+            mats.append(torch.block_diag(*A.unbind(0)))
+        return mats
+
+    def forward(self, y, B, H, W):   # y: LayerNorm output tokens (B*L, C)
+        L, C = H * W, y.shape[1]
+        qkv = fn.linear(y, _w2(self.qkv), None, rounded=True)
+        qkv = fn.PlainDWConvFn.apply(qkv, self.qkv_conv.weight, B, H, W)
+        mats = self._attention_matrices(qkv, B, L, C)
+        out = torch.cat([fn.linear(qkv[b * L:(b + 1) * L, 2 * C:], mats[b]) for b in range(B)], 0)   # attn @ v
+        out = fn.linear(out, _w2(self.project_out))
+        kvf = fn.PlainDWConvFn.apply(fn.linear(out, _w2(self.kv)), self.kv_conv.weight, B, H, W)
+        outf = torch.cat([fn.linear(kvf[b * L:(b + 1) * L, C:], mats[b]) for b in range(B)], 0)      # attn @ vf
+        return fn.linear(outf, _w2(self.project_outf))
+
+
+class GDFN(nn.Module):
+    def __init__(self, channels, expansion_factor):
+        super().__init__()
+        hidden = int(channels * expansion_factor)
+        self.hidden = hidden
+        self.project_in = nn.Conv2d(channels, hidden * 2, kernel_size=1, bias=False)
+        self.conv = nn.Conv2d(hidden * 2, hidden * 2, kernel_size=3, padding=1, groups=hidden * 2, bias=False)
+        self.project_out = nn.Conv2d(hidden, channels, kernel_size=1, bias=False)
+
+    def forward(self, y, B, H, W):
+        # hidden = int(2.66 C) is odd-sized (42, 85, 170, 340): pad each half to a multiple of 4 channels with
+        # zero weights so every row of the token matrices stays 16-byte aligned (zeros stay zeros:
+        # conv(0) = 0 and gelu(0) * 0 = 0)
+        h = self.hidden
+        hp = -(-h // 4) * 4
+        win, wdw, wout = _w2(self.project_in), self.conv.weight, _w2(self.project_out)
+        if hp != h:
+            z1 = win.new_zeros(hp - h, win.shape[1])
+            win = torch.cat([win[:h], z1, win[h:], z1], 0)
+            z2 = wdw.new_zeros(hp - h, 1, 3, 3)
+            wdw = torch.cat([wdw[:h], z2, wdw[h:], z2], 0)
+            wout = torch.cat([wout, wout.new_zeros(wout.shape[0], hp - h)], 1)
+        t = fn.PlainDWConvFn.apply(fn.linear(y, win, None, rounded=True), wdw, B, H, W)
+        return fn.linear(F.gelu(t[:, :hp]) * t[:, hp:], wout)
+
+
+class TransformerBlock(nn.Module):
+    def __init__(self, channels, num_heads, expansion_factor):
+        super().__init__()
+        self.norm1 = nn.LayerNorm(channels)
+        self.attn = MDTA(channels, num_heads)
+        self.norm2 = nn.LayerNorm(channels)
+        self.ffn = GDFN(channels, expansion_factor)
+
+    def forward(self, x, B, H, W):   # tokens (B*L, C)
+        x = x + self.attn(fn.layernorm(x, self.norm1), B, H, W)
+        return x + self.ffn(fn.layernorm(x, self.norm2), B, H, W)
+
+
+def _to_img(t, B, H, W):
+    return t.view(B, H, W, -1).permute(0, 3, 1, 2)
+
+
+def _to_tok(img):
+    B, C, H, W = img.shape
+    return img.permute(0, 2, 3, 1).reshape(B * H * W, C).contiguous()
+
+
+def _conv3x3(t, conv, B, H, W):
+    return fn.Conv3x3Fn.apply(t.view(B, H * W, -1), conv.weight, conv.bias, H, W).view(B * H * W, -1)
+
+
+class DownSample(nn.Module):
+    def __init__(self, channels):
+        super().__init__()
+        self.body = nn.Sequential(nn.Conv2d(channels, channels // 2, kernel_size=3, padding=1, bias=False),
+                                  nn.PixelUnshuffle(2))
+
+    def forward(self, t, B, H, W):
+        return _to_tok(F.pixel_unshuffle(_to_img(_conv3x3(t, self.body[0], B, H, W), B, H, W), 2))
+
+
+class UpSample(nn.Module):
+    """FFT amplitude / phase up-sampler (lines 161-188); ATen this round."""
+
+    def __init__(self, channels, channel_red):
+        super().__init__()
+        self.amp_fuse = nn.Sequential(nn.Conv2d(channels, channels, 1, 1, 0), nn.LeakyReLU(0.1, inplace=False),
+                                      nn.Conv2d(channels, channels, 1, 1, 0))
+        self.pha_fuse = nn.Sequential(nn.Conv2d(channels, channels, 1, 1, 0), nn.LeakyReLU(0.1, inplace=False),
+                                      nn.Conv2d(channels, channels, 1, 1, 0))
+        self.post = nn.Conv2d(channels, channels // 2 if channel_red else channels, 1, 1, 0)
+
+    def forward(self, img):
+        f = torch.fft.fft2(img)
+        Mag = torch.tile(self.amp_fuse(torch.abs(f)), (2, 2))
+        Pha = torch.tile(self.pha_fuse(torch.angle(f)), (2, 2))
+        out = torch.abs(torch.fft.ifft2(torch.complex(Mag * torch.cos(Pha), Mag * torch.sin(Pha))))
+        return self.post(out)
+
+
+class UpSample1(nn.Module):
+    def __init__(self, channels):
+        super().__init__()
+        self.body = nn.Sequential(nn.Conv2d(channels, channels * 2, kernel_size=3, padding=1, bias=False),
+                                  nn.PixelShuffle(2))
+
+    def forward(self, t, B, H, W):
+        return F.pixel_shuffle(_to_img(_conv3x3(t, self.body[0], B, H, W), B, H, W), 2)
+
+
+class UpS(nn.Module):
+    def __init__(self, channels):
+        super().__init__()
+        self.Fups = UpSample(channels, True)
+        self.Sups = UpSample1(channels)
+        self.reduce = nn.Conv2d(channels, channels // 2, kernel_size=1, bias=False)
+
+    def forward(self, t, B, H, W):   # tokens at (H, W) -> tokens at (2H, 2W)
+        cat = torch.cat([self.Fups(_to_img(t, B, H, W)), self.Sups(t, B, H, W)], dim=1)
+        return fn.linear(_to_tok(cat), _w2(self.reduce))
+
+
+class SpectralTransformer(nn.Module):
+    def __init__(self, num_blocks=[2, 3, 3, 4], num_heads=[1, 2, 4, 8], channels=[16, 32, 64, 128], num_refinement=4,
+                 expansion_factor=2.66, ch=[64, 32, 16, 64]):
+        super().__init__()
+        self.embed_conv_rgb = nn.Conv2d(3, channels[0], kernel_size=3, padding=1, bias=False)
+        self.encoders = nn.ModuleList([nn.Sequential(*[TransformerBlock(c, a, expansion_factor) for _ in range(n)])
+                                       for n, a, c in zip(num_blocks, num_heads, channels)])
+        self.down1, self.down2, self.down3 = DownSample(channels[0]), DownSample(channels[1]), DownSample(channels[2])
+        self.ups_1, self.ups_2, self.ups_3, self.ups_4 = UpS(128), UpS(64), UpS(32), UpS(3)
+        self.ups1 = UpSample1(32)
+        self.reduces2 = nn.Conv2d(64, 32, kernel_size=1, bias=False)
+        self.reduces1 = nn.Conv2d(128, 64, kernel_size=1, bias=False)
+        self.decoders = nn.ModuleList([nn.Sequential(*[TransformerBlock(channels[2], num_heads[2], expansion_factor)
+                                                       for _ in range(num_blocks[2])])])
+        self.decoders.append(nn.Sequential(*[TransformerBlock(channels[1], num_heads[1], expansion_factor)
+                                             for _ in range(num_blocks[1])]))
+        self.decoders.append(nn.Sequential(*[TransformerBlock(channels[1], num_heads[0], expansion_factor)
+                                             for _ in range(num_blocks[0])]))
+        self.refinement = nn.Sequential(*[TransformerBlock(channels[1], num_heads[0], expansion_factor)
+                                          for _ in range(num_refinement)])
+        self.output = nn.Conv2d(8, 3, kernel_size=3, padding=1, bias=False)
+        self.output1 = nn.Conv2d(16, 8, kernel_size=3, padding=1, bias=False)
+        self.ups2 = UpSample1(16)
+        self.outputl = nn.Conv2d(32, 8, kernel_size=3, padding=1, bias=False)
+
+    @staticmethod
+    def _stage(blocks, t, B, H, W):
+        for blk in blocks:
+            t = blk(t, B, H, W)
+        return t
+
+    def forward(self, RGB_input):
+        if not RGB_input.is_cuda:
+            raise RuntimeError("uwr SpectralTransformer runs on CUDA (B200) only; there is no CPU fallback")
+        x = RGB_input.contiguous().float()
+        B, _, H, W = x.shape
+        if H % 8 or W % 8:
+            raise ValueError("SpectralTransformer needs H and W divisible by 8")
+        f0 = _to_tok(F.conv2d(x, self.embed_conv_rgb.weight, padding=1))     # 3 -> 16 (K = 27): cuDNN
+        e1 = self._stage(self.encoders[0], f0, B, H, W)
+        e2 = self._stage(self.encoders[1], self.down1(e1, B, H, W), B, H // 2, W // 2)
+        e3 = self._stage(self.encoders[2], self.down2(e2, B, H // 2, W // 2), B, H // 4, W // 4)
+        e4 = self._stage(self.encoders[3], self.down3(e3, B, H // 4, W // 4), B, H // 8, W // 8)
+        d3 = fn.linear(torch.cat([self.ups_1(e4, B, H // 8, W // 8), e3], 1), _w2(self.reduces1))
+        d3 = self._stage(self.decoders[0], d3, B, H // 4, W // 4)
+        d2 = fn.linear(torch.cat([self.ups_2(d3, B, H // 4, W // 4), e2], 1), _w2(self.reduces2))
+        d2 = self._stage(self.decoders[1], d2, B, H // 2, W // 2)
+        fd = self._stage(self.decoders[2], torch.cat([self.ups_3(d2, B, H // 2, W // 2), e1], 1), B, H, W)
+        fr = self._stage(self.refinement, fd, B, H, W)
+        o = _conv3x3(fr, self.outputl, B, H, W)                               # 32 -> 8
+        return F.conv2d(_to_img(o, B, H, W), self.output.weight, padding=1)   # 8 -> 3 (N = 3): cuDNN
