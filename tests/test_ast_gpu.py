@@ -133,3 +133,30 @@ def test_registry_surface():
         uwr.init_model("nope")
     m = uwr.init_model("AST", use_dwt="Fourier")
     assert len(m.state_dict()) == 274
+
+
+def test_graphed_train_step_matches_eager():
+    """CUDA-graph replay of the whole step == eager step (eval mode: no DropPath randomness)."""
+    import uwr
+    from uwr.train import TrainStep
+    from uwr.graph import GraphedTrainStep
+    g = torch.Generator().manual_seed(3)
+    raw = (torch.rand(2, 3, 128, 128, generator=g) * 2 - 1).cuda()
+    ref = (torch.rand(2, 3, 128, 128, generator=g) * 2 - 1).cuda()
+
+    def make():
+        torch.manual_seed(1234)
+        m = uwr.AST(img_size=128).cuda().eval()
+        return m, TrainStep(m, "charbonnier", lr=1e-3, local_batch=2)
+    m1, s1 = make()
+    for _ in range(4):
+        l1, n1 = s1(raw, ref)
+    m2, s2 = make()
+    gs = GraphedTrainStep(s2, raw, ref, warmup=2)
+    for _ in range(2):
+        l2, n2 = gs(raw, ref)
+    torch.cuda.synchronize()
+    assert abs(l1.item() - l2.item()) < 1e-6 * abs(l1.item())
+    num = sum(((a - b).double() ** 2).sum() for a, b in zip(m1.parameters(), m2.parameters())).sqrt().item()
+    den = sum((b.double() ** 2).sum() for b in m1.parameters()).sqrt().item()
+    assert num / den < 1e-7

@@ -1,0 +1,59 @@
+"""Training-step throughput of any registry architecture through uwr.train.TrainStep
+(BASELINE configs 2 and 3: SpectralTransformer B=8 "L1withColor"; NewBigFRFNModel B=16).
+usage: python tools/train_bench.py ARCH LOSS BATCH [SIZE] [STEPS]"""
+import json, os, sys
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "underwater-image-restoration_b200"))
+import torch
+import uwr
+from uwr import ops
+from uwr.train import TrainStep
+
+arch, loss, B = sys.argv[1], sys.argv[2], int(sys.argv[3])
+S = int(sys.argv[4]) if len(sys.argv) > 4 else 256
+steps = int(sys.argv[5]) if len(sys.argv) > 5 else 5
+torch.manual_seed(1234)
+model = uwr.init_model(arch).cuda().train()
+step = TrainStep(model, loss, lr=1e-3, local_batch=B)
+g = torch.Generator().manual_seed(2024)
+raw = (torch.rand(B, 3, S, S, generator=g) * 2 - 1).cuda()
+ref = (torch.rand(B, 3, S, S, generator=g) * 2 - 1).cuda()
+for _ in range(3):
+    l, n = step(raw, ref)
+torch.cuda.synchronize()
+e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+n0 = ops.launch_count()
+e0.record()
+for _ in range(steps):
+    l, n = step(raw, ref)
+e1.record()
+torch.cuda.synchronize()
+ms = e0.elapsed_time(e1) / steps
+ms_graph = None
+try:
+    from uwr.graph import GraphedTrainStep
+    gs = GraphedTrainStep(step, raw, ref, warmup=1)
+    gs(raw, ref)
+    torch.cuda.synchronize()
+    e0.record()
+    for _ in range(steps):
+        gs(raw, ref)
+    e1.record()
+    torch.cuda.synchronize()
+    ms_graph = e0.elapsed_time(e1) / steps
+    del gs
+except Exception as ex:  # report, do not hide
+    print("graph capture failed:", repr(ex)[:300])
+with ops.KernelProfile() as prof:
+    step(raw, ref)
+fam = {}
+for r in prof.table():
+    f = fam.setdefault(r["kernel"], [0.0, 0])
+    f[0] += r["ms_total"]; f[1] += r["launches"]
+res = {"arch": arch, "loss": loss, "batch": B, "size": S, "ms_per_step": ms, "images_per_s": 1000.0 * B / ms,
+       "ms_per_step_graph": ms_graph, "images_per_s_graph": (1000.0 * B / ms_graph) if ms_graph else None,
+       "uwr_launches_per_step": (ops.launch_count() - n0) // (steps + 1), "loss_value": l.item(), "grad_norm": n[0].item(),
+       "max_mem_gb": torch.cuda.max_memory_allocated() / 2 ** 30,
+       "uwr_kernel_ms": {k: round(v[0], 3) for k, v in sorted(fam.items(), key=lambda kv: -kv[1][0])[:8]},
+       "uwr_kernel_ms_total": round(sum(v[0] for v in fam.values()), 2)}
+print(json.dumps(res))

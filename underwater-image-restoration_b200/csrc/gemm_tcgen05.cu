@@ -145,7 +145,7 @@ __host__ __device__ constexpr int t5_smem_bytes() {
     return t5_stages<BN>() * (TM * KC * 4 + BN * KC * 4) + 256 + BN * 4 + EPI_WARPS * 32 * EP_STRIDE * 4 + 1024;
 }
 
-template <int BN, int LAY>
+template <int BN, int LAY, int EPI>
 __global__ void __launch_bounds__(T5_THREADS, 1)
 gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapB,
                     const T5Params p) {
@@ -324,7 +324,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_const
                 const bool col_ok = col < p.N;  // N is a multiple of 4
                 // operand of the epilogue (residual / multiplier): issue the loads before waiting on TMEM
                 float4 rv[8];
-                if (p.epilogue != UWR_EPI_NONE) {
+                if (EPI != UWR_EPI_NONE) {
 #pragma unroll
                     for (int i = 0; i < 8; ++i) {
                         const int row = row0 + i * 4 + rsub;
@@ -352,11 +352,11 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_const
                     float4 o = *reinterpret_cast<const float4*>(st + rr * EP_STRIDE + cc);
                     o.x = (o.x + b4.x) * sc[i]; o.y = (o.y + b4.y) * sc[i];
                     o.z = (o.z + b4.z) * sc[i]; o.w = (o.w + b4.w) * sc[i];
-                    if (p.epilogue == UWR_EPI_RESID) {
+                    if (EPI == UWR_EPI_RESID) {
                         o.x += rv[i].x; o.y += rv[i].y; o.z += rv[i].z; o.w += rv[i].w;
-                    } else if (p.epilogue == UWR_EPI_MUL) {
+                    } else if (EPI == UWR_EPI_MUL) {
                         o.x *= rv[i].x; o.y *= rv[i].y; o.z *= rv[i].z; o.w *= rv[i].w;
-                    } else if (p.epilogue == UWR_EPI_MUL_DGELU) {
+                    } else if (EPI == UWR_EPI_MUL_DGELU) {
                         o.x *= gelu_grad_f(rv[i].x); o.y *= gelu_grad_f(rv[i].y);
                         o.z *= gelu_grad_f(rv[i].z); o.w *= gelu_grad_f(rv[i].w);
                     }
@@ -460,10 +460,10 @@ T5Split t5_plan(int M, int N, int Kc, int lay, int bn) {
     return sp;
 }
 
-template <int BN, int LAY>
+template <int BN, int LAY, int EPI>
 int t5_launch(const CUtensorMap& ma, const CUtensorMap& mb, const T5Params& p, cudaStream_t stream) {
     constexpr int smem = t5_smem_bytes<BN>();
-    auto kern = gemm_tcgen05_kernel<BN, LAY>;
+    auto kern = gemm_tcgen05_kernel<BN, LAY, EPI>;
     static bool configured = false;
     if (!configured) {
         UWR_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
@@ -477,12 +477,22 @@ int t5_launch(const CUtensorMap& ma, const CUtensorMap& mb, const T5Params& p, c
     return 0;
 }
 
+template <int BN, int LAY>
+int t5_dispatch_epi(const CUtensorMap& ma, const CUtensorMap& mb, const T5Params& p, cudaStream_t stream) {
+    switch (p.epilogue) {
+        case UWR_EPI_RESID: return t5_launch<BN, LAY, UWR_EPI_RESID>(ma, mb, p, stream);
+        case UWR_EPI_MUL: return t5_launch<BN, LAY, UWR_EPI_MUL>(ma, mb, p, stream);
+        case UWR_EPI_MUL_DGELU: return t5_launch<BN, LAY, UWR_EPI_MUL_DGELU>(ma, mb, p, stream);
+        default: return t5_launch<BN, LAY, UWR_EPI_NONE>(ma, mb, p, stream);
+    }
+}
+
 template <int BN>
 int t5_dispatch(int lay, const CUtensorMap& ma, const CUtensorMap& mb, const T5Params& p, cudaStream_t stream) {
     switch (lay) {
-        case LAY_NT: return t5_launch<BN, LAY_NT>(ma, mb, p, stream);
-        case LAY_NN: return t5_launch<BN, LAY_NN>(ma, mb, p, stream);
-        default: return t5_launch<BN, LAY_TN>(ma, mb, p, stream);
+        case LAY_NT: return t5_dispatch_epi<BN, LAY_NT>(ma, mb, p, stream);
+        case LAY_NN: return t5_dispatch_epi<BN, LAY_NN>(ma, mb, p, stream);
+        default: return t5_launch<BN, LAY_TN, UWR_EPI_NONE>(ma, mb, p, stream);
     }
 }
 
