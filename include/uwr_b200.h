@@ -98,6 +98,11 @@ int uwr_round_tf32_tensors(const float* const* src, float* const* dst, const lon
                            int n_tensors, long long total_elems, int do_round, uwr_stream_t stream);
 int uwr_scale_round(const float* src, long long ld_src, float* dst, long long rows, int cols,
                     const float* rowscale, int rows_per_group, int do_round, uwr_stream_t stream);
+/* same, plus colsum[cols] = column sums of dst (bias gradient of the consuming Linear);
+ * cols/4 must divide 256; workspace >= 1024*cols floats */
+int uwr_scale_round_colsum(const float* src, long long ld_src, float* dst, long long rows, int cols,
+                           const float* rowscale, int rows_per_group, int do_round, float* colsum,
+                           float* workspace, uwr_stream_t stream);
 
 /* ---- LayerNorm over C (nn.LayerNorm eps 1e-5: AST.py:521,534,593,622) ------------------- */
 int uwr_layernorm_fwd(const float* x, const float* gamma, const float* beta, float* y,
@@ -160,9 +165,10 @@ int uwr_gelu_gate_bwd(const float* dh2, const float* u, long long ld_u, const fl
                       float* du, long long rows, int Ch, int mode, uwr_stream_t stream);
 size_t uwr_dwconv_gelu_bwd_workspace_bytes(int B, int H, int W, int Ch);
 /* dv (gradient w.r.t. the conv output v) -> du[:, :Ch] (row stride ld_u), dweight (Ch,1,3,3),
- * dbias (Ch); only dv needs a halo. */
+ * dbias (Ch); only dv needs a halo.  du_colsum (Ch, optional) = column sums of du, i.e. the bias
+ * gradient of the Linear that produced u (saves a pass over du). */
 int uwr_dwconv_gelu_bwd(const float* dv, const float* u, long long ld_u, const float* weight,
-                        float* du, float* dweight, float* dbias, float* workspace, int B, int H,
+                        float* du, float* dweight, float* dbias, float* du_colsum, float* workspace, int B, int H,
                         int W, int Ch, int plain /* 1: no GELU around the conv (mode 2) */,
                         uwr_stream_t stream);
 

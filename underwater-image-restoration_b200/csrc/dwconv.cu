@@ -171,6 +171,7 @@ __global__ void __launch_bounds__(DW_THREADS, 2) dwconv_bwd_kernel(const float* 
         dwt[k] = make_float2(0.f, 0.f);
     }
     float2 dbs = make_float2(0.f, 0.f);
+    float2 dus = make_float2(0.f, 0.f);  // column sums of du = bias gradient of the Linear that produced u
     const bool sok = blockIdx.y * CG + s4 < Ch;
 
     const int total = B * tiles_per_img;
@@ -248,6 +249,8 @@ __global__ void __launch_bounds__(DW_THREADS, 2) dwconv_bwd_kernel(const float* 
                         dbs.y += win[1][1].y;
                         float2 o = make_float2(dh1.x * fmaf(uc[i].x, pdf0, cdf0), dh1.y * fmaf(uc[i].y, pdf1, cdf1));
                         if (rnd) o = make_float2(tf32_round(o.x), tf32_round(o.y));
+                        dus.x += o.x;
+                        dus.y += o.y;
                         *reinterpret_cast<float2*>(du + (tok0 + lx) * ld_u + c) = o;
                     }
                 }
@@ -265,27 +268,31 @@ __global__ void __launch_bounds__(DW_THREADS, 2) dwconv_bwd_kernel(const float* 
     }
     red[18 * DW_THREADS + tid] = dbs.x;
     red[19 * DW_THREADS + tid] = dbs.y;
+    red[20 * DW_THREADS + tid] = dus.x;
+    red[21 * DW_THREADS + tid] = dus.y;
     __syncthreads();
-    for (int idx = tid; idx < 10 * CG; idx += DW_THREADS) {
-        const int k = idx / CG, l = idx % CG;  // tap (9 = bias), local channel
+    for (int idx = tid; idx < 11 * CG; idx += DW_THREADS) {
+        const int k = idx / CG, l = idx % CG;  // tap (9 = conv bias, 10 = column sum of du), local channel
         const int grp = l >> 1, e = l & 1;
         float sum = 0.f;
 #pragma unroll 8
         for (int j = 0; j < DW_THREADS / 16; ++j) sum += red[(k * 2 + e) * DW_THREADS + j * 16 + grp];
         const int cc = blockIdx.y * CG + l;
-        if (cc < Ch) partials[((long long)blockIdx.x * 10 + k) * Ch + cc] = sum;
+        if (cc < Ch) partials[((long long)blockIdx.x * 11 + k) * Ch + cc] = sum;
     }
 }
 
 __global__ void dwconv_param_reduce_kernel(const float* __restrict__ partials, float* __restrict__ dweight,
-                                           float* __restrict__ dbias, int P, int Ch) {
+                                           float* __restrict__ dbias, float* __restrict__ du_colsum, int P, int Ch) {
     const int idx = blockIdx.x * blockDim.x + threadIdx.x;
-    if (idx >= 10 * Ch) return;
+    if (idx >= 11 * Ch) return;
     const int k = idx / Ch, c = idx % Ch;
+    if (k == 10 && du_colsum == nullptr) return;
     float s = 0.f;
-    for (int p = 0; p < P; ++p) s += partials[((long long)p * 10 + k) * Ch + c];
+    for (int p = 0; p < P; ++p) s += partials[((long long)p * 11 + k) * Ch + c];
     if (k < 9) dweight[c * 9 + k] = s;
-    else dbias[c] = s;
+    else if (k == 9) dbias[c] = s;
+    else du_colsum[c] = s;
 }
 
 int bwd_ctas(int B, int H, int W, int Ch) {
@@ -328,12 +335,12 @@ extern "C" int uwr_gelu_gate_bwd(const float* dh2, const float* u, long long ld_
 }
 
 extern "C" size_t uwr_dwconv_gelu_bwd_workspace_bytes(int B, int H, int W, int Ch) {
-    return (size_t)bwd_ctas(B, H, W, Ch) * 10 * (size_t)Ch * sizeof(float);
+    return (size_t)bwd_ctas(B, H, W, Ch) * 11 * (size_t)Ch * sizeof(float);
 }
 
 extern "C" int uwr_dwconv_gelu_bwd(const float* dv, const float* u, long long ld_u, const float* weight, float* du,
-                                   float* dweight, float* dbias, float* workspace, int B, int H, int W, int Ch,
-                                   int plain, uwr_stream_t stream_) {
+                                   float* dweight, float* dbias, float* du_colsum, float* workspace, int B, int H,
+                                   int W, int Ch, int plain, uwr_stream_t stream_) {
     cudaStream_t stream = (cudaStream_t)stream_;
     UWR_REQUIRE(dv && u && weight && du && dweight && dbias && workspace, "uwr_dwconv_gelu_bwd: null pointer");
     UWR_REQUIRE(Ch % 4 == 0 && ld_u % 4 == 0, "uwr_dwconv_gelu_bwd: Ch and ld_u must be multiples of 4");
@@ -343,7 +350,7 @@ extern "C" int uwr_dwconv_gelu_bwd(const float* dv, const float* u, long long ld
     dwconv_bwd_kernel<<<grid, DW_THREADS, 0, stream>>>(dv, u, ld_u, weight, du, workspace, B, H, W, Ch, tx, tx * ty,
                                                       uwr_round_outputs(), plain);
     UWR_CHECK_LAUNCH("dwconv_bwd_kernel");
-    dwconv_param_reduce_kernel<<<uwr_cdiv(10 * Ch, 128), 128, 0, stream>>>(workspace, dweight, dbias, P, Ch);
+    dwconv_param_reduce_kernel<<<uwr_cdiv(11 * Ch, 128), 128, 0, stream>>>(workspace, dweight, dbias, du_colsum, P, Ch);
     UWR_CHECK_LAUNCH("dwconv_param_reduce_kernel");
     return 0;
 }

@@ -56,7 +56,65 @@ __global__ void __launch_bounds__(256) scale_round_kernel(const float* __restric
     }
 }
 
+// scale + round + column sums: thread -> fixed float4 column group, rows strided; grid-level partials
+__global__ void __launch_bounds__(256) scale_round_colsum_kernel(const float* __restrict__ src, long long ld_src,
+                                                                 float* __restrict__ dst, long long rows, int cols4,
+                                                                 const float* __restrict__ rowscale, int rpg,
+                                                                 int do_round, float* __restrict__ partials) {
+    __shared__ float4 sh[256];
+    const int c4 = threadIdx.x % cols4, rsub = threadIdx.x / cols4, rpb = 256 / cols4;
+    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (long long r = (long long)blockIdx.x * rpb + rsub; r < rows; r += (long long)gridDim.x * rpb) {
+        float4 v = *reinterpret_cast<const float4*>(src + r * ld_src + c4 * 4);
+        const float s = rowscale ? __ldg(rowscale + r / rpg) : 1.f;
+        v.x *= s; v.y *= s; v.z *= s; v.w *= s;
+        if (do_round) {
+            v.x = tf32_round(v.x); v.y = tf32_round(v.y); v.z = tf32_round(v.z); v.w = tf32_round(v.w);
+        }
+        reinterpret_cast<float4*>(dst)[r * cols4 + c4] = v;
+        acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
+    }
+    sh[threadIdx.x] = acc;
+    __syncthreads();
+    if (rsub == 0) {
+        for (int k = 1; k < rpb; ++k) {
+            const float4 o = sh[k * cols4 + c4];
+            acc.x += o.x; acc.y += o.y; acc.z += o.z; acc.w += o.w;
+        }
+        reinterpret_cast<float4*>(partials)[(long long)blockIdx.x * cols4 + c4] = acc;
+    }
+}
+__global__ void colsum_partials_kernel(const float* __restrict__ partials, float* __restrict__ out, int P, int cols) {
+    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= cols) return;
+    float s = 0.f;
+    for (int p = 0; p < P; ++p) s += partials[(long long)p * cols + c];
+    out[c] = s;
+}
+
 }  // namespace
+
+extern "C" int uwr_scale_round_colsum(const float* src, long long ld_src, float* dst, long long rows, int cols,
+                                      const float* rowscale, int rows_per_group, int do_round, float* colsum,
+                                      float* workspace, uwr_stream_t stream_) {
+    cudaStream_t stream = (cudaStream_t)stream_;
+    UWR_REQUIRE(src && dst && colsum && workspace && cols % 4 == 0 && ld_src % 4 == 0, "uwr_scale_round_colsum: bad args");
+    UWR_REQUIRE(cols / 4 <= 256 && 256 % (cols / 4) == 0, "uwr_scale_round_colsum: cols/4 must divide 256");
+    UWR_REQUIRE(!rowscale || rows_per_group > 0, "uwr_scale_round_colsum: rowscale needs rows_per_group");
+    UWR_REQUIRE(rows > 0, "uwr_scale_round_colsum: empty");
+    const int cols4 = cols / 4, rpb = 256 / cols4;
+    long long blocks = (rows + rpb - 1) / rpb;
+    long long cap = 8LL * uwr_sm_count();
+    if (cap > 1024) cap = 1024;
+    if (blocks > cap) blocks = cap;
+    scale_round_colsum_kernel<<<(unsigned)blocks, 256, 0, stream>>>(src, ld_src, dst, rows, cols4, rowscale,
+                                                                   rows_per_group > 0 ? rows_per_group : 1, do_round,
+                                                                   workspace);
+    UWR_CHECK_LAUNCH("scale_round_colsum_kernel");
+    colsum_partials_kernel<<<uwr_cdiv(cols, 128), 128, 0, stream>>>(workspace, colsum, (int)blocks, cols);
+    UWR_CHECK_LAUNCH("colsum_partials_kernel");
+    return 0;
+}
 
 extern "C" int uwr_round_tf32_tensors(const float* const* src, float* const* dst, const long long* offsets,
                                       int n_tensors, long long total_elems, int do_round, uwr_stream_t stream_) {

@@ -73,6 +73,7 @@ SIGNATURES = {
     "uwr_gemm_tcgen05_workspace_bytes": (c_sz, [c_int, c_int, c_int, c_int]),
     "uwr_round_tf32_tensors": (c_int, [c_fp, c_fp, c_fp, c_int, c_ll, c_int, c_stream]),
     "uwr_scale_round": (c_int, [c_fp, c_ll, c_fp, c_ll, c_int, c_fp, c_int, c_int, c_stream]),
+    "uwr_scale_round_colsum": (c_int, [c_fp, c_ll, c_fp, c_ll, c_int, c_fp, c_int, c_int, c_fp, c_fp, c_stream]),
     "uwr_layernorm_fwd": (c_int, [c_fp, c_fp, c_fp, c_fp, c_fp, c_fp, c_ll, c_int, c_f, c_stream]),
     "uwr_layernorm_bwd_workspace_bytes": (c_sz, [c_ll, c_int]),
     "uwr_layernorm_bwd": (c_int, [c_fp] * 10 + [c_ll, c_int, c_stream]),
@@ -82,7 +83,7 @@ SIGNATURES = {
     "uwr_dwconv_gelu_fwd": (c_int, [c_fp, c_ll, c_fp, c_fp, c_fp, c_fp, c_int, c_int, c_int, c_int, c_int, c_int,
                                     c_stream]),
     "uwr_dwconv_gelu_bwd_workspace_bytes": (c_sz, [c_int, c_int, c_int, c_int]),
-    "uwr_dwconv_gelu_bwd": (c_int, [c_fp, c_fp, c_ll, c_fp, c_fp, c_fp, c_fp, c_fp,
+    "uwr_dwconv_gelu_bwd": (c_int, [c_fp, c_fp, c_ll, c_fp, c_fp, c_fp, c_fp, c_fp, c_fp,
                                     c_int, c_int, c_int, c_int, c_int, c_stream]),
     "uwr_gelu_gate_bwd": (c_int, [c_fp, c_fp, c_ll, c_fp, c_fp, c_fp, c_ll, c_int, c_int, c_stream]),
     "uwr_input_proj_fwd": (c_int, [c_fp, c_fp, c_fp, c_fp, c_int, c_int, c_int, c_int, c_int, c_f, c_stream]),

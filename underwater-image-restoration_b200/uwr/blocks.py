@@ -173,10 +173,9 @@ class AttnBlockFn(torch.autograd.Function):
         B, L, Cc, H, W, heads, hd, shift, scale = ctx.meta
         d = _c(dx1).view(B * L, Cc)
         # DropPath-scaled (and, in tf32 mode, TF32-rounded) branch gradient: operand of three GEMMs
-        d_s = ops.scale_round(d, Cc, dp, L)
+        d_s, dbp = ops.scale_round_colsum(d, Cc, dp, L)   # the column sums are the proj bias gradient
         d_o = ops.linear_dgrad(d_s, ops.rounded_weight(wp), t5=True)
         dwp, _ = ops.linear_wgrad(d_s, o, want_bias=False, t5=True)
-        dbp = ops.colsum(d_s, Cc)
         del d_s
         dqkv, _, dtable, dw = ops.window_attn_bwd(d_o, qkv, 0, qkv, Cc, 2 * Cc, table, wparam, B, H, W, heads, hd,
                                                   shift, scale)
@@ -217,18 +216,16 @@ class LeFFBlockFn(torch.autograd.Function):
         x2, n2w, mean, rstd, y2, u, v, h2, w1, dww, w2, dp = ctx.saved_tensors
         B, L, Cc, Ch, H, W = ctx.meta
         d = _c(dout).view(B * L, Cc)
-        d_s = ops.scale_round(d, Cc, dp, L)
+        d_s, db2 = ops.scale_round_colsum(d, Cc, dp, L)   # column sums = linear2 bias gradient
         # dv = (d_s W2) * gelu'(v): the second GELU's derivative (saved by the forward) rides in the
         # GEMM epilogue
         dv = ops.linear_dgrad(d_s, ops.rounded_weight(w2), mul_by=v, t5=True)
         dw2, _ = ops.linear_wgrad(d_s, h2, want_bias=False, t5=True)
-        db2 = ops.colsum(d_s, Cc)
         del d_s
-        du, ddww, ddwb = ops.dwconv_gelu_bwd(dv, u, dww, B, H, W, Ch)
+        du, ddww, ddwb, db1 = ops.dwconv_gelu_bwd(dv, u, dww, B, H, W, Ch, want_du_colsum=True)
         del dv
         dy2 = ops.linear_dgrad(du, ops.rounded_weight(w1), t5=True)
         dw1, _ = ops.linear_wgrad(du, y2, want_bias=False, t5=True)
-        db1 = ops.colsum(du, Ch)
         del du
         dx, dg, db = ops.layernorm_bwd(dy2, x2, n2w, mean, rstd, dres=d)
         return dx.view(B, L, Cc), dg, db, dw1, db1, ddww, ddwb, dw2, db2, None, None, None

@@ -203,6 +203,20 @@ def scale_round(src2d, cols, rowscale=None, rows_per_group=0, out=None):
     return out
 
 
+def scale_round_colsum(src2d, cols, rowscale=None, rows_per_group=0):
+    """scale_round + column sums of the result (bias gradient of the consuming Linear) in one pass."""
+    rows = src2d.shape[0]
+    if cols % 4 or (cols // 4) > 256 or 256 % (cols // 4):
+        out = scale_round(src2d, cols, rowscale, rows_per_group)
+        return out, colsum(out, cols)
+    out = _empty((rows, cols), src2d)
+    cs = _empty((cols,), src2d)
+    ws = _ws(1024 * cols * 4, src2d)
+    _run("uwr_scale_round_colsum", f"rows{rows} C{cols}", 8 * rows * cols, 0.0, _ptr(src2d), src2d.stride(0),
+         _ptr(out), rows, cols, _ptr(rowscale), rows_per_group, int(_PASSES == 1), _ptr(cs), _ptr(ws))
+    return out, cs
+
+
 def _fresh(w, tag):
     ent = getattr(w, tag, None)
     ver = (w.data_ptr(), w._version, WEIGHT_EPOCH, _PASSES)
@@ -322,17 +336,21 @@ def gelu_gate_bwd(dh2, u2d, v, Ch, mode, du=None):
     return dv
 
 
-def dwconv_gelu_bwd(dv, u2d, weight, B, H, W, Ch, du=None, plain=False):
-    """dv = dL/d(conv output).  Returns du (same row stride as u; only [:, :Ch] is written), dweight, dbias."""
+def dwconv_gelu_bwd(dv, u2d, weight, B, H, W, Ch, du=None, plain=False, want_du_colsum=False):
+    """dv = dL/d(conv output).  Returns du (same row stride as u; only [:, :Ch] is written), dweight, dbias
+    [, column sums of du[:, :Ch]]."""
     if du is None:
         du = torch.empty_like(u2d)
     dweight = torch.empty_like(weight)
     dbias = _empty((Ch,), u2d)
+    dusum = _empty((Ch,), u2d) if want_du_colsum else None
     ws = _ws(fn["uwr_dwconv_gelu_bwd_workspace_bytes"](B, H, W, Ch), u2d)
     n = B * H * W * Ch
     _run("uwr_dwconv_gelu_bwd", f"B{B} H{H} Ch{Ch}", 4 * n * 3, 36.0 * n,
-         _ptr(dv), _ptr(u2d), u2d.stride(0), _ptr(weight), _ptr(du), _ptr(dweight), _ptr(dbias), _ptr(ws),
-         B, H, W, Ch, int(plain))
+         _ptr(dv), _ptr(u2d), u2d.stride(0), _ptr(weight), _ptr(du), _ptr(dweight), _ptr(dbias), _ptr(dusum),
+         _ptr(ws), B, H, W, Ch, int(plain))
+    if want_du_colsum:
+        return du, dweight, dbias, dusum
     return du, dweight, dbias
 
 
