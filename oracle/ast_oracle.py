@@ -109,7 +109,13 @@ def transformer_block(sd, pre, x, heads, shift, att, token_mlp, dp_attn=None, dp
             y = y * dp_attn.view(B, 1, 1)
         x = x + y
     y = F.layer_norm(x, (C,), sd[pre + "norm2.weight"], sd[pre + "norm2.bias"], 1e-5)
-    y = leff(sd, pre + "mlp.", y, H, W) if token_mlp == "leff" else frfn(sd, pre + "mlp.", y, H, W)
+    if token_mlp == "leff":
+        y = leff(sd, pre + "mlp.", y, H, W)
+    elif token_mlp == "frfn":
+        y = frfn(sd, pre + "mlp.", y, H, W)
+    else:  # Mlp.forward, AST.py:285-291
+        y = F.linear(F.gelu(F.linear(y, sd[pre + "mlp.fc1.weight"], sd[pre + "mlp.fc1.bias"])),
+                     sd[pre + "mlp.fc2.weight"], sd[pre + "mlp.fc2.bias"])
     if dp_mlp is not None:
         y = y * dp_mlp.view(B, 1, 1)
     return x + y

@@ -119,6 +119,23 @@ def main():
     vals["Luminance"] = LuminanceLoss()(p, t).item()
     vals["charbonnier_identical"] = LossFunction("charbonnier", "cpu").getloss(p, p).item()  # Loss.ipynb:45
     vals["psnr"] = torchPSNR(t, p).item()
+    # "fflMix" with patch P3: pretrained VGG16 weights are not downloadable offline -> the reference's four
+    # vgg16(pretrained=True) calls are redirected to a re-seeded random-init vgg16 (identical each call)
+    import torchvision
+    orig_vgg = torchvision.models.vgg16
+
+    def seeded_vgg(*a, **k):
+        st = torch.random.get_rng_state()
+        torch.manual_seed(777)
+        m = orig_vgg(weights=None)
+        torch.random.set_rng_state(st)
+        return m
+    torchvision.models.vgg16 = seeded_vgg
+    try:
+        mix = LossFunction("fflMix", "cpu").getloss(p, t)
+    finally:
+        torchvision.models.vgg16 = orig_vgg
+    vals["fflMix"] = [v.item() for v in mix]
     img = (np.random.default_rng(0).random((256, 256, 3)) * 255).astype(np.uint8)
     vals["uiqm"] = [float(v) for v in uqim_utils.getUIQM(img)]
     torch.save(vals, os.path.join(OUT, "losses_metrics.pt"))

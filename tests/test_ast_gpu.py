@@ -122,6 +122,11 @@ def test_ast_frfn_train_128():
     _run(2, 128, 128, True, [], token_mlp="frfn")
 
 
+def test_ast_mlp_eval_128():
+    """AST(token_mlp='mlp') (AST.py:536-537)"""
+    _run(1, 128, 128, False, [], token_mlp="mlp")
+
+
 def test_ast_eval_256():
     _run(1, 256, 256, False, [])
 

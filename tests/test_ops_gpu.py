@@ -446,3 +446,22 @@ def test_frfn_block_vs_oracle(C, scales):
     y2 = blk(x2)
     y2.backward(g)
     assert rel_l2(y2, yo) < 1e-3 and rel_l2(x2.grad, xd.grad) < 2e-3
+
+
+def test_fflmix_loss_tuple_matches_reference_golden():
+    """LossFunction("fflMix").getloss returns the reference's 6-tuple (ModelTrainer.py:82-85); values vs
+    the golden produced by the reference (patch P3), gradient flows through every term."""
+    import os
+    from conftest import ROOT
+    from uwr.losses import LossFunction
+    g = torch.load(os.path.join(ROOT, "tests", "golden", "losses_metrics.pt"), weights_only=False)["fflMix"]
+    torch.manual_seed(0)
+    p = torch.rand(2, 3, 256, 256)
+    t = torch.rand(2, 3, 256, 256)
+    pc = p.cuda().requires_grad_()
+    out = LossFunction("fflMix", "cuda").getloss(pc, t.cuda())
+    assert isinstance(out, tuple) and len(out) == 6
+    for got, want in zip(out, g):
+        assert abs(got.item() - want) <= 2e-4 * abs(want), (got.item(), want)
+    out[0].backward()
+    assert torch.isfinite(pc.grad).all() and pc.grad.abs().sum().item() > 0

@@ -172,3 +172,18 @@ def test_spectral_state_dict_and_oracle_match_reference_golden():
     with torch.no_grad():
         y = spectral_oracle.spectral_forward(model.state_dict(), x)
     assert rel_l2(y, g["out"]) < 1e-5
+
+
+def test_fflmix_torch_terms_match_reference_golden():
+    """The PyTorch-op terms of "fflMix" (VGG perceptual with the P3 seeded weights, Laplacian gradient,
+    MS-SSIM) reproduce the reference LossFunction("fflMix") components (losses.py:108-117)."""
+    from uwr import fflmix
+    g = _load("losses_metrics.pt")["fflMix"]          # [loss, charb, perc, grad, ffl, 1 - ms_ssim]
+    torch.manual_seed(0)
+    p = torch.rand(2, 3, 256, 256)
+    t = torch.rand(2, 3, 256, 256)
+    close = lambda a, b: abs(a - b) <= 1e-5 * abs(b) + 1e-8
+    assert close(fflmix.VGGPerceptual()(p, t).item(), g[2])
+    assert close(fflmix.gradient_loss(p, t).item(), g[3])
+    assert close(1 - fflmix.ms_ssim(p, t).item(), g[5])
+    assert close(0.03 * g[1] + 0.025 * g[2] + 0.01 * g[3] + 0.005 * g[4] + 0.1 * g[5], g[0])

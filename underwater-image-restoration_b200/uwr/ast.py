@@ -109,6 +109,29 @@ class LeFF(nn.Module):
         self.eca = nn.Identity()
 
 
+class Mlp(nn.Module):
+    """plain MLP token mixer (AST.py:272-291; `token_mlp in ['ffn','mlp']`, not the registry default):
+    LayerNorm and both Linears on the uwr kernels, GELU / residual as PyTorch elementwise ops."""
+
+    def __init__(self, in_features, hidden_features=None, out_features=None, act_layer=nn.GELU, drop=0.0):
+        super().__init__()
+        out_features = out_features or in_features
+        hidden_features = hidden_features or in_features
+        self.fc1 = nn.Linear(in_features, hidden_features)
+        self.act = act_layer()
+        self.fc2 = nn.Linear(hidden_features, out_features)
+        self.drop = nn.Dropout(drop)
+        self.in_features, self.hidden_features, self.out_features = in_features, hidden_features, out_features
+
+    def block_forward(self, x, norm, dp_scale, H, W):
+        from . import fn
+        y = fn.linear(fn.layernorm(x, norm), self.fc1.weight, self.fc1.bias, rounded=True)
+        y = fn.linear(torch.nn.functional.gelu(y), self.fc2.weight, self.fc2.bias)
+        if dp_scale is not None:
+            y = y * dp_scale.view(-1, 1, 1)
+        return x + y
+
+
 class TransformerBlock(nn.Module):
     def __init__(self, dim, input_resolution, num_heads, win_size=8, shift_size=0, mlp_ratio=4.0, qkv_bias=True,
                  qk_scale=None, drop=0.0, attn_drop=0.0, drop_path=0.0, act_layer=nn.GELU, norm_layer=nn.LayerNorm,
@@ -144,7 +167,7 @@ class TransformerBlock(nn.Module):
             from .frfn import FRFN
             self.mlp = FRFN(dim, hidden, act_layer=act_layer, drop=drop)
         elif token_mlp in ("ffn", "mlp"):
-            raise NotImplementedError("token_mlp='ffn'/'mlp' is not on the B200 hot path (SURVEY.md §8a row 14)")
+            self.mlp = Mlp(in_features=dim, hidden_features=hidden, act_layer=act_layer, drop=drop)
         else:
             raise Exception("FFN error!")
 
