@@ -25,23 +25,40 @@ def _rows(x):
 
 
 class LinearFn(torch.autograd.Function):
+    """In tf32 mode every product runs on the tcgen05 kernel: operands that are not known to be
+    TF32-rounded (`rounded=False`) get a rounded copy first (one extra pass, still far cheaper than
+    the legacy mma.sync kernel at the tall-skinny shapes of these models)."""
+
     @staticmethod
     def forward(ctx, x, w, b, rounded):
         x2 = _rows(x)
-        t5 = bool(rounded)
-        y = ops.linear(x2, ops.rounded_weight(w) if t5 else w, b, t5=t5)
+        fast = ops.fast_path() and x2.shape[1] % 4 == 0 and w.shape[0] % 4 == 0
+        if fast and not rounded:
+            # a rounded copy only pays off on big token matrices (measured: it costs more than it saves on
+            # the many small per-image products of MDTA); small ones take the legacy kernel, which rounds
+            # its fragments in flight
+            fast = x2.shape[0] >= 131072
+            if fast:
+                x2 = ops.scale_round(x2, x2.shape[1])
+        y = ops.linear(x2, ops.rounded_weight(w) if fast else w, b, t5=fast)
         ctx.save_for_backward(x2, w)
-        ctx.meta = (x.shape, b is not None)
+        ctx.meta = (x.shape, b is not None, fast)
         return y.view(*x.shape[:-1], w.shape[0])
 
     @staticmethod
     @once_differentiable
     def backward(ctx, dy):
         x2, w = ctx.saved_tensors
-        shape, has_b = ctx.meta
+        shape, has_b, fast = ctx.meta
         d = _c(dy).view(-1, w.shape[0])
-        dx = ops.linear_dgrad(d, w) if ctx.needs_input_grad[0] else None
-        dw, db = ops.linear_wgrad(d, x2, want_bias=has_b)
+        db = None
+        if fast:
+            d, db = ops.scale_round_colsum(d, d.shape[1]) if has_b else (ops.scale_round(d, d.shape[1]), None)
+            dx = ops.linear_dgrad(d, ops.rounded_weight(w), t5=True) if ctx.needs_input_grad[0] else None
+            dw, _ = ops.linear_wgrad(d, x2, want_bias=False, t5=True)
+        else:
+            dx = ops.linear_dgrad(d, w) if ctx.needs_input_grad[0] else None
+            dw, db = ops.linear_wgrad(d, x2, want_bias=has_b)
         return (dx.view(shape) if dx is not None else None), dw, db, None
 
 
