@@ -65,7 +65,7 @@ if "dwf" in which or "dwb" in which:
     wt, bs = torch.randn(Ch, 1, 3, 3, device=dev) * 0.3, torch.randn(Ch, device=dev)
     n = B * H * H * Ch
     if "dwf" in which:
-        timeit("dwconv fwd B16 H256 Ch256", lambda: ops.dwconv_gelu_fwd(u, wt, bs, B, H, H, Ch), 4 * n * 3, 18.0 * n)
+        timeit("dwconv fwd B16 H256 Ch256", lambda: ops.dwconv_gelu_fwd(u, wt, bs, B, H, H, Ch, v_is_dgelu=True), 4 * n * 3, 18.0 * n)
     if "dwb" in which:
         dv = torch.randn(B * H * H, Ch, device=dev)
         du = torch.empty_like(u)

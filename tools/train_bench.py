@@ -57,3 +57,18 @@ res = {"arch": arch, "loss": loss, "batch": B, "size": S, "ms_per_step": ms, "im
        "uwr_kernel_ms": {k: round(v[0], 3) for k, v in sorted(fam.items(), key=lambda kv: -kv[1][0])[:8]},
        "uwr_kernel_ms_total": round(sum(v[0] for v in fam.values()), 2)}
 print(json.dumps(res))
+if os.environ.get("UWR_TORCHPROF"):
+    # every CUDA kernel of one step (ours + ATen/cuDNN/cuFFT), to see what is still library code
+    from torch.profiler import profile, ProfilerActivity
+    with profile(activities=[ProfilerActivity.CUDA]) as tp:
+        step(raw, ref)
+        torch.cuda.synchronize()
+    agg = {}
+    for ev in tp.events():
+        if ev.device_type == torch.autograd.DeviceType.CUDA:
+            a = agg.setdefault(ev.name[:90], [0.0, 0])
+            a[0] += ev.device_time / 1e3; a[1] += 1
+    tot = sum(v[0] for v in agg.values())
+    print(f"all CUDA kernels of one step: {tot:.2f} ms")
+    for k, v in sorted(agg.items(), key=lambda kv: -kv[1][0])[:int(os.environ["UWR_TORCHPROF"])]:
+        print(f"  {v[0]:8.3f} ms {v[1]:5d}x  {k}")

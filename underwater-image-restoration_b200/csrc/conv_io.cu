@@ -541,12 +541,20 @@ __global__ void colsum_partial_kernel(const float* __restrict__ x, long long ld,
         partials[(long long)blockIdx.x * cols + c] = t;
     }
 }
-__global__ void colsum_final_kernel(const float* __restrict__ partials, float* __restrict__ out, int P, int cols) {
-    const int c = blockIdx.x * blockDim.x + threadIdx.x;
-    if (c >= cols) return;
+// out[c] = sum_p partials[p][c]: 32 columns x 32 row slices per CTA, fixed order (deterministic)
+__global__ void __launch_bounds__(1024) colsum_final_kernel(const float* __restrict__ partials,
+                                                            float* __restrict__ out, int P, int cols) {
+    __shared__ float sh[32][33];
+    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+    const int c = blockIdx.x * 32 + tx;
     float s = 0.f;
-    for (int p = 0; p < P; ++p) s += partials[(long long)p * cols + c];
-    out[c] = s;
+    if (c < cols)
+        for (int p = ty; p < P; p += 32) s += partials[(long long)p * cols + c];
+    sh[ty][tx] = s;
+    __syncthreads();
+    const float v = warp_sum(sh[tx][ty]);
+    const int co = blockIdx.x * 32 + ty;
+    if (tx == 0 && co < cols) out[co] = v;
 }
 
 int ew_blocks(long long n, int threads) {
@@ -744,7 +752,7 @@ extern "C" int uwr_colsum(const float* x, long long ld, float* out, float* works
     if (P < 1) P = 1;
     colsum_partial_kernel<<<dim3((unsigned)P, cgroups), dim3(32, 8), 0, stream>>>(x, ld, workspace, rows, cols);
     UWR_CHECK_LAUNCH("colsum_partial_kernel");
-    colsum_final_kernel<<<uwr_cdiv(cols, 128), 128, 0, stream>>>(workspace, out, (int)P, cols);
+    colsum_final_kernel<<<uwr_cdiv(cols, 32), 1024, 0, stream>>>(workspace, out, (int)P, cols);
     UWR_CHECK_LAUNCH("colsum_final_kernel");
     return 0;
 }

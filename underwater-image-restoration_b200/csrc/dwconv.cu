@@ -12,6 +12,7 @@
 // HBM-bound: fwd reads u (x1.27 halo, mostly L2 hits) and writes v,h2; bwd reads dv (x1.27), u and
 // writes du.
 #include "uwr_common.cuh"
+#include "uwr_tma.cuh"
 #include "../../include/uwr_b200.h"
 
 namespace {
@@ -27,42 +28,51 @@ __device__ __forceinline__ void fma4(float4& a, const float4& x, const float4& w
     a.x = fmaf(x.x, w.x, a.x); a.y = fmaf(x.y, w.y, a.y); a.z = fmaf(x.z, w.z, a.z); a.w = fmaf(x.w, w.w, a.w);
 }
 
-__global__ void __launch_bounds__(DW_THREADS) dwconv_fwd_kernel(const float* __restrict__ u, long long ld_u,
-                                                                const float* __restrict__ weight,
-                                                                const float* __restrict__ bias,
-                                                                float* __restrict__ v, float* __restrict__ h2,
-                                                                int H, int W, int Ch, int mode, int tiles_x, int rnd,
-                                                                int v_is_dgelu) {
-    __shared__ __align__(16) float h1s[HS * HS][CG];
+// Halo tile (18 x 18 pixels x 32 channels, 41 472 B) of tile `t` -> shared memory by ONE TMA
+// instruction: 4-D tensor map over (C, W, H, B), box (32, 18, 18, 1) starting at (cbase, tx0-1, ty0-1, b);
+// the hardware zero-fills everything outside the image / beyond Ch, which is exactly the conv padding.
+constexpr int TILE_BYTES = HS * HS * CG * (int)sizeof(float);
+static_assert(TILE_BYTES % 128 == 0, "tile buffers must stay 128-byte aligned");
+
+__device__ __forceinline__ void dw_tma_tile(float* dst, const CUtensorMap* map, uint64_t* bar, int tile,
+                                            int tiles_per_img, int tiles_x, int cbase) {
+    const int b = tile / tiles_per_img, tl = tile - b * tiles_per_img;
+    const int ty = tl / tiles_x, tx = tl - ty * tiles_x;
+    uwr_tma::mbar_expect_tx(bar, TILE_BYTES);
+    uwr_tma::tma_load_4d(dst, map, bar, cbase, tx * TS - 1, ty * TS - 1, b);
+}
+
+// persistent: grid = (P, Ch/32).  The halo tile of the NEXT (image, tile) is in flight (TMA, mbarrier)
+// while the current one is convolved.  MODE 0 LeFF, 1 FRFN gate, 2 plain conv.  FAST = training hot
+// path (v stored as gelu'(v), h2 rounded to TF32, full 16x16x32 tiles): no flags or bounds in the loop.
+template <int MODE, bool FAST>
+__global__ void __launch_bounds__(DW_THREADS, 2)
+dwconv_fwd_kernel(const __grid_constant__ CUtensorMap map_u, const float* __restrict__ u, long long ld_u,
+                  const float* __restrict__ weight, const float* __restrict__ bias, float* __restrict__ v,
+                  float* __restrict__ h2, int B, int H, int W, int Ch, int tiles_x, int tiles_per_img, int rnd,
+                  int v_is_dgelu) {
+    extern __shared__ __align__(128) unsigned char dw_raw[];
+    // 128-byte alignment for the TMA destination, computed on the shared-window offset so that the
+    // compiler keeps LDS/STS (a generic uintptr_t round-up turned every access into LD.E/ST.E)
+    float* smem = reinterpret_cast<float*>(dw_raw + ((128u - (uwr_tma::smem_u32(dw_raw) & 127u)) & 127u));
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + 2 * (TILE_BYTES / 4));
     const int tid = threadIdx.x;
     const int c4 = (tid & 7) * 4;
-    const int c = blockIdx.y * CG + c4;
-    const bool cok = c < Ch;  // Ch is a multiple of 4
-    const int b = blockIdx.z;
-    const int ty0 = (blockIdx.x / tiles_x) * TS, tx0 = (blockIdx.x % tiles_x) * TS;
-    const float* ub = u + (long long)b * H * W * ld_u;
+    const int cbase = blockIdx.y * CG;
+    const int c = cbase + c4;
+    const bool cok = FAST || c < Ch;  // Ch is a multiple of 4
+    const int total = B * tiles_per_img;
+    int tile = blockIdx.x;
 
-    // ---- stage gelu(u) with halo: 324 pixels x 8 float4, all loads of a batch in flight together
-    constexpr int NV = (HS * HS * (CG / 4) + DW_THREADS - 1) / DW_THREADS;  // 11
-    float4 val[NV];
-#pragma unroll
-    for (int i = 0; i < NV; ++i) {
-        const int idx = tid + i * DW_THREADS;
-        const int pix = idx >> 3;
-        const int y = ty0 + pix / HS - 1, x = tx0 + pix % HS - 1;
-        val[i] = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (pix < HS * HS && cok && y >= 0 && y < H && x >= 0 && x < W)
-            val[i] = ld4(ub + ((long long)y * W + x) * ld_u + c);
+    if (tid == 0) {
+        uwr_tma::mbar_init(&bars[0], 1);
+        uwr_tma::mbar_init(&bars[1], 1);
+        uwr_tma::mbar_init_fence();
+        uwr_tma::tma_prefetch_map(&map_u);
     }
-#pragma unroll
-    for (int i = 0; i < NV; ++i) {
-        const int idx = tid + i * DW_THREADS;
-        const int pix = idx >> 3;
-        if (pix < HS * HS)  // gelu(0) = 0 keeps the zero padding; mode 2 = plain depthwise conv
-            *reinterpret_cast<float4*>(&h1s[pix][c4]) =
-                mode == 2 ? val[i]
-                          : make_float4(gelu_f(val[i].x), gelu_f(val[i].y), gelu_f(val[i].z), gelu_f(val[i].w));
-    }
+    __syncthreads();
+    if (tid == 0 && tile < total) dw_tma_tile(smem, &map_u, &bars[0], tile, tiles_per_img, tiles_x, cbase);
+
     float4 wgt[9];
 #pragma unroll
     for (int k = 0; k < 9; ++k)
@@ -70,50 +80,83 @@ __global__ void __launch_bounds__(DW_THREADS) dwconv_fwd_kernel(const float* __r
                                    weight[(c + 3) * 9 + k])
                      : make_float4(0.f, 0.f, 0.f, 0.f);
     const float4 bv = (cok && bias != nullptr) ? ld4(bias + c) : make_float4(0.f, 0.f, 0.f, 0.f);
-    __syncthreads();
-
-    const int ly = tid >> 4;            // tile row 0..15
+    const int ly = tid >> 4;               // tile row 0..15
     const int lx0 = ((tid >> 3) & 1) * 8;  // first of 8 columns
-    const int y = ty0 + ly;
-    if (!cok || y >= H) return;
-    const long long tok0 = ((long long)b * H + y) * W + tx0;
-    float4 win[3][3];
+    const bool vdg = FAST || v_is_dgelu, rn = FAST || rnd, hasv = FAST || v != nullptr;
+
+    for (int it = 0; tile < total; tile += gridDim.x, ++it) {
+        float* cur = smem + (it & 1) * (TILE_BYTES / 4);
+        const int ntile = tile + gridDim.x;
+        // the other buffer was released by the __syncthreads that ended the previous iteration
+        if (tid == 0 && ntile < total)
+            dw_tma_tile(smem + ((it + 1) & 1) * (TILE_BYTES / 4), &map_u, &bars[(it + 1) & 1], ntile, tiles_per_img,
+                        tiles_x, cbase);
+        uwr_tma::mbar_wait(&bars[it & 1], (it >> 1) & 1);
+        if (MODE != 2) {  // GELU in place, once per staged element (gelu(0) = 0 keeps the zero padding)
+            float4* p4 = reinterpret_cast<float4*>(cur) + tid;
 #pragma unroll
-    for (int ky = 0; ky < 3; ++ky) {
-        win[ky][1] = ld4(&h1s[(ly + ky) * HS + lx0][c4]);
-        win[ky][2] = ld4(&h1s[(ly + ky) * HS + lx0 + 1][c4]);
-    }
-#pragma unroll
-    for (int i = 0; i < 8; ++i) {
-        const int lx = lx0 + i;
-#pragma unroll
-        for (int ky = 0; ky < 3; ++ky) {
-            win[ky][0] = win[ky][1];
-            win[ky][1] = win[ky][2];
-            win[ky][2] = ld4(&h1s[(ly + ky) * HS + lx + 2][c4]);
-        }
-        if (tx0 + lx < W) {
-            float4 acc = bv;
-#pragma unroll
-            for (int ky = 0; ky < 3; ++ky)
-#pragma unroll
-                for (int kx = 0; kx < 3; ++kx) fma4(acc, win[ky][kx], wgt[ky * 3 + kx]);
-            float a[4] = {acc.x, acc.y, acc.z, acc.w}, o[4], sv[4];
-            float4 gate = make_float4(0.f, 0.f, 0.f, 0.f);
-            if (mode == 1) gate = ld4(u + (tok0 + lx) * ld_u + Ch + c);
-            const float gt[4] = {gate.x, gate.y, gate.z, gate.w};
-#pragma unroll
-            for (int e = 0; e < 4; ++e) {
-                float cdf, pdf;
-                gelu_parts(a[e], cdf, pdf);
-                sv[e] = v_is_dgelu ? fmaf(a[e], pdf, cdf) : a[e];
-                o[e] = mode == 2 ? a[e] : a[e] * cdf;
-                if (mode == 1) o[e] *= gelu_f(gt[e]);
-                if (rnd) o[e] = tf32_round(o[e]);
+            for (int i = 0; i < 10; ++i) {  // 18*18*8 = 2592 float4 = 10 * 256 + 32
+                float4 t4 = p4[i * DW_THREADS];
+                p4[i * DW_THREADS] = make_float4(gelu_f(t4.x), gelu_f(t4.y), gelu_f(t4.z), gelu_f(t4.w));
             }
-            if (v) *reinterpret_cast<float4*>(v + (tok0 + lx) * Ch + c) = make_float4(sv[0], sv[1], sv[2], sv[3]);
-            *reinterpret_cast<float4*>(h2 + (tok0 + lx) * Ch + c) = make_float4(o[0], o[1], o[2], o[3]);
+            if (tid < 32) {
+                float4 t4 = p4[10 * DW_THREADS];
+                p4[10 * DW_THREADS] = make_float4(gelu_f(t4.x), gelu_f(t4.y), gelu_f(t4.z), gelu_f(t4.w));
+            }
+            uwr_tma::fence_proxy_async_smem();  // these generic writes precede the TMA that reuses the buffer
+            __syncthreads();
         }
+        const int b = tile / tiles_per_img, tl = tile - b * tiles_per_img;
+        const int ty0 = (tl / tiles_x) * TS, tx0 = (tl % tiles_x) * TS;
+        const int y = ty0 + ly;
+        if (FAST || (cok && y < H)) {
+            const long long tok0 = ((long long)b * H + y) * W + tx0 + lx0;
+            float* h2p = h2 + tok0 * Ch + c;
+            float* vp = hasv ? v + tok0 * Ch + c : nullptr;
+            const float* gp = u + tok0 * ld_u + Ch + c;  // FRFN gate half (MODE 1)
+            const float* sp = cur + (ly * HS + lx0) * CG + c4;
+            float4 col[3][3];  // col[ky][j % 3] = staged pixel (ly + ky, lx0 + j): rotating registers, no moves
+#pragma unroll
+            for (int ky = 0; ky < 3; ++ky) {
+                col[ky][0] = ld4(sp + (ky * HS + 0) * CG);
+                col[ky][1] = ld4(sp + (ky * HS + 1) * CG);
+            }
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+#pragma unroll
+                for (int ky = 0; ky < 3; ++ky) col[ky][(i + 2) % 3] = ld4(sp + (ky * HS + i + 2) * CG);
+                if (FAST || tx0 + lx0 + i < W) {
+                    float4 acc = bv;
+#pragma unroll
+                    for (int ky = 0; ky < 3; ++ky)
+#pragma unroll
+                        for (int kx = 0; kx < 3; ++kx) fma4(acc, col[ky][(i + kx) % 3], wgt[ky * 3 + kx]);
+                    float a[4] = {acc.x, acc.y, acc.z, acc.w}, o[4], sv[4];
+                    float gt[4] = {0.f, 0.f, 0.f, 0.f};
+                    if (MODE == 1) {
+                        const float4 gate = ld4(gp + (long long)i * ld_u);
+                        gt[0] = gate.x; gt[1] = gate.y; gt[2] = gate.z; gt[3] = gate.w;
+                    }
+#pragma unroll
+                    for (int e = 0; e < 4; ++e) {
+                        if (MODE == 2) {
+                            sv[e] = a[e];
+                            o[e] = a[e];
+                        } else {
+                            float cdf, pdf;
+                            gelu_parts(a[e], cdf, pdf);
+                            sv[e] = vdg ? fmaf(a[e], pdf, cdf) : a[e];
+                            o[e] = a[e] * cdf;
+                            if (MODE == 1) o[e] *= gelu_f(gt[e]);
+                        }
+                        if (rn) o[e] = tf32_round(o[e]);
+                    }
+                    if (hasv) *reinterpret_cast<float4*>(vp + (long long)i * Ch) = make_float4(sv[0], sv[1], sv[2], sv[3]);
+                    *reinterpret_cast<float4*>(h2p + (long long)i * Ch) = make_float4(o[0], o[1], o[2], o[3]);
+                }
+            }
+        }
+        __syncthreads();  // everyone is done with `cur` before the TMA of iteration it+1 overwrites it
     }
 }
 
@@ -149,20 +192,32 @@ __device__ __forceinline__ void fma2(float2& a, const float2& x, const float2& w
     a.x = fmaf(x.x, w.x, a.x); a.y = fmaf(x.y, w.y, a.y);
 }
 
-__global__ void __launch_bounds__(DW_THREADS, 2) dwconv_bwd_kernel(const float* __restrict__ dv,
-                                                                   const float* __restrict__ u, long long ld_u,
-                                                                   const float* __restrict__ weight,
-                                                                   float* __restrict__ du,
-                                                                   float* __restrict__ partials, int B, int H, int W,
-                                                                   int Ch, int tiles_x, int tiles_per_img, int rnd,
-                                                                   int plain) {
-    __shared__ __align__(16) float dvs[HS * HS][CG];
+template <bool PLAIN, bool FAST>
+__global__ void __launch_bounds__(DW_THREADS, 2)
+dwconv_bwd_kernel(const __grid_constant__ CUtensorMap map_dv, const float* __restrict__ u, long long ld_u,
+                  const float* __restrict__ weight, float* __restrict__ du, float* __restrict__ partials, int B, int H,
+                  int W, int Ch, int tiles_x, int tiles_per_img, int rnd) {
+    extern __shared__ __align__(128) unsigned char dw_raw[];
+    float* smem = reinterpret_cast<float*>(dw_raw + ((128u - (uwr_tma::smem_u32(dw_raw) & 127u)) & 127u));
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + 2 * (TILE_BYTES / 4));
     const int tid = threadIdx.x;
     const int c2 = (tid & 15) * 2;
-    const int c = blockIdx.y * CG + c2;
-    const bool cok = c < Ch;  // Ch is a multiple of 4
+    const int cbase = blockIdx.y * CG;
+    const int c = cbase + c2;
+    const bool cok = FAST || c < Ch;  // Ch is a multiple of 4
     const int ly = tid >> 4;
-    const int s4 = (tid & 7) * 4;  // staging uses 128-bit pieces
+    const bool rn = FAST || rnd;
+    const int total = B * tiles_per_img;
+    int tile = blockIdx.x;
+
+    if (tid == 0) {
+        uwr_tma::mbar_init(&bars[0], 1);
+        uwr_tma::mbar_init(&bars[1], 1);
+        uwr_tma::mbar_init_fence();
+        uwr_tma::tma_prefetch_map(&map_dv);
+    }
+    __syncthreads();
+    if (tid == 0 && tile < total) dw_tma_tile(smem, &map_dv, &bars[0], tile, tiles_per_img, tiles_x, cbase);
 
     float2 wgt[9], dwt[9];
 #pragma unroll
@@ -172,65 +227,50 @@ __global__ void __launch_bounds__(DW_THREADS, 2) dwconv_bwd_kernel(const float* 
     }
     float2 dbs = make_float2(0.f, 0.f);
     float2 dus = make_float2(0.f, 0.f);  // column sums of du = bias gradient of the Linear that produced u
-    const bool sok = blockIdx.y * CG + s4 < Ch;
 
-    const int total = B * tiles_per_img;
-    for (int tile = blockIdx.x; tile < total; tile += gridDim.x) {
-        const int b = tile / tiles_per_img, tl = tile % tiles_per_img;
+    for (int it = 0; tile < total; tile += gridDim.x, ++it) {
+        const float* dvs = smem + (it & 1) * (TILE_BYTES / 4);
+        const int ntile = tile + gridDim.x;
+        if (tid == 0 && ntile < total)
+            dw_tma_tile(smem + ((it + 1) & 1) * (TILE_BYTES / 4), &map_dv, &bars[(it + 1) & 1], ntile, tiles_per_img,
+                        tiles_x, cbase);
+        const int b = tile / tiles_per_img, tl = tile - b * tiles_per_img;
         const int ty0 = (tl / tiles_x) * TS, tx0 = (tl % tiles_x) * TS;
-        const long long base = (long long)b * H * W;
-        __syncthreads();
-        constexpr int NV = (HS * HS * (CG / 4) + DW_THREADS - 1) / DW_THREADS;  // 11 float4 per thread
-#pragma unroll
-        for (int h = 0; h < 2; ++h) {  // two batches keep the register footprint down
-            float4 val[(NV + 1) / 2];
-#pragma unroll
-            for (int i = 0; i < (NV + 1) / 2; ++i) {
-                const int idx = tid + (h * ((NV + 1) / 2) + i) * DW_THREADS;
-                const int pix = idx >> 3;
-                const int y = ty0 + pix / HS - 1, x = tx0 + pix % HS - 1;
-                val[i] = make_float4(0.f, 0.f, 0.f, 0.f);
-                if (pix < HS * HS && sok && y >= 0 && y < H && x >= 0 && x < W)
-                    val[i] = ld4(dv + (base + (long long)y * W + x) * Ch + blockIdx.y * CG + s4);
-            }
-#pragma unroll
-            for (int i = 0; i < (NV + 1) / 2; ++i) {
-                const int idx = tid + (h * ((NV + 1) / 2) + i) * DW_THREADS;
-                const int pix = idx >> 3;
-                if (pix < HS * HS) *reinterpret_cast<float4*>(&dvs[pix][s4]) = val[i];
-            }
-        }
         const int y = ty0 + ly;
-        const bool rok = cok && y < H;
-        const long long tok0 = base + (long long)y * W + tx0;
-        __syncthreads();
+        const bool rok = FAST || (cok && y < H);
+        const long long tok0 = ((long long)b * H + y) * W + tx0;
+        const float* up = u + tok0 * ld_u + c;
+        float* dup = du + tok0 * ld_u + c;
+        // the first strip's u values are requested before waiting for the halo tile
+        float2 uc[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i)
+            uc[i] = (rok && (FAST || tx0 + i < W)) ? ld2(up + (long long)i * ld_u) : make_float2(0.f, 0.f);
+        uwr_tma::mbar_wait(&bars[it & 1], (it >> 1) & 1);
         if (rok) {
+            const float* sp = dvs + (ly * HS) * CG + c2;
 #pragma unroll
             for (int hx = 0; hx < 2; ++hx) {  // two strips of 8 columns
                 const int lx0 = hx * 8;
-                float2 uc[8];
+                if (hx == 1) {
 #pragma unroll
-                for (int i = 0; i < 8; ++i)
-                    uc[i] = (tx0 + lx0 + i < W) ? ld2(u + (tok0 + lx0 + i) * ld_u + c) : make_float2(0.f, 0.f);
-                // window of dv around the output pixel: win[a][b] = dv[y-1+a][x-1+b]
-                float2 win[3][3];
+                    for (int i = 0; i < 8; ++i)
+                        uc[i] = (FAST || tx0 + 8 + i < W) ? ld2(up + (long long)(8 + i) * ld_u) : make_float2(0.f, 0.f);
+                }
+                // col[a][j % 3] = dv at tile pixel (ly - 1 + a, lx0 - 1 + j): rotating registers, no moves
+                float2 col[3][3];
 #pragma unroll
                 for (int a = 0; a < 3; ++a) {
-                    win[a][1] = ld2(&dvs[(ly + a) * HS + lx0][c2]);
-                    win[a][2] = ld2(&dvs[(ly + a) * HS + lx0 + 1][c2]);
+                    col[a][0] = ld2(sp + (a * HS + lx0 + 0) * CG);
+                    col[a][1] = ld2(sp + (a * HS + lx0 + 1) * CG);
                 }
 #pragma unroll
                 for (int i = 0; i < 8; ++i) {
-                    const int lx = lx0 + i;
 #pragma unroll
-                    for (int a = 0; a < 3; ++a) {
-                        win[a][0] = win[a][1];
-                        win[a][1] = win[a][2];
-                        win[a][2] = ld2(&dvs[(ly + a) * HS + lx + 2][c2]);
-                    }
-                    if (tx0 + lx < W) {
+                    for (int a = 0; a < 3; ++a) col[a][(i + 2) % 3] = ld2(sp + (a * HS + lx0 + i + 2) * CG);
+                    if (FAST || tx0 + lx0 + i < W) {
                         float cdf0 = 1.f, pdf0 = 0.f, cdf1 = 1.f, pdf1 = 0.f;  // plain conv: h1 = u, gelu' = 1
-                        if (!plain) {
+                        if (!PLAIN) {
                             gelu_parts(uc[i].x, cdf0, pdf0);
                             gelu_parts(uc[i].y, cdf1, pdf1);
                         }
@@ -241,26 +281,28 @@ __global__ void __launch_bounds__(DW_THREADS, 2) dwconv_bwd_kernel(const float* 
                         for (int ky = 0; ky < 3; ++ky)
 #pragma unroll
                             for (int kx = 0; kx < 3; ++kx) {
-                                const float2 d = win[2 - ky][2 - kx];
+                                const float2 d = col[2 - ky][(i + 2 - kx) % 3];
                                 fma2(dh1, d, wgt[ky * 3 + kx]);
                                 fma2(dwt[ky * 3 + kx], h1, d);
                             }
-                        dbs.x += win[1][1].x;
-                        dbs.y += win[1][1].y;
-                        float2 o = make_float2(dh1.x * fmaf(uc[i].x, pdf0, cdf0), dh1.y * fmaf(uc[i].y, pdf1, cdf1));
-                        if (rnd) o = make_float2(tf32_round(o.x), tf32_round(o.y));
+                        const float2 ctr = col[1][(i + 1) % 3];
+                        dbs.x += ctr.x;
+                        dbs.y += ctr.y;
+                        float2 o = PLAIN ? dh1
+                                         : make_float2(dh1.x * fmaf(uc[i].x, pdf0, cdf0), dh1.y * fmaf(uc[i].y, pdf1, cdf1));
+                        if (rn) o = make_float2(tf32_round(o.x), tf32_round(o.y));
                         dus.x += o.x;
                         dus.y += o.y;
-                        *reinterpret_cast<float2*>(du + (tok0 + lx) * ld_u + c) = o;
+                        *reinterpret_cast<float2*>(dup + (long long)(lx0 + i) * ld_u) = o;
                     }
                 }
             }
         }
+        __syncthreads();  // everyone is done with this buffer before the next TMA overwrites it
     }
-    // cross-thread reduction: 20 partial sums per thread (10 taps x 2 channels), 16 threads per channel
-    // pair; the tile buffer is reused as red[slot][tid]
-    __syncthreads();
-    float* red = &dvs[0][0];
+    // cross-thread reduction: 22 partial sums per thread (11 slots x 2 channels), 16 threads per channel
+    // pair; the tile buffers (2 x 10 368 floats >= 22 x 256) are reused as red[slot][tid]
+    float* red = smem;
 #pragma unroll
     for (int k = 0; k < 9; ++k) {
         red[(k * 2 + 0) * DW_THREADS + tid] = dwt[k].x;
@@ -295,10 +337,20 @@ __global__ void dwconv_param_reduce_kernel(const float* __restrict__ partials, f
     else du_colsum[c] = s;
 }
 
+constexpr int DW_SMEM_BYTES = 2 * TILE_BYTES + 128 + 16;  // two halo buffers + alignment slack + 2 mbarriers
+
+// (C, W, H, B) view of a token tensor with row stride ld; box = one halo tile of 32 channels
+int dw_halo_map(CUtensorMap* m, const float* base, long long ld, int B, int H, int W, int Ch) {
+    const long long dims[4] = {Ch, W, H, B};
+    const long long strides[3] = {ld, (long long)W * ld, (long long)H * W * ld};
+    const int box[4] = {CG, HS, HS, 1};
+    return uwr_tma::encode_f32(m, base, 4, dims, strides, box, CU_TENSOR_MAP_SWIZZLE_NONE);
+}
+
 int bwd_ctas(int B, int H, int W, int Ch) {
     const int tiles = B * uwr_cdiv(H, TS) * uwr_cdiv(W, TS);
     const int groups = uwr_cdiv(Ch, CG);
-    int p = uwr_cdiv(4 * uwr_sm_count(), groups);
+    int p = uwr_cdiv(2 * uwr_sm_count(), groups);  // 2 CTAs/SM (two 41 KB halo buffers each)
     if (p > tiles) p = tiles;
     return p < 1 ? 1 : p;
 }
@@ -315,9 +367,31 @@ extern "C" int uwr_dwconv_gelu_fwd(const float* u, long long ld_u, const float* 
     UWR_REQUIRE(B > 0 && B <= 65535, "uwr_dwconv_gelu_fwd: bad batch %d", B);
     UWR_REQUIRE(Ch % 4 == 0 && ld_u % 4 == 0, "uwr_dwconv_gelu_fwd: Ch and ld_u must be multiples of 4");
     const int tx = uwr_cdiv(W, TS), ty = uwr_cdiv(H, TS);
-    dim3 grid(tx * ty, uwr_cdiv(Ch, CG), B);
-    dwconv_fwd_kernel<<<grid, DW_THREADS, 0, stream>>>(u, ld_u, weight, bias, v, h2, H, W, Ch, mode, tx, uwr_round_outputs(),
-                                                      v_is_dgelu);
+    CUtensorMap map_u;
+    if (dw_halo_map(&map_u, u, ld_u, B, H, W, Ch) != 0) return -3;
+    const bool fast = v != nullptr && v_is_dgelu && uwr_round_outputs() && H % TS == 0 && W % TS == 0 && Ch % CG == 0;
+    dim3 grid(bwd_ctas(B, H, W, Ch), uwr_cdiv(Ch, CG));
+#define DW_FWD(M, F)                                                                                              \
+    do {                                                                                                          \
+        static bool configured = false;                                                                           \
+        if (!configured) {                                                                                        \
+            UWR_CUDA(cudaFuncSetAttribute(dwconv_fwd_kernel<M, F>, cudaFuncAttributeMaxDynamicSharedMemorySize,   \
+                                          DW_SMEM_BYTES));                                                        \
+            configured = true;                                                                                    \
+        }                                                                                                         \
+        dwconv_fwd_kernel<M, F><<<grid, DW_THREADS, DW_SMEM_BYTES, stream>>>(                                     \
+            map_u, u, ld_u, weight, bias, v, h2, B, H, W, Ch, tx, tx * ty, uwr_round_outputs(), v_is_dgelu);      \
+    } while (0)
+    if (mode == 0) {
+        if (fast) DW_FWD(0, true);
+        else DW_FWD(0, false);
+    } else if (mode == 1) {
+        if (fast) DW_FWD(1, true);
+        else DW_FWD(1, false);
+    } else {
+        DW_FWD(2, false);
+    }
+#undef DW_FWD
     UWR_CHECK_LAUNCH("dwconv_fwd_kernel");
     return 0;
 }
@@ -347,8 +421,28 @@ extern "C" int uwr_dwconv_gelu_bwd(const float* dv, const float* u, long long ld
     const int tx = uwr_cdiv(W, TS), ty = uwr_cdiv(H, TS);
     const int P = bwd_ctas(B, H, W, Ch);
     dim3 grid(P, uwr_cdiv(Ch, CG));
-    dwconv_bwd_kernel<<<grid, DW_THREADS, 0, stream>>>(dv, u, ld_u, weight, du, workspace, B, H, W, Ch, tx, tx * ty,
-                                                      uwr_round_outputs(), plain);
+    CUtensorMap map_dv;
+    if (dw_halo_map(&map_dv, dv, Ch, B, H, W, Ch) != 0) return -3;
+    const bool fast = uwr_round_outputs() && H % TS == 0 && W % TS == 0 && Ch % CG == 0;
+#define DW_BWD(PL, F)                                                                                             \
+    do {                                                                                                          \
+        static bool configured = false;                                                                           \
+        if (!configured) {                                                                                        \
+            UWR_CUDA(cudaFuncSetAttribute(dwconv_bwd_kernel<PL, F>, cudaFuncAttributeMaxDynamicSharedMemorySize,  \
+                                          DW_SMEM_BYTES));                                                        \
+            configured = true;                                                                                    \
+        }                                                                                                         \
+        dwconv_bwd_kernel<PL, F><<<grid, DW_THREADS, DW_SMEM_BYTES, stream>>>(                                    \
+            map_dv, u, ld_u, weight, du, workspace, B, H, W, Ch, tx, tx * ty, uwr_round_outputs());               \
+    } while (0)
+    if (plain) {
+        if (fast) DW_BWD(true, true);
+        else DW_BWD(true, false);
+    } else {
+        if (fast) DW_BWD(false, true);
+        else DW_BWD(false, false);
+    }
+#undef DW_BWD
     UWR_CHECK_LAUNCH("dwconv_bwd_kernel");
     dwconv_param_reduce_kernel<<<uwr_cdiv(11 * Ch, 128), 128, 0, stream>>>(workspace, dweight, dbias, du_colsum, P, Ch);
     UWR_CHECK_LAUNCH("dwconv_param_reduce_kernel");

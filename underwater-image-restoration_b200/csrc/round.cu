@@ -84,12 +84,20 @@ __global__ void __launch_bounds__(256) scale_round_colsum_kernel(const float* __
         reinterpret_cast<float4*>(partials)[(long long)blockIdx.x * cols4 + c4] = acc;
     }
 }
-__global__ void colsum_partials_kernel(const float* __restrict__ partials, float* __restrict__ out, int P, int cols) {
-    const int c = blockIdx.x * blockDim.x + threadIdx.x;
-    if (c >= cols) return;
+// out[c] = sum_p partials[p][c]: 32 columns x 32 row slices per CTA, fixed order (deterministic)
+__global__ void __launch_bounds__(1024) colsum_partials_kernel(const float* __restrict__ partials,
+                                                               float* __restrict__ out, int P, int cols) {
+    __shared__ float sh[32][33];
+    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+    const int c = blockIdx.x * 32 + tx;
     float s = 0.f;
-    for (int p = 0; p < P; ++p) s += partials[(long long)p * cols + c];
-    out[c] = s;
+    if (c < cols)
+        for (int p = ty; p < P; p += 32) s += partials[(long long)p * cols + c];
+    sh[ty][tx] = s;
+    __syncthreads();
+    const float v = warp_sum(sh[tx][ty]);
+    const int co = blockIdx.x * 32 + ty;
+    if (tx == 0 && co < cols) out[co] = v;
 }
 
 }  // namespace
@@ -111,7 +119,7 @@ extern "C" int uwr_scale_round_colsum(const float* src, long long ld_src, float*
                                                                    rows_per_group > 0 ? rows_per_group : 1, do_round,
                                                                    workspace);
     UWR_CHECK_LAUNCH("scale_round_colsum_kernel");
-    colsum_partials_kernel<<<uwr_cdiv(cols, 128), 128, 0, stream>>>(workspace, colsum, (int)blocks, cols);
+    colsum_partials_kernel<<<uwr_cdiv(cols, 32), 1024, 0, stream>>>(workspace, colsum, (int)blocks, cols);
     UWR_CHECK_LAUNCH("colsum_partials_kernel");
     return 0;
 }

@@ -59,15 +59,28 @@ __device__ __forceinline__ float tf32_round(float x) { return __uint_as_float(f2
 // rounding level) needs exp(-z^2) = exp(-x^2/2), which is also the Gaussian density.  ~14
 // instructions for gelu AND gelu' instead of two erff + one expf (the dwconv kernels were
 // ALU-bound on erff).
+// MUFU without the denormal-range fix-up code that __expf / __fdividef expand to without -ftz (the
+// fix-ups were ~40 % of the instructions of the issue-bound dwconv kernels): arguments here are
+// never denormal-sensitive (1 <= 1 + p|x|; exp(-x^2/2) flushing to 0 below 1e-38 is exact enough).
+__device__ __forceinline__ float rcp_ftz(float x) {
+    float r;
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+    return r;
+}
+__device__ __forceinline__ float ex2_ftz(float x) {
+    float r;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+    return r;
+}
 __device__ __forceinline__ void gelu_parts(float x, float& cdf, float& pdf) {
-    const float ax = fabsf(x);
-    const float t = __fdividef(1.0f, fmaf(0.23164189f, ax, 1.0f));  // 1/(1 + p*z), p*z = 0.3275911*|x|/sqrt(2)
-    const float e = __expf(-0.5f * x * x);
-    float poly = fmaf(1.061405429f, t, -1.453152027f);
-    poly = fmaf(poly, t, 1.421413741f);
-    poly = fmaf(poly, t, -0.284496736f);
-    poly = fmaf(poly, t, 0.254829592f);
-    const float tail = 0.5f * poly * t * e;  // = 0.5*(1 - erf(z)) = Phi(-|x|)
+    const float t = rcp_ftz(fmaf(0.23164189f, fabsf(x), 1.0f));  // 1/(1 + p*z), p*z = 0.3275911*|x|/sqrt(2)
+    const float s = x * 0.84932180028801904272f;                 // sqrt(log2(e)/2): exp(-x^2/2) = 2^(-s^2)
+    const float e = ex2_ftz(-(s * s));
+    float poly = fmaf(0.5f * 1.061405429f, t, 0.5f * -1.453152027f);  // the 0.5 of Phi(-|x|) folded in
+    poly = fmaf(poly, t, 0.5f * 1.421413741f);
+    poly = fmaf(poly, t, 0.5f * -0.284496736f);
+    poly = fmaf(poly, t, 0.5f * 0.254829592f);
+    const float tail = (poly * t) * e;  // = 0.5*(1 - erf(z)) = Phi(-|x|)
     cdf = x >= 0.f ? 1.0f - tail : tail;
     pdf = 0.39894228040143267794f * e;
 }

@@ -1,0 +1,117 @@
+// TMA (cp.async.bulk.tensor) + mbarrier wrappers and the host-side tensor-map encoder shared by the
+// kernels that stage tiles through the async proxy (gemm_tcgen05.cu, dwconv.cu, fft2d.cu).
+#pragma once
+#include <cuda.h>
+
+#include "uwr_common.cuh"
+
+namespace uwr_tma {
+
+constexpr uint32_t SPIN_LIMIT = 1u << 24;
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_init_fence() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
+    uint32_t ok;
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+        "selp.u32 %0, 1, 0, p;\n"
+        "}"
+        : "=r"(ok)
+        : "r"(smem_u32(bar)), "r"(parity)
+        : "memory");
+    return ok != 0;
+}
+// bounded spin: a protocol bug traps (launch error) instead of hanging the GPU
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+    uint32_t spins = 0;
+    while (!mbar_try_wait(bar, parity)) {
+        if (++spins > SPIN_LIMIT) __trap();
+    }
+}
+// generic-proxy accesses to shared memory made before this fence are ordered before later
+// async-proxy (TMA) accesses to the same locations
+__device__ __forceinline__ void fence_proxy_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+
+__device__ __forceinline__ void tma_load_2d(void* dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+        ::"r"(smem_u32(dst)), "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
+        : "memory");
+}
+__device__ __forceinline__ void tma_load_3d(void* dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1, int c2) {
+    asm volatile(
+        "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
+        ::"r"(smem_u32(dst)), "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2)
+        : "memory");
+}
+__device__ __forceinline__ void tma_load_4d(void* dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1, int c2,
+                                            int c3) {
+    asm volatile(
+        "cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
+        ::"r"(smem_u32(dst)), "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+        : "memory");
+}
+__device__ __forceinline__ void tma_prefetch_map(const CUtensorMap* map) {
+    asm volatile("prefetch.tensormap [%0];" ::"l"(map) : "memory");
+}
+
+// ------------------------------------------------------------------------------------ host side
+// cuTensorMapEncodeTiled is resolved through the runtime (no link-time dependency on libcuda.so, so
+// the library also loads on a machine without a driver, e.g. for the CPU-side symbol checks).
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static inline EncodeTiledFn encode_tiled_fn() {
+    static EncodeTiledFn fn = nullptr;
+    if (!fn) {
+        void* p = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
+            q == cudaDriverEntryPointSuccess)
+            fn = (EncodeTiledFn)p;
+    }
+    return fn;
+}
+
+// fp32 tensor of `rank` dims (dims[0] innermost, contiguous; strides_elems[i] = elements between
+// consecutive indices of dim i+1), box[] elements per dim, out-of-bounds elements read as 0
+static inline int encode_f32(CUtensorMap* m, const float* base, int rank, const long long* dims,
+                             const long long* strides_elems, const int* box, CUtensorMapSwizzle swz) {
+    cuuint64_t d[5], s[4];
+    cuuint32_t b[5], es[5];
+    for (int i = 0; i < rank; ++i) {
+        d[i] = (cuuint64_t)dims[i];
+        b[i] = (cuuint32_t)box[i];
+        es[i] = 1;
+        if (i + 1 < rank) s[i] = (cuuint64_t)strides_elems[i] * 4;
+    }
+    EncodeTiledFn enc = encode_tiled_fn();
+    if (!enc) {
+        uwr_set_error("cuTensorMapEncodeTiled is not available from the driver");
+        return -3;
+    }
+    CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, (cuuint32_t)rank, (void*)base, d, s, b, es,
+                     CU_TENSOR_MAP_INTERLEAVE_NONE, swz, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) {
+        uwr_set_error("cuTensorMapEncodeTiled(rank %d) failed: %d (dims %lld %lld ..., box %d %d ...)", rank, (int)r,
+                      dims[0], rank > 1 ? dims[1] : 0LL, box[0], rank > 1 ? box[1] : 0);
+        return -3;
+    }
+    return 0;
+}
+
+}  // namespace uwr_tma
