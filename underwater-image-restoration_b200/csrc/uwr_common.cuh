@@ -47,11 +47,12 @@ int uwr_sm_count();
 // ---- numerics ---------------------------------------------------------------------------
 // fp32 -> tf32 with round-to-nearest (ties away); the tensor core would otherwise truncate,
 // which biases every product by ~-1e-3 relative.
-__device__ __forceinline__ uint32_t f2tf32(float x) {
-    uint32_t r;
-    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
-    return r;
-}
+// cvt.rna.tf32.f32 is not a native sm_100a instruction: ptxas expands it to ~6 instructions
+// (FSETP / IADD / LOP3 / SEL ... for the NaN and overflow cases) and it was 40 % of the attention
+// backward's instruction stream.  On the sign-magnitude bit pattern "add half an ulp of the 10-bit
+// mantissa, clear the low 13 bits" is the same rounding (nearest, ties away from zero) for every
+// finite value below the overflow threshold, in two integer instructions.
+__device__ __forceinline__ uint32_t f2tf32(float x) { return (__float_as_uint(x) + 0x1000u) & 0xFFFFE000u; }
 __device__ __forceinline__ float tf32_round(float x) { return __uint_as_float(f2tf32(x)); }
 
 // erf-form GELU as nn.GELU() in the reference (AST.py:295-301).  Phi(x) and phi(x) share ONE
@@ -110,8 +111,8 @@ __device__ __forceinline__ float warp_max(float v) {
 // shape is far below a tcgen05 atom, e.g. 64x64x32 attention windows).
 __device__ __forceinline__ void mma_tf32_16x8x8(float (&d)[4], const uint32_t (&a)[4],
                                                 const uint32_t (&b)[2]) {
-    asm volatile(
-        "mma.sync.aligned.m16n8k8.row.col.f32.tf32.tf32.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, "
+    // not volatile: a pure function of its operands, so the scheduler may interleave independent MMAs
+    asm("mma.sync.aligned.m16n8k8.row.col.f32.tf32.tf32.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, "
         "{%8,%9}, {%0,%1,%2,%3};"
         : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
         : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b[0]), "r"(b[1]));

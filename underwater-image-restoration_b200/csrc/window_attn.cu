@@ -99,9 +99,21 @@ __device__ __forceinline__ void stage_tiles(const TileSrc<HD> (&t)[NT], const lo
     }
 }
 
+// 3xTF32 operand split.  The tensor core reads only the upper 19 bits of an fp32 operand (it
+// truncates), so the "hi" part is the raw value itself and "lo" is what the truncation drops:
+// lo = x - trunc(x), exact in fp32 (13 significant bits; the hardware truncating it again loses
+// < 2^-20 |x|).  Two instructions per element instead of two roundings and a subtraction.
 __device__ __forceinline__ void split_tf32(float x, uint32_t& hi, uint32_t& lo) {
-    hi = f2tf32(x);
-    lo = f2tf32(x - __uint_as_float(hi));
+    hi = __float_as_uint(x);
+    lo = __float_as_uint(x - __uint_as_float(hi & 0xFFFFE000u));
+}
+
+// X3: 3xTF32 split; otherwise a single operand rounded to nearest (a raw value would be truncated,
+// which biases every product)
+template <bool X3>
+__device__ __forceinline__ void prep_tf32(float x, uint32_t& hi, uint32_t& lo) {
+    if (X3) split_tf32(x, hi, lo);
+    else { hi = f2tf32(x); lo = 0u; }
 }
 
 // acc[nt][4] (16 rows x 64 cols) = A[r0.., :HD] * Bm[:, :HD]^T   (both row-major fp32 [64][HD+4]),
@@ -121,15 +133,21 @@ __device__ __forceinline__ void mma_rows_x_rowsT(float (&acc)[8][4], const float
         split_tf32(A[(r0 + g + 8) * ST + ks * 8 + t], ah[1], al[1]);
         split_tf32(A[(r0 + g) * ST + ks * 8 + t + 4], ah[2], al[2]);
         split_tf32(A[(r0 + g + 8) * ST + ks * 8 + t + 4], ah[3], al[3]);
+        // the three passes run over all eight column tiles before the next pass touches the same
+        // accumulator: eight independent MMAs between dependent ones (back-to-back dependent MMAs
+        // left the tensor pipe waiting on its own latency)
+        uint32_t bh[8][2], bl[8][2];
 #pragma unroll
         for (int nt = 0; nt < 8; ++nt) {
-            uint32_t bh[2], bl[2];
-            split_tf32(Bm[(nt * 8 + g) * ST + ks * 8 + t], bh[0], bl[0]);
-            split_tf32(Bm[(nt * 8 + g) * ST + ks * 8 + t + 4], bh[1], bl[1]);
-            mma_tf32_16x8x8(acc[nt], al, bh);
-            mma_tf32_16x8x8(acc[nt], ah, bl);
-            mma_tf32_16x8x8(acc[nt], ah, bh);
+            split_tf32(Bm[(nt * 8 + g) * ST + ks * 8 + t], bh[nt][0], bl[nt][0]);
+            split_tf32(Bm[(nt * 8 + g) * ST + ks * 8 + t + 4], bh[nt][1], bl[nt][1]);
         }
+#pragma unroll
+        for (int nt = 0; nt < 8; ++nt) mma_tf32_16x8x8(acc[nt], al, bh[nt]);
+#pragma unroll
+        for (int nt = 0; nt < 8; ++nt) mma_tf32_16x8x8(acc[nt], ah, bl[nt]);
+#pragma unroll
+        for (int nt = 0; nt < 8; ++nt) mma_tf32_16x8x8(acc[nt], ah, bh[nt]);
     }
 }
 
@@ -146,21 +164,24 @@ __device__ __forceinline__ void mma_regs_x_rows(float (&out)[HD / 8][4], const f
 #pragma unroll
     for (int kb = 0; kb < 8; ++kb) {
         uint32_t a[4], al[4];
-        split_tf32(P[kb][0], a[0], al[0]);
-        split_tf32(P[kb][2], a[1], al[1]);
-        split_tf32(P[kb][1], a[2], al[2]);
-        split_tf32(P[kb][3], a[3], al[3]);
+        prep_tf32<X3>(P[kb][0], a[0], al[0]);
+        prep_tf32<X3>(P[kb][2], a[1], al[1]);
+        prep_tf32<X3>(P[kb][1], a[2], al[2]);
+        prep_tf32<X3>(P[kb][3], a[3], al[3]);
+        uint32_t b[HD / 8][2], bl[HD / 8][2];
 #pragma unroll
         for (int n = 0; n < HD / 8; ++n) {
-            uint32_t b[2], bl[2];
-            split_tf32(Bm[(kb * 8 + 2 * t) * ST + n * 8 + g], b[0], bl[0]);
-            split_tf32(Bm[(kb * 8 + 2 * t + 1) * ST + n * 8 + g], b[1], bl[1]);
-            if (X3) {
-                mma_tf32_16x8x8(out[n], al, b);
-                mma_tf32_16x8x8(out[n], a, bl);
-            }
-            mma_tf32_16x8x8(out[n], a, b);
+            prep_tf32<X3>(Bm[(kb * 8 + 2 * t) * ST + n * 8 + g], b[n][0], bl[n][0]);
+            prep_tf32<X3>(Bm[(kb * 8 + 2 * t + 1) * ST + n * 8 + g], b[n][1], bl[n][1]);
         }
+        if (X3) {
+#pragma unroll
+            for (int n = 0; n < HD / 8; ++n) mma_tf32_16x8x8(out[n], al, b[n]);
+#pragma unroll
+            for (int n = 0; n < HD / 8; ++n) mma_tf32_16x8x8(out[n], a, bl[n]);
+        }
+#pragma unroll
+        for (int n = 0; n < HD / 8; ++n) mma_tf32_16x8x8(out[n], a, b[n]);
     }
 }
 
@@ -420,21 +441,36 @@ __global__ void __launch_bounds__(ATT_THREADS, HD <= 32 ? 3 : 1) attn_bwd_kernel
 #pragma unroll
             for (int kb = 0; kb < 8; ++kb) {
                 uint32_t a[4], al[4];
-                split_tf32(PD[(kb * 8 + t) * PS_STRIDE + r0 + g], a[0], al[0]);
-                split_tf32(PD[(kb * 8 + t) * PS_STRIDE + r0 + g + 8], a[1], al[1]);
-                split_tf32(PD[(kb * 8 + t + 4) * PS_STRIDE + r0 + g], a[2], al[2]);
-                split_tf32(PD[(kb * 8 + t + 4) * PS_STRIDE + r0 + g + 8], a[3], al[3]);
+                // which == 0: P was rounded to TF32 when it was formed (pm), dO is rounded here
+                const float pa0 = PD[(kb * 8 + t) * PS_STRIDE + r0 + g], pa1 = PD[(kb * 8 + t) * PS_STRIDE + r0 + g + 8];
+                const float pa2 = PD[(kb * 8 + t + 4) * PS_STRIDE + r0 + g];
+                const float pa3 = PD[(kb * 8 + t + 4) * PS_STRIDE + r0 + g + 8];
+                if (which == 1) {
+                    split_tf32(pa0, a[0], al[0]); split_tf32(pa1, a[1], al[1]);
+                    split_tf32(pa2, a[2], al[2]); split_tf32(pa3, a[3], al[3]);
+                } else {
+                    a[0] = __float_as_uint(pa0); a[1] = __float_as_uint(pa1);
+                    a[2] = __float_as_uint(pa2); a[3] = __float_as_uint(pa3);
+                }
+                uint32_t bb[HD / 8][2], bl[HD / 8][2];
 #pragma unroll
                 for (int n = 0; n < HD / 8; ++n) {
-                    uint32_t bb[2], bl[2];
-                    split_tf32(Bm[(kb * 8 + t) * ST + n * 8 + g], bb[0], bl[0]);
-                    split_tf32(Bm[(kb * 8 + t + 4) * ST + n * 8 + g], bb[1], bl[1]);
-                    if (which == 1) {  // dK: error-compensated
-                        mma_tf32_16x8x8(acc[n], al, bb);
-                        mma_tf32_16x8x8(acc[n], a, bl);
+                    if (which == 1) {
+                        split_tf32(Bm[(kb * 8 + t) * ST + n * 8 + g], bb[n][0], bl[n][0]);
+                        split_tf32(Bm[(kb * 8 + t + 4) * ST + n * 8 + g], bb[n][1], bl[n][1]);
+                    } else {
+                        bb[n][0] = f2tf32(Bm[(kb * 8 + t) * ST + n * 8 + g]);
+                        bb[n][1] = f2tf32(Bm[(kb * 8 + t + 4) * ST + n * 8 + g]);
                     }
-                    mma_tf32_16x8x8(acc[n], a, bb);
                 }
+                if (which == 1) {  // dK: error-compensated
+#pragma unroll
+                    for (int n = 0; n < HD / 8; ++n) mma_tf32_16x8x8(acc[n], al, bb[n]);
+#pragma unroll
+                    for (int n = 0; n < HD / 8; ++n) mma_tf32_16x8x8(acc[n], a, bl[n]);
+                }
+#pragma unroll
+                for (int n = 0; n < HD / 8; ++n) mma_tf32_16x8x8(acc[n], a, bb[n]);
             }
             const int off = which == 0 ? p.v_off : p.k_off;
 #pragma unroll
