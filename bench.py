@@ -273,7 +273,7 @@ def run_ours(args):
                            "families": {k: {"ms": v[0], "gbs": v[1] / v[0] / 1e6 if v[0] else 0,
                                             "tflops": v[2] / v[0] / 1e9 if v[0] else 0, "launches": v[3]}
                                         for k, v in sorted(fam.items(), key=lambda kv: -kv[1][0])},
-                           "kernels": table[:60]}, f, indent=1)
+                           "kernels": table}, f, indent=1)
 
     cpu_baseline = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:

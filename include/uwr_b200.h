@@ -227,6 +227,25 @@ size_t uwr_ffl_workspace_bytes(int planes, int S);
 int uwr_ffl_loss(const float* pred, const float* truth, float* out, float* grad, float* workspace,
                  int planes, int S, uwr_stream_t stream);
 
+/* ---- frequency-domain mixing (shared-memory FFT passes, csrc/fft.cu) ------------------------
+ * Token tensors are (B, H, W, C) fp32, C contiguous; H, W (and C for *_lc_*) powers of two <= 1024.
+ * uwr_dft_hw_real: y = scale * Re(FFT2 over (H, W))(x)  -- FDFP, src/model/block.py:532-556
+ *                  (fftn(...).real forward: scale 1; ifftn(...).real of a real tensor: scale 1/(H*W);
+ *                  the map is symmetric, so the backward of either is the same call on the cotangent).
+ * uwr_dft_lc_real: y = scale * Re(FFT2 over (L = H*W tokens, C channels))(x) -- EncoderBlock,
+ *                  src/model/model.py:72-88 (forward scale 1, inverse scale 1/(L*C)).
+ * uwr_fft2_hw:     complex FFT2 over (H, W); in_complex 0/1, inverse 0/1 (conjugate kernel; fold the
+ *                  1/(H*W) into scale); out is interleaved complex (B, H, W, C, 2) --
+ *                  SpectralTransformer.UpSample, src/Models/SpectralTransformer.py:174-188.
+ * workspace: uwr_dft_workspace_bytes(B, H, W, C).  x and y may not alias the workspace. */
+size_t uwr_dft_workspace_bytes(int B, int H, int W, int C);
+int uwr_dft_hw_real(const float* x, float* y, float* workspace, int B, int H, int W, int C,
+                    float scale, uwr_stream_t stream);
+int uwr_dft_lc_real(const float* x, float* y, float* workspace, int B, int H, int W, int C,
+                    float scale, uwr_stream_t stream);
+int uwr_fft2_hw(const float* in, float* out, float* workspace, int B, int H, int W, int C,
+                int in_complex, int inverse, float scale, uwr_stream_t stream);
+
 /* ---- optimizer step (ModelTrainer.py:87-88,197-204): clip_grad_norm_(1.0) + Adam/AdamW -----
  * tensor tables are device arrays of pointers; `offsets` (n_tensors+1 entries, offsets[0]=0) is
  * the running element count of the virtual concatenation.

@@ -104,6 +104,10 @@ SIGNATURES = {
     "uwr_pixel_loss": (c_int, [c_fp, c_fp, c_fp, c_fp, c_fp, c_int, c_int, c_int, c_int, c_int, c_int, c_stream]),
     "uwr_ffl_workspace_bytes": (c_sz, [c_int, c_int]),
     "uwr_ffl_loss": (c_int, [c_fp, c_fp, c_fp, c_fp, c_fp, c_int, c_int, c_stream]),
+    "uwr_dft_workspace_bytes": (c_sz, [c_int, c_int, c_int, c_int]),
+    "uwr_dft_hw_real": (c_int, [c_fp, c_fp, c_fp, c_int, c_int, c_int, c_int, c_f, c_stream]),
+    "uwr_dft_lc_real": (c_int, [c_fp, c_fp, c_fp, c_int, c_int, c_int, c_int, c_f, c_stream]),
+    "uwr_fft2_hw": (c_int, [c_fp, c_fp, c_fp, c_int, c_int, c_int, c_int, c_int, c_int, c_f, c_stream]),
     "uwr_grad_norm": (c_int, [c_fp, c_fp, c_int, c_ll, c_f, c_f, c_fp, c_fp, c_stream]),
     "uwr_adam_step": (c_int, [c_fp, c_fp, c_fp, c_fp, c_fp, c_int, c_ll, c_fp, c_f, c_f, c_f, c_f, c_f, c_f,
                               c_int, c_int, c_fp, c_stream]),

@@ -214,3 +214,23 @@ class GramFn(torch.autograd.Function):
         dx = ops._empty((L, n), x)
         ops.gemm(x, S, dx, L, n, n, lda=x.stride(0), ldb=n, ldc=n, b_nk=False)
         return dx
+
+
+class DftRealFn(torch.autograd.Function):
+    """y = scale * Re(FFT2(x)) over the spatial axes ('hw', FDFP block.py:532-556) or over
+    (tokens, channels) ('lc', EncoderBlock model.py:72-88).  x -> Re(F x) is symmetric, so the
+    backward is the same kernel on the cotangent."""
+
+    @staticmethod
+    def forward(ctx, x, B, H, W, C, scale, axes):
+        ctx.args = (B, H, W, C, scale, axes)
+        return ops.dft_real(x, B, H, W, C, scale, axes).view(x.shape)
+
+    @staticmethod
+    def backward(ctx, dy):
+        B, H, W, C, scale, axes = ctx.args
+        return ops.dft_real(_c(dy), B, H, W, C, scale, axes).view(dy.shape), None, None, None, None, None, None
+
+
+def dft_real(x, B, H, W, C, scale, axes):
+    return DftRealFn.apply(x, B, H, W, C, scale, axes)

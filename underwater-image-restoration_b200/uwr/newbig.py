@@ -101,10 +101,11 @@ class FDFP(nn.Module):
         self.act = act_layer()
 
     def forward(self, x):  # (B, H, W, C) tokens
-        f = torch.fft.fftn(x, dim=(1, 2)).real
+        B, H, W, C = x.shape
+        f = fn.dft_real(x, B, H, W, C, 1.0, "hw")                      # Re(fftn over (H, W))
         f = fn.linear(f, self.conv1.weight.flatten(1), self.conv1.bias)
         f = fn.linear(F.gelu(f), self.conv2.weight.flatten(1), self.conv2.bias)
-        return torch.fft.ifftn(f, dim=(1, 2)).real
+        return fn.dft_real(f, B, H, W, C, 1.0 / (H * W), "hw")         # Re(ifftn) of a real tensor
 
 
 class MDASSA(nn.Module):
@@ -154,9 +155,9 @@ class EncoderBlock(nn.Module):
         B, L, C = x.shape
         H = W = int(math.sqrt(L))
         a = self.mlp.block_forward(x, self.norm1, None, H, W, residual=False)
-        f = torch.fft.fftn(a, dim=(-2, -1)).real
+        f = fn.dft_real(a, B, H, W, C, 1.0, "lc")                      # Re(fftn over (L, C))
         f = self.freq_mlp.block_forward(f, None, None, H, W, residual=False)
-        f = torch.fft.ifftn(f, dim=(-2, -1)).real
+        f = fn.dft_real(f, B, H, W, C, 1.0 / (L * C), "lc")            # Re(ifftn) of a real tensor
         # the reference draws drop_path2 (frequency branch) first, then drop_path (model.py:90)
         s2 = self.drop_path2.scale(B, x.device) if isinstance(self.drop_path2, DropPath) else None
         s1 = self.drop_path.scale(B, x.device) if isinstance(self.drop_path, DropPath) else None

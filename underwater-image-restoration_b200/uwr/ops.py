@@ -6,6 +6,8 @@ is an error (the product path has no fallback).
 """
 import ctypes as C
 
+import math
+
 import torch
 
 from . import _lib
@@ -448,6 +450,31 @@ def colsum(x2d, cols):
 
 # --------------------------------------------------------------------------------------------
 LOSS_KINDS = {"L1": 0, "L1withColor": 1, "charbonnier": 2, "L2": 3}
+
+
+def dft_real(x, B, H, W, C, scale, axes):
+    """scale * Re(FFT2(x)) of a real (B, H, W, C) token tensor over axes 'hw' (spatial) or 'lc'
+    (tokens x channels); symmetric linear map => also its own backward (csrc/fft.cu)."""
+    x = x.contiguous()
+    y = torch.empty_like(x)
+    ws = _ws(fn["uwr_dft_workspace_bytes"](B, H, W, C), x)
+    name = "uwr_dft_hw_real" if axes == "hw" else "uwr_dft_lc_real"
+    n = x.numel()
+    _run(name, f"B{B} H{H} W{W} C{C}", 4 * n * (10 if axes == "lc" else 6), 5.0 * n * math.log2(H * W * (C if axes == "lc" else 1)),
+         _ptr(x), _ptr(y), _ptr(ws), B, H, W, C, float(scale))
+    return y
+
+
+def fft2_hw(x, B, H, W, C, in_complex, inverse, scale=1.0):
+    """complex FFT2 over (H, W) of (B, H, W, C) [real] or (B, H, W, C, 2) [interleaved complex];
+    returns (B, H, W, C, 2) float32 (view_as_complex-compatible)."""
+    x = x.contiguous()
+    out = torch.empty((B, H, W, C, 2), device=x.device, dtype=torch.float32)
+    ws = _ws(fn["uwr_dft_workspace_bytes"](B, H, W, C), x)
+    n = B * H * W * C
+    _run("uwr_fft2_hw", f"B{B} H{H} W{W} C{C} c{int(in_complex)} i{int(inverse)}", 4 * n * (7 if not in_complex else 8),
+         5.0 * n * math.log2(H * W), _ptr(x), _ptr(out), _ptr(ws), B, H, W, C, int(in_complex), int(inverse), float(scale))
+    return out
 
 
 def pixel_loss(pred, truth, kind, batch_divisor=None, want_grad=True):
