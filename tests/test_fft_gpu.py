@@ -57,7 +57,7 @@ def test_dft_real_autograd(axes):
     assert rel_l2(x.grad, xd.grad) < TOL
 
 
-@pytest.mark.parametrize("B,H,W,C", [(2, 32, 32, 128), (1, 64, 64, 64), (1, 128, 128, 32)])
+@pytest.mark.parametrize("B,H,W,C", [(2, 32, 32, 128), (1, 64, 64, 64), (1, 128, 128, 32), (2, 12, 24, 16), (1, 8, 12, 128)])
 def test_fft2_hw_complex_roundtrip(B, H, W, C):
     from uwr import ops
     x = _r(B, H, W, C, seed=5)

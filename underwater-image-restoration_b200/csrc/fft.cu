@@ -68,17 +68,27 @@ struct PassParams {
 // grid = (channel groups, NO, B)
 __global__ void __launch_bounds__(FFT_WARPS * 32) fft_pass_kernel(const PassParams p) {
     extern __shared__ __align__(16) float2 fsm[];
-    float2* tw = fsm;               // N/2 twiddles
-    float2* tile = fsm + p.N / 2;   // [FFT_CT][N + 1]
+    float2* tw = fsm;           // N twiddles (the radix-2 path uses the first N/2)
+    float2* tile = fsm + p.N;   // [FFT_CT][N + 1] (+ a second tile for the direct-DFT path)
     const int N = p.N, pitch = N + 1;
+    const bool radix2 = p.log2N >= 0;  // otherwise: N is not a power of two -> direct O(N^2) DFT per line
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    for (int k = threadIdx.x; k < N / 2; k += blockDim.x) {
+    for (int k = threadIdx.x; k < N; k += blockDim.x) {
         float sn, cs;
         sincospif(-2.0f * (float)k / (float)N, &sn, &cs);
         tw[k] = make_float2(cs, sn);
     }
     const int c0 = blockIdx.x * FFT_CT, o = blockIdx.y, b = blockIdx.z;
     const int nc = min(FFT_CT, p.C - c0);
+    // four-step twiddles of this tile (fixed o): tw4[k] = exp(-/+ 2 pi i * o * k / tw_L), once per CTA
+    float2* tw4 = tile + (radix2 ? 1 : 2) * FFT_CT * pitch;
+    if (p.tw_L)
+        for (int k = threadIdx.x; k < N; k += blockDim.x) {
+            const unsigned m = ((unsigned)o * (unsigned)k) & (unsigned)(p.tw_L - 1);  // tw_L is a power of two
+            float sn, cs;
+            sincospif((p.inverse ? 2.0f : -2.0f) * (float)m / (float)p.tw_L, &sn, &cs);
+            tw4[k] = make_float2(cs, sn);
+        }
     const long long ibase = (long long)b * p.in_sB + (long long)o * p.in_sO + c0;
     for (int idx = threadIdx.x; idx < N * FFT_CT; idx += blockDim.x) {
         const int n = idx >> 5, c = idx & 31;
@@ -88,22 +98,39 @@ __global__ void __launch_bounds__(FFT_WARPS * 32) fft_pass_kernel(const PassPara
             if (p.in_complex) v = reinterpret_cast<const float2*>(p.in)[a];
             else v.x = p.in[a];
         }
-        tile[c * pitch + (__brev((unsigned)n) >> (32 - p.log2N))] = v;
+        tile[c * pitch + (radix2 ? (int)(__brev((unsigned)n) >> (32 - p.log2N)) : n)] = v;
     }
     __syncthreads();
-    for (int c = warp; c < nc; c += FFT_WARPS) warp_fft_r2(tile + c * pitch, tw, N, p.log2N, p.inverse != 0, lane);
+    if (radix2) {
+        for (int c = warp; c < nc; c += FFT_WARPS) warp_fft_r2(tile + c * pitch, tw, N, p.log2N, p.inverse != 0, lane);
+    } else {
+        float2* res = tile + FFT_CT * pitch;
+        for (int c = warp; c < nc; c += FFT_WARPS) {
+            const float2* x = tile + c * pitch;
+            for (int k = lane; k < N; k += 32) {
+                float2 acc = make_float2(0.f, 0.f);
+                int m = 0;  // (n * k) mod N
+                for (int n = 0; n < N; ++n) {
+                    float2 w = tw[m];
+                    if (p.inverse) w.y = -w.y;
+                    const float2 t = cmulf(w, x[n]);
+                    acc.x += t.x;
+                    acc.y += t.y;
+                    m += k;
+                    if (m >= N) m -= N;
+                }
+                res[c * pitch + k] = acc;
+            }
+        }
+        tile = res;
+    }
     __syncthreads();
     const long long obase = (long long)b * p.out_sB + (long long)o * p.out_sO + c0;
     for (int idx = threadIdx.x; idx < N * FFT_CT; idx += blockDim.x) {
         const int k = idx >> 5, c = idx & 31;
         if (c >= nc) continue;
         float2 v = tile[c * pitch + k];
-        if (p.tw_L) {
-            const unsigned m = ((unsigned)o * (unsigned)k) & (unsigned)(p.tw_L - 1);  // tw_L is a power of two
-            float sn, cs;
-            sincospif((p.inverse ? 2.0f : -2.0f) * (float)m / (float)p.tw_L, &sn, &cs);
-            v = cmulf(v, make_float2(cs, sn));
-        }
+        if (p.tw_L) v = cmulf(v, tw4[k]);
         const long long a = obase + (long long)k * p.out_sN + c;
         if (p.out_real) p.out[a] = v.x * p.scale;
         else reinterpret_cast<float2*>(p.out)[a] = make_float2(v.x * p.scale, v.y * p.scale);
@@ -149,10 +176,11 @@ int ilog2i(int v) {
 bool pow2(int v) { return v > 0 && (v & (v - 1)) == 0; }
 
 int launch_pass(PassParams& p, int B, cudaStream_t stream) {
-    UWR_REQUIRE(pow2(p.N) && p.N >= 2 && p.N <= 1024, "fft pass: length %d must be a power of two in [2, 1024]", p.N);
+    UWR_REQUIRE(p.N >= 1 && (pow2(p.N) ? p.N <= 1024 : p.N <= 384),
+                "fft pass: length %d unsupported (powers of two <= 1024, other lengths <= 384)", p.N);
     UWR_REQUIRE(B > 0 && B <= 65535 && p.NO > 0 && p.NO <= 65535, "fft pass: bad batch / extent");
-    p.log2N = ilog2i(p.N);
-    const int smem = (p.N / 2 + FFT_CT * (p.N + 1)) * (int)sizeof(float2);
+    p.log2N = pow2(p.N) ? ilog2i(p.N) : -1;
+    const int smem = (2 * p.N + (pow2(p.N) ? 1 : 2) * FFT_CT * (p.N + 1)) * (int)sizeof(float2);
     static int configured = 0;
     if (smem > 48 * 1024 && smem > configured) {
         UWR_CUDA(cudaFuncSetAttribute(fft_pass_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));

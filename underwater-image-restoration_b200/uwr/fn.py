@@ -234,3 +234,23 @@ class DftRealFn(torch.autograd.Function):
 
 def dft_real(x, B, H, W, C, scale, axes):
     return DftRealFn.apply(x, B, H, W, C, scale, axes)
+
+
+class Fft2Fn(torch.autograd.Function):
+    """Complex FFT2 over the spatial axes of a (B, H, W, C) real or (B, H, W, C, 2) interleaved-complex
+    tensor on the shared-memory FFT passes (csrc/fft.cu); returns (B, H, W, C, 2).
+    y = scale * F x (forward) or scale * conj(F) x (inverse); the adjoint of one is the other, and for
+    a real input the cotangent is the real part."""
+
+    @staticmethod
+    def forward(ctx, x, B, H, W, C, in_complex, inverse, scale):
+        ctx.args = (B, H, W, C, in_complex, inverse, scale)
+        return ops.fft2_hw(x, B, H, W, C, in_complex, inverse, scale)
+
+    @staticmethod
+    def backward(ctx, dy):
+        B, H, W, C, in_complex, inverse, scale = ctx.args
+        dx = ops.fft2_hw(_c(dy), B, H, W, C, True, not inverse, scale)
+        if not in_complex:
+            dx = dx[..., 0].contiguous()
+        return dx, None, None, None, None, None, None, None

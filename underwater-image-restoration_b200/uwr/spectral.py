@@ -5,8 +5,9 @@ Native (uwr kernels): LayerNorm over channels (no NCHW<->NHWC round trips), ever
 (tensor-core GEMM on tokens), the depthwise 3x3 convs of MDTA / GDFN (plain mode of the dwconv kernel),
 MDTA's channel attention as two GEMMs per image (Gram matrix of [q|k] over the tokens -> tiny softmax
 -> block-diagonal apply), the dense 3x3 convs with Cin % 4 == 0 (im2col + GEMM).
-Still ATen in this round: the FFT amplitude/phase up-sampler (torch.fft, abs/angle/
-cos/sin), PixelShuffle/Unshuffle, the GELU gate product of GDFN, the 3-channel first / last 3x3 conv.
+The FFT amplitude/phase up-sampler runs its fft2 / ifft2 (and their adjoints) on the shared-memory FFT
+passes of csrc/fft.cu; the (2, 2)-tiled inverse transform is an H x W one scattered to the even pixels.
+Still ATen in this round: abs/angle/cos/sin of the up-sampler, PixelShuffle/Unshuffle, the GELU gate product of GDFN, the 3-channel first / last 3x3 conv.
 Only the live data path is executed: MDTA's FFT branch, `attnf`, q1X1_*, ups_4, ups1, ups2, output1
 are dead in value and gradient in the reference; their parameters are kept.
 """
@@ -136,12 +137,26 @@ class UpSample(nn.Module):
                                       nn.Conv2d(channels, channels, 1, 1, 0))
         self.post = nn.Conv2d(channels, channels // 2 if channel_red else channels, 1, 1, 0)
 
-    def forward(self, img):
-        f = torch.fft.fft2(img)
-        Mag = torch.tile(self.amp_fuse(torch.abs(f)), (2, 2))
-        Pha = torch.tile(self.pha_fuse(torch.angle(f)), (2, 2))
-        out = torch.abs(torch.fft.ifft2(torch.complex(Mag * torch.cos(Pha), Mag * torch.sin(Pha))))
-        return self.post(out)
+    @staticmethod
+    def _mlp(seq, x2d):   # Conv1x1 -> LeakyReLU(0.1) -> Conv1x1 on tokens (tensor-core GEMMs)
+        h = F.leaky_relu(fn.linear(x2d, _w2(seq[0]), seq[0].bias), 0.1)
+        return fn.linear(h, _w2(seq[2]), seq[2].bias)
+
+    def forward(self, t, B, H, W):   # tokens (B*H*W, C) -> tokens (B*2H*2W, C_out)
+        C = t.shape[1]
+        # fft2 on the shared-memory FFT passes (csrc/fft.cu), NHWC, no NCHW round trip
+        f = torch.view_as_complex(fn.Fft2Fn.apply(t.view(B, H, W, C), B, H, W, C, False, False, 1.0))
+        mag = self._mlp(self.amp_fuse, torch.abs(f).view(B * H * W, C))
+        pha = self._mlp(self.pha_fuse, torch.angle(f).view(B * H * W, C))
+        z = torch.stack([mag * torch.cos(pha), mag * torch.sin(pha)], dim=-1).view(B, H, W, C, 2)
+        # ifft2 of the (2, 2)-tiled spectrum at 2H x 2W == ifft2 of the spectrum at H x W written to the even
+        # pixels, exact zeros elsewhere: a quarter of the transform work and no tile()
+        small = torch.abs(torch.view_as_complex(fn.Fft2Fn.apply(z, B, H, W, C, True, True, 1.0 / (H * W))))
+        y = fn.linear(small.view(B * H * W, C), _w2(self.post), self.post.bias)          # post(|z|) at even pixels
+        Co = y.shape[1]
+        out = self.post.bias.view(1, 1, 1, Co).expand(B, 2 * H, 2 * W, Co).contiguous()   # post(0) = bias elsewhere
+        out[:, ::2, ::2, :] = y.view(B, H, W, Co)
+        return out.view(B * 4 * H * W, Co)
 
 
 class UpSample1(nn.Module):
@@ -162,8 +177,8 @@ class UpS(nn.Module):
         self.reduce = nn.Conv2d(channels, channels // 2, kernel_size=1, bias=False)
 
     def forward(self, t, B, H, W):   # tokens at (H, W) -> tokens at (2H, 2W)
-        cat = torch.cat([self.Fups(_to_img(t, B, H, W)), self.Sups(t, B, H, W)], dim=1)
-        return fn.linear(_to_tok(cat), _w2(self.reduce))
+        cat = torch.cat([self.Fups(t, B, H, W), _to_tok(self.Sups(t, B, H, W))], dim=1)
+        return fn.linear(cat, _w2(self.reduce))
 
 
 class SpectralTransformer(nn.Module):
