@@ -477,7 +477,7 @@ __global__ void pixel_scatter_2x2_kernel(const float* __restrict__ g, const floa
 }
 
 __global__ void pixel_gather_2x2_kernel(const float* __restrict__ dout, long long ld_dout, float* __restrict__ dg,
-                                        int B, int H, int W, int Cout) {
+                                        int B, int H, int W, int Cout, int rnd) {
     const long long total = (long long)B * H * W * Cout;
     for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total;
          i += (long long)gridDim.x * blockDim.x) {
@@ -493,6 +493,7 @@ __global__ void pixel_gather_2x2_kernel(const float* __restrict__ dout, long lon
         v.y = dout[o00 + ld_dout];
         v.z = dout[o00 + 2 * W * ld_dout];
         v.w = dout[o00 + 2 * W * ld_dout + ld_dout];
+        if (rnd) v = make_float4(tf32_round(v.x), tf32_round(v.y), tf32_round(v.z), tf32_round(v.w));  // GEMM operand
         reinterpret_cast<float4*>(dg)[i] = v;
     }
 }
@@ -725,7 +726,8 @@ extern "C" int uwr_pixel_gather_2x2(const float* dout, long long ld_dout, float*
     cudaStream_t stream = (cudaStream_t)stream_;
     UWR_REQUIRE(dout && dg, "uwr_pixel_gather_2x2: null pointer");
     const long long total = (long long)B * H * W * Cout;
-    pixel_gather_2x2_kernel<<<ew_blocks(total, 256), 256, 0, stream>>>(dout, ld_dout, dg, B, H, W, Cout);
+    pixel_gather_2x2_kernel<<<ew_blocks(total, 256), 256, 0, stream>>>(dout, ld_dout, dg, B, H, W, Cout,
+                                                                       uwr_round_outputs());
     UWR_CHECK_LAUNCH("pixel_gather_2x2_kernel");
     return 0;
 }

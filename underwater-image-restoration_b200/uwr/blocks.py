@@ -71,8 +71,9 @@ class DownsampleFn(torch.autograd.Function):
         # (Cout, Cin, 4, 4) -> (Cout, 4, 4, Cin): K index = (ky, kx, ci) matches the im2col rows
         wmat = weight.permute(0, 2, 3, 1).reshape(Cout, 16 * Cc)
         col = ops.im2col_4x4s2(x.view(B * L, Cc), B, H, W, Cc)  # TF32-rounded at the store in tf32 mode
-        y = ops.linear(col, ops.scale_round(wmat, 16 * Cc), bias, t5=True)
-        ctx.save_for_backward(x, wmat)
+        wmat_r = ops.scale_round(wmat, 16 * Cc)
+        y = ops.linear(col, wmat_r, bias, t5=True)
+        ctx.save_for_backward(x, wmat_r)
         ctx.dims = (B, H, W, Cc, Cout)
         return y.view(B, L // 4, Cout)
 
@@ -83,9 +84,12 @@ class DownsampleFn(torch.autograd.Function):
         B, H, W, Cc, Cout = ctx.dims
         dy2 = _c(dy).view(-1, Cout)
         col = ops.im2col_4x4s2(x.view(-1, Cc), B, H, W, Cc)  # recomputed, not saved (4x the input)
-        dwmat, dbias = ops.linear_wgrad(dy2, col)
+        fast = ops.fast_path()
+        if fast:  # tcgen05 path: both operands rounded to TF32 (col and wmat already are)
+            dy2 = ops.scale_round(dy2, Cout)
+        dwmat, dbias = ops.linear_wgrad(dy2, col, t5=fast)
         del col
-        dcol = ops.linear_dgrad(dy2, wmat)
+        dcol = ops.linear_dgrad(dy2, wmat, t5=fast)
         dx = ops.col2im_4x4s2(dcol, B, H, W, Cc)
         dweight = dwmat.view(Cout, 4, 4, Cc).permute(0, 3, 1, 2).contiguous()
         return dx.view(B, H * W, Cc), dweight, dbias, None, None
@@ -102,10 +106,13 @@ class UpsampleCatFn(torch.autograd.Function):
         B, L, Cin = x.shape
         Cout = weight.shape[1]
         Cs = skip.shape[2]
-        wmat = weight.view(Cin, Cout * 4)  # stored [K=Cin][N=(co,dy,dx)]
+        fast = ops.fast_path()
+        wmat = (ops.rounded_weight(weight) if fast else weight).view(Cin, Cout * 4)  # stored [K=Cin][N=(co,dy,dx)]
+        if fast:  # tcgen05 path: TF32-rounded copy of the input, also what the weight gradient reads
+            x = ops.scale_round(x.view(B * L, Cin), Cin).view(B, L, Cin)
         g = ops._empty((B * L, Cout * 4), x)
         ops.gemm(x.view(B * L, Cin), wmat, g, B * L, Cout * 4, Cin, lda=Cin, ldb=Cout * 4, ldc=Cout * 4,
-                 b_nk=False)
+                 b_nk=False, t5=fast)
         out = ops._empty((B, 4 * L, Cout + Cs), x)
         out2 = out.view(B * 4 * L, Cout + Cs)
         ops.pixel_scatter_2x2(g, bias, out2, B, H, W, Cout)
@@ -125,14 +132,15 @@ class UpsampleCatFn(torch.autograd.Function):
         ops.copy2d(d2[:, Cout:], dskip.view(B * 4 * L, Cs), Cs)
         dbias = ops.colsum(d2, Cout)
         dg = ops.pixel_gather_2x2(d2, B, H, W, Cout)
-        wmat = weight.view(Cin, Cout * 4)
+        fast = ops.fast_path()  # x (saved) and dg are TF32-rounded in fast mode
+        wmat = (ops.rounded_weight(weight) if fast else weight).view(Cin, Cout * 4)
         # dx[M,Cin] = dg[M,4Cout] wmat^T : B stored [N=Cin][K=4Cout]
         dx = ops._empty((B * L, Cin), x)
-        ops.gemm(dg, wmat, dx, B * L, Cin, Cout * 4, lda=Cout * 4, ldb=Cout * 4, ldc=Cin, b_nk=True)
+        ops.gemm(dg, wmat, dx, B * L, Cin, Cout * 4, lda=Cout * 4, ldb=Cout * 4, ldc=Cin, b_nk=True, t5=fast)
         # dW[Cin,4Cout] = x^T dg
         dwmat = ops._empty((Cin, Cout * 4), x)
         ops.gemm(x.view(B * L, Cin), dg, dwmat, Cin, Cout * 4, B * L, lda=Cin, ldb=Cout * 4, ldc=Cout * 4,
-                 a_km=True, b_nk=False)
+                 a_km=True, b_nk=False, t5=fast)
         return dx.view(B, L, Cin), dwmat.view_as(weight), dbias, dskip, None, None
 
 

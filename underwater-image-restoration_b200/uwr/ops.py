@@ -234,8 +234,8 @@ def rounded_weight(w):
     if ent is None or ent[0] != ver:
         buf = ent[1] if ent is not None and ent[1].shape == w.shape and ent[1].device == w.device else torch.empty_like(w)
         wd = w.detach()
-        scale_round(wd.reshape(-1, wd.shape[-1]) if wd.dim() > 1 else wd.reshape(1, -1), wd.shape[-1],
-                    out=buf.view(-1, wd.shape[-1]) if wd.dim() > 1 else buf.view(1, -1))
+        w2 = wd.reshape(wd.shape[0], -1) if wd.dim() > 1 else wd.reshape(1, -1)   # conv weights: (C0, rest)
+        scale_round(w2, w2.shape[1], out=buf.view(w2.shape))
         w._uwr_rounded = ent = (ver, buf)
     return ent[1]
 
