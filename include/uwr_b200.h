@@ -214,7 +214,8 @@ int uwr_colsum(const float* x, long long ld, float* out, float* workspace, long 
 
 /* ---- losses (LossFunction.getloss, src/Losses/losses.py:54-160) ---------------------------
  * kind: 0 "L1" (55-57), 1 "L1withColor" (58-66 + luminanceLoss.py:5-21), 2 "charbonnier"
- * (80-81,189-193), 3 "L2" (76-78).  out[0] = loss, grad = dLoss/dpred (NULL to skip).
+ * (80-81,189-193), 3 "L2" (76-78), 4 mean((clamp01(p)-clamp01(t))^2) = the MSE inside torchPSNR
+ * (ModelTrainer.py:17-21; grad must be NULL).  out[0] = loss, grad = dLoss/dpred (NULL to skip).
  * `batch_divisor` is the B used in the reference's "/ (B*C)" (pass the GLOBAL batch under
  * data parallelism).  workspace >= 4*1024 floats.
  */

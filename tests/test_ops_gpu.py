@@ -99,7 +99,8 @@ def test_gemm_dgelu_epilogue(ops):
 
 
 # ------------------------------------------------------------------------------------- LayerNorm
-@pytest.mark.parametrize("rows,C", [(4096, 32), (1000, 64), (777, 128), (512, 256), (256, 512), (64, 48)])
+@pytest.mark.parametrize("rows,C", [(4096, 32), (1000, 64), (777, 128), (512, 256), (256, 512), (64, 48), (333, 16),
+                                     (65, 1024), (5, 32)])
 def test_layernorm(exact, rows, C):
     ops = exact
     x = _r(rows, C, seed=1) * 2 + 0.3
@@ -114,6 +115,16 @@ def test_layernorm(exact, rows, C):
     assert rel_l2(dx, xd.grad + dres.double()) < TOL_FP32
     assert rel_l2(dg, gd.grad) < TOL_FP32 * 5
     assert rel_l2(db, bd.grad) < TOL_FP32 * 5
+
+
+def test_torch_psnr_metric():
+    """uwr.metrics.torchPSNR (native clamped-MSE pass) vs the reference formula (ModelTrainer.py:17-21)."""
+    from uwr.metrics import torchPSNR
+    tar, prd = _r(3, 3, 64, 64, seed=7) * 0.5 + 0.5, _r(3, 3, 64, 64, seed=8) * 0.5 + 0.5   # values outside [0, 1] too
+    got = torchPSNR(tar, prd).item()
+    t, p = tar.double().clamp(0, 1), prd.double().clamp(0, 1)
+    ref = (20 * torch.log10(1.0 / torch.sqrt(((p - t) ** 2).mean()))).item()
+    assert abs(got - ref) < 1e-4
 
 
 # ------------------------------------------------------------------------------ window attention

@@ -1,17 +1,19 @@
 #!/bin/bash
-# One GPU-box pass: parity tests, headline bench, ncu launch list of the same bench command, one
-# `--set full` capture of the dominant kernel, and the config-2/3 step tables.  Outputs -> gpurun_out/.
+# One GPU-box pass: parity tests, headline bench, ncu launch list of the same bench command, `--set full`
+# captures of the dominant kernels, and the config-2/3 step tables.  Outputs -> gpurun_out/ (tag $1).
 set -x
-TAG=${1:-v8}
+TAG=${1:-v10}
 mkdir -p gpurun_out
 python -m pytest tests -m gpu -x -q > gpurun_out/pytest_gpu_$TAG.log 2>&1; tail -3 gpurun_out/pytest_gpu_$TAG.log
 python bench.py --steps 10 --warmup 3 --profile-out gpurun_out/prof_r1_b16_$TAG.json > gpurun_out/bench_$TAG.log 2>gpurun_out/bench_$TAG.err; cat gpurun_out/bench_$TAG.log
+python bench.py --impl reference --steps 3 --warmup 1 > gpurun_out/bench_ref_$TAG.log 2>&1; tail -1 gpurun_out/bench_ref_$TAG.log
+# launch list: the eager (non-graph) step issues the same kernels as the replayed graph
 python bench.py --steps 2 --warmup 3 --no-cpu-baseline --no-graph > gpurun_out/plain_launch_$TAG.log 2>&1 &&
 ncu --metrics gpu__time_duration.sum --clock-control none -s 3500 -c 1100 --csv --log-file gpurun_out/launches_$TAG.csv \
     python bench.py --steps 2 --warmup 3 --no-cpu-baseline --no-graph > gpurun_out/ncu_launch_$TAG.log 2>&1
-python tools/kernel_bench.py t5nt > gpurun_out/plain_t5nt_$TAG.log 2>&1 &&
-ncu --set full --clock-control none --import-source on -k regex:gemm_tcgen05 -s 2 -c 2 -o gpurun_out/ncu_t5nt_$TAG \
-    python tools/kernel_bench.py t5nt > gpurun_out/ncu_t5nt_$TAG.log 2>&1
-UWR_TORCHPROF=25 python tools/train_bench.py SpectralTransformer L1withColor 8 > gpurun_out/train_spectral_$TAG.log 2>&1; tail -30 gpurun_out/train_spectral_$TAG.log
-UWR_TORCHPROF=30 python tools/train_bench.py NewBigFRFNModel fflMix 16 > gpurun_out/train_newbig_$TAG.log 2>&1; tail -35 gpurun_out/train_newbig_$TAG.log
-UWR_TORCHPROF=25 python tools/train_bench.py AST L1 16 > gpurun_out/train_ast_$TAG.log 2>&1; tail -30 gpurun_out/train_ast_$TAG.log
+python tools/kernel_bench.py t5nn t5nt dwf dwb attnf attnb lnb > gpurun_out/plain_kb_$TAG.log 2>&1 &&
+ncu --set full --clock-control none --import-source on -k regex:"gemm_tcgen05|dwconv_|attn_|ln_" -c 40 -o gpurun_out/ncu_top_$TAG \
+    python tools/kernel_bench.py t5nn t5nt dwf dwb attnf attnb lnb > gpurun_out/ncu_kb_$TAG.log 2>&1
+cat gpurun_out/plain_kb_$TAG.log
+UWR_TORCHPROF=25 python tools/train_bench.py SpectralTransformer L1withColor 8 > gpurun_out/train_spectral_$TAG.log 2>&1; tail -28 gpurun_out/train_spectral_$TAG.log
+UWR_TORCHPROF=25 python tools/train_bench.py NewBigFRFNModel fflMix 16 > gpurun_out/train_newbig_$TAG.log 2>&1; tail -28 gpurun_out/train_newbig_$TAG.log

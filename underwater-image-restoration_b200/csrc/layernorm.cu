@@ -62,6 +62,74 @@ __global__ void __launch_bounds__(LN_WARPS * 32) ln_fwd_kernel(const float* __re
     }
 }
 
+// Vectorised forward for C = 4 * LPR * V4: LPR lanes share a row (128-bit accesses, 32 / LPR rows per
+// warp pass, RPI passes in flight), so a 128-byte row (C = 32) no longer costs a whole warp two
+// full-width reductions.
+template <int LPR, int V4>
+__global__ void __launch_bounds__(LN_WARPS * 32) ln_fwd_vec_kernel(const float* __restrict__ x,
+                                                                   const float* __restrict__ gamma,
+                                                                   const float* __restrict__ beta,
+                                                                   float* __restrict__ y, float* __restrict__ mean,
+                                                                   float* __restrict__ rstd, long long rows, float eps,
+                                                                   int rnd) {
+    constexpr int C = 4 * LPR * V4;
+    constexpr int RPW = 32 / LPR;               // rows per warp pass
+    constexpr int RPI = V4 <= 2 ? 4 : (V4 <= 4 ? 2 : 1);
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int sub = lane / LPR, l = lane % LPR;
+    float4 gm[V4], bt[V4];
+#pragma unroll
+    for (int i = 0; i < V4; ++i) {
+        gm[i] = *reinterpret_cast<const float4*>(gamma + (l + LPR * i) * 4);
+        bt[i] = *reinterpret_cast<const float4*>(beta + (l + LPR * i) * 4);
+    }
+    constexpr float invC = 1.0f / (float)C;
+    const long long stride = (long long)gridDim.x * LN_WARPS * RPW;
+    for (long long r0 = ((long long)blockIdx.x * LN_WARPS + warp) * RPW + sub; r0 < rows; r0 += stride * RPI) {
+        float4 v[RPI][V4];
+#pragma unroll
+        for (int k = 0; k < RPI; ++k) {
+            const long long r = r0 + k * stride;
+#pragma unroll
+            for (int i = 0; i < V4; ++i)
+                v[k][i] = r < rows ? *reinterpret_cast<const float4*>(x + r * C + (l + LPR * i) * 4)
+                                   : make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+#pragma unroll
+        for (int k = 0; k < RPI; ++k) {
+            const long long r = r0 + k * stride;
+            float s = 0.f;
+#pragma unroll
+            for (int i = 0; i < V4; ++i) s += (v[k][i].x + v[k][i].y) + (v[k][i].z + v[k][i].w);
+#pragma unroll
+            for (int o = LPR / 2; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+            const float mu = s * invC;
+            float q = 0.f;
+#pragma unroll
+            for (int i = 0; i < V4; ++i) {
+                const float a = v[k][i].x - mu, b = v[k][i].y - mu, c = v[k][i].z - mu, d = v[k][i].w - mu;
+                q += (a * a + b * b) + (c * c + d * d);
+            }
+#pragma unroll
+            for (int o = LPR / 2; o > 0; o >>= 1) q += __shfl_xor_sync(0xffffffffu, q, o);
+            const float rs = rsqrtf(q * invC + eps);
+            if (r < rows) {
+#pragma unroll
+                for (int i = 0; i < V4; ++i) {
+                    float4 o4 = make_float4((v[k][i].x - mu) * rs * gm[i].x + bt[i].x, (v[k][i].y - mu) * rs * gm[i].y + bt[i].y,
+                                            (v[k][i].z - mu) * rs * gm[i].z + bt[i].z, (v[k][i].w - mu) * rs * gm[i].w + bt[i].w);
+                    if (rnd) o4 = make_float4(tf32_round(o4.x), tf32_round(o4.y), tf32_round(o4.z), tf32_round(o4.w));
+                    *reinterpret_cast<float4*>(y + r * C + (l + LPR * i) * 4) = o4;
+                }
+                if (l == 0) {
+                    if (mean) mean[r] = mu;
+                    if (rstd) rstd[r] = rs;
+                }
+            }
+        }
+    }
+}
+
 template <int VPL>
 __global__ void __launch_bounds__(LN_WARPS * 32) ln_bwd_kernel(const float* __restrict__ dy,
                                                                const float* __restrict__ x,
@@ -190,6 +258,29 @@ extern "C" int uwr_layernorm_fwd(const float* x, const float* gamma, const float
     UWR_REQUIRE(C > 0 && C <= 1024, "uwr_layernorm_fwd: C=%d unsupported (1..1024)", C);
     if (rows == 0) return 0;
     const int blocks = ln_blocks(rows);
+#define LN_FWD_VEC(L, V)                                                                                         \
+    do {                                                                                                         \
+        long long b = (rows + LN_WARPS * (32 / L) - 1) / (LN_WARPS * (32 / L));                                  \
+        const long long cap = (long long)uwr_sm_count() * 8;                                                     \
+        if (b > cap) b = cap;                                                                                    \
+        ln_fwd_vec_kernel<L, V><<<(unsigned)b, LN_WARPS * 32, 0, stream>>>(x, gamma, beta, y, mean, rstd, rows,  \
+                                                                           eps, uwr_round_outputs());            \
+        UWR_CHECK_LAUNCH("ln_fwd_vec_kernel");                                                                   \
+        return 0;                                                                                                \
+    } while (0)
+    if ((((uintptr_t)x | (uintptr_t)y | (uintptr_t)gamma | (uintptr_t)beta) & 15) == 0) {
+        switch (C) {
+            case 16: LN_FWD_VEC(4, 1);
+            case 32: LN_FWD_VEC(8, 1);
+            case 64: LN_FWD_VEC(16, 1);
+            case 128: LN_FWD_VEC(32, 1);
+            case 256: LN_FWD_VEC(32, 2);
+            case 512: LN_FWD_VEC(32, 4);
+            case 1024: LN_FWD_VEC(32, 8);
+            default: break;
+        }
+    }
+#undef LN_FWD_VEC
     const int vpl = (C + 31) / 32;
 #define LN_FWD(V) ln_fwd_kernel<V><<<blocks, LN_WARPS * 32, 0, stream>>>(x, gamma, beta, y, mean, rstd, rows, C, eps, uwr_round_outputs())
     if (vpl <= 1) LN_FWD(1);

@@ -9,7 +9,7 @@ namespace {
 constexpr int LOSS_THREADS = 256;
 constexpr int LOSS_MAX_BLOCKS = 1024;
 
-// kind: 0 L1, 1 L1withColor, 2 charbonnier, 3 L2
+// kind: 0 L1, 1 L1withColor, 2 charbonnier, 3 L2, 4 mean((clamp01(p) - clamp01(t))^2) (torchPSNR, no gradient)
 __global__ void __launch_bounds__(LOSS_THREADS) pixel_loss_kernel(const float* __restrict__ pred,
                                                                   const float* __restrict__ truth,
                                                                   float* __restrict__ grad,
@@ -44,7 +44,9 @@ __global__ void __launch_bounds__(LOSS_THREADS) pixel_loss_kernel(const float* _
             }
         } else {
             for (int c = 0; c < C; ++c) {
-                const float d = pred[base + c * HW] - truth[base + c * HW];
+                float d = pred[base + c * HW] - truth[base + c * HW];
+                if (kind == 4)  // torchPSNR clamps both images to [0, 1] first (ModelTrainer.py:17-21)
+                    d = fminf(fmaxf(pred[base + c * HW], 0.f), 1.f) - fminf(fmaxf(truth[base + c * HW], 0.f), 1.f);
                 float gv;
                 if (kind == 0) {
                     s_abs += fabsf(d);
@@ -104,6 +106,7 @@ __global__ void pixel_loss_final_kernel(const float* __restrict__ partials, floa
         if (kind == 0) loss = A * inv_n * inv_div;
         else if (kind == 1) loss = (0.5 * Bq * inv_n + 0.25 * A * inv_n + 0.25 * Cl * inv_pix) * inv_div;
         else if (kind == 2) loss = A * inv_n;
+        else if (kind == 4) loss = Bq * inv_n;
         else loss = Bq * inv_n * inv_div;
         out[0] = (float)loss;
     }
@@ -115,7 +118,8 @@ extern "C" int uwr_pixel_loss(const float* pred, const float* truth, float* out,
                               int kind, int B, int C, int H, int W, int batch_divisor, uwr_stream_t stream_) {
     cudaStream_t stream = (cudaStream_t)stream_;
     UWR_REQUIRE(pred && truth && out && workspace, "uwr_pixel_loss: null pointer");
-    UWR_REQUIRE(kind >= 0 && kind <= 3, "uwr_pixel_loss: kind %d unsupported", kind);
+    UWR_REQUIRE(kind >= 0 && kind <= 4, "uwr_pixel_loss: kind %d unsupported", kind);
+    UWR_REQUIRE(kind != 4 || grad == nullptr, "uwr_pixel_loss: kind 4 (clamped MSE) has no gradient");
     UWR_REQUIRE(kind != 1 || C == 3, "uwr_pixel_loss: L1withColor needs 3 channels");
     UWR_REQUIRE(B > 0 && C > 0 && H > 0 && W > 0 && batch_divisor > 0, "uwr_pixel_loss: bad shape");
     const long long HW = (long long)H * W;

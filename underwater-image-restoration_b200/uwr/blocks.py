@@ -85,9 +85,11 @@ class DownsampleFn(torch.autograd.Function):
         dy2 = _c(dy).view(-1, Cout)
         col = ops.im2col_4x4s2(x.view(-1, Cc), B, H, W, Cc)  # recomputed, not saved (4x the input)
         fast = ops.fast_path()
-        if fast:  # tcgen05 path: both operands rounded to TF32 (col and wmat already are)
-            dy2 = ops.scale_round(dy2, Cout)
-        dwmat, dbias = ops.linear_wgrad(dy2, col, t5=fast)
+        if fast:  # tcgen05 path: both operands rounded to TF32 (col and wmat already are); bias gradient =
+            dy2, dbias = ops.scale_round_colsum(dy2, Cout)  # column sums taken in the same pass
+            dwmat, _ = ops.linear_wgrad(dy2, col, want_bias=False, t5=True)
+        else:
+            dwmat, dbias = ops.linear_wgrad(dy2, col)
         del col
         dcol = ops.linear_dgrad(dy2, wmat, t5=fast)
         dx = ops.col2im_4x4s2(dcol, B, H, W, Cc)

@@ -449,7 +449,7 @@ def colsum(x2d, cols):
 
 
 # --------------------------------------------------------------------------------------------
-LOSS_KINDS = {"L1": 0, "L1withColor": 1, "charbonnier": 2, "L2": 3}
+LOSS_KINDS = {"L1": 0, "L1withColor": 1, "charbonnier": 2, "L2": 3, "mse01": 4}
 
 
 def dft_real(x, B, H, W, C, scale, axes):
