@@ -98,3 +98,10 @@ if "lnb" in which:
 if "colsum" in which:
     x = torch.randn(M, 256, device=dev)
     timeit("colsum rows1M C256", lambda: ops.colsum(x, 256), 4 * M * 256, 0.0)
+if "fft" in which:
+    for (B, H, C) in ((16, 256, 32), (16, 64, 128)):
+        x = torch.randn(B, H, H, C, device=dev)
+        n = x.numel()
+        timeit(f"dft_hw_real B{B} {H}x{H} C{C}", lambda: ops.dft_real(x, B, H, H, C, 1.0, "hw"), 4 * n * 6, 5.0 * n * 2 * (H.bit_length() - 1))
+        timeit(f"dft_lc_real B{B} {H}x{H} C{C}", lambda: ops.dft_real(x, B, H, H, C, 1.0, "lc"), 4 * n * 10, 5.0 * n * (2 * (H.bit_length() - 1) + (C.bit_length() - 1)))
+        del x

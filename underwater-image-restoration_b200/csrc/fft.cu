@@ -168,6 +168,151 @@ __global__ void __launch_bounds__(FFT_WARPS * 32) fft_rows_kernel(const float* _
     }
 }
 
+
+// ---------------------------------------------------------------------------------------------
+// Register two-step variant (N = R1 * R2 <= 512): lanes <-> channels, every thread owns whole
+// R-point sub-transforms in registers, so a tile makes ONE round trip through shared memory (the
+// R1 x R2 transposition) instead of log2(N) radix-2 stages, and both global accesses are direct,
+// fully coalesced rows of 32 channels.
+//   step A: for each n2: R1-point FFT over n1 of x[R2*n1 + n2], times W_N^(n2*k1)  -> smem[k1][n2]
+//   step B: for each k1: R2-point FFT over n2                                      -> X[k1 + R1*k2]
+
+// W_32^k = exp(-2 pi i k / 32), k < 16 (compile-time after unrolling)
+__device__ __forceinline__ float2 tw32(int k) {
+    switch (k) {
+        case 0: return make_float2(1.000000000f, -0.000000000f);
+        case 1: return make_float2(0.980785280f, -0.195090322f);
+        case 2: return make_float2(0.923879533f, -0.382683432f);
+        case 3: return make_float2(0.831469612f, -0.555570233f);
+        case 4: return make_float2(0.707106781f, -0.707106781f);
+        case 5: return make_float2(0.555570233f, -0.831469612f);
+        case 6: return make_float2(0.382683432f, -0.923879533f);
+        case 7: return make_float2(0.195090322f, -0.980785280f);
+        case 8: return make_float2(0.000000000f, -1.000000000f);
+        case 9: return make_float2(-0.195090322f, -0.980785280f);
+        case 10: return make_float2(-0.382683432f, -0.923879533f);
+        case 11: return make_float2(-0.555570233f, -0.831469612f);
+        case 12: return make_float2(-0.707106781f, -0.707106781f);
+        case 13: return make_float2(-0.831469612f, -0.555570233f);
+        case 14: return make_float2(-0.923879533f, -0.382683432f);
+        case 15: return make_float2(-0.980785280f, -0.195090322f);
+    }
+    return make_float2(1.f, 0.f);
+}
+
+// in-register radix-2 DIF; natural-order output k is v[bit_reverse(k)]
+template <int R, bool INV>
+__device__ __forceinline__ void fft_reg(float2 (&v)[R]) {
+#pragma unroll
+    for (int span = R / 2; span >= 1; span >>= 1) {
+#pragma unroll
+        for (int blk = 0; blk < R; blk += 2 * span) {
+#pragma unroll
+            for (int j = 0; j < span; ++j) {
+                const float2 a = v[blk + j], b = v[blk + j + span];
+                v[blk + j] = make_float2(a.x + b.x, a.y + b.y);
+                const float2 d = make_float2(a.x - b.x, a.y - b.y);
+                if (j == 0) {
+                    v[blk + j + span] = d;
+                } else {
+                    float2 w = tw32(j * (16 / span));  // W_(2 span)^j
+                    if (INV) w.y = -w.y;
+                    v[blk + j + span] = cmulf(d, w);
+                }
+            }
+        }
+    }
+}
+
+template <int R>
+__host__ __device__ constexpr int brev_r(int k) {
+    int r = 0;
+    for (int b = 1; b < R; b <<= 1) {
+        r = (r << 1) | (k & 1);
+        k >>= 1;
+    }
+    return r;
+}
+
+template <int R1, int R2, bool INV>
+__global__ void __launch_bounds__(FFT_WARPS * 32) fft_pass2_kernel(const PassParams p) {
+    constexpr int N = R1 * R2;
+    extern __shared__ __align__(16) float2 fsm[];
+    float2* buf = fsm;                // [N][32]
+    float2* twN = fsm + N * FFT_CT;   // W_N^m
+    float2* tw4 = twN + N;            // four-step twiddles of this tile
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int c0 = blockIdx.x * FFT_CT, o = blockIdx.y, b = blockIdx.z;
+    const bool cok = c0 + lane < p.C;
+    for (int k = threadIdx.x; k < N; k += blockDim.x) {
+        float sn, cs;
+        sincospif((INV ? 2.0f : -2.0f) * (float)k / (float)N, &sn, &cs);
+        twN[k] = make_float2(cs, sn);
+        if (p.tw_L) {
+            const unsigned m = ((unsigned)o * (unsigned)k) & (unsigned)(p.tw_L - 1);
+            sincospif((INV ? 2.0f : -2.0f) * (float)m / (float)p.tw_L, &sn, &cs);
+            tw4[k] = make_float2(cs, sn);
+        }
+    }
+    __syncthreads();
+    const long long ibase = (long long)b * p.in_sB + (long long)o * p.in_sO + c0 + lane;
+    for (int n2 = warp; n2 < R2; n2 += FFT_WARPS) {
+        float2 v[R1];
+#pragma unroll
+        for (int n1 = 0; n1 < R1; ++n1) {
+            v[n1] = make_float2(0.f, 0.f);
+            if (cok) {
+                const long long a = ibase + (long long)(R2 * n1 + n2) * p.in_sN;
+                if (p.in_complex) v[n1] = reinterpret_cast<const float2*>(p.in)[a];
+                else v[n1].x = p.in[a];
+            }
+        }
+        fft_reg<R1, INV>(v);
+#pragma unroll
+        for (int k1 = 0; k1 < R1; ++k1) {
+            float2 val = v[brev_r<R1>(k1)];
+            if (k1 > 0) val = cmulf(val, twN[n2 * k1]);  // n2 * k1 < N
+            buf[(k1 * R2 + n2) * FFT_CT + lane] = val;
+        }
+    }
+    __syncthreads();
+    const long long obase = (long long)b * p.out_sB + (long long)o * p.out_sO + c0 + lane;
+    for (int k1 = warp; k1 < R1; k1 += FFT_WARPS) {
+        float2 u[R2];
+#pragma unroll
+        for (int n2 = 0; n2 < R2; ++n2) u[n2] = buf[(k1 * R2 + n2) * FFT_CT + lane];
+        fft_reg<R2, INV>(u);
+        if (cok) {
+#pragma unroll
+            for (int k2 = 0; k2 < R2; ++k2) {
+                const int k = k1 + R1 * k2;
+                float2 val = u[brev_r<R2>(k2)];
+                if (p.tw_L) val = cmulf(val, tw4[k]);
+                const long long a = obase + (long long)k * p.out_sN;
+                if (p.out_real) p.out[a] = val.x * p.scale;
+                else reinterpret_cast<float2*>(p.out)[a] = make_float2(val.x * p.scale, val.y * p.scale);
+            }
+        }
+    }
+}
+
+template <int R1, int R2>
+int launch_pass2(const PassParams& p, int B, cudaStream_t stream) {
+    constexpr int N = R1 * R2;
+    constexpr int smem = (N * FFT_CT + 2 * N) * (int)sizeof(float2);
+    static bool configured = false;
+    if (!configured) {
+        UWR_CUDA(cudaFuncSetAttribute(fft_pass2_kernel<R1, R2, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+        UWR_CUDA(cudaFuncSetAttribute(fft_pass2_kernel<R1, R2, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+        configured = true;
+    }
+    const dim3 grid(uwr_cdiv(p.C, FFT_CT), p.NO, B);
+    if (p.inverse) fft_pass2_kernel<R1, R2, true><<<grid, FFT_WARPS * 32, smem, stream>>>(p);
+    else fft_pass2_kernel<R1, R2, false><<<grid, FFT_WARPS * 32, smem, stream>>>(p);
+    UWR_CHECK_LAUNCH("fft_pass2_kernel");
+    return 0;
+}
+
 int ilog2i(int v) {
     int l = 0;
     while ((1 << l) < v) ++l;
@@ -179,6 +324,15 @@ int launch_pass(PassParams& p, int B, cudaStream_t stream) {
     UWR_REQUIRE(p.N >= 1 && (pow2(p.N) ? p.N <= 1024 : p.N <= 384),
                 "fft pass: length %d unsupported (powers of two <= 1024, other lengths <= 384)", p.N);
     UWR_REQUIRE(B > 0 && B <= 65535 && p.NO > 0 && p.NO <= 65535, "fft pass: bad batch / extent");
+    switch (p.N) {  // register two-step kernels
+        case 16: return launch_pass2<4, 4>(p, B, stream);
+        case 32: return launch_pass2<8, 4>(p, B, stream);
+        case 64: return launch_pass2<8, 8>(p, B, stream);
+        case 128: return launch_pass2<16, 8>(p, B, stream);
+        case 256: return launch_pass2<16, 16>(p, B, stream);
+        case 512: return launch_pass2<32, 16>(p, B, stream);
+        default: break;
+    }
     p.log2N = pow2(p.N) ? ilog2i(p.N) : -1;
     const int smem = (2 * p.N + (pow2(p.N) ? 1 : 2) * FFT_CT * (p.N + 1)) * (int)sizeof(float2);
     static int configured = 0;
