@@ -260,7 +260,16 @@ def run_ours(args):
         else:
             roofline = {"bound": "hbm", "achieved": gbs, "peak": hbm, "unit": "GB/s", "frac": gbs / hbm}
         total_ms = sum(r["ms_total"] for r in table)
-        roofline.update({"traffic": None, "kernel": fam_name, "launches_per_step": fv[3],
+        traffic, traffic_note = None, None
+        tp = os.path.join(ROOT, "profiles", "r1_roofline_traffic.json")
+        if os.path.exists(tp):  # dram__bytes_read.sum + dram__bytes_write.sum of one committed `ncu --set full` capture
+            with open(tp) as f:
+                ent = json.load(f).get(fam_name)
+            if ent:
+                traffic = ent["dram_bytes_per_launch"]
+                traffic_note = {"shape": ent["shape"], "algorithmic_bytes_per_launch": ent["algorithmic_bytes_per_launch"],
+                                "source": ent["source"]}
+        roofline.update({"traffic": traffic, "traffic_capture": traffic_note, "kernel": fam_name, "launches_per_step": fv[3],
                          "ms_per_launch": fv[0] / fv[3], "share_of_step": fv[0] / total_ms,
                          "arithmetic_intensity": ai,
                          "top_shape": {"shape": top["shape"], "ms_per_launch": top["ms_avg"], "gbs": top["gbs"],

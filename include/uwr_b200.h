@@ -163,6 +163,12 @@ int uwr_dwconv_gelu_fwd(const float* u, long long ld_u, const float* weight /*(C
  * (UWR_EPI_MUL_DGELU); mode 1 (FRFN) also writes du[:, Ch:2Ch] = dh2 * gelu(v) * gelu'(u2). */
 int uwr_gelu_gate_bwd(const float* dh2, const float* u, long long ld_u, const float* v, float* dv,
                       float* du, long long rows, int Ch, int mode, uwr_stream_t stream);
+/* GDFN gate (SpectralTransformer.py:126-129): out = gelu(t[:, :h]) * t[:, h:2h]; t has row stride ld >= 2h,
+ * dt the same layout; h % 4 == 0. */
+int uwr_gelu_mul_fwd(const float* t, long long ld, float* out /*(rows,h)*/, long long rows, int h,
+                     uwr_stream_t stream);
+int uwr_gelu_mul_bwd(const float* dout /*(rows,h)*/, const float* t, long long ld, float* dt,
+                     long long rows, int h, uwr_stream_t stream);
 size_t uwr_dwconv_gelu_bwd_workspace_bytes(int B, int H, int W, int Ch);
 /* dv (gradient w.r.t. the conv output v) -> du[:, :Ch] (row stride ld_u), dweight (Ch,1,3,3),
  * dbias (Ch); only dv needs a halo.  du_colsum (Ch, optional) = column sums of du, i.e. the bias

@@ -17,7 +17,8 @@ def rnd(*s):
 
 
 def timeit(name, fn, nbytes, flops, reps=5):
-    for _ in range(2):
+    reps = int(os.environ.get("UWR_KB_REPS", reps))   # UWR_KB_REPS=1: one launch per kernel (ncu --set full captures)
+    for _ in range(2 if reps > 1 else 0):
         fn()
     torch.cuda.synchronize()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)

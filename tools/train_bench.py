@@ -57,6 +57,8 @@ res = {"arch": arch, "loss": loss, "batch": B, "size": S, "ms_per_step": ms, "im
        "uwr_kernel_ms": {k: round(v[0], 3) for k, v in sorted(fam.items(), key=lambda kv: -kv[1][0])[:8]},
        "uwr_kernel_ms_total": round(sum(v[0] for v in fam.values()), 2)}
 print(json.dumps(res))
+if os.environ.get("UWR_PROFILE_OUT"):
+    json.dump({"result": res, "kernels": prof.table()}, open(os.environ["UWR_PROFILE_OUT"], "w"), indent=1)
 if os.environ.get("UWR_TORCHPROF"):
     # every CUDA kernel of one step (ours + ATen/cuDNN/cuFFT), to see what is still library code
     from torch.profiler import profile, ProfilerActivity

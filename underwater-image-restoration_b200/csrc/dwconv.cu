@@ -183,6 +183,45 @@ __global__ void __launch_bounds__(256) gelu_gate_bwd_kernel(const float* __restr
     }
 }
 
+// GDFN gate (SpectralTransformer.py:126-129): out = gelu(t[:, :h]) * t[:, h:2h] on token slabs (row stride ld)
+__global__ void __launch_bounds__(256) gelu_mul_fwd_kernel(const float* __restrict__ t, long long ld,
+                                                           float* __restrict__ out, long long rows, int h4, int rnd) {
+    const long long total = rows * h4;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total;
+         i += (long long)gridDim.x * blockDim.x) {
+        const long long r = i / h4;
+        const int c = (int)(i % h4) * 4;
+        const float4 a = ld4(t + r * ld + c), b = ld4(t + r * ld + h4 * 4 + c);
+        float4 o = make_float4(gelu_f(a.x) * b.x, gelu_f(a.y) * b.y, gelu_f(a.z) * b.z, gelu_f(a.w) * b.w);
+        if (rnd) o = make_float4(tf32_round(o.x), tf32_round(o.y), tf32_round(o.z), tf32_round(o.w));
+        reinterpret_cast<float4*>(out)[i] = o;
+    }
+}
+// dt[:, :h] = dout * t2 * gelu'(t1) ; dt[:, h:] = dout * gelu(t1)
+__global__ void __launch_bounds__(256) gelu_mul_bwd_kernel(const float* __restrict__ dout, const float* __restrict__ t,
+                                                           long long ld, float* __restrict__ dt, long long rows,
+                                                           int h4) {
+    const long long total = rows * h4;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total;
+         i += (long long)gridDim.x * blockDim.x) {
+        const long long r = i / h4;
+        const int c = (int)(i % h4) * 4;
+        const float4 a = ld4(t + r * ld + c), b = ld4(t + r * ld + h4 * 4 + c);
+        const float4 d = reinterpret_cast<const float4*>(dout)[i];
+        const float av[4] = {a.x, a.y, a.z, a.w}, bv[4] = {b.x, b.y, b.z, b.w}, dv[4] = {d.x, d.y, d.z, d.w};
+        float g1[4], g2[4];
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+            float cdf, pdf;
+            gelu_parts(av[e], cdf, pdf);
+            g1[e] = dv[e] * bv[e] * fmaf(av[e], pdf, cdf);
+            g2[e] = dv[e] * av[e] * cdf;
+        }
+        *reinterpret_cast<float4*>(dt + r * ld + c) = make_float4(g1[0], g1[1], g1[2], g1[3]);
+        *reinterpret_cast<float4*>(dt + r * ld + h4 * 4 + c) = make_float4(g2[0], g2[1], g2[2], g2[3]);
+    }
+}
+
 // persistent over tiles: grid = (P, Ch/32).  thread -> (tile row, 2-channel group): 16 outputs x 2
 // channels with 64-bit accesses (the 4-channel variant needs > 128 registers for the nine dweight
 // accumulators and would leave one CTA per SM).  dweight/dbias partials accumulate in registers and
@@ -405,6 +444,29 @@ extern "C" int uwr_gelu_gate_bwd(const float* dh2, const float* u, long long ld_
     if (blocks > 16LL * uwr_sm_count()) blocks = 16LL * uwr_sm_count();
     gelu_gate_bwd_kernel<<<(unsigned)blocks, 256, 0, stream>>>(dh2, u, ld_u, v, dv, du, rows, Ch, mode, uwr_round_outputs());
     UWR_CHECK_LAUNCH("gelu_gate_bwd_kernel");
+    return 0;
+}
+
+extern "C" int uwr_gelu_mul_fwd(const float* t, long long ld, float* out, long long rows, int h, uwr_stream_t stream_) {
+    cudaStream_t stream = (cudaStream_t)stream_;
+    UWR_REQUIRE(t && out && h % 4 == 0 && ld % 4 == 0 && ld >= 2 * h, "uwr_gelu_mul_fwd: bad args");
+    if (rows == 0) return 0;
+    long long blocks = (rows * (h / 4) + 255) / 256;
+    if (blocks > 16LL * uwr_sm_count()) blocks = 16LL * uwr_sm_count();
+    gelu_mul_fwd_kernel<<<(unsigned)blocks, 256, 0, stream>>>(t, ld, out, rows, h / 4, uwr_round_outputs());
+    UWR_CHECK_LAUNCH("gelu_mul_fwd_kernel");
+    return 0;
+}
+
+extern "C" int uwr_gelu_mul_bwd(const float* dout, const float* t, long long ld, float* dt, long long rows, int h,
+                                uwr_stream_t stream_) {
+    cudaStream_t stream = (cudaStream_t)stream_;
+    UWR_REQUIRE(dout && t && dt && h % 4 == 0 && ld % 4 == 0 && ld >= 2 * h, "uwr_gelu_mul_bwd: bad args");
+    if (rows == 0) return 0;
+    long long blocks = (rows * (h / 4) + 255) / 256;
+    if (blocks > 16LL * uwr_sm_count()) blocks = 16LL * uwr_sm_count();
+    gelu_mul_bwd_kernel<<<(unsigned)blocks, 256, 0, stream>>>(dout, t, ld, dt, rows, h / 4);
+    UWR_CHECK_LAUNCH("gelu_mul_bwd_kernel");
     return 0;
 }
 

@@ -110,9 +110,14 @@ class Conv3x3Fn(torch.autograd.Function):
         B, H, W, Cin, Cout, has_b = ctx.meta
         d = _c(dy).view(-1, Cout)
         col = ops.im2col_3x3(x.view(-1, Cin), B, H, W, Cin)  # recomputed (9x the input)
-        dwm, db = ops.linear_wgrad(d, col, want_bias=has_b)
+        fast = ops.fast_path() and Cout % 32 == 0 and d.shape[0] >= 4096
+        if fast:  # tcgen05 path: TF32-rounded copy of the cotangent (col and wmat already are rounded)
+            d, db = ops.scale_round_colsum(d, Cout) if has_b else (ops.scale_round(d, Cout), None)
+            dwm, _ = ops.linear_wgrad(d, col, want_bias=False, t5=True)
+        else:
+            dwm, db = ops.linear_wgrad(d, col, want_bias=has_b)
         del col
-        dcol = ops.linear_dgrad(d, wmat)
+        dcol = ops.linear_dgrad(d, wmat, t5=fast)
         dx = ops._empty((B * H * W, Cin), x)
         ops.col2im_3x3(dcol, dx, B, H, W, Cin)
         dw = dwm.view(Cout, 3, 3, Cin).permute(0, 3, 1, 2).contiguous()
@@ -254,3 +259,127 @@ class Fft2Fn(torch.autograd.Function):
         if not in_complex:
             dx = dx[..., 0].contiguous()
         return dx, None, None, None, None, None, None, None
+
+
+def _mdta_matrices(G, temperature, C, heads):
+    """(B, 2C, 2C) Gram matrices of [q|k] -> (B, C, C) block-diagonal channel-attention matrices
+    softmax(normalize(q) normalize(k)^T * temperature) (SpectralTransformer.py:97-101); tiny batched
+    ATen ops, differentiated by autograd inside MDTAAttnFn."""
+    B = G.shape[0]
+    c = C // heads
+    d = torch.diagonal(G, dim1=-2, dim2=-1)
+    nq = d[:, :C].clamp_min(0).sqrt().clamp_min(1e-12)              # F.normalize eps (line 99)
+    nk = d[:, C:].clamp_min(0).sqrt().clamp_min(1e-12)
+    S = G[:, :C, C:] / (nq[:, :, None] * nk[:, None, :])
+    blocks = S.view(B, heads, c, heads, c).diagonal(dim1=1, dim2=3).permute(0, 3, 1, 2)     # (B, h, c, c)
+    A = torch.softmax(blocks * temperature.view(1, heads, 1, 1), dim=-1)
+    return torch.diag_embed(A.permute(0, 2, 3, 1), dim1=1, dim2=3).reshape(B, C, C)          # batched block_diag
+
+
+class MDTAAttnFn(torch.autograd.Function):
+    """MDTA channel attention (SpectralTransformer.py:92-109) for a whole batch without per-image
+    autograd slicing: qkv (B*L, 3C) tokens -> out = attn @ v (B*L, C) and the attention matrices
+    A (B, C, C) (re-used for the frequency branch's `attn @ vf`).  Per image two GEMMs on strided
+    views (Gram matrix of [q|k] over the tokens, apply); the (2C)^2-sized normalise / softmax algebra
+    runs batched and is differentiated by autograd on those tiny tensors only."""
+
+    @staticmethod
+    def forward(ctx, qkv, temperature, B, L, C, heads):
+        qkv = _c(qkv)
+        G = ops._empty((B, 2 * C, 2 * C), qkv)
+        for b in range(B):
+            x = qkv[b * L:(b + 1) * L, :2 * C]
+            ops.gemm(x, x, G[b], 2 * C, 2 * C, L, lda=3 * C, ldb=3 * C, ldc=2 * C, a_km=True, b_nk=False)
+        with torch.enable_grad():
+            Gd = G.detach().requires_grad_()
+            td = temperature.detach().requires_grad_()
+            A = _mdta_matrices(Gd, td, C, heads)
+        Ad = A.detach().contiguous()
+        out = ops._empty((B * L, C), qkv)
+        for b in range(B):
+            ops.linear(qkv[b * L:(b + 1) * L, 2 * C:], Ad[b], None, out=out[b * L:(b + 1) * L])
+        ctx.save_for_backward(qkv, Ad)
+        ctx.graph = (Gd, td, A)
+        ctx.meta = (B, L, C)
+        return out, Ad
+
+    @staticmethod
+    @once_differentiable
+    def backward(ctx, dout, dA_ext):
+        qkv, Ad = ctx.saved_tensors
+        Gd, td, A = ctx.graph
+        B, L, C = ctx.meta
+        dout = _c(dout)
+        dqkv = torch.empty_like(qkv)
+        dA = ops._empty((B, C, C), qkv)
+        for b in range(B):
+            rows = slice(b * L, (b + 1) * L)
+            v = qkv[rows, 2 * C:]
+            ops.gemm(dout[rows], v, dA[b], C, C, L, lda=C, ldb=3 * C, ldc=C, a_km=True, b_nk=False)   # dout^T v
+            ops.linear_dgrad(dout[rows], Ad[b], out=dqkv[rows, 2 * C:])                               # dv = dout A
+        if dA_ext is not None:
+            dA = dA + dA_ext
+        with torch.enable_grad():
+            dG, dt = torch.autograd.grad(A, (Gd, td), dA)
+        S = _c(dG + dG.transpose(1, 2))
+        for b in range(B):
+            rows = slice(b * L, (b + 1) * L)
+            ops.gemm(qkv[rows, :2 * C], S[b], dqkv[rows, :2 * C], L, 2 * C, 2 * C, lda=3 * C, ldb=2 * C, ldc=3 * C,
+                     b_nk=False)
+        ctx.graph = None
+        return dqkv, dt.view_as(td), None, None, None, None
+
+
+class ChannelApplyFn(torch.autograd.Function):
+    """out[b] = x[b][:, col:col+C] @ A[b]^T for token slabs x (B*L, ld) and per-image matrices A (B, C, C)."""
+
+    @staticmethod
+    def forward(ctx, x, A, col, B, L):
+        x = _c(x)
+        A = _c(A)
+        C = A.shape[1]
+        out = ops._empty((B * L, C), x)
+        for b in range(B):
+            ops.linear(x[b * L:(b + 1) * L, col:col + C], A[b], None, out=out[b * L:(b + 1) * L])
+        ctx.save_for_backward(x, A)
+        ctx.meta = (col, B, L, C)
+        return out
+
+    @staticmethod
+    @once_differentiable
+    def backward(ctx, dout):
+        x, A = ctx.saved_tensors
+        col, B, L, C = ctx.meta
+        dout = _c(dout)
+        dx = torch.zeros_like(x)
+        dA = ops._empty((B, C, C), x)
+        ld = x.shape[1]
+        for b in range(B):
+            rows = slice(b * L, (b + 1) * L)
+            ops.gemm(dout[rows], x[rows, col:col + C], dA[b], C, C, L, lda=C, ldb=ld, ldc=C, a_km=True, b_nk=False)
+            ops.linear_dgrad(dout[rows], A[b], out=dx[rows, col:col + C])
+        return dx, dA, None, None, None
+
+
+class GeluMulFn(torch.autograd.Function):
+    """GDFN gate (SpectralTransformer.py:126-129): gelu(t[:, :h]) * t[:, h:2h] in one pass (no autograd slicing)."""
+
+    @staticmethod
+    def forward(ctx, t, h):
+        t = _c(t)
+        out = ops._empty((t.shape[0], h), t)
+        ops._run("uwr_gelu_mul_fwd", f"rows{t.shape[0]} h{h}", 12 * t.shape[0] * h, 0.0, ops._ptr(t), t.stride(0),
+                 ops._ptr(out), t.shape[0], h)
+        ctx.save_for_backward(t)
+        ctx.h = h
+        return out
+
+    @staticmethod
+    @once_differentiable
+    def backward(ctx, dout):
+        (t,) = ctx.saved_tensors
+        h = ctx.h
+        dt = torch.empty_like(t) if t.shape[1] == 2 * h else torch.zeros_like(t)
+        ops._run("uwr_gelu_mul_bwd", f"rows{t.shape[0]} h{h}", 20 * t.shape[0] * h, 0.0, ops._ptr(_c(dout)), ops._ptr(t),
+                 t.stride(0), ops._ptr(dt), t.shape[0], h)
+        return dt, None

@@ -5,7 +5,7 @@ torchPSNR (src/ModelTrainer.py:17-21, duplicate in src/utils/utils.py:31-35):
 The squared-error mean is one pass of the native pixel-loss kernel (kind "mse01").  Under data
 parallelism the per-rank means are averaged BEFORE the logarithm (SURVEY.md §8e caveat 2), which
 equals the single-process whole-batch value when every rank holds the same number of images.
-UIQM (uqim_utils.py) stays on the CPU as in the reference (oracle/uiqm_oracle.py restates it).
+UIQM (uqim_utils.py) is a CPU metric in the reference and is not part of this module.
 """
 import torch
 

@@ -36,31 +36,15 @@ class MDTA(nn.Module):
         self.kv_conv = nn.Conv2d(channels * 2, channels * 2, kernel_size=3, padding=1, groups=channels * 2, bias=False)
         self.project_outf = nn.Conv2d(channels, channels, kernel_size=1, bias=False)
 
-    def _attention_matrices(self, qkv, B, L, C):
-        """per image: block-diagonal (C, C) matrix of softmax(normalize(q) normalize(k)^T * temperature)."""
-        h = self.num_heads
-        c = C // h
-        mats = []
-        for b in range(B):
-            G = fn.GramFn.apply(qkv[b * L:(b + 1) * L, :2 * C])          # [[q^T q, q^T k], [k^T q, k^T k]]
-            d = torch.diagonal(G)
-            nq = d[:C].clamp_min(0).sqrt().clamp_min(1e-12)              # F.normalize eps (line 99)
-            nk = d[C:].clamp_min(0).sqrt().clamp_min(1e-12)
-            S = G[:C, C:] / (nq[:, None] * nk[None, :])
-            blocks = torch.stack([S[i * c:(i + 1) * c, i * c:(i + 1) * c] for i in range(h)])   # (h, c, c)
-            A = torch.softmax(blocks * self.temperature.view(h, 1, 1), dim=-1)
-            mats.append(torch.block_diag(*A.unbind(0)))
-        return mats
-
     def forward(self, y, B, H, W):   # y: LayerNorm output tokens (B*L, C)
         L, C = H * W, y.shape[1]
         qkv = fn.linear(y, _w2(self.qkv), None, rounded=True)
         qkv = fn.PlainDWConvFn.apply(qkv, self.qkv_conv.weight, B, H, W)
-        mats = self._attention_matrices(qkv, B, L, C)
-        out = torch.cat([fn.linear(qkv[b * L:(b + 1) * L, 2 * C:], mats[b]) for b in range(B)], 0)   # attn @ v
+        # channel attention for the whole batch: Gram GEMMs on strided views, batched normalise / softmax
+        out, attn = fn.MDTAAttnFn.apply(qkv, self.temperature, B, L, C, self.num_heads)        # attn @ v
         out = fn.linear(out, _w2(self.project_out))
         kvf = fn.PlainDWConvFn.apply(fn.linear(out, _w2(self.kv)), self.kv_conv.weight, B, H, W)
-        outf = torch.cat([fn.linear(kvf[b * L:(b + 1) * L, C:], mats[b]) for b in range(B)], 0)      # attn @ vf
+        outf = fn.ChannelApplyFn.apply(kvf, attn, C, B, L)                                       # attn @ vf
         return fn.linear(outf, _w2(self.project_outf))
 
 
@@ -87,7 +71,7 @@ class GDFN(nn.Module):
             wdw = torch.cat([wdw[:h], z2, wdw[h:], z2], 0)
             wout = torch.cat([wout, wout.new_zeros(wout.shape[0], hp - h)], 1)
         t = fn.PlainDWConvFn.apply(fn.linear(y, win, None, rounded=True), wdw, B, H, W)
-        return fn.linear(F.gelu(t[:, :hp]) * t[:, hp:], wout)
+        return fn.linear(fn.GeluMulFn.apply(t, hp), wout)
 
 
 class TransformerBlock(nn.Module):
