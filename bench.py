@@ -188,9 +188,9 @@ def run_ours(args):
             dist.all_reduce(ms, op=dist.ReduceOp.MAX)
         return ms.item()
 
-    # Single GPU: the whole step is replayed from one CUDA graph (uwr.graph.GraphedTrainStep); with
-    # N > 1 the NCCL-overlapped step is launched eagerly (graph capture of the hooks is not implemented).
-    use_graph = (world == 1) and not args.no_graph
+    # The step is replayed from CUDA graphs (uwr.graph.GraphedTrainStep): one graph on a single GPU; with
+    # N > 1 forward+backward and clip+Adam are two graphs around the eager NCCL bucket all-reduces.
+    use_graph = not args.no_graph
     graphed = None
     if use_graph:
         from uwr.graph import GraphedTrainStep
@@ -198,7 +198,7 @@ def run_ours(args):
 
     def step_resident():
         if graphed is not None:
-            graphed.graph.replay()
+            graphed.replay()
         else:
             step(raw_d, ref_d)
 

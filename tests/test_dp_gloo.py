@@ -12,7 +12,7 @@ import torch.multiprocessing as mp
 from conftest import ROOT, PKG
 
 
-def _worker(rank, world, port, out):
+def _worker(rank, world, port, out, overlap=True):
     for p in (ROOT, PKG):
         sys.path.insert(0, p)
     os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
@@ -23,6 +23,7 @@ def _worker(rank, world, port, out):
     dead = torch.nn.Parameter(torch.ones(5))          # never receives a gradient
     params = list(net.parameters()) + [dead]
     buckets = GradBuckets(params, bucket_bytes=1024, world_size=world)
+    buckets.overlap = overlap   # False: hooks only count, finish() reduces every bucket (graph-replayed backward)
     g = torch.Generator().manual_seed(1)
     x = torch.randn(8, 16, generator=g)
     y = torch.randn(8, 8, generator=g)
@@ -38,10 +39,11 @@ def _worker(rank, world, port, out):
 
 
 @pytest.mark.timeout(120)
-def test_grad_buckets_match_global_batch(tmp_path):
+@pytest.mark.parametrize("overlap", [True, False])
+def test_grad_buckets_match_global_batch(tmp_path, overlap):
     out = str(tmp_path / "grads.pt")
-    port = 29500 + os.getpid() % 1000
-    mp.spawn(_worker, args=(2, port, out), nprocs=2, join=True)
+    port = 29500 + (os.getpid() + (0 if overlap else 17)) % 1000
+    mp.spawn(_worker, args=(2, port, out, overlap), nprocs=2, join=True)
     got = torch.load(out)
     torch.manual_seed(0)
     net = torch.nn.Sequential(torch.nn.Linear(16, 32), torch.nn.GELU(), torch.nn.Linear(32, 8))

@@ -27,7 +27,32 @@ def run(ws, batch_slice):
     return m, loss, norm
 
 
+def run_steps(ws, batch_slice, graphed, nsteps=2):
+    """nsteps optimizer steps, eagerly (overlapped all-reduce) or through GraphedTrainStep (forward+backward
+    and clip+Adam as two CUDA graphs around the eager bucket all-reduce)."""
+    from uwr.graph import GraphedTrainStep
+    torch.manual_seed(1234)
+    m = uwr.AST(img_size=S).cuda().eval()
+    step = TrainStep(m, "L2", lr=1e-3, world_size=ws, local_batch=batch_slice.stop - batch_slice.start)
+    r, t = raw[batch_slice].cuda(), ref[batch_slice].cuda()
+    if graphed:
+        gs = GraphedTrainStep(step, r, t, warmup=nsteps - 1)
+        gs(r, t)
+    else:
+        for _ in range(nsteps):
+            step(r, t)
+    torch.cuda.synchronize()
+    return m
+
+
 m_dp, loss_dp, norm_dp = run(world, slice(rank * Bl, (rank + 1) * Bl))
+m_e = run_steps(world, slice(rank * Bl, (rank + 1) * Bl), graphed=False)
+m_g = run_steps(world, slice(rank * Bl, (rank + 1) * Bl), graphed=True)
+if rank == 0:
+    num = sum(((a - b).double() ** 2).sum() for a, b in zip(m_g.parameters(), m_e.parameters())).sqrt().item()
+    den = sum((b.double() ** 2).sum() for b in m_e.parameters()).sqrt().item()
+    print(f"DP graphed (2 graphs + eager all-reduce) vs eager overlapped, 2 steps: param rel diff {num / den:.2e}")
+    assert num / den < 1e-6
 if rank == 0:
     m_1, loss_1, norm_1 = run(1, slice(0, Bl * world))
     num = sum(((a - b).double() ** 2).sum() for a, b in zip(m_dp.parameters(), m_1.parameters())).sqrt().item()

@@ -43,30 +43,36 @@ class GradBuckets:
                 self._bucket_of[id(p)] = bi
             self.flat.append(flat)
         self._count = [0] * len(self.buckets)
+        self._launched = [False] * len(self.buckets)
+        self.overlap = True   # False: hooks only count, every bucket is reduced in finish() (graph-replayed backward)
         if self.world > 1:
             for p in self.params:
                 p.register_post_accumulate_grad_hook(self._hook)
 
+    def _reduce(self, bi):
+        self._launched[bi] = True
+        self._handles.append(dist.all_reduce(self.flat[bi], op=dist.ReduceOp.SUM, group=self.group, async_op=True))
+
     def _hook(self, p):
         bi = self._bucket_of[id(p)]
         self._count[bi] += 1
-        if self._count[bi] == len(self.buckets[bi]):
-            self._handles.append(dist.all_reduce(self.flat[bi], op=dist.ReduceOp.SUM, group=self.group,
-                                                 async_op=True))
+        if self.overlap and self._count[bi] == len(self.buckets[bi]):
+            self._reduce(bi)
 
     def zero(self):
         for f in self.flat:
             f.zero_()
         self._count = [0] * len(self.buckets)
+        self._launched = [False] * len(self.buckets)
 
     def finish(self):
-        """Wait for the in-flight all-reduces; buckets whose parameters never received a gradient
-        (dead parameters) are reduced here so every rank stays in lock-step."""
+        """Wait for the in-flight all-reduces; buckets not reduced yet — parameters that never received a
+        gradient (dead parameters), or all of them when overlap is off — are reduced
+        here so every rank stays in lock-step."""
         if self.world > 1:
-            for bi, c in enumerate(self._count):
-                if c != len(self.buckets[bi]):
-                    self._handles.append(dist.all_reduce(self.flat[bi], op=dist.ReduceOp.SUM, group=self.group,
-                                                         async_op=True))
+            for bi in range(len(self.buckets)):
+                if not self._launched[bi]:
+                    self._reduce(bi)
             for h in self._handles:
                 h.wait()
             self._handles = []
@@ -82,13 +88,17 @@ class TrainStep:
         self.opt = FusedClipAdam(model.parameters(), lr=lr, weight_decay=0.01 if optim == "adamw" else 0.0,
                                  decoupled=(optim == "adamw"), max_norm=1.0, grad_prescale=1.0 / world_size)
 
-    def __call__(self, raw, ref):
+    def forward_backward(self, raw, ref):
         self.buckets.zero()
         out = self.model(raw)
         loss = self.lossf.getloss(out, ref)
         if isinstance(loss, tuple):
             loss = loss[0]
         loss.backward()
+        return loss.detach()
+
+    def __call__(self, raw, ref):
+        loss = self.forward_backward(raw, ref)
         self.buckets.finish()
         norm = self.opt.step()
-        return loss.detach(), norm
+        return loss, norm
