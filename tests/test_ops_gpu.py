@@ -476,3 +476,52 @@ def test_fflmix_loss_tuple_matches_reference_golden():
         assert abs(got.item() - want) <= 2e-4 * abs(want), (got.item(), want)
     out[0].backward()
     assert torch.isfinite(pc.grad).all() and pc.grad.abs().sum().item() > 0
+
+
+# ------------------------------------------------------------------ SpectralTransformer pieces
+def test_gdfn_gate():
+    """GeluMulFn (uwr_gelu_mul_fwd/bwd) vs gelu(t[:, :h]) * t[:, h:] (SpectralTransformer.py:126-129)."""
+    from uwr import fn, ops
+    ops.set_gemm_precision("tf32x3")   # no TF32 rounding at the store
+    try:
+        rows, h = 777, 44
+        t = _r(rows, 2 * h, seed=1).requires_grad_()
+        g = _r(rows, h, seed=2)
+        y = fn.GeluMulFn.apply(t, h)
+        y.backward(g)
+        td = t.detach().double().requires_grad_()
+        ref = F.gelu(td[:, :h]) * td[:, h:]
+        ref.backward(g.double())
+        assert rel_l2(y, ref) < TOL_FP32
+        assert rel_l2(t.grad, td.grad) < TOL_FP32
+    finally:
+        ops.set_gemm_precision("tf32")
+
+
+@pytest.mark.parametrize("B,L,C,heads", [(2, 256, 32, 2), (3, 1024, 16, 1)])
+def test_mdta_channel_attention(B, L, C, heads):
+    """MDTAAttnFn / ChannelApplyFn (batched Gram GEMMs + tiny softmax algebra) vs the reference formulation
+    (SpectralTransformer.py:92-109) in fp64, values and gradients, incl. the second use of the attention."""
+    from uwr import fn
+    qkv = _r(B * L, 3 * C, seed=1).requires_grad_()
+    kvf = _r(B * L, 2 * C, seed=2).requires_grad_()
+    temp = (torch.ones(1, heads, 1, 1, device="cuda") * 1.3).requires_grad_()
+    g1, g2 = _r(B * L, C, seed=3), _r(B * L, C, seed=4)
+    out, attn = fn.MDTAAttnFn.apply(qkv, temp, B, L, C, heads)
+    outf = fn.ChannelApplyFn.apply(kvf, attn, C, B, L)
+    (out * g1).sum().add((outf * g2).sum()).backward()
+
+    qd, kd, td = qkv.detach().double().requires_grad_(), kvf.detach().double().requires_grad_(), temp.detach().double().requires_grad_()
+    c = C // heads
+    x = qd.view(B, L, 3 * C).transpose(1, 2)                       # (B, 3C, L) as the reference's NCHW flatten
+    q, k, v = (t.reshape(B, heads, c, L) for t in x.chunk(3, dim=1))
+    q, k = F.normalize(q, dim=-1), F.normalize(k, dim=-1)
+    a = torch.softmax(q @ k.transpose(-2, -1) * td, dim=-1)        # (B, h, c, c)
+    ro = (a @ v).reshape(B, C, L).transpose(1, 2).reshape(B * L, C)
+    vf = kd.view(B, L, 2 * C)[:, :, C:].transpose(1, 2).reshape(B, heads, c, L)
+    rof = (a @ vf).reshape(B, C, L).transpose(1, 2).reshape(B * L, C)
+    (ro * g1.double()).sum().add((rof * g2.double()).sum()).backward()
+    assert rel_l2(out, ro) < TOL_TF32 and rel_l2(outf, rof) < TOL_TF32
+    assert rel_l2(qkv.grad, qd.grad) < 2 * TOL_TF32
+    assert rel_l2(kvf.grad, kd.grad) < 2 * TOL_TF32
+    assert rel_l2(temp.grad, td.grad) < 2 * TOL_TF32
