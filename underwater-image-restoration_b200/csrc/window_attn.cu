@@ -211,14 +211,16 @@ __device__ __forceinline__ void row_softmax(const float (&s)[8][4], float (&p0)[
         float sum = 0.f;
 #pragma unroll
         for (int nt = 0; nt < 8; ++nt) {
-            const float e0 = __expf(s[nt][half * 2] - m), e1 = __expf(s[nt][half * 2 + 1] - m);
+            // exp(x) = 2^(x log2 e) on MUFU.EX2 without the denormal fix-up code of __expf (arguments <= 0)
+            const float e0 = ex2_ftz((s[nt][half * 2] - m) * 1.4426950408889634f);
+            const float e1 = ex2_ftz((s[nt][half * 2 + 1] - m) * 1.4426950408889634f);
             p0[nt][half * 2] = e0;
             p0[nt][half * 2 + 1] = e1;
             sum += e0 + e1;
         }
         sum += __shfl_xor_sync(0xffffffffu, sum, 1);
         sum += __shfl_xor_sync(0xffffffffu, sum, 2);
-        const float inv = 1.0f / sum;
+        const float inv = __fdividef(1.0f, sum);  // 1 <= sum <= 64
 #pragma unroll
         for (int nt = 0; nt < 8; ++nt) {
             p0[nt][half * 2] *= inv;
