@@ -165,3 +165,30 @@ def test_graphed_train_step_matches_eager():
     num = sum(((a - b).double() ** 2).sum() for a, b in zip(m1.parameters(), m2.parameters())).sqrt().item()
     den = sum((b.double() ** 2).sum() for b in m1.parameters()).sqrt().item()
     assert num / den < 1e-7
+
+
+def test_batched_weight_rerounding_is_bit_identical(monkeypatch):
+    """FusedClipAdam refreshes every TF32 weight copy with two multi-tensor launches right after the update;
+    the lazy per-weight path (one launch per weight in the next forward) must give the same bits."""
+    import uwr
+    from uwr import ops
+    from uwr.train import TrainStep
+
+    def run(batched):
+        if not batched:
+            monkeypatch.setattr(ops, "refresh_rounded_copies", lambda: None)
+        torch.manual_seed(1234)
+        m = uwr.AST(img_size=128).cuda().eval()
+        step = TrainStep(m, "L2", lr=1e-3, local_batch=2)
+        g = torch.Generator().manual_seed(3)
+        raw = (torch.rand(2, 3, 128, 128, generator=g) * 2 - 1).cuda()
+        ref = (torch.rand(2, 3, 128, 128, generator=g) * 2 - 1).cuda()
+        for _ in range(3):
+            loss, _ = step(raw, ref)
+        monkeypatch.undo()
+        return loss.item(), [p.detach().clone() for p in m.parameters()]
+
+    l0, p0 = run(False)
+    l1, p1 = run(True)
+    assert l0 == l1
+    assert all(torch.equal(a, b) for a, b in zip(p0, p1))

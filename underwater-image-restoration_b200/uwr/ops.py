@@ -225,6 +225,23 @@ def _fresh(w, tag):
     return ent, ver
 
 
+# Rounded-copy registry: every cached TF32 copy (rounded_weight / packed_qkv) is listed here so that an
+# optimizer that rewrites the parameters behind torch's back can refresh ALL of them with two multi-tensor
+# launches (refresh_rounded_copies) instead of one lazy launch per weight in the next forward (~100 tiny
+# kernels per AST step).
+_ROUNDED = {}          # id(w) -> (weakref(w), kind)
+_ROUNDED_TABLES = None  # (generation, device tables) of the last refresh
+_ROUNDED_GEN = 0
+
+
+def _register_rounded(w, kind):
+    global _ROUNDED_GEN
+    import weakref
+    if id(w) not in _ROUNDED or _ROUNDED[id(w)][0]() is not w:
+        _ROUNDED[id(w)] = (weakref.ref(w), kind)
+        _ROUNDED_GEN += 1
+
+
 def rounded_weight(w):
     """TF32-rounded copy of a weight matrix (cached on the tensor object, refreshed when the parameter
     changes); the weight itself in tf32x3 mode."""
@@ -237,7 +254,77 @@ def rounded_weight(w):
         w2 = wd.reshape(wd.shape[0], -1) if wd.dim() > 1 else wd.reshape(1, -1)   # conv weights: (C0, rest)
         scale_round(w2, w2.shape[1], out=buf.view(w2.shape))
         w._uwr_rounded = ent = (ver, buf)
+        if w.is_contiguous():
+            _register_rounded(w, "w")
     return ent[1]
+
+
+def refresh_rounded_copies():
+    """Re-round every registered TF32 weight copy in two multi-tensor launches (weights: rounded; packed
+    biases: plain copy) and mark the caches fresh.  Called by FusedClipAdam.step() right after the
+    parameter update (also inside a captured CUDA graph)."""
+    global _ROUNDED_TABLES
+    if _PASSES != 1 or not _ROUNDED:
+        return
+    live = []
+    for key, (ref, kind) in list(_ROUNDED.items()):
+        w = ref()
+        if w is None or not w.is_cuda:
+            del _ROUNDED[key]
+            continue
+        live.append((w, kind))
+    if not live:
+        return
+    dev = live[0][0].device
+    sig = (_ROUNDED_GEN, len(live))
+    if _ROUNDED_TABLES is None or _ROUNDED_TABLES[0] != sig:
+        wsrc, wdst, wn, bsrc, bdst, bn = [], [], [], [], [], []
+        for w, kind in live:
+            if kind == "w":
+                ent = getattr(w, "_uwr_rounded", None)
+                if ent is None:
+                    continue
+                wsrc.append(w.data_ptr()); wdst.append(ent[1].data_ptr()); wn.append(w.numel())
+            else:  # packed qkv: kind = (wkv, bq, bkv)
+                ent = getattr(w, "_uwr_qkv", None)
+                if ent is None:
+                    continue
+                wkv, bq, bkv = kind
+                Cq, K = w.shape
+                wsrc += [w.data_ptr(), wkv.data_ptr()]
+                wdst += [ent[1].data_ptr(), ent[1][Cq:].data_ptr()]
+                wn += [w.numel(), wkv.numel()]
+                if bq is not None:
+                    bsrc += [bq.data_ptr(), bkv.data_ptr()]
+                    bdst += [ent[2].data_ptr(), ent[2][Cq:].data_ptr()]
+                    bn += [bq.numel(), bkv.numel()]
+
+        def tables(src, dst, ns):
+            if not src:
+                return None
+            offs = [0]
+            for n in ns:
+                offs.append(offs[-1] + n)
+            i64 = lambda xs: torch.tensor(xs, dtype=torch.int64, device=dev)
+            return (i64(src), i64(dst), i64(offs), len(src), offs[-1])
+        _ROUNDED_TABLES = (sig, tables(wsrc, wdst, wn), tables(bsrc, bdst, bn))
+    _, tw, tb = _ROUNDED_TABLES
+    for t, do_round in ((tw, 1), (tb, 0)):
+        if t is not None:
+            check(fn["uwr_round_tf32_tensors"](t[0].data_ptr(), t[1].data_ptr(), t[2].data_ptr(), t[3], t[4], do_round,
+                                               _stream()), "uwr_round_tf32_tensors")
+    for w, kind in live:   # the copies now match the parameters of THIS epoch
+        if kind == "w":
+            ent = getattr(w, "_uwr_rounded", None)
+            if ent is not None:
+                w._uwr_rounded = ((w.data_ptr(), w._version, WEIGHT_EPOCH, _PASSES), ent[1])
+        else:
+            ent = getattr(w, "_uwr_qkv", None)
+            if ent is not None:
+                wkv, bq, bkv = kind
+                ver = (w.data_ptr(), w._version, WEIGHT_EPOCH, _PASSES) + (
+                    wkv.data_ptr(), wkv._version, None if bq is None else (bq._version, bkv._version))
+                w._uwr_qkv = (ver, ent[1], ent[2])
 
 
 def packed_qkv(wq, bq, wkv, bkv):
@@ -255,6 +342,8 @@ def packed_qkv(wq, bq, wkv, bkv):
             _run("uwr_scale_round", "bias", 0, 0.0, _ptr(bq.detach()), Cq, _ptr(bias), 1, Cq, None, 0, 0)
             _run("uwr_scale_round", "bias", 0, 0.0, _ptr(bkv.detach()), 2 * Cq, _ptr(bias[Cq:]), 1, 2 * Cq, None, 0, 0)
         wq._uwr_qkv = ent = (ver, buf, bias)
+        if wq.is_contiguous() and wkv.is_contiguous():
+            _register_rounded(wq, (wkv, bq, bkv))
     return ent[1], ent[2]
 
 

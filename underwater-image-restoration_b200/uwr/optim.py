@@ -69,5 +69,6 @@ class FusedClipAdam:
                                   float(self.betas[1]), float(self.eps), float(self.weight_decay),
                                   int(self.decoupled), 0, self._step_dev.data_ptr(), stream), "uwr_adam_step")
         from . import ops
-        ops.bump_weight_epoch()  # parameters changed behind torch's version counter: refresh rounded copies
+        ops.bump_weight_epoch()  # parameters changed behind torch's version counter: rounded copies are stale
+        ops.refresh_rounded_copies()  # ... and are re-rounded here, all at once (two multi-tensor launches)
         return self._norm
