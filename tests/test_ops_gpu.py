@@ -525,3 +525,27 @@ def test_mdta_channel_attention(B, L, C, heads):
     assert rel_l2(qkv.grad, qd.grad) < 2 * TOL_TF32
     assert rel_l2(kvf.grad, kd.grad) < 2 * TOL_TF32
     assert rel_l2(temp.grad, td.grad) < 2 * TOL_TF32
+
+
+@pytest.mark.parametrize("B,H,heads,shift", [(2, 16, 2, 0), (1, 32, 1, 4), (2, 24, 4, 4), (1, 64, 2, 4)])
+@pytest.mark.parametrize("sparse", [True, False])
+def test_window_attention_fwd_tcgen05_vs_mma_sync(ops, B, H, heads, shift, sparse):
+    """head_dim 32: the tcgen05/TMA forward (two windows per 128-row MMA tile) against the mma.sync kernel
+    and the fp64 oracle on the same inputs (both use 3xTF32 scores, so they agree far below TF32 level)."""
+    hd, W = 32, H
+    C = heads * hd
+    qkv = _r(B * H * W, 3 * C, seed=11)
+    table = _r(225, heads, seed=12, scale=0.5)
+    w = torch.tensor([0.3, -0.2]).cuda() if sparse else None
+    args = (qkv, 0, qkv, C, 2 * C, table, w, B, H, W, heads, hd, shift, hd ** -0.5)
+    try:
+        ops.set_attn_tcgen05(False)
+        o_ref = ops.window_attn_fwd(*args)
+        ops.set_attn_tcgen05(True)
+        o_t5 = ops.window_attn_fwd(*args)
+    finally:
+        ops.set_attn_tcgen05(True)
+    torch.cuda.synchronize()
+    ref = _attn_ref(qkv.double(), table.double(), (w if sparse else torch.zeros(2).cuda()).double(), B, H, W, heads, shift, sparse)
+    assert rel_l2(o_t5, ref) < TOL_TF32
+    assert rel_l2(o_t5, o_ref) < 3e-4

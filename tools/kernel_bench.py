@@ -81,8 +81,11 @@ if "attnb" in which or "attnf" in which:
     w = torch.ones(2, device=dev)
     tiles = B * (H // 8) ** 2 * heads
     if "attnf" in which:
-        timeit("attn fwd tiles32768 hd32", lambda: ops.window_attn_fwd(qkv, 0, qkv, C, 2 * C, table, w, B, H, H, heads, hd, 4, hd ** -0.5),
-               tiles * 4 * 64 * hd * 4, tiles * 4.0 * 64 * 64 * hd)
+        for t5 in (False, True):
+            ops.set_attn_tcgen05(t5)
+            timeit(f"attn fwd tiles32768 hd32 {'tcgen05' if t5 else 'mma.sync'}",
+                   lambda: ops.window_attn_fwd(qkv, 0, qkv, C, 2 * C, table, w, B, H, H, heads, hd, 4, hd ** -0.5),
+                   tiles * 4 * 64 * hd * 4, tiles * 4.0 * 64 * 64 * hd)
     if "attnb" in which:
         do = torch.randn(B * H * H, C, device=dev)
         dq = torch.empty_like(qkv)

@@ -9,6 +9,7 @@
 // memory.  Algorithmic HBM bytes per tile: fwd 4*64*HD*4 (q,k,v in, o out),
 // bwd 7*64*HD*4 (q,k,v,do in; dq,dk,dv out).
 #include "uwr_common.cuh"
+#include "uwr_tma.cuh"
 #include "../../include/uwr_b200.h"
 
 namespace {
@@ -541,6 +542,276 @@ __global__ void attn_param_reduce_kernel(const float* __restrict__ partials, con
     }
 }
 
+
+// ------------------------------------------------------------------------------------------
+// Forward on the 5th-generation tensor cores (head_dim 32, shift 0 or 4).
+//
+// One item = TWO windows of one head stacked to a 128-row tile, so that S = Q K^T is a single
+// M=128, N=128, K=32 tcgen05.mma tile (the two off-diagonal 64x64 blocks are never read) and
+// O = P V is one M=128, N=32, K=128 tile whose P operand is block diagonal (zeros off the diagonal).
+//   * Q / K / V rows arrive by TMA: an 8x8 window, cyclically shifted by 0 or 4, is four 4x4-pixel
+//     quadrants that never wrap, i.e. four boxes (32 ch, 4 px, 4 rows) of a 4-D (C, W, H, B) tensor map
+//     on the qkv token matrix; tokens are stored quadrant-major (a fixed permutation, undone by the
+//     bias / mask / output index arithmetic).  Q, K use SWIZZLE_128B (K-major operands), V uses
+//     SWIZZLE_128B_ATOM_32B (MN-major B operand of P V).
+//   * 3xTF32 for S: the tensor core truncates fp32 operands, so hi = the TMA tile as it is and
+//     lo = x - trunc(x) is written by the CTA into a second tile: S = Qlo Khi + Qhi Klo + Qhi Khi.
+//   * softmax + relu^2 + learned fusion: one thread per query row on its 64 TMEM columns
+//     (tcgen05.ld 32x32b), no shuffles; P (TF32-rounded) goes back to shared memory as the K-major A
+//     operand of the second MMA (it aliases the Q/K tiles, which are dead by then).
+//   * fp32 accumulators in TMEM: S in columns 0..127, O in columns 128..159 (256 allocated, 2 CTAs/SM).
+constexpr int T5A_THREADS = 128;
+constexpr int T5A_TILE = 128 * 32 * 4;  // one 128-row x 32-float operand tile
+constexpr int T5A_SMEM = 5 * T5A_TILE + 1024 /*bias table*/ + 512 /*regions*/ + 64 /*barriers, TMEM slot*/ + 1024;
+
+__device__ __forceinline__ void t5a_token(int rr, int& i, int& j) {  // quadrant-major slot -> (row, col) in the window
+    const int quad = rr >> 4;
+    i = 4 * (quad >> 1) + ((rr >> 2) & 3);
+    j = 4 * (quad & 1) + (rr & 3);
+}
+
+__global__ void __launch_bounds__(T5A_THREADS, 2)
+attn_fwd_t5_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_constant__ CUtensorMap mapK,
+                   const __grid_constant__ CUtensorMap mapV, const AttnParams p, float* __restrict__ out,
+                   long long ld_out) {
+    using namespace uwr_tma;
+    extern __shared__ uint8_t t5a_raw[];
+    uint8_t* smem = t5a_raw + ((1024u - (smem_u32(t5a_raw) & 1023u)) & 1023u);
+    uint8_t* Qhi = smem;
+    uint8_t* Khi = smem + T5A_TILE;
+    uint8_t* Qlo = smem + 2 * T5A_TILE;
+    uint8_t* Klo = smem + 3 * T5A_TILE;
+    uint8_t* Pm = smem;                       // [4 chunks of 32 K-columns][128 rows][128 B], aliases Q/K
+    uint8_t* Vs = smem + 4 * T5A_TILE;
+    float* tab = reinterpret_cast<float*>(smem + 5 * T5A_TILE);
+    int* reg = reinterpret_cast<int*>(smem + 5 * T5A_TILE + 1024);
+    uint64_t* bar_load = reinterpret_cast<uint64_t*>(smem + 5 * T5A_TILE + 1536);
+    uint64_t* bar_mma = bar_load + 1;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bar_mma + 1);
+
+    const int tid = threadIdx.x, warp = tid >> 5;
+    if (tid == 0) {
+        mbar_init(bar_load, 1);
+        mbar_init(bar_mma, 1);
+        mbar_init_fence();
+        tma_prefetch_map(&mapQ);
+        tma_prefetch_map(&mapK);
+        tma_prefetch_map(&mapV);
+    }
+    if (warp == 0) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "n"(256)
+                     : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+    const uint32_t trow = tmem_base + ((uint32_t)(warp * 32) << 16);  // this warp's 32 TMEM lanes
+
+    // instruction descriptors: D = f32, A = B = tf32, N >> 3 at bit 17, M >> 4 at bit 24; bit 16 = B is MN-major
+    constexpr uint32_t IDESC_S = (1u << 4) | (2u << 7) | (2u << 10) | ((128u >> 3) << 17) | ((128u >> 4) << 24);
+    constexpr uint32_t IDESC_O = (1u << 4) | (2u << 7) | (2u << 10) | (1u << 16) | ((32u >> 3) << 17) | ((128u >> 4) << 24);
+
+    float w0, w1;
+    fusion_weights(p.w_param, w0, w1);
+    const int win = tid >> 6, rr = tid & 63;
+    int ti, tj;
+    t5a_token(rr, ti, tj);
+    const int bias_base = (ti + WIN - 1) * (2 * WIN - 1) + tj + WIN - 1;
+
+    const int pairs = p.nW >> 1;
+    const int items = p.B * pairs * p.heads;
+    uint32_t ph_load = 0, ph_mma = 0;
+    for (int item = blockIdx.x; item < items; item += gridDim.x) {
+        const int h = item % p.heads;
+        const int pr = (item / p.heads) % pairs;
+        const int b = item / (p.heads * pairs);
+        // generic-proxy writes of the previous item (lo tiles, rounded V, P) precede the TMA writes below
+        fence_proxy_async_smem();
+        __syncthreads();
+        if (tid == 0) {
+            mbar_expect_tx(bar_load, 3 * T5A_TILE);
+#pragma unroll
+            for (int w = 0; w < 2; ++w) {
+                const int wlin = 2 * pr + w, wy = wlin / p.nWx, wx = wlin - wy * p.nWx;
+#pragma unroll
+                for (int quad = 0; quad < 4; ++quad) {
+                    int y0 = wy * WIN + p.shift + 4 * (quad >> 1), x0 = wx * WIN + p.shift + 4 * (quad & 1);
+                    if (y0 >= p.H) y0 -= p.H;
+                    if (x0 >= p.W) x0 -= p.W;
+                    const int off = (w * 64 + quad * 16) * 128;
+                    tma_load_4d(Qhi + off, &mapQ, bar_load, p.q_off + h * 32, x0, y0, b);
+                    tma_load_4d(Khi + off, &mapK, bar_load, p.k_off + h * 32, x0, y0, b);
+                    tma_load_4d(Vs + off, &mapV, bar_load, p.v_off + h * 32, x0, y0, b);
+                }
+            }
+        }
+        // per-item tables while the tiles are in flight
+        for (int i = tid; i < NBINS; i += T5A_THREADS) tab[i] = p.table[i * p.heads + h];
+        const int wlin = 2 * pr + win, wy = wlin / p.nWx, wx = wlin - wy * p.nWx;
+        const int n_nat = ti * 8 + tj;  // natural token index of this row inside its window
+        const int myreg = p.shift > 0 ? region_code(p, wy, wx, n_nat) : 0;
+        reg[tid] = myreg;
+        const bool masked = p.shift > 0 && (wy == p.H / WIN - 1 || wx == p.nWx - 1);
+        const long long orow = token_row(p, b, wy, wx, n_nat);
+
+        mbar_wait(bar_load, ph_load);
+        ph_load ^= 1;
+        // lo = x - trunc(x) for Q and K (3xTF32), V rounded to nearest in place (single-pass P V)
+        {
+            const float4* q4 = reinterpret_cast<const float4*>(Qhi);
+            const float4* k4 = reinterpret_cast<const float4*>(Khi);
+            float4* ql = reinterpret_cast<float4*>(Qlo);
+            float4* kl = reinterpret_cast<float4*>(Klo);
+            float4* v4 = reinterpret_cast<float4*>(Vs);
+#pragma unroll
+            for (int i = 0; i < T5A_TILE / 16 / T5A_THREADS; ++i) {
+                const int idx = tid + i * T5A_THREADS;
+                const float4 a = q4[idx], c = k4[idx], v = v4[idx];
+                ql[idx] = make_float4(a.x - __uint_as_float(__float_as_uint(a.x) & 0xFFFFE000u),
+                                      a.y - __uint_as_float(__float_as_uint(a.y) & 0xFFFFE000u),
+                                      a.z - __uint_as_float(__float_as_uint(a.z) & 0xFFFFE000u),
+                                      a.w - __uint_as_float(__float_as_uint(a.w) & 0xFFFFE000u));
+                kl[idx] = make_float4(c.x - __uint_as_float(__float_as_uint(c.x) & 0xFFFFE000u),
+                                      c.y - __uint_as_float(__float_as_uint(c.y) & 0xFFFFE000u),
+                                      c.z - __uint_as_float(__float_as_uint(c.z) & 0xFFFFE000u),
+                                      c.w - __uint_as_float(__float_as_uint(c.w) & 0xFFFFE000u));
+                v4[idx] = make_float4(tf32_round(v.x), tf32_round(v.y), tf32_round(v.z), tf32_round(v.w));
+            }
+        }
+        fence_proxy_async_smem();
+        tc_fence_before();
+        __syncthreads();
+        if (tid == 0) {
+            tc_fence_after();
+            const uint32_t qh = smem_u32(Qhi), kh = smem_u32(Khi), qlw = smem_u32(Qlo), klw = smem_u32(Klo);
+#pragma unroll
+            for (int pass = 0; pass < 3; ++pass) {
+                const uint32_t a = pass == 0 ? qlw : qh, bb = pass == 1 ? klw : kh;
+#pragma unroll
+                for (int k8 = 0; k8 < 4; ++k8)
+                    umma_tf32(tmem_base, make_smem_desc(a + k8 * 32, 16, 1024, 2), make_smem_desc(bb + k8 * 32, 16, 1024, 2),
+                              IDESC_S, (pass > 0 || k8 > 0) ? 1u : 0u);
+            }
+            umma_commit(bar_mma);
+        }
+        mbar_wait(bar_mma, ph_mma);
+        ph_mma ^= 1;
+        tc_fence_after();
+
+        // ---- this thread's query row: 64 scores of its own window (TMEM columns 64*win .. +63)
+        uint32_t sr[2][32];
+        tmem_ld32_issue(trow + win * 64, sr[0]);
+        tmem_ld32_issue(trow + win * 64 + 32, sr[1]);
+        tmem_ld_wait();
+        float sv[64];
+        float mx = -INFINITY;
+#pragma unroll
+        for (int m = 0; m < 64; ++m) {
+            int im, jm;
+            t5a_token(m, im, jm);
+            float v = __uint_as_float(sr[m >> 5][m & 31]) * p.scale + tab[bias_base - (im * (2 * WIN - 1) + jm)];
+            if (masked && reg[win * 64 + m] != myreg) v += -100.0f;
+            sv[m] = v;
+            mx = fmaxf(mx, v);
+        }
+        float sum = 0.f;
+        float pe[64];
+#pragma unroll
+        for (int m = 0; m < 64; ++m) {
+            pe[m] = ex2_ftz((sv[m] - mx) * 1.4426950408889634f);
+            sum += pe[m];
+        }
+        const float inv = __fdividef(1.0f, sum) * w0;
+        // ---- P = w0 softmax + w1 relu^2, TF32-rounded, into the K-major A tile (128B swizzle), zeros off the diagonal
+        {
+            const int sw = tid & 7;
+            uint8_t* prow = Pm + tid * 128;
+#pragma unroll
+            for (int kc = 0; kc < 4; ++kc) {
+                const bool mine = (kc >> 1) == win;
+#pragma unroll
+                for (int c = 0; c < 8; ++c) {
+                    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+                    if (mine) {
+                        float e[4];
+#pragma unroll
+                        for (int q = 0; q < 4; ++q) {
+                            const int m = (kc & 1) * 32 + c * 4 + q;
+                            const float r = fmaxf(sv[m], 0.f);
+                            e[q] = tf32_round(pe[m] * inv + w1 * r * r);
+                        }
+                        v = make_float4(e[0], e[1], e[2], e[3]);
+                    }
+                    *reinterpret_cast<float4*>(prow + kc * T5A_TILE + ((c ^ sw) << 4)) = v;
+                }
+            }
+        }
+        fence_proxy_async_smem();
+        tc_fence_before();
+        __syncthreads();
+        if (tid == 0) {
+            tc_fence_after();
+            const uint32_t pa = smem_u32(Pm), vb = smem_u32(Vs);
+#pragma unroll
+            for (int k8 = 0; k8 < 16; ++k8)
+                umma_tf32(tmem_base + 128, make_smem_desc(pa + (k8 >> 2) * T5A_TILE + (k8 & 3) * 32, 16, 1024, 2),
+                          make_smem_desc(vb + k8 * 1024, 4096, 512, 1), IDESC_O, k8 > 0 ? 1u : 0u);
+            umma_commit(bar_mma);
+        }
+        mbar_wait(bar_mma, ph_mma);
+        ph_mma ^= 1;
+        tc_fence_after();
+        uint32_t orr[32];
+        tmem_ld32_issue(trow + 128, orr);
+        tmem_ld_wait();
+        float* op = out + orow * ld_out + h * 32;
+#pragma unroll
+        for (int c = 0; c < 8; ++c) {
+            float4 v = make_float4(__uint_as_float(orr[4 * c]), __uint_as_float(orr[4 * c + 1]),
+                                   __uint_as_float(orr[4 * c + 2]), __uint_as_float(orr[4 * c + 3]));
+            if (p.rnd) v = make_float4(tf32_round(v.x), tf32_round(v.y), tf32_round(v.z), tf32_round(v.w));
+            *reinterpret_cast<float4*>(op + 4 * c) = v;
+        }
+        tc_fence_before();
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 0) {
+        tc_fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(256) : "memory");
+    }
+}
+
+int g_attn_t5 = 1;  // uwr_set_attn_tcgen05
+
+int launch_fwd_t5(const AttnParams& p, float* out, long long ld_out, cudaStream_t stream) {
+    CUtensorMap mq, mk, mv;
+    const int box[4] = {32, 4, 4, 1};
+    {
+        const long long dims[4] = {p.ld_q, p.W, p.H, p.B};
+        const long long str[3] = {p.ld_q, (long long)p.W * p.ld_q, (long long)p.H * p.W * p.ld_q};
+        if (uwr_tma::encode_f32(&mq, p.q, 4, dims, str, box, CU_TENSOR_MAP_SWIZZLE_128B)) return -3;
+    }
+    {
+        const long long dims[4] = {p.ld_kv, p.W, p.H, p.B};
+        const long long str[3] = {p.ld_kv, (long long)p.W * p.ld_kv, (long long)p.H * p.W * p.ld_kv};
+        if (uwr_tma::encode_f32(&mk, p.kv, 4, dims, str, box, CU_TENSOR_MAP_SWIZZLE_128B)) return -3;
+        if (uwr_tma::encode_f32(&mv, p.kv, 4, dims, str, box, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B)) return -3;
+    }
+    static bool configured = false;
+    if (!configured) {
+        UWR_CUDA(cudaFuncSetAttribute(attn_fwd_t5_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, T5A_SMEM));
+        configured = true;
+    }
+    const long long items = (long long)p.B * (p.nW / 2) * p.heads;
+    const int grid = (int)(items < 2LL * uwr_sm_count() ? items : 2LL * uwr_sm_count());
+    attn_fwd_t5_kernel<<<grid, T5A_THREADS, T5A_SMEM, stream>>>(mq, mk, mv, p, out, ld_out);
+    UWR_CHECK_LAUNCH("attn_fwd_t5_kernel");
+    return 0;
+}
+
 int bwd_ctas_per_head(const uwr_attn_desc* d) {
     const int tiles = d->B * (d->H / WIN) * (d->W / WIN);
     int c = (3 * uwr_sm_count() + d->heads - 1) / d->heads;
@@ -606,6 +877,10 @@ extern "C" int uwr_window_attn_fwd(const uwr_attn_desc* d, float* out, long long
     AttnParams p;
     if (int rc = fill_params(d, p, "uwr_window_attn_fwd")) return rc;
     UWR_REQUIRE(out && ld_out % 2 == 0, "uwr_window_attn_fwd: bad output");
+    // tcgen05 / TMA path: two windows per 128-row MMA tile
+    if (g_attn_t5 && d->head_dim == 32 && (d->shift == 0 || d->shift == 4) && p.nW % 2 == 0 && ld_out % 4 == 0 &&
+        (((uintptr_t)d->q | (uintptr_t)d->kv | (uintptr_t)out) & 15) == 0)
+        return launch_fwd_t5(p, out, ld_out, stream);
     switch (d->head_dim) {
         case 8: return launch_fwd<8>(p, out, ld_out, stream);
         case 16: return launch_fwd<16>(p, out, ld_out, stream);
@@ -615,6 +890,11 @@ extern "C" int uwr_window_attn_fwd(const uwr_attn_desc* d, float* out, long long
     }
     uwr_set_error("uwr_window_attn_fwd: head_dim %d unsupported (8,16,32,64,128)", d->head_dim);
     return -1;
+}
+
+extern "C" int uwr_set_attn_tcgen05(int on) {
+    g_attn_t5 = on ? 1 : 0;
+    return 0;
 }
 
 extern "C" size_t uwr_window_attn_bwd_workspace_bytes(const uwr_attn_desc* d) {

@@ -82,6 +82,7 @@ SIGNATURES = {
     "uwr_window_attn_bwd": (c_int, [C.POINTER(AttnDesc), c_fp, c_ll, c_fp, c_fp, c_fp, c_fp, c_fp, c_stream]),
     "uwr_dwconv_gelu_fwd": (c_int, [c_fp, c_ll, c_fp, c_fp, c_fp, c_fp, c_int, c_int, c_int, c_int, c_int, c_int,
                                     c_stream]),
+    "uwr_set_attn_tcgen05": (c_int, [c_int]),
     "uwr_gelu_mul_fwd": (c_int, [c_fp, c_ll, c_fp, c_ll, c_int, c_stream]),
     "uwr_gelu_mul_bwd": (c_int, [c_fp, c_fp, c_ll, c_fp, c_ll, c_int, c_stream]),
     "uwr_dwconv_gelu_bwd_workspace_bytes": (c_sz, [c_int, c_int, c_int, c_int]),

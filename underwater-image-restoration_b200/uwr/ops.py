@@ -29,6 +29,11 @@ def set_gemm_precision(mode):
     check(fn["uwr_set_gemm_precision"](_PASSES), "uwr_set_gemm_precision")
 
 
+def set_attn_tcgen05(on):
+    """window attention forward (head_dim 32): tcgen05/TMA kernel (default) or the mma.sync kernel."""
+    check(fn["uwr_set_attn_tcgen05"](int(bool(on))), "uwr_set_attn_tcgen05")
+
+
 def fast_path():
     return _PASSES == 1
 
