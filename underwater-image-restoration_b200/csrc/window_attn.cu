@@ -548,7 +548,9 @@ __global__ void attn_param_reduce_kernel(const float* __restrict__ partials, con
 //
 // One item = TWO windows of one head stacked to a 128-row tile, so that S = Q K^T is a single
 // M=128, N=128, K=32 tcgen05.mma tile (the two off-diagonal 64x64 blocks are never read) and
-// O = P V is one M=128, N=32, K=128 tile whose P operand is block diagonal (zeros off the diagonal).
+// O = P V is two M=128, N=32, K=64 tiles, D_w = P V_w, of which window w's 64 rows are read.
+// The next item's Q/K/V tiles are requested as soon as S sits in TMEM, i.e. they land under the
+// softmax / P V / store of the current item.
 //   * Q / K / V rows arrive by TMA: an 8x8 window, cyclically shifted by 0 or 4, is four 4x4-pixel
 //     quadrants that never wrap, i.e. four boxes (32 ch, 4 px, 4 rows) of a 4-D (C, W, H, B) tensor map
 //     on the qkv token matrix; tokens are stored quadrant-major (a fixed permutation, undone by the
@@ -562,12 +564,35 @@ __global__ void attn_param_reduce_kernel(const float* __restrict__ partials, con
 //   * fp32 accumulators in TMEM: S in columns 0..127, O in columns 128..159 (256 allocated, 2 CTAs/SM).
 constexpr int T5A_THREADS = 128;
 constexpr int T5A_TILE = 128 * 32 * 4;  // one 128-row x 32-float operand tile
-constexpr int T5A_SMEM = 5 * T5A_TILE + 1024 /*bias table*/ + 512 /*regions*/ + 64 /*barriers, TMEM slot*/ + 1024;
+constexpr int T5A_SMEM = 6 * T5A_TILE + 1024 /*bias table*/ + 512 /*regions*/ + 64 /*barriers, TMEM slot*/ + 1024;
 
 __device__ __forceinline__ void t5a_token(int rr, int& i, int& j) {  // quadrant-major slot -> (row, col) in the window
     const int quad = rr >> 4;
     i = 4 * (quad >> 1) + ((rr >> 2) & 3);
     j = 4 * (quad & 1) + (rr & 3);
+}
+
+// the 24 quadrant boxes (2 windows x 4 quadrants x {Q, K, V}) of one item, one per lane of warp 0
+__device__ __forceinline__ void t5a_issue_loads(const AttnParams& p, const CUtensorMap* mapQ, const CUtensorMap* mapK,
+                                                const CUtensorMap* mapV, uint8_t* Qhi, uint8_t* Khi, uint8_t* Vs,
+                                                uint64_t* bar, int item, int pairs, int lane) {
+    using namespace uwr_tma;
+    if (lane == 0) mbar_expect_tx(bar, 3 * T5A_TILE);
+    __syncwarp();
+    if (lane < 24) {
+        const int h = item % p.heads;
+        const int pr = (item / p.heads) % pairs;
+        const int b = item / (p.heads * pairs);
+        const int which = lane % 3, quad = (lane / 3) & 3, w = lane / 12;
+        const int wlin = 2 * pr + w, wy = wlin / p.nWx, wx = wlin - wy * p.nWx;
+        int y0 = wy * WIN + p.shift + 4 * (quad >> 1), x0 = wx * WIN + p.shift + 4 * (quad & 1);
+        if (y0 >= p.H) y0 -= p.H;
+        if (x0 >= p.W) x0 -= p.W;
+        const int off = (w * 64 + quad * 16) * 128;
+        if (which == 0) tma_load_4d(Qhi + off, mapQ, bar, p.q_off + h * 32, x0, y0, b);
+        else if (which == 1) tma_load_4d(Khi + off, mapK, bar, p.k_off + h * 32, x0, y0, b);
+        else tma_load_4d(Vs + off, mapV, bar, p.v_off + h * 32, x0, y0, b);
+    }
 }
 
 __global__ void __launch_bounds__(T5A_THREADS, 2)
@@ -581,15 +606,15 @@ attn_fwd_t5_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_consta
     uint8_t* Khi = smem + T5A_TILE;
     uint8_t* Qlo = smem + 2 * T5A_TILE;
     uint8_t* Klo = smem + 3 * T5A_TILE;
-    uint8_t* Pm = smem;                       // [4 chunks of 32 K-columns][128 rows][128 B], aliases Q/K
-    uint8_t* Vs = smem + 4 * T5A_TILE;
-    float* tab = reinterpret_cast<float*>(smem + 5 * T5A_TILE);
-    int* reg = reinterpret_cast<int*>(smem + 5 * T5A_TILE + 1024);
-    uint64_t* bar_load = reinterpret_cast<uint64_t*>(smem + 5 * T5A_TILE + 1536);
+    uint8_t* Pm = Qlo;                        // compact P: [2 chunks of 32 K-columns][128 rows][128 B], aliases Qlo|Klo
+    uint8_t* Vbuf = smem + 4 * T5A_TILE;      // two V tiles (the next item's V lands while this one's P V runs)
+    float* tab = reinterpret_cast<float*>(smem + 6 * T5A_TILE);
+    int* reg = reinterpret_cast<int*>(smem + 6 * T5A_TILE + 1024);
+    uint64_t* bar_load = reinterpret_cast<uint64_t*>(smem + 6 * T5A_TILE + 1536);
     uint64_t* bar_mma = bar_load + 1;
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bar_mma + 1);
 
-    const int tid = threadIdx.x, warp = tid >> 5;
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     if (tid == 0) {
         mbar_init(bar_load, 1);
         mbar_init(bar_mma, 1);
@@ -619,38 +644,22 @@ attn_fwd_t5_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_consta
     int ti, tj;
     t5a_token(rr, ti, tj);
     const int bias_base = (ti + WIN - 1) * (2 * WIN - 1) + tj + WIN - 1;
+    const int n_nat = ti * 8 + tj;  // natural token index of this row inside its window
 
     const int pairs = p.nW >> 1;
     const int items = p.B * pairs * p.heads;
     uint32_t ph_load = 0, ph_mma = 0;
-    for (int item = blockIdx.x; item < items; item += gridDim.x) {
+    if (warp == 0 && (int)blockIdx.x < items)
+        t5a_issue_loads(p, &mapQ, &mapK, &mapV, Qhi, Khi, Vbuf, bar_load, blockIdx.x, pairs, lane);
+    int vb = 0;
+    for (int item = blockIdx.x; item < items; item += gridDim.x, vb ^= 1) {
         const int h = item % p.heads;
         const int pr = (item / p.heads) % pairs;
         const int b = item / (p.heads * pairs);
-        // generic-proxy writes of the previous item (lo tiles, rounded V, P) precede the TMA writes below
-        fence_proxy_async_smem();
-        __syncthreads();
-        if (tid == 0) {
-            mbar_expect_tx(bar_load, 3 * T5A_TILE);
-#pragma unroll
-            for (int w = 0; w < 2; ++w) {
-                const int wlin = 2 * pr + w, wy = wlin / p.nWx, wx = wlin - wy * p.nWx;
-#pragma unroll
-                for (int quad = 0; quad < 4; ++quad) {
-                    int y0 = wy * WIN + p.shift + 4 * (quad >> 1), x0 = wx * WIN + p.shift + 4 * (quad & 1);
-                    if (y0 >= p.H) y0 -= p.H;
-                    if (x0 >= p.W) x0 -= p.W;
-                    const int off = (w * 64 + quad * 16) * 128;
-                    tma_load_4d(Qhi + off, &mapQ, bar_load, p.q_off + h * 32, x0, y0, b);
-                    tma_load_4d(Khi + off, &mapK, bar_load, p.k_off + h * 32, x0, y0, b);
-                    tma_load_4d(Vs + off, &mapV, bar_load, p.v_off + h * 32, x0, y0, b);
-                }
-            }
-        }
-        // per-item tables while the tiles are in flight
+        uint8_t* Vs = Vbuf + vb * T5A_TILE;
+        // per-item tables (the previous item's readers are past their last barrier)
         for (int i = tid; i < NBINS; i += T5A_THREADS) tab[i] = p.table[i * p.heads + h];
         const int wlin = 2 * pr + win, wy = wlin / p.nWx, wx = wlin - wy * p.nWx;
-        const int n_nat = ti * 8 + tj;  // natural token index of this row inside its window
         const int myreg = p.shift > 0 ? region_code(p, wy, wx, n_nat) : 0;
         reg[tid] = myreg;
         const bool masked = p.shift > 0 && (wy == p.H / WIN - 1 || wx == p.nWx - 1);
@@ -699,6 +708,10 @@ attn_fwd_t5_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_consta
         mbar_wait(bar_mma, ph_mma);
         ph_mma ^= 1;
         tc_fence_after();
+        // S is in TMEM: the Q/K tiles are dead -> the next item's tiles (and its V, into the other buffer) start now
+        if (warp == 0 && item + (int)gridDim.x < items)
+            t5a_issue_loads(p, &mapQ, &mapK, &mapV, Qhi, Khi, Vbuf + (vb ^ 1) * T5A_TILE, bar_load, item + gridDim.x, pairs,
+                            lane);
 
         // ---- this thread's query row: 64 scores of its own window (TMEM columns 64*win .. +63)
         uint32_t sr[2][32];
@@ -724,47 +737,44 @@ attn_fwd_t5_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_consta
             sum += pe[m];
         }
         const float inv = __fdividef(1.0f, sum) * w0;
-        // ---- P = w0 softmax + w1 relu^2, TF32-rounded, into the K-major A tile (128B swizzle), zeros off the diagonal
+        // ---- P = w0 softmax + w1 relu^2, TF32-rounded, into the compact K-major A tile (128B swizzle): row r
+        // holds the 64 probabilities of ITS window; the product with the other window's V is never read
         {
             const int sw = tid & 7;
             uint8_t* prow = Pm + tid * 128;
 #pragma unroll
-            for (int kc = 0; kc < 4; ++kc) {
-                const bool mine = (kc >> 1) == win;
+            for (int kc = 0; kc < 2; ++kc)
 #pragma unroll
                 for (int c = 0; c < 8; ++c) {
-                    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-                    if (mine) {
-                        float e[4];
+                    float e[4];
 #pragma unroll
-                        for (int q = 0; q < 4; ++q) {
-                            const int m = (kc & 1) * 32 + c * 4 + q;
-                            const float r = fmaxf(sv[m], 0.f);
-                            e[q] = tf32_round(pe[m] * inv + w1 * r * r);
-                        }
-                        v = make_float4(e[0], e[1], e[2], e[3]);
+                    for (int q = 0; q < 4; ++q) {
+                        const int m = kc * 32 + c * 4 + q;
+                        const float r = fmaxf(sv[m], 0.f);
+                        e[q] = tf32_round(pe[m] * inv + w1 * r * r);
                     }
-                    *reinterpret_cast<float4*>(prow + kc * T5A_TILE + ((c ^ sw) << 4)) = v;
+                    *reinterpret_cast<float4*>(prow + kc * T5A_TILE + ((c ^ sw) << 4)) = make_float4(e[0], e[1], e[2], e[3]);
                 }
-            }
         }
         fence_proxy_async_smem();
         tc_fence_before();
         __syncthreads();
         if (tid == 0) {
             tc_fence_after();
-            const uint32_t pa = smem_u32(Pm), vb = smem_u32(Vs);
+            const uint32_t pa = smem_u32(Pm), vbase = smem_u32(Vs);
 #pragma unroll
-            for (int k8 = 0; k8 < 16; ++k8)
-                umma_tf32(tmem_base + 128, make_smem_desc(pa + (k8 >> 2) * T5A_TILE + (k8 & 3) * 32, 16, 1024, 2),
-                          make_smem_desc(vb + k8 * 1024, 4096, 512, 1), IDESC_O, k8 > 0 ? 1u : 0u);
+            for (int w = 0; w < 2; ++w)  // D_w = P (128 x 64) V_w (64 x 32): rows of window w are the valid ones
+#pragma unroll
+                for (int k8 = 0; k8 < 8; ++k8)
+                    umma_tf32(tmem_base + 128 + 32 * w, make_smem_desc(pa + (k8 >> 2) * T5A_TILE + (k8 & 3) * 32, 16, 1024, 2),
+                              make_smem_desc(vbase + w * 8192 + k8 * 1024, 4096, 512, 1), IDESC_O, k8 > 0 ? 1u : 0u);
             umma_commit(bar_mma);
         }
         mbar_wait(bar_mma, ph_mma);
         ph_mma ^= 1;
         tc_fence_after();
         uint32_t orr[32];
-        tmem_ld32_issue(trow + 128, orr);
+        tmem_ld32_issue(trow + 128 + 32 * win, orr);
         tmem_ld_wait();
         float* op = out + orow * ld_out + h * 32;
 #pragma unroll
@@ -775,6 +785,7 @@ attn_fwd_t5_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_consta
             *reinterpret_cast<float4*>(op + 4 * c) = v;
         }
         tc_fence_before();
+        __syncthreads();  // every warp has read its TMEM rows / tables before the next item overwrites them
     }
     tc_fence_before();
     __syncthreads();
