@@ -127,6 +127,16 @@ def test_ast_mlp_eval_128():
     _run(1, 128, 128, False, [], token_mlp="mlp")
 
 
+def test_ast_train_128_tcgen05_attention():
+    """whole AST (forward through the tcgen05/TMA window-attention kernel, mma.sync backward) vs the oracle"""
+    from uwr import ops
+    ops.set_attn_tcgen05(True)
+    try:
+        _run(2, 128, 128, True, [])
+    finally:
+        ops.set_attn_tcgen05(False)
+
+
 def test_ast_eval_256():
     _run(1, 256, 256, False, [])
 

@@ -527,7 +527,7 @@ def test_mdta_channel_attention(B, L, C, heads):
     assert rel_l2(temp.grad, td.grad) < 2 * TOL_TF32
 
 
-@pytest.mark.parametrize("B,H,heads,shift", [(2, 16, 2, 0), (1, 32, 1, 4), (2, 24, 4, 4), (1, 64, 2, 4)])
+@pytest.mark.parametrize("B,H,heads,shift", [(2, 16, 2, 0), (1, 32, 1, 4), (2, 48, 4, 4), (1, 64, 2, 4)])
 @pytest.mark.parametrize("sparse", [True, False])
 def test_window_attention_fwd_tcgen05_vs_mma_sync(ops, B, H, heads, shift, sparse):
     """head_dim 32: the tcgen05/TMA forward (two windows per 128-row MMA tile) against the mma.sync kernel
@@ -544,8 +544,9 @@ def test_window_attention_fwd_tcgen05_vs_mma_sync(ops, B, H, heads, shift, spars
         ops.set_attn_tcgen05(True)
         o_t5 = ops.window_attn_fwd(*args)
     finally:
-        ops.set_attn_tcgen05(True)
+        ops.set_attn_tcgen05(False)   # library default
     torch.cuda.synchronize()
     ref = _attn_ref(qkv.double(), table.double(), (w if sparse else torch.zeros(2).cuda()).double(), B, H, W, heads, shift, sparse)
     assert rel_l2(o_t5, ref) < TOL_TF32
     assert rel_l2(o_t5, o_ref) < 3e-4
+    assert not torch.equal(o_t5, o_ref)   # two different kernels did run

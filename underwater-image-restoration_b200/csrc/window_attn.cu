@@ -795,7 +795,11 @@ attn_fwd_t5_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_consta
     }
 }
 
-int g_attn_t5 = 1;  // uwr_set_attn_tcgen05
+// uwr_set_attn_tcgen05.  Off by default: measured on B200 (32 768 tiles, head_dim 32) the tcgen05 kernel takes
+// 0.42 ms against 0.31 ms for the mma.sync kernel — each item is one serial chain TMA -> lo split -> MMA -> softmax ->
+// MMA -> store and only two items fit an SM (256 TMEM columns, 97 KB smem each), so it is latency-bound
+// (ncu: issue 26 %, tensor pipe 15 %, a quarter of the samples in mbarrier waits).  See DESIGN.md §8.
+int g_attn_t5 = 0;
 
 int launch_fwd_t5(const AttnParams& p, float* out, long long ld_out, cudaStream_t stream) {
     CUtensorMap mq, mk, mv;

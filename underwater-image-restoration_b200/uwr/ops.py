@@ -30,7 +30,7 @@ def set_gemm_precision(mode):
 
 
 def set_attn_tcgen05(on):
-    """window attention forward (head_dim 32): tcgen05/TMA kernel (default) or the mma.sync kernel."""
+    """window attention forward (head_dim 32): tcgen05/TMA kernel, or the (currently faster, default) mma.sync kernel."""
     check(fn["uwr_set_attn_tcgen05"](int(bool(on))), "uwr_set_attn_tcgen05")
 
 
