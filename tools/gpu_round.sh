@@ -12,8 +12,8 @@ python bench.py --impl reference --steps 3 --warmup 1 > gpurun_out/bench_ref_$TA
 python bench.py --steps 2 --warmup 3 --no-cpu-baseline --no-graph > gpurun_out/plain_launch_$TAG.log 2>&1 &&
 ncu --metrics gpu__time_duration.sum --clock-control none -s 3500 -c 1100 --csv --log-file gpurun_out/launches_$TAG.csv \
     python bench.py --steps 2 --warmup 3 --no-cpu-baseline --no-graph > gpurun_out/ncu_launch_$TAG.log 2>&1
-python tools/kernel_bench.py t5nn dwf dwb attnf attnb lnb fft > gpurun_out/plain_kb_$TAG.log 2>&1 &&
-UWR_KB_REPS=1 ncu --set full --clock-control none -k regex:"gemm_tcgen05|dwconv_.wd|attn_.wd|ln_.wd|fft_pass2" -c 16 \
+python tools/kernel_bench.py t5nn t5nt t5tn dwf dwb attnf attnb lnb fft > gpurun_out/plain_kb_$TAG.log 2>&1 &&
+UWR_KB_REPS=1 ncu --set full --clock-control none -k regex:"gemm_tcgen05|dwconv_.wd|attn_|ln_.wd|fft_pass2" -c 18 \
     -o gpurun_out/ncu_top_$TAG python tools/kernel_bench.py t5nn dwf dwb attnf attnb lnb fft > gpurun_out/ncu_kb_$TAG.log 2>&1
 cat gpurun_out/plain_kb_$TAG.log
 UWR_PROFILE_OUT=gpurun_out/prof_spectral_$TAG.json python tools/train_bench.py SpectralTransformer L1withColor 8 > gpurun_out/train_spectral_$TAG.log 2>&1; tail -1 gpurun_out/train_spectral_$TAG.log

@@ -562,6 +562,15 @@ __global__ void attn_param_reduce_kernel(const float* __restrict__ partials, con
 //     (tcgen05.ld 32x32b), no shuffles; P (TF32-rounded) goes back to shared memory as the K-major A
 //     operand of the second MMA (it aliases the Q/K tiles, which are dead by then).
 //   * fp32 accumulators in TMEM: S in columns 0..127, O in columns 128..159 (256 allocated, 2 CTAs/SM).
+#ifdef T5A_TIMING
+__device__ long long t5a_dbg[16];
+#define T5A_STAMP(k)                                                     \
+    do {                                                                 \
+        if (threadIdx.x == 0 && blockIdx.x == 0 && item_no == 3) t5a_dbg[k] = clock64(); \
+    } while (0)
+#else
+#define T5A_STAMP(k)
+#endif
 constexpr int T5A_THREADS = 128;
 constexpr int T5A_TILE = 128 * 32 * 4;  // one 128-row x 32-float operand tile
 constexpr int T5A_SMEM = 6 * T5A_TILE + 1024 /*bias table*/ + 512 /*regions*/ + 64 /*barriers, TMEM slot*/ + 1024;
@@ -652,7 +661,9 @@ attn_fwd_t5_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_consta
     if (warp == 0 && (int)blockIdx.x < items)
         t5a_issue_loads(p, &mapQ, &mapK, &mapV, Qhi, Khi, Vbuf, bar_load, blockIdx.x, pairs, lane);
     int vb = 0;
-    for (int item = blockIdx.x; item < items; item += gridDim.x, vb ^= 1) {
+    int item_no = 0;
+    for (int item = blockIdx.x; item < items; item += gridDim.x, vb ^= 1, ++item_no) {
+        T5A_STAMP(0);
         const int h = item % p.heads;
         const int pr = (item / p.heads) % pairs;
         const int b = item / (p.heads * pairs);
@@ -667,6 +678,7 @@ attn_fwd_t5_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_consta
 
         mbar_wait(bar_load, ph_load);
         ph_load ^= 1;
+        T5A_STAMP(1);
         // lo = x - trunc(x) for Q and K (3xTF32), V rounded to nearest in place (single-pass P V)
         {
             const float4* q4 = reinterpret_cast<const float4*>(Qhi);
@@ -692,6 +704,7 @@ attn_fwd_t5_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_consta
         fence_proxy_async_smem();
         tc_fence_before();
         __syncthreads();
+        T5A_STAMP(2);
         if (tid == 0) {
             tc_fence_after();
             const uint32_t qh = smem_u32(Qhi), kh = smem_u32(Khi), qlw = smem_u32(Qlo), klw = smem_u32(Klo);
@@ -708,6 +721,7 @@ attn_fwd_t5_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_consta
         mbar_wait(bar_mma, ph_mma);
         ph_mma ^= 1;
         tc_fence_after();
+        T5A_STAMP(3);
         // S is in TMEM: the Q/K tiles are dead -> the next item's tiles (and its V, into the other buffer) start now
         if (warp == 0 && item + (int)gridDim.x < items)
             t5a_issue_loads(p, &mapQ, &mapK, &mapV, Qhi, Khi, Vbuf + (vb ^ 1) * T5A_TILE, bar_load, item + gridDim.x, pairs,
@@ -759,6 +773,7 @@ attn_fwd_t5_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_consta
         fence_proxy_async_smem();
         tc_fence_before();
         __syncthreads();
+        T5A_STAMP(4);
         if (tid == 0) {
             tc_fence_after();
             const uint32_t pa = smem_u32(Pm), vbase = smem_u32(Vs);
@@ -773,6 +788,7 @@ attn_fwd_t5_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_consta
         mbar_wait(bar_mma, ph_mma);
         ph_mma ^= 1;
         tc_fence_after();
+        T5A_STAMP(5);
         uint32_t orr[32];
         tmem_ld32_issue(trow + 128 + 32 * win, orr);
         tmem_ld_wait();
@@ -786,6 +802,7 @@ attn_fwd_t5_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_consta
         }
         tc_fence_before();
         __syncthreads();  // every warp has read its TMEM rows / tables before the next item overwrites them
+        T5A_STAMP(6);
     }
     tc_fence_before();
     __syncthreads();
@@ -906,6 +923,12 @@ extern "C" int uwr_window_attn_fwd(const uwr_attn_desc* d, float* out, long long
     uwr_set_error("uwr_window_attn_fwd: head_dim %d unsupported (8,16,32,64,128)", d->head_dim);
     return -1;
 }
+
+#ifdef T5A_TIMING
+extern "C" int uwr_attn_t5_debug(long long* host_out) {
+    return cudaMemcpyFromSymbol(host_out, t5a_dbg, sizeof(long long) * 16) == cudaSuccess ? 0 : -2;
+}
+#endif
 
 extern "C" int uwr_set_attn_tcgen05(int on) {
     g_attn_t5 = on ? 1 : 0;

@@ -7,7 +7,7 @@ import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "..", "csrc", "libuwr_b200.so")
-LIB_PATH = os.path.normpath(LIB_PATH)
+LIB_PATH = os.path.normpath(os.environ.get("UWR_B200_LIB", LIB_PATH))  # override: instrumented debug builds only
 
 if not os.path.exists(LIB_PATH):
     raise ImportError(
