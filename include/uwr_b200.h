@@ -140,7 +140,7 @@ typedef struct {
 int uwr_window_attn_fwd(const uwr_attn_desc* d, float* out, long long ld_out, uwr_stream_t stream);
 /* head_dim 32 and shift in {0, 4}: uwr_set_attn_tcgen05(1) runs the forward on tcgen05 tensor cores (two
  * windows per 128-row MMA tile, Q/K/V by TMA, scores/outputs in TMEM).  Default 0 = the mma.sync kernel,
- * which is still faster on B200 (0.31 vs 0.42 ms at 32 768 tiles); both are parity-tested. */
+ * which is still faster on B200 (0.31 vs 0.34 ms at 32 768 tiles); both are parity-tested. */
 int uwr_set_attn_tcgen05(int on);
 size_t uwr_window_attn_bwd_workspace_bytes(const uwr_attn_desc* d);
 /* dq/dk/dv are written with the same (ld, offset) addressing as q/k/v into dq_buf/dkv_buf.

@@ -571,9 +571,16 @@ __device__ long long t5a_dbg[16];
 #else
 #define T5A_STAMP(k)
 #endif
-constexpr int T5A_THREADS = 128;
-constexpr int T5A_TILE = 128 * 32 * 4;  // one 128-row x 32-float operand tile
-constexpr int T5A_SMEM = 6 * T5A_TILE + 1024 /*bias table*/ + 512 /*regions*/ + 64 /*barriers, TMEM slot*/ + 1024;
+constexpr int T5A_THREADS = 256;          // two threads per query row (32 score columns each)
+constexpr int T5A_TILE = 128 * 32 * 4;    // one 128-row x 32-float operand tile
+constexpr int T5A_MAXH = 16;              // heads whose bias tables are cached per CTA (C <= 512 at head_dim 32)
+// dynamic shared memory: 6 operand tiles + bias tables of `heads` heads + regions + row max/sum exchange + barriers
+// (+ 1 KB alignment slack): 108.6 KB at 8 heads -> two CTAs per SM (the 232 448-byte limit is tight: the table
+// region is sized by the actual head count)
+__host__ __device__ constexpr int t5a_tab_bytes(int heads) { return ((heads * 228 * 4 + 127) / 128) * 128; }
+__host__ __device__ constexpr int t5a_smem_bytes(int heads) {
+    return 6 * T5A_TILE + t5a_tab_bytes(heads) + 512 + 2048 + 64 + 1024;
+}
 
 __device__ __forceinline__ void t5a_token(int rr, int& i, int& j) {  // quadrant-major slot -> (row, col) in the window
     const int quad = rr >> 4;
@@ -617,9 +624,11 @@ attn_fwd_t5_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_consta
     uint8_t* Klo = smem + 3 * T5A_TILE;
     uint8_t* Pm = Qlo;                        // compact P: [2 chunks of 32 K-columns][128 rows][128 B], aliases Qlo|Klo
     uint8_t* Vbuf = smem + 4 * T5A_TILE;      // two V tiles (the next item's V lands while this one's P V runs)
-    float* tab = reinterpret_cast<float*>(smem + 6 * T5A_TILE);
-    int* reg = reinterpret_cast<int*>(smem + 6 * T5A_TILE + 1024);
-    uint64_t* bar_load = reinterpret_cast<uint64_t*>(smem + 6 * T5A_TILE + 1536);
+    float* tabs = reinterpret_cast<float*>(smem + 6 * T5A_TILE);   // [heads][228] relative-position bias tables
+    const int tab_bytes = t5a_tab_bytes(p.heads);
+    int* reg = reinterpret_cast<int*>(smem + 6 * T5A_TILE + tab_bytes);
+    float* xch = reinterpret_cast<float*>(smem + 6 * T5A_TILE + tab_bytes + 512);   // [2 (max | sum)][2 halves][128 rows]
+    uint64_t* bar_load = reinterpret_cast<uint64_t*>(smem + 6 * T5A_TILE + tab_bytes + 512 + 2048);
     uint64_t* bar_mma = bar_load + 1;
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bar_mma + 1);
 
@@ -637,11 +646,15 @@ attn_fwd_t5_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_consta
                      : "memory");
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
     }
+    for (int i = tid; i < p.heads * NBINS; i += T5A_THREADS) {   // table is (225, heads) in global memory
+        const int bin = i / p.heads, hh = i - bin * p.heads;
+        tabs[hh * 228 + bin] = p.table[i];
+    }
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
-    const uint32_t trow = tmem_base + ((uint32_t)(warp * 32) << 16);  // this warp's 32 TMEM lanes
+    const uint32_t trow = tmem_base + ((uint32_t)((warp & 3) * 32) << 16);  // this warp's 32 TMEM lanes
 
     // instruction descriptors: D = f32, A = B = tf32, N >> 3 at bit 17, M >> 4 at bit 24; bit 16 = B is MN-major
     constexpr uint32_t IDESC_S = (1u << 4) | (2u << 7) | (2u << 10) | ((128u >> 3) << 17) | ((128u >> 4) << 24);
@@ -649,7 +662,8 @@ attn_fwd_t5_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_consta
 
     float w0, w1;
     fusion_weights(p.w_param, w0, w1);
-    const int win = tid >> 6, rr = tid & 63;
+    const int half = tid >> 7, row = tid & 127;   // half: which 32 of the row's 64 score columns / 16 of its 32 outputs
+    const int win = row >> 6, rr = row & 63;
     int ti, tj;
     t5a_token(rr, ti, tj);
     const int bias_base = (ti + WIN - 1) * (2 * WIN - 1) + tj + WIN - 1;
@@ -668,11 +682,10 @@ attn_fwd_t5_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_consta
         const int pr = (item / p.heads) % pairs;
         const int b = item / (p.heads * pairs);
         uint8_t* Vs = Vbuf + vb * T5A_TILE;
-        // per-item tables (the previous item's readers are past their last barrier)
-        for (int i = tid; i < NBINS; i += T5A_THREADS) tab[i] = p.table[i * p.heads + h];
+        const float* tab = tabs + h * 228;
         const int wlin = 2 * pr + win, wy = wlin / p.nWx, wx = wlin - wy * p.nWx;
         const int myreg = p.shift > 0 ? region_code(p, wy, wx, n_nat) : 0;
-        reg[tid] = myreg;
+        if (half == 0) reg[row] = myreg;   // the previous item's readers are past their last barrier
         const bool masked = p.shift > 0 && (wy == p.H / WIN - 1 || wx == p.nWx - 1);
         const long long orow = token_row(p, b, wy, wx, n_nat);
 
@@ -722,53 +735,58 @@ attn_fwd_t5_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_consta
         ph_mma ^= 1;
         tc_fence_after();
         T5A_STAMP(3);
-        // S is in TMEM: the Q/K tiles are dead -> the next item's tiles (and its V, into the other buffer) start now
-        if (warp == 0 && item + (int)gridDim.x < items)
+        // S is in TMEM: the Q/K tiles are dead (and the other V buffer since the previous item's P V) -> the next
+        // item's tiles are requested now and land under this item's softmax / P V / store
+        if (warp == 7 && item + (int)gridDim.x < items)
             t5a_issue_loads(p, &mapQ, &mapK, &mapV, Qhi, Khi, Vbuf + (vb ^ 1) * T5A_TILE, bar_load, item + gridDim.x, pairs,
                             lane);
-
-        // ---- this thread's query row: 64 scores of its own window (TMEM columns 64*win .. +63)
-        uint32_t sr[2][32];
-        tmem_ld32_issue(trow + win * 64, sr[0]);
-        tmem_ld32_issue(trow + win * 64 + 32, sr[1]);
+        // ---- this thread's half of its query row: 32 scores (TMEM columns 64*win + 32*half .. +31)
+        uint32_t sr[32];
+        tmem_ld32_issue(trow + win * 64 + half * 32, sr);
         tmem_ld_wait();
-        float sv[64];
+        float sv[32];
         float mx = -INFINITY;
 #pragma unroll
-        for (int m = 0; m < 64; ++m) {
-            int im, jm;
-            t5a_token(m, im, jm);
-            float v = __uint_as_float(sr[m >> 5][m & 31]) * p.scale + tab[bias_base - (im * (2 * WIN - 1) + jm)];
-            if (masked && reg[win * 64 + m] != myreg) v += -100.0f;
-            sv[m] = v;
+        for (int mm = 0; mm < 32; ++mm) {
+            // column token: quadrant-major slot m = 32*half + mm -> rows 4*half .. 4*half+3 of the window
+            const int im = 4 * half + ((mm >> 2) & 3), jm = 4 * (mm >> 4) + (mm & 3);
+            float v = __uint_as_float(sr[mm]) * p.scale + tab[bias_base - (im * (2 * WIN - 1) + jm)];
+            if (masked && reg[win * 64 + half * 32 + mm] != myreg) v += -100.0f;
+            sv[mm] = v;
             mx = fmaxf(mx, v);
         }
+        // local softmax statistics of this half row, merged with the other half's in ONE exchange (online softmax)
         float sum = 0.f;
-        float pe[64];
+        float pe[32];
 #pragma unroll
-        for (int m = 0; m < 64; ++m) {
-            pe[m] = ex2_ftz((sv[m] - mx) * 1.4426950408889634f);
-            sum += pe[m];
+        for (int mm = 0; mm < 32; ++mm) {
+            pe[mm] = ex2_ftz((sv[mm] - mx) * 1.4426950408889634f);
+            sum += pe[mm];
         }
-        const float inv = __fdividef(1.0f, sum) * w0;
+        reinterpret_cast<float2*>(xch)[half * 128 + row] = make_float2(mx, sum);
+        __syncthreads();
+        const float2 other = reinterpret_cast<const float2*>(xch)[(half ^ 1) * 128 + row];
+        const float mall = fmaxf(mx, other.x);
+        const float mine = ex2_ftz((mx - mall) * 1.4426950408889634f);
+        const float tot = sum * mine + other.y * ex2_ftz((other.x - mall) * 1.4426950408889634f);
+        const float inv = __fdividef(mine, tot) * w0;   // p_m = pe[m] * exp(mx - mall) / tot
         // ---- P = w0 softmax + w1 relu^2, TF32-rounded, into the compact K-major A tile (128B swizzle): row r
-        // holds the 64 probabilities of ITS window; the product with the other window's V is never read
+        // holds the 64 probabilities of ITS window (chunk `half` = its 32 columns); the product with the other
+        // window's V is never read
         {
-            const int sw = tid & 7;
-            uint8_t* prow = Pm + tid * 128;
+            const int sw = row & 7;
+            uint8_t* prow = Pm + half * T5A_TILE + row * 128;
 #pragma unroll
-            for (int kc = 0; kc < 2; ++kc)
+            for (int c = 0; c < 8; ++c) {
+                float e[4];
 #pragma unroll
-                for (int c = 0; c < 8; ++c) {
-                    float e[4];
-#pragma unroll
-                    for (int q = 0; q < 4; ++q) {
-                        const int m = kc * 32 + c * 4 + q;
-                        const float r = fmaxf(sv[m], 0.f);
-                        e[q] = tf32_round(pe[m] * inv + w1 * r * r);
-                    }
-                    *reinterpret_cast<float4*>(prow + kc * T5A_TILE + ((c ^ sw) << 4)) = make_float4(e[0], e[1], e[2], e[3]);
+                for (int q = 0; q < 4; ++q) {
+                    const int mm = c * 4 + q;
+                    const float r = fmaxf(sv[mm], 0.f);
+                    e[q] = tf32_round(pe[mm] * inv + w1 * r * r);
                 }
+                *reinterpret_cast<float4*>(prow + ((c ^ sw) << 4)) = make_float4(e[0], e[1], e[2], e[3]);
+            }
         }
         fence_proxy_async_smem();
         tc_fence_before();
@@ -789,19 +807,19 @@ attn_fwd_t5_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_consta
         ph_mma ^= 1;
         tc_fence_after();
         T5A_STAMP(5);
-        uint32_t orr[32];
-        tmem_ld32_issue(trow + 128 + 32 * win, orr);
+        uint32_t orr[16];
+        tmem_ld16_issue(trow + 128 + 32 * win + 16 * half, orr);
         tmem_ld_wait();
-        float* op = out + orow * ld_out + h * 32;
+        float* op = out + orow * ld_out + h * 32 + 16 * half;
 #pragma unroll
-        for (int c = 0; c < 8; ++c) {
+        for (int c = 0; c < 4; ++c) {
             float4 v = make_float4(__uint_as_float(orr[4 * c]), __uint_as_float(orr[4 * c + 1]),
                                    __uint_as_float(orr[4 * c + 2]), __uint_as_float(orr[4 * c + 3]));
             if (p.rnd) v = make_float4(tf32_round(v.x), tf32_round(v.y), tf32_round(v.z), tf32_round(v.w));
             *reinterpret_cast<float4*>(op + 4 * c) = v;
         }
         tc_fence_before();
-        __syncthreads();  // every warp has read its TMEM rows / tables before the next item overwrites them
+        __syncthreads();  // every warp has read its TMEM rows before the next item's MMAs overwrite them
         T5A_STAMP(6);
     }
     tc_fence_before();
@@ -813,9 +831,9 @@ attn_fwd_t5_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_consta
 }
 
 // uwr_set_attn_tcgen05.  Off by default: measured on B200 (32 768 tiles, head_dim 32) the tcgen05 kernel takes
-// 0.42 ms against 0.31 ms for the mma.sync kernel — each item is one serial chain TMA -> lo split -> MMA -> softmax ->
-// MMA -> store and only two items fit an SM (256 TMEM columns, 97 KB smem each), so it is latency-bound
-// (ncu: issue 26 %, tensor pipe 15 %, a quarter of the samples in mbarrier waits).  See DESIGN.md §8.
+// 0.34 ms against 0.31 ms for the mma.sync kernel — each item is one serial chain TMA -> lo split -> MMA -> softmax ->
+// MMA -> store (~8.9 k cycles) and only two items fit an SM (256 TMEM columns, 109 KB smem each), so it is
+// latency-bound (tensor pipe 15 % busy).  See DESIGN.md §8.
 int g_attn_t5 = 0;
 
 int launch_fwd_t5(const AttnParams& p, float* out, long long ld_out, cudaStream_t stream) {
@@ -834,12 +852,13 @@ int launch_fwd_t5(const AttnParams& p, float* out, long long ld_out, cudaStream_
     }
     static bool configured = false;
     if (!configured) {
-        UWR_CUDA(cudaFuncSetAttribute(attn_fwd_t5_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, T5A_SMEM));
+        UWR_CUDA(cudaFuncSetAttribute(attn_fwd_t5_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                      t5a_smem_bytes(T5A_MAXH)));
         configured = true;
     }
     const long long items = (long long)p.B * (p.nW / 2) * p.heads;
     const int grid = (int)(items < 2LL * uwr_sm_count() ? items : 2LL * uwr_sm_count());
-    attn_fwd_t5_kernel<<<grid, T5A_THREADS, T5A_SMEM, stream>>>(mq, mk, mv, p, out, ld_out);
+    attn_fwd_t5_kernel<<<grid, T5A_THREADS, t5a_smem_bytes(p.heads), stream>>>(mq, mk, mv, p, out, ld_out);
     UWR_CHECK_LAUNCH("attn_fwd_t5_kernel");
     return 0;
 }
@@ -910,7 +929,8 @@ extern "C" int uwr_window_attn_fwd(const uwr_attn_desc* d, float* out, long long
     if (int rc = fill_params(d, p, "uwr_window_attn_fwd")) return rc;
     UWR_REQUIRE(out && ld_out % 2 == 0, "uwr_window_attn_fwd: bad output");
     // tcgen05 / TMA path: two windows per 128-row MMA tile
-    if (g_attn_t5 && d->head_dim == 32 && (d->shift == 0 || d->shift == 4) && p.nW % 2 == 0 && ld_out % 4 == 0 &&
+    if (g_attn_t5 && d->head_dim == 32 && d->heads <= T5A_MAXH && (d->shift == 0 || d->shift == 4) && p.nW % 2 == 0 &&
+        ld_out % 4 == 0 &&
         (((uintptr_t)d->q | (uintptr_t)d->kv | (uintptr_t)out) & 15) == 0)
         return launch_fwd_t5(p, out, ld_out, stream);
     switch (d->head_dim) {
