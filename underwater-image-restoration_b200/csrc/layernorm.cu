@@ -85,7 +85,10 @@ __global__ void __launch_bounds__(LN_WARPS * 32) ln_fwd_vec_kernel(const float* 
     }
     constexpr float invC = 1.0f / (float)C;
     const long long stride = (long long)gridDim.x * LN_WARPS * RPW;
-    for (long long r0 = ((long long)blockIdx.x * LN_WARPS + warp) * RPW + sub; r0 < rows; r0 += stride * RPI) {
+    // the loop bound is warp-uniform (first row of the warp's group): every lane takes part in the shuffles,
+    // rows past the end are masked per lane
+    for (long long rw = ((long long)blockIdx.x * LN_WARPS + warp) * RPW; rw < rows; rw += stride * RPI) {
+        const long long r0 = rw + sub;
         float4 v[RPI][V4];
 #pragma unroll
         for (int k = 0; k < RPI; ++k) {
@@ -213,6 +216,110 @@ __global__ void __launch_bounds__(LN_WARPS * 32) ln_bwd_kernel(const float* __re
     }
 }
 
+// Vectorised backward for C = 4 * LPR * V4 (same lane layout as ln_fwd_vec_kernel): 128-bit accesses, 32 / LPR
+// rows per warp pass, two passes in flight for the narrow rows.  The warp-per-row kernel ran the 128-byte rows
+// (C = 32) at 3.5 TB/s and the short, wide tensors of the deep stages (16 384 x 512) at 1.3 TB/s.
+template <int LPR, int V4>
+__global__ void __launch_bounds__(LN_WARPS * 32) ln_bwd_vec_kernel(const float* __restrict__ dy,
+                                                                   const float* __restrict__ x,
+                                                                   const float* __restrict__ gamma,
+                                                                   const float* __restrict__ mean,
+                                                                   const float* __restrict__ rstd,
+                                                                   const float* __restrict__ dres,
+                                                                   float* __restrict__ dx, float* __restrict__ partials,
+                                                                   long long rows) {
+    constexpr int C = 4 * LPR * V4;
+    constexpr int RPW = 32 / LPR;
+    constexpr int RPI = V4 == 1 ? 2 : 1;
+    __shared__ __align__(16) float sh[LN_WARPS][C];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int sub = lane / LPR, l = lane % LPR;
+    float4 gm[V4], dg[V4], db[V4];
+#pragma unroll
+    for (int i = 0; i < V4; ++i) {
+        gm[i] = *reinterpret_cast<const float4*>(gamma + (l + LPR * i) * 4);
+        dg[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+        db[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+    constexpr float invC = 1.0f / (float)C;
+    const long long stride = (long long)gridDim.x * LN_WARPS * RPW;
+    for (long long rw = ((long long)blockIdx.x * LN_WARPS + warp) * RPW; rw < rows; rw += stride * RPI) {
+        const long long r0 = rw + sub;   // warp-uniform loop bound: every lane takes part in the shuffles
+        float4 xv[RPI][V4], dv[RPI][V4], rv[RPI][V4];
+        float mu[RPI], rs[RPI];
+#pragma unroll
+        for (int k = 0; k < RPI; ++k) {
+            const long long r = r0 + k * stride;
+            const bool ok = r < rows;
+            mu[k] = ok ? mean[r] : 0.f;
+            rs[k] = ok ? rstd[r] : 0.f;
+#pragma unroll
+            for (int i = 0; i < V4; ++i) {
+                const long long o = r * C + (l + LPR * i) * 4;
+                const float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
+                xv[k][i] = ok ? *reinterpret_cast<const float4*>(x + o) : z;
+                dv[k][i] = ok ? *reinterpret_cast<const float4*>(dy + o) : z;
+                rv[k][i] = (ok && dres) ? *reinterpret_cast<const float4*>(dres + o) : z;
+            }
+        }
+#pragma unroll
+        for (int k = 0; k < RPI; ++k) {
+            const long long r = r0 + k * stride;
+            float4 xh[V4], g[V4];
+            float s1 = 0.f, s2 = 0.f;
+#pragma unroll
+            for (int i = 0; i < V4; ++i) {
+                xh[i] = make_float4((xv[k][i].x - mu[k]) * rs[k], (xv[k][i].y - mu[k]) * rs[k],
+                                    (xv[k][i].z - mu[k]) * rs[k], (xv[k][i].w - mu[k]) * rs[k]);
+                g[i] = make_float4(dv[k][i].x * gm[i].x, dv[k][i].y * gm[i].y, dv[k][i].z * gm[i].z, dv[k][i].w * gm[i].w);
+                s1 += (g[i].x + g[i].y) + (g[i].z + g[i].w);
+                s2 += (g[i].x * xh[i].x + g[i].y * xh[i].y) + (g[i].z * xh[i].z + g[i].w * xh[i].w);
+                dg[i].x += dv[k][i].x * xh[i].x; dg[i].y += dv[k][i].y * xh[i].y;
+                dg[i].z += dv[k][i].z * xh[i].z; dg[i].w += dv[k][i].w * xh[i].w;
+                db[i].x += dv[k][i].x; db[i].y += dv[k][i].y; db[i].z += dv[k][i].z; db[i].w += dv[k][i].w;
+            }
+#pragma unroll
+            for (int o = LPR / 2; o > 0; o >>= 1) {
+                s1 += __shfl_xor_sync(0xffffffffu, s1, o);
+                s2 += __shfl_xor_sync(0xffffffffu, s2, o);
+            }
+            s1 *= invC;
+            s2 *= invC;
+            if (r < rows) {
+#pragma unroll
+                for (int i = 0; i < V4; ++i)
+                    *reinterpret_cast<float4*>(dx + r * C + (l + LPR * i) * 4) =
+                        make_float4(rs[k] * (g[i].x - s1 - xh[i].x * s2) + rv[k][i].x, rs[k] * (g[i].y - s1 - xh[i].y * s2) + rv[k][i].y,
+                                    rs[k] * (g[i].z - s1 - xh[i].z * s2) + rv[k][i].z, rs[k] * (g[i].w - s1 - xh[i].w * s2) + rv[k][i].w);
+            }
+        }
+    }
+    // dgamma / dbeta: lanes that share a column group (across the RPW sub-rows of the warp), then the warps
+#pragma unroll
+    for (int pass = 0; pass < 2; ++pass) {
+#pragma unroll
+        for (int i = 0; i < V4; ++i) {
+            float4 v = pass == 0 ? dg[i] : db[i];
+#pragma unroll
+            for (int o = LPR; o < 32; o <<= 1) {
+                v.x += __shfl_xor_sync(0xffffffffu, v.x, o);
+                v.y += __shfl_xor_sync(0xffffffffu, v.y, o);
+                v.z += __shfl_xor_sync(0xffffffffu, v.z, o);
+                v.w += __shfl_xor_sync(0xffffffffu, v.w, o);
+            }
+            if (sub == 0) *reinterpret_cast<float4*>(&sh[warp][(l + LPR * i) * 4]) = v;
+        }
+        __syncthreads();
+        for (int c = threadIdx.x; c < C; c += blockDim.x) {
+            float t = 0.f;
+#pragma unroll
+            for (int w = 0; w < LN_WARPS; ++w) t += sh[w][c];
+            partials[((long long)blockIdx.x * 2 + pass) * C + c] = t;
+        }
+        __syncthreads();
+    }
+}
+
 // dgamma/dbeta = column sums of the per-CTA partial rows: 32 columns x 32 row-slices per CTA (a
 // single thread per column walking ~900 partial rows serially took 70 us per LayerNorm)
 __global__ void __launch_bounds__(1024) ln_param_reduce_kernel(const float* __restrict__ partials,
@@ -305,6 +412,31 @@ extern "C" int uwr_layernorm_bwd(const float* dy, const float* x, const float* g
     UWR_REQUIRE(dy && x && gamma && mean && rstd && dx && dgamma && dbeta && partials, "uwr_layernorm_bwd: null pointer");
     UWR_REQUIRE(C > 0 && C <= 1024, "uwr_layernorm_bwd: C=%d unsupported (1..1024)", C);
     UWR_REQUIRE(rows > 0, "uwr_layernorm_bwd: rows must be positive");
+#define LN_BWD_VEC(L, V)                                                                                          \
+    do {                                                                                                          \
+        long long b = (rows + LN_WARPS * (32 / L) * 8 - 1) / (LN_WARPS * (32 / L) * 8); /* >= 8 rows per lane group */ \
+        const long long cap = ln_blocks(rows);                                                                    \
+        if (b > cap) b = cap;                                                                                     \
+        if (b < 1) b = 1;                                                                                         \
+        ln_bwd_vec_kernel<L, V><<<(unsigned)b, LN_WARPS * 32, 0, stream>>>(dy, x, gamma, mean, rstd, dres, dx,    \
+                                                                           partials, rows);                      \
+        UWR_CHECK_LAUNCH("ln_bwd_vec_kernel");                                                                    \
+        ln_param_reduce_kernel<<<uwr_cdiv(C, 32), 1024, 0, stream>>>(partials, dgamma, dbeta, (int)b, C);         \
+        UWR_CHECK_LAUNCH("ln_param_reduce_kernel");                                                               \
+        return 0;                                                                                                 \
+    } while (0)
+    if ((((uintptr_t)x | (uintptr_t)dy | (uintptr_t)dx | (uintptr_t)gamma | (uintptr_t)(dres ? dres : x)) & 15) == 0) {
+        switch (C) {
+            case 16: LN_BWD_VEC(4, 1);
+            case 32: LN_BWD_VEC(8, 1);
+            case 64: LN_BWD_VEC(16, 1);
+            case 128: LN_BWD_VEC(32, 1);
+            case 256: LN_BWD_VEC(32, 2);
+            case 512: LN_BWD_VEC(32, 4);
+            default: break;
+        }
+    }
+#undef LN_BWD_VEC
     const int blocks = ln_blocks(rows);
     const int vpl = (C + 31) / 32;
 #define LN_BWD(V) \
