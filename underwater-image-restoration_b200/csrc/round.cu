@@ -64,15 +64,26 @@ __global__ void __launch_bounds__(256) scale_round_colsum_kernel(const float* __
     __shared__ float4 sh[256];
     const int c4 = threadIdx.x % cols4, rsub = threadIdx.x / cols4, rpb = 256 / cols4;
     float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
-    for (long long r = (long long)blockIdx.x * rpb + rsub; r < rows; r += (long long)gridDim.x * rpb) {
-        float4 v = *reinterpret_cast<const float4*>(src + r * ld_src + c4 * 4);
-        const float s = rowscale ? __ldg(rowscale + r / rpg) : 1.f;
-        v.x *= s; v.y *= s; v.z *= s; v.w *= s;
-        if (do_round) {
-            v.x = tf32_round(v.x); v.y = tf32_round(v.y); v.z = tf32_round(v.z); v.w = tf32_round(v.w);
+    const long long step = (long long)gridDim.x * rpb;
+    for (long long r0 = (long long)blockIdx.x * rpb + rsub; r0 < rows; r0 += 4 * step) {  // four rows in flight
+        float4 v[4];
+        float sc[4];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            const long long r = r0 + k * step;
+            const bool ok = r < rows;
+            v[k] = ok ? *reinterpret_cast<const float4*>(src + r * ld_src + c4 * 4) : make_float4(0.f, 0.f, 0.f, 0.f);
+            sc[k] = (ok && rowscale) ? __ldg(rowscale + r / rpg) : 1.f;
         }
-        reinterpret_cast<float4*>(dst)[r * cols4 + c4] = v;
-        acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            const long long r = r0 + k * step;
+            if (r >= rows) break;
+            float4 o = make_float4(v[k].x * sc[k], v[k].y * sc[k], v[k].z * sc[k], v[k].w * sc[k]);
+            if (do_round) o = make_float4(tf32_round(o.x), tf32_round(o.y), tf32_round(o.z), tf32_round(o.w));
+            reinterpret_cast<float4*>(dst)[r * cols4 + c4] = o;
+            acc.x += o.x; acc.y += o.y; acc.z += o.z; acc.w += o.w;
+        }
     }
     sh[threadIdx.x] = acc;
     __syncthreads();

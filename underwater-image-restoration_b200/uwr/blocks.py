@@ -73,17 +73,18 @@ class DownsampleFn(torch.autograd.Function):
         col = ops.im2col_4x4s2(x.view(B * L, Cc), B, H, W, Cc)  # TF32-rounded at the store in tf32 mode
         wmat_r = ops.scale_round(wmat, 16 * Cc)
         y = ops.linear(col, wmat_r, bias, t5=True)
-        ctx.save_for_backward(x, wmat_r)
+        # the im2col matrix (4x the input; ~1 GB over the four stages at batch 16) is kept for the weight
+        # gradient instead of being rebuilt in backward
+        ctx.save_for_backward(col, wmat_r)
         ctx.dims = (B, H, W, Cc, Cout)
         return y.view(B, L // 4, Cout)
 
     @staticmethod
     @once_differentiable
     def backward(ctx, dy):
-        x, wmat = ctx.saved_tensors
+        col, wmat = ctx.saved_tensors
         B, H, W, Cc, Cout = ctx.dims
         dy2 = _c(dy).view(-1, Cout)
-        col = ops.im2col_4x4s2(x.view(-1, Cc), B, H, W, Cc)  # recomputed, not saved (4x the input)
         fast = ops.fast_path()
         if fast:  # tcgen05 path: both operands rounded to TF32 (col and wmat already are); bias gradient =
             dy2, dbias = ops.scale_round_colsum(dy2, Cout)  # column sums taken in the same pass
