@@ -208,8 +208,12 @@ def run_ours(args):
     loss_host = torch.zeros(1).pin_memory()
 
     def step_e2e():
+        # every step: pinned host -> device copy of ITS inputs and a device -> host read of its loss.  With the
+        # graphed step the copy of the next step's batch runs on a side stream under the current step
+        # (uwr.graph.GraphedTrainStep.prefetch); the loss is read back (and waited for) every step.
         if graphed is not None:
-            loss, _ = graphed(raw_h, ref_h)          # pinned host -> static device buffers, then replay
+            loss, _ = graphed.step_prefetched()
+            graphed.prefetch(raw_h, ref_h)           # next step's batch, overlapped with this step's kernels
         else:
             r = raw_h.to(dev, non_blocking=True)
             t = ref_h.to(dev, non_blocking=True)
@@ -227,6 +231,8 @@ def run_ours(args):
     step_eager()  # launches per step are counted on one eager step (a graph replay re-issues the same kernels)
     launches = (ops.launch_count() - l0) * args.steps
     clocks = sampler.stop() if rank == 0 else None
+    if graphed is not None:
+        graphed.prefetch(raw_h, ref_h)               # batch of the first e2e step
     step_e2e()
     ms_e2e = timed(step_e2e, args.steps)
 

@@ -74,3 +74,29 @@ class GraphedTrainStep:
         self.ref.copy_(ref, non_blocking=True)
         self.replay()
         return self.loss, self.norm
+
+    # ---- input pipeline: the host -> device copy of step i+1 runs on a side stream under step i ------------
+    def prefetch(self, raw_host, ref_host):
+        """Start copying the NEXT step's (pinned) host batch into device staging buffers on a copy stream."""
+        if not hasattr(self, "_copy_stream"):
+            self._copy_stream = torch.cuda.Stream()
+            self._stage = (torch.empty_like(self.raw), torch.empty_like(self.ref))
+            self._staged = torch.cuda.Event()
+            self._consumed = torch.cuda.Event()
+            self._consumed.record()
+        self._copy_stream.wait_event(self._consumed)        # the previous batch has left the staging buffers
+        with torch.cuda.stream(self._copy_stream):
+            self._stage[0].copy_(raw_host, non_blocking=True)
+            self._stage[1].copy_(ref_host, non_blocking=True)
+            self._staged.record()
+
+    def step_prefetched(self):
+        """Run one step on the batch handed to prefetch(): wait for its copy, move it into the graph's static
+        inputs (device -> device, microseconds) and replay."""
+        cur = torch.cuda.current_stream()
+        cur.wait_event(self._staged)
+        self.raw.copy_(self._stage[0], non_blocking=True)
+        self.ref.copy_(self._stage[1], non_blocking=True)
+        self._consumed.record(cur)
+        self.replay()
+        return self.loss, self.norm
