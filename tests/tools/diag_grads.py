@@ -1,6 +1,6 @@
 """Diagnostic: per-tensor gradient error of the uwr AST vs the fp64 CPU oracle (top contributors)."""
 import os, sys
-ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "underwater-image-restoration_b200"))
 import torch
 from oracle import ast_oracle, losses_oracle

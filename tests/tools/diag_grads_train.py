@@ -1,6 +1,6 @@
 """Diagnostic: train-mode (injected DropPath masks) per-tensor gradient error vs fp64 oracle."""
 import os, sys
-ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "underwater-image-restoration_b200"))
 import torch
 from oracle import ast_oracle, losses_oracle

@@ -2,7 +2,7 @@
 B200, eager launches and CUDA-graph replay, plus PSNR / UIQM parity against the CPU oracle on the
 structured synthetic pair of SURVEY.md §8d.  Writes a JSON summary (profiles/r1_inference_sweep.json)."""
 import json, os, sys, time
-ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "underwater-image-restoration_b200"))
 import numpy as np
 import torch

@@ -18,5 +18,5 @@ UWR_KB_REPS=1 ncu --set full --clock-control none -k regex:"gemm_tcgen05|dwconv_
 cat gpurun_out/plain_kb_$TAG.log
 UWR_PROFILE_OUT=gpurun_out/prof_spectral_$TAG.json python tools/train_bench.py SpectralTransformer L1withColor 8 > gpurun_out/train_spectral_$TAG.log 2>&1; tail -1 gpurun_out/train_spectral_$TAG.log
 UWR_PROFILE_OUT=gpurun_out/prof_newbig_$TAG.json python tools/train_bench.py NewBigFRFNModel fflMix 16 > gpurun_out/train_newbig_$TAG.log 2>&1; tail -1 gpurun_out/train_newbig_$TAG.log
-python tools/infer_sweep.py > gpurun_out/infer_sweep_$TAG.log 2>&1; tail -3 gpurun_out/infer_sweep_$TAG.log
+python tests/tools/infer_sweep.py > gpurun_out/infer_sweep_$TAG.log 2>&1; tail -3 gpurun_out/infer_sweep_$TAG.log
 ls -la gpurun_out | tail -30; du -sh gpurun_out
