@@ -166,20 +166,35 @@ __global__ void __launch_bounds__(256) gelu_gate_bwd_kernel(const float* __restr
                                                             const float* __restrict__ v, float* __restrict__ dv,
                                                             float* __restrict__ du, long long rows, int Ch, int mode,
                                                             int rnd) {
-    const long long total = rows * Ch;
+    const int c4n = Ch >> 2;  // Ch is a multiple of 4: 128-bit accesses
+    const long long total = rows * c4n;
     for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total;
          i += (long long)gridDim.x * blockDim.x) {
-        const long long r = i / Ch;
-        const int c = (int)(i % Ch);
-        const float d = dh2[i], vv = v[i];
-        float g = d * gelu_grad_f(vv);
+        const long long r = i / c4n;
+        const int c = (int)(i - r * c4n) * 4;
+        const float4 d4 = ld4(dh2 + r * Ch + c), v4 = ld4(v + r * Ch + c);
+        const float d[4] = {d4.x, d4.y, d4.z, d4.w}, vv[4] = {v4.x, v4.y, v4.z, v4.w};
+        float g[4], g2[4];
+        float u2[4] = {0.f, 0.f, 0.f, 0.f};
         if (mode == 1) {
-            const float u2 = u[r * ld_u + Ch + c];
-            g *= gelu_f(u2);
-            const float g2 = d * gelu_f(vv) * gelu_grad_f(u2);
-            du[r * ld_u + Ch + c] = rnd ? tf32_round(g2) : g2;
+            const float4 t = ld4(u + r * ld_u + Ch + c);
+            u2[0] = t.x; u2[1] = t.y; u2[2] = t.z; u2[3] = t.w;
         }
-        dv[i] = g;
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+            float cdf, pdf;
+            gelu_parts(vv[e], cdf, pdf);
+            g[e] = d[e] * fmaf(vv[e], pdf, cdf);          // dh2 * gelu'(v)
+            if (mode == 1) {
+                float cdf2, pdf2;
+                gelu_parts(u2[e], cdf2, pdf2);
+                g[e] *= u2[e] * cdf2;                     // ... * gelu(u2)
+                g2[e] = d[e] * (vv[e] * cdf) * fmaf(u2[e], pdf2, cdf2);   // dh2 * gelu(v) * gelu'(u2)
+                if (rnd) g2[e] = tf32_round(g2[e]);
+            }
+        }
+        if (mode == 1) *reinterpret_cast<float4*>(du + r * ld_u + Ch + c) = make_float4(g2[0], g2[1], g2[2], g2[3]);
+        *reinterpret_cast<float4*>(dv + r * Ch + c) = make_float4(g[0], g[1], g[2], g[3]);
     }
 }
 
@@ -439,7 +454,8 @@ extern "C" int uwr_gelu_gate_bwd(const float* dh2, const float* u, long long ld_
                                  float* du, long long rows, int Ch, int mode, uwr_stream_t stream_) {
     cudaStream_t stream = (cudaStream_t)stream_;
     UWR_REQUIRE(dh2 && v && dv && (mode == 0 || (u && du)), "uwr_gelu_gate_bwd: null pointer");
-    const long long total = rows * Ch;
+    UWR_REQUIRE(Ch % 4 == 0 && (mode == 0 || ld_u % 4 == 0), "uwr_gelu_gate_bwd: Ch and ld_u must be multiples of 4");
+    const long long total = rows * (Ch / 4);
     long long blocks = (total + 255) / 256;
     if (blocks > 16LL * uwr_sm_count()) blocks = 16LL * uwr_sm_count();
     gelu_gate_bwd_kernel<<<(unsigned)blocks, 256, 0, stream>>>(dh2, u, ld_u, v, dv, du, rows, Ch, mode, uwr_round_outputs());

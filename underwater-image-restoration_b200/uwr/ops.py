@@ -252,6 +252,12 @@ def rounded_weight(w):
     changes); the weight itself in tf32x3 mode."""
     if _PASSES != 1:
         return w
+    base = w._base
+    if (base is not None and isinstance(base, torch.nn.Parameter) and w.is_contiguous() and base.is_contiguous()
+            and w.numel() == base.numel() and w.data_ptr() == base.data_ptr()):
+        # a reshaped view of a parameter (conv.weight.flatten(1), ...): cache on the parameter itself, views are
+        # new objects on every call
+        return rounded_weight(base).view(w.shape)
     ent, ver = _fresh(w, "_uwr_rounded")
     if ent is None or ent[0] != ver:
         buf = ent[1] if ent is not None and ent[1].shape == w.shape and ent[1].device == w.device else torch.empty_like(w)
@@ -259,7 +265,7 @@ def rounded_weight(w):
         w2 = wd.reshape(wd.shape[0], -1) if wd.dim() > 1 else wd.reshape(1, -1)   # conv weights: (C0, rest)
         scale_round(w2, w2.shape[1], out=buf.view(w2.shape))
         w._uwr_rounded = ent = (ver, buf)
-        if w.is_contiguous():
+        if w.is_contiguous() and isinstance(w, torch.nn.Parameter):   # temporaries would grow the registry
             _register_rounded(w, "w")
     return ent[1]
 
@@ -347,7 +353,7 @@ def packed_qkv(wq, bq, wkv, bkv):
             _run("uwr_scale_round", "bias", 0, 0.0, _ptr(bq.detach()), Cq, _ptr(bias), 1, Cq, None, 0, 0)
             _run("uwr_scale_round", "bias", 0, 0.0, _ptr(bkv.detach()), 2 * Cq, _ptr(bias[Cq:]), 1, 2 * Cq, None, 0, 0)
         wq._uwr_qkv = ent = (ver, buf, bias)
-        if wq.is_contiguous() and wkv.is_contiguous():
+        if wq.is_contiguous() and wkv.is_contiguous() and isinstance(wq, torch.nn.Parameter):
             _register_rounded(wq, (wkv, bq, bkv))
     return ent[1], ent[2]
 
