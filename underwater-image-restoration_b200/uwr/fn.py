@@ -135,33 +135,68 @@ class AttnFn(torch.autograd.Function):
         M, Cc = xq.shape
         hd = Cc // heads
         scale = hd ** -0.5
+        # tf32 mode: every projection on the tcgen05 kernel; inputs of unknown provenance get a TF32-rounded copy
+        # (one extra pass over a C-wide matrix, far cheaper than the legacy kernel at these tall-skinny shapes)
+        fast = ops.fast_path() and Cc % 32 == 0 and M >= 4096
+        if fast:
+            xq = ops.scale_round(xq, Cc)
         if xkv is None:
-            qkv = ops.linear(xq, wq, bq, weight2=wkv, bias2=bkv)
+            if fast:
+                w, bias = ops.packed_qkv(wq, bq, wkv, bkv)
+                qkv = ops.linear(xq, w, bias, t5=True)
+            else:
+                qkv = ops.linear(xq, wq, bq, weight2=wkv, bias2=bkv)
             q_buf, q_off, kv_buf, k_off, v_off = qkv, 0, qkv, Cc, 2 * Cc
         else:
             xkv = _c(xkv)
-            q_buf = ops.linear(xq, wq, bq)
-            kv_buf = ops.linear(xkv, wkv, bkv)
+            if fast:
+                xkv = ops.scale_round(xkv, xkv.shape[1])
+                q_buf = ops.linear(xq, ops.rounded_weight(wq), bq, t5=True)
+                kv_buf = ops.linear(xkv, ops.rounded_weight(wkv), bkv, t5=True)
+            else:
+                q_buf = ops.linear(xq, wq, bq)
+                kv_buf = ops.linear(xkv, wkv, bkv)
             q_off, k_off, v_off = 0, 0, Cc
         o = ops.window_attn_fwd(q_buf, q_off, kv_buf, k_off, v_off, table, wparam, B, H, W, heads, hd, shift, scale)
         y = ops.linear(o, ops.rounded_weight(wp), bp, t5=True)
-        ctx.save_for_backward(xq, xkv, wq, wkv, table, wparam, wp, q_buf, kv_buf, o)
-        ctx.meta = (B, H, W, heads, hd, shift, scale, Cc, bq is not None)
+        ctx.save_for_backward(xq, xkv, wq, wkv, table, wparam, wp, q_buf, kv_buf, o, bq, bkv)
+        ctx.meta = (B, H, W, heads, hd, shift, scale, Cc, bq is not None, fast)
         return y
 
     @staticmethod
     @once_differentiable
     def backward(ctx, dy):
-        xq, xkv, wq, wkv, table, wparam, wp, q_buf, kv_buf, o = ctx.saved_tensors
-        B, H, W, heads, hd, shift, scale, Cc, has_b = ctx.meta
+        xq, xkv, wq, wkv, table, wparam, wp, q_buf, kv_buf, o, bq, bkv = ctx.saved_tensors
+        B, H, W, heads, hd, shift, scale, Cc, has_b, fast = ctx.meta
         d = _c(dy)
-        d_o = ops.linear_dgrad(d, wp)
-        dwp, dbp = ops.linear_wgrad(d, o)
+        if fast:   # rounded cotangent + proj bias gradient in one pass; o was rounded by the attention kernel
+            d, dbp = ops.scale_round_colsum(d, Cc)
+            d_o = ops.linear_dgrad(d, ops.rounded_weight(wp), t5=True)
+            dwp, _ = ops.linear_wgrad(d, o, want_bias=False, t5=True)
+        else:
+            d_o = ops.linear_dgrad(d, wp)
+            dwp, dbp = ops.linear_wgrad(d, o)
         cross = xkv is not None
         q_off, k_off, v_off = (0, 0, Cc) if cross else (0, Cc, 2 * Cc)
         dq_buf, dkv_buf, dtable, dw = ops.window_attn_bwd(d_o, q_buf, q_off, kv_buf, k_off, v_off, table, wparam,
                                                           B, H, W, heads, hd, shift, scale)
-        if cross:
+        if fast:   # dq / dk / dv leave the attention kernel TF32-rounded; xq / xkv were saved rounded
+            if cross:
+                dxq = ops.linear_dgrad(dq_buf, ops.rounded_weight(wq), t5=True)
+                dwq, _ = ops.linear_wgrad(dq_buf, xq, want_bias=False, t5=True)
+                dxkv = ops.linear_dgrad(dkv_buf, ops.rounded_weight(wkv), t5=True)
+                dwkv, _ = ops.linear_wgrad(dkv_buf, xkv, want_bias=False, t5=True)
+                dbq = ops.colsum(dq_buf, Cc) if has_b else None
+                dbkv = ops.colsum(dkv_buf, 2 * Cc) if has_b else None
+            else:
+                w, _ = ops.packed_qkv(wq, bq, wkv, bkv)
+                dxq = ops.linear_dgrad(dq_buf, w, t5=True)
+                dwqkv, _ = ops.linear_wgrad(dq_buf, xq, want_bias=False, t5=True)
+                dbqkv = ops.colsum(dq_buf, 3 * Cc) if has_b else None
+                dwq, dwkv = dwqkv[:Cc], dwqkv[Cc:]
+                dbq, dbkv = (dbqkv[:Cc], dbqkv[Cc:]) if has_b else (None, None)
+                dxkv = None
+        elif cross:
             dxq = ops.linear_dgrad(dq_buf, wq)
             dwq, dbq = ops.linear_wgrad(dq_buf, xq, want_bias=has_b)
             dxkv = ops.linear_dgrad(dkv_buf, wkv)
