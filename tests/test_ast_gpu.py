@@ -202,3 +202,28 @@ def test_batched_weight_rerounding_is_bit_identical(monkeypatch):
     l1, p1 = run(True)
     assert l0 == l1
     assert all(torch.equal(a, b) for a, b in zip(p0, p1))
+
+
+def test_direct_gradient_writes_match_autograd_accumulation():
+    """TrainStep lets the kernels write parameter gradients straight into the bucket slots (ops.grad_slot) and the
+    Functions return None; the plain autograd path (gradients returned and accumulated) must give the same bits."""
+    import uwr
+    from uwr.train import GradBuckets
+
+    g = torch.Generator().manual_seed(5)
+    raw = (torch.rand(2, 3, 128, 128, generator=g) * 2 - 1).cuda()
+    cot = torch.randn(2, 3, 128, 128, generator=g).cuda()
+
+    def grads(direct):
+        torch.manual_seed(1234)
+        m = uwr.AST(img_size=128).cuda().eval()
+        if direct:
+            buckets = GradBuckets(m.parameters())   # .grad = bucket views, flagged for in-place gradient writes
+            buckets.zero()
+        m(raw).backward(cot)
+        return {n: p.grad.detach().clone() for n, p in m.named_parameters()}
+
+    a, b = grads(False), grads(True)
+    assert a.keys() == b.keys()
+    for n in a:
+        assert torch.equal(a[n], b[n]), n

@@ -174,6 +174,7 @@ class AttnBlockFn(torch.autograd.Function):
         o = ops.window_attn_fwd(qkv, 0, qkv, Cc, 2 * Cc, table, wparam, B, H, W, heads, hd, shift, scale)
         x1 = ops.linear(o, ops.rounded_weight(wp), bp, residual=x2, rowscale=dp_scale, rows_per_group=L, t5=True)
         ctx.save_for_backward(x2, n1w, mean, rstd, y1, qkv, o, wq, bq, wkv, bkv, table, wparam, wp, dp_scale)
+        ctx.n1b, ctx.bp = n1b, bp   # only their gradient slots are needed in backward
         ctx.meta = (B, L, Cc, H, W, heads, hd, shift, scale)
         return x1.view(B, L, Cc)
 
@@ -183,23 +184,30 @@ class AttnBlockFn(torch.autograd.Function):
         x2, n1w, mean, rstd, y1, qkv, o, wq, bq, wkv, bkv, table, wparam, wp, dp = ctx.saved_tensors
         B, L, Cc, H, W, heads, hd, shift, scale = ctx.meta
         d = _c(dx1).view(B * L, Cc)
+        # parameter gradients are written straight into their bucket slots when uwr.train owns them (ops.grad_slot);
+        # the Function then returns None for them and autograd's per-parameter `.grad += g` kernel disappears
+        bp = ctx.bp
+        g_bp, g_wp, g_tab, g_w = (ops.grad_slot(t) if t is not None else None for t in (bp, wp, table, wparam))
+        g_n1w, g_n1b = ops.grad_slot(n1w), ops.grad_slot(ctx.n1b)
         # DropPath-scaled (and, in tf32 mode, TF32-rounded) branch gradient: operand of three GEMMs
-        d_s, dbp = ops.scale_round_colsum(d, Cc, dp, L)   # the column sums are the proj bias gradient
+        d_s, dbp = ops.scale_round_colsum(d, Cc, dp, L, cs_out=g_bp)   # the column sums are the proj bias gradient
         d_o = ops.linear_dgrad(d_s, ops.rounded_weight(wp), t5=True)
-        dwp, _ = ops.linear_wgrad(d_s, o, want_bias=False, t5=True)
+        dwp, _ = ops.linear_wgrad(d_s, o, want_bias=False, t5=True, out=g_wp)
         del d_s
         dqkv, _, dtable, dw = ops.window_attn_bwd(d_o, qkv, 0, qkv, Cc, 2 * Cc, table, wparam, B, H, W, heads, hd,
-                                                  shift, scale)
+                                                  shift, scale, dtable_out=g_tab, dw_out=g_w)
         del d_o
         dy1 = _qkv_dgrad(dqkv, wq, bq, wkv, bkv)
         dwqkv, _ = ops.linear_wgrad(dqkv, y1, want_bias=False, t5=True)
         dbqkv = ops.colsum(dqkv, 3 * Cc) if bq is not None else None
         del dqkv
-        dx, dg, db = ops.layernorm_bwd(dy1, x2, n1w, mean, rstd, dres=d)
+        dx, dg, db = ops.layernorm_bwd(dy1, x2, n1w, mean, rstd, dres=d, dgamma_out=g_n1w, dbeta_out=g_n1b)
         dbq = dbqkv[:Cc] if bq is not None else None
         dbkv = dbqkv[Cc:] if bq is not None else None
-        return (dx.view(B, L, Cc), dg, db, dwqkv[:Cc], dbq, dwqkv[Cc:], dbkv, dtable,
-                dw if wparam is not None else None, dwp, dbp, None, None, None, None, None, None)
+        nz = lambda g, slot: None if slot is not None else g
+        return (dx.view(B, L, Cc), nz(dg, g_n1w), nz(db, g_n1b), dwqkv[:Cc], dbq, dwqkv[Cc:], dbkv, nz(dtable, g_tab),
+                nz(dw, g_w) if wparam is not None else None, nz(dwp, g_wp), nz(dbp, g_bp), None, None, None, None, None,
+                None)
 
 
 class LeFFBlockFn(torch.autograd.Function):
@@ -218,6 +226,7 @@ class LeFFBlockFn(torch.autograd.Function):
         out = ops.linear(h2, ops.rounded_weight(w2), b2, residual=x2, rowscale=dp_scale, rows_per_group=L, t5=True)
         if need_bwd:
             ctx.save_for_backward(x2, n2w, mean, rstd, y2, u, v, h2, w1, dww, w2, dp_scale)
+            ctx.biases = (n2b, b1, dwb, b2)   # only their gradient slots are needed in backward
         ctx.meta = (B, L, Cc, Ch, H, W)
         return out.view(B, L, Cc)
 
@@ -227,16 +236,23 @@ class LeFFBlockFn(torch.autograd.Function):
         x2, n2w, mean, rstd, y2, u, v, h2, w1, dww, w2, dp = ctx.saved_tensors
         B, L, Cc, Ch, H, W = ctx.meta
         d = _c(dout).view(B * L, Cc)
-        d_s, db2 = ops.scale_round_colsum(d, Cc, dp, L)   # column sums = linear2 bias gradient
+        n2b, b1, dwb, b2 = ctx.biases
+        g = {k: (ops.grad_slot(t) if t is not None else None)
+             for k, t in dict(n2w=n2w, n2b=n2b, w1=w1, b1=b1, dww=dww, dwb=dwb, w2=w2, b2=b2).items()}
+        d_s, db2 = ops.scale_round_colsum(d, Cc, dp, L, cs_out=g["b2"])   # column sums = linear2 bias gradient
         # dv = (d_s W2) * gelu'(v): the second GELU's derivative (saved by the forward) rides in the
         # GEMM epilogue
         dv = ops.linear_dgrad(d_s, ops.rounded_weight(w2), mul_by=v, t5=True)
-        dw2, _ = ops.linear_wgrad(d_s, h2, want_bias=False, t5=True)
+        dw2, _ = ops.linear_wgrad(d_s, h2, want_bias=False, t5=True, out=g["w2"])
         del d_s
-        du, ddww, ddwb, db1 = ops.dwconv_gelu_bwd(dv, u, dww, B, H, W, Ch, want_du_colsum=True)
+        du, ddww, ddwb, db1 = ops.dwconv_gelu_bwd(dv, u, dww, B, H, W, Ch, want_du_colsum=True, dweight_out=g["dww"],
+                                                  dbias_out=g["dwb"], dusum_out=g["b1"])
         del dv
         dy2 = ops.linear_dgrad(du, ops.rounded_weight(w1), t5=True)
-        dw1, _ = ops.linear_wgrad(du, y2, want_bias=False, t5=True)
+        dw1, _ = ops.linear_wgrad(du, y2, want_bias=False, t5=True, out=g["w1"])
         del du
-        dx, dg, db = ops.layernorm_bwd(dy2, x2, n2w, mean, rstd, dres=d)
+        dx, dg, db = ops.layernorm_bwd(dy2, x2, n2w, mean, rstd, dres=d, dgamma_out=g["n2w"], dbeta_out=g["n2b"])
+        nz = lambda grad, k: None if g[k] is not None else grad
+        dg, db, dw1, db1, ddww, ddwb, dw2, db2 = (nz(dg, "n2w"), nz(db, "n2b"), nz(dw1, "w1"), nz(db1, "b1"),
+                                                  nz(ddww, "dww"), nz(ddwb, "dwb"), nz(dw2, "w2"), nz(db2, "b2"))
         return dx.view(B, L, Cc), dg, db, dw1, db1, ddww, ddwb, dw2, db2, None, None, None

@@ -188,11 +188,11 @@ def linear_dgrad(dy2d, weight, *, weight2=None, rowscale=None, rows_per_group=0,
     return out
 
 
-def linear_wgrad(dy2d, x2d, *, want_bias=True, rowscale=None, rows_per_group=0, t5=False):
-    """dW[N,K] = (s*dy)^T x ; db[N] = colsum(s*dy).  dy: (M,N) view, x: (M,K) view."""
+def linear_wgrad(dy2d, x2d, *, want_bias=True, rowscale=None, rows_per_group=0, t5=False, out=None):
+    """dW[N,K] = (s*dy)^T x ; db[N] = colsum(s*dy).  dy: (M,N) view, x: (M,K) view.  out: dense (N,K) buffer."""
     M, N = dy2d.shape
     K = x2d.shape[1]
-    dW = _empty((N, K), dy2d)
+    dW = out.view(N, K) if out is not None else _empty((N, K), dy2d)
     db = _empty((N,), dy2d) if want_bias else None
     gemm(dy2d, x2d, dW, N, K, M, lda=dy2d.stride(0), ldb=x2d.stride(0), ldc=K, a_km=True, b_nk=False,
          rowscale=rowscale, rows_per_group=rows_per_group, colsum=db, t5=t5)
@@ -210,18 +210,34 @@ def scale_round(src2d, cols, rowscale=None, rows_per_group=0, out=None):
     return out
 
 
-def scale_round_colsum(src2d, cols, rowscale=None, rows_per_group=0):
+def scale_round_colsum(src2d, cols, rowscale=None, rows_per_group=0, cs_out=None):
     """scale_round + column sums of the result (bias gradient of the consuming Linear) in one pass."""
     rows = src2d.shape[0]
     if cols % 4 or (cols // 4) > 256 or 256 % (cols // 4):
         out = scale_round(src2d, cols, rowscale, rows_per_group)
-        return out, colsum(out, cols)
+        cs = colsum(out, cols)
+        if cs_out is not None:
+            cs_out.copy_(cs)
+            cs = cs_out
+        return out, cs
     out = _empty((rows, cols), src2d)
-    cs = _empty((cols,), src2d)
+    cs = cs_out if cs_out is not None else _empty((cols,), src2d)
     ws = _ws(1024 * cols * 4, src2d)
     _run("uwr_scale_round_colsum", f"rows{rows} C{cols}", 8 * rows * cols, 0.0, _ptr(src2d), src2d.stride(0),
          _ptr(out), rows, cols, _ptr(rowscale), rows_per_group, int(_PASSES == 1), _ptr(cs), _ptr(ws))
     return out, cs
+
+
+def grad_slot(p):
+    """The preallocated gradient buffer of a parameter whose gradients are owned by uwr.train.GradBuckets
+    (flag `_uwr_direct`): kernels write the gradient straight into it and the autograd Function returns None,
+    which saves autograd's `.grad += g` kernel per parameter (~250 tiny launches per AST step).  Overwrite
+    semantics: only valid because TrainStep zeroes the buckets and every parameter gets one gradient per step."""
+    if getattr(p, "_uwr_direct", False):
+        g = p.grad
+        if g is not None and g.is_cuda and g.is_contiguous() and g.dtype == torch.float32:
+            return g
+    return None
 
 
 def _fresh(w, tag):
@@ -369,11 +385,11 @@ def layernorm_fwd(x2d, gamma, beta, eps=1e-5, save_stats=True):
     return y, mean, rstd
 
 
-def layernorm_bwd(dy2d, x2d, gamma, mean, rstd, dres=None):
+def layernorm_bwd(dy2d, x2d, gamma, mean, rstd, dres=None, dgamma_out=None, dbeta_out=None):
     rows, Cc = x2d.shape
     dx = torch.empty_like(x2d)
-    dgamma = torch.empty_like(gamma)
-    dbeta = torch.empty_like(gamma)
+    dgamma = dgamma_out if dgamma_out is not None else torch.empty_like(gamma)
+    dbeta = dbeta_out if dbeta_out is not None else torch.empty_like(gamma)
     ws = _ws(fn["uwr_layernorm_bwd_workspace_bytes"](rows, Cc), x2d)
     _run("uwr_layernorm_bwd", f"rows{rows} C{Cc}", (12 + (4 if dres is not None else 0)) * rows * Cc,
          16.0 * rows * Cc, _ptr(dy2d), _ptr(x2d), _ptr(gamma), _ptr(mean), _ptr(rstd), _ptr(dres), _ptr(dx),
@@ -402,14 +418,14 @@ def window_attn_fwd(q_buf, q_off, kv_buf, k_off, v_off, table, w_param, B, H, W,
 
 
 def window_attn_bwd(dout, q_buf, q_off, kv_buf, k_off, v_off, table, w_param, B, H, W, heads, head_dim, shift,
-                    scale, dq_buf=None, dkv_buf=None):
+                    scale, dq_buf=None, dkv_buf=None, dtable_out=None, dw_out=None):
     d = _attn_desc(q_buf, q_off, kv_buf, k_off, v_off, table, w_param, B, H, W, heads, head_dim, shift, scale)
     if dq_buf is None:
         dq_buf = torch.empty_like(q_buf)
     if dkv_buf is None:
         dkv_buf = dq_buf if kv_buf.data_ptr() == q_buf.data_ptr() else torch.empty_like(kv_buf)
-    dtable = torch.empty_like(table)
-    dw = _empty((2,), q_buf)
+    dtable = dtable_out if dtable_out is not None else torch.empty_like(table)
+    dw = dw_out if dw_out is not None else _empty((2,), q_buf)
     ws = _ws(fn["uwr_window_attn_bwd_workspace_bytes"](C.byref(d)), q_buf)
     tiles = B * (H // 8) * (W // 8) * heads
     _run("uwr_window_attn_bwd", f"tiles{tiles} hd{head_dim} shift{shift}", tiles * 7 * 64 * head_dim * 4,
@@ -438,14 +454,15 @@ def gelu_gate_bwd(dh2, u2d, v, Ch, mode, du=None):
     return dv
 
 
-def dwconv_gelu_bwd(dv, u2d, weight, B, H, W, Ch, du=None, plain=False, want_du_colsum=False):
+def dwconv_gelu_bwd(dv, u2d, weight, B, H, W, Ch, du=None, plain=False, want_du_colsum=False, dweight_out=None,
+                    dbias_out=None, dusum_out=None):
     """dv = dL/d(conv output).  Returns du (same row stride as u; only [:, :Ch] is written), dweight, dbias
     [, column sums of du[:, :Ch]]."""
     if du is None:
         du = torch.empty_like(u2d)
-    dweight = torch.empty_like(weight)
-    dbias = _empty((Ch,), u2d)
-    dusum = _empty((Ch,), u2d) if want_du_colsum else None
+    dweight = dweight_out if dweight_out is not None else torch.empty_like(weight)
+    dbias = dbias_out if dbias_out is not None else _empty((Ch,), u2d)
+    dusum = (dusum_out if dusum_out is not None else _empty((Ch,), u2d)) if want_du_colsum else None
     ws = _ws(fn["uwr_dwconv_gelu_bwd_workspace_bytes"](B, H, W, Ch), u2d)
     n = B * H * W * Ch
     _run("uwr_dwconv_gelu_bwd", f"B{B} H{H} Ch{Ch}", 4 * n * 3, 36.0 * n,

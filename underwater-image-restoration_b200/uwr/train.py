@@ -39,6 +39,7 @@ class GradBuckets:
             off = 0
             for p in ps:
                 p.grad = flat[off:off + p.numel()].view_as(p)
+                p._uwr_direct = True   # kernels may write this gradient in place (ops.grad_slot)
                 off += -(-p.numel() // 4) * 4
                 self._bucket_of[id(p)] = bi
             self.flat.append(flat)
