@@ -218,7 +218,8 @@ def test_direct_gradient_writes_match_autograd_accumulation():
         torch.manual_seed(1234)
         m = uwr.AST(img_size=128).cuda().eval()
         if direct:
-            buckets = GradBuckets(m.parameters())   # .grad = bucket views, flagged for in-place gradient writes
+            # .grad = bucket views flagged for in-place gradient writes; to_q | to_kv slots back to back
+            buckets = GradBuckets(m.parameters(), adjacent=m.adjacent_grad_pairs())
             buckets.zero()
         m(raw).backward(cot)
         return {n: p.grad.detach().clone() for n, p in m.named_parameters()}

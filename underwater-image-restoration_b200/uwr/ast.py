@@ -370,6 +370,17 @@ class AST(nn.Module):
         return (f"embed_dim={self.embed_dim}, token_projection={self.token_projection}, "
                 f"token_mlp={self.mlp},win_size={self.win_size}")
 
+    def adjacent_grad_pairs(self):
+        """(to_q, to_kv) weight and bias pairs: their gradients are one packed-QKV GEMM / column sum, so
+        uwr.train.GradBuckets lays their slots out back to back (ops.fused_grad_slot)."""
+        pairs = []
+        for m in self.modules():
+            if isinstance(m, LinearProjection):
+                pairs.append((m.to_q.weight, m.to_kv.weight))
+                if m.to_q.bias is not None:
+                    pairs.append((m.to_q.bias, m.to_kv.bias))
+        return pairs
+
     def forward(self, x, mask=None):
         if not x.is_cuda:
             raise RuntimeError("uwr AST runs on CUDA (B200) only; there is no CPU fallback")

@@ -198,14 +198,18 @@ class AttnBlockFn(torch.autograd.Function):
                                                   shift, scale, dtable_out=g_tab, dw_out=g_w)
         del d_o
         dy1 = _qkv_dgrad(dqkv, wq, bq, wkv, bkv)
-        dwqkv, _ = ops.linear_wgrad(dqkv, y1, want_bias=False, t5=True)
-        dbqkv = ops.colsum(dqkv, 3 * Cc) if bq is not None else None
+        # [to_q; to_kv] weight / bias gradients come out of one GEMM / one column sum: written in place when the two
+        # bucket slots are adjacent (GradBuckets(adjacent=...))
+        g_wqkv = ops.fused_grad_slot(wq, wkv)
+        g_bqkv = ops.fused_grad_slot(bq, bkv) if bq is not None else None
+        dwqkv, _ = ops.linear_wgrad(dqkv, y1, want_bias=False, t5=True, out=g_wqkv)
+        dbqkv = ops.colsum(dqkv, 3 * Cc, out=g_bqkv) if bq is not None else None
         del dqkv
         dx, dg, db = ops.layernorm_bwd(dy1, x2, n1w, mean, rstd, dres=d, dgamma_out=g_n1w, dbeta_out=g_n1b)
-        dbq = dbqkv[:Cc] if bq is not None else None
-        dbkv = dbqkv[Cc:] if bq is not None else None
+        dwq, dwkv = (None, None) if g_wqkv is not None else (dwqkv[:Cc], dwqkv[Cc:])
+        dbq, dbkv = (None, None) if (bq is None or g_bqkv is not None) else (dbqkv[:Cc], dbqkv[Cc:])
         nz = lambda g, slot: None if slot is not None else g
-        return (dx.view(B, L, Cc), nz(dg, g_n1w), nz(db, g_n1b), dwqkv[:Cc], dbq, dwqkv[Cc:], dbkv, nz(dtable, g_tab),
+        return (dx.view(B, L, Cc), nz(dg, g_n1w), nz(db, g_n1b), dwq, dbq, dwkv, dbkv, nz(dtable, g_tab),
                 nz(dw, g_w) if wparam is not None else None, nz(dwp, g_wp), nz(dbp, g_bp), None, None, None, None, None,
                 None)
 

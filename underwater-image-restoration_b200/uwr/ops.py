@@ -240,6 +240,22 @@ def grad_slot(p):
     return None
 
 
+def fused_grad_slot(p0, p1):
+    """One gradient buffer spanning two parameters whose bucket slots are adjacent (to_q | to_kv weights or
+    biases, laid out back to back by GradBuckets): the packed-QKV weight gradient is written once, in place."""
+    g0, g1 = grad_slot(p0), grad_slot(p1)
+    if g0 is None or g1 is None or g0.data_ptr() + g0.numel() * 4 != g1.data_ptr():
+        return None
+    tail = tuple(g0.shape[1:])
+    if tuple(g1.shape[1:]) != tail:
+        return None
+    rows = g0.shape[0] + g1.shape[0]
+    inner = 1
+    for d in tail:
+        inner *= d
+    return torch.as_strided(g0, (rows,) + tail, (inner,) + tuple(g0.stride()[1:]))
+
+
 def _fresh(w, tag):
     ent = getattr(w, tag, None)
     ver = (w.data_ptr(), w._version, WEIGHT_EPOCH, _PASSES)
@@ -556,9 +572,10 @@ def copy2d(src2d, dst2d, cols, accumulate=False):
                            int(accumulate))
 
 
-def colsum(x2d, cols):
+def colsum(x2d, cols, out=None):
     rows = x2d.shape[0]
-    out = _empty((cols,), x2d)
+    if out is None:
+        out = _empty((cols,), x2d)
     ws = _ws(1024 * cols * 4, x2d)
     _run("uwr_colsum", f"rows{rows} C{cols}", 4 * rows * cols, 0.0, _ptr(x2d), x2d.stride(0), _ptr(out), _ptr(ws),
          rows, cols)

@@ -19,10 +19,22 @@ from .optim import FusedClipAdam
 
 
 class GradBuckets:
-    def __init__(self, params, bucket_bytes=32 << 20, group=None, world_size=1):
+    def __init__(self, params, bucket_bytes=32 << 20, group=None, world_size=1, adjacent=()):
+        """adjacent: pairs (p0, p1) whose slots must be laid out back to back, p0 first (their gradients come
+        out of one kernel, e.g. the packed to_q | to_kv weight gradient: ops.fused_grad_slot)."""
         self.params = [p for p in params if p.requires_grad]
         self.group, self.world = group, world_size
         order = list(reversed(self.params))  # roughly the order gradients are produced in backward
+        follower = {id(a): b for a, b in adjacent}
+        led = {id(b) for _, b in adjacent}
+        fixed = []
+        for p in order:
+            if id(p) in led:
+                continue              # placed right after its leader
+            fixed.append(p)
+            if id(p) in follower:
+                fixed.append(follower[id(p)])
+        order = fixed
         self.buckets, cur, cur_n = [], [], 0
         for p in order:
             cur.append(p)
@@ -85,7 +97,8 @@ class TrainStep:
         self.model = model
         self.world = world_size
         self.lossf = LossFunction(loss_name, "cuda", batch_divisor=(local_batch * world_size) if local_batch else None)
-        self.buckets = GradBuckets(model.parameters(), bucket_bytes, group, world_size)
+        adjacent = model.adjacent_grad_pairs() if hasattr(model, "adjacent_grad_pairs") else ()
+        self.buckets = GradBuckets(model.parameters(), bucket_bytes, group, world_size, adjacent=adjacent)
         self.opt = FusedClipAdam(model.parameters(), lr=lr, weight_decay=0.01 if optim == "adamw" else 0.0,
                                  decoupled=(optim == "adamw"), max_norm=1.0, grad_prescale=1.0 / world_size)
 
