@@ -54,3 +54,25 @@ def test_grad_buckets_match_global_batch(tmp_path, overlap):
     for a, p in zip(got, net.parameters()):
         assert torch.allclose(a, p.grad, rtol=1e-5, atol=1e-7)   # SUM over ranks of local/global-divisor grads
     assert torch.count_nonzero(got[-1]) == 0
+
+
+def test_grad_buckets_adjacent_pairs_are_contiguous():
+    """GradBuckets(adjacent=[(a, b)]): b's gradient slot starts right where a's ends (what ops.fused_grad_slot
+    needs for the packed to_q | to_kv gradient), every parameter still owns exactly one slot."""
+    for p in (ROOT, PKG):
+        if p not in sys.path:
+            sys.path.insert(0, p)
+    from uwr.train import GradBuckets
+    torch.manual_seed(0)
+    ps = [torch.nn.Parameter(torch.randn(*s)) for s in ((8, 4), (8,), (16, 4), (16,), (5,), (4, 4))]
+    buckets = GradBuckets(ps, bucket_bytes=1 << 20, adjacent=[(ps[0], ps[2]), (ps[1], ps[3])])
+    for a, b in ((ps[0], ps[2]), (ps[1], ps[3])):
+        assert a.grad.data_ptr() + a.numel() * 4 == b.grad.data_ptr()
+    seen = set()
+    for p in ps:
+        assert p.grad.shape == p.shape and p.grad.data_ptr() % 16 == 0
+        rng = (p.grad.data_ptr(), p.grad.data_ptr() + p.numel() * 4)
+        assert all(rng[1] <= s or rng[0] >= e for s, e in seen)   # no overlap
+        seen.add(rng)
+    buckets.zero()
+    assert all(torch.count_nonzero(p.grad) == 0 for p in ps)
