@@ -114,6 +114,16 @@ size_t uwr_layernorm_bwd_workspace_bytes(long long rows, int C);
 int uwr_layernorm_bwd(const float* dy, const float* x, const float* gamma, const float* mean,
                       const float* rstd, const float* dres, float* dx, float* dgamma,
                       float* dbeta, float* partials, long long rows, int C, uwr_stream_t stream);
+/* uwr_layernorm_bwd that ALSO emits the GEMM operand of the next backward function: ds_out = tf32(rowscale[row /
+ * rows_per_group] * dx) (DropPath-scaled; rounded in single-pass TF32 mode only) and ds_colsum = column sums of
+ * ds_out (bias gradient of the Linear consuming it) -- what uwr_scale_round_colsum would compute in a separate pass.
+ * Served for C in {16,32,64,128,256,512} (uwr_layernorm_bwd_ds_supported); 16-byte aligned pointers. */
+int uwr_layernorm_bwd_ds_supported(long long rows, int C);
+size_t uwr_layernorm_bwd_ds_workspace_bytes(long long rows, int C);
+int uwr_layernorm_bwd_ds(const float* dy, const float* x, const float* gamma, const float* mean,
+                         const float* rstd, const float* dres, float* dx, float* dgamma, float* dbeta,
+                         const float* ds_rowscale, int ds_rows_per_group, float* ds_out, float* ds_colsum,
+                         float* workspace, long long rows, int C, uwr_stream_t stream);
 
 /* ---- adaptive sparse window attention (WindowAttention_sparse.forward, AST.py:187-219;
  *      roll / window_partition / window_reverse, AST.py:377-402,596-618; shift mask 568-588) --

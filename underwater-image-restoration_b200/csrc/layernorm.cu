@@ -219,7 +219,10 @@ __global__ void __launch_bounds__(LN_WARPS * 32) ln_bwd_kernel(const float* __re
 // Vectorised backward for C = 4 * LPR * V4 (same lane layout as ln_fwd_vec_kernel): 128-bit accesses, 32 / LPR
 // rows per warp pass, two passes in flight for the narrow rows.  The warp-per-row kernel ran the 128-byte rows
 // (C = 32) at 3.5 TB/s and the short, wide tensors of the deep stages (16 384 x 512) at 1.3 TB/s.
-template <int LPR, int V4>
+// DS: additionally emit d_s = tf32(rowscale[row / rpg] * dx) and its column sums — the DropPath-scaled, rounded copy
+// of the residual-stream gradient that the NEXT backward function feeds to its GEMMs (it used to be a separate
+// read + write pass, uwr_scale_round_colsum) — as a third partial row.
+template <int LPR, int V4, bool DS>
 __global__ void __launch_bounds__(LN_WARPS * 32) ln_bwd_vec_kernel(const float* __restrict__ dy,
                                                                    const float* __restrict__ x,
                                                                    const float* __restrict__ gamma,
@@ -227,19 +230,21 @@ __global__ void __launch_bounds__(LN_WARPS * 32) ln_bwd_vec_kernel(const float* 
                                                                    const float* __restrict__ rstd,
                                                                    const float* __restrict__ dres,
                                                                    float* __restrict__ dx, float* __restrict__ partials,
-                                                                   long long rows) {
+                                                                   long long rows, const float* __restrict__ ds_scale,
+                                                                   int ds_rpg, float* __restrict__ ds_out, int ds_round) {
     constexpr int C = 4 * LPR * V4;
     constexpr int RPW = 32 / LPR;
     constexpr int RPI = V4 == 1 ? 2 : 1;
     __shared__ __align__(16) float sh[LN_WARPS][C];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int sub = lane / LPR, l = lane % LPR;
-    float4 gm[V4], dg[V4], db[V4];
+    float4 gm[V4], dg[V4], db[V4], cs[DS ? V4 : 1];
 #pragma unroll
     for (int i = 0; i < V4; ++i) {
         gm[i] = *reinterpret_cast<const float4*>(gamma + (l + LPR * i) * 4);
         dg[i] = make_float4(0.f, 0.f, 0.f, 0.f);
         db[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (DS) cs[i] = make_float4(0.f, 0.f, 0.f, 0.f);
     }
     constexpr float invC = 1.0f / (float)C;
     const long long stride = (long long)gridDim.x * LN_WARPS * RPW;
@@ -286,20 +291,32 @@ __global__ void __launch_bounds__(LN_WARPS * 32) ln_bwd_vec_kernel(const float* 
             s1 *= invC;
             s2 *= invC;
             if (r < rows) {
+                const float sc = (DS && ds_scale != nullptr) ? __ldg(ds_scale + r / ds_rpg) : 1.f;
 #pragma unroll
-                for (int i = 0; i < V4; ++i)
-                    *reinterpret_cast<float4*>(dx + r * C + (l + LPR * i) * 4) =
-                        make_float4(rs[k] * (g[i].x - s1 - xh[i].x * s2) + rv[k][i].x, rs[k] * (g[i].y - s1 - xh[i].y * s2) + rv[k][i].y,
-                                    rs[k] * (g[i].z - s1 - xh[i].z * s2) + rv[k][i].z, rs[k] * (g[i].w - s1 - xh[i].w * s2) + rv[k][i].w);
+                for (int i = 0; i < V4; ++i) {
+                    const float4 o = make_float4(rs[k] * (g[i].x - s1 - xh[i].x * s2) + rv[k][i].x,
+                                                 rs[k] * (g[i].y - s1 - xh[i].y * s2) + rv[k][i].y,
+                                                 rs[k] * (g[i].z - s1 - xh[i].z * s2) + rv[k][i].z,
+                                                 rs[k] * (g[i].w - s1 - xh[i].w * s2) + rv[k][i].w);
+                    *reinterpret_cast<float4*>(dx + r * C + (l + LPR * i) * 4) = o;
+                    if (DS) {
+                        float4 q = make_float4(o.x * sc, o.y * sc, o.z * sc, o.w * sc);
+                        if (ds_round) q = make_float4(tf32_round(q.x), tf32_round(q.y), tf32_round(q.z), tf32_round(q.w));
+                        *reinterpret_cast<float4*>(ds_out + r * C + (l + LPR * i) * 4) = q;
+                        cs[i].x += q.x; cs[i].y += q.y; cs[i].z += q.z; cs[i].w += q.w;
+                    }
+                }
             }
         }
     }
-    // dgamma / dbeta: lanes that share a column group (across the RPW sub-rows of the warp), then the warps
+    // dgamma / dbeta [/ column sums of d_s]: lanes that share a column group (across the RPW sub-rows of the
+    // warp), then the warps
+    constexpr int NP = DS ? 3 : 2;
 #pragma unroll
-    for (int pass = 0; pass < 2; ++pass) {
+    for (int pass = 0; pass < NP; ++pass) {
 #pragma unroll
         for (int i = 0; i < V4; ++i) {
-            float4 v = pass == 0 ? dg[i] : db[i];
+            float4 v = pass == 0 ? dg[i] : (pass == 1 ? db[i] : cs[DS ? i : 0]);
 #pragma unroll
             for (int o = LPR; o < 32; o <<= 1) {
                 v.x += __shfl_xor_sync(0xffffffffu, v.x, o);
@@ -314,9 +331,33 @@ __global__ void __launch_bounds__(LN_WARPS * 32) ln_bwd_vec_kernel(const float* 
             float t = 0.f;
 #pragma unroll
             for (int w = 0; w < LN_WARPS; ++w) t += sh[w][c];
-            partials[((long long)blockIdx.x * 2 + pass) * C + c] = t;
+            partials[((long long)blockIdx.x * NP + pass) * C + c] = t;
         }
         __syncthreads();
+    }
+}
+
+// three-output variant of ln_param_reduce_kernel for the DS kernels (partial rows: dgamma, dbeta, colsum(d_s))
+__global__ void __launch_bounds__(1024) ln_param_reduce3_kernel(const float* __restrict__ partials,
+                                                                float* __restrict__ dgamma, float* __restrict__ dbeta,
+                                                                float* __restrict__ colsum, int nblocks, int C) {
+    __shared__ float sh[3][32][33];
+    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+    const int c = blockIdx.x * 32 + tx;
+    float a[3] = {0.f, 0.f, 0.f};
+    if (c < C)
+        for (int i = ty; i < nblocks; i += 32) {
+#pragma unroll
+            for (int k = 0; k < 3; ++k) a[k] += partials[((long long)i * 3 + k) * C + c];
+        }
+#pragma unroll
+    for (int k = 0; k < 3; ++k) sh[k][ty][tx] = a[k];
+    __syncthreads();
+    const int co = blockIdx.x * 32 + ty;
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+        const float v = warp_sum(sh[k][tx][ty]);
+        if (tx == 0 && co < C) (k == 0 ? dgamma : (k == 1 ? dbeta : colsum))[co] = v;
     }
 }
 
@@ -418,8 +459,9 @@ extern "C" int uwr_layernorm_bwd(const float* dy, const float* x, const float* g
         const long long cap = ln_blocks(rows);                                                                    \
         if (b > cap) b = cap;                                                                                     \
         if (b < 1) b = 1;                                                                                         \
-        ln_bwd_vec_kernel<L, V><<<(unsigned)b, LN_WARPS * 32, 0, stream>>>(dy, x, gamma, mean, rstd, dres, dx,    \
-                                                                           partials, rows);                      \
+        ln_bwd_vec_kernel<L, V, false><<<(unsigned)b, LN_WARPS * 32, 0, stream>>>(dy, x, gamma, mean, rstd, dres, \
+                                                                                  dx, partials, rows, nullptr, 1, \
+                                                                                  nullptr, 0);                    \
         UWR_CHECK_LAUNCH("ln_bwd_vec_kernel");                                                                    \
         ln_param_reduce_kernel<<<uwr_cdiv(C, 32), 1024, 0, stream>>>(partials, dgamma, dbeta, (int)b, C);         \
         UWR_CHECK_LAUNCH("ln_param_reduce_kernel");                                                               \
@@ -452,4 +494,51 @@ extern "C" int uwr_layernorm_bwd(const float* dy, const float* x, const float* g
     ln_param_reduce_kernel<<<uwr_cdiv(C, 32), 1024, 0, stream>>>(partials, dgamma, dbeta, blocks, C);
     UWR_CHECK_LAUNCH("ln_param_reduce_kernel");
     return 0;
+}
+
+// ---- LayerNorm backward that also emits the next backward function's GEMM operand ------------------------------
+// d_s = tf32(rowscale[row / rows_per_group] * dx) (rounded only in single-pass TF32 mode) and ds_colsum = column
+// sums of d_s (the bias gradient of the Linear that consumes d_s).  Served for C in {16, 32, 64, 128, 256, 512}.
+extern "C" int uwr_layernorm_bwd_ds_supported(long long rows, int C) {
+    return rows > 0 && (C == 16 || C == 32 || C == 64 || C == 128 || C == 256 || C == 512);
+}
+
+extern "C" size_t uwr_layernorm_bwd_ds_workspace_bytes(long long rows, int C) {
+    return (size_t)ln_blocks(rows) * 3 * (size_t)C * sizeof(float);
+}
+
+extern "C" int uwr_layernorm_bwd_ds(const float* dy, const float* x, const float* gamma, const float* mean,
+                                    const float* rstd, const float* dres, float* dx, float* dgamma, float* dbeta,
+                                    const float* ds_rowscale, int ds_rows_per_group, float* ds_out, float* ds_colsum,
+                                    float* partials, long long rows, int C, uwr_stream_t stream_) {
+    cudaStream_t stream = (cudaStream_t)stream_;
+    UWR_REQUIRE(dy && x && gamma && mean && rstd && dx && dgamma && dbeta && partials && ds_out && ds_colsum,
+                "uwr_layernorm_bwd_ds: null pointer");
+    UWR_REQUIRE(uwr_layernorm_bwd_ds_supported(rows, C), "uwr_layernorm_bwd_ds: C=%d unsupported", C);
+    UWR_REQUIRE((((uintptr_t)x | (uintptr_t)dy | (uintptr_t)dx | (uintptr_t)gamma | (uintptr_t)ds_out |
+                  (uintptr_t)(dres ? dres : x)) & 15) == 0, "uwr_layernorm_bwd_ds: pointers must be 16-byte aligned");
+    UWR_REQUIRE(!ds_rowscale || ds_rows_per_group > 0, "uwr_layernorm_bwd_ds: rowscale needs rows_per_group");
+    const int rpg = ds_rows_per_group > 0 ? ds_rows_per_group : 1;
+#define LN_BWD_DS(L, V)                                                                                          \
+    do {                                                                                                          \
+        long long b = (rows + LN_WARPS * (32 / L) * 8 - 1) / (LN_WARPS * (32 / L) * 8);                           \
+        const long long cap = ln_blocks(rows);                                                                    \
+        if (b > cap) b = cap;                                                                                     \
+        if (b < 1) b = 1;                                                                                         \
+        ln_bwd_vec_kernel<L, V, true><<<(unsigned)b, LN_WARPS * 32, 0, stream>>>(                                 \
+            dy, x, gamma, mean, rstd, dres, dx, partials, rows, ds_rowscale, rpg, ds_out, uwr_round_outputs());   \
+        UWR_CHECK_LAUNCH("ln_bwd_vec_kernel<DS>");                                                                \
+        ln_param_reduce3_kernel<<<uwr_cdiv(C, 32), 1024, 0, stream>>>(partials, dgamma, dbeta, ds_colsum, (int)b, C); \
+        UWR_CHECK_LAUNCH("ln_param_reduce3_kernel");                                                              \
+        return 0;                                                                                                 \
+    } while (0)
+    switch (C) {
+        case 16: LN_BWD_DS(4, 1);
+        case 32: LN_BWD_DS(8, 1);
+        case 64: LN_BWD_DS(16, 1);
+        case 128: LN_BWD_DS(32, 1);
+        case 256: LN_BWD_DS(32, 2);
+        default: LN_BWD_DS(32, 4);
+    }
+#undef LN_BWD_DS
 }

@@ -77,6 +77,10 @@ SIGNATURES = {
     "uwr_layernorm_fwd": (c_int, [c_fp, c_fp, c_fp, c_fp, c_fp, c_fp, c_ll, c_int, c_f, c_stream]),
     "uwr_layernorm_bwd_workspace_bytes": (c_sz, [c_ll, c_int]),
     "uwr_layernorm_bwd": (c_int, [c_fp] * 10 + [c_ll, c_int, c_stream]),
+    "uwr_layernorm_bwd_ds_supported": (c_int, [c_ll, c_int]),
+    "uwr_layernorm_bwd_ds_workspace_bytes": (c_sz, [c_ll, c_int]),
+    "uwr_layernorm_bwd_ds": (c_int, [c_fp, c_fp, c_fp, c_fp, c_fp, c_fp, c_fp, c_fp, c_fp, c_fp, c_int, c_fp, c_fp,
+                                     c_fp, c_ll, c_int, c_stream]),
     "uwr_window_attn_fwd": (c_int, [C.POINTER(AttnDesc), c_fp, c_ll, c_stream]),
     "uwr_window_attn_bwd_workspace_bytes": (c_sz, [C.POINTER(AttnDesc)]),
     "uwr_window_attn_bwd": (c_int, [C.POINTER(AttnDesc), c_fp, c_ll, c_fp, c_fp, c_fp, c_fp, c_fp, c_stream]),

@@ -179,25 +179,35 @@ class TransformerBlock(nn.Module):
         return self.drop_path.scale(batch, device) if isinstance(self.drop_path, DropPath) else None
 
     def forward(self, x, mask=None):
+        return self.forward_linked(x, mask, None)[0]
+
+    def forward_linked(self, x, mask=None, link_prev=None):
+        """forward + the backward link to the NEXT block function (blocks.py: the LayerNorm backward of a function
+        emits the rounded, DropPath-scaled gradient copy its predecessor's backward starts from)."""
         if mask is not None:
             raise NotImplementedError("input masks are never passed by the trainer (AST.py:558-565)")
         B, L, C = x.shape
         H = W = int(math.sqrt(L))
+        m = self.mlp
+        leff = isinstance(m, LeFF)
+        grad = torch.is_grad_enabled()
+        link_mid = {} if (self.att and leff and grad) else None
+        link_next = {} if (leff and grad) else None
         if self.att:
             a = self.attn
             x = blocks.AttnBlockFn.apply(
                 x, self.norm1.weight, self.norm1.bias, a.qkv.to_q.weight, a.qkv.to_q.bias, a.qkv.to_kv.weight,
                 a.qkv.to_kv.bias, a.relative_position_bias_table, a.w if a.sparse else None, a.proj.weight,
-                a.proj.bias, self._dp(B, x.device), H, W, self.num_heads, self.shift_size, float(a.scale))
-        m = self.mlp
-        if isinstance(m, LeFF):
+                a.proj.bias, self._dp(B, x.device), H, W, self.num_heads, self.shift_size, float(a.scale),
+                link_prev, link_mid)
+        if leff:
             x = blocks.LeFFBlockFn.apply(
                 x, self.norm2.weight, self.norm2.bias, m.linear1[0].weight, m.linear1[0].bias,
                 m.dwconv[0].weight, m.dwconv[0].bias, m.linear2[0].weight, m.linear2[0].bias,
-                self._dp(B, x.device), H, W)
+                self._dp(B, x.device), H, W, link_mid if self.att else link_prev, link_next)
         else:
             x = m.block_forward(x, self.norm2, self._dp(B, x.device), H, W)
-        return x
+        return x, link_next
 
 
 class BasicASTLayer(nn.Module):
@@ -226,8 +236,9 @@ class BasicASTLayer(nn.Module):
         return f"dim={self.dim}, input_resolution={self.input_resolution}, depth={self.depth}"
 
     def forward(self, x, mask=None):
+        link = None
         for blk in self.blocks:
-            x = blk(x, mask)
+            x, link = blk.forward_linked(x, mask, link)
         return x
 
 

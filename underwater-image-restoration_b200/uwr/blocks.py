@@ -161,14 +161,53 @@ def _qkv_dgrad(dqkv, wq, bq, wkv, bkv):
     return ops.linear_dgrad(dqkv, wq, weight2=wkv)
 
 
+# ---- links between consecutive block functions -----------------------------------------------------------------
+# The backward of a block function starts by turning the incoming residual-stream gradient d into the GEMM operand
+# d_s = tf32(droppath_scale * d) (+ its column sums = a bias gradient).  d is produced by the LayerNorm backward of the
+# function that ran AFTER it in the forward pass, so that kernel can emit d_s in the same pass (uwr_layernorm_bwd_ds).
+# A link is a plain dict shared by the two apply() calls: the consumer registers what it will need at forward time,
+# the producer leaves the result there at backward time; anything missing simply falls back to the separate pass.
+def _link_register(link, dp_scale, L, bias):
+    if link is not None:
+        link.clear()
+        link.update(dp=dp_scale, L=L, bias=bias)
+
+
+def _link_take(link, d):
+    """(d_s, colsum, colsum_is_grad_slot) left by the producer for exactly this gradient tensor, else None."""
+    if link is None:
+        return None
+    pre = link.pop("ds", None)
+    if pre is None or pre[3] != d.data_ptr():
+        return None
+    return pre[0], pre[1], pre[2]
+
+
+def _ln_bwd_linked(link, dy, x2, nw, mean, rstd, d, g_w, g_b):
+    """LayerNorm backward; when a consumer is registered on `link` the kernel also emits its d_s / column sums."""
+    if link is not None and "dp" in link:
+        bias = link["bias"]
+        slot = ops.grad_slot(bias) if bias is not None else None
+        res = ops.layernorm_bwd_ds(dy, x2, nw, mean, rstd, d, link["dp"], link["L"], dgamma_out=g_w, dbeta_out=g_b,
+                                   cs_out=slot)
+        if res is not None:
+            dx, dg, db, d_s, cs = res
+            link["ds"] = (d_s, cs, slot is not None, dx.data_ptr())
+            return dx, dg, db
+    return ops.layernorm_bwd(dy, x2, nw, mean, rstd, dres=d, dgamma_out=g_w, dbeta_out=g_b)
+
+
 class AttnBlockFn(torch.autograd.Function):
     @staticmethod
-    def forward(ctx, x, n1w, n1b, wq, bq, wkv, bkv, table, wparam, wp, bp, dp_scale, H, W, heads, shift, scale):
+    def forward(ctx, x, n1w, n1b, wq, bq, wkv, bkv, table, wparam, wp, bp, dp_scale, H, W, heads, shift, scale,
+                link_in=None, link_out=None):
         x = _c(x)
         B, L, Cc = x.shape
         M = B * L
         x2 = x.view(M, Cc)
         hd = Cc // heads
+        ctx.link_in, ctx.link_out = link_in, link_out   # producer side (our LN1 backward) / consumer side (our d)
+        _link_register(link_out, dp_scale, L, bp)
         y1, mean, rstd = ops.layernorm_fwd(x2, n1w, n1b)
         qkv = _qkv_forward(y1, wq, bq, wkv, bkv)
         o = ops.window_attn_fwd(qkv, 0, qkv, Cc, 2 * Cc, table, wparam, B, H, W, heads, hd, shift, scale)
@@ -189,8 +228,15 @@ class AttnBlockFn(torch.autograd.Function):
         bp = ctx.bp
         g_bp, g_wp, g_tab, g_w = (ops.grad_slot(t) if t is not None else None for t in (bp, wp, table, wparam))
         g_n1w, g_n1b = ops.grad_slot(n1w), ops.grad_slot(ctx.n1b)
-        # DropPath-scaled (and, in tf32 mode, TF32-rounded) branch gradient: operand of three GEMMs
-        d_s, dbp = ops.scale_round_colsum(d, Cc, dp, L, cs_out=g_bp)   # the column sums are the proj bias gradient
+        # DropPath-scaled (and, in tf32 mode, TF32-rounded) branch gradient: operand of three GEMMs; the column sums
+        # are the proj bias gradient.  Usually already emitted by the LayerNorm backward that produced d (link).
+        pre = _link_take(ctx.link_out, d)
+        if pre is not None:
+            d_s, dbp, direct = pre
+            if direct:
+                g_bp = dbp
+        else:
+            d_s, dbp = ops.scale_round_colsum(d, Cc, dp, L, cs_out=g_bp)
         d_o = ops.linear_dgrad(d_s, ops.rounded_weight(wp), t5=True)
         dwp, _ = ops.linear_wgrad(d_s, o, want_bias=False, t5=True, out=g_wp)
         del d_s
@@ -205,23 +251,25 @@ class AttnBlockFn(torch.autograd.Function):
         dwqkv, _ = ops.linear_wgrad(dqkv, y1, want_bias=False, t5=True, out=g_wqkv)
         dbqkv = ops.colsum(dqkv, 3 * Cc, out=g_bqkv) if bq is not None else None
         del dqkv
-        dx, dg, db = ops.layernorm_bwd(dy1, x2, n1w, mean, rstd, dres=d, dgamma_out=g_n1w, dbeta_out=g_n1b)
+        dx, dg, db = _ln_bwd_linked(ctx.link_in, dy1, x2, n1w, mean, rstd, d, g_n1w, g_n1b)
         dwq, dwkv = (None, None) if g_wqkv is not None else (dwqkv[:Cc], dwqkv[Cc:])
         dbq, dbkv = (None, None) if (bq is None or g_bqkv is not None) else (dbqkv[:Cc], dbqkv[Cc:])
         nz = lambda g, slot: None if slot is not None else g
         return (dx.view(B, L, Cc), nz(dg, g_n1w), nz(db, g_n1b), dwq, dbq, dwkv, dbkv, nz(dtable, g_tab),
                 nz(dw, g_w) if wparam is not None else None, nz(dwp, g_wp), nz(dbp, g_bp), None, None, None, None, None,
-                None)
+                None, None, None)
 
 
 class LeFFBlockFn(torch.autograd.Function):
     @staticmethod
-    def forward(ctx, x, n2w, n2b, w1, b1, dww, dwb, w2, b2, dp_scale, H, W):
+    def forward(ctx, x, n2w, n2b, w1, b1, dww, dwb, w2, b2, dp_scale, H, W, link_in=None, link_out=None):
         x = _c(x)
         B, L, Cc = x.shape
         M = B * L
         Ch = w1.shape[0]
         x2 = x.view(M, Cc)
+        ctx.link_in, ctx.link_out = link_in, link_out
+        _link_register(link_out, dp_scale, L, b2)
         y2, mean, rstd = ops.layernorm_fwd(x2, n2w, n2b)
         u = ops.linear(y2, ops.rounded_weight(w1), b1, t5=True)
         need_bwd = any(ctx.needs_input_grad)
@@ -243,7 +291,13 @@ class LeFFBlockFn(torch.autograd.Function):
         n2b, b1, dwb, b2 = ctx.biases
         g = {k: (ops.grad_slot(t) if t is not None else None)
              for k, t in dict(n2w=n2w, n2b=n2b, w1=w1, b1=b1, dww=dww, dwb=dwb, w2=w2, b2=b2).items()}
-        d_s, db2 = ops.scale_round_colsum(d, Cc, dp, L, cs_out=g["b2"])   # column sums = linear2 bias gradient
+        pre = _link_take(ctx.link_out, d)   # d_s / column sums (= linear2 bias gradient) from the producer of d
+        if pre is not None:
+            d_s, db2, direct = pre
+            if direct:
+                g["b2"] = db2
+        else:
+            d_s, db2 = ops.scale_round_colsum(d, Cc, dp, L, cs_out=g["b2"])
         # dv = (d_s W2) * gelu'(v): the second GELU's derivative (saved by the forward) rides in the
         # GEMM epilogue
         dv = ops.linear_dgrad(d_s, ops.rounded_weight(w2), mul_by=v, t5=True)
@@ -255,8 +309,8 @@ class LeFFBlockFn(torch.autograd.Function):
         dy2 = ops.linear_dgrad(du, ops.rounded_weight(w1), t5=True)
         dw1, _ = ops.linear_wgrad(du, y2, want_bias=False, t5=True, out=g["w1"])
         del du
-        dx, dg, db = ops.layernorm_bwd(dy2, x2, n2w, mean, rstd, dres=d, dgamma_out=g["n2w"], dbeta_out=g["n2b"])
+        dx, dg, db = _ln_bwd_linked(ctx.link_in, dy2, x2, n2w, mean, rstd, d, g["n2w"], g["n2b"])
         nz = lambda grad, k: None if g[k] is not None else grad
         dg, db, dw1, db1, ddww, ddwb, dw2, db2 = (nz(dg, "n2w"), nz(db, "n2b"), nz(dw1, "w1"), nz(db1, "b1"),
                                                   nz(ddww, "dww"), nz(ddwb, "dwb"), nz(dw2, "w2"), nz(db2, "b2"))
-        return dx.view(B, L, Cc), dg, db, dw1, db1, ddww, ddwb, dw2, db2, None, None, None
+        return dx.view(B, L, Cc), dg, db, dw1, db1, ddww, ddwb, dw2, db2, None, None, None, None, None

@@ -401,6 +401,25 @@ def layernorm_fwd(x2d, gamma, beta, eps=1e-5, save_stats=True):
     return y, mean, rstd
 
 
+def layernorm_bwd_ds(dy2d, x2d, gamma, mean, rstd, dres, rowscale, rows_per_group, dgamma_out=None, dbeta_out=None,
+                     cs_out=None):
+    """layernorm_bwd that also emits d_s = tf32(rowscale * dx) and its column sums for the next backward function
+    (saves the separate scale_round_colsum pass).  Returns None when the shape is not served."""
+    rows, Cc = x2d.shape
+    if not fn["uwr_layernorm_bwd_ds_supported"](rows, Cc):
+        return None
+    dx = torch.empty_like(x2d)
+    d_s = torch.empty_like(x2d)
+    dgamma = dgamma_out if dgamma_out is not None else torch.empty_like(gamma)
+    dbeta = dbeta_out if dbeta_out is not None else torch.empty_like(gamma)
+    cs = cs_out if cs_out is not None else _empty((Cc,), x2d)
+    ws = _ws(fn["uwr_layernorm_bwd_ds_workspace_bytes"](rows, Cc), x2d)
+    _run("uwr_layernorm_bwd_ds", f"rows{rows} C{Cc}", (16 + (4 if dres is not None else 0)) * rows * Cc, 16.0 * rows * Cc,
+         _ptr(dy2d), _ptr(x2d), _ptr(gamma), _ptr(mean), _ptr(rstd), _ptr(dres), _ptr(dx), _ptr(dgamma), _ptr(dbeta),
+         _ptr(rowscale), int(rows_per_group), _ptr(d_s), _ptr(cs), _ptr(ws), rows, Cc)
+    return dx, dgamma, dbeta, d_s, cs
+
+
 def layernorm_bwd(dy2d, x2d, gamma, mean, rstd, dres=None, dgamma_out=None, dbeta_out=None):
     rows, Cc = x2d.shape
     dx = torch.empty_like(x2d)
