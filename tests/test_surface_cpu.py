@@ -58,6 +58,19 @@ def test_error_paths_return_codes_not_crashes(build_lib):
     assert _lib.fn["uwr_gemm_tcgen05_supported"](ctypes.byref(d)) == 0
     with pytest.raises(_lib.UwrError):
         _lib.check(_lib.fn["uwr_pixel_loss"](None, None, None, None, None, 0, 1, 3, 8, 8, 1, None), "uwr_pixel_loss")
+    # entry points added later in the round: same contract (negative code + message, nothing launched)
+    f = _lib.fn
+    assert f["uwr_dft_hw_real"](None, None, None, 1, 16, 16, 32, 1.0, None) == -1
+    assert b"null pointer" in f["uwr_last_error"]()
+    assert f["uwr_dft_lc_real"](None, None, None, 1, 16, 16, 32, 1.0, None) == -1
+    assert f["uwr_fft2_hw"](None, None, None, 1, 16, 16, 32, 0, 0, 1.0, None) == -1
+    assert f["uwr_gelu_mul_fwd"](None, 8, None, 4, 4, None) == -1
+    assert f["uwr_gelu_mul_bwd"](None, None, 8, None, 4, 4, None) == -1
+    assert f["uwr_layernorm_bwd_ds_supported"](1024, 64) == 1 and f["uwr_layernorm_bwd_ds_supported"](1024, 48) == 0
+    assert f["uwr_layernorm_bwd_ds_workspace_bytes"](1 << 20, 64) > 0
+    assert f["uwr_layernorm_bwd_ds"](*([None] * 10), 1, None, None, None, 1024, 64, None) == -1
+    assert f["uwr_dft_workspace_bytes"](2, 16, 16, 32) == 2 * 2 * 16 * 16 * 32 * 8
+    assert f["uwr_set_attn_tcgen05"](0) == 0
 
 
 def test_registry_surface():
