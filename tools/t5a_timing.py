@@ -1,5 +1,11 @@
 """Phase timing of attn_fwd_t5_kernel (debug build with -DT5A_TIMING, see csrc/window_attn.cu):
-clock64 stamps of thread 0 / CTA 0 for its 4th item.  usage: UWR_B200_LIB=.../libuwr_dbg.so python tools/t5a_timing.py"""
+clock64 stamps of thread 0 / CTA 0 for its 4th item.
+
+    cd underwater-image-restoration_b200/csrc
+    nvcc -gencode arch=compute_100a,code=sm_100a -O3 -std=c++17 -Xcompiler -fPIC -DT5A_TIMING -c window_attn.cu -o /tmp/wa_dbg.o
+    nvcc -shared -o build/libuwr_dbg.so $(ls build/*.o | grep -v window_attn.o) /tmp/wa_dbg.o
+    UWR_B200_LIB=$PWD/build/libuwr_dbg.so python ../../tools/t5a_timing.py        # on the GPU box
+"""
 import ctypes, os, sys
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, os.path.join(ROOT, "underwater-image-restoration_b200"))
