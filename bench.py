@@ -48,11 +48,9 @@ def cpu_reference_step_rate(steps, warmup, size=256, batch=1, budget_s=40.0):
     """The reference's CPU path for this workload (oracle port: plain PyTorch-eager fp32, autograd,
     torch.optim.Adam, clip_grad_norm_) on all host cores.  Returns images/s and the thread count."""
     import torch
-    from oracle import ast_oracle, losses_oracle
-    from uwr.ast import AST
+    from oracle import ast_init, ast_oracle, losses_oracle
     torch.set_num_threads(os.cpu_count())
-    torch.manual_seed(1234)
-    sd = AST(img_size=size).state_dict()
+    sd = ast_init.ast_state_dict(seed=1234)   # plain torch init: the reference arm never loads the product library
     params = {k: v.clone().requires_grad_() for k, v in sd.items() if v.is_floating_point()}
     full = dict(sd)
     full.update(params)
@@ -73,6 +71,88 @@ def cpu_reference_step_rate(steps, warmup, size=256, batch=1, budget_s=40.0):
         if time.time() - t_begin > budget_s and len(times) >= 1:
             break
     return batch * len(times) / sum(times), torch.get_num_threads(), len(times)
+
+
+def gpu_eager_step_rate(dev, batch, size, steps, warmup, allow_tf32):
+    """The kernel bar: the reference modules' math in PyTorch-eager on the SAME B200
+    (cuBLAS / cuDNN / ATen), fp32 storage, train mode with per-sample DropPath scales, the reference loop
+    body ModelTrainer.py:78-88 without its per-step .item()/print.  Returns (images/s, ms/step)."""
+    import torch
+    from oracle import ast_init, ast_oracle, losses_oracle
+    old = (torch.backends.cuda.matmul.allow_tf32, torch.backends.cudnn.allow_tf32)
+    torch.backends.cuda.matmul.allow_tf32 = allow_tf32
+    torch.backends.cudnn.allow_tf32 = allow_tf32
+    try:
+        sd = {k: v.to(dev) for k, v in ast_init.ast_state_dict(seed=1234).items()}
+        params = {k: v.clone().requires_grad_() for k, v in sd.items() if v.is_floating_point()}
+        full = dict(sd)
+        full.update(params)
+        plist = list(params.values())
+        opt = torch.optim.Adam(plist, lr=1e-3)
+        raw, ref = _synthetic(batch, size)
+        raw, ref = raw.to(dev), ref.to(dev)
+        blocks = sorted({k[: k.index("norm2")] for k in sd if "norm2.weight" in k})
+        rates = torch.linspace(0, 0.1, 8).tolist()   # AST.py:703-705: enc 0..0.1, bottleneck 0.1, dec reversed
+        names = ["encoderlayer_0", "encoderlayer_1", "encoderlayer_2", "encoderlayer_3"]
+        prob = {}
+        for i, n in enumerate(names):
+            for b in range(2):
+                prob[f"{n}.blocks.{b}."] = rates[2 * i + b]
+        for b in range(2):
+            prob[f"conv.blocks.{b}."] = 0.1
+        for i, n in enumerate(["decoderlayer_0", "decoderlayer_1", "decoderlayer_2", "decoderlayer_3"]):
+            for b in range(2):
+                prob[f"{n}.blocks.{b}."] = rates[::-1][2 * i + b]
+
+        def one():
+            drop = {}
+            for pre in blocks:
+                p = prob[pre]
+                if p > 0:
+                    keep = 1.0 - p
+                    m = lambda: torch.empty(batch, device=dev).bernoulli_(keep).div_(keep)
+                    drop[pre] = (m() if (pre + "attn.w") in sd else None, m())
+            opt.zero_grad(set_to_none=True)
+            out = ast_oracle.ast_forward(full, raw, img_size=size, drop_scales=drop)
+            loss = losses_oracle.l1(out, ref)
+            loss.backward()
+            torch.nn.utils.clip_grad_norm_(plist, 1.0)
+            opt.step()
+
+        for _ in range(warmup):
+            one()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(steps):
+            one()
+        e1.record()
+        torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1) / steps
+        return batch / (ms / 1e3), ms
+    finally:
+        torch.backends.cuda.matmul.allow_tf32, torch.backends.cudnn.allow_tf32 = old
+
+
+def run_reference_gpu(args):
+    """`--impl reference-gpu`: the PyTorch-eager kernel bar alone (one GPU, rank 0)."""
+    if int(os.environ.get("RANK", "0")) != 0:
+        return
+    import torch
+    dev = torch.device("cuda", int(os.environ.get("LOCAL_RANK", "0")))
+    torch.cuda.set_device(dev)
+    res = {}
+    for name, tf32 in (("fp32", False), ("tf32", True)):
+        rate, ms = gpu_eager_step_rate(dev, args.batch, args.size, args.steps, max(args.warmup, 3), tf32)
+        res[name] = {"value": rate, "unit": UNIT, "ms_per_step": ms}
+    line = {"impl": "reference-gpu", "metric": METRIC, "value": res["fp32"]["value"], "unit": UNIT, "n_gpus": 1,
+            "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": res["fp32"]["ms_per_step"],
+            "higher_is_better": True, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": f"AST {args.size}x{args.size} train step, batch {args.batch}, PyTorch-eager "
+                                   "(cuBLAS/cuDNN/ATen) port of the reference modules on the same B200",
+                       "batch_per_gpu": args.batch},
+            "gpu_eager": res}
+    print(json.dumps(line))
 
 
 def run_reference(args):
@@ -298,6 +378,21 @@ def run_ours(args):
                         "sample": f"{done} AST 256x256 train steps at batch 1 on the host "
                                   f"({time.time() - t0:.0f} s wall, oracle port of the reference's CPU path)"}
 
+    gpu_eager = None
+    if rank == 0 and world == 1 and not args.no_gpu_eager:
+        # the kernel bar: same step, same batch, PyTorch-eager on this GPU (after our own timing, graph pools released)
+        graphed = None
+        torch.cuda.empty_cache()
+        try:
+            gpu_eager = {}
+            for name, tf32 in (("fp32", False), ("tf32", True)):
+                rate, ems = gpu_eager_step_rate(dev, B, S, min(args.steps, 10), 3, tf32)
+                gpu_eager[name] = {"value": rate, "unit": UNIT, "ms_per_step": ems, "speedup": value / rate}
+            gpu_eager["what"] = ("reference modules' math (oracle port) in PyTorch-eager on the same B200: cuBLAS / cuDNN / "
+                                 "ATen, fp32 storage; 'fp32' = allow_tf32 off, 'tf32' = allow_tf32 on")
+        except RuntimeError as e:   # e.g. out of memory next to our pools: report, do not hide
+            gpu_eager = {"error": str(e).splitlines()[0][:200]}
+
     if rank == 0:
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
@@ -315,6 +410,7 @@ def run_ours(args):
             "clocks": clocks,
             "roofline": roofline,
             "cpu_baseline": cpu_baseline,
+            "gpu_eager": gpu_eager,
         }
         print(json.dumps(line))
     if world > 1:
@@ -328,13 +424,16 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--batch", type=int, default=16, help="images per GPU per step")
     ap.add_argument("--size", type=int, default=256)
-    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference", "reference-gpu"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-gpu-eager", action="store_true", help="skip the PyTorch-eager-on-GPU comparison leg")
     ap.add_argument("--no-graph", action="store_true", help="launch the single-GPU step eagerly instead of replaying a CUDA graph")
     ap.add_argument("--profile-out", default="", help="write the per-kernel event table (JSON) here")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)
+    elif args.impl == "reference-gpu":
+        run_reference_gpu(args)
     else:
         run_ours(args)
 

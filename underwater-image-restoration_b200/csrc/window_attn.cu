@@ -33,6 +33,7 @@ struct AttnParams {
     float scale;
     int nWx, nW;  // windows per row / per image
     int rnd;      // round outputs to TF32 (they are GEMM operands)
+    int x3;       // error-compensated 3xTF32 on the cancelling products (default); 0 = single pass (experiment)
 };
 
 __device__ __forceinline__ long long token_row(const AttnParams& p, int b, int wy, int wx, int n) {
@@ -121,7 +122,7 @@ __device__ __forceinline__ void prep_tf32(float x, uint32_t& hi, uint32_t& lo) {
 // 3xTF32: a*b ~= a_lo*b_hi + a_hi*b_lo + a_hi*b_hi  (fp32-level accuracy on the tensor cores)
 template <int HD>
 __device__ __forceinline__ void mma_rows_x_rowsT(float (&acc)[8][4], const float* A, const float* Bm, int r0,
-                                                 int g, int t) {
+                                                 int g, int t, bool x3 = true) {
     constexpr int ST = HD + 4;
 #pragma unroll
     for (int nt = 0; nt < 8; ++nt)
@@ -143,10 +144,21 @@ __device__ __forceinline__ void mma_rows_x_rowsT(float (&acc)[8][4], const float
             split_tf32(Bm[(nt * 8 + g) * ST + ks * 8 + t], bh[nt][0], bl[nt][0]);
             split_tf32(Bm[(nt * 8 + g) * ST + ks * 8 + t + 4], bh[nt][1], bl[nt][1]);
         }
+        if (!x3) {  // single pass: operands rounded to nearest (a raw value would be truncated)
 #pragma unroll
-        for (int nt = 0; nt < 8; ++nt) mma_tf32_16x8x8(acc[nt], al, bh[nt]);
+            for (int c = 0; c < 4; ++c) ah[c] = (ah[c] + 0x1000u) & 0xFFFFE000u;
 #pragma unroll
-        for (int nt = 0; nt < 8; ++nt) mma_tf32_16x8x8(acc[nt], ah, bl[nt]);
+            for (int nt = 0; nt < 8; ++nt) {
+                bh[nt][0] = (bh[nt][0] + 0x1000u) & 0xFFFFE000u;
+                bh[nt][1] = (bh[nt][1] + 0x1000u) & 0xFFFFE000u;
+            }
+        }
+        if (x3) {
+#pragma unroll
+            for (int nt = 0; nt < 8; ++nt) mma_tf32_16x8x8(acc[nt], al, bh[nt]);
+#pragma unroll
+            for (int nt = 0; nt < 8; ++nt) mma_tf32_16x8x8(acc[nt], ah, bl[nt]);
+        }
 #pragma unroll
         for (int nt = 0; nt < 8; ++nt) mma_tf32_16x8x8(acc[nt], ah, bh[nt]);
     }
@@ -156,7 +168,7 @@ __device__ __forceinline__ void mma_rows_x_rowsT(float (&acc)[8][4], const float
 // key permutation inside each k8 block: slot t <-> key 2t, slot t+4 <-> key 2t+1.
 template <int HD, bool X3>
 __device__ __forceinline__ void mma_regs_x_rows(float (&out)[HD / 8][4], const float (&P)[8][4], const float* Bm,
-                                                int g, int t) {
+                                                int g, int t, bool x3 = true) {
     constexpr int ST = HD + 4;
 #pragma unroll
     for (int n = 0; n < HD / 8; ++n)
@@ -175,7 +187,16 @@ __device__ __forceinline__ void mma_regs_x_rows(float (&out)[HD / 8][4], const f
             prep_tf32<X3>(Bm[(kb * 8 + 2 * t) * ST + n * 8 + g], b[n][0], bl[n][0]);
             prep_tf32<X3>(Bm[(kb * 8 + 2 * t + 1) * ST + n * 8 + g], b[n][1], bl[n][1]);
         }
-        if (X3) {
+        if (X3 && !x3) {
+#pragma unroll
+            for (int c = 0; c < 4; ++c) a[c] = (a[c] + 0x1000u) & 0xFFFFE000u;
+#pragma unroll
+            for (int n = 0; n < HD / 8; ++n) {
+                b[n][0] = (b[n][0] + 0x1000u) & 0xFFFFE000u;
+                b[n][1] = (b[n][1] + 0x1000u) & 0xFFFFE000u;
+            }
+        }
+        if (X3 && x3) {
 #pragma unroll
             for (int n = 0; n < HD / 8; ++n) mma_tf32_16x8x8(out[n], al, b[n]);
 #pragma unroll
@@ -279,7 +300,7 @@ __global__ void __launch_bounds__(ATT_THREADS) attn_fwd_kernel(const AttnParams 
     const int r0 = warp * 16;
 
     float s[8][4], p0[8][4];
-    mma_rows_x_rowsT<HD>(s, Qs, Ks, r0, g, t);
+    mma_rows_x_rowsT<HD>(s, Qs, Ks, r0, g, t, p.x3);
     add_bias_mask(s, tab, reg, r0, g, t, p.shift > 0);
     row_softmax(s, p0);
     float w0, w1;
@@ -369,10 +390,10 @@ __global__ void __launch_bounds__(ATT_THREADS, HD <= 32 ? 3 : 1) attn_bwd_kernel
         float pm[8][4], dp[8][4];  // final mixture P and dP -> dS
         {
             float s[8][4], p0[8][4];
-            mma_rows_x_rowsT<HD>(s, Qs, Ks, r0, g, t);
+            mma_rows_x_rowsT<HD>(s, Qs, Ks, r0, g, t, p.x3);
             add_bias_mask(s, tab, reg, r0, g, t, p.shift > 0);
             row_softmax(s, p0);
-            mma_rows_x_rowsT<HD>(dp, dOs, Vs, r0, g, t);  // dP = dO V^T
+            mma_rows_x_rowsT<HD>(dp, dOs, Vs, r0, g, t, p.x3);  // dP = dO V^T
 #pragma unroll
             for (int half = 0; half < 2; ++half) {
                 float rowdot = 0.f;
@@ -407,7 +428,7 @@ __global__ void __launch_bounds__(ATT_THREADS, HD <= 32 ? 3 : 1) attn_bwd_kernel
         // dQ = scale * dS K  (Qs holds scale*q, so the chain rule adds one more factor scale)
         {
             float dq[HD / 8][4];
-            mma_regs_x_rows<HD, true>(dq, dp, Ks, g, t);  // dS rows sum to ~0: needs 3xTF32
+            mma_regs_x_rows<HD, true>(dq, dp, Ks, g, t, p.x3);  // dS rows sum to ~0: needs 3xTF32
 #pragma unroll
             for (int half = 0; half < 2; ++half) {
                 float* drow = dq_buf + rows[r0 + g + half * 8] * p.ld_q + p.q_off + h * HD;
@@ -466,7 +487,16 @@ __global__ void __launch_bounds__(ATT_THREADS, HD <= 32 ? 3 : 1) attn_bwd_kernel
                         bb[n][1] = f2tf32(Bm[(kb * 8 + t + 4) * ST + n * 8 + g]);
                     }
                 }
-                if (which == 1) {  // dK: error-compensated
+                if (which == 1 && !p.x3) {
+#pragma unroll
+                    for (int c = 0; c < 4; ++c) a[c] = (a[c] + 0x1000u) & 0xFFFFE000u;
+#pragma unroll
+                    for (int n = 0; n < HD / 8; ++n) {
+                        bb[n][0] = (bb[n][0] + 0x1000u) & 0xFFFFE000u;
+                        bb[n][1] = (bb[n][1] + 0x1000u) & 0xFFFFE000u;
+                    }
+                }
+                if (which == 1 && p.x3) {  // dK: error-compensated
 #pragma unroll
                     for (int n = 0; n < HD / 8; ++n) mma_tf32_16x8x8(acc[n], al, bb[n]);
 #pragma unroll
@@ -890,6 +920,8 @@ int fill_params(const uwr_attn_desc* d, AttnParams& p, const char* who) {
     p.B = d->B; p.H = d->H; p.W = d->W; p.heads = d->heads; p.shift = d->shift; p.scale = d->scale;
     p.nWx = d->W / WIN; p.nW = (d->H / WIN) * (d->W / WIN);
     p.rnd = uwr_round_outputs();
+    static const int x3_env = [] { const char* e = getenv("UWR_ATTN_X3"); return e ? atoi(e) : 1; }();
+    p.x3 = x3_env;
     return 0;
 }
 
