@@ -267,6 +267,22 @@ int uwr_dft_lc_real(const float* x, float* y, float* workspace, int B, int H, in
 int uwr_fft2_hw(const float* in, float* out, float* workspace, int B, int H, int W, int C,
                 int in_complex, int inverse, float scale, uwr_stream_t stream);
 
+/* ---- MDTA channel attention (src/Models/SpectralTransformer.py:92-113) -----------------------
+ * Token matrices are (B*L, ld) fp32, the c = C/heads channels of a head contiguous; c in {8,16,32,64},
+ * heads*c <= 256, L a multiple of 64.  Pass pointers already offset to the first channel.
+ * uwr_mdta_gram:  G[b,h,i,j] = sum_l X[b,l,h*c+i] Y[b,l,h*c+j]   (q^T k, line 100; also dA = dout^T v),
+ *                 sqx[b,ch] = sum_l X[b,l,ch]^2, sqy likewise (the L2 norms of line 99; NULL to skip).
+ *                 heads*c*c <= 4096.  Deterministic (per-CTA partials in `workspace`, then one reduce).
+ * uwr_mdta_apply: out[b,l,h*c+i] = sum_j M[b,h,i,j] X[b,l,h*c+j]  (attn @ v, lines 101/109/113;
+ *                 transpose = 1 uses M[b,h,j,i]: dv = A^T dout), optionally + diag[b,h*c+i] * Yd[b,l,h*c+i]
+ *                 (the derivative of the squared norms in the backward: dq = dG k + 2 dsq_q q). */
+size_t uwr_mdta_gram_workspace_bytes(int B, int L, int heads, int c);
+int uwr_mdta_gram(const float* X, long long ldx, const float* Y, long long ldy, int B, int L, int heads,
+                  int c, float* G, float* sqx, float* sqy, float* workspace, uwr_stream_t stream);
+int uwr_mdta_apply(const float* X, long long ldx, const float* M, int transpose, const float* Yd,
+                   long long ldy, const float* diag, float* out, long long ldo, int B, int L, int heads,
+                   int c, uwr_stream_t stream);
+
 /* ---- optimizer step (ModelTrainer.py:87-88,197-204): clip_grad_norm_(1.0) + Adam/AdamW -----
  * tensor tables are device arrays of pointers; `offsets` (n_tensors+1 entries, offsets[0]=0) is
  * the running element count of the virtual concatenation.

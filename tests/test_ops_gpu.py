@@ -550,3 +550,63 @@ def test_window_attention_fwd_tcgen05_vs_mma_sync(ops, B, H, heads, shift, spars
     assert rel_l2(o_t5, ref) < TOL_TF32
     assert rel_l2(o_t5, o_ref) < 3e-4
     assert not torch.equal(o_t5, o_ref)   # two different kernels did run
+
+
+# ------------------------------------------------------------------------------------------ MDTA
+@pytest.mark.parametrize("B,L,heads,c", [(2, 1024, 1, 16), (3, 4096, 2, 16), (2, 1024, 8, 16), (2, 4096, 1, 32),
+                                         (1, 256, 4, 8), (1, 128, 2, 64)])
+def test_mdta_gram_apply(ops, B, L, heads, c):
+    """uwr_mdta_gram / uwr_mdta_apply (SpectralTransformer.py:99-101,109,113) vs fp64 einsum, on column slices of a
+    wider token matrix (the q | k | v layout of the qkv projection)."""
+    C = heads * c
+    qkv = _r(B * L, 3 * C, seed=31)
+    G, sq, sk = ops.mdta_gram(qkv, 0, qkv, C, B, L, heads, c, want_sq=True)
+    q = qkv[:, :C].double().view(B, L, heads, c)
+    k = qkv[:, C:2 * C].double().view(B, L, heads, c)
+    v = qkv[:, 2 * C:].double().view(B, L, heads, c)
+    refG = torch.einsum("blhi,blhj->bhij", q, k)
+    # Gram entries of uncorrelated data cancel to ~sqrt(L): judge against the un-cancelled scale
+    scale = torch.einsum("blhi,blhj->bhij", q.abs(), k.abs()).norm()
+    assert ((G.double() - refG).norm() / scale).item() < TOL_TF32
+    assert rel_l2(sq, (q * q).sum(1).reshape(B, C)) < TOL_FP32
+    assert rel_l2(sk, (k * k).sum(1).reshape(B, C)) < TOL_FP32
+    A = torch.softmax(_r(B, heads, c, c, seed=32), dim=-1)
+    out = ops.mdta_apply(qkv, 2 * C, A, B, L, heads, c)
+    ref = torch.einsum("bhij,blhj->blhi", A.double(), v).reshape(B * L, C)
+    assert rel_l2(out, ref) < TOL_TF32
+    # transposed apply with the diagonal term, written into a column slice of a wider output
+    d = _r(B, C, seed=33)
+    dst = torch.zeros(B * L, 3 * C, device="cuda")
+    ops.mdta_apply(qkv, C, A, B, L, heads, c, transpose=True, yd=qkv, ycol=0, diag=d, out=dst, ocol=C)
+    ref2 = torch.einsum("bhji,blhj->blhi", A.double(), k).reshape(B, L, C) + d.double()[:, None, :] * q.reshape(B, L, C)
+    assert rel_l2(dst[:, C:2 * C], ref2.reshape(B * L, C)) < TOL_TF32
+    assert dst[:, :C].abs().max().item() == 0 and dst[:, 2 * C:].abs().max().item() == 0
+
+
+def test_mdta_attention_fn_vs_autograd(ops):
+    """MDTAAttnFn + ChannelApplyFn (forward and hand-written backward) vs plain autograd on the reference formula."""
+    from uwr import fn
+    B, L, heads, c = 2, 1024, 2, 16
+    C = heads * c
+    qkv = _r(B * L, 3 * C, seed=41).requires_grad_()
+    vf = _r(B * L, 2 * C, seed=42).requires_grad_()
+    temp = (torch.ones(1, heads, 1, 1, device="cuda") * 1.7).requires_grad_()
+    out, A = fn.MDTAAttnFn.apply(qkv, temp, B, L, C, heads)
+    outf = fn.ChannelApplyFn.apply(vf, A, C, B, L)
+    g1, g2 = _r(B * L, C, seed=43), _r(B * L, C, seed=44)
+    (out * g1).sum().add((outf * g2).sum()).backward()
+
+    q64 = qkv.detach().double().requires_grad_()
+    vf64 = vf.detach().double().requires_grad_()
+    t64 = temp.detach().double().requires_grad_()
+    x = q64.view(B, L, 3, heads, c).permute(2, 0, 3, 4, 1)          # (3, B, h, c, L)
+    qn, kn = F.normalize(x[0], dim=-1), F.normalize(x[1], dim=-1)
+    A64 = torch.softmax(qn @ kn.transpose(-2, -1) * t64, dim=-1)
+    o64 = (A64 @ x[2]).permute(0, 3, 1, 2).reshape(B * L, C)
+    vfh = vf64[:, C:].view(B, L, heads, c).permute(0, 2, 3, 1)
+    of64 = (A64 @ vfh).permute(0, 3, 1, 2).reshape(B * L, C)
+    (o64 * g1.double()).sum().add((of64 * g2.double()).sum()).backward()
+    assert rel_l2(out, o64) < TOL_TF32 and rel_l2(outf, of64) < TOL_TF32
+    assert rel_l2(qkv.grad, q64.grad) < 2 * TOL_TF32
+    assert rel_l2(vf.grad, vf64.grad) < TOL_TF32
+    assert rel_l2(temp.grad, t64.grad) < 2 * TOL_TF32

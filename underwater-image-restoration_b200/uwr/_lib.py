@@ -115,6 +115,10 @@ SIGNATURES = {
     "uwr_dft_hw_real": (c_int, [c_fp, c_fp, c_fp, c_int, c_int, c_int, c_int, c_f, c_stream]),
     "uwr_dft_lc_real": (c_int, [c_fp, c_fp, c_fp, c_int, c_int, c_int, c_int, c_f, c_stream]),
     "uwr_fft2_hw": (c_int, [c_fp, c_fp, c_fp, c_int, c_int, c_int, c_int, c_int, c_int, c_f, c_stream]),
+    "uwr_mdta_gram_workspace_bytes": (c_sz, [c_int, c_int, c_int, c_int]),
+    "uwr_mdta_gram": (c_int, [c_fp, c_ll, c_fp, c_ll, c_int, c_int, c_int, c_int, c_fp, c_fp, c_fp, c_fp, c_stream]),
+    "uwr_mdta_apply": (c_int, [c_fp, c_ll, c_fp, c_int, c_fp, c_ll, c_fp, c_fp, c_ll, c_int, c_int, c_int, c_int,
+                               c_stream]),
     "uwr_grad_norm": (c_int, [c_fp, c_fp, c_int, c_ll, c_f, c_f, c_fp, c_fp, c_stream]),
     "uwr_adam_step": (c_int, [c_fp, c_fp, c_fp, c_fp, c_fp, c_int, c_ll, c_fp, c_f, c_f, c_f, c_f, c_f, c_f,
                               c_int, c_int, c_fp, c_stream]),

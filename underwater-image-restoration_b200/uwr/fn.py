@@ -233,29 +233,6 @@ class PlainDWConvFn(torch.autograd.Function):
         return du, dw, None, None, None
 
 
-class GramFn(torch.autograd.Function):
-    """G = X^T X for a token slab X (L, n) (row stride may be larger): one TN GEMM over the tokens.
-    Used for MDTA's channel attention, where q^T k and the L2 norms of q, k are blocks of G."""
-
-    @staticmethod
-    def forward(ctx, x):
-        L, n = x.shape
-        G = ops._empty((n, n), x)
-        ops.gemm(x, x, G, n, n, L, lda=x.stride(0), ldb=x.stride(0), ldc=n, a_km=True, b_nk=False)
-        ctx.save_for_backward(x)
-        return G
-
-    @staticmethod
-    @once_differentiable
-    def backward(ctx, dG):
-        (x,) = ctx.saved_tensors
-        L, n = x.shape
-        S = _c(dG + dG.t())
-        dx = ops._empty((L, n), x)
-        ops.gemm(x, S, dx, L, n, n, lda=x.stride(0), ldb=n, ldc=n, b_nk=False)
-        return dx
-
-
 class DftRealFn(torch.autograd.Function):
     """y = scale * Re(FFT2(x)) over the spatial axes ('hw', FDFP block.py:532-556) or over
     (tokens, channels) ('lc', EncoderBlock model.py:72-88).  x -> Re(F x) is symmetric, so the
@@ -296,103 +273,83 @@ class Fft2Fn(torch.autograd.Function):
         return dx, None, None, None, None, None, None, None
 
 
-def _mdta_matrices(G, temperature, C, heads):
-    """(B, 2C, 2C) Gram matrices of [q|k] -> (B, C, C) block-diagonal channel-attention matrices
-    softmax(normalize(q) normalize(k)^T * temperature) (SpectralTransformer.py:97-101); tiny batched
+def _mdta_matrices(G, sq_q, sq_k, temperature, heads):
+    """per-head Gram blocks G (B, h, c, c) of q^T k and squared norms (B, C) of q, k -> channel-attention
+    matrices softmax(normalize(q) normalize(k)^T * temperature) (SpectralTransformer.py:97-101); tiny batched
     ATen ops, differentiated by autograd inside MDTAAttnFn."""
-    B = G.shape[0]
-    c = C // heads
-    d = torch.diagonal(G, dim1=-2, dim2=-1)
-    nq = d[:, :C].clamp_min(0).sqrt().clamp_min(1e-12)              # F.normalize eps (line 99)
-    nk = d[:, C:].clamp_min(0).sqrt().clamp_min(1e-12)
-    S = G[:, :C, C:] / (nq[:, :, None] * nk[:, None, :])
-    blocks = S.view(B, heads, c, heads, c).diagonal(dim1=1, dim2=3).permute(0, 3, 1, 2)     # (B, h, c, c)
-    A = torch.softmax(blocks * temperature.view(1, heads, 1, 1), dim=-1)
-    return torch.diag_embed(A.permute(0, 2, 3, 1), dim1=1, dim2=3).reshape(B, C, C)          # batched block_diag
+    B, h, c, _ = G.shape
+    nq = sq_q.clamp_min(0).sqrt().clamp_min(1e-12).view(B, h, c, 1)      # F.normalize eps (line 99)
+    nk = sq_k.clamp_min(0).sqrt().clamp_min(1e-12).view(B, h, 1, c)
+    return torch.softmax(G / (nq * nk) * temperature.view(1, heads, 1, 1), dim=-1)
 
 
 class MDTAAttnFn(torch.autograd.Function):
-    """MDTA channel attention (SpectralTransformer.py:92-109) for a whole batch without per-image
-    autograd slicing: qkv (B*L, 3C) tokens -> out = attn @ v (B*L, C) and the attention matrices
-    A (B, C, C) (re-used for the frequency branch's `attn @ vf`).  Per image two GEMMs on strided
-    views (Gram matrix of [q|k] over the tokens, apply); the (2C)^2-sized normalise / softmax algebra
-    runs batched and is differentiated by autograd on those tiny tensors only."""
+    """MDTA channel attention (SpectralTransformer.py:92-109) for a whole batch: qkv (B*L, 3C) tokens ->
+    out = attn @ v (B*L, C) and the attention matrices A (B, heads, c, c) (re-used for the frequency
+    branch's `attn @ vf`).  Two batched per-head kernels (csrc/mdta.cu): uwr_mdta_gram (q^T k and the L2 norms
+    in one pass over the tokens) and uwr_mdta_apply; the (heads, c, c)-sized normalise / softmax algebra runs
+    batched and is differentiated by autograd on those tiny tensors only.  The backward is the same two
+    kernels: dA = gram(dout, v), dv = apply(dout, A^T), dq = apply(k, dG) + 2 dsq_q q, dk = apply(q, dG^T) + 2 dsq_k k."""
 
     @staticmethod
     def forward(ctx, qkv, temperature, B, L, C, heads):
         qkv = _c(qkv)
-        G = ops._empty((B, 2 * C, 2 * C), qkv)
-        for b in range(B):
-            x = qkv[b * L:(b + 1) * L, :2 * C]
-            ops.gemm(x, x, G[b], 2 * C, 2 * C, L, lda=3 * C, ldb=3 * C, ldc=2 * C, a_km=True, b_nk=False)
+        c = C // heads
+        G, sq_q, sq_k = ops.mdta_gram(qkv, 0, qkv, C, B, L, heads, c, want_sq=True)
         with torch.enable_grad():
-            Gd = G.detach().requires_grad_()
-            td = temperature.detach().requires_grad_()
-            A = _mdta_matrices(Gd, td, C, heads)
+            leaves = tuple(t.detach().requires_grad_() for t in (G, sq_q, sq_k, temperature))
+            A = _mdta_matrices(*leaves, heads)
         Ad = A.detach().contiguous()
-        out = ops._empty((B * L, C), qkv)
-        for b in range(B):
-            ops.linear(qkv[b * L:(b + 1) * L, 2 * C:], Ad[b], None, out=out[b * L:(b + 1) * L])
+        out = ops.mdta_apply(qkv, 2 * C, Ad, B, L, heads, c)
         ctx.save_for_backward(qkv, Ad)
-        ctx.graph = (Gd, td, A)
-        ctx.meta = (B, L, C)
+        ctx.graph = (leaves, A)
+        ctx.meta = (B, L, C, heads, c)
         return out, Ad
 
     @staticmethod
     @once_differentiable
     def backward(ctx, dout, dA_ext):
         qkv, Ad = ctx.saved_tensors
-        Gd, td, A = ctx.graph
-        B, L, C = ctx.meta
+        leaves, A = ctx.graph
+        B, L, C, heads, c = ctx.meta
         dout = _c(dout)
         dqkv = torch.empty_like(qkv)
-        dA = ops._empty((B, C, C), qkv)
-        for b in range(B):
-            rows = slice(b * L, (b + 1) * L)
-            v = qkv[rows, 2 * C:]
-            ops.gemm(dout[rows], v, dA[b], C, C, L, lda=C, ldb=3 * C, ldc=C, a_km=True, b_nk=False)   # dout^T v
-            ops.linear_dgrad(dout[rows], Ad[b], out=dqkv[rows, 2 * C:])                               # dv = dout A
+        dA, _, _ = ops.mdta_gram(dout, 0, qkv, 2 * C, B, L, heads, c)                        # dout^T v
+        ops.mdta_apply(dout, 0, Ad, B, L, heads, c, transpose=True, out=dqkv, ocol=2 * C)    # dv = A^T dout
         if dA_ext is not None:
             dA = dA + dA_ext
         with torch.enable_grad():
-            dG, dt = torch.autograd.grad(A, (Gd, td), dA)
-        S = _c(dG + dG.transpose(1, 2))
-        for b in range(B):
-            rows = slice(b * L, (b + 1) * L)
-            ops.gemm(qkv[rows, :2 * C], S[b], dqkv[rows, :2 * C], L, 2 * C, 2 * C, lda=3 * C, ldb=2 * C, ldc=3 * C,
-                     b_nk=False)
+            dG, dsq_q, dsq_k, dt = torch.autograd.grad(A, leaves, dA)
+        dG = _c(dG)
+        ops.mdta_apply(qkv, C, dG, B, L, heads, c, yd=qkv, ycol=0, diag=_c(2 * dsq_q), out=dqkv, ocol=0)
+        ops.mdta_apply(qkv, 0, dG, B, L, heads, c, transpose=True, yd=qkv, ycol=C, diag=_c(2 * dsq_k), out=dqkv,
+                       ocol=C)
         ctx.graph = None
-        return dqkv, dt.view_as(td), None, None, None, None
+        return dqkv, dt.view_as(leaves[3]), None, None, None, None
 
 
 class ChannelApplyFn(torch.autograd.Function):
-    """out[b] = x[b][:, col:col+C] @ A[b]^T for token slabs x (B*L, ld) and per-image matrices A (B, C, C)."""
+    """out[b] = A[b] applied per head to the channels x[b][:, col:col+C] of token slabs x (B*L, ld); A (B, heads, c, c)."""
 
     @staticmethod
     def forward(ctx, x, A, col, B, L):
         x = _c(x)
         A = _c(A)
-        C = A.shape[1]
-        out = ops._empty((B * L, C), x)
-        for b in range(B):
-            ops.linear(x[b * L:(b + 1) * L, col:col + C], A[b], None, out=out[b * L:(b + 1) * L])
+        heads, c = A.shape[1], A.shape[2]
+        out = ops.mdta_apply(x, col, A, B, L, heads, c)
         ctx.save_for_backward(x, A)
-        ctx.meta = (col, B, L, C)
+        ctx.meta = (col, B, L, heads, c)
         return out
 
     @staticmethod
     @once_differentiable
     def backward(ctx, dout):
         x, A = ctx.saved_tensors
-        col, B, L, C = ctx.meta
+        col, B, L, heads, c = ctx.meta
         dout = _c(dout)
         dx = torch.zeros_like(x)
-        dA = ops._empty((B, C, C), x)
-        ld = x.shape[1]
-        for b in range(B):
-            rows = slice(b * L, (b + 1) * L)
-            ops.gemm(dout[rows], x[rows, col:col + C], dA[b], C, C, L, lda=C, ldb=ld, ldc=C, a_km=True, b_nk=False)
-            ops.linear_dgrad(dout[rows], A[b], out=dx[rows, col:col + C])
+        dA, _, _ = ops.mdta_gram(dout, 0, x, col, B, L, heads, c)
+        ops.mdta_apply(dout, 0, A, B, L, heads, c, transpose=True, out=dx, ocol=col)
         return dx, dA, None, None, None
 
 

@@ -602,6 +602,38 @@ def colsum(x2d, cols, out=None):
 
 
 # --------------------------------------------------------------------------------------------
+def _colptr(t, col):
+    """device pointer of column `col` of a 2-D fp32 token matrix"""
+    _ptr(t)
+    return t.data_ptr() + 4 * col
+
+
+def mdta_gram(x, xcol, y, ycol, B, L, heads, c, want_sq=False):
+    """G (B, heads, c, c) = per-head X^T Y over the L tokens of each image (+ squared column norms (B, heads*c))."""
+    C = heads * c
+    G = _empty((B, heads, c, c), x)
+    sqx = _empty((B, C), x) if want_sq else None
+    sqy = _empty((B, C), x) if want_sq else None
+    ws = _ws(fn["uwr_mdta_gram_workspace_bytes"](B, L, heads, c), x)
+    _run("uwr_mdta_gram", f"B{B} L{L} h{heads} c{c}", 8 * B * L * C, 2.0 * B * L * C * c,
+         _colptr(x, xcol), x.stride(0), _colptr(y, ycol), y.stride(0), B, L, heads, c, _ptr(G), _ptr(sqx), _ptr(sqy),
+         _ptr(ws))
+    return G, sqx, sqy
+
+
+def mdta_apply(x, xcol, Mx, B, L, heads, c, transpose=False, yd=None, ycol=0, diag=None, out=None, ocol=0):
+    """out[:, ocol:ocol+C] = per-head M (or M^T) applied to the channels of x[:, xcol:xcol+C] (+ diag * yd)."""
+    C = heads * c
+    if out is None:
+        out = _empty((B * L, C), x)
+    _run("uwr_mdta_apply", f"B{B} L{L} h{heads} c{c}", (8 + (4 if yd is not None else 0)) * B * L * C,
+         2.0 * B * L * C * c, _colptr(x, xcol), x.stride(0), _ptr(Mx), int(transpose),
+         _colptr(yd, ycol) if yd is not None else None, yd.stride(0) if yd is not None else 0, _ptr(diag),
+         _colptr(out, ocol), out.stride(0), B, L, heads, c)
+    return out
+
+
+# --------------------------------------------------------------------------------------------
 LOSS_KINDS = {"L1": 0, "L1withColor": 1, "charbonnier": 2, "L2": 3, "mse01": 4}
 
 
