@@ -267,6 +267,65 @@ int uwr_dft_lc_real(const float* x, float* y, float* workspace, int B, int H, in
 int uwr_fft2_hw(const float* in, float* out, float* workspace, int B, int H, int W, int C,
                 int in_complex, int inverse, float scale, uwr_stream_t stream);
 
+/* PixelShuffle(2) / PixelUnshuffle(2) on NHWC tokens (src/Models/SpectralTransformer.py:151-158,191-198;
+ * src/model/block.py:107-153): in (B*H*W, 4*Cout) -> out (B*2H*2W, ld_out >= Cout) and back; H, W = the COARSE grid. */
+int uwr_pixel_shuffle2(const float* in, float* out, long long ld_out, int B, int H, int W, int Cout,
+                       uwr_stream_t stream);
+int uwr_pixel_unshuffle2(const float* in, long long ld_in, float* out, int B, int H, int W, int Cout,
+                         uwr_stream_t stream);
+
+/* ---- thin 3x3 convolutions (stride 1, pad 1) at the 3- / 8-channel ends -----------------------
+ * SpectralTransformer.embed_conv_rgb 3->16 and .output 8->3 (src/Models/SpectralTransformer.py:217,250,255,269);
+ * InputProjection.proj[0] 3->8 and OutputProjection.proj[2] 8->3 (src/model/block.py:42-88).
+ * A side is an NCHW image (tokens = 0) or a token matrix (B*H*W, ld) (tokens = 1).  Served: image 3 -> tokens 8|16,
+ * tokens 8 -> image 3 (optionally + residual image, the `+ x` of model.py:640).  weight (Cout, Cin, 3, 3), bias may be
+ * NULL.  The data gradient of tokens 8 -> image 3 is the image 3 -> tokens 8 call with flipped, transposed weights. */
+typedef struct {
+    const float* in;
+    int in_tokens;
+    long long ld_in;
+    const float* weight;
+    const float* bias;
+    const float* residual_img;
+    float* out;
+    int out_tokens;
+    long long ld_out;
+    int B, H, W, Cin, Cout;
+    int round_out; /* token output feeds a GEMM: round to TF32 in single-pass mode */
+} uwr_conv_small_desc;
+int uwr_conv3x3_small_fwd(const uwr_conv_small_desc* d, uwr_stream_t stream);
+size_t uwr_conv3x3_small_wgrad_workspace_bytes(int B, int H, int W, int Cin, int Cout);
+int uwr_conv3x3_small_wgrad(const uwr_conv_small_desc* d, const float* dout, long long ld_dout, float* dweight,
+                            float* dbias, float* workspace, uwr_stream_t stream);
+
+/* ---- elementwise passes of the FFT amplitude / phase up-sampler ---------------------------------
+ * SpectralTransformer.UpSample.forward, src/Models/SpectralTransformer.py:174-188.  Complex tensors are interleaved
+ * (re, im) fp32 pairs; n = number of complex (split/join/cabs) or real (leaky) elements, 16-byte aligned.
+ *   polar_split: mag = abs(f), pha = angle(f) (176-177); bwd: df from dmag, dpha (0 at f = 0, as torch)
+ *   polar_join : z = mag*cos(pha) + i*mag*sin(pha) (181-183)
+ *   cabs       : a = |z| (186)
+ *   leaky_relu : LeakyReLU(slope) of amp_fuse / pha_fuse (166-169); bwd takes the saved OUTPUT
+ *   even_scatter: out (B,2H,2W,C) = y (B,H,W,C) on the even pixels, bias elsewhere (post(0) = bias: the inverse
+ *                 transform of the (2,2)-tiled spectrum is zero off the even pixels); even_gather is its adjoint. */
+int uwr_polar_split_fwd(const float* f, float* mag, float* pha, long long n, uwr_stream_t stream);
+int uwr_polar_split_bwd(const float* f, const float* dmag, const float* dpha, float* df, long long n,
+                        uwr_stream_t stream);
+int uwr_polar_join_fwd(const float* mag, const float* pha, float* z, long long n, uwr_stream_t stream);
+int uwr_polar_join_bwd(const float* mag, const float* pha, const float* dz, float* dmag, float* dpha,
+                       long long n, uwr_stream_t stream);
+int uwr_cabs_fwd(const float* z, float* a, long long n, uwr_stream_t stream);
+int uwr_cabs_bwd(const float* z, const float* da, float* dz, long long n, uwr_stream_t stream);
+int uwr_leaky_relu_fwd(const float* x, float* y, long long n, float slope, int round_out,
+                       uwr_stream_t stream); /* round_out: the result feeds a GEMM (TF32 in single-pass mode) */
+int uwr_leaky_relu_bwd(const float* y, const float* dy, float* dx, long long n, float slope,
+                       uwr_stream_t stream);
+/* exact (erf) GELU, nn.GELU(): FDFP (src/model/block.py:541-546), Mlp.act (src/Models/AST.py:285-291) */
+int uwr_gelu_fwd(const float* x, float* y, long long n, int round_out, uwr_stream_t stream);
+int uwr_gelu_bwd(const float* x, const float* dy, float* dx, long long n, uwr_stream_t stream);
+int uwr_even_scatter(const float* y, const float* bias, float* out, int B, int H, int W, int C,
+                     uwr_stream_t stream);
+int uwr_even_gather(const float* dout, float* dy, int B, int H, int W, int C, uwr_stream_t stream);
+
 /* ---- MDTA channel attention (src/Models/SpectralTransformer.py:92-113) -----------------------
  * Token matrices are (B*L, ld) fp32, the c = C/heads channels of a head contiguous; c in {8,16,32,64},
  * heads*c <= 256, L a multiple of 64.  Pass pointers already offset to the first channel.

@@ -35,18 +35,18 @@ def test_tiled_spectrum_inverse_is_scatter_of_small_inverse():
 
 
 def test_batched_mdta_matrices_match_reference_formulation():
-    """uwr.fn._mdta_matrices (batched Gram -> normalise -> per-head softmax -> block diagonal) vs
+    """uwr.fn._mdta_matrices (per-head Gram blocks + squared norms -> normalise -> softmax) vs
     SpectralTransformer.py:97-101 written out with F.normalize / softmax on (b, heads, c, L) tensors."""
     from uwr.fn import _mdta_matrices
     B, L, C, heads = 3, 40, 8, 2
     g = torch.Generator().manual_seed(0)
     qk = torch.randn(B, L, 2 * C, generator=g, dtype=torch.float64)
     temp = torch.tensor([0.7, 1.9], dtype=torch.float64).view(1, heads, 1, 1)
-    G = qk.transpose(1, 2) @ qk                                      # (B, 2C, 2C) Gram of [q|k] over the tokens
-    A = _mdta_matrices(G, temp, C, heads)
     c = C // heads
     q = qk[:, :, :C].transpose(1, 2).reshape(B, heads, c, L)
     k = qk[:, :, C:].transpose(1, 2).reshape(B, heads, c, L)
+    G = q @ k.transpose(-2, -1)                                      # what uwr_mdta_gram returns: (B, heads, c, c)
+    sq_q, sq_k = (q * q).sum(-1).reshape(B, C), (k * k).sum(-1).reshape(B, C)
+    A = _mdta_matrices(G, sq_q, sq_k, temp, heads)
     ref = torch.softmax(F.normalize(q, dim=-1) @ F.normalize(k, dim=-1).transpose(-2, -1) * temp, dim=-1)
-    for b in range(B):
-        assert torch.allclose(A[b], torch.block_diag(*ref[b].unbind(0)), atol=1e-12)
+    assert torch.allclose(A, ref, atol=1e-12)

@@ -554,7 +554,7 @@ def test_window_attention_fwd_tcgen05_vs_mma_sync(ops, B, H, heads, shift, spars
 
 # ------------------------------------------------------------------------------------------ MDTA
 @pytest.mark.parametrize("B,L,heads,c", [(2, 1024, 1, 16), (3, 4096, 2, 16), (2, 1024, 8, 16), (2, 4096, 1, 32),
-                                         (1, 256, 4, 8), (1, 128, 2, 64)])
+                                         (1, 256, 4, 8), (1, 128, 1, 64)])
 def test_mdta_gram_apply(ops, B, L, heads, c):
     """uwr_mdta_gram / uwr_mdta_apply (SpectralTransformer.py:99-101,109,113) vs fp64 einsum, on column slices of a
     wider token matrix (the q | k | v layout of the qkv projection)."""
@@ -610,3 +610,101 @@ def test_mdta_attention_fn_vs_autograd(ops):
     assert rel_l2(qkv.grad, q64.grad) < 2 * TOL_TF32
     assert rel_l2(vf.grad, vf64.grad) < TOL_TF32
     assert rel_l2(temp.grad, t64.grad) < 2 * TOL_TF32
+
+
+# ------------------------------------------------------------------- up-sampler elementwise chain, thin convs
+def test_polar_split_join_cabs_vs_autograd():
+    """csrc/spectral_ew.cu vs torch.abs / angle / cos / sin on complex tensors (SpectralTransformer.py:176-186)."""
+    from uwr import fn
+    f = _r(2, 16, 16, 8, 2, seed=51).requires_grad_()
+    mag, pha = fn.PolarSplitFn.apply(f)
+    z = fn.PolarJoinFn.apply(mag * 1.3, pha + 0.2)
+    a = fn.CAbsFn.apply(z + f)
+    g = _r(*a.shape, seed=52)
+    (a * g).sum().backward()
+    f64 = f.detach().double().requires_grad_()
+    fc = torch.view_as_complex(f64)
+    m64, p64 = torch.abs(fc), torch.angle(fc)
+    z64 = torch.complex(m64 * 1.3 * torch.cos(p64 + 0.2), m64 * 1.3 * torch.sin(p64 + 0.2))
+    a64 = torch.abs(z64 + fc)
+    (a64 * g.double()).sum().backward()
+    assert rel_l2(mag, m64) < TOL_FP32 and rel_l2(pha, p64) < TOL_FP32
+    assert rel_l2(a, a64) < TOL_FP32
+    assert rel_l2(f.grad, f64.grad) < 5 * TOL_FP32
+    # abs'(0) = angle'(0) = 0 (torch's convention)
+    zero = torch.zeros(4, 2, device="cuda", requires_grad=True)
+    m0, p0 = fn.PolarSplitFn.apply(zero)
+    (m0.sum() + p0.sum() + fn.CAbsFn.apply(zero).sum()).backward()
+    assert zero.grad.abs().max().item() == 0
+
+
+def test_leaky_gelu_even_scatter_shuffle(exact):
+    from uwr import fn
+    x = _r(512, 64, seed=53).requires_grad_()
+    y = fn.LeakyReluFn.apply(x, 0.1) + fn.GeluFn.apply(x)
+    g = _r(512, 64, seed=54)
+    (y * g).sum().backward()
+    x64 = x.detach().double().requires_grad_()
+    y64 = F.leaky_relu(x64, 0.1) + F.gelu(x64)
+    (y64 * g.double()).sum().backward()
+    assert rel_l2(y, y64) < TOL_FP32 and rel_l2(x.grad, x64.grad) < TOL_FP32
+    B, H, W, Cc = 2, 8, 12, 16
+    t = _r(B * H * W, Cc, seed=55).requires_grad_()
+    bias = _r(Cc, seed=56).requires_grad_()
+    out = fn.EvenScatterFn.apply(t, bias, B, H, W)
+    go = _r(B * 4 * H * W, Cc, seed=57)
+    (out * go).sum().backward()
+    ref = bias.detach().view(1, 1, 1, Cc).expand(B, 2 * H, 2 * W, Cc).clone()
+    ref[:, ::2, ::2] = t.detach().view(B, H, W, Cc)
+    assert torch.equal(out.view(B, 2 * H, 2 * W, Cc), ref)
+    g4 = go.view(B, 2 * H, 2 * W, Cc)
+    assert torch.equal(t.grad.view(B, H, W, Cc), g4[:, ::2, ::2])
+    assert rel_l2(bias.grad, g4.double().sum((0, 1, 2)) - g4[:, ::2, ::2].double().sum((0, 1, 2))) < 1e-5
+    # PixelShuffle / PixelUnshuffle on tokens vs torch on NCHW
+    tok = _r(B * H * W, 4 * Cc, seed=58).requires_grad_()
+    up = fn.PixelShuffleFn.apply(tok, B, H, W)
+    ref_up = F.pixel_shuffle(tok.detach().view(B, H, W, 4 * Cc).permute(0, 3, 1, 2), 2).permute(0, 2, 3, 1)
+    assert torch.equal(up.view(B, 2 * H, 2 * W, Cc), ref_up)
+    back = fn.PixelUnshuffleFn.apply(up, B, H, W)
+    assert torch.equal(back, tok.detach())
+    (back * tok.detach()).sum().backward()
+    assert torch.equal(tok.grad, tok.detach())
+
+
+@pytest.mark.parametrize("Cout", [8, 16])
+def test_conv_small_img2tok(exact, Cout):
+    from uwr import fn
+    B, H, W = 2, 40, 24
+    img = _r(B, 3, H, W, seed=61)
+    w = _r(Cout, 3, 3, 3, seed=62, scale=0.3).requires_grad_()
+    b = _r(Cout, seed=63).requires_grad_() if Cout == 8 else None
+    tok = fn.ConvImg2TokFn.apply(img, w, b)
+    g = _r(B * H * W, Cout, seed=64)
+    (tok * g).sum().backward()
+    w64 = w.detach().double().requires_grad_()
+    b64 = b.detach().double().requires_grad_() if b is not None else None
+    ref = F.conv2d(img.double(), w64, b64, padding=1).permute(0, 2, 3, 1).reshape(B * H * W, Cout)
+    (ref * g.double()).sum().backward()
+    assert rel_l2(tok, ref) < TOL_FP32
+    assert rel_l2(w.grad, w64.grad) < TOL_FP32
+    if b is not None:
+        assert rel_l2(b.grad, b64.grad) < TOL_FP32
+
+
+def test_conv_small_tok2img(exact):
+    from uwr import fn
+    B, H, W = 2, 24, 40
+    tok = _r(B * H * W, 8, seed=65).requires_grad_()
+    w = _r(3, 8, 3, 3, seed=66, scale=0.3).requires_grad_()
+    b = _r(3, seed=67).requires_grad_()
+    res = _r(B, 3, H, W, seed=68)
+    out = fn.ConvTok2ImgFn.apply(tok, w, b, res, B, H, W)
+    g = _r(B, 3, H, W, seed=69)
+    (out * g).sum().backward()
+    t64 = tok.detach().double().requires_grad_()
+    w64, b64 = w.detach().double().requires_grad_(), b.detach().double().requires_grad_()
+    ref = F.conv2d(t64.view(B, H, W, 8).permute(0, 3, 1, 2), w64, b64, padding=1) + res.double()
+    (ref * g.double()).sum().backward()
+    assert rel_l2(out, ref) < TOL_FP32
+    assert rel_l2(tok.grad, t64.grad) < TOL_FP32
+    assert rel_l2(w.grad, w64.grad) < TOL_FP32 and rel_l2(b.grad, b64.grad) < TOL_FP32

@@ -732,6 +732,28 @@ extern "C" int uwr_pixel_gather_2x2(const float* dout, long long ld_dout, float*
     return 0;
 }
 
+// PixelShuffle(2) / PixelUnshuffle(2) on NHWC tokens (SpectralTransformer.py:151-158,191-198; block.py:107-153):
+// channel co*4 + dy*2 + dx of pixel (y, x)  <->  channel co of pixel (2y+dy, 2x+dx); plain data movement, no rounding.
+extern "C" int uwr_pixel_shuffle2(const float* in, float* out, long long ld_out, int B, int H, int W, int Cout,
+                                  uwr_stream_t stream_) {
+    cudaStream_t stream = (cudaStream_t)stream_;
+    UWR_REQUIRE(in && out && ((uintptr_t)in & 15) == 0, "uwr_pixel_shuffle2: null / unaligned pointer");
+    const long long total = (long long)B * H * W * Cout;
+    pixel_scatter_2x2_kernel<<<ew_blocks(total, 256), 256, 0, stream>>>(in, nullptr, out, ld_out, B, H, W, Cout);
+    UWR_CHECK_LAUNCH("pixel_scatter_2x2_kernel");
+    return 0;
+}
+
+extern "C" int uwr_pixel_unshuffle2(const float* in, long long ld_in, float* out, int B, int H, int W, int Cout,
+                                    uwr_stream_t stream_) {
+    cudaStream_t stream = (cudaStream_t)stream_;
+    UWR_REQUIRE(in && out && ((uintptr_t)out & 15) == 0, "uwr_pixel_unshuffle2: null / unaligned pointer");
+    const long long total = (long long)B * H * W * Cout;
+    pixel_gather_2x2_kernel<<<ew_blocks(total, 256), 256, 0, stream>>>(in, ld_in, out, B, H, W, Cout, 0);
+    UWR_CHECK_LAUNCH("pixel_gather_2x2_kernel");
+    return 0;
+}
+
 extern "C" int uwr_copy2d(const float* src, long long ld_src, float* dst, long long ld_dst, long long rows, int cols,
                           int accumulate, uwr_stream_t stream_) {
     cudaStream_t stream = (cudaStream_t)stream_;

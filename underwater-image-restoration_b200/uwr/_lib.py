@@ -42,6 +42,16 @@ class GemmDesc(C.Structure):
     ]
 
 
+class ConvSmallDesc(C.Structure):
+    _fields_ = [
+        ("inp", c_fp), ("in_tokens", c_int), ("ld_in", c_ll),
+        ("weight", c_fp), ("bias", c_fp), ("residual_img", c_fp),
+        ("out", c_fp), ("out_tokens", c_int), ("ld_out", c_ll),
+        ("B", c_int), ("H", c_int), ("W", c_int), ("Cin", c_int), ("Cout", c_int),
+        ("round_out", c_int),
+    ]
+
+
 class AttnDesc(C.Structure):
     _fields_ = [
         ("q", c_fp), ("ld_q", c_ll), ("q_off", c_int),
@@ -115,6 +125,23 @@ SIGNATURES = {
     "uwr_dft_hw_real": (c_int, [c_fp, c_fp, c_fp, c_int, c_int, c_int, c_int, c_f, c_stream]),
     "uwr_dft_lc_real": (c_int, [c_fp, c_fp, c_fp, c_int, c_int, c_int, c_int, c_f, c_stream]),
     "uwr_fft2_hw": (c_int, [c_fp, c_fp, c_fp, c_int, c_int, c_int, c_int, c_int, c_int, c_f, c_stream]),
+    "uwr_pixel_shuffle2": (c_int, [c_fp, c_fp, c_ll, c_int, c_int, c_int, c_int, c_stream]),
+    "uwr_pixel_unshuffle2": (c_int, [c_fp, c_ll, c_fp, c_int, c_int, c_int, c_int, c_stream]),
+    "uwr_conv3x3_small_fwd": (c_int, [C.POINTER(ConvSmallDesc), c_stream]),
+    "uwr_conv3x3_small_wgrad_workspace_bytes": (c_sz, [c_int] * 5),
+    "uwr_conv3x3_small_wgrad": (c_int, [C.POINTER(ConvSmallDesc), c_fp, c_ll, c_fp, c_fp, c_fp, c_stream]),
+    "uwr_polar_split_fwd": (c_int, [c_fp, c_fp, c_fp, c_ll, c_stream]),
+    "uwr_polar_split_bwd": (c_int, [c_fp, c_fp, c_fp, c_fp, c_ll, c_stream]),
+    "uwr_polar_join_fwd": (c_int, [c_fp, c_fp, c_fp, c_ll, c_stream]),
+    "uwr_polar_join_bwd": (c_int, [c_fp, c_fp, c_fp, c_fp, c_fp, c_ll, c_stream]),
+    "uwr_cabs_fwd": (c_int, [c_fp, c_fp, c_ll, c_stream]),
+    "uwr_cabs_bwd": (c_int, [c_fp, c_fp, c_fp, c_ll, c_stream]),
+    "uwr_leaky_relu_fwd": (c_int, [c_fp, c_fp, c_ll, c_f, c_int, c_stream]),
+    "uwr_gelu_fwd": (c_int, [c_fp, c_fp, c_ll, c_int, c_stream]),
+    "uwr_gelu_bwd": (c_int, [c_fp, c_fp, c_fp, c_ll, c_stream]),
+    "uwr_leaky_relu_bwd": (c_int, [c_fp, c_fp, c_fp, c_ll, c_f, c_stream]),
+    "uwr_even_scatter": (c_int, [c_fp, c_fp, c_fp, c_int, c_int, c_int, c_int, c_stream]),
+    "uwr_even_gather": (c_int, [c_fp, c_fp, c_int, c_int, c_int, c_int, c_stream]),
     "uwr_mdta_gram_workspace_bytes": (c_sz, [c_int, c_int, c_int, c_int]),
     "uwr_mdta_gram": (c_int, [c_fp, c_ll, c_fp, c_ll, c_int, c_int, c_int, c_int, c_fp, c_fp, c_fp, c_fp, c_stream]),
     "uwr_mdta_apply": (c_int, [c_fp, c_ll, c_fp, c_int, c_fp, c_ll, c_fp, c_fp, c_ll, c_int, c_int, c_int, c_int,

@@ -111,7 +111,7 @@ class LeFF(nn.Module):
 
 class Mlp(nn.Module):
     """plain MLP token mixer (AST.py:272-291; `token_mlp in ['ffn','mlp']`, not the registry default):
-    LayerNorm and both Linears on the uwr kernels, GELU / residual as PyTorch elementwise ops."""
+    LayerNorm, both Linears and the GELU on the uwr kernels; the residual add is a PyTorch elementwise op."""
 
     def __init__(self, in_features, hidden_features=None, out_features=None, act_layer=nn.GELU, drop=0.0):
         super().__init__()
@@ -126,7 +126,7 @@ class Mlp(nn.Module):
     def block_forward(self, x, norm, dp_scale, H, W):
         from . import fn
         y = fn.linear(fn.layernorm(x, norm), self.fc1.weight, self.fc1.bias, rounded=True)
-        y = fn.linear(torch.nn.functional.gelu(y), self.fc2.weight, self.fc2.bias)
+        y = fn.linear(fn.GeluFn.apply(y, True), self.fc2.weight, self.fc2.bias, rounded=True)
         if dp_scale is not None:
             y = y * dp_scale.view(-1, 1, 1)
         return x + y

@@ -375,3 +375,179 @@ class GeluMulFn(torch.autograd.Function):
         ops._run("uwr_gelu_mul_bwd", f"rows{t.shape[0]} h{h}", 20 * t.shape[0] * h, 0.0, ops._ptr(_c(dout)), ops._ptr(t),
                  t.stride(0), ops._ptr(dt), t.shape[0], h)
         return dt, None
+
+
+# ---- SpectralTransformer.UpSample elementwise chain (SpectralTransformer.py:174-188) on csrc/spectral_ew.cu -----------
+class PolarSplitFn(torch.autograd.Function):
+    """(abs(f), angle(f)) of an interleaved-complex tensor f (..., 2) in one pass."""
+
+    @staticmethod
+    def forward(ctx, f):
+        f = _c(f)
+        ctx.save_for_backward(f)
+        return ops.polar_split_fwd(f)
+
+    @staticmethod
+    @once_differentiable
+    def backward(ctx, dmag, dpha):
+        (f,) = ctx.saved_tensors
+        return ops.polar_split_bwd(f, _c(dmag), _c(dpha))
+
+
+class PolarJoinFn(torch.autograd.Function):
+    """z = mag * exp(i pha) as interleaved complex (..., 2)."""
+
+    @staticmethod
+    def forward(ctx, mag, pha):
+        mag, pha = _c(mag), _c(pha)
+        ctx.save_for_backward(mag, pha)
+        return ops.polar_join_fwd(mag, pha)
+
+    @staticmethod
+    @once_differentiable
+    def backward(ctx, dz):
+        mag, pha = ctx.saved_tensors
+        return ops.polar_join_bwd(mag, pha, _c(dz))
+
+
+class CAbsFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, z):
+        z = _c(z)
+        ctx.save_for_backward(z)
+        return ops.cabs_fwd(z)
+
+    @staticmethod
+    @once_differentiable
+    def backward(ctx, da):
+        (z,) = ctx.saved_tensors
+        return ops.cabs_bwd(z, _c(da))
+
+
+class GeluFn(torch.autograd.Function):
+    """exact (erf) GELU; `rounded`: the result feeds a GEMM (TF32-rounded at the store in single-pass mode)."""
+
+    @staticmethod
+    def forward(ctx, x, rounded=False):
+        x = _c(x)
+        ctx.save_for_backward(x)
+        return ops.gelu_fwd(x, rounded)
+
+    @staticmethod
+    @once_differentiable
+    def backward(ctx, dy):
+        (x,) = ctx.saved_tensors
+        return ops.gelu_bwd(x, _c(dy)), None
+
+
+class LeakyReluFn(torch.autograd.Function):
+    """LeakyReLU(slope > 0); the output is what is saved.  `rounded`: the result feeds a GEMM."""
+
+    @staticmethod
+    def forward(ctx, x, slope, rounded=False):
+        y = ops.leaky_relu_fwd(_c(x), slope, rounded)
+        ctx.save_for_backward(y)
+        ctx.slope = slope
+        return y
+
+    @staticmethod
+    @once_differentiable
+    def backward(ctx, dy):
+        (y,) = ctx.saved_tensors
+        return ops.leaky_relu_bwd(y, _c(dy), ctx.slope), None, None
+
+
+class EvenScatterFn(torch.autograd.Function):
+    """tokens y (B*H*W, C) -> tokens (B*2H*2W, C): y on the even pixels, `bias` on all the others."""
+
+    @staticmethod
+    def forward(ctx, y, bias, B, H, W):
+        y = _c(y)
+        ctx.dims = (B, H, W, y.shape[1])
+        return ops.even_scatter(y, bias, B, H, W, y.shape[1])
+
+    @staticmethod
+    @once_differentiable
+    def backward(ctx, dout):
+        B, H, W, Cc = ctx.dims
+        dout = _c(dout)
+        dy = ops.even_gather(dout, B, H, W, Cc)
+        dbias = ops.colsum(dout, Cc) - ops.colsum(dy, Cc)       # the gradient of the non-even pixels
+        return dy, dbias, None, None, None
+
+
+class PixelShuffleFn(torch.autograd.Function):
+    """nn.PixelShuffle(2) on tokens (B*H*W, 4C) -> (B*2H*2W, C); the backward is PixelUnshuffle."""
+
+    @staticmethod
+    def forward(ctx, t, B, H, W):
+        Cc = t.shape[1] // 4
+        ctx.dims = (B, H, W, Cc)
+        return ops.pixel_shuffle2(_c(t), B, H, W, Cc)
+
+    @staticmethod
+    @once_differentiable
+    def backward(ctx, dout):
+        B, H, W, Cc = ctx.dims
+        return ops.pixel_unshuffle2(_c(dout), B, H, W, Cc), None, None, None
+
+
+class PixelUnshuffleFn(torch.autograd.Function):
+    """nn.PixelUnshuffle(2) on tokens (B*2H*2W, C) -> (B*H*W, 4C); H, W = the coarse grid."""
+
+    @staticmethod
+    def forward(ctx, t, B, H, W):
+        Cc = t.shape[1]
+        ctx.dims = (B, H, W, Cc)
+        return ops.pixel_unshuffle2(_c(t), B, H, W, Cc)
+
+    @staticmethod
+    @once_differentiable
+    def backward(ctx, dout):
+        B, H, W, Cc = ctx.dims
+        return ops.pixel_shuffle2(_c(dout), B, H, W, Cc), None, None, None
+
+
+class ConvImg2TokFn(torch.autograd.Function):
+    """3x3 s1 p1 conv of an NCHW image (3 ch) to tokens (B*H*W, Cout), Cout in {8, 16}; the image gets no gradient."""
+
+    @staticmethod
+    def forward(ctx, img, weight, bias):
+        img = _c(img)
+        B, _, H, W = img.shape
+        ctx.save_for_backward(img, weight)
+        ctx.has_bias = bias is not None
+        return ops.conv3x3_small_fwd(img, False, weight, bias, B, H, W)
+
+    @staticmethod
+    @once_differentiable
+    def backward(ctx, dtok):
+        img, weight = ctx.saved_tensors
+        if ctx.needs_input_grad[0]:
+            raise NotImplementedError("ConvImg2TokFn: gradient w.r.t. the input image is not implemented")
+        B, _, H, W = img.shape
+        dw, db = ops.conv3x3_small_wgrad(img, False, weight, _c(dtok), B, H, W, want_bias=ctx.has_bias)
+        return None, dw, db
+
+
+class ConvTok2ImgFn(torch.autograd.Function):
+    """3x3 s1 p1 conv of tokens (B*H*W, 8) to an NCHW image (B, 3, H, W) [+ residual image]."""
+
+    @staticmethod
+    def forward(ctx, tok, weight, bias, residual, B, H, W):
+        tok = _c(tok)
+        ctx.save_for_backward(tok, weight)
+        ctx.meta = (B, H, W, bias is not None, residual is not None)
+        return ops.conv3x3_small_fwd(tok, True, weight, bias, B, H, W, residual=residual)
+
+    @staticmethod
+    @once_differentiable
+    def backward(ctx, dimg):
+        tok, weight = ctx.saved_tensors
+        B, H, W, has_bias, has_res = ctx.meta
+        dimg = _c(dimg)
+        dw, db = ops.conv3x3_small_wgrad(tok, True, weight, dimg, B, H, W, want_bias=has_bias)
+        # data gradient = the image -> tokens kernel with flipped, transposed weights
+        wt = weight.detach().flip(2, 3).transpose(0, 1).contiguous()
+        dtok = ops.conv3x3_small_fwd(dimg, False, wt, None, B, H, W)
+        return dtok, dw, db, (dimg if has_res and ctx.needs_input_grad[3] else None), None, None, None

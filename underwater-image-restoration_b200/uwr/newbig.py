@@ -16,7 +16,6 @@ import math
 
 import torch
 import torch.nn as nn
-import torch.nn.functional as F
 
 from . import fn
 from .ast import DropPath, _relative_position_index, _trunc_normal_
@@ -104,7 +103,7 @@ class FDFP(nn.Module):
         B, H, W, C = x.shape
         f = fn.dft_real(x, B, H, W, C, 1.0, "hw")                      # Re(fftn over (H, W))
         f = fn.linear(f, self.conv1.weight.flatten(1), self.conv1.bias)
-        f = fn.linear(F.gelu(f), self.conv2.weight.flatten(1), self.conv2.bias)
+        f = fn.linear(fn.GeluFn.apply(f, True), self.conv2.weight.flatten(1), self.conv2.bias, rounded=True)
         return fn.dft_real(f, B, H, W, C, 1.0 / (H * W), "hw")         # Re(ifftn) of a real tensor
 
 
@@ -198,14 +197,8 @@ class DecoderBlock(nn.Module):
 
 
 def _conv3x3_tokens(t, conv, H, W):
-    """dense 3x3 conv on tokens; the 3-channel ends fall back to the cuDNN call (K = 27 is not a
-    multiple of 4 floats for the TMA/cp.async operand rows)."""
-    Cin = conv.weight.shape[1]
-    if Cin % 4 == 0:
-        return fn.Conv3x3Fn.apply(t, conv.weight, conv.bias, H, W)
-    B, L, _ = t.shape
-    img = t.transpose(1, 2).reshape(B, Cin, H, W)
-    return F.conv2d(img, conv.weight, conv.bias, padding=1).flatten(2).transpose(1, 2).contiguous()
+    """dense 3x3 conv on tokens (Cin % 4 == 0): im2col + tensor-core GEMM"""
+    return fn.Conv3x3Fn.apply(t, conv.weight, conv.bias, H, W)
 
 
 class InputProjection(nn.Module):
@@ -221,10 +214,11 @@ class InputProjection(nn.Module):
 
     def forward(self, x):
         B, C, H, W = x.shape
-        t = x.flatten(2).transpose(1, 2).contiguous()
-        for i in range(3):
-            t = _conv3x3_tokens(t, self.proj[i], H, W)
-        return F.leaky_relu(t, 0.01)
+        # 3 -> 8: thin direct conv straight from the NCHW image to tokens (csrc/conv_small.cu)
+        t = fn.ConvImg2TokFn.apply(x, self.proj[0].weight, self.proj[0].bias).view(B, H * W, 8)
+        t = _conv3x3_tokens(t, self.proj[1], H, W)
+        t = _conv3x3_tokens(t, self.proj[2], H, W)
+        return fn.LeakyReluFn.apply(t, 0.01)
 
 
 class OutputProjection(nn.Module):
@@ -237,12 +231,12 @@ class OutputProjection(nn.Module):
         self.act = None
         self.norm = None
 
-    def forward(self, t, H, W):
+    def forward(self, t, H, W, residual=None):
         t = _conv3x3_tokens(t, self.proj[0], H, W)
         t = _conv3x3_tokens(t, self.proj[1], H, W)
         B = t.shape[0]
-        img = t.transpose(1, 2).reshape(B, 8, H, W)
-        return F.conv2d(img, self.proj[2].weight, self.proj[2].bias, padding=1)   # 8 -> 3: cuDNN (N = 3)
+        # 8 -> 3 straight to the NCHW image, the global residual `+ x` (model.py:640) in the same pass
+        return fn.ConvTok2ImgFn.apply(t.reshape(B * H * W, 8), self.proj[2].weight, self.proj[2].bias, residual, B, H, W)
 
 
 class Downsample(nn.Module):
@@ -255,8 +249,8 @@ class Downsample(nn.Module):
         B, L, C = x.shape
         H = W = int(math.sqrt(L))
         y = fn.Conv3x3Fn.apply(x, self.body[0].weight, None, H, W)                 # (B, L, C/2)
-        y = F.pixel_unshuffle(y.view(B, H, W, C // 2).permute(0, 3, 1, 2), 2)       # (B, 2C, H/2, W/2)
-        return y.flatten(2).transpose(1, 2).contiguous()
+        y = fn.PixelUnshuffleFn.apply(y.view(B * L, C // 2), B, H // 2, W // 2)     # tokens at (H/2, W/2), 2C channels
+        return y.view(B, L // 4, 2 * C)
 
 
 class Upsample(nn.Module):
@@ -269,8 +263,8 @@ class Upsample(nn.Module):
         B, L, C = x.shape
         H = W = int(math.sqrt(L))
         y = fn.Conv3x3Fn.apply(x, self.body[0].weight, None, H, W)                 # (B, L, 2C)
-        y = F.pixel_shuffle(y.view(B, H, W, 2 * C).permute(0, 3, 1, 2), 2)          # (B, C/2, 2H, 2W)
-        return y.flatten(2).transpose(1, 2).contiguous()
+        y = fn.PixelShuffleFn.apply(y.view(B * L, 2 * C), B, H, W)                  # tokens at (2H, 2W), C/2 channels
+        return y.view(B, 4 * L, C // 2)
 
 
 class MyBigFRFNModel(nn.Module):
@@ -332,7 +326,7 @@ class MyBigFRFNModel(nn.Module):
             y = getattr(self, f"upsample_{l}")(y)
             y = getattr(self, f"decoder_{l}")(y, enc_out=skips[l])
             y = getattr(self, f"decoder_{l}_1")(y)
-        return self.output_proj(y, H, W) + x
+        return self.output_proj(y, H, W, residual=x)
 
 
 class _BrokenInReference(nn.Module):

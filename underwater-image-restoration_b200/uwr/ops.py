@@ -11,7 +11,7 @@ import math
 import torch
 
 from . import _lib
-from ._lib import AttnDesc, GemmDesc, check, fn
+from ._lib import AttnDesc, ConvSmallDesc, GemmDesc, check, fn
 
 EPI_NONE, EPI_RESID, EPI_MUL_DGELU, EPI_MUL = 0, 1, 2, 3
 
@@ -599,6 +599,143 @@ def colsum(x2d, cols, out=None):
     _run("uwr_colsum", f"rows{rows} C{cols}", 4 * rows * cols, 0.0, _ptr(x2d), x2d.stride(0), _ptr(out), _ptr(ws),
          rows, cols)
     return out
+
+
+# --------------------------------------------------------------------------------------------
+def pixel_shuffle2(t2d, B, H, W, Cout, out=None, ocol=0):
+    """PixelShuffle(2) on tokens: (B*H*W, 4*Cout) -> (B*2H*2W, Cout) [or columns ocol.. of a wider `out`]."""
+    t2d = t2d if t2d.is_contiguous() else t2d.contiguous()
+    if out is None:
+        out = _empty((B * 4 * H * W, Cout), t2d)
+    n = B * H * W * Cout * 4
+    _run("uwr_pixel_shuffle2", f"B{B} H{H} C{Cout}", 8 * n, 0.0, _ptr(t2d), _colptr(out, ocol), out.stride(0), B, H, W, Cout)
+    return out
+
+
+def pixel_unshuffle2(t2d, B, H, W, Cout, icol=0):
+    """PixelUnshuffle(2) on tokens: (B*2H*2W, ld)[:, icol:icol+Cout] -> (B*H*W, 4*Cout); H, W = the coarse grid."""
+    out = _empty((B * H * W, 4 * Cout), t2d)
+    n = B * H * W * Cout * 4
+    _run("uwr_pixel_unshuffle2", f"B{B} H{H} C{Cout}", 8 * n, 0.0, _colptr(t2d, icol), t2d.stride(0), _ptr(out), B, H, W, Cout)
+    return out
+
+
+def _conv_small_desc(inp, in_tokens, weight, bias, B, H, W, out=None, out_tokens=True, residual=None, round_out=False):
+    d = ConvSmallDesc()
+    Cout, Cin = weight.shape[0], weight.shape[1]
+    d.inp, d.in_tokens, d.ld_in = _ptr(inp), int(in_tokens), (inp.stride(0) if in_tokens else 0)
+    d.weight, d.bias, d.residual_img = _ptr(weight), _ptr(bias), _ptr(residual)
+    d.out, d.out_tokens, d.ld_out = _ptr(out), int(out_tokens), (out.stride(0) if (out is not None and out_tokens) else 0)
+    d.B, d.H, d.W, d.Cin, d.Cout, d.round_out = B, H, W, Cin, Cout, int(round_out)
+    return d
+
+
+def conv3x3_small_fwd(inp, in_tokens, weight, bias, B, H, W, residual=None, round_out=False):
+    """thin direct 3x3 conv: NCHW image (3 ch) -> tokens (8|16 ch), or tokens (8 ch) -> NCHW image (3 ch) [+ residual]."""
+    Cout, Cin = weight.shape[0], weight.shape[1]
+    weight = weight if weight.is_contiguous() else weight.contiguous()
+    out_tokens = not in_tokens
+    out = _empty((B * H * W, Cout), inp) if out_tokens else _empty((B, Cout, H, W), inp)
+    d = _conv_small_desc(inp, in_tokens, weight, bias, B, H, W, out, out_tokens, residual, round_out)
+    n = B * H * W
+    _run("uwr_conv3x3_small_fwd", f"B{B} H{H} {Cin}->{Cout}", 4 * n * (Cin + Cout), 18.0 * n * Cin * Cout, C.byref(d))
+    return out
+
+
+def conv3x3_small_wgrad(inp, in_tokens, weight, dout, B, H, W, want_bias=True):
+    """(dweight, dbias) of conv3x3_small_fwd; dout has the forward output's layout."""
+    Cout, Cin = weight.shape[0], weight.shape[1]
+    d = _conv_small_desc(inp, in_tokens, weight, None, B, H, W, None, not in_tokens)
+    dweight = torch.empty_like(weight, memory_format=torch.contiguous_format)
+    dbias = _empty((Cout,), inp) if want_bias else None
+    ws = _ws(fn["uwr_conv3x3_small_wgrad_workspace_bytes"](B, H, W, Cin, Cout), inp)
+    n = B * H * W
+    _run("uwr_conv3x3_small_wgrad", f"B{B} H{H} {Cin}->{Cout}", 4 * n * (Cin + Cout), 18.0 * n * Cin * Cout,
+         C.byref(d), _ptr(dout), dout.stride(0) if not in_tokens else 0, _ptr(dweight), _ptr(dbias), _ptr(ws))
+    return dweight, dbias
+
+
+def _ew(name, n, nbytes, *args):
+    _run(name, f"n{n}", nbytes, 0.0, *args)
+
+
+def polar_split_fwd(f):
+    """f: (..., 2) interleaved complex -> (abs, angle), SpectralTransformer.py:176-177."""
+    n = f.numel() // 2
+    mag, pha = _empty(f.shape[:-1], f), _empty(f.shape[:-1], f)
+    _ew("uwr_polar_split_fwd", n, 16 * n, _ptr(f), _ptr(mag), _ptr(pha), n)
+    return mag, pha
+
+
+def polar_split_bwd(f, dmag, dpha):
+    n = f.numel() // 2
+    df = torch.empty_like(f)
+    _ew("uwr_polar_split_bwd", n, 24 * n, _ptr(f), _ptr(dmag), _ptr(dpha), _ptr(df), n)
+    return df
+
+
+def polar_join_fwd(mag, pha):
+    n = mag.numel()
+    z = _empty(tuple(mag.shape) + (2,), mag)
+    _ew("uwr_polar_join_fwd", n, 16 * n, _ptr(mag), _ptr(pha), _ptr(z), n)
+    return z
+
+
+def polar_join_bwd(mag, pha, dz):
+    n = mag.numel()
+    dmag, dpha = torch.empty_like(mag), torch.empty_like(mag)
+    _ew("uwr_polar_join_bwd", n, 32 * n, _ptr(mag), _ptr(pha), _ptr(dz), _ptr(dmag), _ptr(dpha), n)
+    return dmag, dpha
+
+
+def cabs_fwd(z):
+    n = z.numel() // 2
+    a = _empty(z.shape[:-1], z)
+    _ew("uwr_cabs_fwd", n, 12 * n, _ptr(z), _ptr(a), n)
+    return a
+
+
+def cabs_bwd(z, da):
+    n = z.numel() // 2
+    dz = torch.empty_like(z)
+    _ew("uwr_cabs_bwd", n, 20 * n, _ptr(z), _ptr(da), _ptr(dz), n)
+    return dz
+
+
+def leaky_relu_fwd(x, slope, round_out=False):
+    y = torch.empty_like(x)
+    _ew("uwr_leaky_relu_fwd", x.numel(), 8 * x.numel(), _ptr(x), _ptr(y), x.numel(), float(slope), int(round_out))
+    return y
+
+
+def gelu_fwd(x, round_out=False):
+    y = torch.empty_like(x)
+    _ew("uwr_gelu_fwd", x.numel(), 8 * x.numel(), _ptr(x), _ptr(y), x.numel(), int(round_out))
+    return y
+
+
+def gelu_bwd(x, dy):
+    dx = torch.empty_like(x)
+    _ew("uwr_gelu_bwd", x.numel(), 12 * x.numel(), _ptr(x), _ptr(dy), _ptr(dx), x.numel())
+    return dx
+
+
+def leaky_relu_bwd(y, dy, slope):
+    dx = torch.empty_like(y)
+    _ew("uwr_leaky_relu_bwd", y.numel(), 12 * y.numel(), _ptr(y), _ptr(dy), _ptr(dx), y.numel(), float(slope))
+    return dx
+
+
+def even_scatter(y, bias, B, H, W, Cc):
+    out = _empty((B * 4 * H * W, Cc), y)
+    _run("uwr_even_scatter", f"B{B} H{H} C{Cc}", 20 * B * H * W * Cc, 0.0, _ptr(y), _ptr(bias), _ptr(out), B, H, W, Cc)
+    return out
+
+
+def even_gather(dout, B, H, W, Cc):
+    dy = _empty((B * H * W, Cc), dout)
+    _run("uwr_even_gather", f"B{B} H{H} C{Cc}", 8 * B * H * W * Cc, 0.0, _ptr(dout), _ptr(dy), B, H, W, Cc)
+    return dy
 
 
 # --------------------------------------------------------------------------------------------

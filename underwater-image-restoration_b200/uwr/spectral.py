@@ -7,13 +7,14 @@ MDTA's channel attention as two GEMMs per image (Gram matrix of [q|k] over the t
 -> block-diagonal apply), the dense 3x3 convs with Cin % 4 == 0 (im2col + GEMM).
 The FFT amplitude/phase up-sampler runs its fft2 / ifft2 (and their adjoints) on the shared-memory FFT
 passes of csrc/fft.cu; the (2, 2)-tiled inverse transform is an H x W one scattered to the even pixels.
-Still ATen in this round: abs/angle/cos/sin of the up-sampler, PixelShuffle/Unshuffle, the GELU gate product of GDFN, the 3-channel first / last 3x3 conv.
+The up-sampler's abs/angle, mag*exp(i pha), |ifft2| and LeakyReLU chains are fused elementwise kernels (csrc/spectral_ew.cu),
+PixelShuffle / PixelUnshuffle are token-layout scatters (csrc/conv_io.cu), the 3-channel first / last 3x3 convs are thin direct
+convolutions (csrc/conv_small.cu).  ATen is left with torch.cat of skip connections and the residual adds.
 Only the live data path is executed: MDTA's FFT branch, `attnf`, q1X1_*, ups_4, ups1, ups2, output1
 are dead in value and gradient in the reference; their parameters are kept.
 """
 import torch
 import torch.nn as nn
-import torch.nn.functional as F
 
 from . import fn
 
@@ -87,15 +88,6 @@ class TransformerBlock(nn.Module):
         return x + self.ffn(fn.layernorm(x, self.norm2), B, H, W)
 
 
-def _to_img(t, B, H, W):
-    return t.view(B, H, W, -1).permute(0, 3, 1, 2)
-
-
-def _to_tok(img):
-    B, C, H, W = img.shape
-    return img.permute(0, 2, 3, 1).reshape(B * H * W, C).contiguous()
-
-
 def _conv3x3(t, conv, B, H, W):
     return fn.Conv3x3Fn.apply(t.view(B, H * W, -1), conv.weight, conv.bias, H, W).view(B * H * W, -1)
 
@@ -107,11 +99,12 @@ class DownSample(nn.Module):
                                   nn.PixelUnshuffle(2))
 
     def forward(self, t, B, H, W):
-        return _to_tok(F.pixel_unshuffle(_to_img(_conv3x3(t, self.body[0], B, H, W), B, H, W), 2))
+        return fn.PixelUnshuffleFn.apply(_conv3x3(t, self.body[0], B, H, W), B, H // 2, W // 2)
 
 
 class UpSample(nn.Module):
-    """FFT amplitude / phase up-sampler (lines 161-188); ATen this round."""
+    """FFT amplitude / phase up-sampler (lines 161-188): FFT passes (csrc/fft.cu), the abs/angle, mag*exp(i pha),
+    |ifft2| and LeakyReLU chains as one fused elementwise kernel each (csrc/spectral_ew.cu), 1x1 convs as GEMMs."""
 
     def __init__(self, channels, channel_red):
         super().__init__()
@@ -123,24 +116,22 @@ class UpSample(nn.Module):
 
     @staticmethod
     def _mlp(seq, x2d):   # Conv1x1 -> LeakyReLU(0.1) -> Conv1x1 on tokens (tensor-core GEMMs)
-        h = F.leaky_relu(fn.linear(x2d, _w2(seq[0]), seq[0].bias), 0.1)
-        return fn.linear(h, _w2(seq[2]), seq[2].bias)
+        h = fn.LeakyReluFn.apply(fn.linear(x2d, _w2(seq[0]), seq[0].bias), 0.1, True)
+        return fn.linear(h, _w2(seq[2]), seq[2].bias, rounded=True)
 
     def forward(self, t, B, H, W):   # tokens (B*H*W, C) -> tokens (B*2H*2W, C_out)
         C = t.shape[1]
         # fft2 on the shared-memory FFT passes (csrc/fft.cu), NHWC, no NCHW round trip
-        f = torch.view_as_complex(fn.Fft2Fn.apply(t.view(B, H, W, C), B, H, W, C, False, False, 1.0))
-        mag = self._mlp(self.amp_fuse, torch.abs(f).view(B * H * W, C))
-        pha = self._mlp(self.pha_fuse, torch.angle(f).view(B * H * W, C))
-        z = torch.stack([mag * torch.cos(pha), mag * torch.sin(pha)], dim=-1).view(B, H, W, C, 2)
+        f = fn.Fft2Fn.apply(t.view(B, H, W, C), B, H, W, C, False, False, 1.0)                 # (B, H, W, C, 2)
+        mag0, pha0 = fn.PolarSplitFn.apply(f)
+        mag = self._mlp(self.amp_fuse, mag0.view(B * H * W, C))
+        pha = self._mlp(self.pha_fuse, pha0.view(B * H * W, C))
+        z = fn.PolarJoinFn.apply(mag, pha).view(B, H, W, C, 2)
         # ifft2 of the (2, 2)-tiled spectrum at 2H x 2W == ifft2 of the spectrum at H x W written to the even
         # pixels, exact zeros elsewhere: a quarter of the transform work and no tile()
-        small = torch.abs(torch.view_as_complex(fn.Fft2Fn.apply(z, B, H, W, C, True, True, 1.0 / (H * W))))
+        small = fn.CAbsFn.apply(fn.Fft2Fn.apply(z, B, H, W, C, True, True, 1.0 / (H * W)))
         y = fn.linear(small.view(B * H * W, C), _w2(self.post), self.post.bias)          # post(|z|) at even pixels
-        Co = y.shape[1]
-        out = self.post.bias.view(1, 1, 1, Co).expand(B, 2 * H, 2 * W, Co).contiguous()   # post(0) = bias elsewhere
-        out[:, ::2, ::2, :] = y.view(B, H, W, Co)
-        return out.view(B * 4 * H * W, Co)
+        return fn.EvenScatterFn.apply(y, self.post.bias, B, H, W)                         # post(0) = bias elsewhere
 
 
 class UpSample1(nn.Module):
@@ -150,7 +141,7 @@ class UpSample1(nn.Module):
                                   nn.PixelShuffle(2))
 
     def forward(self, t, B, H, W):
-        return F.pixel_shuffle(_to_img(_conv3x3(t, self.body[0], B, H, W), B, H, W), 2)
+        return fn.PixelShuffleFn.apply(_conv3x3(t, self.body[0], B, H, W), B, H, W)     # tokens at (2H, 2W)
 
 
 class UpS(nn.Module):
@@ -161,7 +152,7 @@ class UpS(nn.Module):
         self.reduce = nn.Conv2d(channels, channels // 2, kernel_size=1, bias=False)
 
     def forward(self, t, B, H, W):   # tokens at (H, W) -> tokens at (2H, 2W)
-        cat = torch.cat([self.Fups(t, B, H, W), _to_tok(self.Sups(t, B, H, W))], dim=1)
+        cat = torch.cat([self.Fups(t, B, H, W), self.Sups(t, B, H, W)], dim=1)
         return fn.linear(cat, _w2(self.reduce))
 
 
@@ -203,7 +194,7 @@ class SpectralTransformer(nn.Module):
         B, _, H, W = x.shape
         if H % 8 or W % 8:
             raise ValueError("SpectralTransformer needs H and W divisible by 8")
-        f0 = _to_tok(F.conv2d(x, self.embed_conv_rgb.weight, padding=1))     # 3 -> 16 (K = 27): cuDNN
+        f0 = fn.ConvImg2TokFn.apply(x, self.embed_conv_rgb.weight, None)     # 3 -> 16: thin direct conv (csrc/conv_small.cu)
         e1 = self._stage(self.encoders[0], f0, B, H, W)
         e2 = self._stage(self.encoders[1], self.down1(e1, B, H, W), B, H // 2, W // 2)
         e3 = self._stage(self.encoders[2], self.down2(e2, B, H // 2, W // 2), B, H // 4, W // 4)
@@ -215,4 +206,4 @@ class SpectralTransformer(nn.Module):
         fd = self._stage(self.decoders[2], torch.cat([self.ups_3(d2, B, H // 2, W // 2), e1], 1), B, H, W)
         fr = self._stage(self.refinement, fd, B, H, W)
         o = _conv3x3(fr, self.outputl, B, H, W)                               # 32 -> 8
-        return F.conv2d(_to_img(o, B, H, W), self.output.weight, padding=1)   # 8 -> 3 (N = 3): cuDNN
+        return fn.ConvTok2ImgFn.apply(o, self.output.weight, None, None, B, H, W)   # 8 -> 3: thin direct conv
