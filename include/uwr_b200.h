@@ -328,7 +328,7 @@ int uwr_even_gather(const float* dout, float* dy, int B, int H, int W, int C, uw
 
 /* ---- MDTA channel attention (src/Models/SpectralTransformer.py:92-113) -----------------------
  * Token matrices are (B*L, ld) fp32, the c = C/heads channels of a head contiguous; c in {8,16,32,64},
- * heads*c <= 256, L a multiple of 64.  Pass pointers already offset to the first channel.
+ * heads*c <= 256, any L >= 1.  Pass pointers already offset to the first channel.
  * uwr_mdta_gram:  G[b,h,i,j] = sum_l X[b,l,h*c+i] Y[b,l,h*c+j]   (q^T k, line 100; also dA = dout^T v),
  *                 sqx[b,ch] = sum_l X[b,l,ch]^2, sqy likewise (the L2 norms of line 99; NULL to skip).
  *                 heads*c*c <= 4096.  Deterministic (per-CTA partials in `workspace`, then one reduce).

@@ -554,7 +554,7 @@ def test_window_attention_fwd_tcgen05_vs_mma_sync(ops, B, H, heads, shift, spars
 
 # ------------------------------------------------------------------------------------------ MDTA
 @pytest.mark.parametrize("B,L,heads,c", [(2, 1024, 1, 16), (3, 4096, 2, 16), (2, 1024, 8, 16), (2, 4096, 1, 32),
-                                         (1, 256, 4, 8), (1, 128, 1, 64)])
+                                         (1, 256, 4, 8), (1, 128, 1, 64), (2, 96, 2, 16), (1, 40, 1, 32)])
 def test_mdta_gram_apply(ops, B, L, heads, c):
     """uwr_mdta_gram / uwr_mdta_apply (SpectralTransformer.py:99-101,109,113) vs fp64 einsum, on column slices of a
     wider token matrix (the q | k | v layout of the qkv projection)."""
@@ -606,10 +606,14 @@ def test_mdta_attention_fn_vs_autograd(ops):
     vfh = vf64[:, C:].view(B, L, heads, c).permute(0, 2, 3, 1)
     of64 = (A64 @ vfh).permute(0, 3, 1, 2).reshape(B * L, C)
     (o64 * g1.double()).sum().add((of64 * g2.double()).sum()).backward()
-    assert rel_l2(out, o64) < TOL_TF32 and rel_l2(outf, of64) < TOL_TF32
-    assert rel_l2(qkv.grad, q64.grad) < 2 * TOL_TF32
-    assert rel_l2(vf.grad, vf64.grad) < TOL_TF32
-    assert rel_l2(temp.grad, t64.grad) < 2 * TOL_TF32
+    errs = dict(out=rel_l2(out, o64), outf=rel_l2(outf, of64), dq=rel_l2(qkv.grad[:, :C], q64.grad[:, :C]),
+                dk=rel_l2(qkv.grad[:, C:2 * C], q64.grad[:, C:2 * C]), dv=rel_l2(qkv.grad[:, 2 * C:], q64.grad[:, 2 * C:]),
+                dvf=rel_l2(vf.grad, vf64.grad), dtemp=rel_l2(temp.grad, t64.grad))
+    print("mdta fn errors", {k: f"{v:.2e}" for k, v in errs.items()})
+    assert errs["out"] < TOL_TF32 and errs["outf"] < TOL_TF32 and errs["dv"] < TOL_TF32 and errs["dvf"] < TOL_TF32, errs
+    # dq, dk, dtemp pass through the softmax / normalisation Jacobians of a (c x c) matrix whose entries come from
+    # TF32 Gram products that cancel to O(sqrt(L)): a few 1e-3 on random data
+    assert errs["dq"] < 5 * TOL_TF32 and errs["dk"] < 5 * TOL_TF32 and errs["dtemp"] < 5 * TOL_TF32, errs
 
 
 # ------------------------------------------------------------------- up-sampler elementwise chain, thin convs

@@ -122,3 +122,16 @@ def test_droppath_semantics():
     assert all(v == 0.0 or abs(v - 1.0 / 0.75) < 1e-6 for v in s.unique().tolist())
     assert abs((s > 0).float().mean().item() - 0.75) < 0.03
     assert DropPath(0.0).train().scale(4, "cpu") is None
+
+
+def test_torch_library_ops_are_registered():
+    """SURVEY.md §8b: the kernels are exposed as torch.library ops `uwr::<name>` (CUDA-only: a CPU tensor is refused
+    by the dispatcher, there is no fallback kernel)."""
+    import torch
+    import uwr  # noqa: F401
+    from uwr import torchlib
+    for name in torchlib.OPS:
+        op = getattr(torch.ops.uwr, name)
+        assert str(op.default._schema).startswith(f"uwr::{name}(")
+    with pytest.raises(NotImplementedError):
+        torch.ops.uwr.layernorm(torch.zeros(4, 4), torch.ones(4), torch.zeros(4), 1e-5)

@@ -36,7 +36,7 @@ mdta_gram_kernel(const float* __restrict__ X, long long ldx, const float* __rest
     const int b = blockIdx.y, chunk = blockIdx.x;
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int g = lane >> 2, t = lane & 3;
-    const int ntiles = L / GR_TOK;
+    const int ntiles = (L + GR_TOK - 1) / GR_TOK;
     const int t_begin = chunk * tiles_per_cta;
     const int t_end = min(ntiles, t_begin + tiles_per_cta);
     const float* Xb = X + (long long)b * L * ldx;
@@ -58,8 +58,9 @@ mdta_gram_kernel(const float* __restrict__ X, long long ldx, const float* __rest
         for (int idx = tid; idx < GR_TOK * v4; idx += MD_THREADS) {
             const int r = idx / v4, c4 = (idx - r * v4) * 4;
             const long long row = (long long)tile * GR_TOK + r;
-            cp_async16(Xs + (buf * GR_TOK + r) * ST + c4, Xb + row * ldx + c4, true);
-            cp_async16(Ys + (buf * GR_TOK + r) * ST + c4, Yb + row * ldy + c4, true);
+            const bool ok = row < L;   // rows past the image are zero-filled (src-size 0)
+            cp_async16(Xs + (buf * GR_TOK + r) * ST + c4, Xb + (ok ? row : 0) * ldx + c4, ok);
+            cp_async16(Ys + (buf * GR_TOK + r) * ST + c4, Yb + (ok ? row : 0) * ldy + c4, ok);
         }
         cp_async_commit();
     };
@@ -147,7 +148,7 @@ __global__ void mdta_gram_reduce_kernel(const float* __restrict__ partials, int 
 }
 
 int gram_chunks(int B, int L) {
-    const int tiles = L / GR_TOK;
+    const int tiles = (L + GR_TOK - 1) / GR_TOK;
     int chunks = (4 * uwr_sm_count() + B - 1) / B;
     if (chunks > tiles) chunks = tiles;
     if (chunks < 1) chunks = 1;
@@ -170,18 +171,20 @@ mdta_apply_kernel(const float* __restrict__ X, long long ldx, const float* __res
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int g = lane >> 2, t = lane & 3;
-    const int tiles_per_img = L / AP_TOK;
+    const int tiles_per_img = (L + AP_TOK - 1) / AP_TOK;
     const int total = B * tiles_per_img;
     int cur_b = -1;
     for (int tile = blockIdx.x; tile < total; tile += gridDim.x) {
         const int b = tile / tiles_per_img;
-        const long long row0 = (long long)b * L + (long long)(tile - b * tiles_per_img) * AP_TOK;
+        const int l0 = (tile - b * tiles_per_img) * AP_TOK;   // first token of the tile inside its image
+        const long long row0 = (long long)b * L + l0;
+        const int valid = min(AP_TOK, L - l0);
         __syncthreads();   // previous tile's readers are done with Xs (and Ms when the image changes)
         {
             const int v4 = C / 4;
             for (int idx = tid; idx < AP_TOK * v4; idx += MD_THREADS) {
                 const int r = idx / v4, c4 = (idx - r * v4) * 4;
-                cp_async16(Xs + r * ST + c4, X + (row0 + r) * ldx + c4, true);
+                cp_async16(Xs + r * ST + c4, X + (row0 + (r < valid ? r : 0)) * ldx + c4, r < valid);
             }
             cp_async_commit();
         }
@@ -223,6 +226,7 @@ mdta_apply_kernel(const float* __restrict__ X, long long ldx, const float* __res
             }
 #pragma unroll
             for (int half = 0; half < 2; ++half) {
+                if (r0 + g + half * 8 >= valid) continue;
                 const long long row = row0 + r0 + g + half * 8;
 #pragma unroll
                 for (int n = 0; n < CH / 8; ++n) {
@@ -246,7 +250,7 @@ int launch_gram(const float* X, long long ldx, const float* Y, long long ldy, in
                 float* sqx, float* sqy, float* ws, cudaStream_t stream) {
     const int C = heads * CH;
     const int chunks = gram_chunks(B, L);
-    const int tiles = L / GR_TOK;
+    const int tiles = (L + GR_TOK - 1) / GR_TOK;
     const int tpc = uwr_cdiv(tiles, chunks);
     const int smem = 4 * GR_TOK * (C + 8) * 4;
     auto kern = mdta_gram_kernel<CH>;
@@ -275,7 +279,7 @@ int launch_apply(const float* X, long long ldx, const float* Mx, int transpose, 
                                       (AP_TOK * (256 + 4) + 256 * (CH + 4) + 256) * 4));
         configured = true;
     }
-    const long long total = (long long)B * (L / AP_TOK);
+    const long long total = (long long)B * ((L + AP_TOK - 1) / AP_TOK);
     int grid = 4 * uwr_sm_count();
     if (grid > total) grid = (int)total;
     kern<<<grid, MD_THREADS, smem, stream>>>(X, ldx, Mx, transpose, Yd, ldy, diag, out, ldo, B, L, heads,
@@ -285,7 +289,7 @@ int launch_apply(const float* X, long long ldx, const float* Mx, int transpose, 
 }
 
 int check_common(const char* who, int B, int L, int heads, int c) {
-    UWR_REQUIRE(B >= 1 && L >= AP_TOK && L % AP_TOK == 0, "%s: L must be a positive multiple of %d", who, AP_TOK);
+    UWR_REQUIRE(B >= 1 && L >= 1, "%s: B, L must be positive", who);
     UWR_REQUIRE(c == 8 || c == 16 || c == 32 || c == 64, "%s: channels per head %d unsupported (8,16,32,64)", who, c);
     UWR_REQUIRE(heads >= 1 && heads * c <= 256, "%s: heads * c must be <= 256", who);
     return 0;
@@ -294,7 +298,7 @@ int check_common(const char* who, int B, int L, int heads, int c) {
 }  // namespace
 
 extern "C" size_t uwr_mdta_gram_workspace_bytes(int B, int L, int heads, int c) {
-    if (B < 1 || L < GR_TOK) return 0;
+    if (B < 1 || L < 1) return 0;
     return (size_t)B * gram_chunks(B, L) * ((size_t)heads * c * c + 2 * (size_t)heads * c) * sizeof(float);
 }
 
