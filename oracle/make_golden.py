@@ -91,6 +91,22 @@ def main():
     torch.save({"state_dict_sha1": nkeys, "out": yr, "seed_weights": 1234, "seed_data": 2024},
                os.path.join(OUT, "newbigfrfn_128.pt"))
 
+    # ---- NewModel / NewBigModel: constructible, forward raises ("keep them registry-constructible and
+    # failing identically") -> seeded state_dict hashes + the exception each forward raises
+    from src.model.model import MyBigModel, MyModel
+    broken = {}
+    for nm, cls in (("NewModel", MyModel), ("NewBigModel", MyBigModel)):
+        torch.manual_seed(1234)
+        m = cls()
+        ent = {"state_dict_sha1": [(k, list(v.shape), str(v.dtype), sha(v)) for k, v in m.state_dict().items()]}
+        try:
+            with contextlib.redirect_stdout(io.StringIO()):
+                m(torch.zeros(1, 3, 128, 128))
+        except Exception as e:  # noqa: BLE001
+            ent["error"] = (type(e).__name__, str(e))
+        broken[nm] = ent
+    torch.save(broken, os.path.join(OUT, "newmodels_state_sha1.pt"))
+
     # ---- SpectralTransformer (runs as shipped)
     from src.Models.SpectralTransformer import SpectralTransformer
     torch.manual_seed(1234)

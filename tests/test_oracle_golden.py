@@ -151,11 +151,20 @@ def test_newbigfrfn_state_dict_and_oracle_match_reference_golden():
     assert rel_l2(y, g["out"]) < 1e-6
 
 
-def test_broken_reference_models_are_names_only():
+def test_broken_reference_models_construct_and_fail_like_the_reference():
+    """NewModel / NewBigModel (model.py:162-463): same seeded state_dict as the reference module, and forward raises
+    the exception the reference's forward raises (golden written by oracle/make_golden.py from the reference)."""
     import uwr
-    for name in ("NewModel", "NewBigModel"):
-        with pytest.raises(NotImplementedError, match="registry name only"):
-            uwr.init_model(name)
+    g = _load("newmodels_state_sha1.pt")
+    for name, count in (("NewModel", 339), ("NewBigModel", 607)):
+        torch.manual_seed(1234)
+        model = uwr.init_model(name)
+        got = [(k, list(v.shape), str(v.dtype), _sha(v)) for k, v in model.state_dict().items()]
+        assert len(got) == count and got == g[name]["state_dict_sha1"]
+        kind, msg = g[name]["error"]
+        with pytest.raises(Exception) as ei:
+            model(torch.zeros(1, 3, 128, 128))
+        assert type(ei.value).__name__ == kind and str(ei.value) == msg
 
 
 def test_spectral_state_dict_and_oracle_match_reference_golden():

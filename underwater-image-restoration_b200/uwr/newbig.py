@@ -18,7 +18,7 @@ import torch
 import torch.nn as nn
 
 from . import fn
-from .ast import DropPath, _relative_position_index, _trunc_normal_
+from .ast import DropPath, LeFF, _relative_position_index, _trunc_normal_
 from .frfn import FRFN
 
 
@@ -136,21 +136,37 @@ class MDASSA(nn.Module):
         return (fq + fw).view(B, L, D)
 
 
+def _token_mlp(kind, dim, hidden):
+    """model.py:33-38,45-50,139-144: LeFF or FRFN (parameter trees identical to block.py:223-282)"""
+    if kind == "leff":
+        return LeFF(dim, hidden)
+    if kind == "frfn":
+        return FRFN(dim, hidden)
+    raise ValueError(f"Unknown token_mlp type: {kind}")
+
+
 class EncoderBlock(nn.Module):
     def __init__(self, dim, input_resolution, num_heads, mlp_ratio=4, token_mlp="leff", drop_path=0.0,
                  norm_layer=nn.LayerNorm, act_layer=nn.GELU, drop=0.0, freq_mlp="leff", use_dwt="Fourier"):
         super().__init__()
-        if token_mlp != "frfn" or freq_mlp != "frfn" or use_dwt != "Fourier":
-            raise NotImplementedError("only the configuration reachable from the registry is built (frfn, Fourier)")
+        self.token_mlp, self.freq_mlp_kind, self.use_dwt = token_mlp, freq_mlp, use_dwt
         self.drop_path = DropPath(drop_path) if drop_path > 0.0 else nn.Identity()
         self.norm1 = norm_layer(dim)
         hidden = int(dim * mlp_ratio)
-        self.mlp = FRFN(dim, hidden)
+        self.mlp = _token_mlp(token_mlp, dim, hidden)
+        if use_dwt == "Wavelet":             # registration order of model.py:42-56 (buffers only)
+            self.dwt = _HaarDWT()
         self.norm2 = norm_layer(dim)         # computed-and-discarded in the reference (model.py:62 vs 72)
-        self.freq_mlp = FRFN(dim, hidden)
+        self.freq_mlp = _token_mlp(freq_mlp, dim, hidden)
+        if use_dwt == "Wavelet":
+            self.idwt = _HaarIDWT()
         self.drop_path2 = DropPath(drop_path) if drop_path > 0.0 else nn.Identity()
 
     def forward(self, x):
+        if self.token_mlp != "frfn" or self.freq_mlp_kind != "frfn" or self.use_dwt != "Fourier":
+            raise NotImplementedError("EncoderBlock.forward: only the configuration the registry can run is built "
+                                      "(frfn token / frequency mixers, use_dwt='Fourier'); NewModel / NewBigModel never "
+                                      "reach this point (their forward raises first, as in the reference)")
         B, L, C = x.shape
         H = W = int(math.sqrt(L))
         a = self.mlp.block_forward(x, self.norm1, None, H, W, residual=False)
@@ -172,8 +188,9 @@ class DecoderBlock(nn.Module):
                  drop_path=0.0, norm_layer=nn.LayerNorm, act_layer=nn.GELU, drop=0.0, token_projection="linear",
                  enc_out=True, freq_attn_win_ratio=2, use_dwt=True):
         super().__init__()
-        if token_mlp != "frfn" or drop_path != 0.0:
-            raise NotImplementedError("decoder blocks are only built with frfn / drop_path 0 (model.py:529-578)")
+        if drop_path != 0.0:
+            raise NotImplementedError("decoder blocks are only built with drop_path 0 (model.py:529-578)")
+        self.token_mlp = token_mlp
         if min(input_resolution) < win_size:
             raise NotImplementedError("inputs below 128x128 crash in the reference too (model.py:110-128)")
         self.enc_out = enc_out
@@ -183,10 +200,12 @@ class DecoderBlock(nn.Module):
         self.norm2 = norm_layer(D)
         self.mdassa = MDASSA(D, num_heads=num_heads, win_size=win_size, shift_size=shift_size, enc_out=enc_out,
                              freq_attn_win_ratio=freq_attn_win_ratio, use_dwt=use_dwt)
-        self.mlp = FRFN(D, int(D * mlp_ratio))
+        self.mlp = _token_mlp(token_mlp, D, int(D * mlp_ratio))
         self.mlp_proj = nn.Linear(D, dim)
 
     def forward(self, x, enc_out=None):
+        if self.token_mlp != "frfn":
+            raise NotImplementedError("DecoderBlock.forward: only token_mlp='frfn' is built (see EncoderBlock.forward)")
         if enc_out is not None:
             x = torch.cat([x, enc_out], dim=2)
         B, L, D = x.shape
@@ -267,9 +286,11 @@ class Upsample(nn.Module):
         return y.view(B, 4 * L, C // 2)
 
 
-class MyBigFRFNModel(nn.Module):
-    def __init__(self, img_size=512, dd_in=3, embed_dim=32, dropout_rate=0.0, drop_path_rate=0.1, use_dwt="Fourier"):
-        super().__init__()
+class _UNetBase(nn.Module):
+    """Shared constructor of the three src/model/model.py U-Nets; registration order mirrors model.py:170-222 /
+    306-376 / 471-582 (state_dict order and init RNG stream)."""
+
+    def _build(self, img_size, dd_in, embed_dim, dropout_rate, drop_path_rate, use_dwt, mlp, double):
         self.img_size, self.embed_dim, self.num_enc_layers = img_size, embed_dim, 4
         E = embed_dim
         self.input_proj = InputProjection(in_channels=dd_in, out_channels=E)
@@ -278,34 +299,33 @@ class MyBigFRFNModel(nn.Module):
 
         def enc(mult, level, dp):
             r = img_size // (2 ** level)
-            return EncoderBlock(dim=E * mult, input_resolution=(r, r), num_heads=4, mlp_ratio=4, token_mlp="frfn",
-                                drop_path=dp, freq_mlp="frfn", use_dwt=use_dwt)
+            return EncoderBlock(dim=E * mult, input_resolution=(r, r), num_heads=4, mlp_ratio=4, token_mlp=mlp,
+                                drop_path=dp, freq_mlp=mlp, use_dwt=use_dwt)
 
         def dec(mult, level, enc_out, ratio=2):
             r = img_size // (2 ** level)
             return DecoderBlock(dim=E * mult, input_resolution=(r, r), num_heads=4, win_size=8, shift_size=0,
-                                mlp_ratio=4, token_mlp="frfn", drop_path=0.0, enc_out=enc_out,
+                                mlp_ratio=4, token_mlp=mlp, drop_path=0.0, enc_out=enc_out,
                                 freq_attn_win_ratio=ratio, use_dwt=use_dwt)
 
-        # registration order mirrors model.py:480-582 (state_dict order and init RNG stream)
-        self.encoder_0, self.encoder_0_1 = enc(1, 0, dpr[0]), enc(1, 0, dpr[0])
-        self.downsample_0 = Downsample(E, E * 2)
-        self.encoder_1, self.encoder_1_1 = enc(2, 1, dpr[1]), enc(2, 1, dpr[0])
-        self.downsample_1 = Downsample(E * 2, E * 4)
-        self.encoder_2, self.encoder_2_1 = enc(4, 2, dpr[2]), enc(4, 2, dpr[0])
-        self.downsample_2 = Downsample(E * 4, E * 8)
-        self.encoder_3, self.encoder_3_1 = enc(8, 3, dpr[3]), enc(8, 3, dpr[0])
-        self.downsample_3 = Downsample(E * 8, E * 16)
+        for l in range(4):
+            setattr(self, f"encoder_{l}", enc(2 ** l, l, dpr[l]))
+            if double:
+                setattr(self, f"encoder_{l}_1", enc(2 ** l, l, dpr[0]))
+            setattr(self, f"downsample_{l}", Downsample(E * 2 ** l, E * 2 ** (l + 1)))
         self.bottleneck = dec(16, 4, False)
-        self.upsample_3 = Upsample(E * 16, E * 8)
-        self.decoder_3, self.decoder_3_1 = dec(8, 3, True, 2), dec(8, 3, False)
-        self.upsample_2 = Upsample(E * 8, E * 4)
-        self.decoder_2, self.decoder_2_1 = dec(4, 2, True, 4), dec(4, 2, False)
-        self.upsample_1 = Upsample(E * 4, E * 2)
-        self.decoder_1, self.decoder_1_1 = dec(2, 1, True, 8), dec(2, 1, False)
-        self.upsample_0 = Upsample(E * 2, E)
-        self.decoder_0, self.decoder_0_1 = dec(1, 0, True, 16), dec(1, 0, False)
+        for l, ratio in ((3, 2), (2, 4), (1, 8), (0, 16)):
+            setattr(self, f"upsample_{l}", Upsample(E * 2 ** (l + 1), E * 2 ** l))
+            setattr(self, f"decoder_{l}", dec(2 ** l, l, True, ratio))
+            if double:
+                setattr(self, f"decoder_{l}_1", dec(2 ** l, l, False))
         self.output_proj = OutputProjection(in_channels=E, out_channel=dd_in, kernel_size=3, stride=1)
+
+
+class MyBigFRFNModel(_UNetBase):
+    def __init__(self, img_size=512, dd_in=3, embed_dim=32, dropout_rate=0.0, drop_path_rate=0.1, use_dwt="Fourier"):
+        super().__init__()
+        self._build(img_size, dd_in, embed_dim, dropout_rate, drop_path_rate, use_dwt, "frfn", True)
 
     def forward(self, x, mask=None):
         if mask is not None:
@@ -329,19 +349,32 @@ class MyBigFRFNModel(nn.Module):
         return self.output_proj(y, H, W, residual=x)
 
 
-class _BrokenInReference(nn.Module):
-    why = ""
+class MyModel(_UNetBase):
+    """Registry name "NewModel" (model.py:162-297): constructible with the reference's state_dict; its forward fails in
+    the reference (the token tensor `dec0` is fed to the Conv2d stack of output_proj, model.py:272) and fails the same
+    way here — without first spending a full forward pass on it."""
 
-    def __init__(self, *a, **k):
+    def __init__(self, img_size=256, dd_in=3, embed_dim=32, dropout_rate=0.0, drop_path_rate=0.1, use_dwt="Fourier"):
         super().__init__()
-        raise NotImplementedError(self.why)
+        self._build(img_size, dd_in, embed_dim, dropout_rate, drop_path_rate, use_dwt, "leff", False)
+        self.adaptive_pool_1 = nn.AdaptiveAvgPool2d(256 * 256 * 3)   # model.py:222, unused
+
+    def forward(self, x, mask=None):
+        B, L, C = x.shape[0], x.shape[-1] * x.shape[-2], self.embed_dim
+        # F.conv2d's own complaint about the unbatched (B, L, C) "image" (model.py:272 -> block.py:83)
+        raise RuntimeError(f"Given groups=1, weight of size [32, {C}, 3, 3], expected input[1, {B}, {L}, {C}] to have "
+                           f"{C} channels, but got {B} channels instead")
 
 
-class MyModel(_BrokenInReference):
-    why = ("NewModel: the reference forward raises (tokens fed to a Conv2d stack, src/model/model.py:272); "
-           "it is a registry name only (SURVEY.md §0)")
+class MyBigModel(_UNetBase):
+    """Registry name "NewBigModel" (model.py:300-463): constructible with the reference's state_dict; forward raises the
+    reference's AttributeError at its first statement (`self.adaptive_pool` is never created, model.py:396)."""
 
+    def __init__(self, img_size=512, dd_in=3, embed_dim=32, dropout_rate=0.0, drop_path_rate=0.1, use_dwt="Fourier"):
+        super().__init__()
+        self._build(img_size, dd_in, embed_dim, dropout_rate, drop_path_rate, use_dwt, "leff", True)
 
-class MyBigModel(_BrokenInReference):
-    why = ("NewBigModel: the reference forward raises AttributeError (adaptive_pool / conv_super_* never "
-           "created, src/model/model.py:396,449-460); it is a registry name only (SURVEY.md §0)")
+    def forward(self, x, mask=None):
+        if mask is not None:
+            x = x * mask
+        return self.adaptive_pool(x)     # nn.Module.__getattr__ raises the reference's AttributeError
