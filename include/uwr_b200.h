@@ -346,7 +346,9 @@ int uwr_mdta_apply(const float* X, long long ldx, const float* M, int transpose,
  * tensor tables are device arrays of pointers; `offsets` (n_tensors+1 entries, offsets[0]=0) is
  * the running element count of the virtual concatenation.
  * norm_out[0] = total L2 norm, norm_out[1] = clip coefficient min(1, max_norm/(norm+1e-6)).
- * step_dev (optional device int) overrides `step` so a captured CUDA graph can be replayed.
+ * step_dev (optional device int) overrides `step`, lr_dev (optional device float) overrides `lr`, so that a
+ * captured CUDA graph can be replayed while the step counter advances and an LR scheduler (the reference uses
+ * MultiStepLR([1,100,250], 0.25), ModelTrainer.py:55,129) changes the rate.
  */
 int uwr_grad_norm(const float* const* grads, const long long* offsets, int n_tensors,
                   long long total_elems, float max_norm, float grad_prescale, float* norm_out,
@@ -356,7 +358,7 @@ int uwr_adam_step(float* const* params, const float* const* grads, float* const*
                   long long total_elems, const float* clip_coef /* device, may be NULL */,
                   float grad_prescale, float lr, float beta1, float beta2, float eps,
                   float weight_decay, int decoupled, int step, const int* step_dev,
-                  uwr_stream_t stream);
+                  const float* lr_dev, uwr_stream_t stream);
 int uwr_increment_i32(int* counter, uwr_stream_t stream);
 
 #ifdef __cplusplus

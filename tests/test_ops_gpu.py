@@ -470,7 +470,7 @@ def test_fflmix_loss_tuple_matches_reference_golden():
     p = torch.rand(2, 3, 256, 256)
     t = torch.rand(2, 3, 256, 256)
     pc = p.cuda().requires_grad_()
-    out = LossFunction("fflMix", "cuda").getloss(pc, t.cuda())
+    out = LossFunction("fflMix", "cuda", vgg_weights="random").getloss(pc, t.cuda())   # patch P3, explicit opt-in
     assert isinstance(out, tuple) and len(out) == 6
     for got, want in zip(out, g):
         assert abs(got.item() - want) <= 2e-4 * abs(want), (got.item(), want)
@@ -712,3 +712,78 @@ def test_conv_small_tok2img(exact):
     assert rel_l2(out, ref) < TOL_FP32
     assert rel_l2(tok.grad, t64.grad) < TOL_FP32
     assert rel_l2(w.grad, w64.grad) < TOL_FP32 and rel_l2(b.grad, b64.grad) < TOL_FP32
+
+
+def test_fused_clip_adam_is_a_torch_optimizer_with_checkpoint_and_scheduler():
+    """lr lives on the device (graph replays follow a scheduler), state_dict round-trips in
+    torch.optim.Adam's layout (the reference checkpoint's `optimizer_state_dict`, ModelTrainer.py:172-190)."""
+    from uwr.optim import FusedClipAdam
+    torch.manual_seed(0)
+    ps = [torch.nn.Parameter(torch.randn(64, 32).cuda()), torch.nn.Parameter(torch.randn(7).cuda())]
+    qs = [torch.nn.Parameter(p.detach().clone()) for p in ps]
+    opt = FusedClipAdam(ps, lr=1e-3, max_norm=1.0)
+    ref = torch.optim.Adam(qs, lr=1e-3)
+    sched = torch.optim.lr_scheduler.MultiStepLR(opt, milestones=[1, 3], gamma=0.25)   # ModelTrainer.py:55
+    rsched = torch.optim.lr_scheduler.MultiStepLR(ref, milestones=[1, 3], gamma=0.25)
+    grads = [[torch.randn_like(p) for p in ps] for _ in range(5)]
+
+    def both(it):
+        for p, q, g in zip(ps, qs, grads[it]):
+            p.grad, q.grad = g.clone(), g.clone()
+        opt.step()
+        torch.nn.utils.clip_grad_norm_(qs, 1.0)
+        ref.step()
+        sched.step()
+        rsched.step()
+    for it in range(3):
+        both(it)
+    assert opt.param_groups[0]["lr"] == ref.param_groups[0]["lr"] == 1e-3 * 0.25
+    for p, q in zip(ps, qs):
+        assert rel_l2(p, q) < 1e-6
+    # checkpoint in torch layout: loads into a fresh torch.optim.Adam and back into a fresh FusedClipAdam
+    sd = opt.state_dict()
+    assert set(sd) == {"state", "param_groups"} and set(sd["state"][0]) == {"step", "exp_avg", "exp_avg_sq"}
+    assert float(sd["state"][0]["step"]) == 3.0 and opt.step_count == 3
+    ps2 = [torch.nn.Parameter(p.detach().clone()) for p in ps]
+    qs2 = [torch.nn.Parameter(p.detach().clone()) for p in ps]
+    opt2, ref2 = FusedClipAdam(ps2, lr=123.0, max_norm=1.0), torch.optim.Adam(qs2, lr=123.0)
+    opt2.load_state_dict(sd)
+    ref2.load_state_dict(sd)
+    assert opt2.lr == ref2.param_groups[0]["lr"] == 1e-3 * 0.25 and opt2.step_count == 3
+    for p, q, g in zip(ps2, qs2, grads[3]):
+        p.grad, q.grad = g.clone(), g.clone()
+    opt2.step()
+    torch.nn.utils.clip_grad_norm_(qs2, 1.0)
+    ref2.step()
+    for p, q in zip(ps2, qs2):
+        assert rel_l2(p, q) < 1e-6
+    # excluded (never-touched) parameters keep their value under AdamW, as torch's grad-None parameters do
+    a, b = torch.nn.Parameter(torch.ones(8).cuda()), torch.nn.Parameter(torch.ones(8).cuda())
+    o3 = FusedClipAdam([a, b], lr=1e-2, weight_decay=0.1, decoupled=True)
+    a.grad, b.grad = torch.ones_like(a), torch.zeros_like(b)
+    o3.exclude([b])
+    o3.step()
+    assert torch.equal(b.detach(), torch.ones_like(b)) and not torch.equal(a.detach(), torch.ones_like(a))
+    assert b not in o3.state or "exp_avg" not in o3.state[b]
+
+
+def test_graphed_step_follows_lr_changes():
+    """A captured training step replays with the CURRENT learning rate (device scalar) — ADVICE r1."""
+    import uwr
+    from uwr.graph import GraphedTrainStep
+    from uwr.train import TrainStep
+    torch.manual_seed(3)
+    model = uwr.AST(img_size=128).cuda().train()
+    step = TrainStep(model, "L1", lr=1e-3)
+    g = torch.Generator().manual_seed(1)
+    raw = (torch.rand(1, 3, 128, 128, generator=g) * 2 - 1).cuda()
+    ref = (torch.rand(1, 3, 128, 128, generator=g) * 2 - 1).cuda()
+    graphed = GraphedTrainStep(step, raw, ref, warmup=3)
+    p = model.output_proj.proj[0].weight
+    before = p.detach().clone()
+    graphed.replay()
+    d1 = (p.detach() - before).abs().max().item()
+    step.opt.param_groups[0]["lr"] = 0.0          # what a scheduler does
+    before = p.detach().clone()
+    graphed.replay()
+    assert d1 > 0 and torch.equal(p.detach(), before)

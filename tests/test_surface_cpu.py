@@ -135,3 +135,40 @@ def test_torch_library_ops_are_registered():
         assert str(op.default._schema).startswith(f"uwr::{name}(")
     with pytest.raises(NotImplementedError):
         torch.ops.uwr.layernorm(torch.zeros(4, 4), torch.ones(4), torch.zeros(4), 1e-5)
+
+
+def test_fflmix_refuses_to_run_without_vgg_weights(monkeypatch, tmp_path):
+    """no silent random-init perceptual network — absent weights raise unless "random" is requested."""
+    from uwr import fflmix
+    monkeypatch.delenv("UWR_VGG16_WEIGHTS", raising=False)
+    monkeypatch.setattr(torch.hub, "get_dir", lambda: str(tmp_path))
+    with pytest.raises(RuntimeError, match="pretrained VGG16"):
+        fflmix.resolve_vgg16_weights(None)
+    assert fflmix.resolve_vgg16_weights("random") == ("random", None)
+    monkeypatch.setenv("UWR_VGG16_WEIGHTS", "random")
+    assert fflmix.resolve_vgg16_weights(None) == ("random", None)
+    # a real checkpoint in the hub cache (or UWR_VGG16_WEIGHTS=path) is picked up and actually loaded
+    import torchvision
+    net = torchvision.models.vgg16(weights=None)
+    with torch.no_grad():
+        net.features[0].weight.fill_(0.125)
+    ck = tmp_path / "checkpoints"
+    ck.mkdir()
+    torch.save(net.state_dict(), ck / fflmix.VGG_FILE)
+    monkeypatch.delenv("UWR_VGG16_WEIGHTS")
+    kind, path = fflmix.resolve_vgg16_weights(None)
+    assert kind == "file" and path.endswith(fflmix.VGG_FILE)
+    vgg = fflmix.VGGPerceptual(path)
+    assert vgg.weights_source == path and float(vgg.blocks[0][0].weight.flatten()[0]) == 0.125
+
+
+def test_direct_gradient_writes_are_scoped_to_trainstep():
+    """overwrite-semantics gradient writes are only enabled inside TrainStep's own backward."""
+    from uwr import ops
+    p = torch.nn.Parameter(torch.zeros(4))
+    p.grad = torch.zeros(4)
+    p._uwr_direct = True
+    assert ops.grad_slot(p) is None or not p.grad.is_cuda      # outside the context: never a direct slot
+    with ops.direct_grad_writes():
+        pass
+    assert ops._DIRECT_WRITES is False

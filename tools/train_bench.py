@@ -14,7 +14,7 @@ S = int(sys.argv[4]) if len(sys.argv) > 4 else 256
 steps = int(sys.argv[5]) if len(sys.argv) > 5 else 5
 torch.manual_seed(1234)
 model = uwr.init_model(arch).cuda().train()
-step = TrainStep(model, loss, lr=1e-3, local_batch=B)
+step = TrainStep(model, loss, lr=1e-3, local_batch=B, vgg_weights="random" if loss == "fflMix" else None)  # P3: synthetic bench
 g = torch.Generator().manual_seed(2024)
 raw = (torch.rand(B, 3, S, S, generator=g) * 2 - 1).cuda()
 ref = (torch.rand(B, 3, S, S, generator=g) * 2 - 1).cuda()

@@ -72,8 +72,10 @@ __global__ void __launch_bounds__(OPT_THREADS) adam_kernel(float* const* __restr
                                                            long long total, const float* __restrict__ clip_coef,
                                                            float prescale, float lr, float beta1, float beta2,
                                                            float eps, float wd, int decoupled, int step,
-                                                           const int* __restrict__ step_dev) {
+                                                           const int* __restrict__ step_dev,
+                                                           const float* __restrict__ lr_dev) {
     const int st = step_dev ? *step_dev : step;
+    if (lr_dev) lr = *lr_dev;   // device-resident learning rate: a captured CUDA graph follows scheduler updates
     const float gscale = prescale * (clip_coef ? *clip_coef : 1.f);
     const float bc1 = 1.f - powf(beta1, (float)st);
     const float bc2 = 1.f - powf(beta2, (float)st);
@@ -131,14 +133,15 @@ extern "C" int uwr_grad_norm(const float* const* grads, const long long* offsets
 extern "C" int uwr_adam_step(float* const* params, const float* const* grads, float* const* exp_avg,
                              float* const* exp_avg_sq, const long long* offsets, int n_tensors, long long total_elems,
                              const float* clip_coef, float grad_prescale, float lr, float beta1, float beta2, float eps,
-                             float weight_decay, int decoupled, int step, const int* step_dev, uwr_stream_t stream_) {
+                             float weight_decay, int decoupled, int step, const int* step_dev, const float* lr_dev,
+                             uwr_stream_t stream_) {
     cudaStream_t stream = (cudaStream_t)stream_;
     UWR_REQUIRE(params && grads && exp_avg && exp_avg_sq && offsets && n_tensors > 0, "uwr_adam_step: bad args");
     UWR_REQUIRE(step_dev || step >= 1, "uwr_adam_step: step must be >= 1");
     adam_kernel<<<opt_blocks(total_elems), OPT_THREADS, 0, stream>>>(params, grads, exp_avg, exp_avg_sq, offsets,
                                                                     n_tensors, total_elems, clip_coef, grad_prescale,
                                                                     lr, beta1, beta2, eps, weight_decay, decoupled,
-                                                                    step, step_dev);
+                                                                    step, step_dev, lr_dev);
     UWR_CHECK_LAUNCH("adam_kernel");
     return 0;
 }

@@ -148,7 +148,7 @@ SIGNATURES = {
                                c_stream]),
     "uwr_grad_norm": (c_int, [c_fp, c_fp, c_int, c_ll, c_f, c_f, c_fp, c_fp, c_stream]),
     "uwr_adam_step": (c_int, [c_fp, c_fp, c_fp, c_fp, c_fp, c_int, c_ll, c_fp, c_f, c_f, c_f, c_f, c_f, c_f,
-                              c_int, c_int, c_fp, c_stream]),
+                              c_int, c_int, c_fp, c_fp, c_stream]),
     "uwr_increment_i32": (c_int, [c_fp, c_stream]),
 }
 

@@ -36,6 +36,9 @@ class InputProjFn(torch.autograd.Function):
     @once_differentiable
     def backward(ctx, dtokens):
         img, weight, tokens = ctx.saved_tensors
+        if ctx.needs_input_grad[0]:
+            raise NotImplementedError("InputProjFn: the gradient w.r.t. the input image is not implemented "
+                                      "(the training path never needs it, SURVEY.md §8a row 2)")
         dweight, dbias = ops.input_proj_bwd(_c(dtokens), tokens, img, weight, ctx.slope)
         # the image itself never needs a gradient on the training path
         return None, dweight, dbias, None
@@ -57,7 +60,8 @@ class OutputProjFn(torch.autograd.Function):
         tokens, weight = ctx.saved_tensors
         H, W = ctx.hw
         dtokens, dweight, dbias = ops.output_proj_bwd(_c(dout), tokens, weight, tokens.shape[0], H, W)
-        return dtokens, dweight, dbias, None, None, None
+        # out = conv(tokens) + residual_img: the residual's gradient is the cotangent itself
+        return dtokens, dweight, dbias, (dout if ctx.needs_input_grad[3] else None), None, None
 
 
 class DownsampleFn(torch.autograd.Function):

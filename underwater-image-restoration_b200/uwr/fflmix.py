@@ -5,10 +5,20 @@
 returned as the 6-tuple (loss, charb, perc, grad, ffl, ssim) that ModelTrainer.py:82-85 unpacks.
 Charbonnier and the focal frequency term run on the uwr kernels; the VGG16 perceptual term, the
 Laplacian gradient term and MS-SSIM stay on PyTorch/cuDNN ops in this round (SURVEY.md §8a row 35,
-§8f rank 3).  Patch P3: torchvision's ImageNet VGG16 weights cannot be downloaded
-offline, so the perceptual network is a seeded random-init VGG16 (`VGG_SEED`); with real weights
-present, load them into `.vgg` before training.
+§8f rank 3).
+
+VGG16 weights.  The reference builds `torchvision.models.vgg16(pretrained=True)` (losses.py:219-222), i.e. the
+ImageNet checkpoint `vgg16-397923af.pth`.  This module looks for it (a) where `UWR_VGG16_WEIGHTS` points,
+(b) in torch's hub cache (`torch.hub.get_dir()/checkpoints/`), where torchvision itself would have put it.  It never
+downloads.  If the file is absent the loss REFUSES to run — a silently random perceptual network would be a
+different objective — unless the caller asks for the seeded random-init stand-in explicitly
+(`LossFunction("fflMix", dev, vgg_weights="random")` or `UWR_VGG16_WEIGHTS=random`): that is documented patch P3
+(SURVEY.md §8c), used by the parity tests and the synthetic benchmarks, and it warns once.
+`load_vgg_weights(path_or_state_dict, device)` installs weights explicitly.
 """
+import os
+import warnings
+
 import torch
 import torch.nn as nn
 import torch.nn.functional as F
@@ -16,17 +26,46 @@ import torch.nn.functional as F
 VGG_SEED = 777
 
 
+VGG_FILE = "vgg16-397923af.pth"      # torchvision VGG16_Weights.IMAGENET1K_V1
+
+
+def resolve_vgg16_weights(spec=None):
+    """-> ("file", path) | ("random", None) | raises.  `spec`: None (search), a path, or "random"."""
+    spec = spec if spec is not None else os.environ.get("UWR_VGG16_WEIGHTS")
+    if spec is not None:
+        if str(spec).startswith("random"):
+            return "random", None
+        if not os.path.exists(spec):
+            raise FileNotFoundError(f"VGG16 weights not found at {spec!r}")
+        return "file", str(spec)
+    cached = os.path.join(torch.hub.get_dir(), "checkpoints", VGG_FILE)
+    if os.path.exists(cached):
+        return "file", cached
+    raise RuntimeError(
+        f"fflMix needs the pretrained VGG16 weights the reference uses (torchvision {VGG_FILE}); none found in "
+        f"{os.path.dirname(cached)} and UWR_VGG16_WEIGHTS is unset.  Put the file there, point UWR_VGG16_WEIGHTS at it, "
+        "or pass vgg_weights='random' to LossFunction to opt in to the seeded random-init stand-in (a DIFFERENT "
+        "objective; parity tests and synthetic benchmarks only).")
+
+
 class VGGPerceptual(nn.Module):
     """VGGPerceptualLoss (losses.py:215-255): features[:4], [4:9], [9:16], [16:23] of VGG16, inputs
     normalised with the ImageNet mean/std and resized to 224x224, L1 between the four feature taps."""
 
-    def __init__(self):
+    def __init__(self, weights="random"):
+        """weights: "random" (seeded `VGG_SEED`, patch P3), a checkpoint path, or a vgg16 state_dict."""
         super().__init__()
         import torchvision
         state = torch.random.get_rng_state()
         torch.manual_seed(VGG_SEED)
-        feats = torchvision.models.vgg16(weights=None).features
+        net = torchvision.models.vgg16(weights=None)
         torch.random.set_rng_state(state)
+        self.weights_source = "random"
+        if not (isinstance(weights, str) and weights.startswith("random")):
+            sd = torch.load(weights, map_location="cpu", weights_only=True) if isinstance(weights, (str, os.PathLike)) else weights
+            net.load_state_dict(sd)
+            self.weights_source = str(weights) if isinstance(weights, (str, os.PathLike)) else "state_dict"
+        feats = net.features
         self.blocks = nn.ModuleList([feats[:4].eval(), feats[4:9].eval(), feats[9:16].eval(), feats[16:23].eval()])
         for p in self.parameters():
             p.requires_grad = False
@@ -81,16 +120,34 @@ def ms_ssim(X, Y, data_range=1.0, win_size=11, sigma=1.5):
 
 
 _VGG = {}
+_WARNED = False
+
+
+def load_vgg_weights(weights, device):
+    """Install the perceptual network for `device` from a checkpoint path / vgg16 state_dict (or "random")."""
+    _VGG[torch.device(device)] = VGGPerceptual(weights).to(device)
+    return _VGG[torch.device(device)]
+
+
+def _vgg_for(lossfn, dev):
+    global _WARNED
+    dev = torch.device(dev)
+    if dev not in _VGG:
+        kind, path = resolve_vgg16_weights(getattr(lossfn, "vgg_weights", None))
+        if kind == "random" and not _WARNED:
+            warnings.warn("fflMix: using a seeded RANDOM-INIT VGG16 for the perceptual term (explicit opt-in, patch P3); "
+                          "this is not the reference's pretrained objective", RuntimeWarning, stacklevel=3)
+            _WARNED = True
+        load_vgg_weights("random" if kind == "random" else path, dev)
+    return _VGG[dev]
 
 
 def fflmix_loss(lossfn, pred, truth):
     from .ffl import FocalFrequencyFn
     from .losses import PixelLossFn
-    dev = pred.device
-    if dev not in _VGG:
-        _VGG[dev] = VGGPerceptual().to(dev)
+    vgg = _vgg_for(lossfn, pred.device)
     charb = PixelLossFn.apply(pred, truth, "charbonnier", None)
-    perc = _VGG[dev](pred, truth)
+    perc = vgg(pred, truth)
     grad = gradient_loss(pred, truth)
     ffl = FocalFrequencyFn.apply(pred, truth)
     ssim = 1 - ms_ssim(pred, truth)

@@ -29,7 +29,7 @@ class GraphedTrainStep:
     """One whole training step (zero -> forward -> loss -> backward -> clip + Adam) captured in a CUDA
     graph and replayed: ~700 (AST) to ~3000 (SpectralTransformer) kernel launches become one.  Everything
     the step touches is graph-safe by construction: gradient buckets and optimizer pointer tables are
-    static, the Adam step counter and the clip coefficient live on the device, DropPath masks come from
+    static, the Adam step counter, the learning rate and the clip coefficient live on the device, DropPath masks come from
     torch's graph-aware CUDA generator, TF32-rounded weight copies are refreshed by kernels inside the
     graph.  The `warmup` eager steps are real optimizer steps.
 
@@ -62,6 +62,7 @@ class GraphedTrainStep:
                 self.norm = step.opt.step()
 
     def replay(self):
+        self.step.opt.sync_hyper()     # learning-rate changes (schedulers) reach the captured Adam kernel
         self.graph.replay()
         if self.graph_opt is not None:
             b = self.step.buckets

@@ -32,10 +32,13 @@ _PIXEL_KINDS = ("L1", "L2", "L1withColor", "charbonnier")
 
 
 class LossFunction:
-    def __init__(self, loss_name, device=None, batch_divisor=None):
+    def __init__(self, loss_name, device=None, batch_divisor=None, vgg_weights=None):
+        """vgg_weights ("fflMix" only): None = find torchvision's pretrained VGG16 checkpoint (UWR_VGG16_WEIGHTS or
+        the torch hub cache; raises if absent), a path, or "random" for the seeded stand-in (uwr/fflmix.py)."""
         self.loss_name = loss_name
         self.device = device
         self.batch_divisor = batch_divisor
+        self.vgg_weights = vgg_weights
 
     def getloss(self, predicted_data, truth_data):
         name = self.loss_name

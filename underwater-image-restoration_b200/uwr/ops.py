@@ -228,12 +228,30 @@ def scale_round_colsum(src2d, cols, rowscale=None, rows_per_group=0, cs_out=None
     return out, cs
 
 
+_DIRECT_WRITES = False
+
+
+class direct_grad_writes:
+    """Context in which backward kernels may OVERWRITE the bucket slot of a parameter instead of returning its
+    gradient to autograd.  Only uwr.train.TrainStep enters it, around the single backward that follows its bucket
+    zeroing; any other backward (micro-batch accumulation, two forwards before one backward, a plain torch.optim
+    loop) gets ordinary accumulate semantics even if the parameters' .grad are bucket views."""
+
+    def __enter__(self):
+        global _DIRECT_WRITES
+        self._prev, _DIRECT_WRITES = _DIRECT_WRITES, True
+
+    def __exit__(self, *exc):
+        global _DIRECT_WRITES
+        _DIRECT_WRITES = self._prev
+
+
 def grad_slot(p):
     """The preallocated gradient buffer of a parameter whose gradients are owned by uwr.train.GradBuckets
-    (flag `_uwr_direct`): kernels write the gradient straight into it and the autograd Function returns None,
-    which saves autograd's `.grad += g` kernel per parameter (~250 tiny launches per AST step).  Overwrite
-    semantics: only valid because TrainStep zeroes the buckets and every parameter gets one gradient per step."""
-    if getattr(p, "_uwr_direct", False):
+    (flag `_uwr_direct`), inside `direct_grad_writes()`: kernels write the gradient straight into it and the autograd
+    Function returns None, which saves autograd's `.grad += g` kernel per parameter (~250 tiny launches per AST step).
+    Overwrite semantics: only valid because TrainStep zeroes the buckets and every parameter gets one gradient per step."""
+    if _DIRECT_WRITES and getattr(p, "_uwr_direct", False):
         g = p.grad
         if g is not None and g.is_cuda and g.is_contiguous() and g.dtype == torch.float32:
             return g

@@ -14,6 +14,7 @@ gradients (losses.py:57 divides by the local B).
 import torch
 import torch.distributed as dist
 
+from . import ops
 from .losses import LossFunction
 from .optim import FusedClipAdam
 
@@ -93,14 +94,28 @@ class GradBuckets:
 
 class TrainStep:
     def __init__(self, model, loss_name="L1", lr=1e-3, optim="adam", world_size=1, group=None,
-                 local_batch=None, bucket_bytes=32 << 20):
+                 local_batch=None, bucket_bytes=32 << 20, vgg_weights=None):
         self.model = model
         self.world = world_size
-        self.lossf = LossFunction(loss_name, "cuda", batch_divisor=(local_batch * world_size) if local_batch else None)
+        self.lossf = LossFunction(loss_name, "cuda", batch_divisor=(local_batch * world_size) if local_batch else None,
+                                  vgg_weights=vgg_weights)
         adjacent = model.adjacent_grad_pairs() if hasattr(model, "adjacent_grad_pairs") else ()
         self.buckets = GradBuckets(model.parameters(), bucket_bytes, group, world_size, adjacent=adjacent)
         self.opt = FusedClipAdam(model.parameters(), lr=lr, weight_decay=0.01 if optim == "adamw" else 0.0,
                                  decoupled=(optim == "adamw"), max_norm=1.0, grad_prescale=1.0 / world_size)
+
+        self._dead_checked = False
+
+    def _exclude_dead_parameters(self):
+        """Parameters no gradient ever reaches (SpectralTransformer has 230 233 of them, NewBigFRFN 4.2 M: SURVEY.md
+        §3.3/3.4) have `grad is None` under torch and are skipped by torch.optim (no moments, no AdamW decay); here their
+        bucket slots simply stay zero.  Detected once, after the first backward (one host sync), and removed from the
+        optimizer's tables so that the update rule matches."""
+        dead = [p for p in self.buckets.params if not bool(p.grad.any())]
+        if dead:
+            self.opt.exclude(dead)
+        self._dead_checked = True
+        self.dead_parameters = dead
 
     def forward_backward(self, raw, ref):
         self.buckets.zero()
@@ -108,11 +123,16 @@ class TrainStep:
         loss = self.lossf.getloss(out, ref)
         if isinstance(loss, tuple):
             loss = loss[0]
-        loss.backward()
+        # kernels may write parameter gradients straight into the (just zeroed) bucket slots only inside THIS backward:
+        # one gradient per parameter per step, overwrite semantics (uwr.ops.grad_slot)
+        with ops.direct_grad_writes():
+            loss.backward()
         return loss.detach()
 
     def __call__(self, raw, ref):
         loss = self.forward_backward(raw, ref)
         self.buckets.finish()
+        if not self._dead_checked and not torch.cuda.is_current_stream_capturing():
+            self._exclude_dead_parameters()
         norm = self.opt.step()
         return loss, norm
