@@ -112,6 +112,11 @@ def test_ast_train_droppath_128():
     _run(2, 128, 128, True, [])
 
 
+def test_ast_train_droppath_256():
+    """train mode (DropPath masks replayed) at the headline resolution of BASELINE configs 1 / 4"""
+    _run(2, 256, 256, True, [])
+
+
 def test_ast_tf32x3_128():
     """error-compensated GEMMs: the only remaining difference to the fp32 reference is summation order"""
     _run(2, 128, 128, True, [], precision="tf32x3", tol=5e-5)
