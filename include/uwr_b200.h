@@ -71,6 +71,12 @@ typedef struct {
     float* workspace;
     size_t workspace_bytes;
     int round_out; /* store C rounded to TF32 (it feeds another tensor-core GEMM) */
+    /* fp16 storage of the 4C-wide LeFF tensors (tcgen05 path only; DESIGN.md §3 "half storage"): a 10-bit mantissa
+     * is exactly what a TF32 operand keeps, so for O(1)-range activations fp16 halves the HBM bytes at TF32 accuracy.
+     * c_half: C is __half[M][ldc] (ldc in halves, values clamped to +-65504);
+     * r_half: R (UWR_EPI_MUL multiplier / UWR_EPI_RESID residual) is __half[M][ldr]. */
+    int c_half;
+    int r_half;
 } uwr_gemm_desc;
 
 size_t uwr_gemm_workspace_bytes(int M, int N, int K, int a_km);
@@ -179,6 +185,15 @@ int uwr_gelu_gate_bwd(const float* dh2, const float* u, long long ld_u, const fl
                       float* du, long long rows, int Ch, int mode, uwr_stream_t stream);
 /* GDFN gate (SpectralTransformer.py:126-129): out = gelu(t[:, :h]) * t[:, h:2h]; t has row stride ld >= 2h,
  * dt the same layout; h % 4 == 0. */
+/* fp16 storage of the two 4C-wide LeFF tensors that are not tensor-core operands: u (linear1 output,
+ * written by uwr_gemm_tcgen05 with c_half = 1) and gelu'(v) (read back by the linear2 data-gradient epilogue with
+ * r_half = 1).  H, W multiples of 16, Ch of 32, single-pass (tf32) mode.  h2 and du stay fp32 (GEMM operands). */
+int uwr_dwconv_half_supported(int H, int W, int Ch);
+int uwr_dwconv_gelu_fwd_half(const void* u_half, const float* weight, const float* bias, void* dgelu_half,
+                             float* h2, int B, int H, int W, int Ch, uwr_stream_t stream);
+int uwr_dwconv_gelu_bwd_half(const float* dv, const void* u_half, const float* weight, float* du, float* dweight,
+                             float* dbias, float* du_colsum, float* workspace, int B, int H, int W, int Ch,
+                             uwr_stream_t stream);
 int uwr_gelu_mul_fwd(const float* t, long long ld, float* out /*(rows,h)*/, long long rows, int h,
                      uwr_stream_t stream);
 int uwr_gelu_mul_bwd(const float* dout /*(rows,h)*/, const float* t, long long ld, float* dt,

@@ -101,7 +101,7 @@ def _run_inner(B, S, img_size, train, report, tol, token_mlp="leff"):
     assert e_grad < tol
     # per-tensor: gradients that are sums of strongly cancelling terms carry a larger share of the
     # TF32 rounding; bound them looser (they vanish in tf32x3 mode, see test_ast_tf32x3_128)
-    assert worst[0] < 10 * tol, worst
+    assert worst[0] < 7 * tol, worst      # measured <= 5.2e-3 (conv.blocks.*.attn.qkv.to_q.weight, a near-cancelling sum)
 
 
 def test_ast_eval_128():
@@ -279,4 +279,4 @@ def test_train_step_matches_oracle_adam_two_steps():
         den += (upd_o ** 2).sum().item()
     rel = (num / den) ** 0.5
     print(f"train-step parity: losses {losses}, norms {norms}, update rel-L2 {rel:.2e}")
-    assert rel < 5e-2
+    assert rel < 3e-2      # measured 1.7e-2

@@ -737,7 +737,7 @@ def test_fused_clip_adam_is_a_torch_optimizer_with_checkpoint_and_scheduler():
         rsched.step()
     for it in range(3):
         both(it)
-    assert opt.param_groups[0]["lr"] == ref.param_groups[0]["lr"] == 1e-3 * 0.25
+    assert opt.param_groups[0]["lr"] == ref.param_groups[0]["lr"] and abs(opt.lr - 1e-3 * 0.25 ** 2) < 1e-12
     for p, q in zip(ps, qs):
         assert rel_l2(p, q) < 1e-6
     # checkpoint in torch layout: loads into a fresh torch.optim.Adam and back into a fresh FusedClipAdam
@@ -749,7 +749,7 @@ def test_fused_clip_adam_is_a_torch_optimizer_with_checkpoint_and_scheduler():
     opt2, ref2 = FusedClipAdam(ps2, lr=123.0, max_norm=1.0), torch.optim.Adam(qs2, lr=123.0)
     opt2.load_state_dict(sd)
     ref2.load_state_dict(sd)
-    assert opt2.lr == ref2.param_groups[0]["lr"] == 1e-3 * 0.25 and opt2.step_count == 3
+    assert opt2.lr == ref2.param_groups[0]["lr"] == opt.lr and opt2.step_count == 3
     for p, q, g in zip(ps2, qs2, grads[3]):
         p.grad, q.grad = g.clone(), g.clone()
     opt2.step()
@@ -787,3 +787,68 @@ def test_graphed_step_follows_lr_changes():
     before = p.detach().clone()
     graphed.replay()
     assert d1 > 0 and torch.equal(p.detach(), before)
+
+
+# ------------------------------------------------------------------- fp16 storage of the LeFF hidden tensors
+@pytest.mark.parametrize("B,H,C", [(2, 16, 64), (1, 32, 32), (2, 16, 256)])
+def test_leff_block_half_storage_vs_oracle(ops, B, H, C):
+    """LeFF block (LeFFBlockFn) with u / gelu'(v) stored as float16 (the default in single-pass mode) vs the fp64 oracle,
+    next to the same block with fp32 storage: both must sit at TF32 level, and the half path must really be taken."""
+    from oracle import ast_oracle as ao
+    from uwr.ast import TransformerBlock
+    torch.manual_seed(11)
+    blk = TransformerBlock(C, (H, H), max(1, C // 32), win_size=8, shift_size=0, drop_path=0.0, att=False, sparseAtt=False)
+    for p in blk.parameters():
+        torch.nn.init.normal_(p, std=0.08) if p.ndim > 1 else torch.nn.init.normal_(p, mean=0.3, std=0.2)
+    blk = blk.cuda().train()
+    sd = {k: v.detach().double().clone().requires_grad_() if v.is_floating_point() else v.detach().clone()
+          for k, v in blk.state_dict().items()}
+    x = _r(B, H * H, C, seed=12)
+    g = _r(B, H * H, C, seed=13)
+    xd = x.double().requires_grad_()
+    yo = ao.transformer_block(sd, "", xd, max(1, C // 32), 0, False, "leff", None, None)
+    yo.backward(g.double())
+    res = {}
+    for half in (True, False):
+        ops.set_half_storage(half)
+        try:
+            blk.zero_grad(set_to_none=True)
+            xx = x.clone().requires_grad_()
+            n0 = {}
+            with ops.KernelProfile() as prof:
+                y = blk(xx)
+                y.backward(g)
+            names = {r["kernel"] for r in prof.table()}
+            assert ("uwr_dwconv_gelu_fwd_half" in names) == half and ("uwr_dwconv_gelu_bwd_half" in names) == half
+            errs = {"out": rel_l2(y, yo), "dx": rel_l2(xx.grad, xd.grad)}
+            for n, p in blk.named_parameters():
+                errs[n] = rel_l2(p.grad, sd[n].grad)
+            res[half] = errs
+        finally:
+            ops.set_half_storage(True)
+    print("half", {k: f"{v:.1e}" for k, v in res[True].items()})
+    print("fp32", {k: f"{v:.1e}" for k, v in res[False].items()})
+    for half in (True, False):
+        assert res[half]["out"] < 3e-4 and max(res[half].values()) < 1e-3, (half, res[half])
+    # half storage costs at most a TF32-sized extra rounding of u
+    assert max(res[True].values()) < 2 * max(res[False].values()) + 2e-4
+
+
+def test_gemm_half_output_and_multiplier(ops):
+    """tcgen05 GEMM with c_half (float16 C) and r_half (float16 UWR_EPI_MUL operand)."""
+    M, N, K = 4096, 256, 64
+    x = ops.scale_round(_r(M, K, seed=71), K)
+    w = ops.scale_round(_r(N, K, seed=72, scale=0.1), K)
+    b = _r(N, seed=73)
+    y = ops.linear(x, w, b, t5=True, out_half=True)
+    assert y.dtype == torch.float16
+    ref = x.double() @ w.double().t() + b.double()
+    assert rel_l2(y, ref) < 6e-4          # 2^-11 output rounding on top of exact TF32 products
+    big = ops.linear(x * 1e4, w * 1e3, None, t5=True, out_half=True)     # |y| > 65504 saturates instead of inf
+    assert torch.isfinite(big.float()).all() and big.float().abs().max().item() == 65504.0
+    d = ops.scale_round(_r(M, K, seed=74), K)
+    w2 = ops.scale_round(_r(K, N, seed=75, scale=0.1), N)                # stored [N_in=K][K_out=N]: dx = d w2
+    mul = torch.rand(M, N, device="cuda").half()
+    out = ops.linear_dgrad(d, w2, mul_by=mul, t5=True)
+    ref2 = (d.double() @ w2.double()) * mul.double()
+    assert out.dtype == torch.float32 and rel_l2(out, ref2) < 1e-5

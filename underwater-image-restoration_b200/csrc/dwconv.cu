@@ -11,6 +11,8 @@
 //   dh1[p] = sum_k dv[p+1-k] w[k] ; du = dh1 * gelu'(u) ; dw[k] = sum_p gelu(u[p]) dv[p+1-k]
 // HBM-bound: fwd reads u (x1.27 halo, mostly L2 hits) and writes v,h2; bwd reads dv (x1.27), u and
 // writes du.
+#include <cuda_fp16.h>
+
 #include "uwr_common.cuh"
 #include "uwr_tma.cuh"
 #include "../../include/uwr_b200.h"
@@ -34,11 +36,11 @@ __device__ __forceinline__ void fma4(float4& a, const float4& x, const float4& w
 constexpr int TILE_BYTES = HS * HS * CG * (int)sizeof(float);
 static_assert(TILE_BYTES % 128 == 0, "tile buffers must stay 128-byte aligned");
 
-__device__ __forceinline__ void dw_tma_tile(float* dst, const CUtensorMap* map, uint64_t* bar, int tile,
-                                            int tiles_per_img, int tiles_x, int cbase) {
+__device__ __forceinline__ void dw_tma_tile(void* dst, const CUtensorMap* map, uint64_t* bar, int tile,
+                                            int tiles_per_img, int tiles_x, int cbase, int bytes = TILE_BYTES) {
     const int b = tile / tiles_per_img, tl = tile - b * tiles_per_img;
     const int ty = tl / tiles_x, tx = tl - ty * tiles_x;
-    uwr_tma::mbar_expect_tx(bar, TILE_BYTES);
+    uwr_tma::mbar_expect_tx(bar, bytes);
     uwr_tma::tma_load_4d(dst, map, bar, cbase, tx * TS - 1, ty * TS - 1, b);
 }
 
@@ -160,6 +162,114 @@ dwconv_fwd_kernel(const __grid_constant__ CUtensorMap map_u, const float* __rest
     }
 }
 
+// LeFF training hot path with fp16 storage of the 4C-wide tensors (DESIGN.md §3 "half storage"): u arrives as
+// __half (written by the linear1 GEMM epilogue), gelu'(v) leaves as __half (read back by the linear2 data-gradient
+// epilogue); h2 stays fp32 (TF32-rounded A operand of linear2).  Same tiling as dwconv_fwd_kernel<0, true>:
+// the halo tile of halves lands by ONE TMA instruction (20 736 B, half the bytes) and is expanded to fp32 in
+// shared memory by the GELU pass that the fp32 kernel runs in place.  Full tiles only (H, W % 16 == 0, Ch % 32 == 0).
+constexpr int TILE_BYTES_H = HS * HS * CG * 2;
+static_assert(TILE_BYTES_H % 128 == 0, "half tile buffers must stay 128-byte aligned");
+
+__global__ void __launch_bounds__(DW_THREADS, 2)
+dwconv_fwd_half_kernel(const __grid_constant__ CUtensorMap map_u, const float* __restrict__ weight,
+                       const float* __restrict__ bias, __half* __restrict__ v, float* __restrict__ h2, int B, int H, int W,
+                       int Ch, int tiles_x, int tiles_per_img) {
+    extern __shared__ __align__(128) unsigned char dw_raw[];
+    unsigned char* base = dw_raw + ((128u - (uwr_tma::smem_u32(dw_raw) & 127u)) & 127u);
+    float* work = reinterpret_cast<float*>(base);                                  // gelu(u) tile, fp32
+    unsigned char* hbuf = base + TILE_BYTES;                                       // two __half halo tiles
+    uint64_t* bars = reinterpret_cast<uint64_t*>(hbuf + 2 * TILE_BYTES_H);
+    const int tid = threadIdx.x;
+    const int c4 = (tid & 7) * 4;
+    const int cbase = blockIdx.y * CG;
+    const int c = cbase + c4;
+    const int total = B * tiles_per_img;
+    int tile = blockIdx.x;
+
+    if (tid == 0) {
+        uwr_tma::mbar_init(&bars[0], 1);
+        uwr_tma::mbar_init(&bars[1], 1);
+        uwr_tma::mbar_init_fence();
+        uwr_tma::tma_prefetch_map(&map_u);
+    }
+    __syncthreads();
+    if (tid == 0 && tile < total) dw_tma_tile(hbuf, &map_u, &bars[0], tile, tiles_per_img, tiles_x, cbase, TILE_BYTES_H);
+
+    float4 wgt[9];
+#pragma unroll
+    for (int k = 0; k < 9; ++k)
+        wgt[k] = make_float4(weight[c * 9 + k], weight[(c + 1) * 9 + k], weight[(c + 2) * 9 + k], weight[(c + 3) * 9 + k]);
+    const float4 bv = ld4(bias + c);
+    const int ly = tid >> 4;
+    const int lx0 = ((tid >> 3) & 1) * 8;
+
+    for (int it = 0; tile < total; tile += gridDim.x, ++it) {
+        const uint2* cur = reinterpret_cast<const uint2*>(hbuf + (it & 1) * TILE_BYTES_H);
+        const int ntile = tile + gridDim.x;
+        // the other half buffer was drained by the GELU pass of the previous iteration (and a __syncthreads since)
+        if (tid == 0 && ntile < total)
+            dw_tma_tile(hbuf + ((it + 1) & 1) * TILE_BYTES_H, &map_u, &bars[(it + 1) & 1], ntile, tiles_per_img, tiles_x,
+                        cbase, TILE_BYTES_H);
+        uwr_tma::mbar_wait(&bars[it & 1], (it >> 1) & 1);
+        {   // fp16 -> fp32 + GELU, once per staged element (gelu(0) = 0 keeps the zero padding)
+            float4* w4 = reinterpret_cast<float4*>(work) + tid;
+            const uint2* s2 = cur + tid;
+#pragma unroll
+            for (int i = 0; i < 10; ++i) {  // 18*18*8 = 2592 groups of 4 channels = 10 * 256 + 32
+                const uint2 raw = s2[i * DW_THREADS];
+                const float2 a = __half22float2(*reinterpret_cast<const __half2*>(&raw.x));
+                const float2 b2 = __half22float2(*reinterpret_cast<const __half2*>(&raw.y));
+                w4[i * DW_THREADS] = make_float4(gelu_f(a.x), gelu_f(a.y), gelu_f(b2.x), gelu_f(b2.y));
+            }
+            if (tid < 32) {
+                const uint2 raw = s2[10 * DW_THREADS];
+                const float2 a = __half22float2(*reinterpret_cast<const __half2*>(&raw.x));
+                const float2 b2 = __half22float2(*reinterpret_cast<const __half2*>(&raw.y));
+                w4[10 * DW_THREADS] = make_float4(gelu_f(a.x), gelu_f(a.y), gelu_f(b2.x), gelu_f(b2.y));
+            }
+            __syncthreads();
+        }
+        const int b = tile / tiles_per_img, tl = tile - b * tiles_per_img;
+        const int ty0 = (tl / tiles_x) * TS, tx0 = (tl % tiles_x) * TS;
+        const long long tok0 = ((long long)b * H + ty0 + ly) * W + tx0 + lx0;
+        float* h2p = h2 + tok0 * Ch + c;
+        __half* vp = v + tok0 * Ch + c;
+        const float* sp = work + (ly * HS + lx0) * CG + c4;
+        float4 col[3][3];
+#pragma unroll
+        for (int ky = 0; ky < 3; ++ky) {
+            col[ky][0] = ld4(sp + (ky * HS + 0) * CG);
+            col[ky][1] = ld4(sp + (ky * HS + 1) * CG);
+        }
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+#pragma unroll
+            for (int ky = 0; ky < 3; ++ky) col[ky][(i + 2) % 3] = ld4(sp + (ky * HS + i + 2) * CG);
+            float4 acc = bv;
+#pragma unroll
+            for (int ky = 0; ky < 3; ++ky)
+#pragma unroll
+                for (int kx = 0; kx < 3; ++kx) fma4(acc, col[ky][(i + kx) % 3], wgt[ky * 3 + kx]);
+            const float a[4] = {acc.x, acc.y, acc.z, acc.w};
+            float o[4], sv[4];
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+                float cdf, pdf;
+                gelu_parts(a[e], cdf, pdf);
+                sv[e] = fmaf(a[e], pdf, cdf);          // gelu'(v) in [-0.13, 1.13]: fp16 keeps it to 2^-11
+                o[e] = tf32_round(a[e] * cdf);
+            }
+            const __half2 s01 = __floats2half2_rn(sv[0], sv[1]), s23 = __floats2half2_rn(sv[2], sv[3]);
+            uint2 raw;
+            raw.x = *reinterpret_cast<const uint32_t*>(&s01);
+            raw.y = *reinterpret_cast<const uint32_t*>(&s23);
+            *reinterpret_cast<uint2*>(vp + (long long)i * Ch) = raw;
+            *reinterpret_cast<float4*>(h2p + (long long)i * Ch) = make_float4(o[0], o[1], o[2], o[3]);
+        }
+        __syncthreads();  // everyone is done with `work` before the next iteration's GELU pass rewrites it
+    }
+}
+
 // dv = dh2 * gelu'(v) [* gelu(u2)] ; FRFN additionally du[:, Ch:] = dh2 * gelu(v) * gelu'(u2)
 __global__ void __launch_bounds__(256) gelu_gate_bwd_kernel(const float* __restrict__ dh2,
                                                             const float* __restrict__ u, long long ld_u,
@@ -246,7 +356,15 @@ __device__ __forceinline__ void fma2(float2& a, const float2& x, const float2& w
     a.x = fmaf(x.x, w.x, a.x); a.y = fmaf(x.y, w.y, a.y);
 }
 
-template <bool PLAIN, bool FAST>
+// UHALF: u is __half (fp16 storage of the linear1 output, see dwconv_fwd_half_kernel); ld_u counts elements of u and
+// is also the row stride of the fp32 du.
+template <bool UHALF>
+__device__ __forceinline__ float2 ld_u2(const float* p) {
+    if (UHALF) return __half22float2(*reinterpret_cast<const __half2*>(reinterpret_cast<const __half*>(p)));
+    return *reinterpret_cast<const float2*>(p);
+}
+
+template <bool PLAIN, bool FAST, bool UHALF = false>
 __global__ void __launch_bounds__(DW_THREADS, 2)
 dwconv_bwd_kernel(const __grid_constant__ CUtensorMap map_dv, const float* __restrict__ u, long long ld_u,
                   const float* __restrict__ weight, float* __restrict__ du, float* __restrict__ partials, int B, int H,
@@ -293,13 +411,16 @@ dwconv_bwd_kernel(const __grid_constant__ CUtensorMap map_dv, const float* __res
         const int y = ty0 + ly;
         const bool rok = FAST || (cok && y < H);
         const long long tok0 = ((long long)b * H + y) * W + tx0;
-        const float* up = u + tok0 * ld_u + c;
-        float* dup = du + tok0 * ld_u + c;
+        // element offsets; with UHALF the byte address is half of what the float pointer arithmetic would give
+        const long long uoff = tok0 * ld_u + c;
+        const float* up = UHALF ? reinterpret_cast<const float*>(reinterpret_cast<const __half*>(u) + uoff) : u + uoff;
+        const long long ustep = UHALF ? ld_u / 2 : ld_u;   // pointer steps in floats per pixel (ld_u is even)
+        float* dup = du + uoff;
         // the first strip's u values are requested before waiting for the halo tile
         float2 uc[8];
 #pragma unroll
         for (int i = 0; i < 8; ++i)
-            uc[i] = (rok && (FAST || tx0 + i < W)) ? ld2(up + (long long)i * ld_u) : make_float2(0.f, 0.f);
+            uc[i] = (rok && (FAST || tx0 + i < W)) ? ld_u2<UHALF>(up + (long long)i * ustep) : make_float2(0.f, 0.f);
         uwr_tma::mbar_wait(&bars[it & 1], (it >> 1) & 1);
         if (rok) {
             const float* sp = dvs + (ly * HS) * CG + c2;
@@ -309,7 +430,7 @@ dwconv_bwd_kernel(const __grid_constant__ CUtensorMap map_dv, const float* __res
                 if (hx == 1) {
 #pragma unroll
                     for (int i = 0; i < 8; ++i)
-                        uc[i] = (FAST || tx0 + 8 + i < W) ? ld2(up + (long long)(8 + i) * ld_u) : make_float2(0.f, 0.f);
+                        uc[i] = (FAST || tx0 + 8 + i < W) ? ld_u2<UHALF>(up + (long long)(8 + i) * ustep) : make_float2(0.f, 0.f);
                 }
                 // col[a][j % 3] = dv at tile pixel (ly - 1 + a, lx0 - 1 + j): rotating registers, no moves
                 float2 col[3][3];
@@ -450,6 +571,40 @@ extern "C" int uwr_dwconv_gelu_fwd(const float* u, long long ld_u, const float* 
     return 0;
 }
 
+// fp16-storage variant of the LeFF forward (mode 0, training): u is __half (B*H*W, Ch) dense, gelu'(v) is written as
+// __half, h2 as TF32-rounded fp32.  Served when H, W are multiples of 16 and Ch of 32 (uwr_dwconv_half_supported).
+extern "C" int uwr_dwconv_half_supported(int H, int W, int Ch) {
+    return H > 0 && W > 0 && Ch > 0 && H % TS == 0 && W % TS == 0 && Ch % CG == 0;
+}
+
+extern "C" int uwr_dwconv_gelu_fwd_half(const void* u_half, const float* weight, const float* bias, void* dgelu_half,
+                                        float* h2, int B, int H, int W, int Ch, uwr_stream_t stream_) {
+    cudaStream_t stream = (cudaStream_t)stream_;
+    UWR_REQUIRE(u_half && weight && bias && dgelu_half && h2, "uwr_dwconv_gelu_fwd_half: null pointer");
+    UWR_REQUIRE(uwr_dwconv_half_supported(H, W, Ch), "uwr_dwconv_gelu_fwd_half: needs H, W %% 16 == 0 and Ch %% 32 == 0");
+    UWR_REQUIRE(B > 0 && B <= 65535, "uwr_dwconv_gelu_fwd_half: bad batch %d", B);
+    UWR_REQUIRE(uwr_round_outputs(), "uwr_dwconv_gelu_fwd_half: single-pass (tf32) mode only");
+    const int tx = W / TS, ty = H / TS;
+    CUtensorMap map_u;
+    {
+        const long long dims[4] = {Ch, W, H, B};
+        const long long strides[3] = {Ch, (long long)W * Ch, (long long)H * W * Ch};
+        const int box[4] = {CG, HS, HS, 1};
+        if (uwr_tma::encode_f16(&map_u, u_half, 4, dims, strides, box, CU_TENSOR_MAP_SWIZZLE_NONE) != 0) return -3;
+    }
+    constexpr int SMEM = TILE_BYTES + 2 * TILE_BYTES_H + 128 + 16;
+    static bool configured = false;
+    if (!configured) {
+        UWR_CUDA(cudaFuncSetAttribute(dwconv_fwd_half_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM));
+        configured = true;
+    }
+    dim3 grid(bwd_ctas(B, H, W, Ch), Ch / CG);
+    dwconv_fwd_half_kernel<<<grid, DW_THREADS, SMEM, stream>>>(map_u, weight, bias, (__half*)dgelu_half, h2, B, H, W, Ch, tx,
+                                                              tx * ty);
+    UWR_CHECK_LAUNCH("dwconv_fwd_half_kernel");
+    return 0;
+}
+
 extern "C" int uwr_gelu_gate_bwd(const float* dh2, const float* u, long long ld_u, const float* v, float* dv,
                                  float* du, long long rows, int Ch, int mode, uwr_stream_t stream_) {
     cudaStream_t stream = (cudaStream_t)stream_;
@@ -490,10 +645,30 @@ extern "C" size_t uwr_dwconv_gelu_bwd_workspace_bytes(int B, int H, int W, int C
     return (size_t)bwd_ctas(B, H, W, Ch) * 11 * (size_t)Ch * sizeof(float);
 }
 
+static int dwconv_bwd_impl(const float* dv, const float* u, long long ld_u, const float* weight, float* du, float* dweight,
+                           float* dbias, float* du_colsum, float* workspace, int B, int H, int W, int Ch, int plain,
+                           int u_half, cudaStream_t stream);
+
 extern "C" int uwr_dwconv_gelu_bwd(const float* dv, const float* u, long long ld_u, const float* weight, float* du,
                                    float* dweight, float* dbias, float* du_colsum, float* workspace, int B, int H,
                                    int W, int Ch, int plain, uwr_stream_t stream_) {
-    cudaStream_t stream = (cudaStream_t)stream_;
+    return dwconv_bwd_impl(dv, u, ld_u, weight, du, dweight, dbias, du_colsum, workspace, B, H, W, Ch, plain, 0,
+                           (cudaStream_t)stream_);
+}
+
+// same with u stored as __half (B*H*W, Ch) dense (fp16 storage of the linear1 output); du is fp32 (B*H*W, Ch)
+extern "C" int uwr_dwconv_gelu_bwd_half(const float* dv, const void* u_half, const float* weight, float* du,
+                                        float* dweight, float* dbias, float* du_colsum, float* workspace, int B, int H,
+                                        int W, int Ch, uwr_stream_t stream_) {
+    UWR_REQUIRE(uwr_dwconv_half_supported(H, W, Ch) && uwr_round_outputs(),
+                "uwr_dwconv_gelu_bwd_half: needs H, W %% 16 == 0, Ch %% 32 == 0 and single-pass (tf32) mode");
+    return dwconv_bwd_impl(dv, (const float*)u_half, Ch, weight, du, dweight, dbias, du_colsum, workspace, B, H, W, Ch, 0, 1,
+                           (cudaStream_t)stream_);
+}
+
+static int dwconv_bwd_impl(const float* dv, const float* u, long long ld_u, const float* weight, float* du, float* dweight,
+                           float* dbias, float* du_colsum, float* workspace, int B, int H, int W, int Ch, int plain,
+                           int u_half, cudaStream_t stream) {
     UWR_REQUIRE(dv && u && weight && du && dweight && dbias && workspace, "uwr_dwconv_gelu_bwd: null pointer");
     UWR_REQUIRE(Ch % 4 == 0 && ld_u % 4 == 0, "uwr_dwconv_gelu_bwd: Ch and ld_u must be multiples of 4");
     const int tx = uwr_cdiv(W, TS), ty = uwr_cdiv(H, TS);
@@ -502,18 +677,20 @@ extern "C" int uwr_dwconv_gelu_bwd(const float* dv, const float* u, long long ld
     CUtensorMap map_dv;
     if (dw_halo_map(&map_dv, dv, Ch, B, H, W, Ch) != 0) return -3;
     const bool fast = uwr_round_outputs() && H % TS == 0 && W % TS == 0 && Ch % CG == 0;
-#define DW_BWD(PL, F)                                                                                             \
+#define DW_BWD(PL, F, ...)                                                                                        \
     do {                                                                                                          \
         static bool configured = false;                                                                           \
+        auto kern = dwconv_bwd_kernel<PL, F, ##__VA_ARGS__>;                                                      \
         if (!configured) {                                                                                        \
-            UWR_CUDA(cudaFuncSetAttribute(dwconv_bwd_kernel<PL, F>, cudaFuncAttributeMaxDynamicSharedMemorySize,  \
-                                          DW_SMEM_BYTES));                                                        \
+            UWR_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, DW_SMEM_BYTES));     \
             configured = true;                                                                                    \
         }                                                                                                         \
-        dwconv_bwd_kernel<PL, F><<<grid, DW_THREADS, DW_SMEM_BYTES, stream>>>(                                    \
-            map_dv, u, ld_u, weight, du, workspace, B, H, W, Ch, tx, tx * ty, uwr_round_outputs());               \
+        kern<<<grid, DW_THREADS, DW_SMEM_BYTES, stream>>>(map_dv, u, ld_u, weight, du, workspace, B, H, W, Ch, tx,  \
+                                                          tx * ty, uwr_round_outputs());                          \
     } while (0)
-    if (plain) {
+    if (u_half) {
+        DW_BWD(false, true, true);
+    } else if (plain) {
         if (fast) DW_BWD(true, true);
         else DW_BWD(true, false);
     } else {

@@ -17,6 +17,7 @@
 // operands already rounded to TF32 (the producing kernels round at their stores, weights through
 // uwr_round_tf32_tensors); the GEMM itself adds no rounding bias.
 #include <cuda.h>
+#include <cuda_fp16.h>
 
 #include "uwr_common.cuh"
 #include "uwr_tma.cuh"
@@ -50,7 +51,26 @@ struct T5Params {
     int rows_per_group;
     int epilogue;
     int round_out;
+    int c_half;   // C is __half (ldc in halves)
+    int r_half;   // R is __half (ldr in halves)
 };
+
+__device__ __forceinline__ float4 ld_half4(const __half* p) {
+    const uint2 raw = *reinterpret_cast<const uint2*>(p);
+    const float2 a = __half22float2(*reinterpret_cast<const __half2*>(&raw.x));
+    const float2 b = __half22float2(*reinterpret_cast<const __half2*>(&raw.y));
+    return make_float4(a.x, a.y, b.x, b.y);
+}
+__device__ __forceinline__ void st_half4(__half* p, float4 v) {
+    // clamp: fp32 -> fp16 conversion of |x| > 65504 would give inf
+    v.x = fminf(fmaxf(v.x, -65504.f), 65504.f); v.y = fminf(fmaxf(v.y, -65504.f), 65504.f);
+    v.z = fminf(fmaxf(v.z, -65504.f), 65504.f); v.w = fminf(fmaxf(v.w, -65504.f), 65504.f);
+    const __half2 lo = __floats2half2_rn(v.x, v.y), hi = __floats2half2_rn(v.z, v.w);
+    uint2 raw;
+    raw.x = *reinterpret_cast<const uint32_t*>(&lo);
+    raw.y = *reinterpret_cast<const uint32_t*>(&hi);
+    *reinterpret_cast<uint2*>(p) = raw;
+}
 
 // ---------------------------------------------------------------------------------- PTX wrappers
 // -------------------------------------------------------------------------------------- kernel
@@ -244,8 +264,9 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_const
 #pragma unroll
                     for (int i = 0; i < 8; ++i) {
                         const int row = row0 + i * 4 + rsub;
-                        rv[i] = (col_ok && row < p.M) ? *reinterpret_cast<const float4*>(p.R + (long long)row * p.ldr + col)
-                                                      : make_float4(0.f, 0.f, 0.f, 0.f);
+                        if (!(col_ok && row < p.M)) rv[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+                        else if (p.r_half) rv[i] = ld_half4(reinterpret_cast<const __half*>(p.R) + (long long)row * p.ldr + col);
+                        else rv[i] = *reinterpret_cast<const float4*>(p.R + (long long)row * p.ldr + col);
                     }
                 }
                 float4 b4 = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -277,7 +298,10 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_const
                         o.z *= gelu_grad_f(rv[i].z); o.w *= gelu_grad_f(rv[i].w);
                     }
                     if (p.round_out) o = make_float4(tf32_round(o.x), tf32_round(o.y), tf32_round(o.z), tf32_round(o.w));
-                    if (col_ok && row < p.M) *reinterpret_cast<float4*>(cbase + (long long)row * p.ldc + col) = o;
+                    if (col_ok && row < p.M) {
+                        if (p.c_half) st_half4(reinterpret_cast<__half*>(cbase) + (long long)row * p.ldc + col, o);
+                        else *reinterpret_cast<float4*>(cbase + (long long)row * p.ldc + col) = o;
+                    }
                 }
                 __syncwarp();  // the staging buffer is reused by the next chunk
             }
@@ -411,6 +435,8 @@ extern "C" int uwr_gemm_tcgen05_supported(const uwr_gemm_desc* d) {
     if (d->K % 4 || d->N % 4 || d->lda % 4 || d->ldb % 4 || d->ldc % 4) return 0;
     if (((uintptr_t)d->A | (uintptr_t)d->B | (uintptr_t)d->C) % 16) return 0;
     if (d->epilogue != UWR_EPI_NONE && (!d->R || d->ldr % 4 || (uintptr_t)d->R % 16)) return 0;
+    if ((d->c_half || d->r_half) && d->a_km) return 0;                    // half storage: NT / NN layouts only
+    if (d->r_half && d->epilogue == UWR_EPI_MUL_DGELU) return 0;
     if (d->bias && (uintptr_t)d->bias % 16) return 0;
     if (d->a_km && (d->M % 32 || d->N % 32)) return 0;   // MN-major operands: widths in 32-float groups
     if (!d->a_km && !d->b_nk && d->N % 32) return 0;
@@ -449,6 +475,7 @@ extern "C" int uwr_gemm_tcgen05(const uwr_gemm_desc* d, uwr_stream_t stream_) {
     p.rowscale = d->rowscale; p.rows_per_group = d->rows_per_group > 0 ? d->rows_per_group : 1;
     p.epilogue = d->epilogue;
     p.round_out = d->round_out;
+    p.c_half = d->c_half; p.r_half = d->r_half;
     if (sp.splits > 1) {
         const size_t need = (size_t)sp.splits * d->M * d->N * sizeof(float);
         UWR_REQUIRE(d->workspace && d->workspace_bytes >= need, "uwr_gemm_tcgen05: workspace too small (%zu < %zu)",

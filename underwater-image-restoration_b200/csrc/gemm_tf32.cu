@@ -391,6 +391,7 @@ extern "C" int uwr_gemm_tf32(const uwr_gemm_desc* d, uwr_stream_t stream_) {
     cudaStream_t stream = (cudaStream_t)stream_;
     UWR_REQUIRE(d && d->A && d->B && d->C, "uwr_gemm_tf32: null operand");
     UWR_REQUIRE(d->M > 0 && d->N > 0 && d->K > 0, "uwr_gemm_tf32: empty problem %d %d %d", d->M, d->N, d->K);
+    UWR_REQUIRE(!d->c_half && !d->r_half, "uwr_gemm_tf32: fp16 C / R storage is served by uwr_gemm_tcgen05 only");
     UWR_REQUIRE(d->K % 4 == 0 && d->lda % 4 == 0 && d->ldb % 4 == 0 && d->ldc % 2 == 0 && d->N % 2 == 0,
                 "uwr_gemm_tf32: K,lda,ldb must be multiples of 4 and N,ldc even (K=%d lda=%lld ldb=%lld ldc=%lld N=%d)",
                 d->K, d->lda, d->ldb, d->ldc, d->N);

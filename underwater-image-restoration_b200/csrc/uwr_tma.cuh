@@ -141,22 +141,35 @@ static inline EncodeTiledFn encode_tiled_fn() {
 
 // fp32 tensor of `rank` dims (dims[0] innermost, contiguous; strides_elems[i] = elements between
 // consecutive indices of dim i+1), box[] elements per dim, out-of-bounds elements read as 0
+static inline int encode_any(CUtensorMap* m, CUtensorMapDataType dtype, int elem_bytes, const void* base, int rank,
+                             const long long* dims, const long long* strides_elems, const int* box,
+                             CUtensorMapSwizzle swz);
 static inline int encode_f32(CUtensorMap* m, const float* base, int rank, const long long* dims,
                              const long long* strides_elems, const int* box, CUtensorMapSwizzle swz) {
+    return encode_any(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, base, rank, dims, strides_elems, box, swz);
+}
+// same for an fp16 tensor (strides in elements)
+static inline int encode_f16(CUtensorMap* m, const void* base, int rank, const long long* dims,
+                             const long long* strides_elems, const int* box, CUtensorMapSwizzle swz) {
+    return encode_any(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, base, rank, dims, strides_elems, box, swz);
+}
+static inline int encode_any(CUtensorMap* m, CUtensorMapDataType dtype, int elem_bytes, const void* base, int rank,
+                             const long long* dims, const long long* strides_elems, const int* box,
+                             CUtensorMapSwizzle swz) {
     cuuint64_t d[5], s[4];
     cuuint32_t b[5], es[5];
     for (int i = 0; i < rank; ++i) {
         d[i] = (cuuint64_t)dims[i];
         b[i] = (cuuint32_t)box[i];
         es[i] = 1;
-        if (i + 1 < rank) s[i] = (cuuint64_t)strides_elems[i] * 4;
+        if (i + 1 < rank) s[i] = (cuuint64_t)strides_elems[i] * (cuuint64_t)elem_bytes;
     }
     EncodeTiledFn enc = encode_tiled_fn();
     if (!enc) {
         uwr_set_error("cuTensorMapEncodeTiled is not available from the driver");
         return -3;
     }
-    CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, (cuuint32_t)rank, (void*)base, d, s, b, es,
+    CUresult r = enc(m, dtype, (cuuint32_t)rank, (void*)base, d, s, b, es,
                      CU_TENSOR_MAP_INTERLEAVE_NONE, swz, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                      CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) {

@@ -39,6 +39,7 @@ class GemmDesc(C.Structure):
         ("colsum", c_fp),
         ("workspace", c_fp), ("workspace_bytes", c_sz),
         ("round_out", c_int),
+        ("c_half", c_int), ("r_half", c_int),
     ]
 
 
@@ -97,6 +98,10 @@ SIGNATURES = {
     "uwr_dwconv_gelu_fwd": (c_int, [c_fp, c_ll, c_fp, c_fp, c_fp, c_fp, c_int, c_int, c_int, c_int, c_int, c_int,
                                     c_stream]),
     "uwr_set_attn_tcgen05": (c_int, [c_int]),
+    "uwr_dwconv_half_supported": (c_int, [c_int, c_int, c_int]),
+    "uwr_dwconv_gelu_fwd_half": (c_int, [c_fp, c_fp, c_fp, c_fp, c_fp, c_int, c_int, c_int, c_int, c_stream]),
+    "uwr_dwconv_gelu_bwd_half": (c_int, [c_fp, c_fp, c_fp, c_fp, c_fp, c_fp, c_fp, c_fp, c_int, c_int, c_int, c_int,
+                                         c_stream]),
     "uwr_gelu_mul_fwd": (c_int, [c_fp, c_ll, c_fp, c_ll, c_int, c_stream]),
     "uwr_gelu_mul_bwd": (c_int, [c_fp, c_fp, c_ll, c_fp, c_ll, c_int, c_stream]),
     "uwr_dwconv_gelu_bwd_workspace_bytes": (c_sz, [c_int, c_int, c_int, c_int]),

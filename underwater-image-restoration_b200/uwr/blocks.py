@@ -275,10 +275,16 @@ class LeFFBlockFn(torch.autograd.Function):
         ctx.link_in, ctx.link_out = link_in, link_out
         _link_register(link_out, dp_scale, L, b2)
         y2, mean, rstd = ops.layernorm_fwd(x2, n2w, n2b)
-        u = ops.linear(y2, ops.rounded_weight(w1), b1, t5=True)
         need_bwd = any(ctx.needs_input_grad)
-        # the conv pre-activation v is only ever needed as gelu'(v): store that instead
-        v, h2 = ops.dwconv_gelu_fwd(u, dww, dwb, B, H, W, Ch, mode=0, save_v=need_bwd, v_is_dgelu=True)
+        if need_bwd and ops.half_storage_ok(H, W, Ch) and dwb is not None:
+            # fp16 storage of u and gelu'(v) (neither is a tensor-core operand): half the bytes of 5 of the 13 passes
+            # this block makes over 4C-wide tensors, at the accuracy a TF32 operand has anyway
+            u = ops.linear(y2, ops.rounded_weight(w1), b1, t5=True, out_half=True)
+            v, h2 = ops.dwconv_gelu_fwd_half(u, dww, dwb, B, H, W, Ch)
+        else:
+            u = ops.linear(y2, ops.rounded_weight(w1), b1, t5=True)
+            # the conv pre-activation v is only ever needed as gelu'(v): store that instead
+            v, h2 = ops.dwconv_gelu_fwd(u, dww, dwb, B, H, W, Ch, mode=0, save_v=need_bwd, v_is_dgelu=True)
         out = ops.linear(h2, ops.rounded_weight(w2), b2, residual=x2, rowscale=dp_scale, rows_per_group=L, t5=True)
         if need_bwd:
             ctx.save_for_backward(x2, n2w, mean, rstd, y2, u, v, h2, w1, dww, w2, dp_scale)

@@ -38,6 +38,21 @@ def fast_path():
     return _PASSES == 1
 
 
+_HALF_STORAGE = True
+
+
+def set_half_storage(on):
+    """fp16 storage of the two 4C-wide LeFF tensors that are not tensor-core operands: u (linear1 output) and gelu'(v)
+    (DESIGN.md §3).  A 10-bit mantissa is what a TF32 operand keeps anyway, so this halves their HBM bytes at TF32-level
+    accuracy; only in single-pass mode, on the tcgen05 path, for full 16x16 tiles (ops.half_storage_ok)."""
+    global _HALF_STORAGE
+    _HALF_STORAGE = bool(on)
+
+
+def half_storage_ok(H, W, Ch):
+    return _HALF_STORAGE and _PASSES == 1 and bool(fn["uwr_dwconv_half_supported"](H, W, Ch))
+
+
 def bump_weight_epoch():
     global WEIGHT_EPOCH
     WEIGHT_EPOCH += 1
@@ -108,6 +123,22 @@ def _ptr(t):
     return t.data_ptr()
 
 
+def _hptr(t):
+    """device pointer of a CUDA float16 tensor (fp16-storage paths)"""
+    if not t.is_cuda or t.dtype != torch.float16:
+        raise TypeError(f"expected a CUDA float16 tensor, got {t.device} {t.dtype}")
+    return t.data_ptr()
+
+
+def _fptr(t):
+    """float32 or float16 CUDA tensor -> (pointer, is_half)"""
+    if t is None:
+        return None, 0
+    if t.dtype == torch.float16:
+        return _hptr(t), 1
+    return _ptr(t), 0
+
+
 def _empty(shape, like):
     return torch.empty(shape, device=like.device, dtype=torch.float32)
 
@@ -127,15 +158,17 @@ def gemm(A, B, C_out, M, N, K, *, lda, ldb, ldc, a_km=False, b_nk=True, B2=None,
     d.A, d.lda, d.a_km = _ptr(A), lda, int(a_km)
     d.B, d.ldb, d.b_nk = _ptr(B), ldb, int(b_nk)
     d.B2, d.n_split = _ptr(B2), n_split
-    d.C, d.ldc = _ptr(C_out), ldc
+    d.C, d.c_half = _fptr(C_out)
+    d.ldc = ldc
     d.M, d.N, d.K = M, N, K
     d.bias, d.bias2 = _ptr(bias), _ptr(bias2)
     d.epilogue = epilogue
-    d.R, d.ldr = _ptr(R), ldr
+    d.R, d.r_half = _fptr(R)
+    d.ldr = ldr
     d.rowscale, d.rows_per_group = _ptr(rowscale), rows_per_group
     d.colsum = _ptr(colsum)
     d.round_out = int(round_out and _PASSES == 1)
-    nbytes = 4 * (M * K + K * N + M * N + (M * N if R is not None else 0))
+    nbytes = 4 * (M * K + K * N) + (2 if d.c_half else 4) * M * N + ((2 if d.r_half else 4) * M * N if R is not None else 0)
     lay = ("TN" if a_km else ("NT" if b_nk else "NN"))
     ws = None
     if t5 and _PASSES == 1 and fn["uwr_gemm_tcgen05_supported"](C.byref(d)):
@@ -143,8 +176,11 @@ def gemm(A, B, C_out, M, N, K, *, lda, ldb, ldc, a_km=False, b_nk=True, B2=None,
         if wbytes:
             ws = _ws(wbytes, A)
             d.workspace, d.workspace_bytes = ws.data_ptr(), wbytes
-        _run("uwr_gemm_tcgen05", f"{lay} M{M} N{N} K{K} epi{epilogue}", nbytes, 2.0 * M * N * K, C.byref(d))
+        _run("uwr_gemm_tcgen05", f"{lay} M{M} N{N} K{K} epi{epilogue}" + ("h" if (d.c_half or d.r_half) else ""), nbytes,
+             2.0 * M * N * K, C.byref(d))
         return C_out
+    if d.c_half or d.r_half:
+        raise ValueError("fp16 C / R storage needs the tcgen05 GEMM path (t5=True, single-pass mode, supported shape)")
     if a_km:
         wbytes = fn["uwr_gemm_workspace_bytes"](M, N, K, 1)
         if wbytes:
@@ -155,13 +191,14 @@ def gemm(A, B, C_out, M, N, K, *, lda, ldb, ldc, a_km=False, b_nk=True, B2=None,
 
 
 def linear(x2d, weight, bias=None, *, weight2=None, bias2=None, residual=None, rowscale=None,
-           rows_per_group=0, out=None, t5=False, round_out=False):
-    """y = x W^T + b  (optionally [W;W2], optionally residual + s*(.)). x2d: (M,K) view, row stride lda."""
+           rows_per_group=0, out=None, t5=False, round_out=False, out_half=False):
+    """y = x W^T + b  (optionally [W;W2], optionally residual + s*(.)). x2d: (M,K) view, row stride lda.
+    out_half: y is stored as float16 (tcgen05 path only)."""
     M, K = x2d.shape
     lda = x2d.stride(0)
     N = weight.shape[0] + (weight2.shape[0] if weight2 is not None else 0)
     if out is None:
-        out = _empty((M, N), x2d)
+        out = torch.empty((M, N), device=x2d.device, dtype=torch.float16 if out_half else torch.float32)
     epi = EPI_RESID if residual is not None else EPI_NONE
     gemm(x2d, weight, out, M, N, K, lda=lda, ldb=weight.stride(0), ldc=out.stride(0), b_nk=True,
          B2=weight2, n_split=weight.shape[0] if weight2 is not None else 0, bias=bias, bias2=bias2,
@@ -488,6 +525,16 @@ def window_attn_bwd(dout, q_buf, q_off, kv_buf, k_off, v_off, table, w_param, B,
 
 
 # --------------------------------------------------------------------------------------------
+def dwconv_gelu_fwd_half(u_half, weight, bias, B, H, W, Ch):
+    """LeFF forward on a float16 u: returns (gelu'(v) as float16, h2 as TF32-rounded float32)."""
+    dg = torch.empty((B * H * W, Ch), device=u_half.device, dtype=torch.float16)
+    h2 = torch.empty((B * H * W, Ch), device=u_half.device, dtype=torch.float32)
+    n = B * H * W * Ch
+    _run("uwr_dwconv_gelu_fwd_half", f"B{B} H{H} Ch{Ch} half", n * (2 + 2 + 4), 18.0 * n, _hptr(u_half), _ptr(weight),
+         _ptr(bias), _hptr(dg), _ptr(h2), B, H, W, Ch)
+    return dg, h2
+
+
 def dwconv_gelu_fwd(u2d, weight, bias, B, H, W, Ch, mode=0, save_v=True, v_is_dgelu=False):
     """Returns (v or gelu'(v), h2)."""
     v = _empty((B * H * W, Ch), u2d) if save_v else None
@@ -511,13 +558,20 @@ def dwconv_gelu_bwd(dv, u2d, weight, B, H, W, Ch, du=None, plain=False, want_du_
                     dbias_out=None, dusum_out=None):
     """dv = dL/d(conv output).  Returns du (same row stride as u; only [:, :Ch] is written), dweight, dbias
     [, column sums of du[:, :Ch]]."""
+    half = u2d.dtype == torch.float16
     if du is None:
-        du = torch.empty_like(u2d)
+        du = torch.empty(u2d.shape, device=u2d.device, dtype=torch.float32)
     dweight = dweight_out if dweight_out is not None else torch.empty_like(weight)
-    dbias = dbias_out if dbias_out is not None else _empty((Ch,), u2d)
-    dusum = (dusum_out if dusum_out is not None else _empty((Ch,), u2d)) if want_du_colsum else None
-    ws = _ws(fn["uwr_dwconv_gelu_bwd_workspace_bytes"](B, H, W, Ch), u2d)
+    dbias = dbias_out if dbias_out is not None else _empty((Ch,), dv)
+    dusum = (dusum_out if dusum_out is not None else _empty((Ch,), dv)) if want_du_colsum else None
+    ws = _ws(fn["uwr_dwconv_gelu_bwd_workspace_bytes"](B, H, W, Ch), dv)
     n = B * H * W * Ch
+    if half:
+        if plain or u2d.stride(0) != Ch:
+            raise ValueError("float16 u: LeFF mode on a dense (rows, Ch) matrix only")
+        _run("uwr_dwconv_gelu_bwd_half", f"B{B} H{H} Ch{Ch} half", n * (4 + 2 + 4), 36.0 * n, _ptr(dv), _hptr(u2d),
+             _ptr(weight), _ptr(du), _ptr(dweight), _ptr(dbias), _ptr(dusum), _ptr(ws), B, H, W, Ch)
+        return (du, dweight, dbias, dusum) if want_du_colsum else (du, dweight, dbias)
     _run("uwr_dwconv_gelu_bwd", f"B{B} H{H} Ch{Ch}", 4 * n * 3, 36.0 * n,
          _ptr(dv), _ptr(u2d), u2d.stride(0), _ptr(weight), _ptr(du), _ptr(dweight), _ptr(dbias), _ptr(dusum),
          _ptr(ws), B, H, W, Ch, int(plain))
