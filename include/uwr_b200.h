@@ -263,6 +263,30 @@ size_t uwr_ffl_workspace_bytes(int planes, int S);
 int uwr_ffl_loss(const float* pred, const float* truth, float* out, float* grad, float* workspace,
                  int planes, int S, uwr_stream_t stream);
 
+/* ---- remaining "fflMix" terms and the SSIM metric on device (csrc/ssim.cu) -----------------------
+ * Images are NCHW fp32, `planes` = B*C planes of H x W.
+ * uwr_laplacian_l1_loss: Gradient_Loss (src/Losses/losses.py:162-181): mean |lap3x3(pred) - lap3x3(truth)| over the
+ *   valid (H-2) x (W-2) region; loss[0] and grad = dloss/dpred (NULL to skip).
+ * uwr_ssim_scale_fwd: one scale of pytorch_msssim (third party): separable 11-tap Gaussian
+ *   (sigma 1.5), valid convolution; mean_cs[planes], mean_ss[planes] = spatial means of the cs / ssim maps;
+ *   maps (planes, 3, H-10, W-10), optional: per-pixel derivatives of cs (full = 0) or ssim (full = 1) w.r.t.
+ *   blur(X), blur(X^2), blur(XY) for the backward.  ssim() of ModelTrainer.torchSSIM (ModelTrainer.py:23-24) is
+ *   mean(mean_ss) of one scale.
+ * uwr_ssim_scale_bwd: dX = coef[plane] * d(sum of the per-pixel value)/dX (+ 0.25 * dX_coarse upsampled: the adjoint of
+ *   the avg_pool2d(2) between MS-SSIM scales).
+ * uwr_avgpool2_pair: avg_pool2d(2) of both images (even sides). */
+size_t uwr_laplacian_l1_workspace_bytes(int planes, int H, int W);
+int uwr_laplacian_l1_loss(const float* pred, const float* truth, float* loss, float* grad, float* workspace,
+                          int planes, int H, int W, uwr_stream_t stream);
+size_t uwr_ssim_workspace_bytes(int planes, int H, int W);
+int uwr_ssim_scale_fwd(const float* X, const float* Y, float* maps, float* mean_cs, float* mean_ss,
+                       float* workspace, int planes, int H, int W, float data_range, int full,
+                       uwr_stream_t stream);
+int uwr_ssim_scale_bwd(const float* X, const float* Y, const float* maps, const float* coef,
+                       const float* dX_coarse, float* dX, int planes, int H, int W, uwr_stream_t stream);
+int uwr_avgpool2_pair(const float* X, const float* Y, float* Xo, float* Yo, int planes, int H, int W,
+                      uwr_stream_t stream);
+
 /* ---- frequency-domain mixing (shared-memory FFT passes, csrc/fft.cu) ------------------------
  * Token tensors are (B, H, W, C) fp32, C contiguous; H, W (and C for *_lc_*) powers of two <= 1024.
  * uwr_dft_hw_real: y = scale * Re(FFT2 over (H, W))(x)  -- FDFP, src/model/block.py:532-556

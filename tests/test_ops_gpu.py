@@ -852,3 +852,44 @@ def test_gemm_half_output_and_multiplier(ops):
     out = ops.linear_dgrad(d, w2, mul_by=mul, t5=True)
     ref2 = (d.double() @ w2.double()) * mul.double()
     assert out.dtype == torch.float32 and rel_l2(out, ref2) < 1e-5
+
+
+# ------------------------------------------------------------------- fflMix terms and SSIM on the device (csrc/ssim.cu)
+def _shim(name):
+    import importlib
+    import sys
+    sys.path.insert(0, os.path.join(ROOT, "oracle", "shims"))
+    try:
+        return importlib.import_module(name)
+    finally:
+        sys.path.pop(0)
+
+
+@pytest.mark.parametrize("B,S", [(2, 256), (1, 192)])
+def test_laplacian_and_ms_ssim_vs_reference_formulas(B, S):
+    """uwr.ssim (device kernels) vs Gradient_Loss restated from losses.py:162-181 and the pytorch_msssim stand-in of
+    oracle/shims (the published algorithm) evaluated in fp64 on the same GPU."""
+    from uwr import ssim as dev
+    msssim = _shim("pytorch_msssim")
+    g = torch.Generator().manual_seed(5)
+    t = torch.rand(B, 3, S, S, generator=g)
+    p = (t * 0.8 + 0.1 + 0.05 * torch.randn(B, 3, S, S, generator=g)).clamp(0, 1)
+    pc, tc = p.cuda().requires_grad_(), t.cuda()
+    lap = dev.gradient_loss(pc, tc)
+    ms = dev.ms_ssim(pc, tc)
+    (0.3 * lap + 0.7 * (1 - ms)).backward()
+    p64, t64 = p.cuda().double().requires_grad_(), t.cuda().double()
+    k = torch.tensor([[0.0, 1.0, 0.0], [1.0, -4.0, 1.0], [0.0, 1.0, 0.0]], dtype=torch.float64, device="cuda")
+    k = k.view(1, 1, 3, 3).repeat(3, 1, 1, 1)
+    lap64 = F.l1_loss(F.conv2d(p64, k, groups=3), F.conv2d(t64, k, groups=3))
+    ms64 = msssim.MS_SSIM(data_range=1.0, size_average=True, channel=3)(p64, t64)
+    (0.3 * lap64 + 0.7 * (1 - ms64)).backward()
+    print(f"lap {lap.item():.6f}/{lap64.item():.6f} ms_ssim {ms.item():.6f}/{ms64.item():.6f} grad {rel_l2(pc.grad, p64.grad):.2e}")
+    assert abs(lap.item() - lap64.item()) < 1e-5 * abs(lap64.item())
+    assert abs(ms.item() - ms64.item()) < 1e-5
+    assert rel_l2(pc.grad, p64.grad) < 1e-3      # fp32 variances e - a^2 cancel, as in the reference's own fp32 path
+    s1 = dev.ssim(tc, pc.detach())
+    s64 = msssim.ssim(t64, p64.detach(), data_range=1.0, size_average=True)
+    assert abs(s1.item() - s64.item()) < 1e-5
+    import uwr
+    assert abs(uwr.torchSSIM(tc, pc.detach()).item() - s64.item()) < 1e-5

@@ -358,10 +358,20 @@ __device__ __forceinline__ void fma2(float2& a, const float2& x, const float2& w
 
 // UHALF: u is __half (fp16 storage of the linear1 output, see dwconv_fwd_half_kernel); ld_u counts elements of u and
 // is also the row stride of the fp32 du.
+// raw 8-byte (fp32 pair) or 4-byte (fp16 pair, in .x) load; converted where it is used so that the eight loads of a
+// strip are in flight together
 template <bool UHALF>
 __device__ __forceinline__ float2 ld_u2(const float* p) {
-    if (UHALF) return __half22float2(*reinterpret_cast<const __half2*>(reinterpret_cast<const __half*>(p)));
+    if (UHALF) return make_float2(*p, 0.f);
     return *reinterpret_cast<const float2*>(p);
+}
+template <bool UHALF>
+__device__ __forceinline__ float2 cvt_u2(float2 raw) {
+    if (UHALF) {
+        const uint32_t bits = __float_as_uint(raw.x);
+        return __half22float2(*reinterpret_cast<const __half2*>(&bits));
+    }
+    return raw;
 }
 
 template <bool PLAIN, bool FAST, bool UHALF = false>
@@ -445,11 +455,12 @@ dwconv_bwd_kernel(const __grid_constant__ CUtensorMap map_dv, const float* __res
                     for (int a = 0; a < 3; ++a) col[a][(i + 2) % 3] = ld2(sp + (a * HS + lx0 + i + 2) * CG);
                     if (FAST || tx0 + lx0 + i < W) {
                         float cdf0 = 1.f, pdf0 = 0.f, cdf1 = 1.f, pdf1 = 0.f;  // plain conv: h1 = u, gelu' = 1
+                        const float2 uv = cvt_u2<UHALF>(uc[i]);
                         if (!PLAIN) {
-                            gelu_parts(uc[i].x, cdf0, pdf0);
-                            gelu_parts(uc[i].y, cdf1, pdf1);
+                            gelu_parts(uv.x, cdf0, pdf0);
+                            gelu_parts(uv.y, cdf1, pdf1);
                         }
-                        const float2 h1 = make_float2(uc[i].x * cdf0, uc[i].y * cdf1);
+                        const float2 h1 = make_float2(uv.x * cdf0, uv.y * cdf1);
                         float2 dh1 = make_float2(0.f, 0.f);
                         // v[q] = sum_k h1[q + k - 1] w[k]  =>  h1[p] meets dv[p + 1 - k] with weight w[k]
 #pragma unroll
@@ -464,7 +475,7 @@ dwconv_bwd_kernel(const __grid_constant__ CUtensorMap map_dv, const float* __res
                         dbs.x += ctr.x;
                         dbs.y += ctr.y;
                         float2 o = PLAIN ? dh1
-                                         : make_float2(dh1.x * fmaf(uc[i].x, pdf0, cdf0), dh1.y * fmaf(uc[i].y, pdf1, cdf1));
+                                         : make_float2(dh1.x * fmaf(uv.x, pdf0, cdf0), dh1.y * fmaf(uv.y, pdf1, cdf1));
                         if (rn) o = make_float2(tf32_round(o.x), tf32_round(o.y));
                         dus.x += o.x;
                         dus.y += o.y;

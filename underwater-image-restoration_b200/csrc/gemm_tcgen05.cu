@@ -51,25 +51,14 @@ struct T5Params {
     int rows_per_group;
     int epilogue;
     int round_out;
-    int c_half;   // C is __half (ldc in halves)
-    int r_half;   // R is __half (ldr in halves)
 };
 
-__device__ __forceinline__ float4 ld_half4(const __half* p) {
-    const uint2 raw = *reinterpret_cast<const uint2*>(p);
-    const float2 a = __half22float2(*reinterpret_cast<const __half2*>(&raw.x));
-    const float2 b = __half22float2(*reinterpret_cast<const __half2*>(&raw.y));
-    return make_float4(a.x, a.y, b.x, b.y);
-}
-__device__ __forceinline__ void st_half4(__half* p, float4 v) {
-    // clamp: fp32 -> fp16 conversion of |x| > 65504 would give inf
-    v.x = fminf(fmaxf(v.x, -65504.f), 65504.f); v.y = fminf(fmaxf(v.y, -65504.f), 65504.f);
-    v.z = fminf(fmaxf(v.z, -65504.f), 65504.f); v.w = fminf(fmaxf(v.w, -65504.f), 65504.f);
-    const __half2 lo = __floats2half2_rn(v.x, v.y), hi = __floats2half2_rn(v.z, v.w);
-    uint2 raw;
-    raw.x = *reinterpret_cast<const uint32_t*>(&lo);
-    raw.y = *reinterpret_cast<const uint32_t*>(&hi);
-    *reinterpret_cast<uint2*>(p) = raw;
+// two floats -> packed __half2 bits, clamped to the finite fp16 range (|x| > 65504 would convert to inf)
+__device__ __forceinline__ uint32_t pack_half2(float a, float b) {
+    a = fminf(fmaxf(a, -65504.f), 65504.f);
+    b = fminf(fmaxf(b, -65504.f), 65504.f);
+    const __half2 h = __floats2half2_rn(a, b);
+    return *reinterpret_cast<const uint32_t*>(&h);
 }
 
 // ---------------------------------------------------------------------------------- PTX wrappers
@@ -81,13 +70,15 @@ __host__ __device__ constexpr int t5_smem_bytes() {
     return t5_stages<BN>() * (TM * KC * 4 + BN * KC * 4) + 256 + BN * 4 + EPI_WARPS * 32 * EP_STRIDE * 4 + 1024;
 }
 
-template <int BN, int LAY, int EPI>
+// HF: fp16 storage flags, bit 0 = C is __half (EPI_NONE only), bit 1 = R is __half
+template <int BN, int LAY, int EPI, int HF = 0>
 __global__ void __launch_bounds__(T5_THREADS, 1)
 gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapB,
                     const T5Params p) {
     constexpr int STAGES = t5_stages<BN>();
     constexpr bool A_MN = (LAY == LAY_TN);
     constexpr bool B_MN = (LAY != LAY_NT);
+    constexpr bool C_HALF = (HF & 1) != 0, R_HALF = (HF & 2) != 0;
     constexpr int A_BYTES = TM * KC * 4;  // 16 KB
     constexpr int B_BYTES = BN * KC * 4;
     constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
@@ -236,20 +227,42 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_const
             // a per-warp smem buffer so that every global access of the epilogue (C stores, R loads)
             // covers 4 rows x 128 contiguous bytes per warp instruction instead of 32 rows x 16 bytes.
             float* st = sstage + (warp - 2) * (32 * EP_STRIDE);
-            const int rsub = lane >> 3;        // row within a group of 4
-            const int cc = (lane & 7) * 4;     // column offset of this lane's float4
+            // fp32 C: lane -> (row within a group of 4, float4 of the 32-column chunk): 4 rows x 128 B per instruction.
+            // fp16 C: lane -> (row within a group of 8, 8 columns): 8 rows x 64 B per instruction, 16 B per lane.
+            const int rsub = C_HALF ? (lane >> 2) : (lane >> 3);
+            const int cc = C_HALF ? (lane & 3) * 8 : (lane & 7) * 4;
+            constexpr int RGROUPS = C_HALF ? 4 : 8;          // row groups per 32-row chunk
+            constexpr int RSTEP = C_HALF ? 8 : 4;
             const int row0 = tm * TM + q * 32;
-            float sc[8];
+            float sc[RGROUPS];
 #pragma unroll
-            for (int i = 0; i < 8; ++i) {
-                const int row = row0 + i * 4 + rsub;
+            for (int i = 0; i < RGROUPS; ++i) {
+                const int row = row0 + i * RSTEP + rsub;
                 sc[i] = (p.rowscale != nullptr && row < p.M) ? __ldg(p.rowscale + row / p.rows_per_group) : 1.f;
             }
             float* cbase = p.C + (long long)z * p.split_stride;
+            constexpr int NCH = (BN / 32 + 1) / 2;  // chunks per warp (BN = 32: only half 0 works)
+            // fp16 epilogue operand: 8 B per lane and row, so the loads of ALL of this warp's chunks of the tile fit in
+            // registers (NCH x 8 x 8 B) and are issued before the accumulator is even ready: they land under the MMAs
+            uint2 rraw_all[R_HALF ? NCH : 1][8];
+            if (R_HALF) {
+#pragma unroll
+                for (int ci = 0; ci < NCH; ++ci) {
+                    const int c0 = (2 * ci + half) * 32;
+                    const int col = tn * BN + c0 + cc;
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) {
+                        const int row = row0 + i * 4 + rsub;
+                        const bool ok = c0 < BN && col < p.N && row < p.M;
+                        rraw_all[ci][i] = ok ? *reinterpret_cast<const uint2*>(reinterpret_cast<const __half*>(p.R) +
+                                                                               (long long)row * p.ldr + col)
+                                             : make_uint2(0u, 0u);
+                    }
+                }
+            }
             mbar_wait(&tfull_bar[buf], use & 1);
             tc_fence_after();
             const uint32_t tbase = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(buf * BN);
-            constexpr int NCH = (BN / 32 + 1) / 2;  // chunks per warp (BN = 32: only half 0 works)
             uint32_t acc[2][32];
             if (half * 32 < BN) tmem_ld32_issue(tbase + half * 32, acc[0]);
 #pragma unroll
@@ -257,20 +270,23 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_const
                 const int c0 = (2 * ci + half) * 32;
                 if (c0 >= BN) break;
                 const int col = tn * BN + c0 + cc;
-                const bool col_ok = col < p.N;  // N is a multiple of 4
-                // operand of the epilogue (residual / multiplier): issue the loads before waiting on TMEM
+                const bool col_ok = col < p.N;  // N is a multiple of 4 (8 with fp16 C)
+                // operand of the epilogue (residual / multiplier): issue the loads before waiting on TMEM; fp16
+                // operands stay raw (8 B) until they are used, so that the 8 loads are in flight together
                 float4 rv[8];
-                if (EPI != UWR_EPI_NONE) {
+                if (EPI != UWR_EPI_NONE && !R_HALF) {
 #pragma unroll
                     for (int i = 0; i < 8; ++i) {
                         const int row = row0 + i * 4 + rsub;
-                        if (!(col_ok && row < p.M)) rv[i] = make_float4(0.f, 0.f, 0.f, 0.f);
-                        else if (p.r_half) rv[i] = ld_half4(reinterpret_cast<const __half*>(p.R) + (long long)row * p.ldr + col);
-                        else rv[i] = *reinterpret_cast<const float4*>(p.R + (long long)row * p.ldr + col);
+                        rv[i] = (col_ok && row < p.M) ? *reinterpret_cast<const float4*>(p.R + (long long)row * p.ldr + col)
+                                                      : make_float4(0.f, 0.f, 0.f, 0.f);
                     }
                 }
-                float4 b4 = make_float4(0.f, 0.f, 0.f, 0.f);
-                if (p.bias != nullptr) b4 = *reinterpret_cast<const float4*>(sbias + c0 + cc);
+                float4 b4 = make_float4(0.f, 0.f, 0.f, 0.f), b4b = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (p.bias != nullptr) {
+                    b4 = *reinterpret_cast<const float4*>(sbias + c0 + cc);
+                    if (C_HALF) b4b = *reinterpret_cast<const float4*>(sbias + c0 + cc + 4);
+                }
                 tmem_ld_wait();
                 {
                     const uint32_t* a = acc[ci & 1];
@@ -282,25 +298,47 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_const
                 const int cn = c0 + 64;
                 if (ci + 1 < NCH && cn < BN) tmem_ld32_issue(tbase + cn, acc[(ci + 1) & 1]);  // next chunk in flight
                 __syncwarp();
+                if (C_HALF) {
 #pragma unroll
-                for (int i = 0; i < 8; ++i) {
-                    const int rr = i * 4 + rsub;
-                    const int row = row0 + rr;
-                    float4 o = *reinterpret_cast<const float4*>(st + rr * EP_STRIDE + cc);
-                    o.x = (o.x + b4.x) * sc[i]; o.y = (o.y + b4.y) * sc[i];
-                    o.z = (o.z + b4.z) * sc[i]; o.w = (o.w + b4.w) * sc[i];
-                    if (EPI == UWR_EPI_RESID) {
-                        o.x += rv[i].x; o.y += rv[i].y; o.z += rv[i].z; o.w += rv[i].w;
-                    } else if (EPI == UWR_EPI_MUL) {
-                        o.x *= rv[i].x; o.y *= rv[i].y; o.z *= rv[i].z; o.w *= rv[i].w;
-                    } else if (EPI == UWR_EPI_MUL_DGELU) {
-                        o.x *= gelu_grad_f(rv[i].x); o.y *= gelu_grad_f(rv[i].y);
-                        o.z *= gelu_grad_f(rv[i].z); o.w *= gelu_grad_f(rv[i].w);
+                    for (int i = 0; i < 4; ++i) {
+                        const int rr = i * 8 + rsub;
+                        const int row = row0 + rr;
+                        float4 o0 = *reinterpret_cast<const float4*>(st + rr * EP_STRIDE + cc);
+                        float4 o1 = *reinterpret_cast<const float4*>(st + rr * EP_STRIDE + cc + 4);
+                        o0.x = (o0.x + b4.x) * sc[i]; o0.y = (o0.y + b4.y) * sc[i];
+                        o0.z = (o0.z + b4.z) * sc[i]; o0.w = (o0.w + b4.w) * sc[i];
+                        o1.x = (o1.x + b4b.x) * sc[i]; o1.y = (o1.y + b4b.y) * sc[i];
+                        o1.z = (o1.z + b4b.z) * sc[i]; o1.w = (o1.w + b4b.w) * sc[i];
+                        if (col_ok && row < p.M) {
+                            __half* dst = reinterpret_cast<__half*>(cbase) + (long long)row * p.ldc + col;
+                            *reinterpret_cast<uint4*>(dst) = make_uint4(pack_half2(o0.x, o0.y), pack_half2(o0.z, o0.w),
+                                                                        pack_half2(o1.x, o1.y), pack_half2(o1.z, o1.w));
+                        }
                     }
-                    if (p.round_out) o = make_float4(tf32_round(o.x), tf32_round(o.y), tf32_round(o.z), tf32_round(o.w));
-                    if (col_ok && row < p.M) {
-                        if (p.c_half) st_half4(reinterpret_cast<__half*>(cbase) + (long long)row * p.ldc + col, o);
-                        else *reinterpret_cast<float4*>(cbase + (long long)row * p.ldc + col) = o;
+                } else {
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) {
+                        const int rr = i * 4 + rsub;
+                        const int row = row0 + rr;
+                        float4 o = *reinterpret_cast<const float4*>(st + rr * EP_STRIDE + cc);
+                        o.x = (o.x + b4.x) * sc[i]; o.y = (o.y + b4.y) * sc[i];
+                        o.z = (o.z + b4.z) * sc[i]; o.w = (o.w + b4.w) * sc[i];
+                        if (EPI != UWR_EPI_NONE && R_HALF) {
+                            const uint2 raw = rraw_all[R_HALF ? ci : 0][i];
+                            const float2 r01 = __half22float2(*reinterpret_cast<const __half2*>(&raw.x));
+                            const float2 r23 = __half22float2(*reinterpret_cast<const __half2*>(&raw.y));
+                            rv[i] = make_float4(r01.x, r01.y, r23.x, r23.y);
+                        }
+                        if (EPI == UWR_EPI_RESID) {
+                            o.x += rv[i].x; o.y += rv[i].y; o.z += rv[i].z; o.w += rv[i].w;
+                        } else if (EPI == UWR_EPI_MUL) {
+                            o.x *= rv[i].x; o.y *= rv[i].y; o.z *= rv[i].z; o.w *= rv[i].w;
+                        } else if (EPI == UWR_EPI_MUL_DGELU) {
+                            o.x *= gelu_grad_f(rv[i].x); o.y *= gelu_grad_f(rv[i].y);
+                            o.z *= gelu_grad_f(rv[i].z); o.w *= gelu_grad_f(rv[i].w);
+                        }
+                        if (p.round_out) o = make_float4(tf32_round(o.x), tf32_round(o.y), tf32_round(o.z), tf32_round(o.w));
+                        if (col_ok && row < p.M) *reinterpret_cast<float4*>(cbase + (long long)row * p.ldc + col) = o;
                     }
                 }
                 __syncwarp();  // the staging buffer is reused by the next chunk
@@ -383,10 +421,10 @@ T5Split t5_plan(int M, int N, int Kc, int lay, int bn) {
     return sp;
 }
 
-template <int BN, int LAY, int EPI>
+template <int BN, int LAY, int EPI, int HF = 0>
 int t5_launch(const CUtensorMap& ma, const CUtensorMap& mb, const T5Params& p, cudaStream_t stream) {
     constexpr int smem = t5_smem_bytes<BN>();
-    auto kern = gemm_tcgen05_kernel<BN, LAY, EPI>;
+    auto kern = gemm_tcgen05_kernel<BN, LAY, EPI, HF>;
     static bool configured = false;
     if (!configured) {
         UWR_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
@@ -401,7 +439,11 @@ int t5_launch(const CUtensorMap& ma, const CUtensorMap& mb, const T5Params& p, c
 }
 
 template <int BN, int LAY>
-int t5_dispatch_epi(const CUtensorMap& ma, const CUtensorMap& mb, const T5Params& p, cudaStream_t stream) {
+int t5_dispatch_epi(const CUtensorMap& ma, const CUtensorMap& mb, const T5Params& p, int hf, cudaStream_t stream) {
+    // fp16 storage is instantiated for the two LeFF uses only: linear1 forward (NT, C half) and the linear2 data
+    // gradient with the gelu' multiplier (NN, R half)
+    if (hf == 1) return t5_launch<BN, LAY_NT, UWR_EPI_NONE, 1>(ma, mb, p, stream);
+    if (hf == 2) return t5_launch<BN, LAY_NN, UWR_EPI_MUL, 2>(ma, mb, p, stream);
     switch (p.epilogue) {
         case UWR_EPI_RESID: return t5_launch<BN, LAY, UWR_EPI_RESID>(ma, mb, p, stream);
         case UWR_EPI_MUL: return t5_launch<BN, LAY, UWR_EPI_MUL>(ma, mb, p, stream);
@@ -411,10 +453,10 @@ int t5_dispatch_epi(const CUtensorMap& ma, const CUtensorMap& mb, const T5Params
 }
 
 template <int BN>
-int t5_dispatch(int lay, const CUtensorMap& ma, const CUtensorMap& mb, const T5Params& p, cudaStream_t stream) {
+int t5_dispatch(int lay, const CUtensorMap& ma, const CUtensorMap& mb, const T5Params& p, int hf, cudaStream_t stream) {
     switch (lay) {
-        case LAY_NT: return t5_dispatch_epi<BN, LAY_NT>(ma, mb, p, stream);
-        case LAY_NN: return t5_dispatch_epi<BN, LAY_NN>(ma, mb, p, stream);
+        case LAY_NT: return t5_dispatch_epi<BN, LAY_NT>(ma, mb, p, hf, stream);
+        case LAY_NN: return t5_dispatch_epi<BN, LAY_NN>(ma, mb, p, hf, stream);
         default: return t5_launch<BN, LAY_TN, UWR_EPI_NONE>(ma, mb, p, stream);
     }
 }
@@ -435,8 +477,11 @@ extern "C" int uwr_gemm_tcgen05_supported(const uwr_gemm_desc* d) {
     if (d->K % 4 || d->N % 4 || d->lda % 4 || d->ldb % 4 || d->ldc % 4) return 0;
     if (((uintptr_t)d->A | (uintptr_t)d->B | (uintptr_t)d->C) % 16) return 0;
     if (d->epilogue != UWR_EPI_NONE && (!d->R || d->ldr % 4 || (uintptr_t)d->R % 16)) return 0;
-    if ((d->c_half || d->r_half) && d->a_km) return 0;                    // half storage: NT / NN layouts only
-    if (d->r_half && d->epilogue == UWR_EPI_MUL_DGELU) return 0;
+    // fp16 storage: C half for a plain NT product (linear1 forward), R half for the NN product with the stored
+    // gelu' multiplier (linear2 data gradient)
+    if (d->c_half && !(d->b_nk && !d->a_km && d->epilogue == UWR_EPI_NONE && !d->r_half && d->N % 8 == 0 && d->ldc % 8 == 0))
+        return 0;
+    if (d->r_half && !(!d->b_nk && !d->a_km && d->epilogue == UWR_EPI_MUL && !d->c_half)) return 0;
     if (d->bias && (uintptr_t)d->bias % 16) return 0;
     if (d->a_km && (d->M % 32 || d->N % 32)) return 0;   // MN-major operands: widths in 32-float groups
     if (!d->a_km && !d->b_nk && d->N % 32) return 0;
@@ -475,7 +520,6 @@ extern "C" int uwr_gemm_tcgen05(const uwr_gemm_desc* d, uwr_stream_t stream_) {
     p.rowscale = d->rowscale; p.rows_per_group = d->rows_per_group > 0 ? d->rows_per_group : 1;
     p.epilogue = d->epilogue;
     p.round_out = d->round_out;
-    p.c_half = d->c_half; p.r_half = d->r_half;
     if (sp.splits > 1) {
         const size_t need = (size_t)sp.splits * d->M * d->N * sizeof(float);
         UWR_REQUIRE(d->workspace && d->workspace_bytes >= need, "uwr_gemm_tcgen05: workspace too small (%zu < %zu)",
@@ -483,11 +527,12 @@ extern "C" int uwr_gemm_tcgen05(const uwr_gemm_desc* d, uwr_stream_t stream_) {
         UWR_REQUIRE(d->ldc == d->N, "uwr_gemm_tcgen05: split contraction needs a dense C");
         p.C = d->workspace; p.ldc = d->N; p.split_stride = (long long)d->M * d->N;
     }
+    const int hf = (d->c_half ? 1 : 0) | (d->r_half ? 2 : 0);
     switch (bn) {
-        case 32: rc = t5_dispatch<32>(lay, ma, mb, p, stream); break;
-        case 64: rc = t5_dispatch<64>(lay, ma, mb, p, stream); break;
-        case 128: rc = t5_dispatch<128>(lay, ma, mb, p, stream); break;
-        default: rc = t5_dispatch<256>(lay, ma, mb, p, stream); break;
+        case 32: rc = t5_dispatch<32>(lay, ma, mb, p, hf, stream); break;
+        case 64: rc = t5_dispatch<64>(lay, ma, mb, p, hf, stream); break;
+        case 128: rc = t5_dispatch<128>(lay, ma, mb, p, hf, stream); break;
+        default: rc = t5_dispatch<256>(lay, ma, mb, p, hf, stream); break;
     }
     if (rc) return rc;
     if (sp.splits > 1) {

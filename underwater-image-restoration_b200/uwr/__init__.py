@@ -13,5 +13,5 @@ from .registry import get_names, init_model  # noqa: F401
 from .losses import LossFunction  # noqa: F401
 from .ast import AST  # noqa: F401
 from .optim import FusedClipAdam  # noqa: F401
-from .metrics import torchPSNR  # noqa: F401
+from .metrics import torchPSNR, torchSSIM  # noqa: F401
 from . import torchlib  # noqa: F401  (registers torch.ops.uwr.*)

@@ -124,6 +124,12 @@ SIGNATURES = {
     "uwr_copy2d": (c_int, [c_fp, c_ll, c_fp, c_ll, c_ll, c_int, c_int, c_stream]),
     "uwr_colsum": (c_int, [c_fp, c_ll, c_fp, c_fp, c_ll, c_int, c_stream]),
     "uwr_pixel_loss": (c_int, [c_fp, c_fp, c_fp, c_fp, c_fp, c_int, c_int, c_int, c_int, c_int, c_int, c_stream]),
+    "uwr_laplacian_l1_workspace_bytes": (c_sz, [c_int, c_int, c_int]),
+    "uwr_laplacian_l1_loss": (c_int, [c_fp, c_fp, c_fp, c_fp, c_fp, c_int, c_int, c_int, c_stream]),
+    "uwr_ssim_workspace_bytes": (c_sz, [c_int, c_int, c_int]),
+    "uwr_ssim_scale_fwd": (c_int, [c_fp, c_fp, c_fp, c_fp, c_fp, c_fp, c_int, c_int, c_int, c_f, c_int, c_stream]),
+    "uwr_ssim_scale_bwd": (c_int, [c_fp, c_fp, c_fp, c_fp, c_fp, c_fp, c_int, c_int, c_int, c_stream]),
+    "uwr_avgpool2_pair": (c_int, [c_fp, c_fp, c_fp, c_fp, c_int, c_int, c_int, c_stream]),
     "uwr_ffl_workspace_bytes": (c_sz, [c_int, c_int]),
     "uwr_ffl_loss": (c_int, [c_fp, c_fp, c_fp, c_fp, c_fp, c_int, c_int, c_stream]),
     "uwr_dft_workspace_bytes": (c_sz, [c_int, c_int, c_int, c_int]),

@@ -3,9 +3,10 @@
     0.03*Charbonnier + 0.025*VGGPerceptual + 0.01*Gradient + 0.005*FFL + 0.1*(1 - MS_SSIM)
 
 returned as the 6-tuple (loss, charb, perc, grad, ffl, ssim) that ModelTrainer.py:82-85 unpacks.
-Charbonnier and the focal frequency term run on the uwr kernels; the VGG16 perceptual term, the
-Laplacian gradient term and MS-SSIM stay on PyTorch/cuDNN ops in this round (SURVEY.md §8a row 35,
-§8f rank 3).
+Charbonnier, the focal frequency term, the Laplacian gradient term and MS-SSIM run on the uwr kernels
+(csrc/losses.cu, ffl.cu, ssim.cu); the VGG16 perceptual network stays on PyTorch/cuDNN (SURVEY.md §8a row 35 prescribes
+it; §8f rank 3).  `gradient_loss` / `ms_ssim` below are device-agnostic torch restatements kept as the CPU reference the
+golden tests pin against the reference's own values.
 
 VGG16 weights.  The reference builds `torchvision.models.vgg16(pretrained=True)` (losses.py:219-222), i.e. the
 ImageNet checkpoint `vgg16-397923af.pth`.  This module looks for it (a) where `UWR_VGG16_WEIGHTS` points,
@@ -146,10 +147,11 @@ def fflmix_loss(lossfn, pred, truth):
     from .ffl import FocalFrequencyFn
     from .losses import PixelLossFn
     vgg = _vgg_for(lossfn, pred.device)
+    from . import ssim as dev
     charb = PixelLossFn.apply(pred, truth, "charbonnier", None)
     perc = vgg(pred, truth)
-    grad = gradient_loss(pred, truth)
-    ffl = FocalFrequencyFn.apply(pred, truth)
-    ssim = 1 - ms_ssim(pred, truth)
+    grad = dev.gradient_loss(pred, truth)            # csrc/ssim.cu (the torch versions below are the CPU restatements
+    ffl = FocalFrequencyFn.apply(pred, truth)        # that tests/test_oracle_golden.py pins against the reference)
+    ssim = 1 - dev.ms_ssim(pred, truth)
     loss = 0.03 * charb + 0.025 * perc + 0.01 * grad + 0.005 * ffl + 0.1 * ssim
     return loss, charb, perc, grad, ffl, ssim

@@ -32,3 +32,12 @@ def torchPSNR(tar_img, prd_img, group=None):
                              and torch.distributed.get_world_size() > 1):
         torch.distributed.all_reduce(mse, op=torch.distributed.ReduceOp.AVG, group=group)
     return (20.0 * torch.log10(1.0 / torch.sqrt(mse))).reshape(())
+
+
+def torchSSIM(tar_img, prd_img):
+    """Drop-in for src/ModelTrainer.py:23-24: pytorch_msssim.ssim(tar, prd, data_range=1.0, size_average=True) on the
+    separable-Gaussian SSIM kernel (csrc/ssim.cu); returns a 0-dim device tensor."""
+    from .ssim import ssim
+    if not (tar_img.is_cuda and prd_img.is_cuda):
+        raise RuntimeError("uwr.metrics runs on CUDA tensors only; there is no CPU fallback")
+    return ssim(tar_img.float(), prd_img.float(), data_range=1.0, size_average=True)
