@@ -3,12 +3,13 @@
 oracle.ast_oracle.window_attention directly).  Tolerance: TF32 operands, fp32 accumulate ->
 relative L2 <= 1e-3 (north star); pure fp32 kernels <= 2e-5."""
 import math
+import os
 
 import pytest
 import torch
 import torch.nn.functional as F
 
-from conftest import rel_l2
+from conftest import ROOT, rel_l2
 
 pytestmark = pytest.mark.gpu
 TOL_TF32 = 1e-3
@@ -747,8 +748,9 @@ def test_fused_clip_adam_is_a_torch_optimizer_with_checkpoint_and_scheduler():
     ps2 = [torch.nn.Parameter(p.detach().clone()) for p in ps]
     qs2 = [torch.nn.Parameter(p.detach().clone()) for p in ps]
     opt2, ref2 = FusedClipAdam(ps2, lr=123.0, max_norm=1.0), torch.optim.Adam(qs2, lr=123.0)
-    opt2.load_state_dict(sd)
-    ref2.load_state_dict(sd)
+    import copy
+    opt2.load_state_dict(copy.deepcopy(sd))      # torch's loader aliases the tensors of the dict it is given
+    ref2.load_state_dict(copy.deepcopy(sd))
     assert opt2.lr == ref2.param_groups[0]["lr"] == opt.lr and opt2.step_count == 3
     for p, q, g in zip(ps2, qs2, grads[3]):
         p.grad, q.grad = g.clone(), g.clone()

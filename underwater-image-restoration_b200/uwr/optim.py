@@ -144,6 +144,10 @@ class FusedClipAdam(torch.optim.Optimizer):
         groups = [dict(g, decoupled_weight_decay=g.get("decoupled_weight_decay", mine["decoupled_weight_decay"]),
                        capturable=True, fused=True, foreach=None) for g in state_dict["param_groups"]]
         super().load_state_dict({"state": state_dict["state"], "param_groups": groups})
+        for st in self.state.values():      # torch's loader may alias the caller's tensors: own the moments
+            for k in ("exp_avg", "exp_avg_sq"):
+                if k in st:
+                    st[k] = st[k].clone()
         steps = [float(st["step"]) for st in self.state.values() if "step" in st]
         dev = next((p.device for p in self.param_groups[0]["params"] if p.is_cuda), None)
         if dev is not None:
