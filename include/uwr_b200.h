@@ -381,6 +381,17 @@ int uwr_mdta_apply(const float* X, long long ldx, const float* M, int transpose,
                    long long ldy, const float* diag, float* out, long long ldo, int B, int L, int heads,
                    int c, uwr_stream_t stream);
 
+/* ---- Haar "wavelet" mode (use_dwt = "Wavelet": src/model/model.py:64-88, src/model/block.py:532-552) -------
+ * DWT_2D / IDWT_2D of src/model/wave_modules.py:9-181 on token tensors, forward AND the reference's own hand-written
+ * backward formulas (which are not the adjoints of the forwards; csrc/wavelet.cu states them in closed form).
+ * h, w = the COARSE grid; the fine grid is 2h x 2w; C % 4 == 0; idwt_bwd needs h, w % 4 == 0 and a workspace of
+ * B*4*(h*w/16) floats. */
+int uwr_haar_dwt_fwd(const float* in, float* out, int B, int h, int w, int C, uwr_stream_t stream);
+int uwr_haar_dwt_bwd(const float* dout, float* din, int B, int h, int w, int C, uwr_stream_t stream);
+int uwr_haar_idwt_fwd(const float* in, float* out, int B, int h, int w, int C, uwr_stream_t stream);
+int uwr_haar_idwt_bwd(const float* dout, float* din, float* workspace, int B, int h, int w, int C,
+                      uwr_stream_t stream);
+
 /* ---- optimizer step (ModelTrainer.py:87-88,197-204): clip_grad_norm_(1.0) + Adam/AdamW -----
  * tensor tables are device arrays of pointers; `offsets` (n_tensors+1 entries, offsets[0]=0) is
  * the running element count of the virtual concatenation.

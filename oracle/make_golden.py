@@ -91,6 +91,28 @@ def main():
     torch.save({"state_dict_sha1": nkeys, "out": yr, "seed_weights": 1234, "seed_data": 2024},
                os.path.join(OUT, "newbigfrfn_128.pt"))
 
+    # ---- NewBigFRFNModel in Haar-wavelet mode (use_dwt="Wavelet"; unreachable from the CLI):
+    # output + loss gradients of the reference itself, INCLUDING its hand-written (non-adjoint) DWT / IDWT backward
+    torch.manual_seed(1234)
+    nw = MyBigFRFNModel(use_dwt="Wavelet")
+    origw = nw.output_proj.forward
+    nw.output_proj.forward = lambda tk: origw(tk.transpose(1, 2).reshape(tk.shape[0], tk.shape[2], 128, 128).contiguous())
+    nw.eval()
+    gw = torch.Generator().manual_seed(2024)
+    xw = torch.rand(1, 3, 128, 128, generator=gw) * 2 - 1
+    tw = torch.rand(1, 3, 128, 128, generator=gw) * 2 - 1
+    with contextlib.redirect_stdout(io.StringIO()):
+        yw = nw(xw)
+    ((yw - tw) ** 2).mean().backward()
+    pgw = torch.Generator().manual_seed(99)
+    gradsw = {}
+    for n, p in nw.named_parameters():
+        r = torch.randn(p.shape, generator=pgw)
+        if p.grad is not None:
+            gradsw[n] = (p.grad.norm().item(), (p.grad * r).sum().item())
+    torch.save({"out": yw.detach(), "grad_norm_proj": gradsw, "seed_weights": 1234, "seed_data": 2024, "proj_seed": 99},
+               os.path.join(OUT, "newbigfrfn_wavelet_128.pt"))
+
     # ---- NewModel / NewBigModel: constructible, forward raises ("keep them registry-constructible and
     # failing identically") -> seeded state_dict hashes + the exception each forward raises
     from src.model.model import MyBigModel, MyModel

@@ -80,3 +80,63 @@ def _newbig_parity(train, S, grad_tol):
     # dead parameters of the Fourier mode get no gradient, as in the reference
     for n in dead:
         assert named[n].grad is None or float(named[n].grad.abs().max()) == 0.0, n
+
+
+def test_haar_wavelet_kernels_vs_oracle():
+    """csrc/wavelet.cu (DWT / IDWT forward and the reference's own backward formulas) vs oracle/wavelet_oracle.py, which
+    is pinned against the reference's DWT_2D / IDWT_2D modules (tests/golden via oracle/make_golden.py)."""
+    from oracle import wavelet_oracle as wo
+    from uwr import fn
+    g = torch.Generator().manual_seed(4)
+    for B, C, h, w in ((2, 32, 8, 12), (1, 64, 16, 16), (2, 8, 4, 4)):
+        x = torch.randn(B, 4 * h * w, C, generator=g)
+        xc = x.cuda().requires_grad_()
+        y = fn.HaarDWTFn.apply(xc, B, h, w)
+        gy = torch.randn(B, h * w, C, generator=g)
+        y.backward(gy.cuda())
+        assert rel_l2(y, wo.dwt_fwd(x.double(), B, h, w)) < 1e-6
+        assert rel_l2(xc.grad, wo.dwt_bwd(gy.double(), B, h, w)) < 1e-6
+        z = torch.randn(B, h * w, C, generator=g)
+        zc = z.cuda().requires_grad_()
+        o = fn.HaarIDWTFn.apply(zc, B, h, w)
+        go = torch.randn(B, 4 * h * w, C, generator=g)
+        o.backward(go.cuda())
+        assert rel_l2(o, wo.idwt_fwd(z.double(), B, h, w)) < 1e-6
+        assert rel_l2(zc.grad, wo.idwt_bwd(go.double(), B, h, w)) < 1e-6
+
+
+def test_newbigfrfn_wavelet_mode_vs_reference_golden():
+    """MyBigFRFNModel(use_dwt="Wavelet") (model.py:64-88, block.py:532-552) on the uwr kernels vs the output and the
+    loss gradients of the REFERENCE ITSELF (tests/golden/newbigfrfn_wavelet_128.pt, written by oracle/make_golden.py:
+    per-tensor gradient norms and random projections, including the reference's non-adjoint DWT / IDWT backward)."""
+    import os
+    from conftest import ROOT
+    from uwr.newbig import MyBigFRFNModel
+    gold = torch.load(os.path.join(ROOT, "tests", "golden", "newbigfrfn_wavelet_128.pt"), weights_only=False)
+    torch.manual_seed(gold["seed_weights"])
+    model = MyBigFRFNModel(use_dwt="Wavelet").cuda().eval()
+    g = torch.Generator().manual_seed(gold["seed_data"])
+    x = torch.rand(1, 3, 128, 128, generator=g) * 2 - 1
+    t = torch.rand(1, 3, 128, 128, generator=g) * 2 - 1
+    y = model(x.cuda())
+    ((y - t.cuda()) ** 2).mean().backward()
+    e_out = rel_l2(y, gold["out"])
+    pg = torch.Generator().manual_seed(gold["proj_seed"])
+    num = den = 0.0
+    missing = []
+    for n, p in model.named_parameters():
+        r = torch.randn(p.shape, generator=pg)
+        if n not in gold["grad_norm_proj"]:
+            assert p.grad is None or float(p.grad.abs().max()) == 0.0, n
+            continue
+        if p.grad is None:
+            missing.append(n)
+            continue
+        norm_ref, proj_ref = gold["grad_norm_proj"][n]
+        gcpu = p.grad.detach().cpu()
+        num += (gcpu.norm().item() - norm_ref) ** 2 + ((gcpu * r).sum().item() - proj_ref) ** 2
+        den += norm_ref ** 2 + proj_ref ** 2
+    assert not missing, missing
+    print(f"NewBigFRFN wavelet mode vs reference golden: out {e_out:.2e}, gradient norms/projections {(num / den) ** 0.5:.2e}")
+    assert e_out < 1e-3
+    assert (num / den) ** 0.5 < 5e-3

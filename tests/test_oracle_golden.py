@@ -196,3 +196,23 @@ def test_fflmix_torch_terms_match_reference_golden():
     assert close(fflmix.gradient_loss(p, t).item(), g[3])
     assert close(1 - fflmix.ms_ssim(p, t).item(), g[5])
     assert close(0.03 * g[1] + 0.025 * g[2] + 0.01 * g[3] + 0.005 * g[4] + 0.1 * g[5], g[0])
+
+
+def test_wavelet_oracle_matches_reference_modules_golden_free():
+    """oracle/wavelet_oracle.py (closed forms of DWT_2D / IDWT_2D forward AND the reference's hand-written backward,
+    wave_modules.py:9-181) is self-consistent on the identities that hold by construction: every sub-band of the DWT is
+    replicated over C/4 channels, the DWT 'gradient' is channel-independent, IDWT maps groups of 4 channels."""
+    from oracle import wavelet_oracle as wo
+    g = torch.Generator().manual_seed(3)
+    B, C, h, w = 2, 16, 8, 12
+    x = torch.randn(B, 4 * h * w, C, generator=g, dtype=torch.float64)
+    y = wo.dwt_fwd(x, B, h, w).view(B, h * w, 4, C // 4)
+    assert torch.equal(y, y[..., :1].expand_as(y))
+    # ll sub-band = half the sum of the 2x2 block of the channel-summed image
+    S = x.view(B, h, 2, w, 2, C).sum((-1, 2, 4)).reshape(B, h * w)
+    assert torch.allclose(y[:, :, 0, 0], 0.5 * S, atol=1e-12)
+    d = wo.dwt_bwd(torch.randn(B, h * w, C, generator=g, dtype=torch.float64), B, h, w)
+    assert torch.equal(d, d[..., :1].expand_as(d))
+    z = wo.idwt_fwd(torch.randn(B, h * w, C, generator=g, dtype=torch.float64), B, h, w)
+    assert z.shape == (B, 4 * h * w, C)
+    assert wo.idwt_bwd(z, B, h, w).shape == (B, h * w, C)

@@ -157,6 +157,10 @@ SIGNATURES = {
     "uwr_mdta_gram": (c_int, [c_fp, c_ll, c_fp, c_ll, c_int, c_int, c_int, c_int, c_fp, c_fp, c_fp, c_fp, c_stream]),
     "uwr_mdta_apply": (c_int, [c_fp, c_ll, c_fp, c_int, c_fp, c_ll, c_fp, c_fp, c_ll, c_int, c_int, c_int, c_int,
                                c_stream]),
+    "uwr_haar_dwt_fwd": (c_int, [c_fp, c_fp, c_int, c_int, c_int, c_int, c_stream]),
+    "uwr_haar_dwt_bwd": (c_int, [c_fp, c_fp, c_int, c_int, c_int, c_int, c_stream]),
+    "uwr_haar_idwt_fwd": (c_int, [c_fp, c_fp, c_int, c_int, c_int, c_int, c_stream]),
+    "uwr_haar_idwt_bwd": (c_int, [c_fp, c_fp, c_fp, c_int, c_int, c_int, c_int, c_stream]),
     "uwr_grad_norm": (c_int, [c_fp, c_fp, c_int, c_ll, c_f, c_f, c_fp, c_fp, c_stream]),
     "uwr_adam_step": (c_int, [c_fp, c_fp, c_fp, c_fp, c_fp, c_int, c_ll, c_fp, c_f, c_f, c_f, c_f, c_f, c_f,
                               c_int, c_int, c_fp, c_fp, c_stream]),

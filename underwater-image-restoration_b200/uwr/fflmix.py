@@ -151,7 +151,7 @@ def fflmix_loss(lossfn, pred, truth):
     charb = PixelLossFn.apply(pred, truth, "charbonnier", None)
     perc = vgg(pred, truth)
     grad = dev.gradient_loss(pred, truth)            # csrc/ssim.cu (the torch versions below are the CPU restatements
-    ffl = FocalFrequencyFn.apply(pred, truth)        # that tests/test_oracle_golden.py pins against the reference)
+    ffl = FocalFrequencyFn.apply(pred, truth)        # that the golden tests pin against the reference's own values)
     ssim = 1 - dev.ms_ssim(pred, truth)
     loss = 0.03 * charb + 0.025 * perc + 0.01 * grad + 0.005 * ffl + 0.1 * ssim
     return loss, charb, perc, grad, ffl, ssim

@@ -551,3 +551,51 @@ class ConvTok2ImgFn(torch.autograd.Function):
         wt = weight.detach().flip(2, 3).transpose(0, 1).contiguous()
         dtok = ops.conv3x3_small_fwd(dimg, False, wt, None, B, H, W)
         return dtok, dw, db, (dimg if has_res and ctx.needs_input_grad[3] else None), None, None, None
+
+
+# ---- Haar "wavelet" mode (src/model/wave_modules.py) on csrc/wavelet.cu ----------------------------------------------
+class HaarDWTFn(torch.autograd.Function):
+    """DWT_2D on tokens (B, 2h*2w, C) -> (B, h*w, C); the backward is the REFERENCE's formula (DWT_function.backward)."""
+
+    @staticmethod
+    def forward(ctx, x, B, h, w):
+        x = _c(x)
+        C = x.shape[-1]
+        ctx.dims = (B, h, w, C)
+        out = ops._empty((B, h * w, C), x)
+        ops._run("uwr_haar_dwt_fwd", f"B{B} h{h} C{C}", 5 * out.numel() * 4, 0.0, ops._ptr(x), ops._ptr(out), B, h, w, C)
+        return out
+
+    @staticmethod
+    @once_differentiable
+    def backward(ctx, dout):
+        B, h, w, C = ctx.dims
+        dout = _c(dout)
+        din = ops._empty((B, 4 * h * w, C), dout)
+        ops._run("uwr_haar_dwt_bwd", f"B{B} h{h} C{C}", 5 * dout.numel() * 4, 0.0, ops._ptr(dout), ops._ptr(din), B, h, w, C)
+        return din, None, None, None
+
+
+class HaarIDWTFn(torch.autograd.Function):
+    """IDWT_2D on tokens (B, h*w, C) -> (B, 2h*2w, C); the backward is the REFERENCE's formula (IDWT_function.backward,
+    raw NCHW-memory reshapes included)."""
+
+    @staticmethod
+    def forward(ctx, x, B, h, w):
+        x = _c(x)
+        C = x.shape[-1]
+        ctx.dims = (B, h, w, C)
+        out = ops._empty((B, 4 * h * w, C), x)
+        ops._run("uwr_haar_idwt_fwd", f"B{B} h{h} C{C}", 5 * x.numel() * 4, 0.0, ops._ptr(x), ops._ptr(out), B, h, w, C)
+        return out
+
+    @staticmethod
+    @once_differentiable
+    def backward(ctx, dout):
+        B, h, w, C = ctx.dims
+        dout = _c(dout)
+        din = ops._empty((B, h * w, C), dout)
+        ws = ops._ws(B * 4 * (h * w // 16) * 4, dout)
+        ops._run("uwr_haar_idwt_bwd", f"B{B} h{h} C{C}", 5 * din.numel() * 4, 0.0, ops._ptr(dout), ops._ptr(din), ops._ptr(ws),
+                 B, h, w, C)
+        return din, None, None, None

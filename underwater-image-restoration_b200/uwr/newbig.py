@@ -101,10 +101,19 @@ class FDFP(nn.Module):
 
     def forward(self, x):  # (B, H, W, C) tokens
         B, H, W, C = x.shape
-        f = fn.dft_real(x, B, H, W, C, 1.0, "hw")                      # Re(fftn over (H, W))
+        if self.use_dwt == "Wavelet":                                   # block.py:535-536,547-548
+            f = fn.HaarDWTFn.apply(x.reshape(B, H * W, C), B, H // 2, W // 2)
+        elif self.use_dwt == "Fourier":
+            f = fn.dft_real(x, B, H, W, C, 1.0, "hw")                  # Re(fftn over (H, W))
+        else:
+            f = x
         f = fn.linear(f, self.conv1.weight.flatten(1), self.conv1.bias)
         f = fn.linear(fn.GeluFn.apply(f, True), self.conv2.weight.flatten(1), self.conv2.bias, rounded=True)
-        return fn.dft_real(f, B, H, W, C, 1.0 / (H * W), "hw")         # Re(ifftn) of a real tensor
+        if self.use_dwt == "Wavelet":
+            return fn.HaarIDWTFn.apply(f, B, H // 2, W // 2).view(B, H, W, C)
+        if self.use_dwt == "Fourier":
+            return fn.dft_real(f, B, H, W, C, 1.0 / (H * W), "hw")     # Re(ifftn) of a real tensor
+        return f
 
 
 class MDASSA(nn.Module):
@@ -163,16 +172,21 @@ class EncoderBlock(nn.Module):
         self.drop_path2 = DropPath(drop_path) if drop_path > 0.0 else nn.Identity()
 
     def forward(self, x):
-        if self.token_mlp != "frfn" or self.freq_mlp_kind != "frfn" or self.use_dwt != "Fourier":
-            raise NotImplementedError("EncoderBlock.forward: only the configuration the registry can run is built "
-                                      "(frfn token / frequency mixers, use_dwt='Fourier'); NewModel / NewBigModel never "
-                                      "reach this point (their forward raises first, as in the reference)")
+        if self.token_mlp != "frfn" or self.freq_mlp_kind != "frfn" or self.use_dwt not in ("Fourier", "Wavelet"):
+            raise NotImplementedError("EncoderBlock.forward: frfn token / frequency mixers with use_dwt 'Fourier' or "
+                                      "'Wavelet' are built; NewModel / NewBigModel (leff) never reach this point (their "
+                                      "forward raises first, as in the reference)")
         B, L, C = x.shape
         H = W = int(math.sqrt(L))
         a = self.mlp.block_forward(x, self.norm1, None, H, W, residual=False)
-        f = fn.dft_real(a, B, H, W, C, 1.0, "lc")                      # Re(fftn over (L, C))
-        f = self.freq_mlp.block_forward(f, None, None, H, W, residual=False)
-        f = fn.dft_real(f, B, H, W, C, 1.0 / (L * C), "lc")            # Re(ifftn) of a real tensor
+        if self.use_dwt == "Fourier":
+            f = fn.dft_real(a, B, H, W, C, 1.0, "lc")                      # Re(fftn over (L, C)) of the MLP output
+            f = self.freq_mlp.block_forward(f, None, None, H, W, residual=False)
+            f = fn.dft_real(f, B, H, W, C, 1.0 / (L * C), "lc")            # Re(ifftn) of a real tensor
+        else:   # "Wavelet" (model.py:62-69,81-84): the frequency branch starts from norm2(x), at half resolution
+            f = fn.HaarDWTFn.apply(fn.layernorm(x, self.norm2), B, H // 2, W // 2)
+            f = self.freq_mlp.block_forward(f, None, None, H // 2, W // 2, residual=False)
+            f = fn.HaarIDWTFn.apply(f, B, H // 2, W // 2)
         # the reference draws drop_path2 (frequency branch) first, then drop_path (model.py:90)
         s2 = self.drop_path2.scale(B, x.device) if isinstance(self.drop_path2, DropPath) else None
         s1 = self.drop_path.scale(B, x.device) if isinstance(self.drop_path, DropPath) else None

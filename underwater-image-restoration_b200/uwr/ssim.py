@@ -1,8 +1,8 @@
 """Device versions of the Laplacian gradient loss, MS-SSIM and SSIM (csrc/ssim.cu): the two remaining non-VGG terms of
 the reference's "fflMix" loss (src/Losses/losses.py:108-117,162-181) and ModelTrainer.torchSSIM
 (src/ModelTrainer.py:23-24).  pytorch_msssim is a third-party package absent from the reference tree; its published
-algorithm (VainF/pytorch-msssim 1.0.0) is restated in SURVEY.md Appendix C and in oracle/shims/pytorch_msssim, which
-the parity tests compare against ("restatement-pinned").
+algorithm (VainF/pytorch-msssim 1.0.0) is restated in SURVEY.md Appendix C; the parity tests compare against a CPU
+stand-in of that package ("restatement-pinned").
 
 The per-pixel work (separable 11-tap Gaussian blurs of X, Y, X^2, Y^2, XY, the cs / ssim maps, and the blur adjoint
 in the backward) runs in the kernels; MS-SSIM's relu / product-of-powers over (planes x 5 scales) scalars is torch
