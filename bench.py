@@ -244,7 +244,11 @@ def run_ours(args):
     model = uwr.AST(img_size=S).to(dev)
     model.train()
     torch.manual_seed(1000 + rank)  # per-rank DropPath stream (SURVEY.md §8e caveat 4)
-    step = TrainStep(model, "L1", lr=1e-3, world_size=world, local_batch=B)
+    comm = None
+    if world > 1 and not args.torch_allreduce:
+        from uwr.nccl import Communicator
+        comm = Communicator(rank, world)      # raw NCCL: the bucket all-reduces are captured inside the step's graph
+    step = TrainStep(model, "L1", lr=1e-3, world_size=world, local_batch=B, comm=comm)
 
     raw_h, ref_h = _synthetic(B, S, seed=2024 + rank)
     raw_h, ref_h = raw_h.pin_memory(), ref_h.pin_memory()
@@ -427,6 +431,9 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference", "reference-gpu"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-gpu-eager", action="store_true", help="skip the PyTorch-eager-on-GPU comparison leg")
+    ap.add_argument("--torch-allreduce", action="store_true",
+                    help="N > 1: reduce gradients through torch.distributed work objects (two graphs around eager NCCL) "
+                         "instead of the raw NCCL communicator captured in one graph")
     ap.add_argument("--no-graph", action="store_true", help="launch the single-GPU step eagerly instead of replaying a CUDA graph")
     ap.add_argument("--profile-out", default="", help="write the per-kernel event table (JSON) here")
     args = ap.parse_args()

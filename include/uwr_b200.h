@@ -411,6 +411,20 @@ int uwr_adam_step(float* const* params, const float* const* grads, float* const*
                   const float* lr_dev, uwr_stream_t stream);
 int uwr_increment_i32(int* counter, uwr_stream_t stream);
 
+/* ---- data-parallel helpers: the gradient all-reduce over NCCL / NVLink --------------------
+ * Thin wrappers over the libnccl.so.2 already mapped in the process (dlopen at first use; uwr_nccl_available() = 0
+ * when it is absent).  `comm` is an ncclComm_t.  uwr_nccl_allreduce_sum_f32 enqueues an in-place sum all-reduce on
+ * `stream`; being a plain stream-ordered NCCL call it can be captured into a CUDA graph with the kernels around it
+ * (the whole DP step = one graph, uwr/graph.py).  The reference itself is single-device (ModelTrainer.py:33-42). */
+typedef struct {
+    char internal[128];
+} uwr_nccl_id; /* == ncclUniqueId */
+int uwr_nccl_available(void);
+int uwr_nccl_unique_id(uwr_nccl_id* id);                                     /* rank 0, then broadcast the 128 bytes */
+int uwr_nccl_comm_init(void** comm, int nranks, const uwr_nccl_id* id, int rank); /* collective */
+int uwr_nccl_comm_destroy(void* comm);
+int uwr_nccl_allreduce_sum_f32(void* comm, float* buf, size_t count, uwr_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -32,7 +32,7 @@ def color(pred, truth):
 
 def luminance(pred, truth):
     """LuminanceLoss, luminanceLoss.py:5-21."""
-    y = torch.tensor([0.299, 0.587, 0.114], dtype=pred.dtype).view(1, 3, 1, 1)
+    y = torch.tensor([0.299, 0.587, 0.114], dtype=pred.dtype, device=pred.device).view(1, 3, 1, 1)
     return (((pred - truth) * y).sum(1, keepdim=True) ** 2).mean()
 
 

@@ -53,6 +53,10 @@ class ConvSmallDesc(C.Structure):
     ]
 
 
+class NcclId(C.Structure):
+    _fields_ = [("internal", C.c_char * 128)]
+
+
 class AttnDesc(C.Structure):
     _fields_ = [
         ("q", c_fp), ("ld_q", c_ll), ("q_off", c_int),
@@ -161,6 +165,11 @@ SIGNATURES = {
     "uwr_haar_dwt_bwd": (c_int, [c_fp, c_fp, c_int, c_int, c_int, c_int, c_stream]),
     "uwr_haar_idwt_fwd": (c_int, [c_fp, c_fp, c_int, c_int, c_int, c_int, c_stream]),
     "uwr_haar_idwt_bwd": (c_int, [c_fp, c_fp, c_fp, c_int, c_int, c_int, c_int, c_stream]),
+    "uwr_nccl_available": (c_int, []),
+    "uwr_nccl_unique_id": (c_int, [C.POINTER(NcclId)]),
+    "uwr_nccl_comm_init": (c_int, [C.POINTER(C.c_void_p), c_int, C.POINTER(NcclId), c_int]),
+    "uwr_nccl_comm_destroy": (c_int, [C.c_void_p]),
+    "uwr_nccl_allreduce_sum_f32": (c_int, [C.c_void_p, c_fp, c_sz, c_stream]),
     "uwr_grad_norm": (c_int, [c_fp, c_fp, c_int, c_ll, c_f, c_f, c_fp, c_fp, c_stream]),
     "uwr_adam_step": (c_int, [c_fp, c_fp, c_fp, c_fp, c_fp, c_int, c_ll, c_fp, c_f, c_f, c_f, c_f, c_f, c_f,
                               c_int, c_int, c_fp, c_fp, c_stream]),

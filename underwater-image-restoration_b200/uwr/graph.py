@@ -33,8 +33,10 @@ class GraphedTrainStep:
     torch's graph-aware CUDA generator, TF32-rounded weight copies are refreshed by kernels inside the
     graph.  The `warmup` eager steps are real optimizer steps.
 
-    Data parallel (world > 1): NCCL collectives are kept OUT of the graphs (capturing ProcessGroupNCCL work
-    hung on this stack).  The step becomes graph A (zero -> forward -> loss -> backward, hooks only count) ->
+    Data parallel (world > 1) with a raw NCCL communicator (uwr.nccl.Communicator, the default of bench.py): the
+    stream-ordered ncclAllReduce calls are captured too — ONE graph, reduces forked onto a side stream.
+    Data parallel through torch.distributed work objects: those collectives are kept OUT of the graphs (capturing
+    ProcessGroupNCCL work hung on this stack).  The step becomes graph A (zero -> forward -> loss -> backward, hooks only count) ->
     eager per-bucket all-reduce (79.7 MB, ~0.3 ms over NVSwitch, not overlapped) -> graph B (clip + Adam):
     the ~2.5 ms of host launch gaps it removes outweigh the lost overlap."""
 
@@ -49,7 +51,9 @@ class GraphedTrainStep:
         torch.cuda.current_stream().wait_stream(s)
         self.graph = torch.cuda.CUDAGraph()
         self.graph_opt = None
-        if step.world == 1:
+        if step.world == 1 or step.buckets.comm is not None:
+            # one graph for the whole step; with a raw NCCL communicator (uwr.nccl) the bucket all-reduces are
+            # captured too, forked onto a side stream as soon as a bucket is complete and joined before clip + Adam
             with torch.cuda.graph(self.graph):
                 self.loss, self.norm = step(self.raw, self.ref)
         else:

@@ -19,6 +19,17 @@ MS_WEIGHTS = (0.0448, 0.2856, 0.3001, 0.2363, 0.1333)
 WIN = 11
 
 
+_WTS = {}
+
+
+def _weights(like):
+    """MS-SSIM scale weights as a device tensor, created once per device (a host -> device copy is not allowed inside
+    a CUDA-graph capture; the eager warm-up steps that precede a capture create it)."""
+    if like.device not in _WTS:
+        _WTS[like.device] = torch.tensor(MS_WEIGHTS, dtype=torch.float32, device=like.device)
+    return _WTS[like.device]
+
+
 def _c(t):
     return t if t.is_contiguous() else t.contiguous()
 
@@ -85,7 +96,7 @@ class MsSsimFn(torch.autograd.Function):
                 x, y, h, w = xo, yo, h // 2, w // 2
         with torch.enable_grad():
             leaves = [v.detach().requires_grad_() for v in vals]
-            wts = X.new_tensor(MS_WEIGHTS)
+            wts = _weights(X)
             stack = torch.relu(torch.stack(leaves, 0))                       # (5, planes)
             res = torch.prod(stack ** wts.view(-1, 1), 0).mean()
         if want:

@@ -20,11 +20,15 @@ from .optim import FusedClipAdam
 
 
 class GradBuckets:
-    def __init__(self, params, bucket_bytes=32 << 20, group=None, world_size=1, adjacent=()):
+    def __init__(self, params, bucket_bytes=32 << 20, group=None, world_size=1, adjacent=(), comm=None):
         """adjacent: pairs (p0, p1) whose slots must be laid out back to back, p0 first (their gradients come
-        out of one kernel, e.g. the packed to_q | to_kv weight gradient: ops.fused_grad_slot)."""
+        out of one kernel, e.g. the packed to_q | to_kv weight gradient: ops.fused_grad_slot).
+        comm: a uwr.nccl.Communicator — the buckets are then reduced with raw, stream-ordered ncclAllReduce calls
+        (graph-capturable) on a side stream instead of torch.distributed work objects."""
         self.params = [p for p in params if p.requires_grad]
         self.group, self.world = group, world_size
+        self.comm = comm
+        self._side = None
         order = list(reversed(self.params))  # roughly the order gradients are produced in backward
         follower = {id(a): b for a, b in adjacent}
         led = {id(b) for _, b in adjacent}
@@ -65,6 +69,16 @@ class GradBuckets:
 
     def _reduce(self, bi):
         self._launched[bi] = True
+        if self.comm is not None:
+            # fork: the side stream picks up where the (possibly capturing) compute stream is now, reduces the bucket
+            # there, and finish() joins it back -> the reduce overlaps whatever backward work is issued afterwards
+            cur = torch.cuda.current_stream()
+            if self._side is None:
+                self._side = torch.cuda.Stream()
+            self._side.wait_stream(cur)
+            self.comm.all_reduce_sum_(self.flat[bi], self._side)
+            self._forked = True
+            return
         self._handles.append(dist.all_reduce(self.flat[bi], op=dist.ReduceOp.SUM, group=self.group, async_op=True))
 
     def _hook(self, p):
@@ -90,17 +104,20 @@ class GradBuckets:
             for h in self._handles:
                 h.wait()
             self._handles = []
+            if getattr(self, "_forked", False):
+                torch.cuda.current_stream().wait_stream(self._side)   # join
+                self._forked = False
 
 
 class TrainStep:
     def __init__(self, model, loss_name="L1", lr=1e-3, optim="adam", world_size=1, group=None,
-                 local_batch=None, bucket_bytes=32 << 20, vgg_weights=None):
+                 local_batch=None, bucket_bytes=32 << 20, vgg_weights=None, comm=None):
         self.model = model
         self.world = world_size
         self.lossf = LossFunction(loss_name, "cuda", batch_divisor=(local_batch * world_size) if local_batch else None,
                                   vgg_weights=vgg_weights)
         adjacent = model.adjacent_grad_pairs() if hasattr(model, "adjacent_grad_pairs") else ()
-        self.buckets = GradBuckets(model.parameters(), bucket_bytes, group, world_size, adjacent=adjacent)
+        self.buckets = GradBuckets(model.parameters(), bucket_bytes, group, world_size, adjacent=adjacent, comm=comm)
         self.opt = FusedClipAdam(model.parameters(), lr=lr, weight_decay=0.01 if optim == "adamw" else 0.0,
                                  decoupled=(optim == "adamw"), max_norm=1.0, grad_prescale=1.0 / world_size)
 
