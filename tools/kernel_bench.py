@@ -55,6 +55,37 @@ if "t5nn" in which:
     timeit("t5 NN M1M N256 K64 plain", lambda: ops.linear_dgrad(d, w2, out=out, t5=True),
            4 * (M * 64 + M * 256), 2.0 * M * 256 * 64)
     del d, v, out
+if "t5h" in which:
+    # fp16 storage of the LeFF tensors: linear1 forward with a float16 C, linear2 data gradient with the
+    # float16 gelu' multiplier
+    x, w, b = rnd(M, 64), rnd(256, 64), rnd(256)
+    outh = torch.empty(M, 256, device=dev, dtype=torch.float16)
+    timeit("t5 NT M1M N256 K64 bias -> fp16 C", lambda: ops.linear(x, w, b, out=outh, t5=True),
+           4 * (M * 64 + 256 * 64) + 2 * M * 256, 2.0 * M * 256 * 64)
+    d, w2 = rnd(M, 64), rnd(64, 256)
+    vh = torch.rand(M, 256, device=dev).half()
+    out = torch.empty(M, 256, device=dev)
+    timeit("t5 NN M1M N256 K64 mul fp16 R", lambda: ops.linear_dgrad(d, w2, mul_by=vh, out=out, t5=True),
+           4 * (M * 64 + M * 256) + 2 * M * 256, 2.0 * M * 256 * 64)
+    del x, outh, d, vh, out
+if "dwh" in which:
+    B, H, Ch = 16, 256, 256
+    uh = torch.randn(B * H * H, Ch, device=dev).half()
+    wt, bs = torch.randn(Ch, 1, 3, 3, device=dev) * 0.3, torch.randn(Ch, device=dev)
+    n = B * H * H * Ch
+    timeit("dwconv fwd fp16 u/v B16 H256 Ch256", lambda: ops.dwconv_gelu_fwd_half(uh, wt, bs, B, H, H, Ch), n * 8, 18.0 * n)
+    dv = torch.randn(B * H * H, Ch, device=dev)
+    du = torch.empty(B * H * H, Ch, device=dev)
+    timeit("dwconv bwd fp16 u B16 H256 Ch256", lambda: ops.dwconv_gelu_bwd(dv, uh, wt, B, H, H, Ch, du=du), n * 10, 36.0 * n)
+    del uh, dv, du
+if "mdta" in which:
+    B, L, heads, c = 8, 65536, 1, 32
+    C = heads * c
+    qkv = torch.randn(B * L, 3 * C, device=dev)
+    A = torch.softmax(torch.randn(B, heads, c, c, device=dev), -1)
+    timeit("mdta gram B8 L65536 C32", lambda: ops.mdta_gram(qkv, 0, qkv, C, B, L, heads, c, want_sq=True), 8 * B * L * C, 2.0 * B * L * C * c)
+    timeit("mdta apply B8 L65536 C32", lambda: ops.mdta_apply(qkv, 2 * C, A, B, L, heads, c), 8 * B * L * C, 2.0 * B * L * C * c)
+    del qkv
 if "t5tn" in which:
     du, y = rnd(M, 256), rnd(M, 64)
     timeit("t5 TN M256 N64 K1M", lambda: ops.linear_wgrad(du, y, want_bias=False, t5=True), 4 * (M * 320), 2.0 * M * 256 * 64)

@@ -1,11 +1,12 @@
 """Turn the ncu outputs of tools/gpu_round.sh into the small, committed summaries under profiles/:
   launches CSV (gpu__time_duration per launch)  ->  per-kernel share table (JSON)
   --set full report (.ncu-rep)                  ->  per-kernel DRAM traffic / throughput / occupancy (JSON)
-usage: python tools/ncu_summarize.py TAG        (reads gpurun_out/*_TAG.*, writes profiles/r1_*_TAG.json)"""
+usage: python tools/ncu_summarize.py TAG [PREFIX] (reads gpurun_out/*_TAG.*, writes profiles/PREFIX_ncu_summary_TAG.json; PREFIX default r2)"""
 import collections, csv, json, os, subprocess, sys
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 tag = sys.argv[1]
+prefix = sys.argv[2] if len(sys.argv) > 2 else "r2"
 out = {}
 
 lp = os.path.join(ROOT, "gpurun_out", f"launches_{tag}.csv")
@@ -42,6 +43,7 @@ if os.path.exists(rp):
             "launch__registers_per_thread": "regs", "launch__grid_size": "grid", "launch__block_size": "block",
             "sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_active": "tensor_pipe_pct",
             "smsp__inst_executed.sum": "warp_instructions"}
+    idx = {k: hdr.index(k) for k in want if k in hdr}
     caps = []
     for r in rows[2:]:
         e = {"kernel": r[hdr.index("Kernel Name")].split("(")[0].replace("<unnamed>::", "").replace("void ", "")}
@@ -58,6 +60,6 @@ if os.path.exists(rp):
                                        "python tools/kernel_bench.py t5nn t5nt dwf dwb attnf attnb lnb", "captures": caps}
 
 os.makedirs(os.path.join(ROOT, "profiles"), exist_ok=True)
-dst = os.path.join(ROOT, "profiles", f"r1_ncu_summary_{tag}.json")
+dst = os.path.join(ROOT, "profiles", f"{prefix}_ncu_summary_{tag}.json")
 json.dump(out, open(dst, "w"), indent=1)
 print("wrote", dst)
