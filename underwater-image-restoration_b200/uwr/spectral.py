@@ -43,10 +43,10 @@ class MDTA(nn.Module):
         qkv = fn.PlainDWConvFn.apply(qkv, self.qkv_conv.weight, B, H, W)
         # channel attention for the whole batch: Gram GEMMs on strided views, batched normalise / softmax
         out, attn = fn.MDTAAttnFn.apply(qkv, self.temperature, B, L, C, self.num_heads)        # attn @ v
-        out = fn.linear(out, _w2(self.project_out))
+        out = fn.linear(out, _w2(self.project_out), rounded=True)       # uwr_mdta_apply rounds its output to TF32
         kvf = fn.PlainDWConvFn.apply(fn.linear(out, _w2(self.kv)), self.kv_conv.weight, B, H, W)
         outf = fn.ChannelApplyFn.apply(kvf, attn, C, B, L)                                       # attn @ vf
-        return fn.linear(outf, _w2(self.project_outf))
+        return fn.linear(outf, _w2(self.project_outf), rounded=True)
 
 
 class GDFN(nn.Module):
@@ -72,7 +72,7 @@ class GDFN(nn.Module):
             wdw = torch.cat([wdw[:h], z2, wdw[h:], z2], 0)
             wout = torch.cat([wout, wout.new_zeros(wout.shape[0], hp - h)], 1)
         t = fn.PlainDWConvFn.apply(fn.linear(y, win, None, rounded=True), wdw, B, H, W)
-        return fn.linear(fn.GeluMulFn.apply(t, hp), wout)
+        return fn.linear(fn.GeluMulFn.apply(t, hp), wout, rounded=True)   # the gate kernel rounds its output
 
 
 class TransformerBlock(nn.Module):

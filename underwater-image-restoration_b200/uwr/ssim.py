@@ -97,8 +97,13 @@ class MsSsimFn(torch.autograd.Function):
         with torch.enable_grad():
             leaves = [v.detach().requires_grad_() for v in vals]
             wts = _weights(X)
-            stack = torch.relu(torch.stack(leaves, 0))                       # (5, planes)
-            res = torch.prod(stack ** wts.view(-1, 1), 0).mean()
+            # product of powers written as explicit multiplications: torch.prod's backward counts zeros with .item(),
+            # a host sync that invalidates a CUDA-graph capture
+            res = None
+            for s, v in enumerate(leaves):
+                term = torch.relu(v) ** wts[s]
+                res = term if res is None else res * term
+            res = res.mean()
         if want:
             ctx.graph = (leaves, res)
             ctx.pyr = pyr
