@@ -52,7 +52,10 @@ class GraphedTrainStep:
         # the warm-up's activations sit in the caching allocator's default pool; the capture allocates the same amount
         # again in the graph's private pool.  Returning the cached blocks first halves the peak (batch 64 per GPU, BASELINE
         # config 4 at 2 GPUs, needs it).
+        # (the last warm-up step's autograd graph is cyclic garbage until Python's collector runs: collect it first)
+        import gc
         torch.cuda.synchronize()
+        gc.collect()
         torch.cuda.empty_cache()
         self.graph = torch.cuda.CUDAGraph()
         self.graph_opt = None
