@@ -141,6 +141,7 @@ def run_reference_gpu(args):
     import torch
     dev = torch.device("cuda", int(os.environ.get("LOCAL_RANK", "0")))
     torch.cuda.set_device(dev)
+    args.batch = args.batch or 16
     res = {}
     for name, tf32 in (("fp32", False), ("tf32", True)):
         rate, ms = gpu_eager_step_rate(dev, args.batch, args.size, args.steps, max(args.warmup, 3), tf32)
@@ -238,7 +239,8 @@ def run_ours(args):
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     dev = torch.device("cuda", local)
-    B, S = args.batch, args.size
+    # per-GPU batch: 16 on one GPU; N >= 2 GPUs run BASELINE config 4 as written, global batch 128 (64 / 32 / 16 per GPU)
+    B, S = (args.batch if args.batch > 0 else (16 if world == 1 else max(1, 128 // world))), args.size
 
     torch.manual_seed(1234)
     model = uwr.AST(img_size=S).to(dev)
@@ -272,8 +274,14 @@ def run_ours(args):
             dist.all_reduce(ms, op=dist.ReduceOp.MAX)
         return ms.item()
 
-    # The step is replayed from CUDA graphs (uwr.graph.GraphedTrainStep): one graph on a single GPU; with
-    # N > 1 forward+backward and clip+Adam are two graphs around the eager NCCL bucket all-reduces.
+    # kernel launches of one step, counted on an eager step BEFORE the graph exists (a replay re-issues the same
+    # kernels; an eager step next to the graph's private memory pool would double the footprint at batch 64)
+    l0 = ops.launch_count()
+    step(raw_d, ref_d)
+    launches_per_step = ops.launch_count() - l0
+
+    # The step is replayed from ONE CUDA graph (uwr.graph.GraphedTrainStep); with N > 1 the raw NCCL bucket all-reduces
+    # are captured inside it (--torch-allreduce: two graphs around eager torch.distributed all-reduces instead).
     use_graph = not args.no_graph
     graphed = None
     if use_graph:
@@ -311,9 +319,7 @@ def run_ours(args):
     if rank == 0:
         sampler.start()
     ms = timed(step_resident, args.steps)
-    l0 = ops.launch_count()
-    step_eager()  # launches per step are counted on one eager step (a graph replay re-issues the same kernels)
-    launches = (ops.launch_count() - l0) * args.steps
+    launches = launches_per_step * args.steps
     clocks = sampler.stop() if rank == 0 else None
     if graphed is not None:
         graphed.prefetch(raw_h, ref_h)               # batch of the first e2e step
@@ -323,7 +329,13 @@ def run_ours(args):
     value = world * B * args.steps / (ms / 1e3)
     e2e = world * B * args.steps / (ms_e2e / 1e3)
 
-    # ---- roofline of the dominant kernel: one extra instrumented step (CUDA events per launch) ----
+    # ---- roofline of the dominant kernel: one extra instrumented EAGER step (CUDA events per launch), after the graph
+    # and its memory pool are gone ----
+    import gc
+    graphed = None
+    gc.collect()
+    torch.cuda.synchronize()
+    torch.cuda.empty_cache()
     roofline, table = None, None
     if rank != 0:
         step_eager()  # every rank takes part in the instrumented step's all-reduces
@@ -351,7 +363,7 @@ def run_ours(args):
             roofline = {"bound": "hbm", "achieved": gbs, "peak": hbm, "unit": "GB/s", "frac": gbs / hbm}
         total_ms = sum(r["ms_total"] for r in table)
         traffic, traffic_note = None, None
-        tp = os.path.join(ROOT, "profiles", "r1_roofline_traffic.json")
+        tp = os.path.join(ROOT, "profiles", "r2_roofline_traffic.json")
         if os.path.exists(tp):  # dram__bytes_read.sum + dram__bytes_write.sum of one committed `ncu --set full` capture
             with open(tp) as f:
                 ent = json.load(f).get(fam_name)
@@ -385,7 +397,6 @@ def run_ours(args):
     gpu_eager = None
     if rank == 0 and world == 1 and not args.no_gpu_eager:
         # the kernel bar: same step, same batch, PyTorch-eager on this GPU (after our own timing, graph pools released)
-        graphed = None
         torch.cuda.empty_cache()
         try:
             gpu_eager = {}
@@ -401,13 +412,15 @@ def run_ours(args):
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
             "warmup": max(args.warmup, 3), "ms_per_step": ms / args.steps, "higher_is_better": True,
-            "scaling": "weak", "vs_baseline": None, "dtype": "tf32", "data": "synthetic",
+            "scaling": "weak" if B == 16 else "strong", "vs_baseline": None, "dtype": "tf32", "data": "synthetic",
             "config": {"workload": f"AST {S}x{S} train step: fwd + L1 + bwd + clip_grad_norm(1.0) + Adam, "
                                    f"train mode (drop_path 0.1), batch {B}/GPU, global batch {B * world}",
                        "batch_per_gpu": B, "global_batch": B * world, "image": S,
                        "parallelism": f"dp{world}", "cuda_graph": bool(use_graph), "l2": "working set per step >> 126 MB L2 (no flush needed)",
-                       "storage": "fp32 activations/weights, TF32 tensor-core products (3xTF32 inside attention "
-                                  "scores), fp32 accumulate"},
+                       "scaling_note": "N = 1: 16 images; N >= 2: global batch 128 (BASELINE config 4), i.e. 64 / 32 / 16 per GPU",
+                       "storage": "fp32 residual stream / weights / gradients, fp16 for the LeFF tensors u and gelu'(v) "
+                                  "(10-bit mantissa = what a TF32 operand keeps), TF32 tensor-core products (3xTF32 inside "
+                                  "attention), fp32 accumulate"},
             "e2e": {"value": e2e, "unit": UNIT, "h2d_bytes_per_step": 2 * raw_h.numel() * 4 * world,
                     "d2h_bytes_per_step": 4 * world, "ms_per_step": ms_e2e / args.steps},
             "gpu_launches": int(launches),
@@ -426,7 +439,8 @@ def main():
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
-    ap.add_argument("--batch", type=int, default=16, help="images per GPU per step")
+    ap.add_argument("--batch", type=int, default=0,
+                    help="images per GPU per step (default: 16 on one GPU, 128 / N on N >= 2 GPUs = BASELINE config 4)")
     ap.add_argument("--size", type=int, default=256)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference", "reference-gpu"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
