@@ -151,6 +151,10 @@ typedef struct {
     const float* w_param;    /* (2,) raw parameter; NULL => plain softmax attention */
     int B, H, W, heads, head_dim, shift;
     float scale;
+    /* q, k, v (and dout in the backward) are exactly TF32-representable (their producing GEMM epilogues rounded them,
+     * uwr_gemm_desc.round_out): the products are then exact in one tensor-core pass and the kernels skip the 3xTF32
+     * hi/lo compensation they otherwise apply to full-fp32 operands. */
+    int operands_rounded;
 } uwr_attn_desc;
 
 int uwr_window_attn_fwd(const uwr_attn_desc* d, float* out, long long ld_out, uwr_stream_t stream);

@@ -189,6 +189,35 @@ def test_window_attention_fwd_bwd(ops, B, H, heads, hd, shift, sparse):
         assert rel_l2(dw, wd.grad) < 5 * TOL_TF32
 
 
+@pytest.mark.parametrize("B,H,heads,hd,shift,t5", [(2, 16, 2, 32, 0, False), (1, 32, 2, 32, 4, False), (2, 16, 4, 16, 4, False),
+                                                   (1, 16, 1, 64, 0, False), (2, 16, 2, 32, 4, True), (1, 32, 4, 32, 0, True)])
+def test_window_attention_exact_tf32_operands(ops, B, H, heads, hd, shift, t5):
+    """operands_rounded = 1: q, k, v, dout arrive as exact TF32 values (rounded by the producing GEMM epilogues), the
+    kernels then run ONE tensor-core pass per product — exact products, so the bounds of the 3xTF32 path still hold
+    against fp64 math on the same (rounded) operands.  t5: forward through the tcgen05 / TMA kernel."""
+    W = H
+    C = heads * hd
+    qkv = ops.scale_round(_r(B * H * W, 3 * C, seed=1), 3 * C)
+    table = _r(225, heads, seed=2, scale=0.5)
+    w = torch.tensor([0.3, -0.2]).cuda()
+    scale = hd ** -0.5
+    ops.set_attn_tcgen05(t5)
+    try:
+        o = ops.window_attn_fwd(qkv, 0, qkv, C, 2 * C, table, w, B, H, W, heads, hd, shift, scale, rounded=True)
+    finally:
+        ops.set_attn_tcgen05(False)
+    qd, td, wd = qkv.double().requires_grad_(), table.double().requires_grad_(), w.double().requires_grad_()
+    ref = _attn_ref(qd, td, wd, B, H, W, heads, shift, True)
+    assert rel_l2(o, ref) < TOL_TF32
+    do = ops.scale_round(_r(B * H * W, C, seed=3), C)
+    ref.backward(do.double())
+    dqkv, _, dtable, dw = ops.window_attn_bwd(do, qkv, 0, qkv, C, 2 * C, table, w, B, H, W, heads, hd, shift, scale,
+                                              rounded=True)
+    assert rel_l2(dqkv, qd.grad) < 2 * TOL_TF32
+    assert rel_l2(dtable, td.grad) < 2 * TOL_TF32
+    assert rel_l2(dw, wd.grad) < 5 * TOL_TF32
+
+
 # ------------------------------------------------------------------------------------ dwconv+GELU
 @pytest.mark.parametrize("B,H,Ch,mode", [(2, 16, 64, 0), (1, 32, 128, 0), (2, 24, 48, 0), (1, 16, 64, 1),
                                          (1, 40, 32, 1)])

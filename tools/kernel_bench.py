@@ -112,17 +112,20 @@ if "attnb" in which or "attnf" in which:
     w = torch.ones(2, device=dev)
     tiles = B * (H // 8) ** 2 * heads
     if "attnf" in which:
-        for t5 in (False, True):
-            ops.set_attn_tcgen05(t5)
-            timeit(f"attn fwd tiles32768 hd32 {'tcgen05' if t5 else 'mma.sync'}",
-                   lambda: ops.window_attn_fwd(qkv, 0, qkv, C, 2 * C, table, w, B, H, H, heads, hd, 4, hd ** -0.5),
-                   tiles * 4 * 64 * hd * 4, tiles * 4.0 * 64 * 64 * hd)
+        for rounded in (False, True):     # True: operands are exact TF32 values -> one tensor-core pass per product
+            for t5 in (False, True):
+                ops.set_attn_tcgen05(t5)
+                timeit(f"attn fwd tiles32768 hd32 {'tcgen05' if t5 else 'mma.sync'}{' exact-tf32 operands' if rounded else ''}",
+                       lambda: ops.window_attn_fwd(qkv, 0, qkv, C, 2 * C, table, w, B, H, H, heads, hd, 4, hd ** -0.5, rounded=rounded),
+                       tiles * 4 * 64 * hd * 4, tiles * 4.0 * 64 * 64 * hd)
         ops.set_attn_tcgen05(False)
     if "attnb" in which:
         do = torch.randn(B * H * H, C, device=dev)
         dq = torch.empty_like(qkv)
-        timeit("attn bwd tiles32768 hd32", lambda: ops.window_attn_bwd(do, qkv, 0, qkv, C, 2 * C, table, w, B, H, H, heads, hd, 4, hd ** -0.5, dq_buf=dq, dkv_buf=dq),
-               tiles * 7 * 64 * hd * 4, tiles * 10.0 * 64 * 64 * hd)
+        for rounded in (False, True):
+            timeit(f"attn bwd tiles32768 hd32{' exact-tf32 operands' if rounded else ''}",
+                   lambda: ops.window_attn_bwd(do, qkv, 0, qkv, C, 2 * C, table, w, B, H, H, heads, hd, 4, hd ** -0.5, dq_buf=dq, dkv_buf=dq, rounded=rounded),
+                   tiles * 7 * 64 * hd * 4, tiles * 10.0 * 64 * 64 * hd)
         del do, dq
     del qkv
 if "lnb" in which:

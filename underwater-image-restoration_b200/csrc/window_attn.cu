@@ -33,7 +33,8 @@ struct AttnParams {
     float scale;
     int nWx, nW;  // windows per row / per image
     int rnd;      // round outputs to TF32 (they are GEMM operands)
-    int x3;       // error-compensated 3xTF32 on the cancelling products (default); 0 = single pass (experiment)
+    int x3;       // 1: full-fp32 operands, error-compensated 3xTF32 on the cancelling products; 0: operands are exact TF32
+                  //    values (uwr_attn_desc.operands_rounded), one pass is exact
 };
 
 __device__ __forceinline__ long long token_row(const AttnParams& p, int b, int wy, int wx, int n) {
@@ -722,8 +723,9 @@ attn_fwd_t5_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_consta
         mbar_wait(bar_load, ph_load);
         ph_load ^= 1;
         T5A_STAMP(1);
-        // lo = x - trunc(x) for Q and K (3xTF32), V rounded to nearest in place (single-pass P V)
-        {
+        // lo = x - trunc(x) for Q and K (3xTF32), V rounded to nearest in place (single-pass P V); nothing to do when
+        // the operands arrive as exact TF32 values
+        if (p.x3) {
             const float4* q4 = reinterpret_cast<const float4*>(Qhi);
             const float4* k4 = reinterpret_cast<const float4*>(Khi);
             float4* ql = reinterpret_cast<float4*>(Qlo);
@@ -751,13 +753,13 @@ attn_fwd_t5_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_consta
         if (tid == 0) {
             tc_fence_after();
             const uint32_t qh = smem_u32(Qhi), kh = smem_u32(Khi), qlw = smem_u32(Qlo), klw = smem_u32(Klo);
-#pragma unroll
-            for (int pass = 0; pass < 3; ++pass) {
+            const int pass0 = p.x3 ? 0 : 2;   // exact TF32 operands: only the hi * hi pass
+            for (int pass = pass0; pass < 3; ++pass) {
                 const uint32_t a = pass == 0 ? qlw : qh, bb = pass == 1 ? klw : kh;
 #pragma unroll
                 for (int k8 = 0; k8 < 4; ++k8)
                     umma_tf32(tmem_base, make_smem_desc(a + k8 * 32, 16, 1024, 2), make_smem_desc(bb + k8 * 32, 16, 1024, 2),
-                              IDESC_S, (pass > 0 || k8 > 0) ? 1u : 0u);
+                              IDESC_S, (pass > pass0 || k8 > 0) ? 1u : 0u);
             }
             umma_commit(bar_mma);
         }
@@ -920,8 +922,7 @@ int fill_params(const uwr_attn_desc* d, AttnParams& p, const char* who) {
     p.B = d->B; p.H = d->H; p.W = d->W; p.heads = d->heads; p.shift = d->shift; p.scale = d->scale;
     p.nWx = d->W / WIN; p.nW = (d->H / WIN) * (d->W / WIN);
     p.rnd = uwr_round_outputs();
-    static const int x3_env = [] { const char* e = getenv("UWR_ATTN_X3"); return e ? atoi(e) : 1; }();
-    p.x3 = x3_env;
+    p.x3 = d->operands_rounded ? 0 : 1;
     return 0;
 }
 

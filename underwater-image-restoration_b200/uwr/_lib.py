@@ -63,7 +63,7 @@ class AttnDesc(C.Structure):
         ("kv", c_fp), ("ld_kv", c_ll), ("k_off", c_int), ("v_off", c_int),
         ("bias_table", c_fp), ("w_param", c_fp),
         ("B", c_int), ("H", c_int), ("W", c_int), ("heads", c_int), ("head_dim", c_int),
-        ("shift", c_int), ("scale", c_f),
+        ("shift", c_int), ("scale", c_f), ("operands_rounded", c_int),
     ]
 
 

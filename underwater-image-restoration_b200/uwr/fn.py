@@ -143,7 +143,7 @@ class AttnFn(torch.autograd.Function):
         if xkv is None:
             if fast:
                 w, bias = ops.packed_qkv(wq, bq, wkv, bkv)
-                qkv = ops.linear(xq, w, bias, t5=True)
+                qkv = ops.linear(xq, w, bias, t5=True, round_out=True)
             else:
                 qkv = ops.linear(xq, wq, bq, weight2=wkv, bias2=bkv)
             q_buf, q_off, kv_buf, k_off, v_off = qkv, 0, qkv, Cc, 2 * Cc
@@ -151,13 +151,14 @@ class AttnFn(torch.autograd.Function):
             xkv = _c(xkv)
             if fast:
                 xkv = ops.scale_round(xkv, xkv.shape[1])
-                q_buf = ops.linear(xq, ops.rounded_weight(wq), bq, t5=True)
-                kv_buf = ops.linear(xkv, ops.rounded_weight(wkv), bkv, t5=True)
+                q_buf = ops.linear(xq, ops.rounded_weight(wq), bq, t5=True, round_out=True)
+                kv_buf = ops.linear(xkv, ops.rounded_weight(wkv), bkv, t5=True, round_out=True)
             else:
                 q_buf = ops.linear(xq, wq, bq)
                 kv_buf = ops.linear(xkv, wkv, bkv)
             q_off, k_off, v_off = 0, 0, Cc
-        o = ops.window_attn_fwd(q_buf, q_off, kv_buf, k_off, v_off, table, wparam, B, H, W, heads, hd, shift, scale)
+        o = ops.window_attn_fwd(q_buf, q_off, kv_buf, k_off, v_off, table, wparam, B, H, W, heads, hd, shift, scale,
+                                rounded=fast)
         y = ops.linear(o, ops.rounded_weight(wp), bp, t5=True)
         ctx.save_for_backward(xq, xkv, wq, wkv, table, wparam, wp, q_buf, kv_buf, o, bq, bkv)
         ctx.meta = (B, H, W, heads, hd, shift, scale, Cc, bq is not None, fast)
@@ -171,7 +172,7 @@ class AttnFn(torch.autograd.Function):
         d = _c(dy)
         if fast:   # rounded cotangent + proj bias gradient in one pass; o was rounded by the attention kernel
             d, dbp = ops.scale_round_colsum(d, Cc)
-            d_o = ops.linear_dgrad(d, ops.rounded_weight(wp), t5=True)
+            d_o = ops.linear_dgrad(d, ops.rounded_weight(wp), t5=True, round_out=True)
             dwp, _ = ops.linear_wgrad(d, o, want_bias=False, t5=True)
         else:
             d_o = ops.linear_dgrad(d, wp)
@@ -179,7 +180,7 @@ class AttnFn(torch.autograd.Function):
         cross = xkv is not None
         q_off, k_off, v_off = (0, 0, Cc) if cross else (0, Cc, 2 * Cc)
         dq_buf, dkv_buf, dtable, dw = ops.window_attn_bwd(d_o, q_buf, q_off, kv_buf, k_off, v_off, table, wparam,
-                                                          B, H, W, heads, hd, shift, scale)
+                                                          B, H, W, heads, hd, shift, scale, rounded=fast)
         if fast:   # dq / dk / dv leave the attention kernel TF32-rounded; xq / xkv were saved rounded
             if cross:
                 dxq = ops.linear_dgrad(dq_buf, ops.rounded_weight(wq), t5=True)

@@ -208,7 +208,7 @@ def linear(x2d, weight, bias=None, *, weight2=None, bias2=None, residual=None, r
 
 
 def linear_dgrad(dy2d, weight, *, weight2=None, rowscale=None, rows_per_group=0, out=None, dgelu_of=None,
-                 mul_by=None, t5=False):
+                 mul_by=None, t5=False, round_out=False):
     """dx = (s*dy) [W;W2]   (dy: (M,N), W: (N1,K), W2: (N2,K)); dgelu_of=v multiplies by gelu'(v),
     mul_by=g multiplies elementwise by g (a stored gelu'(v))."""
     M, N = dy2d.shape
@@ -221,7 +221,7 @@ def linear_dgrad(dy2d, weight, *, weight2=None, rowscale=None, rows_per_group=0,
          epilogue=EPI_MUL_DGELU if dgelu_of is not None else (EPI_MUL if mul_by is not None else EPI_NONE),
          R=dgelu_of if dgelu_of is not None else mul_by,
          ldr=(dgelu_of if dgelu_of is not None else mul_by).stride(0) if (dgelu_of is not None or mul_by is not None) else 0,
-         t5=t5)
+         t5=t5, round_out=round_out)
     return out
 
 
@@ -488,8 +488,9 @@ def layernorm_bwd(dy2d, x2d, gamma, mean, rstd, dres=None, dgamma_out=None, dbet
 
 
 # --------------------------------------------------------------------------------------------
-def _attn_desc(q_buf, q_off, kv_buf, k_off, v_off, table, w_param, B, H, W, heads, head_dim, shift, scale):
+def _attn_desc(q_buf, q_off, kv_buf, k_off, v_off, table, w_param, B, H, W, heads, head_dim, shift, scale, rounded=False):
     d = AttnDesc()
+    d.operands_rounded = int(bool(rounded) and _PASSES == 1)
     d.q, d.ld_q, d.q_off = _ptr(q_buf), q_buf.stride(0), q_off
     d.kv, d.ld_kv, d.k_off, d.v_off = _ptr(kv_buf), kv_buf.stride(0), k_off, v_off
     d.bias_table, d.w_param = _ptr(table), _ptr(w_param)
@@ -497,9 +498,11 @@ def _attn_desc(q_buf, q_off, kv_buf, k_off, v_off, table, w_param, B, H, W, head
     return d
 
 
-def window_attn_fwd(q_buf, q_off, kv_buf, k_off, v_off, table, w_param, B, H, W, heads, head_dim, shift, scale):
-    """q_buf/kv_buf: 2-D token matrices (B*H*W, ld). Returns O (B*H*W, heads*head_dim)."""
-    d = _attn_desc(q_buf, q_off, kv_buf, k_off, v_off, table, w_param, B, H, W, heads, head_dim, shift, scale)
+def window_attn_fwd(q_buf, q_off, kv_buf, k_off, v_off, table, w_param, B, H, W, heads, head_dim, shift, scale,
+                    rounded=False):
+    """q_buf/kv_buf: 2-D token matrices (B*H*W, ld). Returns O (B*H*W, heads*head_dim).
+    rounded: q, k, v are exact TF32 values (producing GEMM ran with round_out) -> single exact tensor-core pass."""
+    d = _attn_desc(q_buf, q_off, kv_buf, k_off, v_off, table, w_param, B, H, W, heads, head_dim, shift, scale, rounded)
     out = _empty((B * H * W, heads * head_dim), q_buf)
     tiles = B * (H // 8) * (W // 8) * heads
     _run("uwr_window_attn_fwd", f"tiles{tiles} hd{head_dim} shift{shift}", tiles * 4 * 64 * head_dim * 4,
@@ -508,8 +511,9 @@ def window_attn_fwd(q_buf, q_off, kv_buf, k_off, v_off, table, w_param, B, H, W,
 
 
 def window_attn_bwd(dout, q_buf, q_off, kv_buf, k_off, v_off, table, w_param, B, H, W, heads, head_dim, shift,
-                    scale, dq_buf=None, dkv_buf=None, dtable_out=None, dw_out=None):
-    d = _attn_desc(q_buf, q_off, kv_buf, k_off, v_off, table, w_param, B, H, W, heads, head_dim, shift, scale)
+                    scale, dq_buf=None, dkv_buf=None, dtable_out=None, dw_out=None, rounded=False):
+    """rounded: q, k, v AND dout are exact TF32 values."""
+    d = _attn_desc(q_buf, q_off, kv_buf, k_off, v_off, table, w_param, B, H, W, heads, head_dim, shift, scale, rounded)
     if dq_buf is None:
         dq_buf = torch.empty_like(q_buf)
     if dkv_buf is None:
