@@ -158,10 +158,11 @@ typedef struct {
 } uwr_attn_desc;
 
 int uwr_window_attn_fwd(const uwr_attn_desc* d, float* out, long long ld_out, uwr_stream_t stream);
-/* head_dim 32 and shift in {0, 4}: uwr_set_attn_tcgen05(1) runs the forward on tcgen05 tensor cores (two
- * windows per 128-row MMA tile, Q/K/V by TMA, scores/outputs in TMEM).  Default 0 = the mma.sync kernel,
- * which is still faster on B200 (0.31 vs 0.34 ms at 32 768 tiles); both are parity-tested. */
-int uwr_set_attn_tcgen05(int on);
+/* Forward on the tcgen05 tensor cores (head_dim 32, shift in {0, 4}, an even number of windows per image: two
+ * windows per 128-row MMA tile, Q/K/V by TMA, scores / outputs in TMEM).  mode 0 = never, 1 = whenever eligible,
+ * 2 = auto (default): when d->operands_rounded, where it is the faster kernel (0.279 vs 0.285 ms at 32 768 tiles;
+ * with full-fp32 operands mma.sync wins, 0.316 vs 0.347 ms).  Both are parity-tested. */
+int uwr_set_attn_tcgen05(int mode);
 size_t uwr_window_attn_bwd_workspace_bytes(const uwr_attn_desc* d);
 /* dq/dk/dv are written with the same (ld, offset) addressing as q/k/v into dq_buf/dkv_buf.
  * dbias_table (225,heads) and dw (2,) are overwritten. */

@@ -205,7 +205,7 @@ def test_window_attention_exact_tf32_operands(ops, B, H, heads, hd, shift, t5):
     try:
         o = ops.window_attn_fwd(qkv, 0, qkv, C, 2 * C, table, w, B, H, W, heads, hd, shift, scale, rounded=True)
     finally:
-        ops.set_attn_tcgen05(False)
+        ops.set_attn_tcgen05("auto")
     qd, td, wd = qkv.double().requires_grad_(), table.double().requires_grad_(), w.double().requires_grad_()
     ref = _attn_ref(qd, td, wd, B, H, W, heads, shift, True)
     assert rel_l2(o, ref) < TOL_TF32
@@ -215,7 +215,8 @@ def test_window_attention_exact_tf32_operands(ops, B, H, heads, hd, shift, t5):
                                               rounded=True)
     assert rel_l2(dqkv, qd.grad) < 2 * TOL_TF32
     assert rel_l2(dtable, td.grad) < 2 * TOL_TF32
-    assert rel_l2(dw, wd.grad) < 5 * TOL_TF32
+    # dw: two scalars, w0 * (g1 - (w0 g1 + w1 g2)) over every score of the tensor — the most cancelling sum there is
+    assert rel_l2(dw, wd.grad) < 1e-2
 
 
 # ------------------------------------------------------------------------------------ dwconv+GELU
@@ -574,7 +575,7 @@ def test_window_attention_fwd_tcgen05_vs_mma_sync(ops, B, H, heads, shift, spars
         ops.set_attn_tcgen05(True)
         o_t5 = ops.window_attn_fwd(*args)
     finally:
-        ops.set_attn_tcgen05(False)   # library default
+        ops.set_attn_tcgen05("auto")   # library default
     torch.cuda.synchronize()
     ref = _attn_ref(qkv.double(), table.double(), (w if sparse else torch.zeros(2).cuda()).double(), B, H, W, heads, shift, sparse)
     assert rel_l2(o_t5, ref) < TOL_TF32

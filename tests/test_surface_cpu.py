@@ -70,7 +70,7 @@ def test_error_paths_return_codes_not_crashes(build_lib):
     assert f["uwr_layernorm_bwd_ds_workspace_bytes"](1 << 20, 64) > 0
     assert f["uwr_layernorm_bwd_ds"](*([None] * 10), 1, None, None, None, 1024, 64, None) == -1
     assert f["uwr_dft_workspace_bytes"](2, 16, 16, 32) == 2 * 2 * 16 * 16 * 32 * 8
-    assert f["uwr_set_attn_tcgen05"](0) == 0
+    assert f["uwr_set_attn_tcgen05"](0) == 0 and f["uwr_set_attn_tcgen05"](2) == 0     # back to the default (auto)
 
 
 def test_registry_surface():

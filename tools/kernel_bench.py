@@ -118,7 +118,7 @@ if "attnb" in which or "attnf" in which:
                 timeit(f"attn fwd tiles32768 hd32 {'tcgen05' if t5 else 'mma.sync'}{' exact-tf32 operands' if rounded else ''}",
                        lambda: ops.window_attn_fwd(qkv, 0, qkv, C, 2 * C, table, w, B, H, H, heads, hd, 4, hd ** -0.5, rounded=rounded),
                        tiles * 4 * 64 * hd * 4, tiles * 4.0 * 64 * 64 * hd)
-        ops.set_attn_tcgen05(False)
+        ops.set_attn_tcgen05("auto")
     if "attnb" in which:
         do = torch.randn(B * H * H, C, device=dev)
         dq = torch.empty_like(qkv)

@@ -862,11 +862,12 @@ attn_fwd_t5_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_consta
     }
 }
 
-// uwr_set_attn_tcgen05.  Off by default: measured on B200 (32 768 tiles, head_dim 32) the tcgen05 kernel takes
-// 0.34 ms against 0.31 ms for the mma.sync kernel — each item is one serial chain TMA -> lo split -> MMA -> softmax ->
-// MMA -> store (~8.9 k cycles) and only two items fit an SM (256 TMEM columns, 109 KB smem each), so it is
-// latency-bound (tensor pipe 15 % busy).  See DESIGN.md §8.
-int g_attn_t5 = 0;
+// uwr_set_attn_tcgen05: 0 = never, 1 = whenever the shape is eligible, 2 = auto (default): when the operands arrive as
+// exact TF32 values (uwr_attn_desc.operands_rounded — the training / inference path of the models).  Measured on B200
+// (32 768 tiles, head_dim 32): with full-fp32 operands the tcgen05 kernel needs the lo split and three S passes and
+// takes 0.347 ms against 0.316 ms for mma.sync; with exact TF32 operands it is one pass, no split: 0.279 ms against
+// 0.285 ms.  Each item is still one serial chain TMA -> MMA -> softmax -> MMA -> store with two items per SM.
+int g_attn_t5 = 2;
 
 int launch_fwd_t5(const AttnParams& p, float* out, long long ld_out, cudaStream_t stream) {
     CUtensorMap mq, mk, mv;
@@ -962,7 +963,8 @@ extern "C" int uwr_window_attn_fwd(const uwr_attn_desc* d, float* out, long long
     if (int rc = fill_params(d, p, "uwr_window_attn_fwd")) return rc;
     UWR_REQUIRE(out && ld_out % 2 == 0, "uwr_window_attn_fwd: bad output");
     // tcgen05 / TMA path: two windows per 128-row MMA tile
-    if (g_attn_t5 && d->head_dim == 32 && d->heads <= T5A_MAXH && (d->shift == 0 || d->shift == 4) && p.nW % 2 == 0 &&
+    const bool want_t5 = g_attn_t5 == 1 || (g_attn_t5 == 2 && d->operands_rounded);
+    if (want_t5 && d->head_dim == 32 && d->heads <= T5A_MAXH && (d->shift == 0 || d->shift == 4) && p.nW % 2 == 0 &&
         ld_out % 4 == 0 &&
         (((uintptr_t)d->q | (uintptr_t)d->kv | (uintptr_t)out) & 15) == 0)
         return launch_fwd_t5(p, out, ld_out, stream);
@@ -983,8 +985,8 @@ extern "C" int uwr_attn_t5_debug(long long* host_out) {
 }
 #endif
 
-extern "C" int uwr_set_attn_tcgen05(int on) {
-    g_attn_t5 = on ? 1 : 0;
+extern "C" int uwr_set_attn_tcgen05(int mode) {
+    g_attn_t5 = (mode == 2) ? 2 : (mode ? 1 : 0);
     return 0;
 }
 

@@ -29,9 +29,11 @@ def set_gemm_precision(mode):
     check(fn["uwr_set_gemm_precision"](_PASSES), "uwr_set_gemm_precision")
 
 
-def set_attn_tcgen05(on):
-    """window attention forward (head_dim 32): tcgen05/TMA kernel, or the (currently faster, default) mma.sync kernel."""
-    check(fn["uwr_set_attn_tcgen05"](int(bool(on))), "uwr_set_attn_tcgen05")
+def set_attn_tcgen05(mode):
+    """window attention forward (head_dim 32) on the tcgen05/TMA kernel: False / 0 = never, True / 1 = whenever the shape
+    is eligible, "auto" / 2 (library default) = when the operands are exact TF32 values (the models' path)."""
+    m = 2 if mode in ("auto", 2) else int(bool(mode))
+    check(fn["uwr_set_attn_tcgen05"](m), "uwr_set_attn_tcgen05")
 
 
 def fast_path():
