@@ -92,6 +92,9 @@ int uwr_gemm_tf32(const uwr_gemm_desc* d, uwr_stream_t stream);
  * weights via uwr_round_tf32_tensors.  `_supported` tells whether a descriptor is served here
  * (no segmented weights / colsum / k-scale; MN-major widths in multiples of 32). */
 int uwr_gemm_tcgen05_supported(const uwr_gemm_desc* d);
+/* Thread-block cluster pairs with TMA multicast of the B tile for the tensor-bound shapes (arithmetic intensity >= 96
+ * flop/B, N tile >= 128): 1 = auto (default), 0 = off. */
+int uwr_set_gemm_cluster(int mode);
 size_t uwr_gemm_tcgen05_workspace_bytes(int M, int N, int K, int a_km);
 int uwr_gemm_tcgen05(const uwr_gemm_desc* d, uwr_stream_t stream);
 

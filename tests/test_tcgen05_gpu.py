@@ -87,3 +87,35 @@ def test_t5_tn(M, N, K):
     out = torch.full((M, N), float("nan"), device="cuda")
     _t5(dy, x, out, M, N, K, M, N, N, a_km=True, b_nk=False)
     assert rel_l2(out, dy.double().t() @ x.double()) < 5e-6
+
+
+@pytest.mark.parametrize("lay,M,N,K", [("nt", 384, 512, 1024), ("nt", 4096, 2048, 512), ("nt", 1152, 256, 2048),
+                                       ("nn", 640, 1024, 2048), ("nn", 2048, 512, 1024), ("tn", 512, 2048, 16384),
+                                       ("tn", 384, 256, 65536), ("tn", 2048, 512, 4096)])
+def test_t5_cluster_multicast_matches_single_cta(lay, M, N, K):
+    """Tensor-bound shapes run as cluster pairs with TMA multicast of the B tile (gemm_tcgen05_kernel<..., CL = 2>):
+    bit-identical to the single-CTA kernel (same products, same accumulation order per tile) and within TF32-exact
+    distance of fp64, including an odd number of row tiles (the unpaired CTA computes on zero-filled rows)."""
+    from uwr import ops
+    bias = _r(N, seed=5) if lay == "nt" else None
+    if lay == "nt":
+        A, Bm = _r(M, K, seed=1), _r(N, K, seed=2, scale=0.1)
+        ref = A.double() @ Bm.double().t() + bias.double()
+        kw = dict(lda=K, ldb=K, ldc=N, bias=bias)
+    elif lay == "nn":
+        A, Bm = _r(M, K, seed=1), _r(K, N, seed=2, scale=0.1)
+        ref = A.double() @ Bm.double()
+        kw = dict(lda=K, ldb=N, ldc=N, b_nk=False)
+    else:
+        A, Bm = _r(K, M, seed=1), _r(K, N, seed=2, scale=0.1)
+        ref = A.double().t() @ Bm.double()
+        kw = dict(lda=M, ldb=N, ldc=N, a_km=True, b_nk=False)
+    outs = {}
+    for on in (True, False):
+        ops.set_gemm_cluster(on)
+        try:
+            outs[on] = _t5(A, Bm, torch.full((M, N), float("nan"), device="cuda"), M, N, K, **kw).clone()
+        finally:
+            ops.set_gemm_cluster(True)
+    assert torch.equal(outs[True], outs[False])
+    assert rel_l2(outs[True], ref) < 2e-5

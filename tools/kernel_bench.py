@@ -86,6 +86,26 @@ if "mdta" in which:
     timeit("mdta gram B8 L65536 C32", lambda: ops.mdta_gram(qkv, 0, qkv, C, B, L, heads, c, want_sq=True), 8 * B * L * C, 2.0 * B * L * C * c)
     timeit("mdta apply B8 L65536 C32", lambda: ops.mdta_apply(qkv, 2 * C, A, B, L, heads, c), 8 * B * L * C, 2.0 * B * L * C * c)
     del qkv
+if "t5big" in which:
+    # tensor-bound shapes of the bottleneck / dec0 stages: cluster pairs with B-tile multicast vs single CTAs
+    for (lay, Mm, Nn, Kk) in (("nt", 16384, 2048, 512), ("nt", 65536, 1024, 256), ("nn", 16384, 2048, 512), ("nn", 65536, 256, 1024),
+                              ("tn", 512, 2048, 16384), ("tn", 1024, 256, 65536)):
+        for on in (False, True):
+            ops.set_gemm_cluster(on)
+            if lay == "nt":
+                a, b_ = rnd(Mm, Kk), rnd(Nn, Kk)
+                o = torch.empty(Mm, Nn, device=dev)
+                f = lambda: ops.linear(a, b_, None, out=o, t5=True)
+            elif lay == "nn":
+                a, b_ = rnd(Mm, Kk), rnd(Kk, Nn)
+                o = torch.empty(Mm, Nn, device=dev)
+                f = lambda: ops.linear_dgrad(a, b_, out=o, t5=True)
+            else:
+                a, b_ = rnd(Kk, Mm), rnd(Kk, Nn)
+                f = lambda: ops.linear_wgrad(a, b_, want_bias=False, t5=True)
+            timeit(f"t5 {lay.upper()} M{Mm} N{Nn} K{Kk} {'cluster2+multicast' if on else 'single CTA'}", f,
+                   4.0 * (Mm * Kk + Kk * Nn + Mm * Nn), 2.0 * Mm * Nn * Kk, reps=20)
+    ops.set_gemm_cluster(True)
 if "t5tn" in which:
     du, y = rnd(M, 256), rnd(M, 64)
     timeit("t5 TN M256 N64 K1M", lambda: ops.linear_wgrad(du, y, want_bias=False, t5=True), 4 * (M * 320), 2.0 * M * 256 * 64)

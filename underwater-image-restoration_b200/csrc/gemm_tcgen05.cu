@@ -70,8 +70,13 @@ __host__ __device__ constexpr int t5_smem_bytes() {
     return t5_stages<BN>() * (TM * KC * 4 + BN * KC * 4) + 256 + BN * 4 + EPI_WARPS * 32 * EP_STRIDE * 4 + 1024;
 }
 
-// HF: fp16 storage flags, bit 0 = C is __half (EPI_NONE only), bit 1 = R is __half
-template <int BN, int LAY, int EPI, int HF = 0>
+// HF: fp16 storage flags, bit 0 = C is __half (EPI_NONE only), bit 1 = R is __half.
+// CL: thread-block cluster size along M (1 or 2).  With CL = 2 the two CTAs of a cluster work on neighbouring row
+// tiles of the SAME column tile: each TMA-loads half of the B tile and MULTICASTS it into both CTAs' shared memory, so
+// the L2 -> SM operand traffic per CTA and contraction chunk drops from A + B to A + B/2 (48 -> 32 KB at BN = 256) —
+// the tensor-bound shapes are limited by exactly that traffic.  A stage may only be refilled when BOTH CTAs' MMAs have
+// consumed it: every CTA's tcgen05.commit arrives on the stage's empty barrier in both CTAs (count CL).
+template <int BN, int LAY, int EPI, int HF = 0, int CL = 1>
 __global__ void __launch_bounds__(T5_THREADS, 1)
 gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapB,
                     const T5Params p) {
@@ -98,12 +103,17 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_const
     float* sstage = sbias + BN;  // [EPI_WARPS][32][EP_STRIDE] accumulator transposition buffers
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int items = p.tiles_m * p.tiles_n * p.splits;
+    // work items are enumerated per CLUSTER: (row-tile group, column tile, split); CTA `crank` takes row tile CL*g + crank
+    const int crank = CL > 1 ? (int)cluster_ctarank() : 0;
+    const int tiles_mg = (p.tiles_m + CL - 1) / CL;
+    const int items = tiles_mg * p.tiles_n * p.splits;
+    const int first_item = (int)blockIdx.x / CL, item_step = (int)gridDim.x / CL;
+    constexpr uint16_t CMASK = (uint16_t)((1u << CL) - 1u);
 
     if (threadIdx.x == 0) {
         for (int s = 0; s < STAGES; ++s) {
             mbar_init(&full_bar[s], 1);
-            mbar_init(&empty_bar[s], 1);
+            mbar_init(&empty_bar[s], CL);   // one tcgen05.commit arrival per CTA of the cluster
         }
         for (int b = 0; b < 2; ++b) {
             mbar_init(&tfull_bar[b], 1);
@@ -119,6 +129,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_const
     }
     tc_fence_before();
     __syncthreads();
+    if (CL > 1) cluster_sync_all();   // barriers of every CTA are initialised before any remote TMA / commit touches them
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
 
@@ -129,10 +140,10 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_const
             asm volatile("prefetch.tensormap [%0];" ::"l"(&mapB) : "memory");
             int stage = 0;
             uint32_t phase = 0;
-            for (int item = blockIdx.x; item < items; item += gridDim.x) {
-                const int tm = item % p.tiles_m;
-                const int tn = (item / p.tiles_m) % p.tiles_n;
-                const int z = item / (p.tiles_m * p.tiles_n);
+            for (int item = first_item; item < items; item += item_step) {
+                const int tm = (item % tiles_mg) * CL + crank;   // may be >= tiles_m for the last group: TMA zero-fills
+                const int tn = (item / tiles_mg) % p.tiles_n;
+                const int z = item / (tiles_mg * p.tiles_n);
                 const int c_begin = z * p.chunks_per_split;
                 const int c_end = min(p.chunks, c_begin + p.chunks_per_split);
                 for (int c = c_begin; c < c_end; ++c) {
@@ -148,12 +159,27 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_const
                         for (int g = 0; g < TM / 32; ++g)
                             tma_load_2d(sa + g * 4096, &mapA, &full_bar[stage], tm * TM + g * 32, c * KC);
                     }
-                    if (!B_MN) {
-                        tma_load_2d(sb, &mapB, &full_bar[stage], c * KC, tn * BN);
-                    } else {
+                    if (CL == 1) {
+                        if (!B_MN) {
+                            tma_load_2d(sb, &mapB, &full_bar[stage], c * KC, tn * BN);
+                        } else {
 #pragma unroll
-                        for (int g = 0; g < BN / 32; ++g)
-                            tma_load_2d(sb + g * 4096, &mapB, &full_bar[stage], tn * BN + g * 32, c * KC);
+                            for (int g = 0; g < BN / 32; ++g)
+                                tma_load_2d(sb + g * 4096, &mapB, &full_bar[stage], tn * BN + g * 32, c * KC);
+                        }
+                    } else {
+                        // this CTA's share of the B tile (mapB's box is BN / CL rows here), multicast to the whole cluster
+                        constexpr int SHARE = BN / CL;
+                        if (!B_MN) {
+                            tma_load_2d_mc(sb + crank * SHARE * 128, &mapB, &full_bar[stage], c * KC, tn * BN + crank * SHARE,
+                                           CMASK);
+                        } else {
+#pragma unroll
+                            for (int g = 0; g < SHARE / 32; ++g) {
+                                const int gg = crank * (SHARE / 32) + g;
+                                tma_load_2d_mc(sb + gg * 4096, &mapB, &full_bar[stage], tn * BN + gg * 32, c * KC, CMASK);
+                            }
+                        }
                     }
                     if (++stage == STAGES) {
                         stage = 0;
@@ -168,8 +194,8 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_const
             int stage = 0;
             uint32_t phase = 0;
             int local = 0;
-            for (int item = blockIdx.x; item < items; item += gridDim.x, ++local) {
-                const int z = item / (p.tiles_m * p.tiles_n);
+            for (int item = first_item; item < items; item += item_step, ++local) {
+                const int z = item / (tiles_mg * p.tiles_n);
                 const int c_begin = z * p.chunks_per_split;
                 const int c_end = min(p.chunks, c_begin + p.chunks_per_split);
                 const int buf = local & 1;
@@ -193,7 +219,9 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_const
                                                  : make_smem_desc(sb + k8 * 32, 16, 1024, 2);
                         umma_tf32(d_tmem, ad, bd, IDESC, (c > c_begin || k8 > 0) ? 1u : 0u);
                     }
-                    umma_commit(&empty_bar[stage]);  // frees the smem slot once these MMAs retire
+                    // frees the smem slot once these MMAs retire — in every CTA that multicasts into it
+                    if (CL == 1) umma_commit(&empty_bar[stage]);
+                    else umma_commit_mc(&empty_bar[stage], CMASK);
                     if (++stage == STAGES) {
                         stage = 0;
                         phase ^= 1;
@@ -208,10 +236,10 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_const
         const int half = (warp - 2) >> 2;    // 0/1: which 32-column chunks (even/odd)
         const int etid = threadIdx.x - 64;   // 0..255 inside the epilogue group
         int local = 0, cur_tn = -1;
-        for (int item = blockIdx.x; item < items; item += gridDim.x, ++local) {
-            const int tm = item % p.tiles_m;
-            const int tn = (item / p.tiles_m) % p.tiles_n;
-            const int z = item / (p.tiles_m * p.tiles_n);
+        for (int item = first_item; item < items; item += item_step, ++local) {
+            const int tm = (item % tiles_mg) * CL + crank;
+            const int tn = (item / tiles_mg) % p.tiles_n;
+            const int z = item / (tiles_mg * p.tiles_n);
             const int buf = local & 1;
             const uint32_t use = (uint32_t)(local >> 1);
             if (p.bias != nullptr && tn != cur_tn) {  // uniform across the epilogue warps
@@ -351,6 +379,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_const
 
     tc_fence_before();
     __syncthreads();
+    if (CL > 1) cluster_sync_all();   // no CTA leaves while a peer can still multicast into it or arrive on its barriers
     if (warp == 1) {
         tc_fence_after();
         asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(TMEM_COLS) : "memory");
@@ -421,29 +450,55 @@ T5Split t5_plan(int M, int N, int Kc, int lay, int bn) {
     return sp;
 }
 
-template <int BN, int LAY, int EPI, int HF = 0>
+template <int BN, int LAY, int EPI, int HF = 0, int CL = 1>
 int t5_launch(const CUtensorMap& ma, const CUtensorMap& mb, const T5Params& p, cudaStream_t stream) {
     constexpr int smem = t5_smem_bytes<BN>();
-    auto kern = gemm_tcgen05_kernel<BN, LAY, EPI, HF>;
+    auto kern = gemm_tcgen05_kernel<BN, LAY, EPI, HF, CL>;
     static bool configured = false;
     if (!configured) {
         UWR_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
         configured = true;
     }
-    const int items = p.tiles_m * p.tiles_n * p.splits;
-    int grid = uwr_sm_count();
-    if (grid > items) grid = items;
-    kern<<<grid, T5_THREADS, smem, stream>>>(ma, mb, p);
+    const int items = ((p.tiles_m + CL - 1) / CL) * p.tiles_n * p.splits;   // per cluster
+    int clusters = uwr_sm_count() / CL;
+    if (clusters > items) clusters = items;
+    if (CL == 1) {
+        kern<<<clusters, T5_THREADS, smem, stream>>>(ma, mb, p);
+    } else {
+        cudaLaunchConfig_t cfg = {};
+        cfg.gridDim = dim3(clusters * CL);
+        cfg.blockDim = dim3(T5_THREADS);
+        cfg.dynamicSmemBytes = smem;
+        cfg.stream = stream;
+        cudaLaunchAttribute attr;
+        attr.id = cudaLaunchAttributeClusterDimension;
+        attr.val.clusterDim.x = CL;
+        attr.val.clusterDim.y = 1;
+        attr.val.clusterDim.z = 1;
+        cfg.attrs = &attr;
+        cfg.numAttrs = 1;
+        UWR_CUDA(cudaLaunchKernelEx(&cfg, kern, ma, mb, p));
+    }
     UWR_CHECK_LAUNCH("gemm_tcgen05_kernel");
     return 0;
 }
 
 template <int BN, int LAY>
-int t5_dispatch_epi(const CUtensorMap& ma, const CUtensorMap& mb, const T5Params& p, int hf, cudaStream_t stream) {
+int t5_dispatch_epi(const CUtensorMap& ma, const CUtensorMap& mb, const T5Params& p, int hf, int cl, cudaStream_t stream) {
     // fp16 storage is instantiated for the two LeFF uses only: linear1 forward (NT, C half) and the linear2 data
     // gradient with the gelu' multiplier (NN, R half)
     if (hf == 1) return t5_launch<BN, LAY_NT, UWR_EPI_NONE, 1>(ma, mb, p, stream);
     if (hf == 2) return t5_launch<BN, LAY_NN, UWR_EPI_MUL, 2>(ma, mb, p, stream);
+    if (cl == 2) {   // cluster pair with B-tile multicast: the tensor-bound shapes (BN >= 128 only)
+        if constexpr (BN >= 128) {
+            switch (p.epilogue) {
+                case UWR_EPI_RESID: return t5_launch<BN, LAY, UWR_EPI_RESID, 0, 2>(ma, mb, p, stream);
+                case UWR_EPI_MUL: return t5_launch<BN, LAY, UWR_EPI_MUL, 0, 2>(ma, mb, p, stream);
+                case UWR_EPI_NONE: return t5_launch<BN, LAY, UWR_EPI_NONE, 0, 2>(ma, mb, p, stream);
+                default: break;
+            }
+        }
+    }
     switch (p.epilogue) {
         case UWR_EPI_RESID: return t5_launch<BN, LAY, UWR_EPI_RESID>(ma, mb, p, stream);
         case UWR_EPI_MUL: return t5_launch<BN, LAY, UWR_EPI_MUL>(ma, mb, p, stream);
@@ -453,15 +508,36 @@ int t5_dispatch_epi(const CUtensorMap& ma, const CUtensorMap& mb, const T5Params
 }
 
 template <int BN>
-int t5_dispatch(int lay, const CUtensorMap& ma, const CUtensorMap& mb, const T5Params& p, int hf, cudaStream_t stream) {
+int t5_dispatch(int lay, const CUtensorMap& ma, const CUtensorMap& mb, const T5Params& p, int hf, int cl, cudaStream_t stream) {
     switch (lay) {
-        case LAY_NT: return t5_dispatch_epi<BN, LAY_NT>(ma, mb, p, hf, stream);
-        case LAY_NN: return t5_dispatch_epi<BN, LAY_NN>(ma, mb, p, hf, stream);
-        default: return t5_launch<BN, LAY_TN, UWR_EPI_NONE>(ma, mb, p, stream);
+        case LAY_NT: return t5_dispatch_epi<BN, LAY_NT>(ma, mb, p, hf, cl, stream);
+        case LAY_NN: return t5_dispatch_epi<BN, LAY_NN>(ma, mb, p, hf, cl, stream);
+        default:
+            if constexpr (BN >= 128) {
+                if (cl == 2) return t5_launch<BN, LAY_TN, UWR_EPI_NONE, 0, 2>(ma, mb, p, stream);
+            }
+            return t5_launch<BN, LAY_TN, UWR_EPI_NONE>(ma, mb, p, stream);
     }
 }
 
+// cluster pairs pay off where the L2 -> SM operand stream, not HBM, limits the kernel: high arithmetic intensity
+// (flop per algorithmic byte), at least two row tiles to pair, a B tile wide enough to split.  0 = off, 1 = auto.
+int g_t5_cluster = 1;
+int t5_pick_cluster(const uwr_gemm_desc* d, int bn, int hf) {
+    if (!g_t5_cluster || hf || bn < 128 || d->epilogue == UWR_EPI_MUL_DGELU) return 1;
+    if (uwr_cdiv(d->M, TM) < 2) return 1;
+    const double flops = 2.0 * d->M * d->N * d->K;
+    const double bytes = 4.0 * ((double)d->M * d->K + (double)d->K * d->N + (double)d->M * d->N);
+    return flops / bytes >= 96.0 ? 2 : 1;
+}
+
 }  // namespace
+
+// 0 = never pair CTAs, 1 = auto (default)
+extern "C" int uwr_set_gemm_cluster(int mode) {
+    g_t5_cluster = mode ? 1 : 0;
+    return 0;
+}
 
 extern "C" size_t uwr_gemm_tcgen05_workspace_bytes(int M, int N, int K, int a_km) {
     if (!a_km) return 0;
@@ -495,6 +571,8 @@ extern "C" int uwr_gemm_tcgen05(const uwr_gemm_desc* d, uwr_stream_t stream_) {
     const int lay = d->a_km ? LAY_TN : (d->b_nk ? LAY_NT : LAY_NN);
     const int bn = t5_pick_bn(d->N);
     const T5Split sp = t5_plan(d->M, d->N, d->K, lay, bn);
+    const int hf = (d->c_half ? 1 : 0) | (d->r_half ? 2 : 0);
+    const int cl = t5_pick_cluster(d, bn, hf);
 
     CUtensorMap ma, mb;
     int rc;
@@ -504,8 +582,8 @@ extern "C" int uwr_gemm_tcgen05(const uwr_gemm_desc* d, uwr_stream_t stream_) {
         if ((rc = encode_mn(&mb, d->B, d->N, d->K, d->ldb))) return rc;
     } else {
         if ((rc = encode_2d(&ma, d->A, d->K, d->M, d->lda, TM))) return rc;
-        if (lay == LAY_NT) {
-            if ((rc = encode_2d(&mb, d->B, d->K, d->N, d->ldb, bn))) return rc;
+        if (lay == LAY_NT) {   // K-major B: with a cluster pair each CTA's box is its half of the tile's rows
+            if ((rc = encode_2d(&mb, d->B, d->K, d->N, d->ldb, bn / cl))) return rc;
         } else {
             if ((rc = encode_mn(&mb, d->B, d->N, d->K, d->ldb))) return rc;
         }
@@ -527,12 +605,11 @@ extern "C" int uwr_gemm_tcgen05(const uwr_gemm_desc* d, uwr_stream_t stream_) {
         UWR_REQUIRE(d->ldc == d->N, "uwr_gemm_tcgen05: split contraction needs a dense C");
         p.C = d->workspace; p.ldc = d->N; p.split_stride = (long long)d->M * d->N;
     }
-    const int hf = (d->c_half ? 1 : 0) | (d->r_half ? 2 : 0);
     switch (bn) {
-        case 32: rc = t5_dispatch<32>(lay, ma, mb, p, hf, stream); break;
-        case 64: rc = t5_dispatch<64>(lay, ma, mb, p, hf, stream); break;
-        case 128: rc = t5_dispatch<128>(lay, ma, mb, p, hf, stream); break;
-        default: rc = t5_dispatch<256>(lay, ma, mb, p, hf, stream); break;
+        case 32: rc = t5_dispatch<32>(lay, ma, mb, p, hf, cl, stream); break;
+        case 64: rc = t5_dispatch<64>(lay, ma, mb, p, hf, cl, stream); break;
+        case 128: rc = t5_dispatch<128>(lay, ma, mb, p, hf, cl, stream); break;
+        default: rc = t5_dispatch<256>(lay, ma, mb, p, hf, cl, stream); break;
     }
     if (rc) return rc;
     if (sp.splits > 1) {

@@ -84,6 +84,7 @@ SIGNATURES = {
     "uwr_gemm_workspace_bytes": (c_sz, [c_int, c_int, c_int, c_int]),
     "uwr_gemm_tf32": (c_int, [C.POINTER(GemmDesc), c_stream]),
     "uwr_gemm_tcgen05": (c_int, [C.POINTER(GemmDesc), c_stream]),
+    "uwr_set_gemm_cluster": (c_int, [c_int]),
     "uwr_gemm_tcgen05_supported": (c_int, [C.POINTER(GemmDesc)]),
     "uwr_gemm_tcgen05_workspace_bytes": (c_sz, [c_int, c_int, c_int, c_int]),
     "uwr_round_tf32_tensors": (c_int, [c_fp, c_fp, c_fp, c_int, c_ll, c_int, c_stream]),

@@ -36,6 +36,11 @@ def set_attn_tcgen05(mode):
     check(fn["uwr_set_attn_tcgen05"](m), "uwr_set_attn_tcgen05")
 
 
+def set_gemm_cluster(on):
+    """tcgen05 GEMM: pair CTAs into clusters of 2 with TMA multicast of the B tile on the tensor-bound shapes (default on)."""
+    check(fn["uwr_set_gemm_cluster"](int(bool(on))), "uwr_set_gemm_cluster")
+
+
 def fast_path():
     return _PASSES == 1
 
