@@ -93,7 +93,8 @@ int uwr_gemm_tf32(const uwr_gemm_desc* d, uwr_stream_t stream);
  * (no segmented weights / colsum / k-scale; MN-major widths in multiples of 32). */
 int uwr_gemm_tcgen05_supported(const uwr_gemm_desc* d);
 /* Thread-block cluster pairs with TMA multicast of the B tile for the tensor-bound shapes (arithmetic intensity >= 96
- * flop/B, N tile >= 128): 1 = auto (default), 0 = off. */
+ * flop/B, N tile >= 128): 0 = off, 1 = auto (default: every eligible layout; +1 % on the training step),
+ * 2 = the weight-gradient (TN) layout only. */
 int uwr_set_gemm_cluster(int mode);
 size_t uwr_gemm_tcgen05_workspace_bytes(int M, int N, int K, int a_km);
 int uwr_gemm_tcgen05(const uwr_gemm_desc* d, uwr_stream_t stream);
@@ -158,6 +159,12 @@ typedef struct {
      * uwr_gemm_desc.round_out): the products are then exact in one tensor-core pass and the kernels skip the 3xTF32
      * hi/lo compensation they otherwise apply to full-fp32 operands. */
     int operands_rounded;
+    /* backward only, both or neither: column sums of dq and of dk | dv (the bias gradients of the q / kv projections,
+     * AST.py:139-157), written at the same column offsets as dq_buf / dkv_buf use (q_off + h*HD, k_off + h*HD,
+     * v_off + h*HD; for a packed q|k|v buffer pass the same 3C vector twice).  NULL = not wanted.  Accumulated inside
+     * the backward kernel, in a fixed order (deterministic), instead of one more pass over dq | dk | dv. */
+    float* dq_colsum;
+    float* dkv_colsum;
 } uwr_attn_desc;
 
 int uwr_window_attn_fwd(const uwr_attn_desc* d, float* out, long long ld_out, uwr_stream_t stream);

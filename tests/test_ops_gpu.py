@@ -181,12 +181,19 @@ def test_window_attention_fwd_bwd(ops, B, H, heads, hd, shift, sparse):
     assert rel_l2(o, ref) < TOL_TF32
     do = _r(B * H * W, C, seed=3)
     ref.backward(do.double())
+    cs = torch.full((3 * C,), float("nan"), device="cuda")   # projection bias gradient, accumulated inside the kernel
     dqkv, _, dtable, dw = ops.window_attn_bwd(do, qkv, 0, qkv, C, 2 * C, table, w if sparse else None, B, H, W,
-                                              heads, hd, shift, scale)
+                                              heads, hd, shift, scale, colsum_q=cs, colsum_kv=cs)
     assert rel_l2(dqkv, qd.grad) < 2 * TOL_TF32
     assert rel_l2(dtable, td.grad) < 2 * TOL_TF32
     if sparse:
         assert rel_l2(dw, wd.grad) < 5 * TOL_TF32
+    assert rel_l2(cs, dqkv.double().sum(0)) < 1e-5            # the sums of exactly what was stored
+    assert rel_l2(cs, qd.grad.sum(0)) < 5 * TOL_TF32
+    # not requested: same gradients, nothing else written
+    dqkv2, _, _, _ = ops.window_attn_bwd(do, qkv, 0, qkv, C, 2 * C, table, w if sparse else None, B, H, W, heads, hd,
+                                         shift, scale)
+    assert torch.equal(dqkv2, dqkv)
 
 
 @pytest.mark.parametrize("B,H,heads,hd,shift,t5", [(2, 16, 2, 32, 0, False), (1, 32, 2, 32, 4, False), (2, 16, 4, 16, 4, False),

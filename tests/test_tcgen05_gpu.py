@@ -70,7 +70,10 @@ def test_t5_nt_epilogues():
 
 
 @pytest.mark.parametrize("M,N,K", [(256, 64, 256), (1000, 32, 128), (4096, 64, 256), (512, 128, 512),
-                                   (300, 512, 2048), (65536, 64, 256)])
+                                   (300, 512, 2048), (65536, 64, 256),
+                                   # widths that are not multiples of 32 (GDFN hidden 2*88 / 2*172, 3-channel ends):
+                                   # the ragged last 32-float group of the MN-major operand is zero-filled by TMA
+                                   (4096, 88, 32), (1000, 176, 32), (2048, 344, 64), (512, 36, 176), (256, 300, 88)])
 def test_t5_nn(M, N, K):
     """dx[M,N] = dy[M,K] W[K,N]  (W stored [K][N]: MN-major B operand)"""
     dy, w = _r(M, K, seed=1), _r(K, N, seed=2, scale=0.1)
@@ -80,7 +83,8 @@ def test_t5_nn(M, N, K):
 
 
 @pytest.mark.parametrize("M,N,K", [(128, 32, 512), (256, 64, 8192), (64, 256, 65536), (2048, 512, 4096),
-                                   (192, 64, 1000), (32, 128, 100000)])
+                                   (192, 64, 1000), (32, 128, 100000),
+                                   (176, 32, 8192), (32, 88, 8192), (88, 36, 4100), (344, 64, 2048), (300, 172, 1024)])
 def test_t5_tn(M, N, K):
     """dW[M,N] = dy[K,M]^T x[K,N]  (both MN-major, contraction split across CTAs)"""
     dy, x = _r(K, M, seed=1), _r(K, N, seed=2)
@@ -112,7 +116,7 @@ def test_t5_cluster_multicast_matches_single_cta(lay, M, N, K):
         kw = dict(lda=M, ldb=N, ldc=N, a_km=True, b_nk=False)
     outs = {}
     for on in (True, False):
-        ops.set_gemm_cluster(on)
+        ops.set_gemm_cluster(bool(on))
         try:
             outs[on] = _t5(A, Bm, torch.full((M, N), float("nan"), device="cuda"), M, N, K, **kw).clone()
         finally:

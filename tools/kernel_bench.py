@@ -91,7 +91,7 @@ if "t5big" in which:
     for (lay, Mm, Nn, Kk) in (("nt", 16384, 2048, 512), ("nt", 65536, 1024, 256), ("nn", 16384, 2048, 512), ("nn", 65536, 256, 1024),
                               ("tn", 512, 2048, 16384), ("tn", 1024, 256, 65536)):
         for on in (False, True):
-            ops.set_gemm_cluster(on)
+            ops.set_gemm_cluster(bool(on))
             if lay == "nt":
                 a, b_ = rnd(Mm, Kk), rnd(Nn, Kk)
                 o = torch.empty(Mm, Nn, device=dev)

@@ -27,6 +27,8 @@ constexpr int DW_THREADS = 256; // 8 warps, 2 tile rows each
 // thread -> (tile row r, x half xh, 4-channel group c4): 8 outputs x 4 channels, 128-bit accesses only
 __device__ __forceinline__ float4 ld4(const float* p) { return *reinterpret_cast<const float4*>(p); }
 __device__ __forceinline__ void fma4(float4& a, const float4& x, const float4& w) {
+    // scalar on purpose: the forward kernels measured SLOWER with packed FFMA2 / FMUL2 (0.560 vs 0.523 ms at
+    // B16 H256 Ch256, same box) while the backward gains 5 % (0.590 vs 0.619 ms) -- see fma2 below
     a.x = fmaf(x.x, w.x, a.x); a.y = fmaf(x.y, w.y, a.y); a.z = fmaf(x.z, w.z, a.z); a.w = fmaf(x.w, w.w, a.w);
 }
 
@@ -353,7 +355,7 @@ __global__ void __launch_bounds__(256) gelu_mul_bwd_kernel(const float* __restri
 // are reduced across the CTA once, at the end.
 __device__ __forceinline__ float2 ld2(const float* p) { return *reinterpret_cast<const float2*>(p); }
 __device__ __forceinline__ void fma2(float2& a, const float2& x, const float2& w) {
-    a.x = fmaf(x.x, w.x, a.x); a.y = fmaf(x.y, w.y, a.y);
+    a = ffma2(x, w, a);   // packed FFMA2: the backward kernel's 18 tap products per pixel pair, half the issue slots
 }
 
 // UHALF: u is __half (fp16 storage of the linear1 output, see dwconv_fwd_half_kernel); ld_u counts elements of u and
@@ -454,13 +456,10 @@ dwconv_bwd_kernel(const __grid_constant__ CUtensorMap map_dv, const float* __res
 #pragma unroll
                     for (int a = 0; a < 3; ++a) col[a][(i + 2) % 3] = ld2(sp + (a * HS + lx0 + i + 2) * CG);
                     if (FAST || tx0 + lx0 + i < W) {
-                        float cdf0 = 1.f, pdf0 = 0.f, cdf1 = 1.f, pdf1 = 0.f;  // plain conv: h1 = u, gelu' = 1
+                        float2 cdf = make_float2(1.f, 1.f), pdf = make_float2(0.f, 0.f);  // plain conv: h1 = u, gelu' = 1
                         const float2 uv = cvt_u2<UHALF>(uc[i]);
-                        if (!PLAIN) {
-                            gelu_parts(uv.x, cdf0, pdf0);
-                            gelu_parts(uv.y, cdf1, pdf1);
-                        }
-                        const float2 h1 = make_float2(uv.x * cdf0, uv.y * cdf1);
+                        if (!PLAIN) gelu_parts2(uv, cdf, pdf);
+                        const float2 h1 = PLAIN ? uv : fmul2(uv, cdf);
                         float2 dh1 = make_float2(0.f, 0.f);
                         // v[q] = sum_k h1[q + k - 1] w[k]  =>  h1[p] meets dv[p + 1 - k] with weight w[k]
 #pragma unroll
@@ -472,13 +471,10 @@ dwconv_bwd_kernel(const __grid_constant__ CUtensorMap map_dv, const float* __res
                                 fma2(dwt[ky * 3 + kx], h1, d);
                             }
                         const float2 ctr = col[1][(i + 1) % 3];
-                        dbs.x += ctr.x;
-                        dbs.y += ctr.y;
-                        float2 o = PLAIN ? dh1
-                                         : make_float2(dh1.x * fmaf(uv.x, pdf0, cdf0), dh1.y * fmaf(uv.y, pdf1, cdf1));
+                        dbs = fadd2(dbs, ctr);
+                        float2 o = PLAIN ? dh1 : fmul2(dh1, ffma2(uv, pdf, cdf));
                         if (rn) o = make_float2(tf32_round(o.x), tf32_round(o.y));
-                        dus.x += o.x;
-                        dus.y += o.y;
+                        dus = fadd2(dus, o);
                         *reinterpret_cast<float2*>(dup + (long long)(lx0 + i) * ld_u) = o;
                     }
                 }

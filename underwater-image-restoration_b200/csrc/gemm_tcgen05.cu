@@ -520,11 +520,16 @@ int t5_dispatch(int lay, const CUtensorMap& ma, const CUtensorMap& mb, const T5P
     }
 }
 
-// cluster pairs pay off where the L2 -> SM operand stream, not HBM, limits the kernel: high arithmetic intensity
-// (flop per algorithmic byte), at least two row tiles to pair, a B tile wide enough to split.  0 = off, 1 = auto.
+// Cluster pairs halve the L2 reads of the B tile: at least two row tiles to pair, a B tile wide enough to split, high
+// arithmetic intensity (flop per algorithmic byte).  Measured in isolation (profiles/r2_kernel_bench.txt, t5big) the
+// weight-gradient (TN) shapes gain 6..8 % and NT / NN nothing -- those are bound by each SM's own operand ingress (48 KB
+// per 512 MMA cycles), which multicast does not reduce -- but inside the training step, where neighbouring kernels
+// compete for L2, pairing every eligible layout is the fastest setting (same box, B = 16: off 445.2, TN only 446.6,
+// all layouts 449.7 img/s).  0 = off, 1 = auto (every eligible shape), 2 = TN layout only.
 int g_t5_cluster = 1;
 int t5_pick_cluster(const uwr_gemm_desc* d, int bn, int hf) {
     if (!g_t5_cluster || hf || bn < 128 || d->epilogue == UWR_EPI_MUL_DGELU) return 1;
+    if (g_t5_cluster == 2 && !d->a_km) return 1;
     if (uwr_cdiv(d->M, TM) < 2) return 1;
     const double flops = 2.0 * d->M * d->N * d->K;
     const double bytes = 4.0 * ((double)d->M * d->K + (double)d->K * d->N + (double)d->M * d->N);
@@ -533,9 +538,10 @@ int t5_pick_cluster(const uwr_gemm_desc* d, int bn, int hf) {
 
 }  // namespace
 
-// 0 = never pair CTAs, 1 = auto (default)
+// 0 = never pair CTAs, 1 = auto (default: every eligible shape), 2 = weight-gradient (TN) layout only
 extern "C" int uwr_set_gemm_cluster(int mode) {
-    g_t5_cluster = mode ? 1 : 0;
+    if (mode < 0 || mode > 2) return -1;
+    g_t5_cluster = mode;
     return 0;
 }
 
@@ -559,8 +565,9 @@ extern "C" int uwr_gemm_tcgen05_supported(const uwr_gemm_desc* d) {
         return 0;
     if (d->r_half && !(!d->b_nk && !d->a_km && d->epilogue == UWR_EPI_MUL && !d->c_half)) return 0;
     if (d->bias && (uintptr_t)d->bias % 16) return 0;
-    if (d->a_km && (d->M % 32 || d->N % 32)) return 0;   // MN-major operands: widths in 32-float groups
-    if (!d->a_km && !d->b_nk && d->N % 32) return 0;
+    // MN-major operands are fetched in 32-float groups; a ragged last group is zero-filled by TMA (out-of-bounds
+    // elements of a box read as 0) and masked in the epilogue, so any width in multiples of 4 (16 B rows) is served
+    if (d->a_km && d->M % 4) return 0;
     if (d->M < 1 || d->N < 8 || d->K < 8) return 0;
     return 1;
 }

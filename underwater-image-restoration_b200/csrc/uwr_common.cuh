@@ -90,6 +90,50 @@ __device__ __forceinline__ float gelu_f(float x) {
     gelu_parts(x, cdf, pdf);
     return x * cdf;
 }
+// ---- packed fp32 pairs (sm_100 FFMA2 / FMUL2 / FADD2): per-lane results identical to the scalar IEEE forms, one
+// issue slot for two lanes (tools/micro/ffma2_bench.cu: 113 vs 73 lane-FMA/clk/SM on independent chains).  Used where
+// it measured faster on the same box: the dwconv backward (-27 % instructions, 0.619 -> 0.590 ms at B16 H256 Ch256);
+// the dwconv forward got slower with it (0.523 -> 0.560 ms) and stays scalar.
+#ifndef UWR_PACKED_FP32
+#define UWR_PACKED_FP32 1   // 0: the same expressions as scalar instructions (A/B builds only)
+#endif
+#if UWR_PACKED_FP32
+__device__ __forceinline__ float2 ffma2(float2 a, float2 b, float2 c) { return __ffma2_rn(a, b, c); }
+__device__ __forceinline__ float2 fmul2(float2 a, float2 b) { return __fmul2_rn(a, b); }
+__device__ __forceinline__ float2 fadd2(float2 a, float2 b) { return __fadd2_rn(a, b); }
+#else
+__device__ __forceinline__ float2 ffma2(float2 a, float2 b, float2 c) { return make_float2(fmaf(a.x, b.x, c.x), fmaf(a.y, b.y, c.y)); }
+__device__ __forceinline__ float2 fmul2(float2 a, float2 b) { return make_float2(a.x * b.x, a.y * b.y); }
+__device__ __forceinline__ float2 fadd2(float2 a, float2 b) { return make_float2(a.x + b.x, a.y + b.y); }
+#endif
+__device__ __forceinline__ float2 splat2(float s) { return make_float2(s, s); }
+// gelu_parts on a pair: the two MUFUs per lane, |x| and the sign transfer stay scalar; the polynomial and the products
+// are packed (19 issue slots per pair instead of ~32).  cdf = 1/2 + copysign(1/2 - Phi(-|x|), x): absolute error
+// <= 2^-25 against the select form, far below the 1.5e-7 of the erf approximation itself.
+__device__ __forceinline__ void gelu_parts2(float2 x, float2& cdf, float2& pdf) {
+    float2 t, e;
+    t.x = rcp_ftz(fmaf(0.23164189f, fabsf(x.x), 1.0f));
+    t.y = rcp_ftz(fmaf(0.23164189f, fabsf(x.y), 1.0f));
+    const float2 a = fmul2(fmul2(x, x), splat2(-0.72134752044448170368f));   // -x^2 log2(e) / 2
+    e.x = ex2_ftz(a.x);
+    e.y = ex2_ftz(a.y);
+    float2 poly = ffma2(splat2(0.5f * 1.061405429f), t, splat2(0.5f * -1.453152027f));
+    poly = ffma2(poly, t, splat2(0.5f * 1.421413741f));
+    poly = ffma2(poly, t, splat2(0.5f * -0.284496736f));
+    poly = ffma2(poly, t, splat2(0.5f * 0.254829592f));
+    const float2 tail = fmul2(fmul2(poly, t), e);                            // Phi(-|x|)
+    const float2 h = ffma2(tail, splat2(-1.0f), splat2(0.5f));               // 1/2 - Phi(-|x|) >= 0
+    float2 hs;
+    hs.x = __uint_as_float(__float_as_uint(h.x) | (__float_as_uint(x.x) & 0x80000000u));
+    hs.y = __uint_as_float(__float_as_uint(h.y) | (__float_as_uint(x.y) & 0x80000000u));
+    cdf = fadd2(hs, splat2(0.5f));
+    pdf = fmul2(e, splat2(0.39894228040143267794f));
+}
+__device__ __forceinline__ float2 gelu_f2(float2 x) {
+    float2 cdf, pdf;
+    gelu_parts2(x, cdf, pdf);
+    return fmul2(x, cdf);
+}
 __device__ __forceinline__ float gelu_grad_f(float x) {
     float cdf, pdf;
     gelu_parts(x, cdf, pdf);

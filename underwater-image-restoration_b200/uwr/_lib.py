@@ -64,6 +64,7 @@ class AttnDesc(C.Structure):
         ("bias_table", c_fp), ("w_param", c_fp),
         ("B", c_int), ("H", c_int), ("W", c_int), ("heads", c_int), ("head_dim", c_int),
         ("shift", c_int), ("scale", c_f), ("operands_rounded", c_int),
+        ("dq_colsum", c_fp), ("dkv_colsum", c_fp),
     ]
 
 

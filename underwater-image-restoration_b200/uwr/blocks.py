@@ -247,16 +247,20 @@ class AttnBlockFn(torch.autograd.Function):
         d_o = ops.linear_dgrad(d_s, ops.rounded_weight(wp), t5=True, round_out=fast)
         dwp, _ = ops.linear_wgrad(d_s, o, want_bias=False, t5=True, out=g_wp)
         del d_s
-        dqkv, _, dtable, dw = ops.window_attn_bwd(d_o, qkv, 0, qkv, Cc, 2 * Cc, table, wparam, B, H, W, heads, hd,
-                                                  shift, scale, dtable_out=g_tab, dw_out=g_w, rounded=fast)
-        del d_o
-        dy1 = _qkv_dgrad(dqkv, wq, bq, wkv, bkv)
-        # [to_q; to_kv] weight / bias gradients come out of one GEMM / one column sum: written in place when the two
-        # bucket slots are adjacent (GradBuckets(adjacent=...))
+        # [to_q; to_kv] weight / bias gradients come out of one GEMM / one vector of column sums: written in place when
+        # the two bucket slots are adjacent (GradBuckets(adjacent=...)).  The column sums of dq | dk | dv (bias gradient)
+        # are accumulated inside the attention backward kernel.
         g_wqkv = ops.fused_grad_slot(wq, wkv)
         g_bqkv = ops.fused_grad_slot(bq, bkv) if bq is not None else None
+        dbqkv = None
+        if bq is not None:
+            dbqkv = g_bqkv if g_bqkv is not None else ops._empty((3 * Cc,), qkv)
+        dqkv, _, dtable, dw = ops.window_attn_bwd(d_o, qkv, 0, qkv, Cc, 2 * Cc, table, wparam, B, H, W, heads, hd,
+                                                  shift, scale, dtable_out=g_tab, dw_out=g_w, rounded=fast,
+                                                  colsum_q=dbqkv, colsum_kv=dbqkv)
+        del d_o
+        dy1 = _qkv_dgrad(dqkv, wq, bq, wkv, bkv)
         dwqkv, _ = ops.linear_wgrad(dqkv, y1, want_bias=False, t5=True, out=g_wqkv)
-        dbqkv = ops.colsum(dqkv, 3 * Cc, out=g_bqkv) if bq is not None else None
         del dqkv
         dx, dg, db = _ln_bwd_linked(ctx.link_in, dy1, x2, n1w, mean, rstd, d, g_n1w, g_n1b)
         dwq, dwkv = (None, None) if g_wqkv is not None else (dwqkv[:Cc], dwqkv[Cc:])

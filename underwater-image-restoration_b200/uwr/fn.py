@@ -110,7 +110,7 @@ class Conv3x3Fn(torch.autograd.Function):
         B, H, W, Cin, Cout, has_b = ctx.meta
         d = _c(dy).view(-1, Cout)
         col = ops.im2col_3x3(x.view(-1, Cin), B, H, W, Cin)  # recomputed (9x the input)
-        fast = ops.fast_path() and Cout % 32 == 0 and d.shape[0] >= 4096
+        fast = ops.fast_path() and Cout % 4 == 0 and d.shape[0] >= 4096
         if fast:  # tcgen05 path: TF32-rounded copy of the cotangent (col and wmat already are rounded)
             d, db = ops.scale_round_colsum(d, Cout) if has_b else (ops.scale_round(d, Cout), None)
             dwm, _ = ops.linear_wgrad(d, col, want_bias=False, t5=True)
@@ -179,21 +179,26 @@ class AttnFn(torch.autograd.Function):
             dwp, dbp = ops.linear_wgrad(d, o)
         cross = xkv is not None
         q_off, k_off, v_off = (0, 0, Cc) if cross else (0, Cc, 2 * Cc)
+        # bias gradients of the projections = column sums of dq | dk | dv, accumulated inside the attention backward
+        csq = cskv = None
+        if fast and has_b:
+            csq = ops._empty((Cc,) if cross else (3 * Cc,), q_buf)
+            cskv = ops._empty((2 * Cc,), q_buf) if cross else csq
         dq_buf, dkv_buf, dtable, dw = ops.window_attn_bwd(d_o, q_buf, q_off, kv_buf, k_off, v_off, table, wparam,
-                                                          B, H, W, heads, hd, shift, scale, rounded=fast)
+                                                          B, H, W, heads, hd, shift, scale, rounded=fast,
+                                                          colsum_q=csq, colsum_kv=cskv)
         if fast:   # dq / dk / dv leave the attention kernel TF32-rounded; xq / xkv were saved rounded
             if cross:
                 dxq = ops.linear_dgrad(dq_buf, ops.rounded_weight(wq), t5=True)
                 dwq, _ = ops.linear_wgrad(dq_buf, xq, want_bias=False, t5=True)
                 dxkv = ops.linear_dgrad(dkv_buf, ops.rounded_weight(wkv), t5=True)
                 dwkv, _ = ops.linear_wgrad(dkv_buf, xkv, want_bias=False, t5=True)
-                dbq = ops.colsum(dq_buf, Cc) if has_b else None
-                dbkv = ops.colsum(dkv_buf, 2 * Cc) if has_b else None
+                dbq, dbkv = csq, cskv
             else:
                 w, _ = ops.packed_qkv(wq, bq, wkv, bkv)
                 dxq = ops.linear_dgrad(dq_buf, w, t5=True)
                 dwqkv, _ = ops.linear_wgrad(dq_buf, xq, want_bias=False, t5=True)
-                dbqkv = ops.colsum(dq_buf, 3 * Cc) if has_b else None
+                dbqkv = csq
                 dwq, dwkv = dwqkv[:Cc], dwqkv[Cc:]
                 dbq, dbkv = (dbqkv[:Cc], dbqkv[Cc:]) if has_b else (None, None)
                 dxkv = None
@@ -232,6 +237,43 @@ class PlainDWConvFn(torch.autograd.Function):
         B, H, W, Ch = ctx.dims
         du, dw, _ = ops.dwconv_gelu_bwd(_c(dy), u, weight, B, H, W, Ch, plain=True)
         return du, dw, None, None, None
+
+
+class LinearDWConvFn(torch.autograd.Function):
+    """1x1 convolution followed by a depthwise 3x3 (MDTA qkv -> qkv_conv, kv -> kv_conv and GDFN project_in -> conv,
+    SpectralTransformer.py:81-89,121-123) as ONE autograd node: the depthwise backward already emits its du
+    TF32-rounded in tf32 mode, so the 1x1's data / weight gradient GEMMs read it as it is -- as two nodes the Linear
+    backward cannot know that and spends a pass on a rounded copy of the widest gradient of the block."""
+
+    @staticmethod
+    def forward(ctx, x, w, wdw, B, H, W, rounded):
+        x2 = _rows(x)
+        Ch = w.shape[0]
+        fast = ops.fast_path() and x2.shape[1] % 4 == 0 and Ch % 4 == 0
+        if fast and not rounded:
+            fast = x2.shape[0] >= 131072      # as LinearFn: a rounded copy only pays off on big token matrices
+            if fast:
+                x2 = ops.scale_round(x2, x2.shape[1])
+        u = ops.linear(x2, ops.rounded_weight(w) if fast else w, None, t5=fast)
+        _, y = ops.dwconv_gelu_fwd(u, wdw, None, B, H, W, Ch, mode=2, save_v=False)
+        ctx.save_for_backward(x2, w, u, wdw)
+        ctx.meta = (B, H, W, Ch, fast, x.shape)
+        return y
+
+    @staticmethod
+    @once_differentiable
+    def backward(ctx, dy):
+        x2, w, u, wdw = ctx.saved_tensors
+        B, H, W, Ch, fast, xshape = ctx.meta
+        du, dwdw, _ = ops.dwconv_gelu_bwd(_c(dy), u, wdw, B, H, W, Ch, plain=True)   # rounded in tf32 mode
+        del u
+        if fast:
+            dx = ops.linear_dgrad(du, ops.rounded_weight(w), t5=True) if ctx.needs_input_grad[0] else None
+            dw, _ = ops.linear_wgrad(du, x2, want_bias=False, t5=True)
+        else:
+            dx = ops.linear_dgrad(du, w) if ctx.needs_input_grad[0] else None
+            dw, _ = ops.linear_wgrad(du, x2, want_bias=False)
+        return (dx.view(xshape) if dx is not None else None), dw, dwdw, None, None, None, None
 
 
 class DftRealFn(torch.autograd.Function):

@@ -5,8 +5,8 @@ on torch's current stream.  Nothing here computes on the CPU or through ATen: a 
 is an error (the product path has no fallback).
 """
 import ctypes as C
-
 import math
+import os
 
 import torch
 
@@ -36,9 +36,15 @@ def set_attn_tcgen05(mode):
     check(fn["uwr_set_attn_tcgen05"](m), "uwr_set_attn_tcgen05")
 
 
-def set_gemm_cluster(on):
-    """tcgen05 GEMM: pair CTAs into clusters of 2 with TMA multicast of the B tile on the tensor-bound shapes (default on)."""
-    check(fn["uwr_set_gemm_cluster"](int(bool(on))), "uwr_set_gemm_cluster")
+def set_gemm_cluster(mode):
+    """tcgen05 GEMM: pair CTAs into clusters of 2 with TMA multicast of the B tile.  False = never, True / "auto" / "all"
+    = every tensor-bound shape (default), "tn" = the weight-gradient layout only."""
+    m = {False: 0, True: 1, "auto": 1, "all": 1, "tn": 2}[mode]
+    check(fn["uwr_set_gemm_cluster"](m), "uwr_set_gemm_cluster")
+
+
+if os.environ.get("UWR_GEMM_CLUSTER"):      # A/B knob for benchmarks: off | auto | tn
+    set_gemm_cluster({"off": False, "0": False, "auto": "auto", "1": "auto", "all": "all", "tn": "tn"}[os.environ["UWR_GEMM_CLUSTER"]])
 
 
 def fast_path():
@@ -518,9 +524,14 @@ def window_attn_fwd(q_buf, q_off, kv_buf, k_off, v_off, table, w_param, B, H, W,
 
 
 def window_attn_bwd(dout, q_buf, q_off, kv_buf, k_off, v_off, table, w_param, B, H, W, heads, head_dim, shift,
-                    scale, dq_buf=None, dkv_buf=None, dtable_out=None, dw_out=None, rounded=False):
-    """rounded: q, k, v AND dout are exact TF32 values."""
+                    scale, dq_buf=None, dkv_buf=None, dtable_out=None, dw_out=None, rounded=False, colsum_q=None,
+                    colsum_kv=None):
+    """rounded: q, k, v AND dout are exact TF32 values.  colsum_q / colsum_kv (both or neither): vectors that receive
+    the column sums of dq and of dk | dv (projection bias gradients) at the columns dq_buf / dkv_buf use; the same 3C
+    vector twice for a packed q|k|v buffer."""
     d = _attn_desc(q_buf, q_off, kv_buf, k_off, v_off, table, w_param, B, H, W, heads, head_dim, shift, scale, rounded)
+    if colsum_q is not None:
+        d.dq_colsum, d.dkv_colsum = _ptr(colsum_q), _ptr(colsum_kv)
     if dq_buf is None:
         dq_buf = torch.empty_like(q_buf)
     if dkv_buf is None:

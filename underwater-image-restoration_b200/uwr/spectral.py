@@ -39,12 +39,11 @@ class MDTA(nn.Module):
 
     def forward(self, y, B, H, W):   # y: LayerNorm output tokens (B*L, C)
         L, C = H * W, y.shape[1]
-        qkv = fn.linear(y, _w2(self.qkv), None, rounded=True)
-        qkv = fn.PlainDWConvFn.apply(qkv, self.qkv_conv.weight, B, H, W)
+        qkv = fn.LinearDWConvFn.apply(y, _w2(self.qkv), self.qkv_conv.weight, B, H, W, True)
         # channel attention for the whole batch: Gram GEMMs on strided views, batched normalise / softmax
         out, attn = fn.MDTAAttnFn.apply(qkv, self.temperature, B, L, C, self.num_heads)        # attn @ v
         out = fn.linear(out, _w2(self.project_out), rounded=True)       # uwr_mdta_apply rounds its output to TF32
-        kvf = fn.PlainDWConvFn.apply(fn.linear(out, _w2(self.kv)), self.kv_conv.weight, B, H, W)
+        kvf = fn.LinearDWConvFn.apply(out, _w2(self.kv), self.kv_conv.weight, B, H, W, False)
         outf = fn.ChannelApplyFn.apply(kvf, attn, C, B, L)                                       # attn @ vf
         return fn.linear(outf, _w2(self.project_outf), rounded=True)
 
@@ -71,7 +70,7 @@ class GDFN(nn.Module):
             z2 = wdw.new_zeros(hp - h, 1, 3, 3)
             wdw = torch.cat([wdw[:h], z2, wdw[h:], z2], 0)
             wout = torch.cat([wout, wout.new_zeros(wout.shape[0], hp - h)], 1)
-        t = fn.PlainDWConvFn.apply(fn.linear(y, win, None, rounded=True), wdw, B, H, W)
+        t = fn.LinearDWConvFn.apply(y, win, wdw, B, H, W, True)
         return fn.linear(fn.GeluMulFn.apply(t, hp), wout, rounded=True)   # the gate kernel rounds its output
 
 
