@@ -271,23 +271,31 @@ def test_input_proj():
     assert rel_l2(b.grad, bd.grad) < TOL_FP32 * 10
 
 
-@pytest.mark.parametrize("Cin", [64, 32])
-def test_output_proj(Cin):
+@pytest.mark.parametrize("precision", ["tf32", "tf32x3"])
+@pytest.mark.parametrize("Cin,H", [(64, 40), (32, 40), (64, 16), (32, 24)])
+def test_output_proj(ops, Cin, H, precision):
+    """Forward: direct fp32 kernel.  Backward: tensor-core kernel (TF32 operands, both gradients from the im2col of the
+    3-channel cotangent) in the default mode, the scalar fp32 kernel in tf32x3; ragged tiles (40 = 2.5 x 16) included."""
     from uwr.blocks import OutputProjFn
-    B, H = 2, 40
-    tok = _r(B, H * H, Cin, seed=1).requires_grad_()
-    img = _r(B, 3, H, H, seed=5)
-    w, b = _r(3, Cin, 3, 3, seed=2, scale=0.1).requires_grad_(), _r(3, seed=3, scale=0.1).requires_grad_()
-    out = OutputProjFn.apply(tok, w, b, img, H, H)
-    td, wd, bd = (t.detach().double().requires_grad_() for t in (tok, w, b))
-    ref = img.double() + F.conv2d(td.transpose(1, 2).reshape(B, Cin, H, H), wd, bd, padding=1)
-    assert rel_l2(out, ref) < TOL_FP32
-    g = _r(B, 3, H, H, seed=4)
-    out.backward(g)
-    ref.backward(g.double())
-    assert rel_l2(tok.grad, td.grad) < TOL_FP32 * 5
-    assert rel_l2(w.grad, wd.grad) < TOL_FP32 * 10
-    assert rel_l2(b.grad, bd.grad) < TOL_FP32 * 10
+    ops.set_gemm_precision(precision)
+    try:
+        B = 2
+        tok = _r(B, H * H, Cin, seed=1).requires_grad_()
+        img = _r(B, 3, H, H, seed=5)
+        w, b = _r(3, Cin, 3, 3, seed=2, scale=0.1).requires_grad_(), _r(3, seed=3, scale=0.1).requires_grad_()
+        out = OutputProjFn.apply(tok, w, b, img, H, H)
+        td, wd, bd = (t.detach().double().requires_grad_() for t in (tok, w, b))
+        ref = img.double() + F.conv2d(td.transpose(1, 2).reshape(B, Cin, H, H), wd, bd, padding=1)
+        assert rel_l2(out, ref) < TOL_FP32
+        g = _r(B, 3, H, H, seed=4)
+        out.backward(g)
+        ref.backward(g.double())
+        tol = TOL_TF32 if precision == "tf32" else TOL_FP32 * 10
+        assert rel_l2(tok.grad, td.grad) < tol
+        assert rel_l2(w.grad, wd.grad) < tol
+        assert rel_l2(b.grad, bd.grad) < TOL_FP32 * 10
+    finally:
+        ops.set_gemm_precision("tf32")
 
 
 def test_downsample():

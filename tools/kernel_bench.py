@@ -164,3 +164,25 @@ if "fft" in which:
         timeit(f"dft_hw_real B{B} {H}x{H} C{C}", lambda: ops.dft_real(x, B, H, H, C, 1.0, "hw"), 4 * n * 6, 5.0 * n * 2 * (H.bit_length() - 1))
         timeit(f"dft_lc_real B{B} {H}x{H} C{C}", lambda: ops.dft_real(x, B, H, H, C, 1.0, "lc"), 4 * n * 10, 5.0 * n * (2 * (H.bit_length() - 1) + (C.bit_length() - 1)))
         del x
+
+if "oproj" in which:
+    # AST boundary convolutions at B = 16, 256 x 256: InputProj 3 -> 32, OutputProj 64 -> 3 (+ residual)
+    B_, H_ = 16, 256
+    img = torch.randn(B_, 3, H_, H_, device=dev)
+    wi, bi = torch.randn(32, 3, 3, 3, device=dev) * 0.1, torch.randn(32, device=dev) * 0.1
+    tok64 = torch.randn(B_, H_ * H_, 64, device=dev)
+    wo, bo = torch.randn(3, 64, 3, 3, device=dev) * 0.1, torch.randn(3, device=dev) * 0.1
+    dimg = torch.randn(B_, 3, H_, H_, device=dev)
+    npx = B_ * H_ * H_
+    timeit("input_proj fwd 3->32", lambda: ops.input_proj_fwd(img, wi, bi), 4 * npx * (3 + 32), 2.0 * npx * 27 * 32)
+    tk = ops.input_proj_fwd(img, wi, bi)
+    dtk = torch.randn_like(tk)
+    timeit("input_proj bwd 3->32", lambda: ops.input_proj_bwd(dtk, tk, img, wi), 4 * npx * (3 + 64), 2.0 * npx * 27 * 32)
+    timeit("output_proj fwd 64->3", lambda: ops.output_proj_fwd(tok64, wo, bo, img, B_, H_, H_), 4 * npx * (64 + 6),
+           2.0 * npx * 27 * 64)
+    timeit("output_proj bwd 64->3 (tensor core)", lambda: ops.output_proj_bwd(dimg, tok64, wo, B_, H_, H_),
+           4 * npx * (128 + 3), 4.0 * npx * 27 * 64)
+    ops.set_gemm_precision("tf32x3")
+    timeit("output_proj bwd 64->3 (scalar fp32)", lambda: ops.output_proj_bwd(dimg, tok64, wo, B_, H_, H_),
+           4 * npx * (128 + 3), 4.0 * npx * 27 * 64)
+    ops.set_gemm_precision("tf32")

@@ -333,6 +333,184 @@ __global__ void __launch_bounds__(256) output_proj_bwd_kernel(const float* __res
     }
 }
 
+// OutputProj backward on the tensor cores (single-pass TF32 mode).  With the im2col of the 3-channel cotangent
+//   A[p][k] = dY[co][py + 1 - ky][px + 1 - kx],   k = co*9 + ky*3 + kx  (27 columns, padded to 32)
+// both gradients are thin GEMMs over the pixels p of a tile that share A:
+//   dX[p][ci]  = sum_k A[p][k] Wm[k][ci]            (M = 16 pixels per warp, N = Cin, K = 32)
+//   dW[k][ci] += sum_p A[p][k] X[p][ci]             (M = 32, N = 8 channels per warp, K = the tile's pixels)
+// A is never materialised: its fragments are read straight from the 3 x 10 x 18 halo tile of dY.  The scalar kernel
+// above spends 54 FMAs per (pixel, channel) on the CUDA cores (0.70 ms for B=16 256x256 Cin=64, 8x its HBM time);
+// here the CUDA cores only stage and round the operands.
+constexpr int OPM_XS = 8;   // row padding of the X / Wm tiles: fragment loads (k = t, n = g) hit 32 distinct banks
+
+template <int CIN>
+__global__ void __launch_bounds__(256, 2) output_proj_bwd_mma_kernel(const float* __restrict__ dout,
+                                                                     const float* __restrict__ tokens, long long ld,
+                                                                     const float* __restrict__ weight,
+                                                                     float* __restrict__ dtokens,
+                                                                     float* __restrict__ partials, int B, int H, int W,
+                                                                     int tiles_x, int tiles_per_img) {
+    constexpr int XS = CIN + OPM_XS;
+    constexpr int NT = CIN / 8;          // 8-channel column tiles
+    constexpr int KSPLIT = 8 / NT;       // warps sharing a column tile split the tile's pixels (Cin = 32: two halves)
+    constexpr int NPIX = OP_TY * OP_TX;  // 128
+    extern __shared__ __align__(16) float smem[];
+    float* xs = smem;                     // [128][XS]   X at the tile's pixels, TF32-rounded
+    float* wm = xs + NPIX * XS;           // [32][XS]    Wm[k][ci], TF32-rounded, rows 27..31 zero
+    float* dys = wm + 32 * XS;            // [3][10][18] dY halo tile, TF32-rounded, zero outside the image
+    __shared__ float dbred[8][3];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int g = lane >> 2, t = lane & 3;
+
+    for (int idx = threadIdx.x; idx < 32 * CIN; idx += 256) {
+        const int k = idx / CIN, ci = idx % CIN;
+        float v = 0.f;
+        if (k < 27) v = weight[((k / 9) * CIN + ci) * 9 + k % 9];
+        wm[k * XS + ci] = tf32_round(v);
+    }
+    // offsets of this lane's A columns inside the halo tile: k = ks*8 + t (+4); columns >= 27 are zero
+    int aoff[8];
+    unsigned avalid = 0;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+        const int k = (j >> 1) * 8 + t + (j & 1) * 4;
+        const int kk = k < 27 ? k : 0, co = kk / 9, ky = (kk % 9) / 3, kx = kk % 3;
+        aoff[j] = co * (OP_HY * OP_HX) + (2 - ky) * OP_HX + (2 - kx);
+        if (k < 27) avalid |= 1u << j;
+    }
+    // ... and of its A^T rows m = mt*16 + g (+8) for the weight gradient
+    int moff[4];
+    unsigned mvalid = 0;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+        const int m = (j >> 1) * 16 + g + (j & 1) * 8;
+        const int mm = m < 27 ? m : 0, co = mm / 9, ky = (mm % 9) / 3, kx = mm % 3;
+        moff[j] = co * (OP_HY * OP_HX) + (2 - ky) * OP_HX + (2 - kx);
+        if (m < 27) mvalid |= 1u << j;
+    }
+    const int nt2 = warp % NT, kh = warp / NT;   // weight-gradient role of this warp
+    float dwacc[2][4];
+#pragma unroll
+    for (int mt = 0; mt < 2; ++mt)
+#pragma unroll
+        for (int c = 0; c < 4; ++c) dwacc[mt][c] = 0.f;
+    float db0 = 0.f, db1 = 0.f, db2 = 0.f;
+
+    const int total = B * tiles_per_img;
+    for (int tile = blockIdx.x; tile < total; tile += gridDim.x) {
+        const int b = tile / tiles_per_img, tl = tile % tiles_per_img;
+        const int ty0 = (tl / tiles_x) * OP_TY, tx0 = (tl % tiles_x) * OP_TX;
+        __syncthreads();   // the previous tile's readers are done (also orders the wm fill before its first use)
+        for (int idx = threadIdx.x; idx < NPIX * (CIN / 4); idx += 256) {
+            const int pix = idx / (CIN / 4), c4 = (idx % (CIN / 4)) * 4;
+            const int y = ty0 + pix / OP_TX, x = tx0 + pix % OP_TX;
+            float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (y < H && x < W) v = *reinterpret_cast<const float4*>(tokens + (((long long)b * H + y) * W + x) * ld + c4);
+            *reinterpret_cast<float4*>(xs + pix * XS + c4) =
+                make_float4(tf32_round(v.x), tf32_round(v.y), tf32_round(v.z), tf32_round(v.w));
+        }
+        for (int idx = threadIdx.x; idx < 3 * OP_HY * OP_HX; idx += 256) {
+            const int co = idx / (OP_HY * OP_HX), rem = idx % (OP_HY * OP_HX);
+            const int hy = rem / OP_HX, hx = rem % OP_HX;
+            const int y = ty0 + hy - 1, x = tx0 + hx - 1;
+            float v = 0.f;
+            if (y >= 0 && y < H && x >= 0 && x < W) v = dout[(((long long)b * 3 + co) * H + y) * W + x];
+            dys[idx] = tf32_round(v);
+            if (hy >= 1 && hy <= OP_TY && hx >= 1 && hx <= OP_TX) {   // the tile's own pixels: bias gradient
+                db0 += co == 0 ? v : 0.f;
+                db1 += co == 1 ? v : 0.f;
+                db2 += co == 2 ? v : 0.f;
+            }
+        }
+        __syncthreads();
+
+        // ---- dX: this warp's row of 16 pixels (rows g, g + 8 of the m16 tile) ----
+        {
+            const int ly = warp;
+            uint32_t a[4][4];
+#pragma unroll
+            for (int ks = 0; ks < 4; ++ks) {
+                const float* r0 = dys + aoff[2 * ks] + ly * OP_HX + g;
+                const float* r1 = dys + aoff[2 * ks + 1] + ly * OP_HX + g;
+                a[ks][0] = (avalid >> (2 * ks)) & 1u ? __float_as_uint(r0[0]) : 0u;
+                a[ks][1] = (avalid >> (2 * ks)) & 1u ? __float_as_uint(r0[8]) : 0u;
+                a[ks][2] = (avalid >> (2 * ks + 1)) & 1u ? __float_as_uint(r1[0]) : 0u;
+                a[ks][3] = (avalid >> (2 * ks + 1)) & 1u ? __float_as_uint(r1[8]) : 0u;
+            }
+            const int y = ty0 + ly;
+#pragma unroll
+            for (int nt = 0; nt < NT; ++nt) {
+                float acc[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+                for (int ks = 0; ks < 4; ++ks) {
+                    uint32_t bf[2];
+                    bf[0] = __float_as_uint(wm[(ks * 8 + t) * XS + nt * 8 + g]);
+                    bf[1] = __float_as_uint(wm[(ks * 8 + t + 4) * XS + nt * 8 + g]);
+                    mma_tf32_16x8x8(acc, a[ks], bf);
+                }
+                if (y < H) {
+                    float* dp = dtokens + (((long long)b * H + y) * W + tx0) * CIN + nt * 8 + 2 * t;
+                    if (tx0 + g < W) *reinterpret_cast<float2*>(dp + (long long)g * CIN) = make_float2(acc[0], acc[1]);
+                    if (tx0 + g + 8 < W) *reinterpret_cast<float2*>(dp + (long long)(g + 8) * CIN) = make_float2(acc[2], acc[3]);
+                }
+            }
+        }
+        // ---- dW: rows = the 32 A columns, this warp's 8 input channels, contraction over its share of the pixels ----
+        {
+            constexpr int STEPS = NPIX / 8 / KSPLIT;
+#pragma unroll 4
+            for (int s8 = 0; s8 < STEPS; ++s8) {
+                const int pix = (kh * STEPS + s8) * 8 + t;           // pixel of fragment column t (t + 4 is in the same row)
+                const int poff = (pix / OP_TX) * OP_HX + pix % OP_TX;
+                uint32_t bf[2];
+                bf[0] = __float_as_uint(xs[pix * XS + nt2 * 8 + g]);
+                bf[1] = __float_as_uint(xs[(pix + 4) * XS + nt2 * 8 + g]);
+#pragma unroll
+                for (int mt = 0; mt < 2; ++mt) {
+                    uint32_t a[4];
+                    const bool v0 = (mvalid >> (2 * mt)) & 1u, v1 = (mvalid >> (2 * mt + 1)) & 1u;
+                    a[0] = v0 ? __float_as_uint(dys[moff[2 * mt] + poff]) : 0u;
+                    a[1] = v1 ? __float_as_uint(dys[moff[2 * mt + 1] + poff]) : 0u;
+                    a[2] = v0 ? __float_as_uint(dys[moff[2 * mt] + poff + 4]) : 0u;
+                    a[3] = v1 ? __float_as_uint(dys[moff[2 * mt + 1] + poff + 4]) : 0u;
+                    mma_tf32_16x8x8(dwacc[mt], a, bf);
+                }
+            }
+        }
+    }
+    // ---- per-CTA partial sums in the weight's own layout [co][ci][tap] (+ 3 bias sums), as the scalar kernel ----
+    __syncthreads();
+    float* red = smem;   // [32][CIN]
+    for (int half = 0; half < KSPLIT; ++half) {
+        if (kh == half) {
+#pragma unroll
+            for (int mt = 0; mt < 2; ++mt)
+#pragma unroll
+                for (int c = 0; c < 4; ++c) {
+                    const int m = mt * 16 + g + (c >> 1) * 8, n = nt2 * 8 + 2 * t + (c & 1);
+                    if (half == 0) red[m * CIN + n] = dwacc[mt][c];
+                    else red[m * CIN + n] += dwacc[mt][c];
+                }
+        }
+        __syncthreads();
+    }
+    float* part = partials + (long long)blockIdx.x * (27 * CIN + 3);
+    for (int idx = threadIdx.x; idx < 27 * CIN; idx += 256) {
+        const int co = idx / (9 * CIN), ci = (idx / 9) % CIN, tap = idx % 9;
+        part[idx] = red[(co * 9 + tap) * CIN + ci];
+    }
+    db0 = warp_sum(db0);
+    db1 = warp_sum(db1);
+    db2 = warp_sum(db2);
+    if (lane == 0) dbred[warp][0] = db0, dbred[warp][1] = db1, dbred[warp][2] = db2;
+    __syncthreads();
+    if (threadIdx.x < 3) {
+        float sum = 0.f;
+        for (int ww = 0; ww < 8; ++ww) sum += dbred[ww][threadIdx.x];
+        part[27 * CIN + threadIdx.x] = sum;
+    }
+}
+
 __global__ void output_proj_reduce_kernel(const float* __restrict__ partials, float* __restrict__ dweight,
                                           float* __restrict__ dbias, int P, int Cin) {
     const int n = 27 * Cin + 3;
@@ -651,7 +829,25 @@ extern "C" int uwr_output_proj_bwd(const float* dout_img, const float* tokens, l
     int smem = (OP_HY * OP_HX * Cin + 3 * OP_HY * OP_HX) * (int)sizeof(float);
     const int red = 8 * 9 * Cin * (int)sizeof(float);
     if (red > smem) smem = red;
-    if (Cin == 32) {
+    if (uwr_round_outputs()) {   // single-pass TF32 mode: both gradients on the tensor cores
+        const int msmem = ((OP_TY * OP_TX + 32) * (Cin + OPM_XS) + 3 * OP_HY * OP_HX) * (int)sizeof(float);
+        if (Cin == 32) {
+            static bool configured = false;
+            if (!configured) {
+                UWR_CUDA(cudaFuncSetAttribute(output_proj_bwd_mma_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, msmem));
+                configured = true;
+            }
+            output_proj_bwd_mma_kernel<32><<<P, 256, msmem, stream>>>(dout_img, tokens, ld, weight, dtokens, workspace, B, H, W, tx, tx * ty);
+        } else {
+            static bool configured = false;
+            if (!configured) {
+                UWR_CUDA(cudaFuncSetAttribute(output_proj_bwd_mma_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, msmem));
+                configured = true;
+            }
+            output_proj_bwd_mma_kernel<64><<<P, 256, msmem, stream>>>(dout_img, tokens, ld, weight, dtokens, workspace, B, H, W, tx, tx * ty);
+        }
+        UWR_CHECK_LAUNCH("output_proj_bwd_mma_kernel");
+    } else if (Cin == 32) {
         static bool configured = false;
         if (!configured) {
             UWR_CUDA(cudaFuncSetAttribute(output_proj_bwd_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
