@@ -255,20 +255,28 @@ def test_dwconv_gelu(exact, B, H, Ch, mode):
 
 
 # ------------------------------------------------------------------------------- boundary convs
-def test_input_proj():
+@pytest.mark.parametrize("precision", ["tf32", "tf32x3"])
+@pytest.mark.parametrize("Cout,H", [(32, 48), (64, 40), (32, 24)])
+def test_input_proj(ops, Cout, H, precision):
+    """Default mode: tensor-core kernels (forward 3xTF32 = fp32-level, weight gradient single-pass TF32); tf32x3: the
+    scalar fp32 kernels.  H = 40 and 24 leave ragged 16-pixel tiles."""
     from uwr.blocks import InputProjFn
-    B, H = 2, 48
-    img = _r(B, 3, H, H, seed=1)
-    w, b = _r(32, 3, 3, 3, seed=2, scale=0.2).requires_grad_(), _r(32, seed=3, scale=0.1).requires_grad_()
-    tok = InputProjFn.apply(img, w, b, 0.01)
-    wd, bd = w.detach().double().requires_grad_(), b.detach().double().requires_grad_()
-    ref = F.leaky_relu(F.conv2d(img.double(), wd, bd, padding=1), 0.01).flatten(2).transpose(1, 2)
-    assert rel_l2(tok, ref) < TOL_FP32
-    g = _r(B, H * H, 32, seed=4)
-    tok.backward(g)
-    ref.backward(g.double())
-    assert rel_l2(w.grad, wd.grad) < TOL_FP32 * 10
-    assert rel_l2(b.grad, bd.grad) < TOL_FP32 * 10
+    ops.set_gemm_precision(precision)
+    try:
+        B = 2
+        img = _r(B, 3, H, H, seed=1)
+        w, b = _r(Cout, 3, 3, 3, seed=2, scale=0.2).requires_grad_(), _r(Cout, seed=3, scale=0.1).requires_grad_()
+        tok = InputProjFn.apply(img, w, b, 0.01)
+        wd, bd = w.detach().double().requires_grad_(), b.detach().double().requires_grad_()
+        ref = F.leaky_relu(F.conv2d(img.double(), wd, bd, padding=1), 0.01).flatten(2).transpose(1, 2)
+        assert rel_l2(tok, ref) < TOL_FP32
+        g = _r(B, H * H, Cout, seed=4)
+        tok.backward(g)
+        ref.backward(g.double())
+        assert rel_l2(w.grad, wd.grad) < (TOL_TF32 if precision == "tf32" else TOL_FP32 * 10)
+        assert rel_l2(b.grad, bd.grad) < TOL_FP32 * 10
+    finally:
+        ops.set_gemm_precision("tf32")
 
 
 @pytest.mark.parametrize("precision", ["tf32", "tf32x3"])

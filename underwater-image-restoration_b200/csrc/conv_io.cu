@@ -344,7 +344,7 @@ __global__ void __launch_bounds__(256) output_proj_bwd_kernel(const float* __res
 constexpr int OPM_XS = 8;   // row padding of the X / Wm tiles: fragment loads (k = t, n = g) hit 32 distinct banks
 
 template <int CIN>
-__global__ void __launch_bounds__(256, 2) output_proj_bwd_mma_kernel(const float* __restrict__ dout,
+__global__ void __launch_bounds__(256, 3) output_proj_bwd_mma_kernel(const float* __restrict__ dout,
                                                                      const float* __restrict__ tokens, long long ld,
                                                                      const float* __restrict__ weight,
                                                                      float* __restrict__ dtokens,
@@ -508,6 +508,196 @@ __global__ void __launch_bounds__(256, 2) output_proj_bwd_mma_kernel(const float
         float sum = 0.f;
         for (int ww = 0; ww < 8; ++ww) sum += dbred[ww][threadIdx.x];
         part[27 * CIN + threadIdx.x] = sum;
+    }
+}
+
+// InputProj (3 -> Cout, + LeakyReLU) on the tensor cores.  A[p][k] = img[ci][py + ky - 1][px + kx - 1], k = ci*9 + ky*3 + kx
+// (27 columns padded to 32), read straight from the 3 x 10 x 18 halo tile of the image:
+//   forward   T[p][co] = leaky(b[co] + sum_k A[p][k] Wm[k][co])      3xTF32 (hi/lo split of both operands): fp32-level
+//   backward  dW[k][co] = sum_p A[p][k] dZ[p][co],  dZ = dT * leaky'(T)      single-pass TF32, as every weight gradient
+// The scalar kernels above run 864 FMAs per pixel on the CUDA cores (0.15 / 0.36 ms at B=16 256x256, 7x their HBM time).
+template <int COUT>
+__global__ void __launch_bounds__(256, 2) input_proj_fwd_mma_kernel(const float* __restrict__ img,
+                                                                    const float* __restrict__ weight,
+                                                                    const float* __restrict__ bias,
+                                                                    float* __restrict__ tokens, int B, int H, int W,
+                                                                    float slope, int tiles_x, int tiles_per_img) {
+    constexpr int NT = COUT / 8;
+    __shared__ float ims[3 * OP_HY * OP_HX];
+    // Wm[k][co], rows 27..31 zero, split once: hi = RN to TF32, lo = the exact remainder
+    __shared__ uint32_t wh[32 * (COUT + OPM_XS)], wl[32 * (COUT + OPM_XS)];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int g = lane >> 2, t = lane & 3;
+    for (int idx = threadIdx.x; idx < 32 * COUT; idx += 256) {
+        const int k = idx / COUT, co = idx % COUT;
+        const float v = k < 27 ? weight[co * 27 + k] : 0.f;
+        const uint32_t hi = f2tf32(v);
+        wh[k * (COUT + OPM_XS) + co] = hi;
+        wl[k * (COUT + OPM_XS) + co] = __float_as_uint(v - __uint_as_float(hi));
+    }
+    float2 bv[NT];
+#pragma unroll
+    for (int nt = 0; nt < NT; ++nt) bv[nt] = *reinterpret_cast<const float2*>(bias + nt * 8 + 2 * t);
+    int aoff[8];
+    unsigned avalid = 0;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+        const int k = (j >> 1) * 8 + t + (j & 1) * 4;
+        const int kk = k < 27 ? k : 0;
+        aoff[j] = (kk / 9) * (OP_HY * OP_HX) + ((kk % 9) / 3) * OP_HX + kk % 3;
+        if (k < 27) avalid |= 1u << j;
+    }
+    const int total = B * tiles_per_img;
+    for (int tile = blockIdx.x; tile < total; tile += gridDim.x) {
+        const int b = tile / tiles_per_img, tl = tile % tiles_per_img;
+        const int ty0 = (tl / tiles_x) * OP_TY, tx0 = (tl % tiles_x) * OP_TX;
+        __syncthreads();
+        for (int idx = threadIdx.x; idx < 3 * OP_HY * OP_HX; idx += 256) {
+            const int ci = idx / (OP_HY * OP_HX), rem = idx % (OP_HY * OP_HX);
+            const int y = ty0 + rem / OP_HX - 1, x = tx0 + rem % OP_HX - 1;
+            float v = 0.f;
+            if (y >= 0 && y < H && x >= 0 && x < W) v = img[(((long long)b * 3 + ci) * H + y) * W + x];
+            ims[idx] = v;
+        }
+        __syncthreads();
+        const int ly = warp, y = ty0 + ly;
+        uint32_t ah[4][4], al[4][4];
+#pragma unroll
+        for (int ks = 0; ks < 4; ++ks)
+#pragma unroll
+            for (int c = 0; c < 4; ++c) {
+                const int j = 2 * ks + (c >> 1);
+                const float v = (avalid >> j) & 1u ? ims[aoff[j] + ly * OP_HX + g + (c & 1) * 8] : 0.f;
+                ah[ks][c] = f2tf32(v);
+                al[ks][c] = __float_as_uint(v - __uint_as_float(ah[ks][c]));
+            }
+        if (y < H) {
+#pragma unroll
+            for (int nt = 0; nt < NT; ++nt) {
+                float acc[4] = {bv[nt].x, bv[nt].y, bv[nt].x, bv[nt].y};
+#pragma unroll
+                for (int ks = 0; ks < 4; ++ks) {   // B fragments: k = ks*8 + t (+4), n = nt*8 + g
+                    const int o0 = (ks * 8 + t) * (COUT + OPM_XS) + nt * 8 + g, o1 = o0 + 4 * (COUT + OPM_XS);
+                    const uint32_t bh[2] = {wh[o0], wh[o1]}, bl[2] = {wl[o0], wl[o1]};
+                    mma_tf32_16x8x8(acc, al[ks], bh);
+                    mma_tf32_16x8x8(acc, ah[ks], bl);
+                    mma_tf32_16x8x8(acc, ah[ks], bh);
+                }
+#pragma unroll
+                for (int c = 0; c < 4; ++c) acc[c] = acc[c] > 0.f ? acc[c] : acc[c] * slope;
+                float* tp = tokens + (((long long)b * H + y) * W + tx0) * COUT + nt * 8 + 2 * t;
+                if (tx0 + g < W) *reinterpret_cast<float2*>(tp + (long long)g * COUT) = make_float2(acc[0], acc[1]);
+                if (tx0 + g + 8 < W) *reinterpret_cast<float2*>(tp + (long long)(g + 8) * COUT) = make_float2(acc[2], acc[3]);
+            }
+        }
+    }
+}
+
+template <int COUT>
+__global__ void __launch_bounds__(256, 3) input_proj_bwd_mma_kernel(const float* __restrict__ dtokens,
+                                                                    const float* __restrict__ tokens,
+                                                                    const float* __restrict__ img,
+                                                                    float* __restrict__ partials, int B, int H, int W,
+                                                                    float slope, int tiles_x, int tiles_per_img) {
+    constexpr int ZS = COUT + OPM_XS;
+    constexpr int NT = COUT / 8, KSPLIT = 8 / NT, NPIX = OP_TY * OP_TX;
+    constexpr int C4 = COUT / 4;            // float4 groups per token; 256 % C4 == 0: a thread always stages the same group
+    extern __shared__ __align__(16) float smem[];
+    float* zs = smem;                       // [128][ZS]  dZ at the tile's pixels, TF32-rounded
+    float* ims = zs + NPIX * ZS;            // [3][10][18] image halo tile, TF32-rounded
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int g = lane >> 2, t = lane & 3;
+    int moff[4];
+    unsigned mvalid = 0;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+        const int m = (j >> 1) * 16 + g + (j & 1) * 8;
+        const int mm = m < 27 ? m : 0;
+        moff[j] = (mm / 9) * (OP_HY * OP_HX) + ((mm % 9) / 3) * OP_HX + mm % 3;
+        if (m < 27) mvalid |= 1u << j;
+    }
+    const int nt2 = warp % NT, kh = warp / NT;
+    float dwacc[2][4];
+#pragma unroll
+    for (int mt = 0; mt < 2; ++mt)
+#pragma unroll
+        for (int c = 0; c < 4; ++c) dwacc[mt][c] = 0.f;
+    float4 dbs = make_float4(0.f, 0.f, 0.f, 0.f);   // bias gradient of this thread's channel group (full fp32 dZ)
+    const int c4 = (threadIdx.x % C4) * 4;
+
+    const int total = B * tiles_per_img;
+    for (int tile = blockIdx.x; tile < total; tile += gridDim.x) {
+        const int b = tile / tiles_per_img, tl = tile % tiles_per_img;
+        const int ty0 = (tl / tiles_x) * OP_TY, tx0 = (tl % tiles_x) * OP_TX;
+        __syncthreads();
+        for (int idx = threadIdx.x; idx < NPIX * C4; idx += 256) {
+            const int pix = idx / C4;
+            const int y = ty0 + pix / OP_TX, x = tx0 + pix % OP_TX;
+            float4 d = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (y < H && x < W) {
+                const long long tok = ((long long)b * H + y) * W + x;
+                const float4 o = *reinterpret_cast<const float4*>(tokens + tok * COUT + c4);
+                d = *reinterpret_cast<const float4*>(dtokens + tok * COUT + c4);
+                d.x *= o.x > 0.f ? 1.f : slope; d.y *= o.y > 0.f ? 1.f : slope;
+                d.z *= o.z > 0.f ? 1.f : slope; d.w *= o.w > 0.f ? 1.f : slope;
+            }
+            dbs.x += d.x; dbs.y += d.y; dbs.z += d.z; dbs.w += d.w;
+            *reinterpret_cast<float4*>(zs + pix * ZS + c4) =
+                make_float4(tf32_round(d.x), tf32_round(d.y), tf32_round(d.z), tf32_round(d.w));
+        }
+        for (int idx = threadIdx.x; idx < 3 * OP_HY * OP_HX; idx += 256) {
+            const int ci = idx / (OP_HY * OP_HX), rem = idx % (OP_HY * OP_HX);
+            const int y = ty0 + rem / OP_HX - 1, x = tx0 + rem % OP_HX - 1;
+            float v = 0.f;
+            if (y >= 0 && y < H && x >= 0 && x < W) v = img[(((long long)b * 3 + ci) * H + y) * W + x];
+            ims[idx] = tf32_round(v);
+        }
+        __syncthreads();
+        constexpr int STEPS = NPIX / 8 / KSPLIT;
+#pragma unroll 4
+        for (int s8 = 0; s8 < STEPS; ++s8) {
+            const int pix = (kh * STEPS + s8) * 8 + t;
+            const int poff = (pix / OP_TX) * OP_HX + pix % OP_TX;
+            uint32_t bf[2];
+            bf[0] = __float_as_uint(zs[pix * ZS + nt2 * 8 + g]);
+            bf[1] = __float_as_uint(zs[(pix + 4) * ZS + nt2 * 8 + g]);
+#pragma unroll
+            for (int mt = 0; mt < 2; ++mt) {
+                uint32_t a[4];
+                const bool v0 = (mvalid >> (2 * mt)) & 1u, v1 = (mvalid >> (2 * mt + 1)) & 1u;
+                a[0] = v0 ? __float_as_uint(ims[moff[2 * mt] + poff]) : 0u;
+                a[1] = v1 ? __float_as_uint(ims[moff[2 * mt + 1] + poff]) : 0u;
+                a[2] = v0 ? __float_as_uint(ims[moff[2 * mt] + poff + 4]) : 0u;
+                a[3] = v1 ? __float_as_uint(ims[moff[2 * mt + 1] + poff + 4]) : 0u;
+                mma_tf32_16x8x8(dwacc[mt], a, bf);
+            }
+        }
+    }
+    // per-CTA partials [k][Cout], k = 27 -> bias (the layout input_proj_reduce_kernel sums)
+    __syncthreads();
+    float* red = smem;          // [32][COUT]
+    float* dbr = smem + 32 * COUT;   // [256][4]
+    for (int half = 0; half < KSPLIT; ++half) {
+        if (kh == half) {
+#pragma unroll
+            for (int mt = 0; mt < 2; ++mt)
+#pragma unroll
+                for (int c = 0; c < 4; ++c) {
+                    const int m = mt * 16 + g + (c >> 1) * 8, n = nt2 * 8 + 2 * t + (c & 1);
+                    if (half == 0) red[m * COUT + n] = dwacc[mt][c];
+                    else red[m * COUT + n] += dwacc[mt][c];
+                }
+        }
+        __syncthreads();
+    }
+    *reinterpret_cast<float4*>(dbr + threadIdx.x * 4) = dbs;
+    __syncthreads();
+    float* part = partials + (long long)blockIdx.x * 28 * COUT;
+    for (int idx = threadIdx.x; idx < 27 * COUT; idx += 256) part[idx] = red[idx];
+    if (threadIdx.x < COUT) {
+        float sum = 0.f;
+        for (int j = 0; j < 256 / C4; ++j) sum += dbr[(j * C4 + threadIdx.x / 4) * 4 + threadIdx.x % 4];
+        part[27 * COUT + threadIdx.x] = sum;
     }
 }
 
@@ -743,8 +933,8 @@ int ew_blocks(long long n, int threads) {
     return (int)(b < 1 ? 1 : b);
 }
 
-int persistent_ctas(int tiles) {
-    int p = 2 * uwr_sm_count();
+int persistent_ctas(int tiles, int per_sm = 2) {
+    int p = per_sm * uwr_sm_count();
     if (p > tiles) p = tiles;
     return p < 1 ? 1 : p;
 }
@@ -757,6 +947,14 @@ extern "C" int uwr_input_proj_fwd(const float* img, const float* weight, const f
     UWR_REQUIRE(img && weight && bias && tokens, "uwr_input_proj_fwd: null pointer");
     UWR_REQUIRE(Cin >= 1 && Cin <= IP_MAXCIN && (Cout == 32 || Cout == 64), "uwr_input_proj_fwd: Cin<=4, Cout in {32,64}");
     UWR_REQUIRE(B > 0 && B <= 65535, "uwr_input_proj_fwd: bad batch");
+    if (Cin == 3 && uwr_round_outputs()) {   // tensor-core kernel (3xTF32: fp32-level); tf32x3 mode keeps the scalar one
+        const int mx = uwr_cdiv(W, OP_TX), my = uwr_cdiv(H, OP_TY);
+        const int P = persistent_ctas(B * mx * my, 2);
+        if (Cout == 32) input_proj_fwd_mma_kernel<32><<<P, 256, 0, stream>>>(img, weight, bias, tokens, B, H, W, slope, mx, mx * my);
+        else input_proj_fwd_mma_kernel<64><<<P, 256, 0, stream>>>(img, weight, bias, tokens, B, H, W, slope, mx, mx * my);
+        UWR_CHECK_LAUNCH("input_proj_fwd_mma_kernel");
+        return 0;
+    }
     const int tx = uwr_cdiv(W, IP_TS), ty = uwr_cdiv(H, IP_TS);
     dim3 grid(tx * ty, 1, B);
     if (Cout == 32) input_proj_fwd_kernel<1><<<grid, 256, 0, stream>>>(img, weight, bias, tokens, H, W, Cin, Cout, slope, tx);
@@ -766,8 +964,8 @@ extern "C" int uwr_input_proj_fwd(const float* img, const float* weight, const f
 }
 
 extern "C" size_t uwr_input_proj_bwd_workspace_bytes(int B, int H, int W, int Cin, int Cout) {
-    const int tiles = B * uwr_cdiv(W, IP_TS) * uwr_cdiv(H, IP_TS);
-    return (size_t)persistent_ctas(tiles) * (Cin * 9 + 1) * Cout * sizeof(float);
+    const int tiles = B * uwr_cdiv(W, OP_TX) * uwr_cdiv(H, OP_TY);   // the tensor-core kernel's tiling: the larger count
+    return (size_t)persistent_ctas(tiles, 3) * (Cin * 9 + 1) * Cout * sizeof(float);
 }
 
 extern "C" int uwr_input_proj_bwd(const float* dtokens, const float* tokens, const float* img, float* dweight,
@@ -776,6 +974,25 @@ extern "C" int uwr_input_proj_bwd(const float* dtokens, const float* tokens, con
     cudaStream_t stream = (cudaStream_t)stream_;
     UWR_REQUIRE(dtokens && tokens && img && dweight && dbias && workspace, "uwr_input_proj_bwd: null pointer");
     UWR_REQUIRE(Cin >= 1 && Cin <= IP_MAXCIN && (Cout == 32 || Cout == 64), "uwr_input_proj_bwd: Cin<=4, Cout in {32,64}");
+    if (Cin == 3 && uwr_round_outputs()) {
+        const int mx = uwr_cdiv(W, OP_TX), my = uwr_cdiv(H, OP_TY);
+        const int P = persistent_ctas(B * mx * my, 3);
+        const int msmem = (OP_TY * OP_TX * (Cout + OPM_XS) + 3 * OP_HY * OP_HX) * (int)sizeof(float);
+        if (Cout == 32) {
+            input_proj_bwd_mma_kernel<32><<<P, 256, msmem, stream>>>(dtokens, tokens, img, workspace, B, H, W, slope, mx, mx * my);
+        } else {
+            static bool configured = false;
+            if (!configured) {
+                UWR_CUDA(cudaFuncSetAttribute(input_proj_bwd_mma_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, msmem));
+                configured = true;
+            }
+            input_proj_bwd_mma_kernel<64><<<P, 256, msmem, stream>>>(dtokens, tokens, img, workspace, B, H, W, slope, mx, mx * my);
+        }
+        UWR_CHECK_LAUNCH("input_proj_bwd_mma_kernel");
+        input_proj_reduce_kernel<<<uwr_cdiv(28 * Cout, 128), 128, 0, stream>>>(workspace, dweight, dbias, P, Cin, Cout);
+        UWR_CHECK_LAUNCH("input_proj_reduce_kernel");
+        return 0;
+    }
     const int tx = uwr_cdiv(W, IP_TS), ty = uwr_cdiv(H, IP_TS);
     const int P = persistent_ctas(B * tx * ty);
     if (Cout == 32)
@@ -814,7 +1031,7 @@ extern "C" int uwr_output_proj_fwd(const float* tokens, long long ld, const floa
 
 extern "C" size_t uwr_output_proj_bwd_workspace_bytes(int B, int H, int W, int Cin) {
     const int tiles = B * uwr_cdiv(W, OP_TX) * uwr_cdiv(H, OP_TY);
-    return (size_t)persistent_ctas(tiles) * (27 * Cin + 3) * sizeof(float);
+    return (size_t)persistent_ctas(tiles, 3) * (27 * Cin + 3) * sizeof(float);   // the tensor-core kernel runs 3 CTAs per SM
 }
 
 extern "C" int uwr_output_proj_bwd(const float* dout_img, const float* tokens, long long ld, const float* weight,
@@ -824,7 +1041,7 @@ extern "C" int uwr_output_proj_bwd(const float* dout_img, const float* tokens, l
     UWR_REQUIRE(dout_img && tokens && weight && dtokens && dweight && dbias && workspace, "uwr_output_proj_bwd: null pointer");
     UWR_REQUIRE((Cin == 32 || Cin == 64) && ld % 4 == 0, "uwr_output_proj_bwd: Cin in {32,64}, ld %% 4 == 0");
     const int tx = uwr_cdiv(W, OP_TX), ty = uwr_cdiv(H, OP_TY);
-    const int P = persistent_ctas(B * tx * ty);
+    const int P = persistent_ctas(B * tx * ty, uwr_round_outputs() ? 3 : 2);
     // tile + dY halo; the cross-warp reduction reuses the same buffer (8 * 9 * Cin floats)
     int smem = (OP_HY * OP_HX * Cin + 3 * OP_HY * OP_HX) * (int)sizeof(float);
     const int red = 8 * 9 * Cin * (int)sizeof(float);
