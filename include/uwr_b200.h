@@ -99,6 +99,39 @@ int uwr_set_gemm_cluster(int mode);
 size_t uwr_gemm_tcgen05_workspace_bytes(int M, int N, int K, int a_km);
 int uwr_gemm_tcgen05(const uwr_gemm_desc* d, uwr_stream_t stream);
 
+/* ---- convolutions on token (NHWC) tensors as implicit GEMMs on the tcgen05 kernel ------------------------------
+ * Replaces im2col + GEMM for the dense convolutions between scales: Downsample Conv4x4 s2 p1 (AST.py:408-424), the 3x3
+ * convolutions of NewBigFRFN (block.py:42-153) and SpectralTransformer (SpectralTransformer.py:133-159).  The im2col
+ * matrix is never written: x (B*H*W, ld_x) is addressed by a 4-D (C, W, H, B) tensor map and every K chunk (32 channels of
+ * one tap) is one TMA box at the tap's offset; out-of-image pixels are zero-filled by TMA (= the padding), stride 2 uses
+ * the map's element strides.  Operands must be TF32-rounded (as for uwr_gemm_tcgen05).
+ *   mode 0: y[B*OH*OW, Cout] = im2col(x) . w^T (+ bias)      w: (Cout, kh*kw*Cin), K index = (ky, kx, ci)
+ *           (the data gradient of a stride-1 convolution is the same call on dy with the flipped, transposed weights)
+ *   mode 1: dw[Cout, kh*kw*Cin] = dy^T . im2col(x)            dy: (B*OH*OW, ld_dy); contraction split across CTAs
+ * Served when Cin % 32 == 0 and OH*OW is a multiple of 128 (mode 0) / 32 (mode 1) with power-of-two or box-multiple
+ * widths (see `_supported`); callers fall back to uwr_im2col_* + uwr_gemm_tcgen05 otherwise. */
+typedef struct {
+    int mode;
+    const float* x;
+    long long ld_x;
+    int B, H, W, Cin;
+    int kh, kw, stride, pad;
+    int Cout;
+    const float* w;      /* mode 0 */
+    const float* bias;   /* mode 0, optional */
+    float* y;            /* mode 0 */
+    long long ld_y;
+    int round_out;       /* mode 0: round y to TF32 at the store (it feeds another tensor-core product) */
+    const float* dy;     /* mode 1 */
+    long long ld_dy;
+    float* dw;           /* mode 1, dense (Cout, kh*kw*Cin) */
+    float* workspace;    /* mode 1: uwr_convgemm_tcgen05_workspace_bytes */
+    size_t workspace_bytes;
+} uwr_convgemm_desc;
+int uwr_convgemm_tcgen05_supported(const uwr_convgemm_desc* d);
+size_t uwr_convgemm_tcgen05_workspace_bytes(const uwr_convgemm_desc* d);
+int uwr_convgemm_tcgen05(const uwr_convgemm_desc* d, uwr_stream_t stream);
+
 /* TF32 operand preparation (tcgen05 truncates; operands are rounded to nearest where produced).
  * In single-pass mode (uwr_set_gemm_precision(1)) the producers of GEMM operands — layernorm_fwd,
  * window_attn_fwd/bwd, dwconv_gelu_fwd (h2) / _bwd (du), im2col — round at their stores.

@@ -123,3 +123,41 @@ def test_t5_cluster_multicast_matches_single_cta(lay, M, N, K):
             ops.set_gemm_cluster(True)
     assert torch.equal(outs[True], outs[False])
     assert rel_l2(outs[True], ref) < 2e-5
+
+
+@pytest.mark.parametrize("B,H,W,Cin,Cout,k,stride,pad", [
+    (2, 16, 16, 32, 64, 3, 1, 1),       # 2 rows of 16 x 8 = one 128-pixel box
+    (1, 32, 32, 64, 32, 3, 1, 1),
+    (2, 64, 64, 32, 16, 3, 1, 1),       # thin output (PixelUnshuffle downsample of SpectralTransformer)
+    (1, 128, 128, 32, 32, 3, 1, 1),     # one box = one full row
+    (1, 256, 256, 32, 8, 3, 1, 1),      # half a row per box
+    (2, 32, 32, 64, 128, 4, 2, 1),      # AST Downsample: Conv4x4 stride 2 (element strides in the tensor map)
+    (1, 64, 64, 32, 64, 4, 2, 1),
+    (1, 256, 256, 32, 64, 4, 2, 1),
+    (2, 16, 48, 32, 32, 3, 1, 1),       # width neither a power of two nor a multiple of the box: must be refused
+])
+def test_conv_implicit_gemm(B, H, W, Cin, Cout, k, stride, pad):
+    """uwr_convgemm_tcgen05 (TMA-materialised im2col tiles, no im2col buffer) vs fp64 F.conv2d on the same TF32-rounded
+    operands: forward (+ bias) and weight gradient."""
+    from uwr import ops
+    x = _r(B * H * W, Cin, seed=1)                                         # tokens, NHWC
+    w = _r(Cout, Cin, k, k, seed=2, scale=0.1)
+    bias = _r(Cout, seed=3)
+    wmat = w.permute(0, 2, 3, 1).reshape(Cout, k * k * Cin).contiguous()   # K index = (ky, kx, ci)
+    y = ops.conv_gemm_fwd(x, wmat, bias, B, H, W, k, k, stride, pad)
+    if W == 48:
+        assert y is None
+        return
+    assert y is not None
+    xd = x.double().view(B, H, W, Cin).permute(0, 3, 1, 2)
+    ref = F.conv2d(xd, w.double(), bias.double(), stride=stride, padding=pad)
+    OH, OW = ref.shape[2], ref.shape[3]
+    torch.cuda.synchronize()
+    assert rel_l2(y.view(B, OH, OW, Cout), ref.permute(0, 2, 3, 1)) < 1e-5
+    dy = _r(B * OH * OW, Cout, seed=4)
+    dw = ops.conv_gemm_wgrad(dy, x, B, H, W, k, k, stride, pad)
+    assert dw is not None
+    wd = w.double().requires_grad_()
+    F.conv2d(xd, wd, None, stride=stride, padding=pad).backward(dy.double().view(B, OH, OW, Cout).permute(0, 3, 1, 2))
+    torch.cuda.synchronize()
+    assert rel_l2(dw.view(Cout, k, k, Cin), wd.grad.permute(0, 2, 3, 1)) < 1e-5

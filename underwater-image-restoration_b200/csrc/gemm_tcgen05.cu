@@ -35,7 +35,22 @@ constexpr int T5_THREADS = 64 + EPI_WARPS * 32;
 
 enum { LAY_NT = 0, LAY_NN = 1, LAY_TN = 2 };
 
+// Virtual im2col operand (template parameter CV): the token matrix x (B*H*W, ld) is addressed as a 4-D (C, W, H, B)
+// tensor and each 32-channel K chunk (CV = 1: A operand, rows = 128 output pixels) or 32-wide column group (CV = 2: B
+// operand of the weight gradient, rows = 32 output pixels) is ONE box at the tap's offset -- out-of-image pixels are
+// zero-filled by TMA (the padding), a stride-2 convolution uses the map's element strides.  No im2col buffer.
+struct T5Conv {
+    int cpt;      // 32-channel chunks per tap (Cin / 32)
+    int kw;       // kernel width: tap -> (ky, kx) = (tap / kw, tap % kw)
+    int taps;     // kh * kw
+    int pad, stride;
+    int ow, ohw;  // output width, output pixels per image
+    int cin;
+    int nb;       // batch: a coordinate >= nb in the outermost dimension reads zeros (padding column groups)
+};
+
 struct T5Params {
+    T5Conv cv;
     float* C;
     long long ldc;
     int M, N;            // output extent
@@ -76,7 +91,7 @@ __host__ __device__ constexpr int t5_smem_bytes() {
 // the L2 -> SM operand traffic per CTA and contraction chunk drops from A + B to A + B/2 (48 -> 32 KB at BN = 256) —
 // the tensor-bound shapes are limited by exactly that traffic.  A stage may only be refilled when BOTH CTAs' MMAs have
 // consumed it: every CTA's tcgen05.commit arrives on the stage's empty barrier in both CTAs (count CL).
-template <int BN, int LAY, int EPI, int HF = 0, int CL = 1>
+template <int BN, int LAY, int EPI, int HF = 0, int CL = 1, int CV = 0>
 __global__ void __launch_bounds__(T5_THREADS, 1)
 gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapB,
                     const T5Params p) {
@@ -151,7 +166,15 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_const
                     uint8_t* sa = smem + stage * STAGE_BYTES;
                     uint8_t* sb = sa + A_BYTES;
                     mbar_expect_tx(&full_bar[stage], STAGE_BYTES);
-                    if (!A_MN) {
+                    if (CV == 1) {
+                        // virtual im2col rows: the tile's 128 output pixels (one box) at tap (ky, kx), channels c0..c0+31
+                        const int m0 = tm * TM, b = m0 / p.cv.ohw, r = m0 - b * p.cv.ohw;
+                        const int oy0 = r / p.cv.ow, ox0 = r - oy0 * p.cv.ow;
+                        const int tap = c / p.cv.cpt, c0 = (c - tap * p.cv.cpt) * KC;
+                        const int ky = tap / p.cv.kw, kx = tap - ky * p.cv.kw;
+                        tma_load_4d(sa, &mapA, &full_bar[stage], c0, ox0 * p.cv.stride + kx - p.cv.pad,
+                                    oy0 * p.cv.stride + ky - p.cv.pad, b);
+                    } else if (!A_MN) {
                         tma_load_2d(sa, &mapA, &full_bar[stage], c * KC, tm * TM);
                     } else {
                         // MN-major: one 32(mn) x 32(k) box per 32-wide group -> [group][k][128 B]
@@ -159,7 +182,18 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_const
                         for (int g = 0; g < TM / 32; ++g)
                             tma_load_2d(sa + g * 4096, &mapA, &full_bar[stage], tm * TM + g * 32, c * KC);
                     }
-                    if (CL == 1) {
+                    if (CV == 2) {
+                        // virtual im2col columns: this chunk's 32 output pixels x the 32-channel group of tap (ky, kx)
+                        const int k0 = c * KC, b = k0 / p.cv.ohw, r = k0 - b * p.cv.ohw;
+                        const int oy0 = r / p.cv.ow, ox0 = r - oy0 * p.cv.ow;
+#pragma unroll
+                        for (int g = 0; g < BN / 32; ++g) {
+                            const int n0 = tn * BN + g * 32, tap = n0 / p.cv.cin, c0 = n0 - tap * p.cv.cin;
+                            const int ky = tap / p.cv.kw, kx = tap - ky * p.cv.kw;
+                            tma_load_4d(sb + g * 4096, &mapB, &full_bar[stage], c0, ox0 * p.cv.stride + kx - p.cv.pad,
+                                        oy0 * p.cv.stride + ky - p.cv.pad, tap < p.cv.taps ? b : p.cv.nb);
+                        }
+                    } else if (CL == 1) {
                         if (!B_MN) {
                             tma_load_2d(sb, &mapB, &full_bar[stage], c * KC, tn * BN);
                         } else {
@@ -450,10 +484,10 @@ T5Split t5_plan(int M, int N, int Kc, int lay, int bn) {
     return sp;
 }
 
-template <int BN, int LAY, int EPI, int HF = 0, int CL = 1>
+template <int BN, int LAY, int EPI, int HF = 0, int CL = 1, int CV = 0>
 int t5_launch(const CUtensorMap& ma, const CUtensorMap& mb, const T5Params& p, cudaStream_t stream) {
     constexpr int smem = t5_smem_bytes<BN>();
-    auto kern = gemm_tcgen05_kernel<BN, LAY, EPI, HF, CL>;
+    auto kern = gemm_tcgen05_kernel<BN, LAY, EPI, HF, CL, CV>;
     static bool configured = false;
     if (!configured) {
         UWR_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
@@ -596,7 +630,7 @@ extern "C" int uwr_gemm_tcgen05(const uwr_gemm_desc* d, uwr_stream_t stream_) {
         }
     }
 
-    T5Params p;
+    T5Params p{};
     p.C = d->C; p.ldc = d->ldc; p.M = d->M; p.N = d->N;
     p.chunks = uwr_cdiv(d->K, KC);
     p.chunks_per_split = sp.chunks_per_split; p.splits = sp.splits; p.split_stride = 0;
@@ -624,6 +658,142 @@ extern "C" int uwr_gemm_tcgen05(const uwr_gemm_desc* d, uwr_stream_t stream_) {
         int blocks = (int)((n / 4 + 255) / 256);
         if (blocks > 4 * uwr_sm_count()) blocks = 4 * uwr_sm_count();
         t5_splitk_reduce_kernel<<<blocks, 256, 0, stream>>>(d->workspace, d->C, n, n, sp.splits);
+        UWR_CHECK_LAUNCH("t5_splitk_reduce_kernel");
+    }
+    return 0;
+}
+
+
+// ------------------------------------------------------------------------------------------------------------------
+// Convolutions on token (NHWC) tensors as implicit GEMMs: the im2col matrix is a *view* that TMA materialises tile by
+// tile straight into shared memory (T5Conv above), never in HBM.  Replaces im2col_* + uwr_gemm_tcgen05 for
+//   3x3 stride 1 pad 1   (block.py:42-153 Down/Upsample + in/out convs, SpectralTransformer.py:133-159)
+//   4x4 stride 2 pad 1   (AST.py:408-424 Downsample)
+// mode 0: y = im2col(x) w^T + bias (forward; also the stride-1 data gradient, called with flipped weights);
+// mode 1: dw = dy^T im2col(x) (weight gradient, contraction over the output pixels, split across CTAs).
+namespace {
+
+struct ConvGeom {
+    int OH, OW, taps, bw, bh, pw, ph;
+};
+bool conv_geom(const uwr_convgemm_desc* d, ConvGeom& g) {
+    if (d->kh < 1 || d->kw < 1 || d->kh > 7 || d->kw > 7 || d->stride < 1 || d->stride > 2 || d->pad < 0 || d->pad > 3) return false;
+    g.OH = (d->H + 2 * d->pad - d->kh) / d->stride + 1;
+    g.OW = (d->W + 2 * d->pad - d->kw) / d->stride + 1;
+    g.taps = d->kh * d->kw;
+    if (g.OH < 1 || g.OW < 1) return false;
+    // mode 0: one box = 128 output pixels = bw x bh (part of a row, or whole rows); mode 1: 32 output pixels = pw x ph
+    g.bw = g.OW < TM ? g.OW : TM;  g.bh = TM / g.bw;
+    g.pw = g.OW < KC ? g.OW : KC;  g.ph = KC / g.pw;
+    if (g.bw * g.bh != TM || g.pw * g.ph != KC) return false;            // OW a power of two below the box, or a multiple
+    if (g.OW % g.bw || g.OH % g.bh || g.OW % g.pw || g.OH % g.ph) return false;
+    if (g.bw * d->stride > 256 || g.bh * d->stride > 256) return false;  // TMA box limit
+    return true;
+}
+// (C, W, H, B) view of the token matrix; the box covers bw x bh output pixels of one tap (element strides = conv stride)
+int encode_conv(CUtensorMap* m, const uwr_convgemm_desc* d, int bw, int bh, CUtensorMapSwizzle swz) {
+    cuuint64_t dims[4] = {(cuuint64_t)d->Cin, (cuuint64_t)d->W, (cuuint64_t)d->H, (cuuint64_t)d->B};
+    cuuint64_t strides[3] = {(cuuint64_t)d->ld_x * 4, (cuuint64_t)d->ld_x * 4 * d->W, (cuuint64_t)d->ld_x * 4 * d->W * d->H};
+    cuuint32_t box[4] = {KC, (cuuint32_t)((bw - 1) * d->stride + 1), (cuuint32_t)((bh - 1) * d->stride + 1), 1};
+    cuuint32_t es[4] = {1, (cuuint32_t)d->stride, (cuuint32_t)d->stride, 1};
+    EncodeTiledFn enc = encode_tiled_fn();
+    if (!enc) {
+        uwr_set_error("cuTensorMapEncodeTiled is not available from the driver");
+        return -3;
+    }
+    CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, (void*)d->x, dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                     swz, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) {
+        uwr_set_error("cuTensorMapEncodeTiled(conv 4d) failed: %d (C %d W %d H %d B %d ld %lld box %u x %u stride %d)", (int)r,
+                      d->Cin, d->W, d->H, d->B, d->ld_x, box[1], box[2], d->stride);
+        return -3;
+    }
+    return 0;
+}
+
+template <int BN>
+int conv_dispatch(int mode, const CUtensorMap& ma, const CUtensorMap& mb, const T5Params& p, cudaStream_t stream) {
+    if (mode == 0) return t5_launch<BN, LAY_NT, UWR_EPI_NONE, 0, 1, 1>(ma, mb, p, stream);
+    return t5_launch<BN, LAY_TN, UWR_EPI_NONE, 0, 1, 2>(ma, mb, p, stream);
+}
+
+}  // namespace
+
+extern "C" int uwr_convgemm_tcgen05_supported(const uwr_convgemm_desc* d) {
+    ConvGeom g;
+    if (!d || !d->x || d->Cin % 32 || d->ld_x % 4 || (uintptr_t)d->x % 16 || !conv_geom(d, g)) return 0;
+    if (d->B < 1 || d->Cout < 8 || d->Cout % 4) return 0;
+    const long long pixels = (long long)d->B * g.OH * g.OW;
+    if (d->mode == 0) {
+        if (!d->w || !d->y || d->ld_y % 4 || ((uintptr_t)d->w | (uintptr_t)d->y) % 16) return 0;
+        if (d->bias && (uintptr_t)d->bias % 16) return 0;
+        return (g.OH * g.OW) % TM == 0 && pixels < (1ll << 31);
+    }
+    if (d->mode == 1) {
+        if (!d->dy || !d->dw || d->ld_dy % 4 || ((uintptr_t)d->dy | (uintptr_t)d->dw) % 16) return 0;
+        return (g.OH * g.OW) % KC == 0 && pixels < (1ll << 31);
+    }
+    return 0;
+}
+
+extern "C" size_t uwr_convgemm_tcgen05_workspace_bytes(const uwr_convgemm_desc* d) {
+    ConvGeom g;
+    if (!d || d->mode != 1 || !conv_geom(d, g)) return 0;
+    const int N = g.taps * d->Cin;
+    const long long K = (long long)d->B * g.OH * g.OW;
+    const T5Split sp = t5_plan(d->Cout, N, (int)K, LAY_TN, t5_pick_bn(N));
+    return sp.splits > 1 ? (size_t)sp.splits * d->Cout * N * sizeof(float) : 0;
+}
+
+extern "C" int uwr_convgemm_tcgen05(const uwr_convgemm_desc* d, uwr_stream_t stream_) {
+    cudaStream_t stream = (cudaStream_t)stream_;
+    UWR_REQUIRE(uwr_convgemm_tcgen05_supported(d), "uwr_convgemm_tcgen05: unsupported geometry / alignment");
+    ConvGeom g;
+    conv_geom(d, g);
+    const long long pixels = (long long)d->B * g.OH * g.OW;
+    const int KN = g.taps * d->Cin;   // im2col width
+    T5Params p{};
+    p.cv.cpt = d->Cin / KC; p.cv.kw = d->kw; p.cv.taps = g.taps; p.cv.pad = d->pad; p.cv.stride = d->stride;
+    p.cv.ow = g.OW; p.cv.ohw = g.OH * g.OW; p.cv.cin = d->Cin; p.cv.nb = d->B;
+    p.rows_per_group = 1;
+    p.epilogue = UWR_EPI_NONE;
+    CUtensorMap ma, mb;
+    int rc, bn;
+    T5Split sp{1, 0};
+    if (d->mode == 0) {
+        bn = t5_pick_bn(d->Cout);
+        if ((rc = encode_conv(&ma, d, g.bw, g.bh, CU_TENSOR_MAP_SWIZZLE_128B))) return rc;
+        if ((rc = encode_2d(&mb, d->w, KN, d->Cout, KN, bn))) return rc;
+        p.C = d->y; p.ldc = d->ld_y; p.M = (int)pixels; p.N = d->Cout;
+        p.chunks = KN / KC; p.chunks_per_split = p.chunks; p.splits = 1;
+        p.bias = d->bias; p.round_out = d->round_out;
+    } else {
+        bn = t5_pick_bn(KN);
+        sp = t5_plan(d->Cout, KN, (int)pixels, LAY_TN, bn);
+        if ((rc = encode_mn(&ma, d->dy, d->Cout, pixels, d->ld_dy))) return rc;
+        if ((rc = encode_conv(&mb, d, g.pw, g.ph, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B))) return rc;
+        p.C = d->dw; p.ldc = KN; p.M = d->Cout; p.N = KN;
+        p.chunks = (int)(pixels / KC); p.chunks_per_split = sp.chunks_per_split; p.splits = sp.splits;
+        if (sp.splits > 1) {
+            const size_t need = (size_t)sp.splits * d->Cout * KN * sizeof(float);
+            UWR_REQUIRE(d->workspace && d->workspace_bytes >= need, "uwr_convgemm_tcgen05: workspace too small (%zu < %zu)",
+                        d->workspace_bytes, need);
+            p.C = d->workspace; p.split_stride = (long long)d->Cout * KN;
+        }
+    }
+    p.tiles_m = uwr_cdiv(p.M, TM); p.tiles_n = uwr_cdiv(p.N, bn);
+    switch (bn) {
+        case 32: rc = conv_dispatch<32>(d->mode, ma, mb, p, stream); break;
+        case 64: rc = conv_dispatch<64>(d->mode, ma, mb, p, stream); break;
+        case 128: rc = conv_dispatch<128>(d->mode, ma, mb, p, stream); break;
+        default: rc = conv_dispatch<256>(d->mode, ma, mb, p, stream); break;
+    }
+    if (rc) return rc;
+    if (d->mode == 1 && sp.splits > 1) {
+        const long long n = (long long)d->Cout * KN;
+        int blocks = (int)((n / 4 + 255) / 256);
+        if (blocks > 4 * uwr_sm_count()) blocks = 4 * uwr_sm_count();
+        t5_splitk_reduce_kernel<<<blocks, 256, 0, stream>>>(d->workspace, d->dw, n, n, sp.splits);
         UWR_CHECK_LAUNCH("t5_splitk_reduce_kernel");
     }
     return 0;

@@ -68,6 +68,16 @@ class AttnDesc(C.Structure):
     ]
 
 
+class ConvGemmDesc(C.Structure):
+    _fields_ = [
+        ("mode", c_int), ("x", c_fp), ("ld_x", c_ll),
+        ("B", c_int), ("H", c_int), ("W", c_int), ("Cin", c_int),
+        ("kh", c_int), ("kw", c_int), ("stride", c_int), ("pad", c_int), ("Cout", c_int),
+        ("w", c_fp), ("bias", c_fp), ("y", c_fp), ("ld_y", c_ll), ("round_out", c_int),
+        ("dy", c_fp), ("ld_dy", c_ll), ("dw", c_fp), ("workspace", c_fp), ("workspace_bytes", c_sz),
+    ]
+
+
 def _sig(name, restype, argtypes):
     fn = getattr(lib, name)
     fn.restype = restype
@@ -87,6 +97,9 @@ SIGNATURES = {
     "uwr_gemm_tcgen05": (c_int, [C.POINTER(GemmDesc), c_stream]),
     "uwr_set_gemm_cluster": (c_int, [c_int]),
     "uwr_gemm_tcgen05_supported": (c_int, [C.POINTER(GemmDesc)]),
+    "uwr_convgemm_tcgen05_supported": (c_int, [C.POINTER(ConvGemmDesc)]),
+    "uwr_convgemm_tcgen05_workspace_bytes": (c_sz, [C.POINTER(ConvGemmDesc)]),
+    "uwr_convgemm_tcgen05": (c_int, [C.POINTER(ConvGemmDesc), c_stream]),
     "uwr_gemm_tcgen05_workspace_bytes": (c_sz, [c_int, c_int, c_int, c_int]),
     "uwr_round_tf32_tensors": (c_int, [c_fp, c_fp, c_fp, c_int, c_ll, c_int, c_stream]),
     "uwr_scale_round": (c_int, [c_fp, c_ll, c_fp, c_ll, c_int, c_fp, c_int, c_int, c_stream]),

@@ -65,7 +65,9 @@ class OutputProjFn(torch.autograd.Function):
 
 
 class DownsampleFn(torch.autograd.Function):
-    """Conv4x4 stride 2 pad 1 on tokens = im2col (tap-major K) + TF32 GEMM."""
+    """Conv4x4 stride 2 pad 1 on tokens (AST.py:408-424).  tf32 mode: implicit GEMM -- the im2col tiles are materialised
+    by TMA inside the tcgen05 kernel (uwr_convgemm_tcgen05), forward and weight gradient read a TF32-rounded copy of x;
+    otherwise (tf32x3, geometry not served) im2col (tap-major K) + GEMM."""
 
     @staticmethod
     def forward(ctx, x, weight, bias, H, W):
@@ -74,13 +76,21 @@ class DownsampleFn(torch.autograd.Function):
         Cout = weight.shape[0]
         # (Cout, Cin, 4, 4) -> (Cout, 4, 4, Cin): K index = (ky, kx, ci) matches the im2col rows
         wmat = weight.permute(0, 2, 3, 1).reshape(Cout, 16 * Cc)
+        ctx.dims = (B, H, W, Cc, Cout)
+        if ops.fast_path():
+            xr = ops.scale_round(x.view(B * L, Cc), Cc)
+            wmat_r = ops.scale_round(wmat, 16 * Cc)
+            y = ops.conv_gemm_fwd(xr, wmat_r, bias, B, H, W, 4, 4, 2, 1)
+            if y is not None:
+                ctx.save_for_backward(xr, wmat_r)   # x itself (1/4 of the im2col matrix) is all the weight gradient needs
+                ctx.implicit = True
+                return y.view(B, L // 4, Cout)
+        ctx.implicit = False
         col = ops.im2col_4x4s2(x.view(B * L, Cc), B, H, W, Cc)  # TF32-rounded at the store in tf32 mode
         wmat_r = ops.scale_round(wmat, 16 * Cc)
         y = ops.linear(col, wmat_r, bias, t5=True)
-        # the im2col matrix (4x the input; ~1 GB over the four stages at batch 16) is kept for the weight
-        # gradient instead of being rebuilt in backward
+        # the im2col matrix (4x the input) is kept for the weight gradient instead of being rebuilt in backward
         ctx.save_for_backward(col, wmat_r)
-        ctx.dims = (B, H, W, Cc, Cout)
         return y.view(B, L // 4, Cout)
 
     @staticmethod
@@ -90,9 +100,13 @@ class DownsampleFn(torch.autograd.Function):
         B, H, W, Cc, Cout = ctx.dims
         dy2 = _c(dy).view(-1, Cout)
         fast = ops.fast_path()
-        if fast:  # tcgen05 path: both operands rounded to TF32 (col and wmat already are); bias gradient =
+        if fast:  # tcgen05 path: both operands rounded to TF32 (col / x and wmat already are); bias gradient =
             dy2, dbias = ops.scale_round_colsum(dy2, Cout)  # column sums taken in the same pass
-            dwmat, _ = ops.linear_wgrad(dy2, col, want_bias=False, t5=True)
+            dwmat = ops.conv_gemm_wgrad(dy2, col, B, H, W, 4, 4, 2, 1) if ctx.implicit else None
+            if dwmat is None:
+                if ctx.implicit:
+                    col = ops.im2col_4x4s2(col, B, H, W, Cc)
+                dwmat, _ = ops.linear_wgrad(dy2, col, want_bias=False, t5=True)
         else:
             dwmat, dbias = ops.linear_wgrad(dy2, col)
         del col

@@ -97,31 +97,51 @@ class Conv3x3Fn(torch.autograd.Function):
         B, L, Cin = x.shape
         Cout = weight.shape[0]
         wmat = ops.scale_round(weight.permute(0, 2, 3, 1).reshape(Cout, 9 * Cin), 9 * Cin)
+        ctx.meta = (B, H, W, Cin, Cout, bias is not None)
+        ctx.implicit = False
+        if ops.fast_path() and Cin % 32 == 0:
+            # implicit GEMM: TMA builds the im2col tiles inside the tcgen05 kernel from a TF32-rounded copy of x
+            xr = ops.scale_round(x.view(B * L, Cin), Cin)
+            y = ops.conv_gemm_fwd(xr, wmat, bias, B, H, W, 3, 3, 1, 1)
+            if y is not None:
+                ctx.save_for_backward(xr, wmat, weight)
+                ctx.implicit = True
+                return y.view(B, L, Cout)
         col = ops.im2col_3x3(x.view(B * L, Cin), B, H, W, Cin)
         y = ops.linear(col, wmat, bias, t5=True)
-        ctx.save_for_backward(x, wmat)
-        ctx.meta = (B, H, W, Cin, Cout, bias is not None)
+        ctx.save_for_backward(x, wmat, weight)
         return y.view(B, L, Cout)
 
     @staticmethod
     @once_differentiable
     def backward(ctx, dy):
-        x, wmat = ctx.saved_tensors
+        x, wmat, weight = ctx.saved_tensors
         B, H, W, Cin, Cout, has_b = ctx.meta
         d = _c(dy).view(-1, Cout)
-        col = ops.im2col_3x3(x.view(-1, Cin), B, H, W, Cin)  # recomputed (9x the input)
         fast = ops.fast_path() and Cout % 4 == 0 and d.shape[0] >= 4096
-        if fast:  # tcgen05 path: TF32-rounded copy of the cotangent (col and wmat already are rounded)
+        db = dwm = dx = None
+        if fast:  # tcgen05 path: TF32-rounded copy of the cotangent (x / col and wmat already are rounded)
             d, db = ops.scale_round_colsum(d, Cout) if has_b else (ops.scale_round(d, Cout), None)
-            dwm, _ = ops.linear_wgrad(d, col, want_bias=False, t5=True)
-        else:
-            dwm, db = ops.linear_wgrad(d, col, want_bias=has_b)
-        del col
-        dcol = ops.linear_dgrad(d, wmat, t5=fast)
-        dx = ops._empty((B * H * W, Cin), x)
-        ops.col2im_3x3(dcol, dx, B, H, W, Cin)
+            if ctx.implicit:
+                dwm = ops.conv_gemm_wgrad(d, x.view(-1, Cin), B, H, W, 3, 3, 1, 1)
+                if ctx.needs_input_grad[0] and Cout % 32 == 0:
+                    # data gradient = the same convolution of dy with the flipped, transposed weights
+                    wflip = ops.scale_round(weight.detach().flip(2, 3).permute(1, 2, 3, 0).reshape(Cin, 9 * Cout), 9 * Cout)
+                    dx = ops.conv_gemm_fwd(d, wflip, None, B, H, W, 3, 3, 1, 1)
+        col = None
+        if dwm is None:
+            col = ops.im2col_3x3(x.view(-1, Cin), B, H, W, Cin)  # recomputed (9x the input)
+            if fast:
+                dwm, _ = ops.linear_wgrad(d, col, want_bias=False, t5=True)
+            else:
+                dwm, db = ops.linear_wgrad(d, col, want_bias=has_b)
+            del col
+        if dx is None and ctx.needs_input_grad[0]:
+            dcol = ops.linear_dgrad(d, wmat, t5=fast)
+            dx = ops._empty((B * H * W, Cin), x)
+            ops.col2im_3x3(dcol, dx, B, H, W, Cin)
         dw = dwm.view(Cout, 3, 3, Cin).permute(0, 3, 1, 2).contiguous()
-        return dx.view(B, H * W, Cin), dw, db, None, None
+        return (dx.view(B, H * W, Cin) if dx is not None else None), dw, db, None, None
 
 
 class AttnFn(torch.autograd.Function):

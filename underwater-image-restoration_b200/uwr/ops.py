@@ -11,7 +11,7 @@ import os
 import torch
 
 from . import _lib
-from ._lib import AttnDesc, ConvSmallDesc, GemmDesc, check, fn
+from ._lib import AttnDesc, ConvGemmDesc, ConvSmallDesc, GemmDesc, check, fn
 
 EPI_NONE, EPI_RESID, EPI_MUL_DGELU, EPI_MUL = 0, 1, 2, 3
 
@@ -640,6 +640,57 @@ def output_proj_bwd(dout_img, tokens, weight, B, H, W):
     _run("uwr_output_proj_bwd", "", 0, 0.0, _ptr(dout_img), _ptr(tokens), tokens.stride(-2), _ptr(weight), _ptr(dtokens),
                                     _ptr(dweight), _ptr(dbias), _ptr(ws), B, H, W, Cin)
     return dtokens, dweight, dbias
+
+
+def _convgemm_desc(x2d, B, H, W, Cin, Cout, kh, kw, stride, pad):
+    d = ConvGemmDesc()
+    d.x, d.ld_x, d.B, d.H, d.W, d.Cin, d.Cout = _ptr(x2d), x2d.stride(0), B, H, W, Cin, Cout
+    d.kh, d.kw, d.stride, d.pad = kh, kw, stride, pad
+    return d
+
+
+def _conv_out(H, W, kh, kw, stride, pad):
+    return (H + 2 * pad - kh) // stride + 1, (W + 2 * pad - kw) // stride + 1
+
+
+def conv_gemm_fwd(x2d, wmat, bias, B, H, W, kh, kw, stride, pad, round_out=False, out=None):
+    """y = im2col(x) wmat^T (+ bias) as an implicit GEMM (no im2col buffer); x2d (B*H*W, Cin) and wmat (Cout, kh*kw*Cin,
+    K index = (ky, kx, ci)) TF32-rounded.  Returns None when the geometry is not served (caller: im2col + GEMM)."""
+    if _PASSES != 1:
+        return None
+    Cin, Cout = x2d.shape[1], wmat.shape[0]
+    d = _convgemm_desc(x2d, B, H, W, Cin, Cout, kh, kw, stride, pad)
+    OH, OW = _conv_out(H, W, kh, kw, stride, pad)
+    y = out if out is not None else _empty((B * OH * OW, Cout), x2d)
+    d.mode, d.w, d.bias, d.y, d.ld_y, d.round_out = 0, _ptr(wmat), _ptr(bias), _ptr(y), y.stride(0), int(round_out)
+    if not wmat.is_contiguous() or not fn["uwr_convgemm_tcgen05_supported"](C.byref(d)):
+        return None
+    rows, K = B * OH * OW, kh * kw * Cin
+    _run("uwr_convgemm_tcgen05", f"fwd {kh}x{kw}s{stride} M{rows} N{Cout} K{K}", 4 * (B * H * W * Cin + Cout * K + rows * Cout),
+         2.0 * rows * Cout * K, C.byref(d))
+    return y
+
+
+def conv_gemm_wgrad(dy2d, x2d, B, H, W, kh, kw, stride, pad, out=None):
+    """dwmat (Cout, kh*kw*Cin) = dy^T im2col(x) as an implicit GEMM; dy2d (B*OH*OW, Cout) and x2d TF32-rounded.
+    Returns None when the geometry is not served."""
+    if _PASSES != 1:
+        return None
+    Cin, Cout = x2d.shape[1], dy2d.shape[1]
+    d = _convgemm_desc(x2d, B, H, W, Cin, Cout, kh, kw, stride, pad)
+    d.mode, d.dy, d.ld_dy = 1, _ptr(dy2d), dy2d.stride(0)
+    K = kh * kw * Cin
+    dw = out if out is not None else _empty((Cout, K), x2d)
+    d.dw = _ptr(dw)
+    if not fn["uwr_convgemm_tcgen05_supported"](C.byref(d)):
+        return None
+    nbytes = fn["uwr_convgemm_tcgen05_workspace_bytes"](C.byref(d))
+    ws = _ws(nbytes, x2d) if nbytes else None
+    d.workspace, d.workspace_bytes = _ptr(ws), nbytes
+    rows = dy2d.shape[0]
+    _run("uwr_convgemm_tcgen05", f"wgrad {kh}x{kw}s{stride} M{Cout} N{K} K{rows}", 4 * (B * H * W * Cin + rows * Cout + Cout * K),
+         2.0 * rows * Cout * K, C.byref(d))
+    return dw
 
 
 def im2col_4x4s2(tokens2d, B, H, W, Cc):
