@@ -108,6 +108,9 @@ int uwr_gemm_tcgen05(const uwr_gemm_desc* d, uwr_stream_t stream);
  *   mode 0: y[B*OH*OW, Cout] = im2col(x) . w^T (+ bias)      w: (Cout, kh*kw*Cin), K index = (ky, kx, ci)
  *           (the data gradient of a stride-1 convolution is the same call on dy with the flipped, transposed weights)
  *   mode 1: dw[Cout, kh*kw*Cin] = dy^T . im2col(x)            dy: (B*OH*OW, ld_dy); contraction split across CTAs
+ *   mode 2: dw^T[kh*kw*Cin, Cout] = im2col(x)^T . dy          the same gradient, transposed: the im2col view is the
+ *           128-row operand, so a thin Cout costs a thin N tile instead of padding the M tile (5x fewer MMA cycles
+ *           at Cout = 32, 3x3)
  * Served when Cin % 32 == 0 and OH*OW is a multiple of 128 (mode 0) / 32 (mode 1) with power-of-two or box-multiple
  * widths (see `_supported`); callers fall back to uwr_im2col_* + uwr_gemm_tcgen05 otherwise. */
 typedef struct {
@@ -124,8 +127,8 @@ typedef struct {
     int round_out;       /* mode 0: round y to TF32 at the store (it feeds another tensor-core product) */
     const float* dy;     /* mode 1 */
     long long ld_dy;
-    float* dw;           /* mode 1, dense (Cout, kh*kw*Cin) */
-    float* workspace;    /* mode 1: uwr_convgemm_tcgen05_workspace_bytes */
+    float* dw;           /* mode 1: dense (Cout, kh*kw*Cin); mode 2: dense (kh*kw*Cin, Cout) */
+    float* workspace;    /* modes 1, 2: uwr_convgemm_tcgen05_workspace_bytes */
     size_t workspace_bytes;
 } uwr_convgemm_desc;
 int uwr_convgemm_tcgen05_supported(const uwr_convgemm_desc* d);

@@ -160,4 +160,4 @@ def test_conv_implicit_gemm(B, H, W, Cin, Cout, k, stride, pad):
     wd = w.double().requires_grad_()
     F.conv2d(xd, wd, None, stride=stride, padding=pad).backward(dy.double().view(B, OH, OW, Cout).permute(0, 3, 1, 2))
     torch.cuda.synchronize()
-    assert rel_l2(dw.view(Cout, k, k, Cin), wd.grad.permute(0, 2, 3, 1)) < 1e-5
+    assert rel_l2(dw.reshape(Cout, k, k, Cin), wd.grad.permute(0, 2, 3, 1)) < 1e-5

@@ -186,3 +186,24 @@ if "oproj" in which:
     timeit("output_proj bwd 64->3 (scalar fp32)", lambda: ops.output_proj_bwd(dimg, tok64, wo, B_, H_, H_),
            4 * npx * (128 + 3), 4.0 * npx * 27 * 64)
     ops.set_gemm_precision("tf32")
+
+if "conv" in which:
+    # dense convolutions: im2col + GEMM vs the implicit GEMM (TMA-materialised im2col tiles)
+    for (B_, H_, Cin, Cout, k, st) in ((16, 256, 32, 64, 4, 2), (16, 128, 64, 128, 4, 2), (16, 64, 128, 256, 4, 2),
+                                       (16, 256, 32, 32, 3, 1), (16, 128, 64, 64, 3, 1)):
+        x = rnd(B_ * H_ * H_, Cin)
+        wm = rnd(Cout, k * k * Cin) * 0.1
+        wm = ((wm.view(torch.int32) + 0x1000) & ~0x1FFF).view(torch.float32)
+        OH = H_ // st
+        rows = B_ * OH * OH
+        dy = rnd(rows, Cout)
+        nb, fl = 4 * (x.numel() + wm.numel() + rows * Cout), 2.0 * rows * Cout * k * k * Cin
+        tag = f"{k}x{k}s{st} B{B_} H{H_} {Cin}->{Cout}"
+        im2col = (lambda: ops.im2col_4x4s2(x, B_, H_, H_, Cin)) if k == 4 else (lambda: ops.im2col_3x3(x, B_, H_, H_, Cin))
+        timeit(f"conv {tag} im2col", im2col, nb, 0.0)
+        col = im2col()
+        timeit(f"conv {tag} GEMM on col", lambda: ops.linear(col, wm, None, t5=True), nb, fl)
+        timeit(f"conv {tag} implicit fwd", lambda: ops.conv_gemm_fwd(x, wm, None, B_, H_, H_, k, k, st, 1), nb, fl)
+        timeit(f"conv {tag} wgrad on col", lambda: ops.linear_wgrad(dy, col, want_bias=False, t5=True), nb, fl)
+        timeit(f"conv {tag} implicit wgrad", lambda: ops.conv_gemm_wgrad(dy, x, B_, H_, H_, k, k, st, 1), nb, fl)
+        del col

@@ -45,6 +45,7 @@ struct T5Conv {
     int taps;     // kh * kw
     int pad, stride;
     int ow, ohw;  // output width, output pixels per image
+    int pw, ph;   // CV = 2: the 32 output pixels of one K chunk are a pw x ph patch
     int cin;
     int nb;       // batch: a coordinate >= nb in the outermost dimension reads zeros (padding column groups)
 };
@@ -161,6 +162,35 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_const
                 const int z = item / (tiles_mg * p.tiles_n);
                 const int c_begin = z * p.chunks_per_split;
                 const int c_end = min(p.chunks, c_begin + p.chunks_per_split);
+                // virtual im2col operands: all index divisions happen once per work item, the chunk loop only steps
+                // (the single producer thread must stay far below one MMA chunk, 512 cycles, per iteration)
+                int cvb = 0, cvx = 0, cvy = 0;          // CV 1: image / origin of the tile; CV 2: of the current chunk
+                int cvc0 = 0, cvkx = 0, cvky = 0;       // CV 1: channel offset and tap of the current chunk
+                constexpr int NG = CV == 2 ? BN / 32 : (CV == 3 ? TM / 32 : 1);   // 32-wide groups of the virtual operand
+                int gx[NG], gy[NG], gc[NG];
+                if (CV == 1) {
+                    const int m0 = tm * TM, r = m0 % p.cv.ohw, oy0 = r / p.cv.ow;
+                    cvb = m0 / p.cv.ohw;
+                    cvx = (r - oy0 * p.cv.ow) * p.cv.stride - p.cv.pad;
+                    cvy = oy0 * p.cv.stride - p.cv.pad;
+                    const int tap = c_begin / p.cv.cpt;
+                    cvc0 = (c_begin - tap * p.cv.cpt) * KC;
+                    cvky = tap / p.cv.kw;
+                    cvkx = tap - cvky * p.cv.kw;
+                }
+                if (CV == 2 || CV == 3) {
+                    const int k0 = c_begin * KC, r = k0 % p.cv.ohw;
+                    cvb = k0 / p.cv.ohw;
+                    cvy = r / p.cv.ow;                  // in output pixels; scaled where the box is issued
+                    cvx = r - cvy * p.cv.ow;
+#pragma unroll
+                    for (int g = 0; g < NG; ++g) {
+                        const int n0 = (CV == 2 ? tn * BN : tm * TM) + g * 32, tap = n0 / p.cv.cin, ky = tap / p.cv.kw;
+                        gc[g] = tap < p.cv.taps ? n0 - tap * p.cv.cin : -1;   // -1: padding group beyond the last tap
+                        gy[g] = ky - p.cv.pad;
+                        gx[g] = tap - ky * p.cv.kw - p.cv.pad;
+                    }
+                }
                 for (int c = c_begin; c < c_end; ++c) {
                     mbar_wait(&empty_bar[stage], phase ^ 1);
                     uint8_t* sa = smem + stage * STAGE_BYTES;
@@ -168,12 +198,22 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_const
                     mbar_expect_tx(&full_bar[stage], STAGE_BYTES);
                     if (CV == 1) {
                         // virtual im2col rows: the tile's 128 output pixels (one box) at tap (ky, kx), channels c0..c0+31
-                        const int m0 = tm * TM, b = m0 / p.cv.ohw, r = m0 - b * p.cv.ohw;
-                        const int oy0 = r / p.cv.ow, ox0 = r - oy0 * p.cv.ow;
-                        const int tap = c / p.cv.cpt, c0 = (c - tap * p.cv.cpt) * KC;
-                        const int ky = tap / p.cv.kw, kx = tap - ky * p.cv.kw;
-                        tma_load_4d(sa, &mapA, &full_bar[stage], c0, ox0 * p.cv.stride + kx - p.cv.pad,
-                                    oy0 * p.cv.stride + ky - p.cv.pad, b);
+                        tma_load_4d(sa, &mapA, &full_bar[stage], cvc0, cvx + cvkx, cvy + cvky, cvb);
+                        cvc0 += KC;
+                        if (cvc0 == p.cv.cin) {
+                            cvc0 = 0;
+                            if (++cvkx == p.cv.kw) {
+                                cvkx = 0;
+                                ++cvky;
+                            }
+                        }
+                    } else if (CV == 3) {
+                        // virtual im2col as the MN-major A operand (transposed weight gradient): 32-pixel patch x 32-channel group
+                        const int xs = cvx * p.cv.stride, ys = cvy * p.cv.stride;
+#pragma unroll
+                        for (int g = 0; g < TM / 32; ++g)
+                            tma_load_4d(sa + g * 4096, &mapA, &full_bar[stage], gc[g] < 0 ? 0 : gc[g], xs + gx[g], ys + gy[g],
+                                        gc[g] < 0 ? p.cv.nb : cvb);
                     } else if (!A_MN) {
                         tma_load_2d(sa, &mapA, &full_bar[stage], c * KC, tm * TM);
                     } else {
@@ -184,15 +224,11 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_const
                     }
                     if (CV == 2) {
                         // virtual im2col columns: this chunk's 32 output pixels x the 32-channel group of tap (ky, kx)
-                        const int k0 = c * KC, b = k0 / p.cv.ohw, r = k0 - b * p.cv.ohw;
-                        const int oy0 = r / p.cv.ow, ox0 = r - oy0 * p.cv.ow;
+                        const int xs = cvx * p.cv.stride, ys = cvy * p.cv.stride;
 #pragma unroll
-                        for (int g = 0; g < BN / 32; ++g) {
-                            const int n0 = tn * BN + g * 32, tap = n0 / p.cv.cin, c0 = n0 - tap * p.cv.cin;
-                            const int ky = tap / p.cv.kw, kx = tap - ky * p.cv.kw;
-                            tma_load_4d(sb + g * 4096, &mapB, &full_bar[stage], c0, ox0 * p.cv.stride + kx - p.cv.pad,
-                                        oy0 * p.cv.stride + ky - p.cv.pad, tap < p.cv.taps ? b : p.cv.nb);
-                        }
+                        for (int g = 0; g < BN / 32; ++g)
+                            tma_load_4d(sb + g * 4096, &mapB, &full_bar[stage], gc[g] < 0 ? 0 : gc[g], xs + gx[g], ys + gy[g],
+                                        gc[g] < 0 ? p.cv.nb : cvb);
                     } else if (CL == 1) {
                         if (!B_MN) {
                             tma_load_2d(sb, &mapB, &full_bar[stage], c * KC, tn * BN);
@@ -212,6 +248,17 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_const
                             for (int g = 0; g < SHARE / 32; ++g) {
                                 const int gg = crank * (SHARE / 32) + g;
                                 tma_load_2d_mc(sb + gg * 4096, &mapB, &full_bar[stage], tn * BN + gg * 32, c * KC, CMASK);
+                            }
+                        }
+                    }
+                    if (CV == 2 || CV == 3) {
+                        cvx += p.cv.pw;                  // next 32-pixel patch: along the row, then down, then the next image
+                        if (cvx == p.cv.ow) {
+                            cvx = 0;
+                            cvy += p.cv.ph;
+                            if (cvy * p.cv.ow == p.cv.ohw) {
+                                cvy = 0;
+                                ++cvb;
                             }
                         }
                     }
@@ -475,11 +522,25 @@ T5Split t5_plan(int M, int N, int Kc, int lay, int bn) {
     T5Split sp{1, chunks};
     if (lay != LAY_TN) return sp;
     const long long tiles = (long long)uwr_cdiv(M, TM) * uwr_cdiv(N, bn);
-    int splits = (int)((uwr_sm_count() + tiles - 1) / tiles);
+    const int sms = uwr_sm_count();
     const int max_splits = chunks / 8 > 0 ? chunks / 8 : 1;  // >= 256 contraction rows per split
-    if (splits > max_splits) splits = max_splits;
-    if (splits < 1) splits = 1;
-    sp.chunks_per_split = uwr_cdiv(chunks, splits);
+    // the persistent grid runs tiles * splits work items in waves of one per SM: pick the split count with the fewest
+    // chunk-steps on the critical path.  (Rounding the split count UP, as this did before, made 150 items out of 3 tiles x
+    // 50 splits -- two waves on 148 SMs, i.e. twice the time of 3 x 49.)
+    int best = 1;
+    long long best_cost = -1;
+    int limit = (int)(2 * sms / tiles) + 1;
+    if (limit > max_splits) limit = max_splits;
+    for (int s = 1; s <= limit; ++s) {
+        const int cps = uwr_cdiv(chunks, s), real = uwr_cdiv(chunks, cps);
+        const long long waves = (tiles * real + sms - 1) / sms;
+        const long long cost = waves * (cps + 6);             // + a fixed per-item cost (pipeline fill, epilogue)
+        if (best_cost < 0 || cost < best_cost) {
+            best_cost = cost;
+            best = s;
+        }
+    }
+    sp.chunks_per_split = uwr_cdiv(chunks, best);
     sp.splits = uwr_cdiv(chunks, sp.chunks_per_split);
     return sp;
 }
@@ -714,6 +775,7 @@ int encode_conv(CUtensorMap* m, const uwr_convgemm_desc* d, int bw, int bh, CUte
 template <int BN>
 int conv_dispatch(int mode, const CUtensorMap& ma, const CUtensorMap& mb, const T5Params& p, cudaStream_t stream) {
     if (mode == 0) return t5_launch<BN, LAY_NT, UWR_EPI_NONE, 0, 1, 1>(ma, mb, p, stream);
+    if (mode == 2) return t5_launch<BN, LAY_TN, UWR_EPI_NONE, 0, 1, 3>(ma, mb, p, stream);
     return t5_launch<BN, LAY_TN, UWR_EPI_NONE, 0, 1, 2>(ma, mb, p, stream);
 }
 
@@ -729,7 +791,7 @@ extern "C" int uwr_convgemm_tcgen05_supported(const uwr_convgemm_desc* d) {
         if (d->bias && (uintptr_t)d->bias % 16) return 0;
         return (g.OH * g.OW) % TM == 0 && pixels < (1ll << 31);
     }
-    if (d->mode == 1) {
+    if (d->mode == 1 || d->mode == 2) {
         if (!d->dy || !d->dw || d->ld_dy % 4 || ((uintptr_t)d->dy | (uintptr_t)d->dw) % 16) return 0;
         return (g.OH * g.OW) % KC == 0 && pixels < (1ll << 31);
     }
@@ -738,11 +800,12 @@ extern "C" int uwr_convgemm_tcgen05_supported(const uwr_convgemm_desc* d) {
 
 extern "C" size_t uwr_convgemm_tcgen05_workspace_bytes(const uwr_convgemm_desc* d) {
     ConvGeom g;
-    if (!d || d->mode != 1 || !conv_geom(d, g)) return 0;
-    const int N = g.taps * d->Cin;
+    if (!d || (d->mode != 1 && d->mode != 2) || !conv_geom(d, g)) return 0;
+    const int KN = g.taps * d->Cin;
+    const int M = d->mode == 1 ? d->Cout : KN, N = d->mode == 1 ? KN : d->Cout;
     const long long K = (long long)d->B * g.OH * g.OW;
-    const T5Split sp = t5_plan(d->Cout, N, (int)K, LAY_TN, t5_pick_bn(N));
-    return sp.splits > 1 ? (size_t)sp.splits * d->Cout * N * sizeof(float) : 0;
+    const T5Split sp = t5_plan(M, N, (int)K, LAY_TN, t5_pick_bn(N));
+    return sp.splits > 1 ? (size_t)sp.splits * M * N * sizeof(float) : 0;
 }
 
 extern "C" int uwr_convgemm_tcgen05(const uwr_convgemm_desc* d, uwr_stream_t stream_) {
@@ -754,7 +817,7 @@ extern "C" int uwr_convgemm_tcgen05(const uwr_convgemm_desc* d, uwr_stream_t str
     const int KN = g.taps * d->Cin;   // im2col width
     T5Params p{};
     p.cv.cpt = d->Cin / KC; p.cv.kw = d->kw; p.cv.taps = g.taps; p.cv.pad = d->pad; p.cv.stride = d->stride;
-    p.cv.ow = g.OW; p.cv.ohw = g.OH * g.OW; p.cv.cin = d->Cin; p.cv.nb = d->B;
+    p.cv.ow = g.OW; p.cv.ohw = g.OH * g.OW; p.cv.cin = d->Cin; p.cv.nb = d->B; p.cv.pw = g.pw; p.cv.ph = g.ph;
     p.rows_per_group = 1;
     p.epilogue = UWR_EPI_NONE;
     CUtensorMap ma, mb;
@@ -767,6 +830,21 @@ extern "C" int uwr_convgemm_tcgen05(const uwr_convgemm_desc* d, uwr_stream_t str
         p.C = d->y; p.ldc = d->ld_y; p.M = (int)pixels; p.N = d->Cout;
         p.chunks = KN / KC; p.chunks_per_split = p.chunks; p.splits = 1;
         p.bias = d->bias; p.round_out = d->round_out;
+    } else if (d->mode == 2) {
+        // transposed weight gradient dw^T (KN, Cout) = im2col(x)^T dy: the im2col view is the (MN-major) A operand, so a
+        // thin Cout costs a thin N tile instead of padding the 128-row M tile
+        bn = t5_pick_bn(d->Cout);
+        sp = t5_plan(KN, d->Cout, (int)pixels, LAY_TN, bn);
+        if ((rc = encode_conv(&ma, d, g.pw, g.ph, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B))) return rc;
+        if ((rc = encode_mn(&mb, d->dy, d->Cout, pixels, d->ld_dy))) return rc;
+        p.C = d->dw; p.ldc = d->Cout; p.M = KN; p.N = d->Cout;
+        p.chunks = (int)(pixels / KC); p.chunks_per_split = sp.chunks_per_split; p.splits = sp.splits;
+        if (sp.splits > 1) {
+            const size_t need = (size_t)sp.splits * d->Cout * KN * sizeof(float);
+            UWR_REQUIRE(d->workspace && d->workspace_bytes >= need, "uwr_convgemm_tcgen05: workspace too small (%zu < %zu)",
+                        d->workspace_bytes, need);
+            p.C = d->workspace; p.split_stride = (long long)d->Cout * KN;
+        }
     } else {
         bn = t5_pick_bn(KN);
         sp = t5_plan(d->Cout, KN, (int)pixels, LAY_TN, bn);
@@ -789,7 +867,7 @@ extern "C" int uwr_convgemm_tcgen05(const uwr_convgemm_desc* d, uwr_stream_t str
         default: rc = conv_dispatch<256>(d->mode, ma, mb, p, stream); break;
     }
     if (rc) return rc;
-    if (d->mode == 1 && sp.splits > 1) {
+    if (d->mode != 0 && sp.splits > 1) {
         const long long n = (long long)d->Cout * KN;
         int blocks = (int)((n / 4 + 255) / 256);
         if (blocks > 4 * uwr_sm_count()) blocks = 4 * uwr_sm_count();

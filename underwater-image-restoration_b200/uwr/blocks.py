@@ -112,7 +112,7 @@ class DownsampleFn(torch.autograd.Function):
         del col
         dcol = ops.linear_dgrad(dy2, wmat, t5=fast)
         dx = ops.col2im_4x4s2(dcol, B, H, W, Cc)
-        dweight = dwmat.view(Cout, 4, 4, Cc).permute(0, 3, 1, 2).contiguous()
+        dweight = dwmat.reshape(Cout, 4, 4, Cc).permute(0, 3, 1, 2).contiguous()
         return dx.view(B, H * W, Cc), dweight, dbias, None, None
 
 

@@ -140,7 +140,7 @@ class Conv3x3Fn(torch.autograd.Function):
             dcol = ops.linear_dgrad(d, wmat, t5=fast)
             dx = ops._empty((B * H * W, Cin), x)
             ops.col2im_3x3(dcol, dx, B, H, W, Cin)
-        dw = dwm.view(Cout, 3, 3, Cin).permute(0, 3, 1, 2).contiguous()
+        dw = dwm.reshape(Cout, 3, 3, Cin).permute(0, 3, 1, 2).contiguous()
         return (dx.view(B, H * W, Cin) if dx is not None else None), dw, db, None, None
 
 

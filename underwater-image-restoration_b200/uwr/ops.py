@@ -671,16 +671,20 @@ def conv_gemm_fwd(x2d, wmat, bias, B, H, W, kh, kw, stride, pad, round_out=False
     return y
 
 
-def conv_gemm_wgrad(dy2d, x2d, B, H, W, kh, kw, stride, pad, out=None):
-    """dwmat (Cout, kh*kw*Cin) = dy^T im2col(x) as an implicit GEMM; dy2d (B*OH*OW, Cout) and x2d TF32-rounded.
-    Returns None when the geometry is not served."""
+def conv_gemm_wgrad(dy2d, x2d, B, H, W, kh, kw, stride, pad):
+    """Weight gradient of the convolution as an implicit GEMM; dy2d (B*OH*OW, Cout) and x2d TF32-rounded.  Returns dwmat
+    as a (Cout, kh*kw*Cin) tensor (K index = (ky, kx, ci)) -- a transposed view when the kernel ran in the orientation
+    that puts the im2col view on the 128-row operand (thin Cout) -- or None when the geometry is not served."""
     if _PASSES != 1:
         return None
     Cin, Cout = x2d.shape[1], dy2d.shape[1]
-    d = _convgemm_desc(x2d, B, H, W, Cin, Cout, kh, kw, stride, pad)
-    d.mode, d.dy, d.ld_dy = 1, _ptr(dy2d), dy2d.stride(0)
     K = kh * kw * Cin
-    dw = out if out is not None else _empty((Cout, K), x2d)
+    # MMA cycles ~ padded M x padded N: (Cout -> 128-row tiles, K -> column tiles) vs (K -> rows, Cout -> columns)
+    pad_n = lambda n: 32 if n <= 32 else 64 if n <= 64 else 128 if n <= 128 else -(-n // 256) * 256
+    transposed = -(-K // 128) * 128 * pad_n(Cout) < -(-Cout // 128) * 128 * pad_n(K)
+    d = _convgemm_desc(x2d, B, H, W, Cin, Cout, kh, kw, stride, pad)
+    d.mode, d.dy, d.ld_dy = (2 if transposed else 1), _ptr(dy2d), dy2d.stride(0)
+    dw = _empty((K, Cout) if transposed else (Cout, K), x2d)
     d.dw = _ptr(dw)
     if not fn["uwr_convgemm_tcgen05_supported"](C.byref(d)):
         return None
@@ -688,9 +692,9 @@ def conv_gemm_wgrad(dy2d, x2d, B, H, W, kh, kw, stride, pad, out=None):
     ws = _ws(nbytes, x2d) if nbytes else None
     d.workspace, d.workspace_bytes = _ptr(ws), nbytes
     rows = dy2d.shape[0]
-    _run("uwr_convgemm_tcgen05", f"wgrad {kh}x{kw}s{stride} M{Cout} N{K} K{rows}", 4 * (B * H * W * Cin + rows * Cout + Cout * K),
-         2.0 * rows * Cout * K, C.byref(d))
-    return dw
+    _run("uwr_convgemm_tcgen05", f"wgrad{'T' if transposed else ''} {kh}x{kw}s{stride} M{Cout} N{K} K{rows}",
+         4 * (B * H * W * Cin + rows * Cout + Cout * K), 2.0 * rows * Cout * K, C.byref(d))
+    return dw.t() if transposed else dw
 
 
 def im2col_4x4s2(tokens2d, B, H, W, Cc):
