@@ -188,7 +188,7 @@ def test_window_attention_fwd_bwd(ops, B, H, heads, hd, shift, sparse):
     assert rel_l2(dtable, td.grad) < 2 * TOL_TF32
     if sparse:
         assert rel_l2(dw, wd.grad) < 5 * TOL_TF32
-    assert rel_l2(cs, dqkv.double().sum(0)) < 1e-5            # the sums of exactly what was stored
+    assert rel_l2(cs, dqkv.double().sum(0)) < 5e-4            # sums of the unrounded values vs the stored (TF32-rounded) ones
     assert rel_l2(cs, qd.grad.sum(0)) < 5 * TOL_TF32
     # not requested: same gradients, nothing else written
     dqkv2, _, _, _ = ops.window_attn_bwd(do, qkv, 0, qkv, C, 2 * C, table, w if sparse else None, B, H, W, heads, hd,

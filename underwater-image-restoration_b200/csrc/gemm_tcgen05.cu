@@ -514,6 +514,25 @@ int t5_pick_bn(int N) {
     return 256;
 }
 
+// NT / NN: the persistent grid runs tiles_m x tiles_n work items in waves of one per SM.  With few row tiles (the 16 x 16
+// bottleneck stages: M = 4096) the widest column tile leaves most SMs idle -- N = 512 at BN = 256 is 64 items on 148 SMs --
+// so take the narrower tile when that shortens the critical path (per-item cost ~ the operand bytes per chunk, A + B).
+int t5_pick_bn_mn(int M, int N) {
+    int best = t5_pick_bn(N);
+    if (best <= 64) return best;
+    const int sms = uwr_sm_count();
+    const long long tm = uwr_cdiv(M, TM);
+    long long best_cost = ((tm * uwr_cdiv(N, best) + sms - 1) / sms) * (TM + best);
+    for (int bn = best / 2; bn >= 64; bn /= 2) {
+        const long long cost = ((tm * uwr_cdiv(N, bn) + sms - 1) / sms) * (TM + bn);
+        if (cost * 10 < best_cost * 9) {   // at least 10 % shorter
+            best_cost = cost;
+            best = bn;
+        }
+    }
+    return best;
+}
+
 struct T5Split {
     int splits, chunks_per_split;
 };
@@ -671,9 +690,9 @@ extern "C" int uwr_gemm_tcgen05(const uwr_gemm_desc* d, uwr_stream_t stream_) {
     cudaStream_t stream = (cudaStream_t)stream_;
     UWR_REQUIRE(uwr_gemm_tcgen05_supported(d), "uwr_gemm_tcgen05: unsupported shape/layout (use uwr_gemm_tf32)");
     const int lay = d->a_km ? LAY_TN : (d->b_nk ? LAY_NT : LAY_NN);
-    const int bn = t5_pick_bn(d->N);
-    const T5Split sp = t5_plan(d->M, d->N, d->K, lay, bn);
     const int hf = (d->c_half ? 1 : 0) | (d->r_half ? 2 : 0);
+    const int bn = (lay == LAY_TN || hf) ? t5_pick_bn(d->N) : t5_pick_bn_mn(d->M, d->N);
+    const T5Split sp = t5_plan(d->M, d->N, d->K, lay, bn);
     const int cl = t5_pick_cluster(d, bn, hf);
 
     CUtensorMap ma, mb;

@@ -328,27 +328,18 @@ __global__ void __launch_bounds__(ATT_THREADS) attn_fwd_kernel(const AttnParams 
     }
 }
 
-// Column sums of a 16-row accumulator block (rows g / g + 8 of this warp, columns n*8 + 2t + e) as it is stored
-// (scaled, TF32-rounded when the outputs are): three shuffles fold the eight row groups, the g == 0 lanes add into the
-// warp's private slice.  Fixed order -> deterministic.  These are the bias gradients of the q / kv projections, which
-// would otherwise cost one more pass over dq | dk | dv (uwr_colsum, 0.64 ms per training step at B = 16).
+// Column sums of dq | dk | dv (the bias gradients of the q / kv projections, which would otherwise cost one more pass over
+// the 3C-wide gradient: uwr_colsum, 0.64 ms per training step at B = 16).  Each thread keeps running sums of ITS
+// accumulator slots (rows g and g + 8 folded, columns n*8 + 2t + e) across all the tiles it walks -- one add per value and
+// tile; the eight row groups and the four warps are folded once, after the tile loop (fixed order -> deterministic).
+// The sums are of the unrounded values (the rounding of the stored gradient is zero-mean noise on top of them).
 template <int HD>
-__device__ __forceinline__ void colsum_add(float* acc_w, const float (&v)[HD / 8][4], float mul, bool rnd, int g, int t) {
+__device__ __forceinline__ void colsum_add(float (&cs)[HD / 8][2], const float (&v)[HD / 8][4]) {
 #pragma unroll
-    for (int n = 0; n < HD / 8; ++n)
-#pragma unroll
-        for (int e = 0; e < 2; ++e) {
-            float a = v[n][e] * mul, b = v[n][2 + e] * mul;
-            if (rnd) {
-                a = tf32_round(a);
-                b = tf32_round(b);
-            }
-            float sum = a + b;
-            sum += __shfl_xor_sync(0xffffffffu, sum, 4);
-            sum += __shfl_xor_sync(0xffffffffu, sum, 8);
-            sum += __shfl_xor_sync(0xffffffffu, sum, 16);
-            if (g == 0) acc_w[n * 8 + 2 * t + e] += sum;
-        }
+    for (int n = 0; n < HD / 8; ++n) {
+        cs[n][0] += v[n][0] + v[n][2];
+        cs[n][1] += v[n][1] + v[n][3];
+    }
 }
 // one row of per-CTA partial sums: 225 bias-table bins, the two fusion-weight sums (+1 pad), 3 x HD column sums
 __host__ __device__ constexpr int bwd_part_stride(int hd) { return NBINS + 3 + 3 * hd; }
@@ -387,7 +378,9 @@ __global__ void __launch_bounds__(ATT_THREADS, HD <= 32 ? 3 : 1) attn_bwd_kernel
     const bool want_colsum = p.dq_colsum != nullptr;
 
     for (int i = threadIdx.x; i < NBINS; i += ATT_THREADS) tab[i] = p.table[i * p.heads + h];
-    for (int i = lane; i < 3 * HD; i += 32) colacc[warp][i] = 0.f;
+    float csq[HD / 8][2], csk[HD / 8][2], csv[HD / 8][2];
+#pragma unroll
+    for (int n = 0; n < HD / 8; ++n) csq[n][0] = csq[n][1] = csk[n][0] = csk[n][1] = csv[n][0] = csv[n][1] = 0.f;
     float w0, w1;
     fusion_weights(p.w_param, w0, w1);
 
@@ -460,7 +453,7 @@ __global__ void __launch_bounds__(ATT_THREADS, HD <= 32 ? 3 : 1) attn_bwd_kernel
         {
             float dq[HD / 8][4];
             mma_regs_x_rows<HD, true>(dq, dp, Ks, g, t, p.x3);  // dS rows sum to ~0: needs 3xTF32
-            if (want_colsum) colsum_add<HD>(colacc[warp], dq, p.scale, p.rnd != 0, g, t);
+            if (want_colsum) colsum_add<HD>(csq, dq);   // scaled by p.scale when it is folded, after the tile loop
 #pragma unroll
             for (int half = 0; half < 2; ++half) {
                 float* drow = dq_buf + rows[r0 + g + half * 8] * p.ld_q + p.q_off + h * HD;
@@ -538,7 +531,10 @@ __global__ void __launch_bounds__(ATT_THREADS, HD <= 32 ? 3 : 1) attn_bwd_kernel
                 for (int n = 0; n < HD / 8; ++n) mma_tf32_16x8x8(acc[n], a, bb[n]);
             }
             const int off = which == 0 ? p.v_off : p.k_off;
-            if (want_colsum) colsum_add<HD>(colacc[warp] + (which == 0 ? 2 * HD : HD), acc, 1.0f, p.rnd != 0, g, t);
+            if (want_colsum) {
+                if (which == 0) colsum_add<HD>(csv, acc);
+                else colsum_add<HD>(csk, acc);
+            }
 #pragma unroll
             for (int half = 0; half < 2; ++half) {
                 float* drow = dkv_buf + rows[r0 + g + half * 8] * p.ld_kv + off + h * HD;
@@ -551,6 +547,25 @@ __global__ void __launch_bounds__(ATT_THREADS, HD <= 32 ? 3 : 1) attn_bwd_kernel
         }
     }
 
+    if (want_colsum) {   // fold the eight row groups (lanes with equal t), then the g == 0 lanes publish the warp's sums
+#pragma unroll
+        for (int n = 0; n < HD / 8; ++n)
+#pragma unroll
+            for (int e = 0; e < 2; ++e) {
+                float a = csq[n][e] * p.scale, b = csk[n][e], c = csv[n][e];
+#pragma unroll
+                for (int o = 4; o < 32; o <<= 1) {
+                    a += __shfl_xor_sync(0xffffffffu, a, o);
+                    b += __shfl_xor_sync(0xffffffffu, b, o);
+                    c += __shfl_xor_sync(0xffffffffu, c, o);
+                }
+                if (g == 0) {
+                    colacc[warp][n * 8 + 2 * t + e] = a;
+                    colacc[warp][HD + n * 8 + 2 * t + e] = b;
+                    colacc[warp][2 * HD + n * 8 + 2 * t + e] = c;
+                }
+            }
+    }
     // ---- bin the accumulated dS into the 225 relative-position slots (deterministic) ----
     __syncthreads();
     g1 = warp_sum(g1);
@@ -561,8 +576,9 @@ __global__ void __launch_bounds__(ATT_THREADS, HD <= 32 ? 3 : 1) attn_bwd_kernel
     }
     __syncthreads();
     float* part = partials + ((long long)h * gridDim.x + blockIdx.x) * bwd_part_stride(HD);
-    for (int i = threadIdx.x; i < 3 * HD; i += ATT_THREADS)   // (the __syncthreads above ordered the warps' slices)
-        part[NBINS + 3 + i] = colacc[0][i] + colacc[1][i] + colacc[2][i] + colacc[3][i];
+    if (want_colsum)
+        for (int i = threadIdx.x; i < 3 * HD; i += ATT_THREADS)   // (the __syncthreads above ordered the warps' slices)
+            part[NBINS + 3 + i] = colacc[0][i] + colacc[1][i] + colacc[2][i] + colacc[3][i];
     for (int bin = threadIdx.x; bin < NBINS; bin += ATT_THREADS) {
         const int dy = bin / 15 - 7, dx = bin % 15 - 7;
         float sum = 0.f;
