@@ -10,11 +10,14 @@ python bench.py --impl reference --steps 3 --warmup 1 > gpurun_out/bench_ref_$TA
 python bench.py --steps 2 --warmup 3 --no-cpu-baseline --no-gpu-eager --no-graph > gpurun_out/plain_launch_$TAG.log 2>&1 &&
 ncu --metrics gpu__time_duration.sum --clock-control none -s 3500 -c 1100 --csv --log-file gpurun_out/launches_$TAG.csv \
     python bench.py --steps 2 --warmup 3 --no-cpu-baseline --no-gpu-eager --no-graph > gpurun_out/ncu_launch_$TAG.log 2>&1
-python tools/kernel_bench.py t5h t5nn t5nt t5tn dwh attnf attnb lnb mdta > gpurun_out/plain_kb_$TAG.log 2>&1 &&
-UWR_KB_REPS=1 ncu --set full --clock-control none -k regex:"gemm_tcgen05|dwconv_|attn_|ln_.wd|mdta_" -c 22 \
-    -o gpurun_out/ncu_top_$TAG python tools/kernel_bench.py t5h t5nn t5nt t5tn dwh attnf attnb lnb mdta > gpurun_out/ncu_kb_$TAG.log 2>&1
+python tools/kernel_bench.py t5h t5nn t5nt t5tn t5big dwh attnf attnb lnb mdta oproj conv > gpurun_out/plain_kb_$TAG.log 2>&1 &&
+UWR_KB_REPS=1 ncu --set full --clock-control none -k regex:"gemm_tcgen05|dwconv_|attn_|ln_.wd|mdta_|proj_.*mma" -c 26 \
+    -o gpurun_out/ncu_top_$TAG python tools/kernel_bench.py t5h t5nn t5nt t5tn dwh attnf attnb lnb mdta oproj > gpurun_out/ncu_kb_$TAG.log 2>&1
+# gpurun copies back at most 64 MiB: keep the raw-page CSV of the report (what tools/ncu_summarize.py reads), drop the report
+ncu -i gpurun_out/ncu_top_$TAG.ncu-rep --page raw --csv > gpurun_out/ncu_top_$TAG.raw.csv 2>/dev/null && rm -f gpurun_out/ncu_top_$TAG.ncu-rep
 cat gpurun_out/plain_kb_$TAG.log
 UWR_EAGER_REF=1 UWR_PROFILE_OUT=gpurun_out/prof_spectral_$TAG.json python tools/train_bench.py SpectralTransformer L1withColor 8 > gpurun_out/train_spectral_$TAG.log 2>&1; tail -1 gpurun_out/train_spectral_$TAG.log | cut -c1-600
 UWR_EAGER_REF=1 UWR_PROFILE_OUT=gpurun_out/prof_newbig_$TAG.json python tools/train_bench.py NewBigFRFNModel fflMix 16 > gpurun_out/train_newbig_$TAG.log 2>&1; tail -1 gpurun_out/train_newbig_$TAG.log | cut -c1-600
 python tests/tools/infer_sweep.py > gpurun_out/infer_sweep_$TAG.log 2>&1; tail -3 gpurun_out/infer_sweep_$TAG.log
 ls -la gpurun_out | tail -20; du -sh gpurun_out
+tools/micro/ffma2_bench > gpurun_out/ffma2_$TAG.txt 2>&1; cat gpurun_out/ffma2_$TAG.txt | tail -3

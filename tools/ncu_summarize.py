@@ -32,8 +32,10 @@ if os.path.exists(lp):
                                       for k, v in agg.most_common()]}
 
 rp = os.path.join(ROOT, "gpurun_out", f"ncu_top_{tag}.ncu-rep")
-if os.path.exists(rp):
-    txt = subprocess.run(["ncu", "-i", rp, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+rc = os.path.join(ROOT, "gpurun_out", f"ncu_top_{tag}.raw.csv")    # exported on the GPU box when the report is too big to copy
+if os.path.exists(rp) or os.path.exists(rc):
+    txt = (open(rc).read() if os.path.exists(rc) else
+           subprocess.run(["ncu", "-i", rp, "--page", "raw", "--csv"], capture_output=True, text=True).stdout)
     rows = list(csv.reader(txt.splitlines()))
     hdr, units = rows[0], rows[1]
     want = {"gpu__time_duration.sum": "duration", "dram__bytes_read.sum": "dram_read", "dram__bytes_write.sum": "dram_write",
