@@ -18,8 +18,11 @@ step = TrainStep(model, loss, lr=1e-3, local_batch=B, vgg_weights="random" if lo
 g = torch.Generator().manual_seed(2024)
 raw = (torch.rand(B, 3, S, S, generator=g) * 2 - 1).cuda()
 ref = (torch.rand(B, 3, S, S, generator=g) * 2 - 1).cuda()
+first = None
 for _ in range(3):
     l, n = step(raw, ref)
+    if first is None:   # the seeded first step: comparable across kernel versions (later steps follow a chaotic trajectory at
+        first = (l.item(), n[0].item())   # lr 1e-3 on random targets, their loss / norm are only a liveness check)
 torch.cuda.synchronize()
 e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
 n0 = ops.launch_count()
@@ -53,7 +56,7 @@ for r in kernel_table:
     f[0] += r["ms_total"]; f[1] += r["launches"]
 res = {"arch": arch, "loss": loss, "batch": B, "size": S, "ms_per_step": ms, "images_per_s": 1000.0 * B / ms,
        "ms_per_step_graph": ms_graph, "images_per_s_graph": (1000.0 * B / ms_graph) if ms_graph else None,
-       "uwr_launches_per_step": (ops.launch_count() - n0) // (steps + 1), "loss_value": l.item(), "grad_norm": n[0].item(),
+       "uwr_launches_per_step": (ops.launch_count() - n0) // (steps + 1), "loss_first_step": first[0], "grad_norm_first_step": first[1], "loss_value": l.item(), "grad_norm": n[0].item(),
        "max_mem_gb": torch.cuda.max_memory_allocated() / 2 ** 30,
        "uwr_kernel_ms": {k: round(v[0], 3) for k, v in sorted(fam.items(), key=lambda kv: -kv[1][0])[:8]},
        "uwr_kernel_ms_total": round(sum(v[0] for v in fam.values()), 2)}

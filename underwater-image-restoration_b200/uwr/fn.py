@@ -34,10 +34,10 @@ class LinearFn(torch.autograd.Function):
         x2 = _rows(x)
         fast = ops.fast_path() and x2.shape[1] % 4 == 0 and w.shape[0] % 4 == 0
         if fast and not rounded:
-            # a rounded copy only pays off on big token matrices (measured: it costs more than it saves on
-            # the many small per-image products of MDTA); small ones take the legacy kernel, which rounds
-            # its fragments in flight
-            fast = x2.shape[0] >= 131072
+            # a rounded copy does not pay off on tiny token matrices (a launch for a few KB); those take the legacy
+            # kernel, which rounds its fragments in flight.  From 8 192 rows on the tcgen05 kernel wins even with the
+            # copy (NT M65536 N512 K256: 0.18 ms legacy vs ~0.05 ms)
+            fast = x2.shape[0] >= 8192
             if fast:
                 x2 = ops.scale_round(x2, x2.shape[1])
         y = ops.linear(x2, ops.rounded_weight(w) if fast else w, b, t5=fast)
@@ -271,7 +271,7 @@ class LinearDWConvFn(torch.autograd.Function):
         Ch = w.shape[0]
         fast = ops.fast_path() and x2.shape[1] % 4 == 0 and Ch % 4 == 0
         if fast and not rounded:
-            fast = x2.shape[0] >= 131072      # as LinearFn: a rounded copy only pays off on big token matrices
+            fast = x2.shape[0] >= 8192        # as LinearFn: a rounded copy does not pay off on tiny token matrices
             if fast:
                 x2 = ops.scale_round(x2, x2.shape[1])
         u = ops.linear(x2, ops.rounded_weight(w) if fast else w, None, t5=fast)

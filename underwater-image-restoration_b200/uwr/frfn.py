@@ -48,24 +48,27 @@ class FRFNBlockFn(torch.autograd.Function):
         B, L, Cc, Cq, Ch, H, W, residual = ctx.meta
         M = B * L
         d = (dout if dout.is_contiguous() else dout.contiguous()).view(M, Cc)
-        d_s = ops.scale_round(d, Cc, dp, L)
+        d_s, db2 = ops.scale_round_colsum(d, Cc, dp, L)          # rounded cotangent + linear2 bias gradient, one pass
         dh = ops.linear_dgrad(d_s, ops.rounded_weight(w2), t5=True)
         dw2, _ = ops.linear_wgrad(d_s, h, want_bias=False, t5=True)
-        db2 = ops.colsum(d_s, Cc)
         del d_s
         du = torch.empty_like(u)
         dv = ops.gelu_gate_bwd(dh, u, v, Ch, 1, du=du)          # also fills du[:, Ch:]
         del dh
-        _, ddww, ddwb = ops.dwconv_gelu_bwd(dv, u, dww, B, H, W, Ch, du=du)
+        # linear1 bias gradient = column sums of du: the conv half comes out of the depthwise backward itself
+        db1 = ops._empty((2 * Ch,), du)
+        _, ddww, ddwb, _ = ops.dwconv_gelu_bwd(dv, u, dww, B, H, W, Ch, du=du, want_du_colsum=True, dusum_out=db1[:Ch])
+        ops.colsum(du[:, Ch:], Ch, out=db1[Ch:])
         del dv
         dxp = ops.linear_dgrad(du, ops.rounded_weight(w1), t5=True)
         dw1, _ = ops.linear_wgrad(du, xp, want_bias=False, t5=True)
-        db1 = ops.colsum(du, 2 * Ch)
         del du
-        # partial conv backward (small GEMMs on a strided view: legacy kernel)
-        g1 = dxp[:, :Cq]
-        dwpm, _ = ops.linear_wgrad(g1, col, want_bias=False)
-        dcol = ops.linear_dgrad(g1, wpm)
+        # partial conv backward: a dense TF32-rounded copy of the C/4-wide slice feeds the tcgen05 kernel (the strided,
+        # un-rounded view used to take the legacy mma.sync GEMM: 4 ms per NewBigFRFN step)
+        fast = ops.fast_path()
+        g1 = ops.scale_round(dxp[:, :Cq], Cq) if fast else dxp[:, :Cq]
+        dwpm, _ = ops.linear_wgrad(g1, col, want_bias=False, t5=fast)
+        dcol = ops.linear_dgrad(g1, wpm, t5=fast)
         ops.col2im_3x3(dcol, dxp, B, H, W, Cq)                   # overwrites dxp[:, :Cq] with d/d(FRFN input)
         dg = db = None
         if nw is not None:
