@@ -347,7 +347,10 @@ __host__ __device__ constexpr int bwd_part_stride(int hd) { return NBINS + 3 + 3
 // ------------------------------------------------------------------------------------------
 // Backward.  grid = (ctas_per_head, heads); each CTA walks the (batch, window) tiles of one head
 // so that the relative-position-bias gradient accumulates in registers and is binned once.
-template <int HD>
+// X3: full-fp32 operands (3xTF32 compensation) vs exact TF32 operands (one pass); a template parameter, not a branch on
+// p.x3: the kernel body is fully unrolled and ncu attributes 11 % of its stalls to instruction fetch -- only one of the
+// two variants of every product is compiled in.
+template <int HD, bool X3>
 __global__ void __launch_bounds__(ATT_THREADS, HD <= 32 ? 3 : 1) attn_bwd_kernel(const AttnParams p,
                                                                               const float* __restrict__ dout,
                                                                               long long ld_dout,
@@ -414,10 +417,10 @@ __global__ void __launch_bounds__(ATT_THREADS, HD <= 32 ? 3 : 1) attn_bwd_kernel
         float pm[8][4], dp[8][4];  // final mixture P and dP -> dS
         {
             float s[8][4], p0[8][4];
-            mma_rows_x_rowsT<HD>(s, Qs, Ks, r0, g, t, p.x3);
+            mma_rows_x_rowsT<HD>(s, Qs, Ks, r0, g, t, X3);
             add_bias_mask(s, tab, reg, r0, g, t, p.shift > 0);
             row_softmax(s, p0);
-            mma_rows_x_rowsT<HD>(dp, dOs, Vs, r0, g, t, p.x3);  // dP = dO V^T
+            mma_rows_x_rowsT<HD>(dp, dOs, Vs, r0, g, t, X3);  // dP = dO V^T
 #pragma unroll
             for (int half = 0; half < 2; ++half) {
                 float rowdot = 0.f;
@@ -452,7 +455,7 @@ __global__ void __launch_bounds__(ATT_THREADS, HD <= 32 ? 3 : 1) attn_bwd_kernel
         // dQ = scale * dS K  (Qs holds scale*q, so the chain rule adds one more factor scale)
         {
             float dq[HD / 8][4];
-            mma_regs_x_rows<HD, true>(dq, dp, Ks, g, t, p.x3);  // dS rows sum to ~0: needs 3xTF32
+            mma_regs_x_rows<HD, true>(dq, dp, Ks, g, t, X3);  // dS rows sum to ~0: needs 3xTF32
             if (want_colsum) colsum_add<HD>(csq, dq);   // scaled by p.scale when it is folded, after the tile loop
 #pragma unroll
             for (int half = 0; half < 2; ++half) {
@@ -512,7 +515,7 @@ __global__ void __launch_bounds__(ATT_THREADS, HD <= 32 ? 3 : 1) attn_bwd_kernel
                         bb[n][1] = f2tf32(Bm[(kb * 8 + t + 4) * ST + n * 8 + g]);
                     }
                 }
-                if (which == 1 && !p.x3) {
+                if (which == 1 && !X3) {
 #pragma unroll
                     for (int c = 0; c < 4; ++c) a[c] = (a[c] + 0x1000u) & 0xFFFFE000u;
 #pragma unroll
@@ -521,7 +524,7 @@ __global__ void __launch_bounds__(ATT_THREADS, HD <= 32 ? 3 : 1) attn_bwd_kernel
                         bb[n][1] = (bb[n][1] + 0x1000u) & 0xFFFFE000u;
                     }
                 }
-                if (which == 1 && p.x3) {  // dK: error-compensated
+                if (which == 1 && X3) {  // dK: error-compensated
 #pragma unroll
                     for (int n = 0; n < HD / 8; ++n) mma_tf32_16x8x8(acc[n], al, bb[n]);
 #pragma unroll
@@ -1003,10 +1006,10 @@ int launch_fwd(const AttnParams& p, float* out, long long ld_out, cudaStream_t s
     return 0;
 }
 
-template <int HD>
-int launch_bwd(const AttnParams& p, const float* dout, long long ld_dout, float* dq, float* dkv, float* partials,
-               int cph, cudaStream_t stream) {
-    auto kern = attn_bwd_kernel<HD>;
+template <int HD, bool X3>
+int launch_bwd_x(const AttnParams& p, const float* dout, long long ld_dout, float* dq, float* dkv, float* partials,
+                 int cph, cudaStream_t stream) {
+    auto kern = attn_bwd_kernel<HD, X3>;
     static bool configured = false;
     if (!configured) {
         UWR_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, bwd_smem<HD>()));
@@ -1015,6 +1018,12 @@ int launch_bwd(const AttnParams& p, const float* dout, long long ld_dout, float*
     kern<<<dim3(cph, p.heads), ATT_THREADS, bwd_smem<HD>(), stream>>>(p, dout, ld_dout, dq, dkv, partials);
     UWR_CHECK_LAUNCH("attn_bwd_kernel");
     return 0;
+}
+template <int HD>
+int launch_bwd(const AttnParams& p, const float* dout, long long ld_dout, float* dq, float* dkv, float* partials,
+               int cph, cudaStream_t stream) {
+    return p.x3 ? launch_bwd_x<HD, true>(p, dout, ld_dout, dq, dkv, partials, cph, stream)
+                : launch_bwd_x<HD, false>(p, dout, ld_dout, dq, dkv, partials, cph, stream);
 }
 
 }  // namespace
