@@ -70,6 +70,7 @@ struct TileSrc {
     int col;
     float mul;
     float* dst;
+    int rnd = 0;   // round the staged values to TF32 (exact-operand mode: scale * q is the only inexact tile)
 };
 
 template <int HD, int NT>
@@ -98,8 +99,9 @@ __device__ __forceinline__ void stage_tiles(const TileSrc<HD> (&t)[NT], const lo
                 const float m = t[g0 + g].mul;
                 // full fp32 is kept in shared memory: S, dP, dQ, dK use error-compensated 3xTF32 (hi/lo
                 // split at fragment load) because softmax' and the dS cancellations amplify rounding
-                *reinterpret_cast<float4*>(t[g0 + g].dst + r * ST + c4) =
-                    make_float4(buf[g][i].x * m, buf[g][i].y * m, buf[g][i].z * m, buf[g][i].w * m);
+                float4 v = make_float4(buf[g][i].x * m, buf[g][i].y * m, buf[g][i].z * m, buf[g][i].w * m);
+                if (t[g0 + g].rnd) v = make_float4(tf32_round(v.x), tf32_round(v.y), tf32_round(v.z), tf32_round(v.w));
+                *reinterpret_cast<float4*>(t[g0 + g].dst + r * ST + c4) = v;
             }
     }
 }
@@ -123,7 +125,8 @@ __device__ __forceinline__ void prep_tf32(float x, uint32_t& hi, uint32_t& lo) {
 
 // acc[nt][4] (16 rows x 64 cols) = A[r0.., :HD] * Bm[:, :HD]^T   (both row-major fp32 [64][HD+4]),
 // 3xTF32: a*b ~= a_lo*b_hi + a_hi*b_lo + a_hi*b_hi  (fp32-level accuracy on the tensor cores)
-template <int HD>
+// EXACT (with x3 = false): both operands already hold TF32 values -- no rounding at the fragment load
+template <int HD, bool EXACT = false>
 __device__ __forceinline__ void mma_rows_x_rowsT(float (&acc)[8][4], const float* A, const float* Bm, int r0,
                                                  int g, int t, bool x3 = true) {
     constexpr int ST = HD + 4;
@@ -147,7 +150,7 @@ __device__ __forceinline__ void mma_rows_x_rowsT(float (&acc)[8][4], const float
             split_tf32(Bm[(nt * 8 + g) * ST + ks * 8 + t], bh[nt][0], bl[nt][0]);
             split_tf32(Bm[(nt * 8 + g) * ST + ks * 8 + t + 4], bh[nt][1], bl[nt][1]);
         }
-        if (!x3) {  // single pass: operands rounded to nearest (a raw value would be truncated)
+        if (!x3 && !EXACT) {  // single pass: operands rounded to nearest (a raw value would be truncated)
 #pragma unroll
             for (int c = 0; c < 4; ++c) ah[c] = (ah[c] + 0x1000u) & 0xFFFFE000u;
 #pragma unroll
@@ -169,7 +172,7 @@ __device__ __forceinline__ void mma_rows_x_rowsT(float (&acc)[8][4], const float
 
 // out[nt2][4] (16 rows x HD) = P(regs, 16 x 64 in C-fragment layout) * Bm[64][HD+4]
 // key permutation inside each k8 block: slot t <-> key 2t, slot t+4 <-> key 2t+1.
-template <int HD, bool X3>
+template <int HD, bool X3, bool EXACT = false>
 __device__ __forceinline__ void mma_regs_x_rows(float (&out)[HD / 8][4], const float (&P)[8][4], const float* Bm,
                                                 int g, int t, bool x3 = true) {
     constexpr int ST = HD + 4;
@@ -190,7 +193,7 @@ __device__ __forceinline__ void mma_regs_x_rows(float (&out)[HD / 8][4], const f
             prep_tf32<X3>(Bm[(kb * 8 + 2 * t) * ST + n * 8 + g], b[n][0], bl[n][0]);
             prep_tf32<X3>(Bm[(kb * 8 + 2 * t + 1) * ST + n * 8 + g], b[n][1], bl[n][1]);
         }
-        if (X3 && !x3) {
+        if (X3 && !x3 && !EXACT) {
 #pragma unroll
             for (int c = 0; c < 4; ++c) a[c] = (a[c] + 0x1000u) & 0xFFFFE000u;
 #pragma unroll
@@ -406,7 +409,9 @@ __global__ void __launch_bounds__(ATT_THREADS, HD <= 32 ? 3 : 1) attn_bwd_kernel
         }
         __syncthreads();
         {
-            const TileSrc<HD> src[4] = {{p.q, p.ld_q, p.q_off + h * HD, p.scale, Qs},
+            // exact-operand mode (!X3): k, v, dout are TF32 values already; scale * q is rounded here, once, so that no
+            // product of this kernel converts a fragment (a third of the instruction stream before)
+            const TileSrc<HD> src[4] = {{p.q, p.ld_q, p.q_off + h * HD, p.scale, Qs, X3 ? 0 : 1},
                                         {p.kv, p.ld_kv, p.k_off + h * HD, 1.0f, Ks},
                                         {p.kv, p.ld_kv, p.v_off + h * HD, 1.0f, Vs},
                                         {dout, ld_dout, h * HD, 1.0f, dOs}};
@@ -417,10 +422,10 @@ __global__ void __launch_bounds__(ATT_THREADS, HD <= 32 ? 3 : 1) attn_bwd_kernel
         float pm[8][4], dp[8][4];  // final mixture P and dP -> dS
         {
             float s[8][4], p0[8][4];
-            mma_rows_x_rowsT<HD>(s, Qs, Ks, r0, g, t, X3);
+            mma_rows_x_rowsT<HD, !X3>(s, Qs, Ks, r0, g, t, X3);
             add_bias_mask(s, tab, reg, r0, g, t, p.shift > 0);
             row_softmax(s, p0);
-            mma_rows_x_rowsT<HD>(dp, dOs, Vs, r0, g, t, X3);  // dP = dO V^T
+            mma_rows_x_rowsT<HD, !X3>(dp, dOs, Vs, r0, g, t, X3);  // dP = dO V^T
 #pragma unroll
             for (int half = 0; half < 2; ++half) {
                 float rowdot = 0.f;
@@ -443,7 +448,7 @@ __global__ void __launch_bounds__(ATT_THREADS, HD <= 32 ? 3 : 1) attn_bwd_kernel
                         g2 += dP * r * r;
                         pm[nt][c] = tf32_round(w0 * P0 + w1 * r * r);
                         const float ds = w0 * P0 * (dP - rowdot) + w1 * 2.f * r * dP;
-                        dp[nt][c] = ds;  // dp now holds dS (full fp32: dQ / dK are error-compensated)
+                        dp[nt][c] = X3 ? ds : tf32_round(ds);  // dp now holds dS (full fp32 when dQ / dK are error-compensated)
                         dv[e] = ds;
                     }
                     float2* accp = reinterpret_cast<float2*>(dSacc + i * PS_STRIDE + nt * 8 + 2 * t);
@@ -455,7 +460,7 @@ __global__ void __launch_bounds__(ATT_THREADS, HD <= 32 ? 3 : 1) attn_bwd_kernel
         // dQ = scale * dS K  (Qs holds scale*q, so the chain rule adds one more factor scale)
         {
             float dq[HD / 8][4];
-            mma_regs_x_rows<HD, true>(dq, dp, Ks, g, t, X3);  // dS rows sum to ~0: needs 3xTF32
+            mma_regs_x_rows<HD, true, !X3>(dq, dp, Ks, g, t, X3);  // dS rows sum to ~0: needs 3xTF32
             if (want_colsum) colsum_add<HD>(csq, dq);   // scaled by p.scale when it is folded, after the tile loop
 #pragma unroll
             for (int half = 0; half < 2; ++half) {
@@ -510,12 +515,15 @@ __global__ void __launch_bounds__(ATT_THREADS, HD <= 32 ? 3 : 1) attn_bwd_kernel
                     if (which == 1) {
                         split_tf32(Bm[(kb * 8 + t) * ST + n * 8 + g], bb[n][0], bl[n][0]);
                         split_tf32(Bm[(kb * 8 + t + 4) * ST + n * 8 + g], bb[n][1], bl[n][1]);
-                    } else {
+                    } else if (X3) {
                         bb[n][0] = f2tf32(Bm[(kb * 8 + t) * ST + n * 8 + g]);
                         bb[n][1] = f2tf32(Bm[(kb * 8 + t + 4) * ST + n * 8 + g]);
+                    } else {   // dO holds TF32 values
+                        bb[n][0] = __float_as_uint(Bm[(kb * 8 + t) * ST + n * 8 + g]);
+                        bb[n][1] = __float_as_uint(Bm[(kb * 8 + t + 4) * ST + n * 8 + g]);
                     }
                 }
-                if (which == 1 && !X3) {
+                if (false) {   // (exact-operand mode: dS was rounded when it was formed, scale * q when it was staged)
 #pragma unroll
                     for (int c = 0; c < 4; ++c) a[c] = (a[c] + 0x1000u) & 0xFFFFE000u;
 #pragma unroll
