@@ -467,17 +467,38 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_const
     }
 }
 
-__global__ void t5_splitk_reduce_kernel(const float* __restrict__ ws, float* __restrict__ out, long long n,
-                                        long long stride, int splits) {
-    long long i = ((long long)blockIdx.x * blockDim.x + threadIdx.x) * 4;
-    const long long step = (long long)gridDim.x * blockDim.x * 4;
-    for (; i < n; i += step) {
+// Sum of the per-split partial tiles (deterministic: fixed assignment, fixed order).  A CTA = 32 float4 columns x 8 split
+// groups: the partials of a thin weight gradient are only a few thousand float4 wide, so one thread per column (the first
+// version) walked up to 148 splits as a chain of dependent-latency loads with ~4 in flight -- 14 us for 10 MB.  Eight
+// threads per column, four loads in flight each, then a fixed-order fold through shared memory.
+constexpr int RED_GROUPS = 8;
+__global__ void __launch_bounds__(32 * RED_GROUPS) t5_splitk_reduce_kernel(const float* __restrict__ ws,
+                                                                          float* __restrict__ out, long long n,
+                                                                          long long stride, int splits) {
+    __shared__ float4 sh[RED_GROUPS][32];
+    const int col = threadIdx.x & 31, grp = threadIdx.x >> 5;
+    const long long cols = n / 4;
+    for (long long base = (long long)blockIdx.x * 32; base < cols; base += (long long)gridDim.x * 32) {
+        const long long i = (base + col) * 4;
         float4 s = make_float4(0.f, 0.f, 0.f, 0.f);
-        for (int z = 0; z < splits; ++z) {
-            const float4 v = *reinterpret_cast<const float4*>(ws + z * stride + i);
-            s.x += v.x; s.y += v.y; s.z += v.z; s.w += v.w;
+        if (base + col < cols) {
+#pragma unroll 4
+            for (int z = grp; z < splits; z += RED_GROUPS) {
+                const float4 v = *reinterpret_cast<const float4*>(ws + z * stride + i);
+                s.x += v.x; s.y += v.y; s.z += v.z; s.w += v.w;
+            }
         }
-        *reinterpret_cast<float4*>(out + i) = s;
+        sh[grp][col] = s;
+        __syncthreads();
+        if (grp == 0 && base + col < cols) {
+#pragma unroll
+            for (int g = 1; g < RED_GROUPS; ++g) {
+                const float4 v = sh[g][col];
+                s.x += v.x; s.y += v.y; s.z += v.z; s.w += v.w;
+            }
+            *reinterpret_cast<float4*>(out + i) = s;
+        }
+        __syncthreads();
     }
 }
 
@@ -735,9 +756,9 @@ extern "C" int uwr_gemm_tcgen05(const uwr_gemm_desc* d, uwr_stream_t stream_) {
     if (rc) return rc;
     if (sp.splits > 1) {
         const long long n = (long long)d->M * d->N;
-        int blocks = (int)((n / 4 + 255) / 256);
-        if (blocks > 4 * uwr_sm_count()) blocks = 4 * uwr_sm_count();
-        t5_splitk_reduce_kernel<<<blocks, 256, 0, stream>>>(d->workspace, d->C, n, n, sp.splits);
+        int blocks = (int)((n / 4 + 31) / 32);
+        if (blocks > 8 * uwr_sm_count()) blocks = 8 * uwr_sm_count();
+        t5_splitk_reduce_kernel<<<blocks, 32 * RED_GROUPS, 0, stream>>>(d->workspace, d->C, n, n, sp.splits);
         UWR_CHECK_LAUNCH("t5_splitk_reduce_kernel");
     }
     return 0;
@@ -888,9 +909,9 @@ extern "C" int uwr_convgemm_tcgen05(const uwr_convgemm_desc* d, uwr_stream_t str
     if (rc) return rc;
     if (d->mode != 0 && sp.splits > 1) {
         const long long n = (long long)d->Cout * KN;
-        int blocks = (int)((n / 4 + 255) / 256);
-        if (blocks > 4 * uwr_sm_count()) blocks = 4 * uwr_sm_count();
-        t5_splitk_reduce_kernel<<<blocks, 256, 0, stream>>>(d->workspace, d->dw, n, n, sp.splits);
+        int blocks = (int)((n / 4 + 31) / 32);
+        if (blocks > 8 * uwr_sm_count()) blocks = 8 * uwr_sm_count();
+        t5_splitk_reduce_kernel<<<blocks, 32 * RED_GROUPS, 0, stream>>>(d->workspace, d->dw, n, n, sp.splits);
         UWR_CHECK_LAUNCH("t5_splitk_reduce_kernel");
     }
     return 0;

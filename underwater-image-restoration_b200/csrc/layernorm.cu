@@ -66,7 +66,7 @@ __global__ void __launch_bounds__(LN_WARPS * 32) ln_fwd_kernel(const float* __re
 // warp pass, RPI passes in flight), so a 128-byte row (C = 32) no longer costs a whole warp two
 // full-width reductions.
 template <int LPR, int V4>
-__global__ void __launch_bounds__(LN_WARPS * 32) ln_fwd_vec_kernel(const float* __restrict__ x,
+__global__ void __launch_bounds__(LN_WARPS * 32, V4 <= 2 ? 4 : 2) ln_fwd_vec_kernel(const float* __restrict__ x,
                                                                    const float* __restrict__ gamma,
                                                                    const float* __restrict__ beta,
                                                                    float* __restrict__ y, float* __restrict__ mean,
@@ -409,7 +409,7 @@ extern "C" int uwr_layernorm_fwd(const float* x, const float* gamma, const float
 #define LN_FWD_VEC(L, V)                                                                                         \
     do {                                                                                                         \
         long long b = (rows + LN_WARPS * (32 / L) - 1) / (LN_WARPS * (32 / L));                                  \
-        const long long cap = (long long)uwr_sm_count() * 8;                                                     \
+        const long long cap = (long long)uwr_sm_count() * (V <= 2 ? 4 : 2);   /* one resident wave */            \
         if (b > cap) b = cap;                                                                                    \
         ln_fwd_vec_kernel<L, V><<<(unsigned)b, LN_WARPS * 32, 0, stream>>>(x, gamma, beta, y, mean, rstd, rows,  \
                                                                            eps, uwr_round_outputs());            \
