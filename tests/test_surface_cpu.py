@@ -172,3 +172,56 @@ def test_direct_gradient_writes_are_scoped_to_trainstep():
     with ops.direct_grad_writes():
         pass
     assert ops._DIRECT_WRITES is False
+
+
+def test_split_plan_fits_one_wave_and_conv_geometry_gate(build_lib):
+    """Host logic of the tcgen05 GEMM that needs no GPU: (1) the split-contraction plan never creates more work items
+    than SMs when fewer tiles than SMs exist (a rounded-up split count once ran 3 tiles x 50 splits = 150 items on 148
+    SMs, two waves, on several AST weight-gradient shapes); (2) which convolution geometries the implicit-GEMM entry
+    point serves; (3) the new descriptor structs mirror the C layout."""
+    import subprocess, tempfile
+    from uwr import _lib
+    f = _lib.fn
+    sms = f["uwr_device_sm_count"]()
+    pick_bn = lambda n: 32 if n <= 32 else 64 if n <= 64 else 128 if n <= 128 else 256
+    for M, N, K in [(64, 256, 1 << 20), (384, 128, 262144), (768, 256, 65536), (1536, 512, 16384), (256, 1024, 65536),
+                    (2048, 512, 4096), (512, 512, 16384), (288, 32, 1 << 20), (32, 128, 1 << 20), (128, 128, 262144)]:
+        tiles = -(-M // 128) * -(-N // pick_bn(N))
+        nbytes = f["uwr_gemm_tcgen05_workspace_bytes"](M, N, K, 1)
+        splits = max(1, nbytes // (M * N * 4))
+        assert tiles * splits <= sms, (M, N, K, tiles, splits)
+        assert tiles * (splits + 1) > 0.7 * sms or splits * 8 * 32 >= K // 2, (M, N, K, tiles, splits)   # and it does fill the chip
+    assert f["uwr_gemm_tcgen05_workspace_bytes"](64, 256, 4096, 0) == 0
+
+    def desc(mode, B, H, W, Cin, Cout, k, stride, pad):
+        d = _lib.ConvGemmDesc()
+        d.mode, d.x, d.ld_x, d.B, d.H, d.W, d.Cin, d.Cout = mode, 0x1000, Cin, B, H, W, Cin, Cout
+        d.kh = d.kw = k
+        d.stride, d.pad = stride, pad
+        d.w = d.y = d.dy = d.dw = 0x2000
+        d.ld_y = d.ld_dy = Cout
+        return d
+    ok = lambda *a: f["uwr_convgemm_tcgen05_supported"](ctypes.byref(desc(*a)))
+    assert ok(0, 16, 256, 256, 32, 64, 4, 2, 1) == 1      # AST Downsample, forward
+    assert ok(1, 16, 256, 256, 32, 64, 4, 2, 1) == 1      # ... weight gradient
+    assert ok(2, 16, 256, 256, 32, 32, 3, 1, 1) == 1      # transposed weight gradient
+    assert ok(0, 2, 16, 16, 32, 64, 3, 1, 1) == 1
+    assert ok(0, 2, 16, 48, 32, 32, 3, 1, 1) == 0         # width neither a power of two nor a multiple of the box
+    assert ok(0, 2, 16, 16, 24, 64, 3, 1, 1) == 0         # Cin % 32
+    assert ok(0, 1, 8, 8, 32, 64, 3, 1, 1) == 0           # 64 output pixels < one 128-row tile
+    assert ok(1, 1, 8, 8, 32, 64, 3, 1, 1) == 1           # ... but a multiple of the 32-pixel contraction chunk
+    assert ok(3, 2, 16, 16, 32, 64, 3, 1, 1) == 0         # unknown mode
+    d = desc(1, 16, 256, 256, 32, 64, 4, 2, 1)
+    assert f["uwr_convgemm_tcgen05_workspace_bytes"](ctypes.byref(d)) % (64 * 512 * 4) == 0
+    assert f["uwr_convgemm_tcgen05"](ctypes.byref(desc(0, 2, 16, 48, 32, 32, 3, 1, 1)), None) == -1
+    assert b"unsupported geometry" in f["uwr_last_error"]()
+    with tempfile.TemporaryDirectory() as td:
+        src = os.path.join(td, "sz.c")
+        open(src, "w").write('#include <stdio.h>\n#include "uwr_b200.h"\nint main(void){printf("%zu %zu %zu %zu", '
+                             'sizeof(uwr_convgemm_desc), __builtin_offsetof(uwr_convgemm_desc, workspace_bytes), '
+                             'sizeof(uwr_attn_desc), __builtin_offsetof(uwr_attn_desc, dkv_colsum));return 0;}\n')
+        exe = os.path.join(td, "sz")
+        subprocess.check_call(["gcc", "-I", os.path.join(ROOT, "include"), src, "-o", exe])
+        cs, co, asz, ao = map(int, subprocess.check_output([exe]).split())
+    assert ctypes.sizeof(_lib.ConvGemmDesc) == cs and _lib.ConvGemmDesc.workspace_bytes.offset == co
+    assert ctypes.sizeof(_lib.AttnDesc) == asz and _lib.AttnDesc.dkv_colsum.offset == ao

@@ -776,6 +776,7 @@ namespace {
 
 struct ConvGeom {
     int OH, OW, taps, bw, bh, pw, ph;
+    bool ok_rows, ok_patch;   // the 128-pixel row box (mode 0) / the 32-pixel contraction patch (modes 1, 2) tile the image
 };
 bool conv_geom(const uwr_convgemm_desc* d, ConvGeom& g) {
     if (d->kh < 1 || d->kw < 1 || d->kh > 7 || d->kw > 7 || d->stride < 1 || d->stride > 2 || d->pad < 0 || d->pad > 3) return false;
@@ -786,9 +787,9 @@ bool conv_geom(const uwr_convgemm_desc* d, ConvGeom& g) {
     // mode 0: one box = 128 output pixels = bw x bh (part of a row, or whole rows); mode 1: 32 output pixels = pw x ph
     g.bw = g.OW < TM ? g.OW : TM;  g.bh = TM / g.bw;
     g.pw = g.OW < KC ? g.OW : KC;  g.ph = KC / g.pw;
-    if (g.bw * g.bh != TM || g.pw * g.ph != KC) return false;            // OW a power of two below the box, or a multiple
-    if (g.OW % g.bw || g.OH % g.bh || g.OW % g.pw || g.OH % g.ph) return false;
-    if (g.bw * d->stride > 256 || g.bh * d->stride > 256) return false;  // TMA box limit
+    // OW a power of two below the box, or a multiple of it; boxes never straddle rows / images; TMA box limit 256
+    g.ok_rows = g.bw * g.bh == TM && g.OW % g.bw == 0 && g.OH % g.bh == 0 && g.bw * d->stride <= 256 && g.bh * d->stride <= 256;
+    g.ok_patch = g.pw * g.ph == KC && g.OW % g.pw == 0 && g.OH % g.ph == 0;
     return true;
 }
 // (C, W, H, B) view of the token matrix; the box covers bw x bh output pixels of one tap (element strides = conv stride)
@@ -829,11 +830,11 @@ extern "C" int uwr_convgemm_tcgen05_supported(const uwr_convgemm_desc* d) {
     if (d->mode == 0) {
         if (!d->w || !d->y || d->ld_y % 4 || ((uintptr_t)d->w | (uintptr_t)d->y) % 16) return 0;
         if (d->bias && (uintptr_t)d->bias % 16) return 0;
-        return (g.OH * g.OW) % TM == 0 && pixels < (1ll << 31);
+        return g.ok_rows && (g.OH * g.OW) % TM == 0 && pixels < (1ll << 31);
     }
     if (d->mode == 1 || d->mode == 2) {
         if (!d->dy || !d->dw || d->ld_dy % 4 || ((uintptr_t)d->dy | (uintptr_t)d->dw) % 16) return 0;
-        return (g.OH * g.OW) % KC == 0 && pixels < (1ll << 31);
+        return g.ok_patch && (g.OH * g.OW) % KC == 0 && pixels < (1ll << 31);
     }
     return 0;
 }
