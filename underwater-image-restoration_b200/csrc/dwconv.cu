@@ -429,9 +429,11 @@ dwconv_bwd_kernel(const __grid_constant__ CUtensorMap map_dv, const float* __res
         const long long ustep = UHALF ? ld_u / 2 : ld_u;   // pointer steps in floats per pixel (ld_u is even)
         float* dup = du + uoff;
         // the first strip's u values are requested before waiting for the halo tile
-        float2 uc[8];
+        // both strips' u values are requested before waiting for the halo tile (fp16 u: 16 four-byte loads in flight; the
+        // second strip used to issue its loads after the first strip's arithmetic: long_scoreboard was 36 % of the stalls)
+        float2 uc[UHALF ? 16 : 8];
 #pragma unroll
-        for (int i = 0; i < 8; ++i)
+        for (int i = 0; i < (UHALF ? 16 : 8); ++i)
             uc[i] = (rok && (FAST || tx0 + i < W)) ? ld_u2<UHALF>(up + (long long)i * ustep) : make_float2(0.f, 0.f);
         uwr_tma::mbar_wait(&bars[it & 1], (it >> 1) & 1);
         if (rok) {
@@ -439,7 +441,7 @@ dwconv_bwd_kernel(const __grid_constant__ CUtensorMap map_dv, const float* __res
 #pragma unroll
             for (int hx = 0; hx < 2; ++hx) {  // two strips of 8 columns
                 const int lx0 = hx * 8;
-                if (hx == 1) {
+                if (hx == 1 && !UHALF) {
 #pragma unroll
                     for (int i = 0; i < 8; ++i)
                         uc[i] = (FAST || tx0 + 8 + i < W) ? ld_u2<UHALF>(up + (long long)(8 + i) * ustep) : make_float2(0.f, 0.f);
@@ -457,7 +459,7 @@ dwconv_bwd_kernel(const __grid_constant__ CUtensorMap map_dv, const float* __res
                     for (int a = 0; a < 3; ++a) col[a][(i + 2) % 3] = ld2(sp + (a * HS + lx0 + i + 2) * CG);
                     if (FAST || tx0 + lx0 + i < W) {
                         float2 cdf = make_float2(1.f, 1.f), pdf = make_float2(0.f, 0.f);  // plain conv: h1 = u, gelu' = 1
-                        const float2 uv = cvt_u2<UHALF>(uc[i]);
+                        const float2 uv = cvt_u2<UHALF>(uc[UHALF ? lx0 + i : i]);
                         if (!PLAIN) gelu_parts2(uv, cdf, pdf);
                         const float2 h1 = PLAIN ? uv : fmul2(uv, cdf);
                         float2 dh1 = make_float2(0.f, 0.f);
