@@ -258,8 +258,8 @@ def test_dwconv_gelu(exact, B, H, Ch, mode):
 @pytest.mark.parametrize("precision", ["tf32", "tf32x3"])
 @pytest.mark.parametrize("Cout,H", [(32, 48), (64, 40), (32, 24)])
 def test_input_proj(ops, Cout, H, precision):
-    """Default mode: tensor-core kernels (forward 3xTF32 = fp32-level, weight gradient single-pass TF32); tf32x3: the
-    scalar fp32 kernels.  H = 40 and 24 leave ragged 16-pixel tiles."""
+    """Default mode: tensor-core kernels (3xTF32: fp32-level, forward and weight gradient); tf32x3: the scalar fp32
+    kernels.  H = 40 and 24 leave ragged 16-pixel tiles."""
     from uwr.blocks import InputProjFn
     ops.set_gemm_precision(precision)
     try:
@@ -273,7 +273,7 @@ def test_input_proj(ops, Cout, H, precision):
         g = _r(B, H * H, Cout, seed=4)
         tok.backward(g)
         ref.backward(g.double())
-        assert rel_l2(w.grad, wd.grad) < (TOL_TF32 if precision == "tf32" else TOL_FP32 * 10)
+        assert rel_l2(w.grad, wd.grad) < TOL_FP32 * 10
         assert rel_l2(b.grad, bd.grad) < TOL_FP32 * 10
     finally:
         ops.set_gemm_precision("tf32")
@@ -282,8 +282,9 @@ def test_input_proj(ops, Cout, H, precision):
 @pytest.mark.parametrize("precision", ["tf32", "tf32x3"])
 @pytest.mark.parametrize("Cin,H", [(64, 40), (32, 40), (64, 16), (32, 24)])
 def test_output_proj(ops, Cin, H, precision):
-    """Forward: direct fp32 kernel.  Backward: tensor-core kernel (TF32 operands, both gradients from the im2col of the
-    3-channel cotangent) in the default mode, the scalar fp32 kernel in tf32x3; ragged tiles (40 = 2.5 x 16) included."""
+    """Forward: direct fp32 kernel.  Backward: tensor-core kernel (both gradients from the im2col of the 3-channel
+    cotangent, 3xTF32) in the default mode, the scalar fp32 kernel in tf32x3; ragged
+    tiles (40 = 2.5 x 16) included."""
     from uwr.blocks import OutputProjFn
     ops.set_gemm_precision(precision)
     try:
@@ -298,9 +299,10 @@ def test_output_proj(ops, Cin, H, precision):
         g = _r(B, 3, H, H, seed=4)
         out.backward(g)
         ref.backward(g.double())
-        tol = TOL_TF32 if precision == "tf32" else TOL_FP32 * 10
-        assert rel_l2(tok.grad, td.grad) < tol
-        assert rel_l2(w.grad, wd.grad) < tol
+        # both gradients are 3xTF32 on the tensor cores: fp32-level in either mode (every gradient of the network flows
+        # through this data gradient, and the boundary weight gradients carry a large share of the gradient norm)
+        assert rel_l2(tok.grad, td.grad) < TOL_FP32 * 10
+        assert rel_l2(w.grad, wd.grad) < TOL_FP32 * 10
         assert rel_l2(b.grad, bd.grad) < TOL_FP32 * 10
     finally:
         ops.set_gemm_precision("tf32")

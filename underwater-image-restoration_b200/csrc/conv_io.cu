@@ -5,6 +5,7 @@
 //   Upsample   ConvTranspose2x2 s2       (AST.py:428-443)      uwr_gemm_tf32 + 2x2 pixel scatter
 // plus the strided copy used for the skip concatenation (AST.py:904-916) and a deterministic
 // column sum (bias gradients).  All of these are HBM-bound data movement around the GEMMs.
+#include <cstdlib>
 #include "uwr_common.cuh"
 #include "../../include/uwr_b200.h"
 
@@ -336,12 +337,17 @@ __global__ void __launch_bounds__(256) output_proj_bwd_kernel(const float* __res
 // OutputProj backward on the tensor cores (single-pass TF32 mode).  With the im2col of the 3-channel cotangent
 //   A[p][k] = dY[co][py + 1 - ky][px + 1 - kx],   k = co*9 + ky*3 + kx  (27 columns, padded to 32)
 // both gradients are thin GEMMs over the pixels p of a tile that share A:
-//   dX[p][ci]  = sum_k A[p][k] Wm[k][ci]            (M = 16 pixels per warp, N = Cin, K = 32)
-//   dW[k][ci] += sum_p A[p][k] X[p][ci]             (M = 32, N = 8 channels per warp, K = the tile's pixels)
+//   dX[p][ci]  = sum_k A[p][k] Wm[k][ci]            (M = 16 pixels per warp, N = Cin, K = 32; 3xTF32: fp32-level)
+//   dW[k][ci] += sum_p A[p][k] X[p][ci]             (M = 32, N = 8 channels per warp, K = the tile's pixels; 3xTF32)
 // A is never materialised: its fragments are read straight from the 3 x 10 x 18 halo tile of dY.  The scalar kernel
 // above spends 54 FMAs per (pixel, channel) on the CUDA cores (0.70 ms for B=16 256x256 Cin=64, 8x its HBM time);
 // here the CUDA cores only stage and round the operands.
-constexpr int OPM_XS = 8;   // row padding of the X / Wm tiles: fragment loads (k = t, n = g) hit 32 distinct banks
+constexpr int OPM_XS = 8;
+// 3xTF32 operand split: hi = the value rounded to TF32, lo = the exact remainder (the tensor core truncates it again: < 2^-21)
+__device__ __forceinline__ void split_hi_lo(float v, uint32_t& hi, uint32_t& lo) {
+    hi = f2tf32(v);
+    lo = __float_as_uint(v - __uint_as_float(hi));
+}   // row padding of the X / Wm tiles: fragment loads (k = t, n = g) hit 32 distinct banks
 
 template <int CIN>
 __global__ void __launch_bounds__(256, 3) output_proj_bwd_mma_kernel(const float* __restrict__ dout,
@@ -355,9 +361,12 @@ __global__ void __launch_bounds__(256, 3) output_proj_bwd_mma_kernel(const float
     constexpr int KSPLIT = 8 / NT;       // warps sharing a column tile split the tile's pixels (Cin = 32: two halves)
     constexpr int NPIX = OP_TY * OP_TX;  // 128
     extern __shared__ __align__(16) float smem[];
-    float* xs = smem;                     // [128][XS]   X at the tile's pixels, TF32-rounded
-    float* wm = xs + NPIX * XS;           // [32][XS]    Wm[k][ci], TF32-rounded, rows 27..31 zero
-    float* dys = wm + 32 * XS;            // [3][10][18] dY halo tile, TF32-rounded, zero outside the image
+    float* xs = smem;                     // [128][XS]   X at the tile's pixels, full fp32
+    float* wm = xs + NPIX * XS;           // [32][XS]    Wm[k][ci], TF32-rounded (hi part), rows 27..31 zero
+    float* wl = wm + 32 * XS;             // [32][XS]    Wm - hi: the data gradient is 3xTF32 (every gradient of the network
+                                          //             flows through it; single-pass TF32 here doubled the model's gradient error)
+    float* dyf = wl + 32 * XS;            // [3][10][18] dY halo tile in full fp32, zero outside the image (hi / lo split at the
+                                          //             fragment loads: both gradients are 3xTF32)
     __shared__ float dbred[8][3];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int g = lane >> 2, t = lane & 3;
@@ -366,7 +375,9 @@ __global__ void __launch_bounds__(256, 3) output_proj_bwd_mma_kernel(const float
         const int k = idx / CIN, ci = idx % CIN;
         float v = 0.f;
         if (k < 27) v = weight[((k / 9) * CIN + ci) * 9 + k % 9];
-        wm[k * XS + ci] = tf32_round(v);
+        const float hi = tf32_round(v);
+        wm[k * XS + ci] = hi;
+        wl[k * XS + ci] = v - hi;
     }
     // offsets of this lane's A columns inside the halo tile: k = ks*8 + t (+4); columns >= 27 are zero
     int aoff[8];
@@ -406,8 +417,7 @@ __global__ void __launch_bounds__(256, 3) output_proj_bwd_mma_kernel(const float
             const int y = ty0 + pix / OP_TX, x = tx0 + pix % OP_TX;
             float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
             if (y < H && x < W) v = *reinterpret_cast<const float4*>(tokens + (((long long)b * H + y) * W + x) * ld + c4);
-            *reinterpret_cast<float4*>(xs + pix * XS + c4) =
-                make_float4(tf32_round(v.x), tf32_round(v.y), tf32_round(v.z), tf32_round(v.w));
+            *reinterpret_cast<float4*>(xs + pix * XS + c4) = v;   // full fp32: split into hi / lo at the fragment load
         }
         for (int idx = threadIdx.x; idx < 3 * OP_HY * OP_HX; idx += 256) {
             const int co = idx / (OP_HY * OP_HX), rem = idx % (OP_HY * OP_HX);
@@ -415,7 +425,7 @@ __global__ void __launch_bounds__(256, 3) output_proj_bwd_mma_kernel(const float
             const int y = ty0 + hy - 1, x = tx0 + hx - 1;
             float v = 0.f;
             if (y >= 0 && y < H && x >= 0 && x < W) v = dout[(((long long)b * 3 + co) * H + y) * W + x];
-            dys[idx] = tf32_round(v);
+            dyf[idx] = v;
             if (hy >= 1 && hy <= OP_TY && hx >= 1 && hx <= OP_TX) {   // the tile's own pixels: bias gradient
                 db0 += co == 0 ? v : 0.f;
                 db1 += co == 1 ? v : 0.f;
@@ -427,15 +437,18 @@ __global__ void __launch_bounds__(256, 3) output_proj_bwd_mma_kernel(const float
         // ---- dX: this warp's row of 16 pixels (rows g, g + 8 of the m16 tile) ----
         {
             const int ly = warp;
-            uint32_t a[4][4];
+            uint32_t a[4][4], al[4][4];
 #pragma unroll
             for (int ks = 0; ks < 4; ++ks) {
-                const float* r0 = dys + aoff[2 * ks] + ly * OP_HX + g;
-                const float* r1 = dys + aoff[2 * ks + 1] + ly * OP_HX + g;
-                a[ks][0] = (avalid >> (2 * ks)) & 1u ? __float_as_uint(r0[0]) : 0u;
-                a[ks][1] = (avalid >> (2 * ks)) & 1u ? __float_as_uint(r0[8]) : 0u;
-                a[ks][2] = (avalid >> (2 * ks + 1)) & 1u ? __float_as_uint(r1[0]) : 0u;
-                a[ks][3] = (avalid >> (2 * ks + 1)) & 1u ? __float_as_uint(r1[8]) : 0u;
+                const float* r0 = dyf + aoff[2 * ks] + ly * OP_HX + g;
+                const float* r1 = dyf + aoff[2 * ks + 1] + ly * OP_HX + g;
+                const float v[4] = {(avalid >> (2 * ks)) & 1u ? r0[0] : 0.f, (avalid >> (2 * ks)) & 1u ? r0[8] : 0.f,
+                                    (avalid >> (2 * ks + 1)) & 1u ? r1[0] : 0.f, (avalid >> (2 * ks + 1)) & 1u ? r1[8] : 0.f};
+#pragma unroll
+                for (int c = 0; c < 4; ++c) {
+                    a[ks][c] = f2tf32(v[c]);
+                    al[ks][c] = __float_as_uint(v[c] - __uint_as_float(a[ks][c]));
+                }
             }
             const int y = ty0 + ly;
 #pragma unroll
@@ -443,9 +456,11 @@ __global__ void __launch_bounds__(256, 3) output_proj_bwd_mma_kernel(const float
                 float acc[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
                 for (int ks = 0; ks < 4; ++ks) {
-                    uint32_t bf[2];
-                    bf[0] = __float_as_uint(wm[(ks * 8 + t) * XS + nt * 8 + g]);
-                    bf[1] = __float_as_uint(wm[(ks * 8 + t + 4) * XS + nt * 8 + g]);
+                    const int o0 = (ks * 8 + t) * XS + nt * 8 + g, o1 = o0 + 4 * XS;
+                    const uint32_t bf[2] = {__float_as_uint(wm[o0]), __float_as_uint(wm[o1])};
+                    const uint32_t bl[2] = {__float_as_uint(wl[o0]), __float_as_uint(wl[o1])};
+                    mma_tf32_16x8x8(acc, al[ks], bf);
+                    mma_tf32_16x8x8(acc, a[ks], bl);
                     mma_tf32_16x8x8(acc, a[ks], bf);
                 }
                 if (y < H) {
@@ -462,17 +477,21 @@ __global__ void __launch_bounds__(256, 3) output_proj_bwd_mma_kernel(const float
             for (int s8 = 0; s8 < STEPS; ++s8) {
                 const int pix = (kh * STEPS + s8) * 8 + t;           // pixel of fragment column t (t + 4 is in the same row)
                 const int poff = (pix / OP_TX) * OP_HX + pix % OP_TX;
-                uint32_t bf[2];
-                bf[0] = __float_as_uint(xs[pix * XS + nt2 * 8 + g]);
-                bf[1] = __float_as_uint(xs[(pix + 4) * XS + nt2 * 8 + g]);
+                // 3xTF32 (hi / lo split of both operands): the weight gradients of the first and the last layer carry a
+                // large share of the model's gradient norm, single-pass TF32 here was visible in the whole-model parity
+                uint32_t bf[2], bl[2];
+                split_hi_lo(xs[pix * XS + nt2 * 8 + g], bf[0], bl[0]);
+                split_hi_lo(xs[(pix + 4) * XS + nt2 * 8 + g], bf[1], bl[1]);
 #pragma unroll
                 for (int mt = 0; mt < 2; ++mt) {
-                    uint32_t a[4];
+                    uint32_t a[4], al[4];
                     const bool v0 = (mvalid >> (2 * mt)) & 1u, v1 = (mvalid >> (2 * mt + 1)) & 1u;
-                    a[0] = v0 ? __float_as_uint(dys[moff[2 * mt] + poff]) : 0u;
-                    a[1] = v1 ? __float_as_uint(dys[moff[2 * mt + 1] + poff]) : 0u;
-                    a[2] = v0 ? __float_as_uint(dys[moff[2 * mt] + poff + 4]) : 0u;
-                    a[3] = v1 ? __float_as_uint(dys[moff[2 * mt + 1] + poff + 4]) : 0u;
+                    split_hi_lo(v0 ? dyf[moff[2 * mt] + poff] : 0.f, a[0], al[0]);
+                    split_hi_lo(v1 ? dyf[moff[2 * mt + 1] + poff] : 0.f, a[1], al[1]);
+                    split_hi_lo(v0 ? dyf[moff[2 * mt] + poff + 4] : 0.f, a[2], al[2]);
+                    split_hi_lo(v1 ? dyf[moff[2 * mt + 1] + poff + 4] : 0.f, a[3], al[3]);
+                    mma_tf32_16x8x8(dwacc[mt], al, bf);
+                    mma_tf32_16x8x8(dwacc[mt], a, bl);
                     mma_tf32_16x8x8(dwacc[mt], a, bf);
                 }
             }
@@ -514,7 +533,7 @@ __global__ void __launch_bounds__(256, 3) output_proj_bwd_mma_kernel(const float
 // InputProj (3 -> Cout, + LeakyReLU) on the tensor cores.  A[p][k] = img[ci][py + ky - 1][px + kx - 1], k = ci*9 + ky*3 + kx
 // (27 columns padded to 32), read straight from the 3 x 10 x 18 halo tile of the image:
 //   forward   T[p][co] = leaky(b[co] + sum_k A[p][k] Wm[k][co])      3xTF32 (hi/lo split of both operands): fp32-level
-//   backward  dW[k][co] = sum_p A[p][k] dZ[p][co],  dZ = dT * leaky'(T)      single-pass TF32, as every weight gradient
+//   backward  dW[k][co] = sum_p A[p][k] dZ[p][co],  dZ = dT * leaky'(T)      3xTF32 as well (see the OutputProj kernel)
 // The scalar kernels above run 864 FMAs per pixel on the CUDA cores (0.15 / 0.36 ms at B=16 256x256, 7x their HBM time).
 template <int COUT>
 __global__ void __launch_bounds__(256, 2) input_proj_fwd_mma_kernel(const float* __restrict__ img,
@@ -603,8 +622,8 @@ __global__ void __launch_bounds__(256, 3) input_proj_bwd_mma_kernel(const float*
     constexpr int NT = COUT / 8, KSPLIT = 8 / NT, NPIX = OP_TY * OP_TX;
     constexpr int C4 = COUT / 4;            // float4 groups per token; 256 % C4 == 0: a thread always stages the same group
     extern __shared__ __align__(16) float smem[];
-    float* zs = smem;                       // [128][ZS]  dZ at the tile's pixels, TF32-rounded
-    float* ims = zs + NPIX * ZS;            // [3][10][18] image halo tile, TF32-rounded
+    float* zs = smem;                       // [128][ZS]  dZ at the tile's pixels, full fp32
+    float* ims = zs + NPIX * ZS;            // [3][10][18] image halo tile, full fp32
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int g = lane >> 2, t = lane & 3;
     int moff[4];
@@ -642,15 +661,14 @@ __global__ void __launch_bounds__(256, 3) input_proj_bwd_mma_kernel(const float*
                 d.z *= o.z > 0.f ? 1.f : slope; d.w *= o.w > 0.f ? 1.f : slope;
             }
             dbs.x += d.x; dbs.y += d.y; dbs.z += d.z; dbs.w += d.w;
-            *reinterpret_cast<float4*>(zs + pix * ZS + c4) =
-                make_float4(tf32_round(d.x), tf32_round(d.y), tf32_round(d.z), tf32_round(d.w));
+            *reinterpret_cast<float4*>(zs + pix * ZS + c4) = d;   // full fp32: hi / lo split at the fragment load
         }
         for (int idx = threadIdx.x; idx < 3 * OP_HY * OP_HX; idx += 256) {
             const int ci = idx / (OP_HY * OP_HX), rem = idx % (OP_HY * OP_HX);
             const int y = ty0 + rem / OP_HX - 1, x = tx0 + rem % OP_HX - 1;
             float v = 0.f;
             if (y >= 0 && y < H && x >= 0 && x < W) v = img[(((long long)b * 3 + ci) * H + y) * W + x];
-            ims[idx] = tf32_round(v);
+            ims[idx] = v;
         }
         __syncthreads();
         constexpr int STEPS = NPIX / 8 / KSPLIT;
@@ -658,17 +676,19 @@ __global__ void __launch_bounds__(256, 3) input_proj_bwd_mma_kernel(const float*
         for (int s8 = 0; s8 < STEPS; ++s8) {
             const int pix = (kh * STEPS + s8) * 8 + t;
             const int poff = (pix / OP_TX) * OP_HX + pix % OP_TX;
-            uint32_t bf[2];
-            bf[0] = __float_as_uint(zs[pix * ZS + nt2 * 8 + g]);
-            bf[1] = __float_as_uint(zs[(pix + 4) * ZS + nt2 * 8 + g]);
+            uint32_t bf[2], bl[2];   // 3xTF32, as the OutputProj weight gradient
+            split_hi_lo(zs[pix * ZS + nt2 * 8 + g], bf[0], bl[0]);
+            split_hi_lo(zs[(pix + 4) * ZS + nt2 * 8 + g], bf[1], bl[1]);
 #pragma unroll
             for (int mt = 0; mt < 2; ++mt) {
-                uint32_t a[4];
+                uint32_t a[4], al[4];
                 const bool v0 = (mvalid >> (2 * mt)) & 1u, v1 = (mvalid >> (2 * mt + 1)) & 1u;
-                a[0] = v0 ? __float_as_uint(ims[moff[2 * mt] + poff]) : 0u;
-                a[1] = v1 ? __float_as_uint(ims[moff[2 * mt + 1] + poff]) : 0u;
-                a[2] = v0 ? __float_as_uint(ims[moff[2 * mt] + poff + 4]) : 0u;
-                a[3] = v1 ? __float_as_uint(ims[moff[2 * mt + 1] + poff + 4]) : 0u;
+                split_hi_lo(v0 ? ims[moff[2 * mt] + poff] : 0.f, a[0], al[0]);
+                split_hi_lo(v1 ? ims[moff[2 * mt + 1] + poff] : 0.f, a[1], al[1]);
+                split_hi_lo(v0 ? ims[moff[2 * mt] + poff + 4] : 0.f, a[2], al[2]);
+                split_hi_lo(v1 ? ims[moff[2 * mt + 1] + poff + 4] : 0.f, a[3], al[3]);
+                mma_tf32_16x8x8(dwacc[mt], al, bf);
+                mma_tf32_16x8x8(dwacc[mt], a, bl);
                 mma_tf32_16x8x8(dwacc[mt], a, bf);
             }
         }
@@ -933,6 +953,12 @@ int ew_blocks(long long n, int threads) {
     return (int)(b < 1 ? 1 : b);
 }
 
+// Precision knob (accuracy studies): UWR_BOUNDARY_TF32=0 keeps the scalar fp32 kernels for the boundary convolutions in tf32 mode
+bool boundary_tensor_core() {
+    static const bool on = [] { const char* e = getenv("UWR_BOUNDARY_TF32"); return !(e && e[0] == '0'); }();
+    return on && uwr_round_outputs();
+}
+
 int persistent_ctas(int tiles, int per_sm = 2) {
     int p = per_sm * uwr_sm_count();
     if (p > tiles) p = tiles;
@@ -947,7 +973,7 @@ extern "C" int uwr_input_proj_fwd(const float* img, const float* weight, const f
     UWR_REQUIRE(img && weight && bias && tokens, "uwr_input_proj_fwd: null pointer");
     UWR_REQUIRE(Cin >= 1 && Cin <= IP_MAXCIN && (Cout == 32 || Cout == 64), "uwr_input_proj_fwd: Cin<=4, Cout in {32,64}");
     UWR_REQUIRE(B > 0 && B <= 65535, "uwr_input_proj_fwd: bad batch");
-    if (Cin == 3 && uwr_round_outputs()) {   // tensor-core kernel (3xTF32: fp32-level); tf32x3 mode keeps the scalar one
+    if (Cin == 3 && boundary_tensor_core()) {   // tensor-core kernel (3xTF32: fp32-level); tf32x3 mode keeps the scalar one
         const int mx = uwr_cdiv(W, OP_TX), my = uwr_cdiv(H, OP_TY);
         const int P = persistent_ctas(B * mx * my, 2);
         if (Cout == 32) input_proj_fwd_mma_kernel<32><<<P, 256, 0, stream>>>(img, weight, bias, tokens, B, H, W, slope, mx, mx * my);
@@ -974,7 +1000,7 @@ extern "C" int uwr_input_proj_bwd(const float* dtokens, const float* tokens, con
     cudaStream_t stream = (cudaStream_t)stream_;
     UWR_REQUIRE(dtokens && tokens && img && dweight && dbias && workspace, "uwr_input_proj_bwd: null pointer");
     UWR_REQUIRE(Cin >= 1 && Cin <= IP_MAXCIN && (Cout == 32 || Cout == 64), "uwr_input_proj_bwd: Cin<=4, Cout in {32,64}");
-    if (Cin == 3 && uwr_round_outputs()) {
+    if (Cin == 3 && boundary_tensor_core()) {
         const int mx = uwr_cdiv(W, OP_TX), my = uwr_cdiv(H, OP_TY);
         const int P = persistent_ctas(B * mx * my, 3);
         const int msmem = (OP_TY * OP_TX * (Cout + OPM_XS) + 3 * OP_HY * OP_HX) * (int)sizeof(float);
@@ -1041,13 +1067,13 @@ extern "C" int uwr_output_proj_bwd(const float* dout_img, const float* tokens, l
     UWR_REQUIRE(dout_img && tokens && weight && dtokens && dweight && dbias && workspace, "uwr_output_proj_bwd: null pointer");
     UWR_REQUIRE((Cin == 32 || Cin == 64) && ld % 4 == 0, "uwr_output_proj_bwd: Cin in {32,64}, ld %% 4 == 0");
     const int tx = uwr_cdiv(W, OP_TX), ty = uwr_cdiv(H, OP_TY);
-    const int P = persistent_ctas(B * tx * ty, uwr_round_outputs() ? 3 : 2);
+    const int P = persistent_ctas(B * tx * ty, boundary_tensor_core() ? 3 : 2);
     // tile + dY halo; the cross-warp reduction reuses the same buffer (8 * 9 * Cin floats)
     int smem = (OP_HY * OP_HX * Cin + 3 * OP_HY * OP_HX) * (int)sizeof(float);
     const int red = 8 * 9 * Cin * (int)sizeof(float);
     if (red > smem) smem = red;
-    if (uwr_round_outputs()) {   // single-pass TF32 mode: both gradients on the tensor cores
-        const int msmem = ((OP_TY * OP_TX + 32) * (Cin + OPM_XS) + 3 * OP_HY * OP_HX) * (int)sizeof(float);
+    if (boundary_tensor_core()) {   // single-pass TF32 mode: both gradients on the tensor cores
+        const int msmem = ((OP_TY * OP_TX + 64) * (Cin + OPM_XS) + 3 * OP_HY * OP_HX) * (int)sizeof(float);
         if (Cin == 32) {
             static bool configured = false;
             if (!configured) {

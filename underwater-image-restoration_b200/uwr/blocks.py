@@ -169,7 +169,7 @@ def _qkv_forward(y1, wq, bq, wkv, bkv):
     if ops.fast_path():
         w, b = ops.packed_qkv(wq, bq, wkv, bkv)
         # q | k | v leave the epilogue TF32-rounded: the attention kernels' products are then exact in one pass
-        return ops.linear(y1, w, b, t5=True, round_out=True)
+        return ops.linear(y1, w, b, t5=True, round_out=ops.attn_rounded())
     return ops.linear(y1, wq, bq, weight2=wkv, bias2=bkv)
 
 
@@ -230,7 +230,7 @@ class AttnBlockFn(torch.autograd.Function):
         y1, mean, rstd = ops.layernorm_fwd(x2, n1w, n1b)
         qkv = _qkv_forward(y1, wq, bq, wkv, bkv)
         o = ops.window_attn_fwd(qkv, 0, qkv, Cc, 2 * Cc, table, wparam, B, H, W, heads, hd, shift, scale,
-                                rounded=ops.fast_path())
+                                rounded=ops.attn_rounded())
         x1 = ops.linear(o, ops.rounded_weight(wp), bp, residual=x2, rowscale=dp_scale, rows_per_group=L, t5=True)
         ctx.save_for_backward(x2, n1w, mean, rstd, y1, qkv, o, wq, bq, wkv, bkv, table, wparam, wp, dp_scale)
         ctx.n1b, ctx.bp = n1b, bp   # only their gradient slots are needed in backward
@@ -258,7 +258,7 @@ class AttnBlockFn(torch.autograd.Function):
         else:
             d_s, dbp = ops.scale_round_colsum(d, Cc, dp, L, cs_out=g_bp)
         fast = ops.fast_path()
-        d_o = ops.linear_dgrad(d_s, ops.rounded_weight(wp), t5=True, round_out=fast)
+        d_o = ops.linear_dgrad(d_s, ops.rounded_weight(wp), t5=True, round_out=fast and ops.attn_rounded())
         dwp, _ = ops.linear_wgrad(d_s, o, want_bias=False, t5=True, out=g_wp)
         del d_s
         # [to_q; to_kv] weight / bias gradients come out of one GEMM / one vector of column sums: written in place when
@@ -270,7 +270,7 @@ class AttnBlockFn(torch.autograd.Function):
         if bq is not None:
             dbqkv = g_bqkv if g_bqkv is not None else ops._empty((3 * Cc,), qkv)
         dqkv, _, dtable, dw = ops.window_attn_bwd(d_o, qkv, 0, qkv, Cc, 2 * Cc, table, wparam, B, H, W, heads, hd,
-                                                  shift, scale, dtable_out=g_tab, dw_out=g_w, rounded=fast,
+                                                  shift, scale, dtable_out=g_tab, dw_out=g_w, rounded=fast and ops.attn_rounded(),
                                                   colsum_q=dbqkv, colsum_kv=dbqkv)
         del d_o
         dy1 = _qkv_dgrad(dqkv, wq, bq, wkv, bkv)

@@ -51,6 +51,16 @@ def fast_path():
     return _PASSES == 1
 
 
+# Precision knob (debugging / accuracy studies): UWR_ATTN_ROUNDED=0 keeps q | k | v and d_o in full fp32 and runs the attention
+# products with 3xTF32 compensation instead (AST gradient error 2e-4 instead of 3e-4, attention ~0.5 ms per step slower).
+_ATTN_ROUNDED = os.environ.get("UWR_ATTN_ROUNDED", "1") != "0"
+
+
+def attn_rounded():
+    """True when the attention operands are rounded to TF32 where they are produced (default in tf32 mode)."""
+    return _PASSES == 1 and _ATTN_ROUNDED
+
+
 _HALF_STORAGE = True
 
 
