@@ -1,0 +1,54 @@
+// HBM ceiling for a given read:write mix (float4 streams, persistent grid).  The streaming GEMMs write 2-4x what they
+// read; the measured copy peak (1:1) is not their roofline if the write-heavy mixes top out lower.
+//   nvcc -gencode arch=compute_100a,code=sm_100a -O3 -o rw_mix rw_mix.cu && ./rw_mix
+#include <cstdio>
+#include <cuda_runtime.h>
+
+template <int NR, int NW>
+__global__ void __launch_bounds__(512) mix(const float4* __restrict__ in, float4* __restrict__ out, long long n) {
+    // per iteration: NR loads from NR disjoint input streams, NW stores to NW disjoint output streams
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+        float4 a = make_float4(1.f, 2.f, 3.f, 4.f);
+#pragma unroll
+        for (int r = 0; r < NR; ++r) {
+            const float4 v = in[r * n + i];
+            a.x += v.x; a.y += v.y; a.z += v.z; a.w += v.w;
+        }
+#pragma unroll
+        for (int w = 0; w < NW; ++w) out[w * n + i] = a;
+        if (NW == 0 && a.x == 12345.678f) out[0] = a;   // keeps the loads alive
+    }
+}
+
+template <int NR, int NW>
+void run(const float4* in, float4* out, long long total_f4) {
+    const long long n = total_f4 / (NR + NW > 0 ? (NR > NW ? NR : NW) : 1) / 4 * 4 / 2;   // keep every stream in range
+    cudaEvent_t e0, e1;
+    cudaEventCreate(&e0); cudaEventCreate(&e1);
+    for (int rep = 0; rep < 2; ++rep) mix<NR, NW><<<148 * 4, 512>>>(in, out, n);
+    cudaEventRecord(e0);
+    const int reps = 5;
+    for (int rep = 0; rep < reps; ++rep) mix<NR, NW><<<148 * 4, 512>>>(in, out, n);
+    cudaEventRecord(e1);
+    cudaEventSynchronize(e1);
+    float ms; cudaEventElapsedTime(&ms, e0, e1); ms /= reps;
+    const double bytes = 16.0 * n * (NR + NW);
+    printf("read:write %d:%d  %8.3f ms  %7.0f GB/s  (%.2f GB per launch)\n", NR, NW, ms, bytes / ms / 1e6, bytes / 1e9);
+}
+
+int main() {
+    const long long total_f4 = (4LL << 30) / 16;   // 4 GiB each side
+    float4 *in, *out;
+    cudaMalloc(&in, total_f4 * 16); cudaMalloc(&out, total_f4 * 16);
+    cudaMemset(in, 0, total_f4 * 16); cudaMemset(out, 0, total_f4 * 16);
+    run<1, 0>(in, out, total_f4);
+    run<4, 1>(in, out, total_f4);
+    run<2, 1>(in, out, total_f4);
+    run<1, 1>(in, out, total_f4);
+    run<1, 2>(in, out, total_f4);
+    run<1, 4>(in, out, total_f4);
+    run<0, 1>(in, out, total_f4);
+    printf("%s\n", cudaGetErrorString(cudaDeviceSynchronize()));
+    return 0;
+}

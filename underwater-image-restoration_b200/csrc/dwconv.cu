@@ -534,7 +534,10 @@ int dw_halo_map(CUtensorMap* m, const float* base, long long ld, int B, int H, i
 int bwd_ctas(int B, int H, int W, int Ch) {
     const int tiles = B * uwr_cdiv(H, TS) * uwr_cdiv(W, TS);
     const int groups = uwr_cdiv(Ch, CG);
-    int p = uwr_cdiv(2 * uwr_sm_count(), groups);  // 2 CTAs/SM (two 41 KB halo buffers each)
+    // 2 CTAs/SM (two 41 KB halo buffers each), ONE resident wave: rounded DOWN.  Rounded up, 16 channel groups got 19 CTAs
+    // each = 304 CTAs on 296 slots, and the 8 left-over CTAs walked their 54 tiles after everyone else had finished
+    // (Ch = 512 / 1024 / 2048 ran at 2.6 TB/s where Ch = 256, 37 x 8 = 296, reached 3.9)
+    int p = (2 * uwr_sm_count()) / groups;
     if (p > tiles) p = tiles;
     return p < 1 ? 1 : p;
 }

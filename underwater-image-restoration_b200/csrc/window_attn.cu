@@ -967,19 +967,48 @@ int launch_fwd_t5(const AttnParams& p, float* out, long long ld_out, cudaStream_
     return 0;
 }
 
-int bwd_ctas_per_head(const uwr_attn_desc* d) {
-    const int tiles = d->B * (d->H / WIN) * (d->W / WIN);
-    int c = (3 * uwr_sm_count() + d->heads - 1) / d->heads;
-    if (c > tiles) c = tiles;
-    if (c < 1) c = 1;
-    return c;
-}
-
 template <int HD>
 constexpr int fwd_smem() { return (3 * NTOK * (HD + 4) + 228 + NTOK) * 4 + NTOK * 8; }
 template <int HD>
 constexpr int bwd_smem() {
     return (4 * NTOK * (HD + 4) + ((2 * (HD + 4) >= PS_STRIDE) ? 1 : 2) * NTOK * PS_STRIDE + 228 + NTOK) * 4 + NTOK * 8;
+}
+
+// CTAs of the backward kernel that are resident per SM (registers and shared memory of the compiled kernel, asked from
+// the runtime once per head_dim; the smaller of the two operand-mode variants)
+template <int HD>
+int bwd_resident_per_sm() {
+    static int n = 0;
+    if (n == 0) {
+        int a = 0, b = 0;
+        cudaFuncSetAttribute(attn_bwd_kernel<HD, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, bwd_smem<HD>());
+        cudaFuncSetAttribute(attn_bwd_kernel<HD, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, bwd_smem<HD>());
+        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&a, attn_bwd_kernel<HD, true>, ATT_THREADS, bwd_smem<HD>()) != cudaSuccess) a = 1;
+        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&b, attn_bwd_kernel<HD, false>, ATT_THREADS, bwd_smem<HD>()) != cudaSuccess) b = 1;
+        n = a < b ? a : b;
+        if (n < 1) n = 1;
+        (void)cudaGetLastError();
+    }
+    return n;
+}
+
+// The backward grid is (CTAs per head, heads), every CTA strides over its head's windows: ONE resident wave.  The CTA
+// count per head is rounded DOWN -- rounding up (the first version) put 56 x 8 = 448 CTAs on 444 slots for 8 heads, and
+// the four left-over CTAs ran their ~18 windows after everyone else had finished: up to twice the kernel time.
+int bwd_ctas_per_head(const uwr_attn_desc* d) {
+    const int tiles = d->B * (d->H / WIN) * (d->W / WIN);
+    int res = 1;
+    switch (d->head_dim) {
+        case 8: res = bwd_resident_per_sm<8>(); break;
+        case 16: res = bwd_resident_per_sm<16>(); break;
+        case 32: res = bwd_resident_per_sm<32>(); break;
+        case 64: res = bwd_resident_per_sm<64>(); break;
+        case 128: res = bwd_resident_per_sm<128>(); break;
+    }
+    int c = (res * uwr_sm_count()) / d->heads;
+    if (c > tiles) c = tiles;
+    if (c < 1) c = 1;
+    return c;
 }
 
 int fill_params(const uwr_attn_desc* d, AttnParams& p, const char* who) {
