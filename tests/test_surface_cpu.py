@@ -225,3 +225,41 @@ def test_split_plan_fits_one_wave_and_conv_geometry_gate(build_lib):
         cs, co, asz, ao = map(int, subprocess.check_output([exe]).split())
     assert ctypes.sizeof(_lib.ConvGemmDesc) == cs and _lib.ConvGemmDesc.workspace_bytes.offset == co
     assert ctypes.sizeof(_lib.AttnDesc) == asz and _lib.AttnDesc.dkv_colsum.offset == ao
+
+
+def test_persistent_grids_fit_one_resident_wave(build_lib):
+    """The depthwise and attention-backward kernels are persistent: a fixed number of CTAs per channel group / head, each
+    striding over that group's tiles.  The per-group count must be rounded DOWN -- rounded up, 16 channel groups got
+    19 CTAs each (304 on 296 slots) and 8 heads 56 each (448 on 444), and the left-over CTAs ran their whole share after
+    the first wave: up to twice the kernel time at the three deepest AST levels.  Host logic only, read back through the
+    workspace-size entry points."""
+    from uwr import _lib
+    f = _lib.fn
+    sms = f["uwr_device_sm_count"]()
+    for B, H, Ch in [(16, 256, 128), (16, 256, 256), (16, 128, 512), (16, 64, 1024), (16, 32, 2048), (16, 16, 2048),
+                     (8, 256, 96), (8, 256, 176), (8, 128, 352), (1, 256, 256), (1, 16, 2048), (2, 32, 10240)]:
+        groups = -(-Ch // 32)
+        tiles = B * (H // 16) ** 2
+        ctas = f["uwr_dwconv_gelu_bwd_workspace_bytes"](B, H, H, Ch) // (11 * Ch * 4)
+        assert 1 <= ctas <= tiles
+        if groups <= 2 * sms:
+            assert ctas * groups <= 2 * sms, (B, H, Ch, ctas, groups)          # two CTAs per SM: one resident wave
+            if tiles * groups >= 2 * sms:
+                assert (ctas + 1) * groups > 2 * sms, (B, H, Ch, ctas, groups)  # ... and the wave is as full as it can be
+        else:
+            assert ctas == 1
+    for heads, hd, H in [(1, 32, 256), (2, 32, 256), (4, 32, 128), (8, 32, 64), (16, 32, 32), (32, 32, 16), (2, 16, 256),
+                         (4, 8, 256), (3, 64, 64), (5, 128, 32)]:
+        d = _lib.AttnDesc()
+        d.B, d.H, d.W, d.heads, d.head_dim = 16, H, H, heads, hd
+        per_head = f["uwr_window_attn_bwd_workspace_bytes"](ctypes.byref(d)) // (heads * (225 + 3 + 3 * hd) * 4)
+        tiles = 16 * (H // 8) ** 2
+        assert 1 <= per_head <= tiles
+        # CTAs per head = floor(resident slots / heads): without a device the resident count per SM falls back to 1, on
+        # a B200 it is what the runtime reports (3 for head_dim <= 32).  So heads x CTAs-per-head fills k x SMs slots
+        # for a whole k, from below: never one CTA more than the slots, never a whole head's worth less.
+        total = per_head * heads
+        k = -(-total // sms)
+        assert total <= k * sms and (total > k * sms - heads or per_head == tiles), (heads, hd, per_head, k)
+        if not torch.cuda.is_available():
+            assert k == 1
