@@ -96,6 +96,10 @@ int uwr_gemm_tcgen05_supported(const uwr_gemm_desc* d);
  * flop/B, N tile >= 128): 0 = off, 1 = auto (default: every eligible layout; +1 % on the training step),
  * 2 = the weight-gradient (TN) layout only. */
 int uwr_set_gemm_cluster(int mode);
+/* Programmatic dependent launch of the library's kernels (the next grid is launched while the running one drains and
+ * blocks in griddepcontrol.wait until it has completed; results are those of plain stream order): 0 = plain launches (default),
+ * 1 = on (also UWR_PDL=1 in the environment).  Pays for launch-bound steps (SpectralTransformer +2 %), not for AST. */
+int uwr_set_pdl(int on);
 size_t uwr_gemm_tcgen05_workspace_bytes(int M, int N, int K, int a_km);
 int uwr_gemm_tcgen05(const uwr_gemm_desc* d, uwr_stream_t stream);
 

@@ -210,6 +210,45 @@ def test_batched_weight_rerounding_is_bit_identical(monkeypatch):
     assert all(torch.equal(a, b) for a, b in zip(p0, p1))
 
 
+def test_programmatic_dependent_launch_is_bit_identical():
+    """uwr.ops.set_pdl(True): every library kernel is launched with the programmatic-stream-serialization attribute and
+    starts with griddepcontrol.launch_dependents / .wait (csrc/uwr_common.cuh).  That must be plain stream order as far
+    as results go: three eager training steps and three replays of the captured step (the attribute becomes a
+    programmatic edge of the CUDA graph), train mode with DropPath, against the same runs with plain launches."""
+    import uwr
+    from uwr import ops
+    from uwr.train import TrainStep
+    from uwr.graph import GraphedTrainStep
+
+    def run(pdl, graphed):
+        ops.set_pdl(pdl)
+        try:
+            torch.manual_seed(1234)
+            torch.cuda.manual_seed(77)
+            m = uwr.AST(img_size=128).cuda().train()
+            step = TrainStep(m, "L1", lr=1e-3, local_batch=2)
+            g = torch.Generator().manual_seed(3)
+            raw = (torch.rand(2, 3, 128, 128, generator=g) * 2 - 1).cuda()
+            ref = (torch.rand(2, 3, 128, 128, generator=g) * 2 - 1).cuda()
+            if graphed:
+                gs = GraphedTrainStep(step, raw, ref, warmup=1)
+                for _ in range(3):
+                    loss, _ = gs(raw, ref)
+            else:
+                for _ in range(3):
+                    loss, _ = step(raw, ref)
+            torch.cuda.synchronize()
+            return loss.item(), [p.detach().clone() for p in m.parameters()]
+        finally:
+            ops.set_pdl(False)
+
+    for graphed in (False, True):
+        l0, p0 = run(False, graphed)
+        l1, p1 = run(True, graphed)
+        assert l0 == l1, (graphed, l0, l1)
+        assert all(torch.equal(a, b) for a, b in zip(p0, p1)), graphed
+
+
 def test_direct_gradient_writes_match_autograd_accumulation():
     """TrainStep lets the kernels write parameter gradients straight into the bucket slots (ops.grad_slot) and the
     Functions return None; the plain autograd path (gradients returned and accumulated) must give the same bits."""

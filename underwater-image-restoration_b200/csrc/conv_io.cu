@@ -23,6 +23,7 @@ __global__ void __launch_bounds__(256) input_proj_fwd_kernel(const float* __rest
                                                              const float* __restrict__ bias,
                                                              float* __restrict__ tokens, int H, int W, int Cin,
                                                              int Cout, float slope, int tiles_x) {
+    uwr_pdl_enter();
     __shared__ float in_s[IP_MAXCIN][IP_HS][IP_HS];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int b = blockIdx.z;
@@ -79,6 +80,7 @@ __global__ void __launch_bounds__(256) input_proj_bwd_kernel(const float* __rest
                                                              float* __restrict__ partials, int B, int H, int W,
                                                              int Cin, int Cout, float slope, int tiles_x,
                                                              int tiles_per_img) {
+    uwr_pdl_enter();
     __shared__ float in_s[IP_MAXCIN][IP_HS][IP_HS];
     __shared__ float red[8][32];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -150,6 +152,7 @@ __global__ void __launch_bounds__(256) input_proj_bwd_kernel(const float* __rest
 
 __global__ void input_proj_reduce_kernel(const float* __restrict__ partials, float* __restrict__ dweight,
                                          float* __restrict__ dbias, int P, int Cin, int Cout) {
+    uwr_pdl_enter();
     const int nk = Cin * 9 + 1;
     const int idx = blockIdx.x * blockDim.x + threadIdx.x;
     if (idx >= nk * Cout) return;
@@ -171,6 +174,7 @@ __global__ void __launch_bounds__(256) output_proj_fwd_kernel(const float* __res
                                                               const float* __restrict__ bias,
                                                               const float* __restrict__ residual,
                                                               float* __restrict__ out, int H, int W, int tiles_x) {
+    uwr_pdl_enter();
     constexpr int Cin = 32 * CPL;
     extern __shared__ __align__(16) float smem[];  // [OP_HY*OP_HX][Cin]
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -234,6 +238,7 @@ __global__ void __launch_bounds__(256) output_proj_bwd_kernel(const float* __res
                                                               float* __restrict__ dtokens,
                                                               float* __restrict__ partials, int B, int H, int W,
                                                               int tiles_x, int tiles_per_img) {
+    uwr_pdl_enter();
     constexpr int Cin = 32 * CPL;
     extern __shared__ __align__(16) float smem[];
     float* xs = smem;                           // [OP_HY*OP_HX][Cin]
@@ -356,6 +361,7 @@ __global__ void __launch_bounds__(256, 3) output_proj_bwd_mma_kernel(const float
                                                                      float* __restrict__ dtokens,
                                                                      float* __restrict__ partials, int B, int H, int W,
                                                                      int tiles_x, int tiles_per_img) {
+    uwr_pdl_enter();
     constexpr int XS = CIN + OPM_XS;
     constexpr int NT = CIN / 8;          // 8-channel column tiles
     constexpr int KSPLIT = 8 / NT;       // warps sharing a column tile split the tile's pixels (Cin = 32: two halves)
@@ -541,6 +547,7 @@ __global__ void __launch_bounds__(256, 2) input_proj_fwd_mma_kernel(const float*
                                                                     const float* __restrict__ bias,
                                                                     float* __restrict__ tokens, int B, int H, int W,
                                                                     float slope, int tiles_x, int tiles_per_img) {
+    uwr_pdl_enter();
     constexpr int NT = COUT / 8;
     __shared__ float ims[3 * OP_HY * OP_HX];
     // Wm[k][co], rows 27..31 zero, split once: hi = RN to TF32, lo = the exact remainder
@@ -618,6 +625,7 @@ __global__ void __launch_bounds__(256, 3) input_proj_bwd_mma_kernel(const float*
                                                                     const float* __restrict__ img,
                                                                     float* __restrict__ partials, int B, int H, int W,
                                                                     float slope, int tiles_x, int tiles_per_img) {
+    uwr_pdl_enter();
     constexpr int ZS = COUT + OPM_XS;
     constexpr int NT = COUT / 8, KSPLIT = 8 / NT, NPIX = OP_TY * OP_TX;
     constexpr int C4 = COUT / 4;            // float4 groups per token; 256 % C4 == 0: a thread always stages the same group
@@ -723,6 +731,7 @@ __global__ void __launch_bounds__(256, 3) input_proj_bwd_mma_kernel(const float*
 
 __global__ void output_proj_reduce_kernel(const float* __restrict__ partials, float* __restrict__ dweight,
                                           float* __restrict__ dbias, int P, int Cin) {
+    uwr_pdl_enter();
     const int n = 27 * Cin + 3;
     const int idx = blockIdx.x * blockDim.x + threadIdx.x;
     if (idx >= n) return;
@@ -735,6 +744,7 @@ __global__ void output_proj_reduce_kernel(const float* __restrict__ partials, fl
 // ------------------------------------------------------------------------------------------
 __global__ void im2col_4x4s2_kernel(const float* __restrict__ x, long long ld, float* __restrict__ col, int B, int H,
                                     int W, int C, int rnd) {
+    uwr_pdl_enter();
     const int Ho = H / 2, Wo = W / 2, C4 = C / 4;
     const long long total = (long long)B * Ho * Wo * 16 * C4;
     for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total;
@@ -758,6 +768,7 @@ __global__ void im2col_4x4s2_kernel(const float* __restrict__ x, long long ld, f
 
 __global__ void col2im_4x4s2_kernel(const float* __restrict__ dcol, float* __restrict__ dx, int B, int H, int W,
                                     int C) {
+    uwr_pdl_enter();
     const int Ho = H / 2, Wo = W / 2, C4 = C / 4;
     const long long total = (long long)B * H * W * C4;
     for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total;
@@ -791,6 +802,7 @@ __global__ void col2im_4x4s2_kernel(const float* __restrict__ dcol, float* __res
 // dense 3x3 stride-1 pad-1 convolution as a GEMM: col[row][(ky*3+kx)*C + ci] = x[b][y+ky-1][x+kx-1][ci]
 __global__ void im2col_3x3_kernel(const float* __restrict__ x, long long ld, float* __restrict__ col, int B, int H,
                                   int W, int C, int rnd) {
+    uwr_pdl_enter();
     const int C4 = C / 4;
     const long long total = (long long)B * H * W * 9 * C4;
     for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total;
@@ -815,6 +827,7 @@ __global__ void im2col_3x3_kernel(const float* __restrict__ x, long long ld, flo
 // dx[b][y][x][ci] (+)= sum_taps dcol[(b, y-ky+1, x-kx+1)][tap*C + ci]
 __global__ void col2im_3x3_kernel(const float* __restrict__ dcol, float* __restrict__ dx, long long ld_dx, int B, int H,
                                   int W, int C, int accumulate) {
+    uwr_pdl_enter();
     const int C4 = C / 4;
     const long long total = (long long)B * H * W * C4;
     for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total;
@@ -845,6 +858,7 @@ __global__ void col2im_3x3_kernel(const float* __restrict__ dcol, float* __restr
 
 __global__ void pixel_scatter_2x2_kernel(const float* __restrict__ g, const float* __restrict__ bias,
                                          float* __restrict__ out, long long ld_out, int B, int H, int W, int Cout) {
+    uwr_pdl_enter();
     const long long total = (long long)B * H * W * Cout;
     for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total;
          i += (long long)gridDim.x * blockDim.x) {
@@ -866,6 +880,7 @@ __global__ void pixel_scatter_2x2_kernel(const float* __restrict__ g, const floa
 
 __global__ void pixel_gather_2x2_kernel(const float* __restrict__ dout, long long ld_dout, float* __restrict__ dg,
                                         int B, int H, int W, int Cout, int rnd) {
+    uwr_pdl_enter();
     const long long total = (long long)B * H * W * Cout;
     for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total;
          i += (long long)gridDim.x * blockDim.x) {
@@ -888,6 +903,7 @@ __global__ void pixel_gather_2x2_kernel(const float* __restrict__ dout, long lon
 
 __global__ void copy2d_kernel(const float* __restrict__ src, long long ld_src, float* __restrict__ dst,
                               long long ld_dst, long long rows, int cols4, int accumulate) {
+    uwr_pdl_enter();
     const long long total = rows * cols4;
     for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total;
          i += (long long)gridDim.x * blockDim.x) {
@@ -906,6 +922,7 @@ __global__ void copy2d_kernel(const float* __restrict__ src, long long ld_src, f
 // column sums: grid (P, ceil(cols/32)), block (32, 8)
 __global__ void colsum_partial_kernel(const float* __restrict__ x, long long ld, float* __restrict__ partials,
                                       long long rows, int cols) {
+    uwr_pdl_enter();
     __shared__ float sh[8][33];
     const int c = blockIdx.y * 32 + threadIdx.x;
     float s = 0.f;
@@ -933,6 +950,7 @@ __global__ void colsum_partial_kernel(const float* __restrict__ x, long long ld,
 // out[c] = sum_p partials[p][c]: 32 columns x 32 row slices per CTA, fixed order (deterministic)
 __global__ void __launch_bounds__(1024) colsum_final_kernel(const float* __restrict__ partials,
                                                             float* __restrict__ out, int P, int cols) {
+    uwr_pdl_enter();
     __shared__ float sh[32][33];
     const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
     const int c = blockIdx.x * 32 + tx;
@@ -976,15 +994,15 @@ extern "C" int uwr_input_proj_fwd(const float* img, const float* weight, const f
     if (Cin == 3 && boundary_tensor_core()) {   // tensor-core kernel (3xTF32: fp32-level); tf32x3 mode keeps the scalar one
         const int mx = uwr_cdiv(W, OP_TX), my = uwr_cdiv(H, OP_TY);
         const int P = persistent_ctas(B * mx * my, 2);
-        if (Cout == 32) input_proj_fwd_mma_kernel<32><<<P, 256, 0, stream>>>(img, weight, bias, tokens, B, H, W, slope, mx, mx * my);
-        else input_proj_fwd_mma_kernel<64><<<P, 256, 0, stream>>>(img, weight, bias, tokens, B, H, W, slope, mx, mx * my);
+        if (Cout == 32) (void)uwr_launch_pdl(input_proj_fwd_mma_kernel<32>, dim3(P), dim3(256), 0, stream, img, weight, bias, tokens, B, H, W, slope, mx, mx * my);
+        else (void)uwr_launch_pdl(input_proj_fwd_mma_kernel<64>, dim3(P), dim3(256), 0, stream, img, weight, bias, tokens, B, H, W, slope, mx, mx * my);
         UWR_CHECK_LAUNCH("input_proj_fwd_mma_kernel");
         return 0;
     }
     const int tx = uwr_cdiv(W, IP_TS), ty = uwr_cdiv(H, IP_TS);
     dim3 grid(tx * ty, 1, B);
-    if (Cout == 32) input_proj_fwd_kernel<1><<<grid, 256, 0, stream>>>(img, weight, bias, tokens, H, W, Cin, Cout, slope, tx);
-    else input_proj_fwd_kernel<2><<<grid, 256, 0, stream>>>(img, weight, bias, tokens, H, W, Cin, Cout, slope, tx);
+    if (Cout == 32) (void)uwr_launch_pdl(input_proj_fwd_kernel<1>, dim3(grid), dim3(256), 0, stream, img, weight, bias, tokens, H, W, Cin, Cout, slope, tx);
+    else (void)uwr_launch_pdl(input_proj_fwd_kernel<2>, dim3(grid), dim3(256), 0, stream, img, weight, bias, tokens, H, W, Cin, Cout, slope, tx);
     UWR_CHECK_LAUNCH("input_proj_fwd_kernel");
     return 0;
 }
@@ -1005,28 +1023,28 @@ extern "C" int uwr_input_proj_bwd(const float* dtokens, const float* tokens, con
         const int P = persistent_ctas(B * mx * my, 3);
         const int msmem = (OP_TY * OP_TX * (Cout + OPM_XS) + 3 * OP_HY * OP_HX) * (int)sizeof(float);
         if (Cout == 32) {
-            input_proj_bwd_mma_kernel<32><<<P, 256, msmem, stream>>>(dtokens, tokens, img, workspace, B, H, W, slope, mx, mx * my);
+            (void)uwr_launch_pdl(input_proj_bwd_mma_kernel<32>, dim3(P), dim3(256), msmem, stream, dtokens, tokens, img, workspace, B, H, W, slope, mx, mx * my);
         } else {
             static bool configured = false;
             if (!configured) {
                 UWR_CUDA(cudaFuncSetAttribute(input_proj_bwd_mma_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, msmem));
                 configured = true;
             }
-            input_proj_bwd_mma_kernel<64><<<P, 256, msmem, stream>>>(dtokens, tokens, img, workspace, B, H, W, slope, mx, mx * my);
+            (void)uwr_launch_pdl(input_proj_bwd_mma_kernel<64>, dim3(P), dim3(256), msmem, stream, dtokens, tokens, img, workspace, B, H, W, slope, mx, mx * my);
         }
         UWR_CHECK_LAUNCH("input_proj_bwd_mma_kernel");
-        input_proj_reduce_kernel<<<uwr_cdiv(28 * Cout, 128), 128, 0, stream>>>(workspace, dweight, dbias, P, Cin, Cout);
+        (void)uwr_launch_pdl(input_proj_reduce_kernel, dim3(uwr_cdiv(28 * Cout, 128)), dim3(128), 0, stream, workspace, dweight, dbias, P, Cin, Cout);
         UWR_CHECK_LAUNCH("input_proj_reduce_kernel");
         return 0;
     }
     const int tx = uwr_cdiv(W, IP_TS), ty = uwr_cdiv(H, IP_TS);
     const int P = persistent_ctas(B * tx * ty);
     if (Cout == 32)
-        input_proj_bwd_kernel<1><<<P, 256, 0, stream>>>(dtokens, tokens, img, workspace, B, H, W, Cin, Cout, slope, tx, tx * ty);
+        (void)uwr_launch_pdl(input_proj_bwd_kernel<1>, dim3(P), dim3(256), 0, stream, dtokens, tokens, img, workspace, B, H, W, Cin, Cout, slope, tx, tx * ty);
     else
-        input_proj_bwd_kernel<2><<<P, 256, 0, stream>>>(dtokens, tokens, img, workspace, B, H, W, Cin, Cout, slope, tx, tx * ty);
+        (void)uwr_launch_pdl(input_proj_bwd_kernel<2>, dim3(P), dim3(256), 0, stream, dtokens, tokens, img, workspace, B, H, W, Cin, Cout, slope, tx, tx * ty);
     UWR_CHECK_LAUNCH("input_proj_bwd_kernel");
-    input_proj_reduce_kernel<<<uwr_cdiv((Cin * 9 + 1) * Cout, 128), 128, 0, stream>>>(workspace, dweight, dbias, P, Cin, Cout);
+    (void)uwr_launch_pdl(input_proj_reduce_kernel, dim3(uwr_cdiv((Cin * 9 + 1) * Cout, 128)), dim3(128), 0, stream, workspace, dweight, dbias, P, Cin, Cout);
     UWR_CHECK_LAUNCH("input_proj_reduce_kernel");
     return 0;
 }
@@ -1042,14 +1060,14 @@ extern "C" int uwr_output_proj_fwd(const float* tokens, long long ld, const floa
     dim3 grid(tx * ty, 1, B);
     const int smem = OP_HY * OP_HX * Cin * (int)sizeof(float);
     if (Cin == 32) {
-        output_proj_fwd_kernel<1><<<grid, 256, smem, stream>>>(tokens, ld, weight, bias, residual_img, out_img, H, W, tx);
+        (void)uwr_launch_pdl(output_proj_fwd_kernel<1>, dim3(grid), dim3(256), smem, stream, tokens, ld, weight, bias, residual_img, out_img, H, W, tx);
     } else {
         static bool configured = false;
         if (!configured) {
             UWR_CUDA(cudaFuncSetAttribute(output_proj_fwd_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
             configured = true;
         }
-        output_proj_fwd_kernel<2><<<grid, 256, smem, stream>>>(tokens, ld, weight, bias, residual_img, out_img, H, W, tx);
+        (void)uwr_launch_pdl(output_proj_fwd_kernel<2>, dim3(grid), dim3(256), smem, stream, tokens, ld, weight, bias, residual_img, out_img, H, W, tx);
     }
     UWR_CHECK_LAUNCH("output_proj_fwd_kernel");
     return 0;
@@ -1080,14 +1098,14 @@ extern "C" int uwr_output_proj_bwd(const float* dout_img, const float* tokens, l
                 UWR_CUDA(cudaFuncSetAttribute(output_proj_bwd_mma_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, msmem));
                 configured = true;
             }
-            output_proj_bwd_mma_kernel<32><<<P, 256, msmem, stream>>>(dout_img, tokens, ld, weight, dtokens, workspace, B, H, W, tx, tx * ty);
+            (void)uwr_launch_pdl(output_proj_bwd_mma_kernel<32>, dim3(P), dim3(256), msmem, stream, dout_img, tokens, ld, weight, dtokens, workspace, B, H, W, tx, tx * ty);
         } else {
             static bool configured = false;
             if (!configured) {
                 UWR_CUDA(cudaFuncSetAttribute(output_proj_bwd_mma_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, msmem));
                 configured = true;
             }
-            output_proj_bwd_mma_kernel<64><<<P, 256, msmem, stream>>>(dout_img, tokens, ld, weight, dtokens, workspace, B, H, W, tx, tx * ty);
+            (void)uwr_launch_pdl(output_proj_bwd_mma_kernel<64>, dim3(P), dim3(256), msmem, stream, dout_img, tokens, ld, weight, dtokens, workspace, B, H, W, tx, tx * ty);
         }
         UWR_CHECK_LAUNCH("output_proj_bwd_mma_kernel");
     } else if (Cin == 32) {
@@ -1096,17 +1114,17 @@ extern "C" int uwr_output_proj_bwd(const float* dout_img, const float* tokens, l
             UWR_CUDA(cudaFuncSetAttribute(output_proj_bwd_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
             configured = true;
         }
-        output_proj_bwd_kernel<1><<<P, 256, smem, stream>>>(dout_img, tokens, ld, weight, dtokens, workspace, B, H, W, tx, tx * ty);
+        (void)uwr_launch_pdl(output_proj_bwd_kernel<1>, dim3(P), dim3(256), smem, stream, dout_img, tokens, ld, weight, dtokens, workspace, B, H, W, tx, tx * ty);
     } else {
         static bool configured = false;
         if (!configured) {
             UWR_CUDA(cudaFuncSetAttribute(output_proj_bwd_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
             configured = true;
         }
-        output_proj_bwd_kernel<2><<<P, 256, smem, stream>>>(dout_img, tokens, ld, weight, dtokens, workspace, B, H, W, tx, tx * ty);
+        (void)uwr_launch_pdl(output_proj_bwd_kernel<2>, dim3(P), dim3(256), smem, stream, dout_img, tokens, ld, weight, dtokens, workspace, B, H, W, tx, tx * ty);
     }
     UWR_CHECK_LAUNCH("output_proj_bwd_kernel");
-    output_proj_reduce_kernel<<<uwr_cdiv(27 * Cin + 3, 128), 128, 0, stream>>>(workspace, dweight, dbias, P, Cin);
+    (void)uwr_launch_pdl(output_proj_reduce_kernel, dim3(uwr_cdiv(27 * Cin + 3, 128)), dim3(128), 0, stream, workspace, dweight, dbias, P, Cin);
     UWR_CHECK_LAUNCH("output_proj_reduce_kernel");
     return 0;
 }
@@ -1116,7 +1134,7 @@ extern "C" int uwr_im2col_4x4s2(const float* tokens, long long ld, float* col, i
     cudaStream_t stream = (cudaStream_t)stream_;
     UWR_REQUIRE(tokens && col && C % 4 == 0 && ld % 4 == 0 && H % 2 == 0 && W % 2 == 0, "uwr_im2col_4x4s2: bad args");
     const long long total = (long long)B * (H / 2) * (W / 2) * 16 * (C / 4);
-    im2col_4x4s2_kernel<<<ew_blocks(total, 256), 256, 0, stream>>>(tokens, ld, col, B, H, W, C, uwr_round_outputs());
+    (void)uwr_launch_pdl(im2col_4x4s2_kernel, dim3(ew_blocks(total, 256)), dim3(256), 0, stream, tokens, ld, col, B, H, W, C, uwr_round_outputs());
     UWR_CHECK_LAUNCH("im2col_4x4s2_kernel");
     return 0;
 }
@@ -1125,7 +1143,7 @@ extern "C" int uwr_col2im_4x4s2(const float* dcol, float* dtokens, int B, int H,
     cudaStream_t stream = (cudaStream_t)stream_;
     UWR_REQUIRE(dcol && dtokens && C % 4 == 0 && H % 2 == 0 && W % 2 == 0, "uwr_col2im_4x4s2: bad args");
     const long long total = (long long)B * H * W * (C / 4);
-    col2im_4x4s2_kernel<<<ew_blocks(total, 256), 256, 0, stream>>>(dcol, dtokens, B, H, W, C);
+    (void)uwr_launch_pdl(col2im_4x4s2_kernel, dim3(ew_blocks(total, 256)), dim3(256), 0, stream, dcol, dtokens, B, H, W, C);
     UWR_CHECK_LAUNCH("col2im_4x4s2_kernel");
     return 0;
 }
@@ -1135,7 +1153,7 @@ extern "C" int uwr_im2col_3x3(const float* tokens, long long ld, float* col, int
     cudaStream_t stream = (cudaStream_t)stream_;
     UWR_REQUIRE(tokens && col && C % 4 == 0 && ld % 4 == 0, "uwr_im2col_3x3: bad args");
     const long long total = (long long)B * H * W * 9 * (C / 4);
-    im2col_3x3_kernel<<<ew_blocks(total, 256), 256, 0, stream>>>(tokens, ld, col, B, H, W, C, uwr_round_outputs());
+    (void)uwr_launch_pdl(im2col_3x3_kernel, dim3(ew_blocks(total, 256)), dim3(256), 0, stream, tokens, ld, col, B, H, W, C, uwr_round_outputs());
     UWR_CHECK_LAUNCH("im2col_3x3_kernel");
     return 0;
 }
@@ -1145,7 +1163,7 @@ extern "C" int uwr_col2im_3x3(const float* dcol, float* dtokens, long long ld, i
     cudaStream_t stream = (cudaStream_t)stream_;
     UWR_REQUIRE(dcol && dtokens && C % 4 == 0 && ld % 4 == 0, "uwr_col2im_3x3: bad args");
     const long long total = (long long)B * H * W * (C / 4);
-    col2im_3x3_kernel<<<ew_blocks(total, 256), 256, 0, stream>>>(dcol, dtokens, ld, B, H, W, C, accumulate);
+    (void)uwr_launch_pdl(col2im_3x3_kernel, dim3(ew_blocks(total, 256)), dim3(256), 0, stream, dcol, dtokens, ld, B, H, W, C, accumulate);
     UWR_CHECK_LAUNCH("col2im_3x3_kernel");
     return 0;
 }
@@ -1155,7 +1173,7 @@ extern "C" int uwr_pixel_scatter_2x2(const float* g, const float* bias, float* o
     cudaStream_t stream = (cudaStream_t)stream_;
     UWR_REQUIRE(g && out, "uwr_pixel_scatter_2x2: null pointer");
     const long long total = (long long)B * H * W * Cout;
-    pixel_scatter_2x2_kernel<<<ew_blocks(total, 256), 256, 0, stream>>>(g, bias, out, ld_out, B, H, W, Cout);
+    (void)uwr_launch_pdl(pixel_scatter_2x2_kernel, dim3(ew_blocks(total, 256)), dim3(256), 0, stream, g, bias, out, ld_out, B, H, W, Cout);
     UWR_CHECK_LAUNCH("pixel_scatter_2x2_kernel");
     return 0;
 }
@@ -1165,7 +1183,7 @@ extern "C" int uwr_pixel_gather_2x2(const float* dout, long long ld_dout, float*
     cudaStream_t stream = (cudaStream_t)stream_;
     UWR_REQUIRE(dout && dg, "uwr_pixel_gather_2x2: null pointer");
     const long long total = (long long)B * H * W * Cout;
-    pixel_gather_2x2_kernel<<<ew_blocks(total, 256), 256, 0, stream>>>(dout, ld_dout, dg, B, H, W, Cout,
+    (void)uwr_launch_pdl(pixel_gather_2x2_kernel, dim3(ew_blocks(total, 256)), dim3(256), 0, stream, dout, ld_dout, dg, B, H, W, Cout,
                                                                        uwr_round_outputs());
     UWR_CHECK_LAUNCH("pixel_gather_2x2_kernel");
     return 0;
@@ -1178,7 +1196,7 @@ extern "C" int uwr_pixel_shuffle2(const float* in, float* out, long long ld_out,
     cudaStream_t stream = (cudaStream_t)stream_;
     UWR_REQUIRE(in && out && ((uintptr_t)in & 15) == 0, "uwr_pixel_shuffle2: null / unaligned pointer");
     const long long total = (long long)B * H * W * Cout;
-    pixel_scatter_2x2_kernel<<<ew_blocks(total, 256), 256, 0, stream>>>(in, nullptr, out, ld_out, B, H, W, Cout);
+    (void)uwr_launch_pdl(pixel_scatter_2x2_kernel, dim3(ew_blocks(total, 256)), dim3(256), 0, stream, in, nullptr, out, ld_out, B, H, W, Cout);
     UWR_CHECK_LAUNCH("pixel_scatter_2x2_kernel");
     return 0;
 }
@@ -1188,7 +1206,7 @@ extern "C" int uwr_pixel_unshuffle2(const float* in, long long ld_in, float* out
     cudaStream_t stream = (cudaStream_t)stream_;
     UWR_REQUIRE(in && out && ((uintptr_t)out & 15) == 0, "uwr_pixel_unshuffle2: null / unaligned pointer");
     const long long total = (long long)B * H * W * Cout;
-    pixel_gather_2x2_kernel<<<ew_blocks(total, 256), 256, 0, stream>>>(in, ld_in, out, B, H, W, Cout, 0);
+    (void)uwr_launch_pdl(pixel_gather_2x2_kernel, dim3(ew_blocks(total, 256)), dim3(256), 0, stream, in, ld_in, out, B, H, W, Cout, 0);
     UWR_CHECK_LAUNCH("pixel_gather_2x2_kernel");
     return 0;
 }
@@ -1198,7 +1216,7 @@ extern "C" int uwr_copy2d(const float* src, long long ld_src, float* dst, long l
     cudaStream_t stream = (cudaStream_t)stream_;
     UWR_REQUIRE(src && dst && cols % 4 == 0 && ld_src % 4 == 0 && ld_dst % 4 == 0, "uwr_copy2d: cols/ld must be multiples of 4");
     if (rows == 0 || cols == 0) return 0;
-    copy2d_kernel<<<ew_blocks(rows * (cols / 4), 256), 256, 0, stream>>>(src, ld_src, dst, ld_dst, rows, cols / 4, accumulate);
+    (void)uwr_launch_pdl(copy2d_kernel, dim3(ew_blocks(rows * (cols / 4), 256)), dim3(256), 0, stream, src, ld_src, dst, ld_dst, rows, cols / 4, accumulate);
     UWR_CHECK_LAUNCH("copy2d_kernel");
     return 0;
 }
@@ -1213,9 +1231,9 @@ extern "C" int uwr_colsum(const float* x, long long ld, float* out, float* works
     if (cap > 1024) cap = 1024;
     if (P > cap) P = cap;
     if (P < 1) P = 1;
-    colsum_partial_kernel<<<dim3((unsigned)P, cgroups), dim3(32, 8), 0, stream>>>(x, ld, workspace, rows, cols);
+    (void)uwr_launch_pdl(colsum_partial_kernel, dim3(dim3((unsigned)P, cgroups)), dim3(dim3(32, 8)), 0, stream, x, ld, workspace, rows, cols);
     UWR_CHECK_LAUNCH("colsum_partial_kernel");
-    colsum_final_kernel<<<uwr_cdiv(cols, 32), 1024, 0, stream>>>(workspace, out, (int)P, cols);
+    (void)uwr_launch_pdl(colsum_final_kernel, dim3(uwr_cdiv(cols, 32)), dim3(1024), 0, stream, workspace, out, (int)P, cols);
     UWR_CHECK_LAUNCH("colsum_final_kernel");
     return 0;
 }

@@ -22,6 +22,7 @@ __global__ void __launch_bounds__(CS_THREADS)
 conv_small_fwd_kernel(const float* __restrict__ in, long long ld_in, const float* __restrict__ w,
                       const float* __restrict__ bias, const float* __restrict__ resid, float* __restrict__ out,
                       long long ld_out, int B, int H, int W, int rnd) {
+    uwr_pdl_enter();
     __shared__ float ws[COUT * CIN * 9 + COUT];
     for (int i = threadIdx.x; i < COUT * CIN * 9; i += CS_THREADS) ws[i] = w[i];
     for (int i = threadIdx.x; i < COUT; i += CS_THREADS) ws[COUT * CIN * 9 + i] = bias ? bias[i] : 0.f;
@@ -76,6 +77,7 @@ template <int CIN, int COUT, bool IN_TOK, bool DOUT_TOK>
 __global__ void __launch_bounds__(CS_THREADS)
 conv_small_wgrad_kernel(const float* __restrict__ in, long long ld_in, const float* __restrict__ dout, long long ld_dout,
                         float* __restrict__ partials, int B, int H, int W) {
+    uwr_pdl_enter();
     constexpr int HT = CS_TILE + 2;
     constexpr int NOUT = COUT * CIN * 9 + COUT;
     constexpr int PER = (NOUT + CS_THREADS - 1) / CS_THREADS;
@@ -135,6 +137,7 @@ conv_small_wgrad_kernel(const float* __restrict__ in, long long ld_in, const flo
 
 __global__ void conv_small_reduce_kernel(const float* __restrict__ partials, int nparts, int nw, int nb,
                                          float* __restrict__ dweight, float* __restrict__ dbias) {
+    uwr_pdl_enter();
     const int o = blockIdx.x * blockDim.x + threadIdx.x;
     if (o >= nw + nb) return;
     float s = 0.f;
@@ -155,7 +158,7 @@ int launch_fwd(const uwr_conv_small_desc* d, cudaStream_t stream) {
     long long grid = (total + CS_THREADS - 1) / CS_THREADS;
     const long long cap = 16LL * uwr_sm_count();
     if (grid > cap) grid = cap;
-    conv_small_fwd_kernel<CIN, COUT, IN_TOK, OUT_TOK><<<(int)grid, CS_THREADS, 0, stream>>>(
+    (void)uwr_launch_pdl(conv_small_fwd_kernel<CIN, COUT, IN_TOK, OUT_TOK>, dim3((int)grid), dim3(CS_THREADS), 0, stream, 
         d->in, d->ld_in, d->weight, d->bias, d->residual_img, d->out, d->ld_out, d->B, d->H, d->W,
         (OUT_TOK && d->round_out) ? uwr_round_outputs() : 0);
     UWR_CHECK_LAUNCH("conv_small_fwd_kernel");
@@ -166,11 +169,11 @@ template <int CIN, int COUT, bool IN_TOK, bool DOUT_TOK>
 int launch_wgrad(const uwr_conv_small_desc* d, const float* dout, long long ld_dout, float* dweight, float* dbias,
                  float* ws, cudaStream_t stream) {
     const int ctas = wgrad_ctas(d->B, d->H, d->W);
-    conv_small_wgrad_kernel<CIN, COUT, IN_TOK, DOUT_TOK><<<ctas, CS_THREADS, 0, stream>>>(d->in, d->ld_in, dout, ld_dout, ws,
+    (void)uwr_launch_pdl(conv_small_wgrad_kernel<CIN, COUT, IN_TOK, DOUT_TOK>, dim3(ctas), dim3(CS_THREADS), 0, stream, d->in, d->ld_in, dout, ld_dout, ws,
                                                                                          d->B, d->H, d->W);
     UWR_CHECK_LAUNCH("conv_small_wgrad_kernel");
     const int nw = COUT * CIN * 9;
-    conv_small_reduce_kernel<<<uwr_cdiv(nw + COUT, 128), 128, 0, stream>>>(ws, ctas, nw, COUT, dweight, dbias);
+    (void)uwr_launch_pdl(conv_small_reduce_kernel, dim3(uwr_cdiv(nw + COUT, 128)), dim3(128), 0, stream, ws, ctas, nw, COUT, dweight, dbias);
     UWR_CHECK_LAUNCH("conv_small_reduce_kernel");
     return 0;
 }

@@ -55,6 +55,7 @@ dwconv_fwd_kernel(const __grid_constant__ CUtensorMap map_u, const float* __rest
                   const float* __restrict__ weight, const float* __restrict__ bias, float* __restrict__ v,
                   float* __restrict__ h2, int B, int H, int W, int Ch, int tiles_x, int tiles_per_img, int rnd,
                   int v_is_dgelu) {
+    uwr_pdl_enter();
     extern __shared__ __align__(128) unsigned char dw_raw[];
     // 128-byte alignment for the TMA destination, computed on the shared-window offset so that the
     // compiler keeps LDS/STS (a generic uintptr_t round-up turned every access into LD.E/ST.E)
@@ -176,6 +177,7 @@ __global__ void __launch_bounds__(DW_THREADS, 2)
 dwconv_fwd_half_kernel(const __grid_constant__ CUtensorMap map_u, const float* __restrict__ weight,
                        const float* __restrict__ bias, __half* __restrict__ v, float* __restrict__ h2, int B, int H, int W,
                        int Ch, int tiles_x, int tiles_per_img) {
+    uwr_pdl_enter();
     extern __shared__ __align__(128) unsigned char dw_raw[];
     unsigned char* base = dw_raw + ((128u - (uwr_tma::smem_u32(dw_raw) & 127u)) & 127u);
     float* work = reinterpret_cast<float*>(base);                                  // gelu(u) tile, fp32
@@ -278,6 +280,7 @@ __global__ void __launch_bounds__(256) gelu_gate_bwd_kernel(const float* __restr
                                                             const float* __restrict__ v, float* __restrict__ dv,
                                                             float* __restrict__ du, long long rows, int Ch, int mode,
                                                             int rnd) {
+    uwr_pdl_enter();
     const int c4n = Ch >> 2;  // Ch is a multiple of 4: 128-bit accesses
     const long long total = rows * c4n;
     for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total;
@@ -313,6 +316,7 @@ __global__ void __launch_bounds__(256) gelu_gate_bwd_kernel(const float* __restr
 // GDFN gate (SpectralTransformer.py:126-129): out = gelu(t[:, :h]) * t[:, h:2h] on token slabs (row stride ld)
 __global__ void __launch_bounds__(256) gelu_mul_fwd_kernel(const float* __restrict__ t, long long ld,
                                                            float* __restrict__ out, long long rows, int h4, int rnd) {
+    uwr_pdl_enter();
     const long long total = rows * h4;
     for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total;
          i += (long long)gridDim.x * blockDim.x) {
@@ -328,6 +332,7 @@ __global__ void __launch_bounds__(256) gelu_mul_fwd_kernel(const float* __restri
 __global__ void __launch_bounds__(256) gelu_mul_bwd_kernel(const float* __restrict__ dout, const float* __restrict__ t,
                                                            long long ld, float* __restrict__ dt, long long rows,
                                                            int h4) {
+    uwr_pdl_enter();
     const long long total = rows * h4;
     for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total;
          i += (long long)gridDim.x * blockDim.x) {
@@ -381,6 +386,7 @@ __global__ void __launch_bounds__(DW_THREADS, 2)
 dwconv_bwd_kernel(const __grid_constant__ CUtensorMap map_dv, const float* __restrict__ u, long long ld_u,
                   const float* __restrict__ weight, float* __restrict__ du, float* __restrict__ partials, int B, int H,
                   int W, int Ch, int tiles_x, int tiles_per_img, int rnd) {
+    uwr_pdl_enter();
     extern __shared__ __align__(128) unsigned char dw_raw[];
     float* smem = reinterpret_cast<float*>(dw_raw + ((128u - (uwr_tma::smem_u32(dw_raw) & 127u)) & 127u));
     uint64_t* bars = reinterpret_cast<uint64_t*>(smem + 2 * (TILE_BYTES / 4));
@@ -510,6 +516,7 @@ dwconv_bwd_kernel(const __grid_constant__ CUtensorMap map_dv, const float* __res
 
 __global__ void dwconv_param_reduce_kernel(const float* __restrict__ partials, float* __restrict__ dweight,
                                            float* __restrict__ dbias, float* __restrict__ du_colsum, int P, int Ch) {
+    uwr_pdl_enter();
     const int idx = blockIdx.x * blockDim.x + threadIdx.x;
     if (idx >= 11 * Ch) return;
     const int k = idx / Ch, c = idx % Ch;
@@ -566,7 +573,7 @@ extern "C" int uwr_dwconv_gelu_fwd(const float* u, long long ld_u, const float* 
                                           DW_SMEM_BYTES));                                                        \
             configured = true;                                                                                    \
         }                                                                                                         \
-        dwconv_fwd_kernel<M, F><<<grid, DW_THREADS, DW_SMEM_BYTES, stream>>>(                                     \
+        (void)uwr_launch_pdl(dwconv_fwd_kernel<M, F>, dim3(grid), dim3(DW_THREADS), DW_SMEM_BYTES, stream,                                      \
             map_u, u, ld_u, weight, bias, v, h2, B, H, W, Ch, tx, tx * ty, uwr_round_outputs(), v_is_dgelu);      \
     } while (0)
     if (mode == 0) {
@@ -611,7 +618,7 @@ extern "C" int uwr_dwconv_gelu_fwd_half(const void* u_half, const float* weight,
         configured = true;
     }
     dim3 grid(bwd_ctas(B, H, W, Ch), Ch / CG);
-    dwconv_fwd_half_kernel<<<grid, DW_THREADS, SMEM, stream>>>(map_u, weight, bias, (__half*)dgelu_half, h2, B, H, W, Ch, tx,
+    (void)uwr_launch_pdl(dwconv_fwd_half_kernel, dim3(grid), dim3(DW_THREADS), SMEM, stream, map_u, weight, bias, (__half*)dgelu_half, h2, B, H, W, Ch, tx,
                                                               tx * ty);
     UWR_CHECK_LAUNCH("dwconv_fwd_half_kernel");
     return 0;
@@ -625,7 +632,7 @@ extern "C" int uwr_gelu_gate_bwd(const float* dh2, const float* u, long long ld_
     const long long total = rows * (Ch / 4);
     long long blocks = (total + 255) / 256;
     if (blocks > 16LL * uwr_sm_count()) blocks = 16LL * uwr_sm_count();
-    gelu_gate_bwd_kernel<<<(unsigned)blocks, 256, 0, stream>>>(dh2, u, ld_u, v, dv, du, rows, Ch, mode, uwr_round_outputs());
+    (void)uwr_launch_pdl(gelu_gate_bwd_kernel, dim3((unsigned)blocks), dim3(256), 0, stream, dh2, u, ld_u, v, dv, du, rows, Ch, mode, uwr_round_outputs());
     UWR_CHECK_LAUNCH("gelu_gate_bwd_kernel");
     return 0;
 }
@@ -636,7 +643,7 @@ extern "C" int uwr_gelu_mul_fwd(const float* t, long long ld, float* out, long l
     if (rows == 0) return 0;
     long long blocks = (rows * (h / 4) + 255) / 256;
     if (blocks > 16LL * uwr_sm_count()) blocks = 16LL * uwr_sm_count();
-    gelu_mul_fwd_kernel<<<(unsigned)blocks, 256, 0, stream>>>(t, ld, out, rows, h / 4, uwr_round_outputs());
+    (void)uwr_launch_pdl(gelu_mul_fwd_kernel, dim3((unsigned)blocks), dim3(256), 0, stream, t, ld, out, rows, h / 4, uwr_round_outputs());
     UWR_CHECK_LAUNCH("gelu_mul_fwd_kernel");
     return 0;
 }
@@ -648,7 +655,7 @@ extern "C" int uwr_gelu_mul_bwd(const float* dout, const float* t, long long ld,
     if (rows == 0) return 0;
     long long blocks = (rows * (h / 4) + 255) / 256;
     if (blocks > 16LL * uwr_sm_count()) blocks = 16LL * uwr_sm_count();
-    gelu_mul_bwd_kernel<<<(unsigned)blocks, 256, 0, stream>>>(dout, t, ld, dt, rows, h / 4);
+    (void)uwr_launch_pdl(gelu_mul_bwd_kernel, dim3((unsigned)blocks), dim3(256), 0, stream, dout, t, ld, dt, rows, h / 4);
     UWR_CHECK_LAUNCH("gelu_mul_bwd_kernel");
     return 0;
 }
@@ -697,7 +704,7 @@ static int dwconv_bwd_impl(const float* dv, const float* u, long long ld_u, cons
             UWR_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, DW_SMEM_BYTES));     \
             configured = true;                                                                                    \
         }                                                                                                         \
-        kern<<<grid, DW_THREADS, DW_SMEM_BYTES, stream>>>(map_dv, u, ld_u, weight, du, workspace, B, H, W, Ch, tx,  \
+        (void)uwr_launch_pdl(kern, dim3(grid), dim3(DW_THREADS), DW_SMEM_BYTES, stream, map_dv, u, ld_u, weight, du, workspace, B, H, W, Ch, tx,  \
                                                           tx * ty, uwr_round_outputs());                          \
     } while (0)
     if (u_half) {
@@ -711,7 +718,7 @@ static int dwconv_bwd_impl(const float* dv, const float* u, long long ld_u, cons
     }
 #undef DW_BWD
     UWR_CHECK_LAUNCH("dwconv_bwd_kernel");
-    dwconv_param_reduce_kernel<<<uwr_cdiv(11 * Ch, 128), 128, 0, stream>>>(workspace, dweight, dbias, du_colsum, P, Ch);
+    (void)uwr_launch_pdl(dwconv_param_reduce_kernel, dim3(uwr_cdiv(11 * Ch, 128)), dim3(128), 0, stream, workspace, dweight, dbias, du_colsum, P, Ch);
     UWR_CHECK_LAUNCH("dwconv_param_reduce_kernel");
     return 0;
 }

@@ -53,6 +53,7 @@ __global__ void __launch_bounds__(FFL_WARPS * 32) ffl_rows_fwd_kernel(const floa
                                                                      float2* __restrict__ W1,
                                                                      unsigned* __restrict__ plane_max, int S,
                                                                      int log2S, float scale) {
+    uwr_pdl_enter();
     extern __shared__ __align__(16) float2 sm2[];
     float2* tw = sm2;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -78,6 +79,7 @@ __global__ void __launch_bounds__(FFL_WARPS * 32) ffl_cols_kernel(const float2* 
                                                                  unsigned* __restrict__ plane_max,
                                                                  float* __restrict__ partials, int S, int log2S,
                                                                  float scale) {
+    uwr_pdl_enter();
     extern __shared__ __align__(16) float2 sm2[];
     __shared__ float red[FFL_WARPS];
     float2* tw = sm2;
@@ -129,6 +131,7 @@ __global__ void __launch_bounds__(FFL_WARPS * 32) ffl_cols_kernel(const float2* 
 __global__ void __launch_bounds__(FFL_WARPS * 32) ffl_rows_inv_kernel(const float2* __restrict__ W1,
                                                                      float* __restrict__ grad, int S, int log2S,
                                                                      float scale) {
+    uwr_pdl_enter();
     extern __shared__ __align__(16) float2 sm2[];
     float2* tw = sm2;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -145,6 +148,7 @@ __global__ void __launch_bounds__(FFL_WARPS * 32) ffl_rows_inv_kernel(const floa
 }
 
 __global__ void ffl_final_kernel(const float* __restrict__ partials, int n, float inv_count, float* __restrict__ out) {
+    uwr_pdl_enter();
     __shared__ double sh[32];
     double a = 0.0;
     for (int i = threadIdx.x; i < n; i += 32) a += partials[i];
@@ -193,17 +197,17 @@ extern "C" int uwr_ffl_loss(const float* pred, const float* truth, float* out, f
         configured = true;
     }
     const dim3 rgrid(planes, uwr_cdiv(S, FFL_WARPS)), cgrid(planes, S / COLS_PER_CTA);
-    ffl_rows_fwd_kernel<<<rgrid, FFL_WARPS * 32, row_smem, stream>>>(pred, truth, W1, pmax, S, log2S, sc);
+    (void)uwr_launch_pdl(ffl_rows_fwd_kernel, dim3(rgrid), dim3(FFL_WARPS * 32), row_smem, stream, pred, truth, W1, pmax, S, log2S, sc);
     UWR_CHECK_LAUNCH("ffl_rows_fwd_kernel");
-    ffl_cols_kernel<0><<<cgrid, FFL_WARPS * 32, col_smem, stream>>>(W1, W2, pmax, partials, S, log2S, sc);
+    (void)uwr_launch_pdl(ffl_cols_kernel<0>, dim3(cgrid), dim3(FFL_WARPS * 32), col_smem, stream, W1, W2, pmax, partials, S, log2S, sc);
     UWR_CHECK_LAUNCH("ffl_cols_kernel<0>");
-    ffl_cols_kernel<1><<<cgrid, FFL_WARPS * 32, col_smem, stream>>>(W2, W1, pmax, partials, S, log2S, sc);
+    (void)uwr_launch_pdl(ffl_cols_kernel<1>, dim3(cgrid), dim3(FFL_WARPS * 32), col_smem, stream, W2, W1, pmax, partials, S, log2S, sc);
     UWR_CHECK_LAUNCH("ffl_cols_kernel<1>");
     const double count = (double)planes * S * S;
-    ffl_final_kernel<<<1, 32, 0, stream>>>(partials, planes * (S / COLS_PER_CTA), (float)(1.0 / count), out);
+    (void)uwr_launch_pdl(ffl_final_kernel, dim3(1), dim3(32), 0, stream, partials, planes * (S / COLS_PER_CTA), (float)(1.0 / count), out);
     UWR_CHECK_LAUNCH("ffl_final_kernel");
     if (grad) {
-        ffl_rows_inv_kernel<<<rgrid, FFL_WARPS * 32, row_smem, stream>>>(W1, grad, S, log2S, sc * (float)(2.0 / count));
+        (void)uwr_launch_pdl(ffl_rows_inv_kernel, dim3(rgrid), dim3(FFL_WARPS * 32), row_smem, stream, W1, grad, S, log2S, sc * (float)(2.0 / count));
         UWR_CHECK_LAUNCH("ffl_rows_inv_kernel");
     }
     return 0;

@@ -67,6 +67,7 @@ struct PassParams {
 
 // grid = (channel groups, NO, B)
 __global__ void __launch_bounds__(FFT_WARPS * 32) fft_pass_kernel(const PassParams p) {
+    uwr_pdl_enter();
     extern __shared__ __align__(16) float2 fsm[];
     float2* tw = fsm;           // N twiddles (the radix-2 path uses the first N/2)
     float2* tile = fsm + p.N;   // [FFT_CT][N + 1] (+ a second tile for the direct-DFT path)
@@ -141,6 +142,7 @@ __global__ void __launch_bounds__(FFT_WARPS * 32) fft_pass_kernel(const PassPara
 __global__ void __launch_bounds__(FFT_WARPS * 32) fft_rows_kernel(const float* __restrict__ in, float* __restrict__ out,
                                                                  int in_complex, int out_real, int inverse,
                                                                  long long rows, int N, int log2N, float scale) {
+    uwr_pdl_enter();
     extern __shared__ __align__(16) float2 fsm[];
     float2* tw = fsm;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -236,6 +238,7 @@ __host__ __device__ constexpr int brev_r(int k) {
 
 template <int R1, int R2, bool INV>
 __global__ void __launch_bounds__(FFT_WARPS * 32) fft_pass2_kernel(const PassParams p) {
+    uwr_pdl_enter();
     constexpr int N = R1 * R2;
     extern __shared__ __align__(16) float2 fsm[];
     float2* buf = fsm;                // [N][32]
@@ -307,8 +310,8 @@ int launch_pass2(const PassParams& p, int B, cudaStream_t stream) {
         configured = true;
     }
     const dim3 grid(uwr_cdiv(p.C, FFT_CT), p.NO, B);
-    if (p.inverse) fft_pass2_kernel<R1, R2, true><<<grid, FFT_WARPS * 32, smem, stream>>>(p);
-    else fft_pass2_kernel<R1, R2, false><<<grid, FFT_WARPS * 32, smem, stream>>>(p);
+    if (p.inverse) (void)uwr_launch_pdl(fft_pass2_kernel<R1, R2, true>, dim3(grid), dim3(FFT_WARPS * 32), smem, stream, p);
+    else (void)uwr_launch_pdl(fft_pass2_kernel<R1, R2, false>, dim3(grid), dim3(FFT_WARPS * 32), smem, stream, p);
     UWR_CHECK_LAUNCH("fft_pass2_kernel");
     return 0;
 }
@@ -340,7 +343,7 @@ int launch_pass(PassParams& p, int B, cudaStream_t stream) {
         UWR_CUDA(cudaFuncSetAttribute(fft_pass_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
         configured = smem;
     }
-    fft_pass_kernel<<<dim3(uwr_cdiv(p.C, FFT_CT), p.NO, B), FFT_WARPS * 32, smem, stream>>>(p);
+    (void)uwr_launch_pdl(fft_pass_kernel, dim3(dim3(uwr_cdiv(p.C, FFT_CT), p.NO, B)), dim3(FFT_WARPS * 32), smem, stream, p);
     UWR_CHECK_LAUNCH("fft_pass_kernel");
     return 0;
 }
@@ -356,7 +359,7 @@ int launch_rows(const float* in, float* out, int in_complex, int out_real, int i
     }
     long long blocks = (rows + FFT_WARPS - 1) / FFT_WARPS;
     if (blocks > 16LL * uwr_sm_count()) blocks = 16LL * uwr_sm_count();
-    fft_rows_kernel<<<(unsigned)blocks, FFT_WARPS * 32, smem, stream>>>(in, out, in_complex, out_real, inverse, rows, N,
+    (void)uwr_launch_pdl(fft_rows_kernel, dim3((unsigned)blocks), dim3(FFT_WARPS * 32), smem, stream, in, out, in_complex, out_real, inverse, rows, N,
                                                                        ilog2i(N), scale);
     UWR_CHECK_LAUNCH("fft_rows_kernel");
     return 0;

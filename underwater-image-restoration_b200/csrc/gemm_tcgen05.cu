@@ -118,6 +118,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_const
     float* sbias = reinterpret_cast<float*>(smem + STAGES * STAGE_BYTES + 256);  // [BN]
     float* sstage = sbias + BN;  // [EPI_WARPS][32][EP_STRIDE] accumulator transposition buffers
 
+    uwr_pdl_trigger();   // PDL: the next grid may be launched; the set-up below overlaps the predecessor's tail
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     // work items are enumerated per CLUSTER: (row-tile group, column tile, split); CTA `crank` takes row tile CL*g + crank
     const int crank = CL > 1 ? (int)cluster_ctarank() : 0;
@@ -148,6 +149,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_const
     if (CL > 1) cluster_sync_all();   // barriers of every CTA are initialised before any remote TMA / commit touches them
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
+    uwr_pdl_wait();      // the predecessor grid has completed: global memory may be read and written from here on
 
     if (warp == 0) {
         // ================================ TMA producer ================================
@@ -476,6 +478,7 @@ __global__ void __launch_bounds__(32 * RED_GROUPS) t5_splitk_reduce_kernel(const
                                                                           float* __restrict__ out, long long n,
                                                                           long long stride, int splits) {
     __shared__ float4 sh[RED_GROUPS][32];
+    uwr_pdl_enter();
     const int col = threadIdx.x & 31, grp = threadIdx.x >> 5;
     const long long cols = n / 4;
     for (long long base = (long long)blockIdx.x * 32; base < cols; base += (long long)gridDim.x * 32) {
@@ -598,20 +601,22 @@ int t5_launch(const CUtensorMap& ma, const CUtensorMap& mb, const T5Params& p, c
     int clusters = uwr_sm_count() / CL;
     if (clusters > items) clusters = items;
     if (CL == 1) {
-        kern<<<clusters, T5_THREADS, smem, stream>>>(ma, mb, p);
+        UWR_CUDA(uwr_launch_pdl(kern, dim3(clusters), dim3(T5_THREADS), smem, stream, ma, mb, p));
     } else {
         cudaLaunchConfig_t cfg = {};
         cfg.gridDim = dim3(clusters * CL);
         cfg.blockDim = dim3(T5_THREADS);
         cfg.dynamicSmemBytes = smem;
         cfg.stream = stream;
-        cudaLaunchAttribute attr;
-        attr.id = cudaLaunchAttributeClusterDimension;
-        attr.val.clusterDim.x = CL;
-        attr.val.clusterDim.y = 1;
-        attr.val.clusterDim.z = 1;
-        cfg.attrs = &attr;
-        cfg.numAttrs = 1;
+        cudaLaunchAttribute attr[2];
+        attr[0].id = cudaLaunchAttributeClusterDimension;
+        attr[0].val.clusterDim.x = CL;
+        attr[0].val.clusterDim.y = 1;
+        attr[0].val.clusterDim.z = 1;
+        attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+        attr[1].val.programmaticStreamSerializationAllowed = uwr_pdl_enabled();
+        cfg.attrs = attr;
+        cfg.numAttrs = 2;
         UWR_CUDA(cudaLaunchKernelEx(&cfg, kern, ma, mb, p));
     }
     UWR_CHECK_LAUNCH("gemm_tcgen05_kernel");
@@ -758,7 +763,8 @@ extern "C" int uwr_gemm_tcgen05(const uwr_gemm_desc* d, uwr_stream_t stream_) {
         const long long n = (long long)d->M * d->N;
         int blocks = (int)((n / 4 + 31) / 32);
         if (blocks > 8 * uwr_sm_count()) blocks = 8 * uwr_sm_count();
-        t5_splitk_reduce_kernel<<<blocks, 32 * RED_GROUPS, 0, stream>>>(d->workspace, d->C, n, n, sp.splits);
+        UWR_CUDA(uwr_launch_pdl(t5_splitk_reduce_kernel, dim3(blocks), dim3(32 * RED_GROUPS), 0, stream,
+                                (const float*)d->workspace, d->C, n, n, sp.splits));
         UWR_CHECK_LAUNCH("t5_splitk_reduce_kernel");
     }
     return 0;
@@ -912,7 +918,8 @@ extern "C" int uwr_convgemm_tcgen05(const uwr_convgemm_desc* d, uwr_stream_t str
         const long long n = (long long)d->Cout * KN;
         int blocks = (int)((n / 4 + 31) / 32);
         if (blocks > 8 * uwr_sm_count()) blocks = 8 * uwr_sm_count();
-        t5_splitk_reduce_kernel<<<blocks, 32 * RED_GROUPS, 0, stream>>>(d->workspace, d->dw, n, n, sp.splits);
+        UWR_CUDA(uwr_launch_pdl(t5_splitk_reduce_kernel, dim3(blocks), dim3(32 * RED_GROUPS), 0, stream,
+                                (const float*)d->workspace, d->dw, n, n, sp.splits));
         UWR_CHECK_LAUNCH("t5_splitk_reduce_kernel");
     }
     return 0;

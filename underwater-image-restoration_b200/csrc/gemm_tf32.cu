@@ -49,6 +49,7 @@ struct TileCfg {
 
 template <int BN, bool A_KM, bool B_NK, int EPI, bool KSCALE, bool X3>
 __global__ void __launch_bounds__(NTHREADS, X3 ? 1 : 2) gemm_tf32_kernel(const GemmParams p) {
+    uwr_pdl_enter();
     using Cfg = TileCfg<BN, A_KM, B_NK>;
     extern __shared__ __align__(16) float smem[];
     float* As = smem;
@@ -289,6 +290,7 @@ __global__ void __launch_bounds__(NTHREADS, X3 ? 1 : 2) gemm_tf32_kernel(const G
 __global__ void splitk_reduce_kernel(const float* __restrict__ ws, float* __restrict__ out,
                                      long long n, long long stride, int splits, long long ld_out,
                                      int ncols) {
+    uwr_pdl_enter();
     long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     const long long step = (long long)gridDim.x * blockDim.x;
     for (; i < n; i += step) {
@@ -339,7 +341,7 @@ int launch_x(const GemmParams& p, int splits, cudaStream_t stream) {
         configured = true;
     }
     dim3 grid(uwr_cdiv(p.N, BN), uwr_cdiv(p.M, BM), splits);
-    kern<<<grid, NTHREADS, Cfg::SMEM_BYTES, stream>>>(p);
+    (void)uwr_launch_pdl(kern, dim3(grid), dim3(NTHREADS), Cfg::SMEM_BYTES, stream, p);
     UWR_CHECK_LAUNCH("gemm_tf32_kernel");
     return 0;
 }
@@ -444,10 +446,10 @@ extern "C" int uwr_gemm_tf32(const uwr_gemm_desc* d, uwr_stream_t stream_) {
         const long long n = (long long)d->M * d->N;
         int blocks = (int)((n + 255) / 256);
         if (blocks > 4 * uwr_sm_count()) blocks = 4 * uwr_sm_count();
-        splitk_reduce_kernel<<<blocks, 256, 0, stream>>>(ws_c, d->C, n, n, sp.splits, d->ldc, d->N);
+        (void)uwr_launch_pdl(splitk_reduce_kernel, dim3(blocks), dim3(256), 0, stream, ws_c, d->C, n, n, sp.splits, d->ldc, d->N);
         UWR_CHECK_LAUNCH("splitk_reduce_kernel");
         if (d->colsum) {
-            splitk_reduce_kernel<<<uwr_cdiv(d->M, 256), 256, 0, stream>>>(ws_cs, d->colsum, d->M, d->M, sp.splits,
+            (void)uwr_launch_pdl(splitk_reduce_kernel, dim3(uwr_cdiv(d->M, 256)), dim3(256), 0, stream, ws_cs, d->colsum, d->M, d->M, sp.splits,
                                                                          d->M, d->M);
             UWR_CHECK_LAUNCH("splitk_reduce_kernel(colsum)");
         }

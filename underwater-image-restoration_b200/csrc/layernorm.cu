@@ -17,6 +17,7 @@ __global__ void __launch_bounds__(LN_WARPS * 32) ln_fwd_kernel(const float* __re
                                                                float* __restrict__ y, float* __restrict__ mean,
                                                                float* __restrict__ rstd, long long rows, int C,
                                                                float eps, int rnd) {
+    uwr_pdl_enter();
     const int lane = threadIdx.x & 31;
     const int warp = threadIdx.x >> 5;
     float gm[VPL], bt[VPL];
@@ -72,6 +73,7 @@ __global__ void __launch_bounds__(LN_WARPS * 32, V4 <= 2 ? 4 : 2) ln_fwd_vec_ker
                                                                    float* __restrict__ y, float* __restrict__ mean,
                                                                    float* __restrict__ rstd, long long rows, float eps,
                                                                    int rnd) {
+    uwr_pdl_enter();
     constexpr int C = 4 * LPR * V4;
     constexpr int RPW = 32 / LPR;               // rows per warp pass
     constexpr int RPI = V4 <= 2 ? 4 : (V4 <= 4 ? 2 : 1);
@@ -142,6 +144,7 @@ __global__ void __launch_bounds__(LN_WARPS * 32) ln_bwd_kernel(const float* __re
                                                                const float* __restrict__ dres,
                                                                float* __restrict__ dx, float* __restrict__ partials,
                                                                long long rows, int C) {
+    uwr_pdl_enter();
     // RPI rows per warp iteration: all their loads are issued before the first reduction, which is
     // what keeps enough bytes in flight (one row per iteration ran at ~1.3 TB/s)
     constexpr int RPI = VPL <= 2 ? 4 : (VPL <= 8 ? 2 : 1);
@@ -232,6 +235,7 @@ __global__ void __launch_bounds__(LN_WARPS * 32) ln_bwd_vec_kernel(const float* 
                                                                    float* __restrict__ dx, float* __restrict__ partials,
                                                                    long long rows, const float* __restrict__ ds_scale,
                                                                    int ds_rpg, float* __restrict__ ds_out, int ds_round) {
+    uwr_pdl_enter();
     constexpr int C = 4 * LPR * V4;
     constexpr int RPW = 32 / LPR;
     constexpr int RPI = V4 == 1 ? 2 : 1;
@@ -341,6 +345,7 @@ __global__ void __launch_bounds__(LN_WARPS * 32) ln_bwd_vec_kernel(const float* 
 __global__ void __launch_bounds__(1024) ln_param_reduce3_kernel(const float* __restrict__ partials,
                                                                 float* __restrict__ dgamma, float* __restrict__ dbeta,
                                                                 float* __restrict__ colsum, int nblocks, int C) {
+    uwr_pdl_enter();
     __shared__ float sh[3][32][33];
     const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
     const int c = blockIdx.x * 32 + tx;
@@ -366,6 +371,7 @@ __global__ void __launch_bounds__(1024) ln_param_reduce3_kernel(const float* __r
 __global__ void __launch_bounds__(1024) ln_param_reduce_kernel(const float* __restrict__ partials,
                                                                float* __restrict__ dgamma,
                                                                float* __restrict__ dbeta, int nblocks, int C) {
+    uwr_pdl_enter();
     __shared__ float sa[32][33], sb[32][33];
     const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
     const int c = blockIdx.x * 32 + tx;
@@ -411,7 +417,7 @@ extern "C" int uwr_layernorm_fwd(const float* x, const float* gamma, const float
         long long b = (rows + LN_WARPS * (32 / L) - 1) / (LN_WARPS * (32 / L));                                  \
         const long long cap = (long long)uwr_sm_count() * (V <= 2 ? 4 : 2);   /* one resident wave */            \
         if (b > cap) b = cap;                                                                                    \
-        ln_fwd_vec_kernel<L, V><<<(unsigned)b, LN_WARPS * 32, 0, stream>>>(x, gamma, beta, y, mean, rstd, rows,  \
+        (void)uwr_launch_pdl(ln_fwd_vec_kernel<L, V>, dim3((unsigned)b), dim3(LN_WARPS * 32), 0, stream, x, gamma, beta, y, mean, rstd, rows,  \
                                                                            eps, uwr_round_outputs());            \
         UWR_CHECK_LAUNCH("ln_fwd_vec_kernel");                                                                   \
         return 0;                                                                                                \
@@ -430,7 +436,7 @@ extern "C" int uwr_layernorm_fwd(const float* x, const float* gamma, const float
     }
 #undef LN_FWD_VEC
     const int vpl = (C + 31) / 32;
-#define LN_FWD(V) ln_fwd_kernel<V><<<blocks, LN_WARPS * 32, 0, stream>>>(x, gamma, beta, y, mean, rstd, rows, C, eps, uwr_round_outputs())
+#define LN_FWD(V) (void)uwr_launch_pdl(ln_fwd_kernel<V>, dim3(blocks), dim3(LN_WARPS * 32), 0, stream, x, gamma, beta, y, mean, rstd, rows, C, eps, uwr_round_outputs())
     if (vpl <= 1) LN_FWD(1);
     else if (vpl <= 2) LN_FWD(2);
     else if (vpl <= 4) LN_FWD(4);
@@ -459,11 +465,11 @@ extern "C" int uwr_layernorm_bwd(const float* dy, const float* x, const float* g
         const long long cap = ln_blocks(rows);                                                                    \
         if (b > cap) b = cap;                                                                                     \
         if (b < 1) b = 1;                                                                                         \
-        ln_bwd_vec_kernel<L, V, false><<<(unsigned)b, LN_WARPS * 32, 0, stream>>>(dy, x, gamma, mean, rstd, dres, \
+        (void)uwr_launch_pdl(ln_bwd_vec_kernel<L, V, false>, dim3((unsigned)b), dim3(LN_WARPS * 32), 0, stream, dy, x, gamma, mean, rstd, dres, \
                                                                                   dx, partials, rows, nullptr, 1, \
                                                                                   nullptr, 0);                    \
         UWR_CHECK_LAUNCH("ln_bwd_vec_kernel");                                                                    \
-        ln_param_reduce_kernel<<<uwr_cdiv(C, 32), 1024, 0, stream>>>(partials, dgamma, dbeta, (int)b, C);         \
+        (void)uwr_launch_pdl(ln_param_reduce_kernel, dim3(uwr_cdiv(C, 32)), dim3(1024), 0, stream, partials, dgamma, dbeta, (int)b, C);         \
         UWR_CHECK_LAUNCH("ln_param_reduce_kernel");                                                               \
         return 0;                                                                                                 \
     } while (0)
@@ -482,7 +488,7 @@ extern "C" int uwr_layernorm_bwd(const float* dy, const float* x, const float* g
     const int blocks = ln_blocks(rows);
     const int vpl = (C + 31) / 32;
 #define LN_BWD(V) \
-    ln_bwd_kernel<V><<<blocks, LN_WARPS * 32, 0, stream>>>(dy, x, gamma, mean, rstd, dres, dx, partials, rows, C)
+    (void)uwr_launch_pdl(ln_bwd_kernel<V>, dim3(blocks), dim3(LN_WARPS * 32), 0, stream, dy, x, gamma, mean, rstd, dres, dx, partials, rows, C)
     if (vpl <= 1) LN_BWD(1);
     else if (vpl <= 2) LN_BWD(2);
     else if (vpl <= 4) LN_BWD(4);
@@ -491,7 +497,7 @@ extern "C" int uwr_layernorm_bwd(const float* dy, const float* x, const float* g
     else LN_BWD(32);
 #undef LN_BWD
     UWR_CHECK_LAUNCH("ln_bwd_kernel");
-    ln_param_reduce_kernel<<<uwr_cdiv(C, 32), 1024, 0, stream>>>(partials, dgamma, dbeta, blocks, C);
+    (void)uwr_launch_pdl(ln_param_reduce_kernel, dim3(uwr_cdiv(C, 32)), dim3(1024), 0, stream, partials, dgamma, dbeta, blocks, C);
     UWR_CHECK_LAUNCH("ln_param_reduce_kernel");
     return 0;
 }
@@ -525,10 +531,10 @@ extern "C" int uwr_layernorm_bwd_ds(const float* dy, const float* x, const float
         const long long cap = ln_blocks(rows);                                                                    \
         if (b > cap) b = cap;                                                                                     \
         if (b < 1) b = 1;                                                                                         \
-        ln_bwd_vec_kernel<L, V, true><<<(unsigned)b, LN_WARPS * 32, 0, stream>>>(                                 \
+        (void)uwr_launch_pdl(ln_bwd_vec_kernel<L, V, true>, dim3((unsigned)b), dim3(LN_WARPS * 32), 0, stream,                                  \
             dy, x, gamma, mean, rstd, dres, dx, partials, rows, ds_rowscale, rpg, ds_out, uwr_round_outputs());   \
         UWR_CHECK_LAUNCH("ln_bwd_vec_kernel<DS>");                                                                \
-        ln_param_reduce3_kernel<<<uwr_cdiv(C, 32), 1024, 0, stream>>>(partials, dgamma, dbeta, ds_colsum, (int)b, C); \
+        (void)uwr_launch_pdl(ln_param_reduce3_kernel, dim3(uwr_cdiv(C, 32)), dim3(1024), 0, stream, partials, dgamma, dbeta, ds_colsum, (int)b, C); \
         UWR_CHECK_LAUNCH("ln_param_reduce3_kernel");                                                              \
         return 0;                                                                                                 \
     } while (0)

@@ -16,6 +16,7 @@ __global__ void __launch_bounds__(LOSS_THREADS) pixel_loss_kernel(const float* _
                                                                   float* __restrict__ partials, int kind, int B,
                                                                   int C, long long HW, float inv_n, float inv_pix,
                                                                   float inv_div) {
+    uwr_pdl_enter();
     __shared__ float red[3][LOSS_THREADS / 32];
     float s_abs = 0.f, s_sq = 0.f, s_lum = 0.f;
     const long long npix = (long long)B * HW;
@@ -83,6 +84,7 @@ __global__ void __launch_bounds__(LOSS_THREADS) pixel_loss_kernel(const float* _
 
 __global__ void pixel_loss_final_kernel(const float* __restrict__ partials, float* __restrict__ out, int nblocks,
                                         int kind, float inv_n, float inv_pix, float inv_div) {
+    uwr_pdl_enter();
     __shared__ double sh[3][32];
     const int lane = threadIdx.x;  // 32 threads
     double a = 0.0, b = 0.0, c = 0.0;
@@ -130,10 +132,10 @@ extern "C" int uwr_pixel_loss(const float* pred, const float* truth, float* out,
     const float inv_n = (float)(1.0 / ((double)npix * C));
     const float inv_pix = (float)(1.0 / (double)npix);
     const float inv_div = (float)(1.0 / ((double)batch_divisor * C));
-    pixel_loss_kernel<<<blocks, LOSS_THREADS, 0, stream>>>(pred, truth, grad, workspace, kind, B, C, HW, inv_n, inv_pix,
+    (void)uwr_launch_pdl(pixel_loss_kernel, dim3(blocks), dim3(LOSS_THREADS), 0, stream, pred, truth, grad, workspace, kind, B, C, HW, inv_n, inv_pix,
                                                           inv_div);
     UWR_CHECK_LAUNCH("pixel_loss_kernel");
-    pixel_loss_final_kernel<<<1, 32, 0, stream>>>(workspace, out, blocks, kind, inv_n, inv_pix, inv_div);
+    (void)uwr_launch_pdl(pixel_loss_final_kernel, dim3(1), dim3(32), 0, stream, workspace, out, blocks, kind, inv_n, inv_pix, inv_div);
     UWR_CHECK_LAUNCH("pixel_loss_final_kernel");
     return 0;
 }

@@ -27,6 +27,7 @@ template <int CH>   // CH = c
 __global__ void __launch_bounds__(MD_THREADS)
 mdta_gram_kernel(const float* __restrict__ X, long long ldx, const float* __restrict__ Y, long long ldy, int L,
                  int heads, int tiles_per_cta, float* __restrict__ partials, int want_sq) {
+    uwr_pdl_enter();
     const int C = heads * CH;
     const int ST = C + 8;   // t*ST + g hits 32 distinct banks for the transposed fragment reads
     extern __shared__ __align__(16) float smem[];
@@ -136,6 +137,7 @@ mdta_gram_kernel(const float* __restrict__ X, long long ldx, const float* __rest
 
 __global__ void mdta_gram_reduce_kernel(const float* __restrict__ partials, int chunks, int per, int gsz, int C,
                                         float* __restrict__ G, float* __restrict__ sqx, float* __restrict__ sqy) {
+    uwr_pdl_enter();
     const int b = blockIdx.y;
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= per) return;
@@ -161,6 +163,7 @@ __global__ void __launch_bounds__(MD_THREADS)
 mdta_apply_kernel(const float* __restrict__ X, long long ldx, const float* __restrict__ Mx, int transpose,
                   const float* __restrict__ Yd, long long ldy, const float* __restrict__ diag, float* __restrict__ out,
                   long long ldo, int B, int L, int heads, int round_out) {
+    uwr_pdl_enter();
     const int C = heads * CH;
     const int ST = C + 4;     // g*ST + t: conflict-free row-major fragment reads
     constexpr int MS = CH + 4;
@@ -259,10 +262,10 @@ int launch_gram(const float* X, long long ldx, const float* Y, long long ldy, in
         UWR_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 4 * GR_TOK * (256 + 8) * 4));
         configured = true;
     }
-    kern<<<dim3(chunks, B), MD_THREADS, smem, stream>>>(X, ldx, Y, ldy, L, heads, tpc, ws, (sqx || sqy) ? 1 : 0);
+    (void)uwr_launch_pdl(kern, dim3(dim3(chunks, B)), dim3(MD_THREADS), smem, stream, X, ldx, Y, ldy, L, heads, tpc, ws, (sqx || sqy) ? 1 : 0);
     UWR_CHECK_LAUNCH("mdta_gram_kernel");
     const int gsz = heads * CH * CH, per = gsz + 2 * C;
-    mdta_gram_reduce_kernel<<<dim3(uwr_cdiv(per, 128), B), 128, 0, stream>>>(ws, chunks, per, gsz, C, G, sqx, sqy);
+    (void)uwr_launch_pdl(mdta_gram_reduce_kernel, dim3(dim3(uwr_cdiv(per, 128), B)), dim3(128), 0, stream, ws, chunks, per, gsz, C, G, sqx, sqy);
     UWR_CHECK_LAUNCH("mdta_gram_reduce_kernel");
     return 0;
 }
@@ -282,7 +285,7 @@ int launch_apply(const float* X, long long ldx, const float* Mx, int transpose, 
     const long long total = (long long)B * ((L + AP_TOK - 1) / AP_TOK);
     int grid = 4 * uwr_sm_count();
     if (grid > total) grid = (int)total;
-    kern<<<grid, MD_THREADS, smem, stream>>>(X, ldx, Mx, transpose, Yd, ldy, diag, out, ldo, B, L, heads,
+    (void)uwr_launch_pdl(kern, dim3(grid), dim3(MD_THREADS), smem, stream, X, ldx, Mx, transpose, Yd, ldy, diag, out, ldo, B, L, heads,
                                              uwr_round_outputs());
     UWR_CHECK_LAUNCH("mdta_apply_kernel");
     return 0;

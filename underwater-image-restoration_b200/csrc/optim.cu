@@ -23,6 +23,7 @@ __global__ void __launch_bounds__(OPT_THREADS) grad_sqsum_kernel(const float* co
                                                                  const long long* __restrict__ offsets, int n,
                                                                  long long total, float prescale,
                                                                  float* __restrict__ partials) {
+    uwr_pdl_enter();
     __shared__ float red[OPT_THREADS / 32];
     float s = 0.f;
     for (long long c0 = (long long)blockIdx.x * OPT_CHUNK; c0 < total; c0 += (long long)gridDim.x * OPT_CHUNK) {
@@ -49,6 +50,7 @@ __global__ void __launch_bounds__(OPT_THREADS) grad_sqsum_kernel(const float* co
 
 __global__ void grad_norm_final_kernel(const float* __restrict__ partials, int nblocks, float max_norm,
                                        float* __restrict__ out) {
+    uwr_pdl_enter();
     __shared__ double sh[32];
     double a = 0.0;
     for (int i = threadIdx.x; i < nblocks; i += 32) a += partials[i];
@@ -74,6 +76,7 @@ __global__ void __launch_bounds__(OPT_THREADS) adam_kernel(float* const* __restr
                                                            float eps, float wd, int decoupled, int step,
                                                            const int* __restrict__ step_dev,
                                                            const float* __restrict__ lr_dev) {
+    uwr_pdl_enter();
     const int st = step_dev ? *step_dev : step;
     if (lr_dev) lr = *lr_dev;   // device-resident learning rate: a captured CUDA graph follows scheduler updates
     const float gscale = prescale * (clip_coef ? *clip_coef : 1.f);
@@ -105,7 +108,8 @@ __global__ void __launch_bounds__(OPT_THREADS) adam_kernel(float* const* __restr
     }
 }
 
-__global__ void increment_kernel(int* p) { *p += 1; }
+__global__ void increment_kernel(int* p) {
+    uwr_pdl_enter(); *p += 1; }
 
 int opt_blocks(long long total) {
     long long b = (total + OPT_CHUNK - 1) / OPT_CHUNK;
@@ -123,9 +127,9 @@ extern "C" int uwr_grad_norm(const float* const* grads, const long long* offsets
     cudaStream_t stream = (cudaStream_t)stream_;
     UWR_REQUIRE(grads && offsets && norm_out && workspace && n_tensors > 0, "uwr_grad_norm: bad args");
     const int blocks = opt_blocks(total_elems);
-    grad_sqsum_kernel<<<blocks, OPT_THREADS, 0, stream>>>(grads, offsets, n_tensors, total_elems, grad_prescale, workspace);
+    (void)uwr_launch_pdl(grad_sqsum_kernel, dim3(blocks), dim3(OPT_THREADS), 0, stream, grads, offsets, n_tensors, total_elems, grad_prescale, workspace);
     UWR_CHECK_LAUNCH("grad_sqsum_kernel");
-    grad_norm_final_kernel<<<1, 32, 0, stream>>>(workspace, blocks, max_norm, norm_out);
+    (void)uwr_launch_pdl(grad_norm_final_kernel, dim3(1), dim3(32), 0, stream, workspace, blocks, max_norm, norm_out);
     UWR_CHECK_LAUNCH("grad_norm_final_kernel");
     return 0;
 }
@@ -138,7 +142,7 @@ extern "C" int uwr_adam_step(float* const* params, const float* const* grads, fl
     cudaStream_t stream = (cudaStream_t)stream_;
     UWR_REQUIRE(params && grads && exp_avg && exp_avg_sq && offsets && n_tensors > 0, "uwr_adam_step: bad args");
     UWR_REQUIRE(step_dev || step >= 1, "uwr_adam_step: step must be >= 1");
-    adam_kernel<<<opt_blocks(total_elems), OPT_THREADS, 0, stream>>>(params, grads, exp_avg, exp_avg_sq, offsets,
+    (void)uwr_launch_pdl(adam_kernel, dim3(opt_blocks(total_elems)), dim3(OPT_THREADS), 0, stream, params, grads, exp_avg, exp_avg_sq, offsets,
                                                                     n_tensors, total_elems, clip_coef, grad_prescale,
                                                                     lr, beta1, beta2, eps, weight_decay, decoupled,
                                                                     step, step_dev, lr_dev);
@@ -147,7 +151,7 @@ extern "C" int uwr_adam_step(float* const* params, const float* const* grads, fl
 }
 
 extern "C" int uwr_increment_i32(int* counter, uwr_stream_t stream_) {
-    increment_kernel<<<1, 1, 0, (cudaStream_t)stream_>>>(counter);
+    (void)uwr_launch_pdl(increment_kernel, dim3(1), dim3(1), 0, (cudaStream_t)stream_, counter);
     UWR_CHECK_LAUNCH("increment_kernel");
     return 0;
 }

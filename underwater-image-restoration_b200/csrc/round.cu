@@ -23,6 +23,7 @@ __global__ void __launch_bounds__(256) round_tensors_kernel(const float* const* 
                                                             float* const* __restrict__ dst,
                                                             const long long* __restrict__ offsets, int n,
                                                             long long total, int do_round) {
+    uwr_pdl_enter();
     constexpr int CHUNK = 4096;
     for (long long c0 = (long long)blockIdx.x * CHUNK; c0 < total; c0 += (long long)gridDim.x * CHUNK) {
         const long long c1 = min(total, c0 + CHUNK);
@@ -41,6 +42,7 @@ __global__ void __launch_bounds__(256) scale_round_kernel(const float* __restric
                                                           float* __restrict__ dst, long long rows, int cols4,
                                                           const float* __restrict__ rowscale, int rpg,
                                                           int do_round) {
+    uwr_pdl_enter();
     const long long total = rows * cols4;
     for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total;
          i += (long long)gridDim.x * blockDim.x) {
@@ -61,6 +63,7 @@ __global__ void __launch_bounds__(256) scale_round_colsum_kernel(const float* __
                                                                  float* __restrict__ dst, long long rows, int cols4,
                                                                  const float* __restrict__ rowscale, int rpg,
                                                                  int do_round, float* __restrict__ partials) {
+    uwr_pdl_enter();
     __shared__ float4 sh[256];
     const int c4 = threadIdx.x % cols4, rsub = threadIdx.x / cols4, rpb = 256 / cols4;
     float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -98,6 +101,7 @@ __global__ void __launch_bounds__(256) scale_round_colsum_kernel(const float* __
 // out[c] = sum_p partials[p][c]: 32 columns x 32 row slices per CTA, fixed order (deterministic)
 __global__ void __launch_bounds__(1024) colsum_partials_kernel(const float* __restrict__ partials,
                                                                float* __restrict__ out, int P, int cols) {
+    uwr_pdl_enter();
     __shared__ float sh[32][33];
     const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
     const int c = blockIdx.x * 32 + tx;
@@ -126,11 +130,11 @@ extern "C" int uwr_scale_round_colsum(const float* src, long long ld_src, float*
     long long cap = 8LL * uwr_sm_count();
     if (cap > 1024) cap = 1024;
     if (blocks > cap) blocks = cap;
-    scale_round_colsum_kernel<<<(unsigned)blocks, 256, 0, stream>>>(src, ld_src, dst, rows, cols4, rowscale,
+    (void)uwr_launch_pdl(scale_round_colsum_kernel, dim3((unsigned)blocks), dim3(256), 0, stream, src, ld_src, dst, rows, cols4, rowscale,
                                                                    rows_per_group > 0 ? rows_per_group : 1, do_round,
                                                                    workspace);
     UWR_CHECK_LAUNCH("scale_round_colsum_kernel");
-    colsum_partials_kernel<<<uwr_cdiv(cols, 32), 1024, 0, stream>>>(workspace, colsum, (int)blocks, cols);
+    (void)uwr_launch_pdl(colsum_partials_kernel, dim3(uwr_cdiv(cols, 32)), dim3(1024), 0, stream, workspace, colsum, (int)blocks, cols);
     UWR_CHECK_LAUNCH("colsum_partials_kernel");
     return 0;
 }
@@ -142,7 +146,7 @@ extern "C" int uwr_round_tf32_tensors(const float* const* src, float* const* dst
     long long blocks = (total_elems + 4095) / 4096;
     if (blocks > 8LL * uwr_sm_count()) blocks = 8LL * uwr_sm_count();
     if (blocks < 1) blocks = 1;
-    round_tensors_kernel<<<(unsigned)blocks, 256, 0, stream>>>(src, dst, offsets, n_tensors, total_elems, do_round);
+    (void)uwr_launch_pdl(round_tensors_kernel, dim3((unsigned)blocks), dim3(256), 0, stream, src, dst, offsets, n_tensors, total_elems, do_round);
     UWR_CHECK_LAUNCH("round_tensors_kernel");
     return 0;
 }
@@ -155,7 +159,7 @@ extern "C" int uwr_scale_round(const float* src, long long ld_src, float* dst, l
     if (rows == 0) return 0;
     long long blocks = (rows * (cols / 4) + 255) / 256;
     if (blocks > 16LL * uwr_sm_count()) blocks = 16LL * uwr_sm_count();
-    scale_round_kernel<<<(unsigned)blocks, 256, 0, stream>>>(src, ld_src, dst, rows, cols / 4, rowscale,
+    (void)uwr_launch_pdl(scale_round_kernel, dim3((unsigned)blocks), dim3(256), 0, stream, src, ld_src, dst, rows, cols / 4, rowscale,
                                                             rows_per_group > 0 ? rows_per_group : 1, do_round);
     UWR_CHECK_LAUNCH("scale_round_kernel");
     return 0;

@@ -26,6 +26,7 @@ inline int ew_grid(long long work) {
 // n complex numbers, two per thread iteration (one float4 in, one float2 to each output)
 __global__ void polar_split_fwd_kernel(const float4* __restrict__ f, float2* __restrict__ mag, float2* __restrict__ pha,
                                        long long n2) {
+    uwr_pdl_enter();
     for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n2; i += (long long)gridDim.x * blockDim.x) {
         const float4 v = f[i];
         mag[i] = make_float2(hypotf(v.x, v.y), hypotf(v.z, v.w));
@@ -42,6 +43,7 @@ __device__ __forceinline__ float2 polar_split_grad(float re, float im, float dm,
 
 __global__ void polar_split_bwd_kernel(const float4* __restrict__ f, const float2* __restrict__ dmag,
                                        const float2* __restrict__ dpha, float4* __restrict__ df, long long n2) {
+    uwr_pdl_enter();
     for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n2; i += (long long)gridDim.x * blockDim.x) {
         const float4 v = f[i];
         const float2 dm = dmag[i], dp = dpha[i];
@@ -52,6 +54,7 @@ __global__ void polar_split_bwd_kernel(const float4* __restrict__ f, const float
 
 __global__ void polar_join_fwd_kernel(const float2* __restrict__ mag, const float2* __restrict__ pha,
                                       float4* __restrict__ z, long long n2) {
+    uwr_pdl_enter();
     for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n2; i += (long long)gridDim.x * blockDim.x) {
         const float2 m = mag[i], p = pha[i];
         float s0, c0, s1, c1;
@@ -64,6 +67,7 @@ __global__ void polar_join_fwd_kernel(const float2* __restrict__ mag, const floa
 __global__ void polar_join_bwd_kernel(const float2* __restrict__ mag, const float2* __restrict__ pha,
                                       const float4* __restrict__ dz, float2* __restrict__ dmag, float2* __restrict__ dpha,
                                       long long n2) {
+    uwr_pdl_enter();
     for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n2; i += (long long)gridDim.x * blockDim.x) {
         const float2 m = mag[i], p = pha[i];
         const float4 d = dz[i];
@@ -76,6 +80,7 @@ __global__ void polar_join_bwd_kernel(const float2* __restrict__ mag, const floa
 }
 
 __global__ void cabs_fwd_kernel(const float4* __restrict__ z, float2* __restrict__ a, long long n2) {
+    uwr_pdl_enter();
     for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n2; i += (long long)gridDim.x * blockDim.x) {
         const float4 v = z[i];
         a[i] = make_float2(hypotf(v.x, v.y), hypotf(v.z, v.w));
@@ -84,6 +89,7 @@ __global__ void cabs_fwd_kernel(const float4* __restrict__ z, float2* __restrict
 
 __global__ void cabs_bwd_kernel(const float4* __restrict__ z, const float2* __restrict__ da, float4* __restrict__ dz,
                                 long long n2) {
+    uwr_pdl_enter();
     for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n2; i += (long long)gridDim.x * blockDim.x) {
         const float4 v = z[i];
         const float2 d = da[i];
@@ -95,6 +101,7 @@ __global__ void cabs_bwd_kernel(const float4* __restrict__ z, const float2* __re
 
 // y = x > 0 ? x : slope * x ; backward selects on the sign of the saved OUTPUT (slope > 0 keeps the sign)
 __global__ void leaky_fwd_kernel(const float4* __restrict__ x, float4* __restrict__ y, long long n4, float slope, int rnd) {
+    uwr_pdl_enter();
     for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (long long)gridDim.x * blockDim.x) {
         float4 v = x[i];
         v.x = v.x > 0.f ? v.x : slope * v.x; v.y = v.y > 0.f ? v.y : slope * v.y;
@@ -106,6 +113,7 @@ __global__ void leaky_fwd_kernel(const float4* __restrict__ x, float4* __restric
 
 __global__ void leaky_bwd_kernel(const float4* __restrict__ y, const float4* __restrict__ dy, float4* __restrict__ dx,
                                  long long n4, float slope) {
+    uwr_pdl_enter();
     for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (long long)gridDim.x * blockDim.x) {
         const float4 v = y[i], d = dy[i];
         dx[i] = make_float4(v.x > 0.f ? d.x : slope * d.x, v.y > 0.f ? d.y : slope * d.y, v.z > 0.f ? d.z : slope * d.z,
@@ -115,6 +123,7 @@ __global__ void leaky_bwd_kernel(const float4* __restrict__ y, const float4* __r
 
 // exact (erf) GELU as nn.GELU(): FDFP between its two 1x1 convs (block.py:541-546), Mlp.act (AST.py:285-291)
 __global__ void gelu_fwd_kernel(const float4* __restrict__ x, float4* __restrict__ y, long long n4, int rnd) {
+    uwr_pdl_enter();
     for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (long long)gridDim.x * blockDim.x) {
         const float4 v = x[i];
         float4 o = make_float4(gelu_f(v.x), gelu_f(v.y), gelu_f(v.z), gelu_f(v.w));
@@ -125,6 +134,7 @@ __global__ void gelu_fwd_kernel(const float4* __restrict__ x, float4* __restrict
 
 __global__ void gelu_bwd_kernel(const float4* __restrict__ x, const float4* __restrict__ dy, float4* __restrict__ dx,
                                 long long n4) {
+    uwr_pdl_enter();
     for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (long long)gridDim.x * blockDim.x) {
         const float4 v = x[i], d = dy[i];
         dx[i] = make_float4(d.x * gelu_grad_f(v.x), d.y * gelu_grad_f(v.y), d.z * gelu_grad_f(v.z), d.w * gelu_grad_f(v.w));
@@ -134,6 +144,7 @@ __global__ void gelu_bwd_kernel(const float4* __restrict__ x, const float4* __re
 // out (B, 2H, 2W, C): even pixels <- y (B, H, W, C), every other pixel <- bias.  One float4 of out per thread step.
 __global__ void even_scatter_kernel(const float* __restrict__ y, const float* __restrict__ bias, float* __restrict__ out,
                                     int H, int W, int C, long long total4) {
+    uwr_pdl_enter();
     const int c4n = C / 4;
     for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total4; i += (long long)gridDim.x * blockDim.x) {
         const int c4 = (int)(i % c4n);
@@ -152,6 +163,7 @@ __global__ void even_scatter_kernel(const float* __restrict__ y, const float* __
 // dy (B, H, W, C) <- the even pixels of dout (B, 2H, 2W, C)
 __global__ void even_gather_kernel(const float* __restrict__ dout, float* __restrict__ dy, int H, int W, int C,
                                    long long total4) {
+    uwr_pdl_enter();
     const int c4n = C / 4;
     for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total4; i += (long long)gridDim.x * blockDim.x) {
         const int c4 = (int)(i % c4n);
@@ -174,7 +186,7 @@ extern "C" int uwr_polar_split_fwd(const float* f, float* mag, float* pha, long 
     cudaStream_t stream = (cudaStream_t)stream_;
     UWR_REQUIRE(f && mag && pha, "uwr_polar_split_fwd: null pointer");
     EW_CHECK_N2("uwr_polar_split_fwd");
-    polar_split_fwd_kernel<<<ew_grid(n / 2), EW_THREADS, 0, stream>>>((const float4*)f, (float2*)mag, (float2*)pha, n / 2);
+    (void)uwr_launch_pdl(polar_split_fwd_kernel, dim3(ew_grid(n / 2)), dim3(EW_THREADS), 0, stream, (const float4*)f, (float2*)mag, (float2*)pha, n / 2);
     UWR_CHECK_LAUNCH("polar_split_fwd_kernel");
     return 0;
 }
@@ -184,7 +196,7 @@ extern "C" int uwr_polar_split_bwd(const float* f, const float* dmag, const floa
     cudaStream_t stream = (cudaStream_t)stream_;
     UWR_REQUIRE(f && dmag && dpha && df, "uwr_polar_split_bwd: null pointer");
     EW_CHECK_N2("uwr_polar_split_bwd");
-    polar_split_bwd_kernel<<<ew_grid(n / 2), EW_THREADS, 0, stream>>>((const float4*)f, (const float2*)dmag,
+    (void)uwr_launch_pdl(polar_split_bwd_kernel, dim3(ew_grid(n / 2)), dim3(EW_THREADS), 0, stream, (const float4*)f, (const float2*)dmag,
                                                                      (const float2*)dpha, (float4*)df, n / 2);
     UWR_CHECK_LAUNCH("polar_split_bwd_kernel");
     return 0;
@@ -194,7 +206,7 @@ extern "C" int uwr_polar_join_fwd(const float* mag, const float* pha, float* z, 
     cudaStream_t stream = (cudaStream_t)stream_;
     UWR_REQUIRE(mag && pha && z, "uwr_polar_join_fwd: null pointer");
     EW_CHECK_N2("uwr_polar_join_fwd");
-    polar_join_fwd_kernel<<<ew_grid(n / 2), EW_THREADS, 0, stream>>>((const float2*)mag, (const float2*)pha, (float4*)z, n / 2);
+    (void)uwr_launch_pdl(polar_join_fwd_kernel, dim3(ew_grid(n / 2)), dim3(EW_THREADS), 0, stream, (const float2*)mag, (const float2*)pha, (float4*)z, n / 2);
     UWR_CHECK_LAUNCH("polar_join_fwd_kernel");
     return 0;
 }
@@ -204,7 +216,7 @@ extern "C" int uwr_polar_join_bwd(const float* mag, const float* pha, const floa
     cudaStream_t stream = (cudaStream_t)stream_;
     UWR_REQUIRE(mag && pha && dz && dmag && dpha, "uwr_polar_join_bwd: null pointer");
     EW_CHECK_N2("uwr_polar_join_bwd");
-    polar_join_bwd_kernel<<<ew_grid(n / 2), EW_THREADS, 0, stream>>>((const float2*)mag, (const float2*)pha,
+    (void)uwr_launch_pdl(polar_join_bwd_kernel, dim3(ew_grid(n / 2)), dim3(EW_THREADS), 0, stream, (const float2*)mag, (const float2*)pha,
                                                                     (const float4*)dz, (float2*)dmag, (float2*)dpha, n / 2);
     UWR_CHECK_LAUNCH("polar_join_bwd_kernel");
     return 0;
@@ -214,7 +226,7 @@ extern "C" int uwr_cabs_fwd(const float* z, float* a, long long n, uwr_stream_t 
     cudaStream_t stream = (cudaStream_t)stream_;
     UWR_REQUIRE(z && a, "uwr_cabs_fwd: null pointer");
     EW_CHECK_N2("uwr_cabs_fwd");
-    cabs_fwd_kernel<<<ew_grid(n / 2), EW_THREADS, 0, stream>>>((const float4*)z, (float2*)a, n / 2);
+    (void)uwr_launch_pdl(cabs_fwd_kernel, dim3(ew_grid(n / 2)), dim3(EW_THREADS), 0, stream, (const float4*)z, (float2*)a, n / 2);
     UWR_CHECK_LAUNCH("cabs_fwd_kernel");
     return 0;
 }
@@ -223,7 +235,7 @@ extern "C" int uwr_cabs_bwd(const float* z, const float* da, float* dz, long lon
     cudaStream_t stream = (cudaStream_t)stream_;
     UWR_REQUIRE(z && da && dz, "uwr_cabs_bwd: null pointer");
     EW_CHECK_N2("uwr_cabs_bwd");
-    cabs_bwd_kernel<<<ew_grid(n / 2), EW_THREADS, 0, stream>>>((const float4*)z, (const float2*)da, (float4*)dz, n / 2);
+    (void)uwr_launch_pdl(cabs_bwd_kernel, dim3(ew_grid(n / 2)), dim3(EW_THREADS), 0, stream, (const float4*)z, (const float2*)da, (float4*)dz, n / 2);
     UWR_CHECK_LAUNCH("cabs_bwd_kernel");
     return 0;
 }
@@ -231,7 +243,7 @@ extern "C" int uwr_cabs_bwd(const float* z, const float* da, float* dz, long lon
 extern "C" int uwr_gelu_fwd(const float* x, float* y, long long n, int round_out, uwr_stream_t stream_) {
     cudaStream_t stream = (cudaStream_t)stream_;
     UWR_REQUIRE(x && y && n > 0 && n % 4 == 0, "uwr_gelu_fwd: n %% 4 == 0 required");
-    gelu_fwd_kernel<<<ew_grid(n / 4), EW_THREADS, 0, stream>>>((const float4*)x, (float4*)y, n / 4,
+    (void)uwr_launch_pdl(gelu_fwd_kernel, dim3(ew_grid(n / 4)), dim3(EW_THREADS), 0, stream, (const float4*)x, (float4*)y, n / 4,
                                                               round_out && uwr_round_outputs());
     UWR_CHECK_LAUNCH("gelu_fwd_kernel");
     return 0;
@@ -240,7 +252,7 @@ extern "C" int uwr_gelu_fwd(const float* x, float* y, long long n, int round_out
 extern "C" int uwr_gelu_bwd(const float* x, const float* dy, float* dx, long long n, uwr_stream_t stream_) {
     cudaStream_t stream = (cudaStream_t)stream_;
     UWR_REQUIRE(x && dy && dx && n > 0 && n % 4 == 0, "uwr_gelu_bwd: n %% 4 == 0 required");
-    gelu_bwd_kernel<<<ew_grid(n / 4), EW_THREADS, 0, stream>>>((const float4*)x, (const float4*)dy, (float4*)dx, n / 4);
+    (void)uwr_launch_pdl(gelu_bwd_kernel, dim3(ew_grid(n / 4)), dim3(EW_THREADS), 0, stream, (const float4*)x, (const float4*)dy, (float4*)dx, n / 4);
     UWR_CHECK_LAUNCH("gelu_bwd_kernel");
     return 0;
 }
@@ -248,7 +260,7 @@ extern "C" int uwr_gelu_bwd(const float* x, const float* dy, float* dx, long lon
 extern "C" int uwr_leaky_relu_fwd(const float* x, float* y, long long n, float slope, int round_out, uwr_stream_t stream_) {
     cudaStream_t stream = (cudaStream_t)stream_;
     UWR_REQUIRE(x && y && n > 0 && n % 4 == 0 && slope > 0.f, "uwr_leaky_relu_fwd: n %% 4 == 0 and slope > 0 required");
-    leaky_fwd_kernel<<<ew_grid(n / 4), EW_THREADS, 0, stream>>>((const float4*)x, (float4*)y, n / 4, slope,
+    (void)uwr_launch_pdl(leaky_fwd_kernel, dim3(ew_grid(n / 4)), dim3(EW_THREADS), 0, stream, (const float4*)x, (float4*)y, n / 4, slope,
                                                                round_out && uwr_round_outputs());
     UWR_CHECK_LAUNCH("leaky_fwd_kernel");
     return 0;
@@ -258,7 +270,7 @@ extern "C" int uwr_leaky_relu_bwd(const float* y, const float* dy, float* dx, lo
                                   uwr_stream_t stream_) {
     cudaStream_t stream = (cudaStream_t)stream_;
     UWR_REQUIRE(y && dy && dx && n > 0 && n % 4 == 0 && slope > 0.f, "uwr_leaky_relu_bwd: n %% 4 == 0 and slope > 0 required");
-    leaky_bwd_kernel<<<ew_grid(n / 4), EW_THREADS, 0, stream>>>((const float4*)y, (const float4*)dy, (float4*)dx, n / 4, slope);
+    (void)uwr_launch_pdl(leaky_bwd_kernel, dim3(ew_grid(n / 4)), dim3(EW_THREADS), 0, stream, (const float4*)y, (const float4*)dy, (float4*)dx, n / 4, slope);
     UWR_CHECK_LAUNCH("leaky_bwd_kernel");
     return 0;
 }
@@ -268,7 +280,7 @@ extern "C" int uwr_even_scatter(const float* y, const float* bias, float* out, i
     cudaStream_t stream = (cudaStream_t)stream_;
     UWR_REQUIRE(y && bias && out && C % 4 == 0 && B > 0 && H > 0 && W > 0, "uwr_even_scatter: bad args (C %% 4 == 0)");
     const long long total4 = (long long)B * 4 * H * W * (C / 4);
-    even_scatter_kernel<<<ew_grid(total4), EW_THREADS, 0, stream>>>(y, bias, out, H, W, C, total4);
+    (void)uwr_launch_pdl(even_scatter_kernel, dim3(ew_grid(total4)), dim3(EW_THREADS), 0, stream, y, bias, out, H, W, C, total4);
     UWR_CHECK_LAUNCH("even_scatter_kernel");
     return 0;
 }
@@ -277,7 +289,7 @@ extern "C" int uwr_even_gather(const float* dout, float* dy, int B, int H, int W
     cudaStream_t stream = (cudaStream_t)stream_;
     UWR_REQUIRE(dout && dy && C % 4 == 0 && B > 0 && H > 0 && W > 0, "uwr_even_gather: bad args (C %% 4 == 0)");
     const long long total4 = (long long)B * H * W * (C / 4);
-    even_gather_kernel<<<ew_grid(total4), EW_THREADS, 0, stream>>>(dout, dy, H, W, C, total4);
+    (void)uwr_launch_pdl(even_gather_kernel, dim3(ew_grid(total4)), dim3(EW_THREADS), 0, stream, dout, dy, H, W, C, total4);
     UWR_CHECK_LAUNCH("even_gather_kernel");
     return 0;
 }

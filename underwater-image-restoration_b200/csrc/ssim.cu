@@ -29,6 +29,7 @@ struct Gauss {
 __global__ void __launch_bounds__(256) lap_sign_kernel(const float* __restrict__ p, const float* __restrict__ t,
                                                        float* __restrict__ s, float* __restrict__ partials, int planes,
                                                        int H, int W) {
+    uwr_pdl_enter();
     __shared__ float red[8];
     const long long total = (long long)planes * H * W;
     float acc = 0.f;
@@ -57,6 +58,7 @@ __global__ void __launch_bounds__(256) lap_sign_kernel(const float* __restrict__
 __global__ void __launch_bounds__(256) lap_grad_kernel(const float* __restrict__ s, const float* __restrict__ partials,
                                                        int nparts, float* __restrict__ grad, float* __restrict__ loss,
                                                        int planes, int H, int W, float inv_n) {
+    uwr_pdl_enter();
     const long long total = (long long)planes * H * W;
     for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
         if (grad == nullptr) break;
@@ -83,6 +85,7 @@ __global__ void __launch_bounds__(SS_THREADS)
 ssim_fwd_kernel(const float* __restrict__ X, const float* __restrict__ Y, float* __restrict__ maps,
                 float* __restrict__ part_cs, float* __restrict__ part_ss, int H, int W, Gauss gw, float C1, float C2,
                 int full) {
+    uwr_pdl_enter();
     __shared__ float xs[SH * SH], ys[SH * SH];
     __shared__ float hz[5][SH * ST];
     __shared__ float red[2][SS_THREADS / 32];
@@ -160,6 +163,7 @@ ssim_fwd_kernel(const float* __restrict__ X, const float* __restrict__ Y, float*
 // means[plane] = sum of that plane's tile partials / (Ho*Wo), for cs and ssim
 __global__ void ssim_mean_kernel(const float* __restrict__ part_cs, const float* __restrict__ part_ss, int tiles,
                                  float inv_count, float* __restrict__ mean_cs, float* __restrict__ mean_ss) {
+    uwr_pdl_enter();
     const int plane = blockIdx.x;
     __shared__ double sh[2][32];
     double a = 0.0, b = 0.0;
@@ -184,6 +188,7 @@ __global__ void __launch_bounds__(SS_THREADS)
 ssim_bwd_kernel(const float* __restrict__ X, const float* __restrict__ Y, const float* __restrict__ maps,
                 const float* __restrict__ coef, const float* __restrict__ dXc, float* __restrict__ dX, int H, int W,
                 Gauss gw) {
+    uwr_pdl_enter();
     __shared__ float ms[3][SH * SH];
     __shared__ float hz[3][SH * ST];
     const int Ho = H - WIN + 1, Wo = W - WIN + 1;
@@ -232,6 +237,7 @@ ssim_bwd_kernel(const float* __restrict__ X, const float* __restrict__ Y, const 
 __global__ void __launch_bounds__(256) avgpool2_pair_kernel(const float* __restrict__ X, const float* __restrict__ Y,
                                                             float* __restrict__ Xo, float* __restrict__ Yo, int planes,
                                                             int H, int W) {
+    uwr_pdl_enter();
     const int Ho = H / 2, Wo = W / 2;
     const long long total = (long long)planes * Ho * Wo;
     for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
@@ -275,10 +281,10 @@ extern "C" int uwr_laplacian_l1_loss(const float* pred, const float* truth, floa
     int blocks = ew_blocks2(total);
     if (blocks > 8192) blocks = 8192;
     float* s = workspace + 8192;
-    lap_sign_kernel<<<blocks, 256, 0, stream>>>(pred, truth, s, workspace, planes, H, W);
+    (void)uwr_launch_pdl(lap_sign_kernel, dim3(blocks), dim3(256), 0, stream, pred, truth, s, workspace, planes, H, W);
     UWR_CHECK_LAUNCH("lap_sign_kernel");
     const float inv_n = (float)(1.0 / ((double)planes * (H - 2) * (W - 2)));
-    lap_grad_kernel<<<grad ? blocks : 1, 256, 0, stream>>>(s, workspace, blocks, grad, loss, planes, H, W, inv_n);
+    (void)uwr_launch_pdl(lap_grad_kernel, dim3(grad ? blocks : 1), dim3(256), 0, stream, s, workspace, blocks, grad, loss, planes, H, W, inv_n);
     UWR_CHECK_LAUNCH("lap_grad_kernel");
     return 0;
 }
@@ -301,9 +307,9 @@ extern "C" int uwr_ssim_scale_fwd(const float* X, const float* Y, float* maps, f
     float* pcs = workspace;
     float* pss = workspace + (size_t)planes * tiles;
     const float C1 = (0.01f * data_range) * (0.01f * data_range), C2 = (0.03f * data_range) * (0.03f * data_range);
-    ssim_fwd_kernel<<<grid, SS_THREADS, 0, stream>>>(X, Y, maps, pcs, pss, H, W, make_gauss(), C1, C2, full);
+    (void)uwr_launch_pdl(ssim_fwd_kernel, dim3(grid), dim3(SS_THREADS), 0, stream, X, Y, maps, pcs, pss, H, W, make_gauss(), C1, C2, full);
     UWR_CHECK_LAUNCH("ssim_fwd_kernel");
-    ssim_mean_kernel<<<planes, 32, 0, stream>>>(pcs, pss, tiles, (float)(1.0 / ((double)Ho * Wo)), mean_cs, mean_ss);
+    (void)uwr_launch_pdl(ssim_mean_kernel, dim3(planes), dim3(32), 0, stream, pcs, pss, tiles, (float)(1.0 / ((double)Ho * Wo)), mean_cs, mean_ss);
     UWR_CHECK_LAUNCH("ssim_mean_kernel");
     return 0;
 }
@@ -316,7 +322,7 @@ extern "C" int uwr_ssim_scale_bwd(const float* X, const float* Y, const float* m
     UWR_REQUIRE(H >= WIN && W >= WIN && (dX_coarse == nullptr || (H % 2 == 0 && W % 2 == 0)),
                 "uwr_ssim_scale_bwd: planes >= 11 x 11, even sides below a coarser scale");
     dim3 grid(uwr_cdiv(W, ST), uwr_cdiv(H, ST), planes);
-    ssim_bwd_kernel<<<grid, SS_THREADS, 0, stream>>>(X, Y, maps, coef, dX_coarse, dX, H, W, make_gauss());
+    (void)uwr_launch_pdl(ssim_bwd_kernel, dim3(grid), dim3(SS_THREADS), 0, stream, X, Y, maps, coef, dX_coarse, dX, H, W, make_gauss());
     UWR_CHECK_LAUNCH("ssim_bwd_kernel");
     return 0;
 }
@@ -326,7 +332,7 @@ extern "C" int uwr_avgpool2_pair(const float* X, const float* Y, float* Xo, floa
     cudaStream_t stream = (cudaStream_t)stream_;
     UWR_REQUIRE(X && Y && Xo && Yo && planes > 0 && H % 2 == 0 && W % 2 == 0 && H >= 2 && W >= 2,
                 "uwr_avgpool2_pair: even plane sides required");
-    avgpool2_pair_kernel<<<ew_blocks2((long long)planes * (H / 2) * (W / 2)), 256, 0, stream>>>(X, Y, Xo, Yo, planes, H, W);
+    (void)uwr_launch_pdl(avgpool2_pair_kernel, dim3(ew_blocks2((long long)planes * (H / 2) * (W / 2))), dim3(256), 0, stream, X, Y, Xo, Yo, planes, H, W);
     UWR_CHECK_LAUNCH("avgpool2_pair_kernel");
     return 0;
 }

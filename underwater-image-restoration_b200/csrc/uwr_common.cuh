@@ -44,6 +44,43 @@ extern unsigned long long g_uwr_launches;  // kernels launched by this library (
 static inline int uwr_cdiv(long long a, long long b) { return (int)((a + b - 1) / b); }
 int uwr_sm_count();
 
+// ---- programmatic dependent launch (PDL) -------------------------------------------------
+// A training step is ~600 dependent kernels on one stream; between two of them the GPU drains, the next grid is
+// launched, its CTAs run their set-up (barrier init, TMEM allocation, weight / table loads into registers).  With PDL the
+// next grid is launched as soon as every CTA of the running one has started (griddepcontrol.launch_dependents, the first
+// instruction of every converted kernel), its CTAs become resident wherever an SM has room -- first in the tail of the
+// running kernel -- do whatever needs no global data, and block in griddepcontrol.wait until the WHOLE preceding grid has
+// completed and its memory is visible.  Rules that keep this equivalent to plain stream order:
+//   * a kernel launched through uwr_launch_pdl() executes uwr_pdl_wait() (or uwr_pdl_enter()) on every path before its
+//     first global-memory access of any kind -- reads of a predecessor's output AND writes a predecessor might still read;
+//     kernel parameters (tensor maps included) are not global memory in this sense;
+//   * everything else keeps the <<<>>> launch: it then starts after the converted kernel before it has completed, and a
+//     converted kernel after it is launched when it completes (no trigger = trigger at exit).
+// Stream capture turns the attribute into a programmatic edge of the CUDA graph.  Without the attribute (the default:
+// UWR_PDL unset / uwr_set_pdl(0)) the same launches are plain stream-ordered launches and the device instructions no-ops.
+__device__ __forceinline__ void uwr_pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;"); }
+__device__ __forceinline__ void uwr_pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void uwr_pdl_enter() {
+    uwr_pdl_trigger();
+    uwr_pdl_wait();
+}
+int uwr_pdl_enabled();
+template <typename... KArgs, typename... Args>
+static inline cudaError_t uwr_launch_pdl(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t stream,
+                                         Args&&... args) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = grid;
+    cfg.blockDim = block;
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = stream;
+    cudaLaunchAttribute attr;
+    attr.id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr.val.programmaticStreamSerializationAllowed = uwr_pdl_enabled();
+    cfg.attrs = &attr;
+    cfg.numAttrs = 1;
+    return cudaLaunchKernelEx(&cfg, kern, static_cast<Args&&>(args)...);
+}
+
 // ---- numerics ---------------------------------------------------------------------------
 // fp32 -> tf32 with round-to-nearest (ties away); the tensor core would otherwise truncate,
 // which biases every product by ~-1e-3 relative.

@@ -32,6 +32,7 @@ __device__ __forceinline__ float haar_w(int n, int dy, int dx) {
 // ---- DWT forward: in (B, 2h*2w, C) -> out (B, h*w, C).  One warp per output pixel.
 __global__ void __launch_bounds__(256) dwt_fwd_kernel(const float* __restrict__ in, float* __restrict__ out, int B, int h,
                                                       int w, int C) {
+    uwr_pdl_enter();
     const int lane = threadIdx.x & 31;
     const long long warp = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const long long nwarps = ((long long)gridDim.x * blockDim.x) >> 5;
@@ -61,6 +62,7 @@ __global__ void __launch_bounds__(256) dwt_fwd_kernel(const float* __restrict__ 
 // ---- DWT backward (reference formula): dout (B, h*w, C) -> din (B, 2h*2w, C)
 __global__ void __launch_bounds__(256) dwt_bwd_kernel(const float* __restrict__ dout, float* __restrict__ din, int B, int h,
                                                       int w, int C) {
+    uwr_pdl_enter();
     const int lane = threadIdx.x & 31;
     const long long warp = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const long long nwarps = ((long long)gridDim.x * blockDim.x) >> 5;
@@ -92,6 +94,7 @@ __global__ void __launch_bounds__(256) dwt_bwd_kernel(const float* __restrict__ 
 // ---- IDWT forward: in (B, h*w, C) -> out (B, 2h*2w, C); thread per (coarse pixel, group of 4 channels)
 __global__ void __launch_bounds__(256) idwt_fwd_kernel(const float* __restrict__ in, float* __restrict__ out, int B, int h,
                                                        int w, int C) {
+    uwr_pdl_enter();
     const int G = C / 4;
     const long long total = (long long)B * h * w * G;
     for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
@@ -116,6 +119,7 @@ __global__ void __launch_bounds__(256) idwt_fwd_kernel(const float* __restrict__
 // flat NCHW index f of dout[b] -> channel f / (4hw), row (f % 4hw) / 2w, column f % 2w.  One warp per (b, y, x).
 __global__ void __launch_bounds__(256) idwt_bwd_v_kernel(const float* __restrict__ dout, float* __restrict__ V, int B, int h,
                                                          int w, int C) {
+    uwr_pdl_enter();
     const int lane = threadIdx.x & 31;
     const long long warp = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const long long nwarps = ((long long)gridDim.x * blockDim.x) >> 5;
@@ -150,6 +154,7 @@ __global__ void __launch_bounds__(256) idwt_bwd_v_kernel(const float* __restrict
 // step 2: din (B, h*w, C): channel n*C/4 + c' at (Y, X) <- V_n[(c'*h*w + Y*w + X) mod (h*w/16)]
 __global__ void __launch_bounds__(256) idwt_bwd_scatter_kernel(const float* __restrict__ V, float* __restrict__ din, int B,
                                                                int h, int w, int C) {
+    uwr_pdl_enter();
     const long long total = (long long)B * h * w * C;
     const int q = C / 4;
     const long long m = (long long)h * w / 16;
@@ -175,21 +180,21 @@ int wl_blocks(long long work) {
 // h, w: the COARSE grid (the fine grid is 2h x 2w).  C % 4 == 0.
 extern "C" int uwr_haar_dwt_fwd(const float* in, float* out, int B, int h, int w, int C, uwr_stream_t stream_) {
     UWR_REQUIRE(in && out && B > 0 && h > 0 && w > 0 && C % 4 == 0, "uwr_haar_dwt_fwd: bad args (C %% 4 == 0)");
-    dwt_fwd_kernel<<<wl_blocks((long long)B * h * w * 32), 256, 0, (cudaStream_t)stream_>>>(in, out, B, h, w, C);
+    (void)uwr_launch_pdl(dwt_fwd_kernel, dim3(wl_blocks((long long)B * h * w * 32)), dim3(256), 0, (cudaStream_t)stream_, in, out, B, h, w, C);
     UWR_CHECK_LAUNCH("dwt_fwd_kernel");
     return 0;
 }
 
 extern "C" int uwr_haar_dwt_bwd(const float* dout, float* din, int B, int h, int w, int C, uwr_stream_t stream_) {
     UWR_REQUIRE(dout && din && B > 0 && h > 0 && w > 0 && C % 4 == 0, "uwr_haar_dwt_bwd: bad args (C %% 4 == 0)");
-    dwt_bwd_kernel<<<wl_blocks((long long)B * h * w * 32), 256, 0, (cudaStream_t)stream_>>>(dout, din, B, h, w, C);
+    (void)uwr_launch_pdl(dwt_bwd_kernel, dim3(wl_blocks((long long)B * h * w * 32)), dim3(256), 0, (cudaStream_t)stream_, dout, din, B, h, w, C);
     UWR_CHECK_LAUNCH("dwt_bwd_kernel");
     return 0;
 }
 
 extern "C" int uwr_haar_idwt_fwd(const float* in, float* out, int B, int h, int w, int C, uwr_stream_t stream_) {
     UWR_REQUIRE(in && out && B > 0 && h > 0 && w > 0 && C % 4 == 0, "uwr_haar_idwt_fwd: bad args (C %% 4 == 0)");
-    idwt_fwd_kernel<<<wl_blocks((long long)B * h * w * (C / 4)), 256, 0, (cudaStream_t)stream_>>>(in, out, B, h, w, C);
+    (void)uwr_launch_pdl(idwt_fwd_kernel, dim3(wl_blocks((long long)B * h * w * (C / 4))), dim3(256), 0, (cudaStream_t)stream_, in, out, B, h, w, C);
     UWR_CHECK_LAUNCH("idwt_fwd_kernel");
     return 0;
 }
@@ -200,9 +205,9 @@ extern "C" int uwr_haar_idwt_bwd(const float* dout, float* din, float* workspace
     cudaStream_t stream = (cudaStream_t)stream_;
     UWR_REQUIRE(dout && din && workspace && B > 0 && C % 4 == 0, "uwr_haar_idwt_bwd: bad args (C %% 4 == 0)");
     UWR_REQUIRE(h % 4 == 0 && w % 4 == 0 && h > 0 && w > 0, "uwr_haar_idwt_bwd: h and w must be multiples of 4");
-    idwt_bwd_v_kernel<<<wl_blocks((long long)B * (h / 4) * (w / 4) * 32), 256, 0, stream>>>(dout, workspace, B, h, w, C);
+    (void)uwr_launch_pdl(idwt_bwd_v_kernel, dim3(wl_blocks((long long)B * (h / 4) * (w / 4) * 32)), dim3(256), 0, stream, dout, workspace, B, h, w, C);
     UWR_CHECK_LAUNCH("idwt_bwd_v_kernel");
-    idwt_bwd_scatter_kernel<<<wl_blocks((long long)B * h * w * C), 256, 0, stream>>>(workspace, din, B, h, w, C);
+    (void)uwr_launch_pdl(idwt_bwd_scatter_kernel, dim3(wl_blocks((long long)B * h * w * C)), dim3(256), 0, stream, workspace, din, B, h, w, C);
     UWR_CHECK_LAUNCH("idwt_bwd_scatter_kernel");
     return 0;
 }

@@ -272,6 +272,7 @@ __device__ __forceinline__ void fusion_weights(const float* w_param, float& w0, 
 template <int HD>
 __global__ void __launch_bounds__(ATT_THREADS) attn_fwd_kernel(const AttnParams p, float* __restrict__ out,
                                                                long long ld_out) {
+    uwr_pdl_enter();
     constexpr int ST = HD + 4;
     extern __shared__ __align__(16) float smem[];
     float* Qs = smem;
@@ -360,6 +361,7 @@ __global__ void __launch_bounds__(ATT_THREADS, HD <= 32 ? 3 : 1) attn_bwd_kernel
                                                                               float* __restrict__ dq_buf,
                                                                               float* __restrict__ dkv_buf,
                                                                               float* __restrict__ partials) {
+    uwr_pdl_enter();
     constexpr int ST = HD + 4;
     // the transposed products dV = P^T dO and dK = dS^T q need P / dS in shared memory; K and V are dead
     // by then, so (for HD >= 32) the 64 x 72 staging buffer aliases their tiles
@@ -610,6 +612,7 @@ __global__ void attn_param_reduce_kernel(const float* __restrict__ partials, con
                                          float* __restrict__ dtable, float* __restrict__ dw, int heads,
                                          int ctas_per_head, int hd, float* __restrict__ dq_colsum,
                                          float* __restrict__ dkv_colsum, int q_off, int k_off, int v_off) {
+    uwr_pdl_enter();
     const int idx = blockIdx.x * blockDim.x + threadIdx.x;
     const int ps = bwd_part_stride(hd);
     if (idx < NBINS * heads) {
@@ -717,6 +720,7 @@ __global__ void __launch_bounds__(T5A_THREADS, 2)
 attn_fwd_t5_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_constant__ CUtensorMap mapK,
                    const __grid_constant__ CUtensorMap mapV, const AttnParams p, float* __restrict__ out,
                    long long ld_out) {
+    uwr_pdl_enter();
     using namespace uwr_tma;
     extern __shared__ uint8_t t5a_raw[];
     uint8_t* smem = t5a_raw + ((1024u - (smem_u32(t5a_raw) & 1023u)) & 1023u);
@@ -962,7 +966,7 @@ int launch_fwd_t5(const AttnParams& p, float* out, long long ld_out, cudaStream_
     }
     const long long items = (long long)p.B * (p.nW / 2) * p.heads;
     const int grid = (int)(items < 2LL * uwr_sm_count() ? items : 2LL * uwr_sm_count());
-    attn_fwd_t5_kernel<<<grid, T5A_THREADS, t5a_smem_bytes(p.heads), stream>>>(mq, mk, mv, p, out, ld_out);
+    (void)uwr_launch_pdl(attn_fwd_t5_kernel, dim3(grid), dim3(T5A_THREADS), t5a_smem_bytes(p.heads), stream, mq, mk, mv, p, out, ld_out);
     UWR_CHECK_LAUNCH("attn_fwd_t5_kernel");
     return 0;
 }
@@ -1038,7 +1042,7 @@ int launch_fwd(const AttnParams& p, float* out, long long ld_out, cudaStream_t s
         configured = true;
     }
     const long long tiles = (long long)p.B * p.nW * p.heads;
-    kern<<<(unsigned)tiles, ATT_THREADS, fwd_smem<HD>(), stream>>>(p, out, ld_out);
+    (void)uwr_launch_pdl(kern, dim3((unsigned)tiles), dim3(ATT_THREADS), fwd_smem<HD>(), stream, p, out, ld_out);
     UWR_CHECK_LAUNCH("attn_fwd_kernel");
     return 0;
 }
@@ -1052,7 +1056,7 @@ int launch_bwd_x(const AttnParams& p, const float* dout, long long ld_dout, floa
         UWR_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, bwd_smem<HD>()));
         configured = true;
     }
-    kern<<<dim3(cph, p.heads), ATT_THREADS, bwd_smem<HD>(), stream>>>(p, dout, ld_dout, dq, dkv, partials);
+    (void)uwr_launch_pdl(kern, dim3(dim3(cph, p.heads)), dim3(ATT_THREADS), bwd_smem<HD>(), stream, p, dout, ld_dout, dq, dkv, partials);
     UWR_CHECK_LAUNCH("attn_bwd_kernel");
     return 0;
 }
@@ -1123,7 +1127,7 @@ extern "C" int uwr_window_attn_bwd(const uwr_attn_desc* d, const float* dout, lo
     }
     if (rc) return rc;
     UWR_REQUIRE((d->dq_colsum == nullptr) == (d->dkv_colsum == nullptr), "uwr_window_attn_bwd: dq_colsum and dkv_colsum go together");
-    attn_param_reduce_kernel<<<uwr_cdiv((NBINS + 3 * d->head_dim) * d->heads, 128), 128, 0, stream>>>(
+    (void)uwr_launch_pdl(attn_param_reduce_kernel, dim3(uwr_cdiv((NBINS + 3 * d->head_dim) * d->heads, 128)), dim3(128), 0, stream, 
         workspace, d->w_param, dbias_table, dw, d->heads, cph, d->head_dim, d->dq_colsum, d->dkv_colsum, d->q_off, d->k_off,
         d->v_off);
     UWR_CHECK_LAUNCH("attn_param_reduce_kernel");

@@ -96,6 +96,7 @@ SIGNATURES = {
     "uwr_gemm_tf32": (c_int, [C.POINTER(GemmDesc), c_stream]),
     "uwr_gemm_tcgen05": (c_int, [C.POINTER(GemmDesc), c_stream]),
     "uwr_set_gemm_cluster": (c_int, [c_int]),
+    "uwr_set_pdl": (c_int, [c_int]),
     "uwr_gemm_tcgen05_supported": (c_int, [C.POINTER(GemmDesc)]),
     "uwr_convgemm_tcgen05_supported": (c_int, [C.POINTER(ConvGemmDesc)]),
     "uwr_convgemm_tcgen05_workspace_bytes": (c_sz, [C.POINTER(ConvGemmDesc)]),
