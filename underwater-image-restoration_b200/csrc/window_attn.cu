@@ -608,42 +608,56 @@ __global__ void __launch_bounds__(ATT_THREADS, HD <= 32 ? 3 : 1) attn_bwd_kernel
     }
 }
 
-__global__ void attn_param_reduce_kernel(const float* __restrict__ partials, const float* __restrict__ w_param,
-                                         float* __restrict__ dtable, float* __restrict__ dw, int heads,
-                                         int ctas_per_head, int hd, float* __restrict__ dq_colsum,
-                                         float* __restrict__ dkv_colsum, int q_off, int k_off, int v_off) {
+// One WARP per output element: lanes stride over the CTAs' partials (all loads independent), then a fixed-order shuffle
+// fold -- deterministic.  (One THREAD per element, the first version, walked up to 444 partials as a serial chain of L2
+// latencies, and thread 0 walked all heads x CTAs twice for the mixing-weight gradient: 29 us per launch under ncu, ten
+// launches per AST step, for a few KB of output.)
+__global__ void __launch_bounds__(128) attn_param_reduce_kernel(const float* __restrict__ partials,
+                                                                const float* __restrict__ w_param, float* __restrict__ dtable,
+                                                                float* __restrict__ dw, int heads, int ctas_per_head, int hd,
+                                                                float* __restrict__ dq_colsum, float* __restrict__ dkv_colsum,
+                                                                int q_off, int k_off, int v_off) {
     uwr_pdl_enter();
-    const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+    const int idx = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
     const int ps = bwd_part_stride(hd);
-    if (idx < NBINS * heads) {
+    const int n_table = NBINS * heads, n_all = (NBINS + 3 * hd) * heads;
+    if (idx < n_table) {
         const int bin = idx / heads, h = idx % heads;
         float s = 0.f;
-        for (int c = 0; c < ctas_per_head; ++c) s += partials[((long long)h * ctas_per_head + c) * ps + bin];
-        dtable[idx] = s;
-    } else if (dq_colsum != nullptr && idx < (NBINS + 3 * hd) * heads) {
+        for (int c = lane; c < ctas_per_head; c += 32) s += partials[((long long)h * ctas_per_head + c) * ps + bin];
+        s = warp_sum(s);
+        if (lane == 0) dtable[idx] = s;
+    } else if (idx < n_all) {
+        if (dq_colsum == nullptr) return;
         // column sums of dq | dk | dv, written with the column addressing of dq_buf / dkv_buf
-        const int j = idx - NBINS * heads;
+        const int j = idx - n_table;
         const int h = j / (3 * hd), r = j % (3 * hd), which = r / hd, c = r % hd;
         float s = 0.f;
-        for (int k = 0; k < ctas_per_head; ++k) s += partials[((long long)h * ctas_per_head + k) * ps + NBINS + 3 + r];
-        if (which == 0) dq_colsum[q_off + h * hd + c] = s;
-        else dkv_colsum[(which == 1 ? k_off : v_off) + h * hd + c] = s;
-    }
-    if (idx == 0 && dw != nullptr) {
+        for (int k = lane; k < ctas_per_head; k += 32) s += partials[((long long)h * ctas_per_head + k) * ps + NBINS + 3 + r];
+        s = warp_sum(s);
+        if (lane == 0) {
+            if (which == 0) dq_colsum[q_off + h * hd + c] = s;
+            else dkv_colsum[(which == 1 ? k_off : v_off) + h * hd + c] = s;
+        }
+    } else if (idx == n_all && dw != nullptr) {
         float g1 = 0.f, g2 = 0.f;
-        for (int i = 0; i < heads * ctas_per_head; ++i) {
+        for (int i = lane; i < heads * ctas_per_head; i += 32) {
             g1 += partials[(long long)i * ps + NBINS];
             g2 += partials[(long long)i * ps + NBINS + 1];
         }
-        float w0 = 1.f, w1 = 0.f;
-        if (w_param) {
-            const float e0 = expf(w_param[0]), e1 = expf(w_param[1]);
-            w0 = e0 / (e0 + e1);
-            w1 = e1 / (e0 + e1);
+        g1 = warp_sum(g1);
+        g2 = warp_sum(g2);
+        if (lane == 0) {
+            float w0 = 1.f, w1 = 0.f;
+            if (w_param) {
+                const float e0 = expf(w_param[0]), e1 = expf(w_param[1]);
+                w0 = e0 / (e0 + e1);
+                w1 = e1 / (e0 + e1);
+            }
+            const float mix = w0 * g1 + w1 * g2;
+            dw[0] = w0 * (g1 - mix);
+            dw[1] = w1 * (g2 - mix);
         }
-        const float mix = w0 * g1 + w1 * g2;
-        dw[0] = w0 * (g1 - mix);
-        dw[1] = w1 * (g2 - mix);
     }
 }
 
@@ -1127,7 +1141,8 @@ extern "C" int uwr_window_attn_bwd(const uwr_attn_desc* d, const float* dout, lo
     }
     if (rc) return rc;
     UWR_REQUIRE((d->dq_colsum == nullptr) == (d->dkv_colsum == nullptr), "uwr_window_attn_bwd: dq_colsum and dkv_colsum go together");
-    (void)uwr_launch_pdl(attn_param_reduce_kernel, dim3(uwr_cdiv((NBINS + 3 * d->head_dim) * d->heads, 128)), dim3(128), 0, stream, 
+    // one warp per output element (+ one for the mixing-weight gradient), four warps per CTA
+    (void)uwr_launch_pdl(attn_param_reduce_kernel, dim3(uwr_cdiv((NBINS + 3 * d->head_dim) * d->heads + 1, 4)), dim3(128), 0, stream, 
         workspace, d->w_param, dbias_table, dw, d->heads, cph, d->head_dim, d->dq_colsum, d->dkv_colsum, d->q_off, d->k_off,
         d->v_off);
     UWR_CHECK_LAUNCH("attn_param_reduce_kernel");

@@ -20,6 +20,52 @@ def _trunc_normal_(t, std=0.02):
     return nn.init.trunc_normal_(t, mean=0.0, std=std, a=-2.0, b=2.0)
 
 
+class DropPathPool:
+    """All DropPath scale vectors of one forward pass drawn by TWO kernels instead of two per residual branch.
+
+    A training forward of AST asks for 36 per-sample scale vectors (18 blocks x attention / FFN branch), each a
+    `bernoulli_` + `div_` on `batch` floats: 72 launches of ~2 us in the step's CUDA graph.  The pool learns the
+    sequence of requests (module, keep probability) during the first training forward, and from then on draws the whole
+    (requests, batch) matrix at the top of the forward -- `torch.bernoulli` of the per-row keep probabilities, divided by
+    them -- and hands out its rows.  Same distribution per row (independent Bernoulli(keep_i) / keep_i, timm semantics);
+    a request that does not match the learnt sequence (injected masks, a patched `scale`, another batch size) falls back
+    to the per-call draw."""
+
+    def __init__(self):
+        self.order = None      # ids of the DropPath modules in request order
+        self.keep = None       # (requests, 1) keep probabilities on the device
+        self.rows = None
+        self.i = 0
+        self.recording = None
+
+    def begin(self, batch, device):
+        self.rows, self.i = None, 0
+        if self.order is None:
+            self.recording = []
+        elif self.order:
+            if self.keep.device != device:
+                self.keep = self.keep.to(device)
+            self.rows = torch.bernoulli(self.keep.expand(-1, batch)).div_(self.keep)
+
+    def take(self, mod, batch, device):
+        if self.rows is not None:
+            if self.i < len(self.order) and self.order[self.i] == id(mod) and self.rows.shape[1] == batch:
+                self.i += 1
+                return self.rows[self.i - 1]
+            self.rows = None   # out of sequence: the rest of this forward draws per call
+        if self.recording is not None:
+            self.recording.append((id(mod), 1.0 - mod.drop_prob))
+        return None
+
+    def end(self, device):
+        if self.recording is not None:
+            self.order = [m for m, _ in self.recording]
+            if self.order:
+                self.keep = torch.tensor([[k] for _, k in self.recording], dtype=torch.float32, device=device)
+            self.recording = None
+        self.rows = None
+
+
 class DropPath(nn.Module):
     """timm DropPath semantics expressed as a per-sample scale vector that the
     residual GEMM epilogue consumes; `forced` lets parity tests inject the reference's masks."""
@@ -28,12 +74,17 @@ class DropPath(nn.Module):
         super().__init__()
         self.drop_prob = drop_prob
         self.forced = None
+        self.pool = None       # DropPathPool of the owning model (AST), if any
 
     def scale(self, batch, device):
         if self.forced is not None:
             return self.forced.to(device=device, dtype=torch.float32).reshape(batch).contiguous()
         if self.drop_prob == 0.0 or not self.training:
             return None
+        if self.pool is not None:
+            row = self.pool.take(self, batch, device)
+            if row is not None:
+                return row
         keep = 1.0 - self.drop_prob
         m = torch.empty(batch, device=device, dtype=torch.float32).bernoulli_(keep)
         return m.div_(keep)
@@ -359,6 +410,11 @@ class AST(nn.Module):
         self.decoderlayer_3 = layer(2, 0, 8, dec_dpr[sum(depths[5:8]):sum(depths[5:9])], True)
 
         self.apply(self._init_weights)
+        # one pool of DropPath draws per forward (a plain attribute: no parameters, nothing in the state_dict)
+        object.__setattr__(self, "_dp_pool", DropPathPool())
+        for m in self.modules():
+            if isinstance(m, DropPath):
+                m.pool = self._dp_pool
 
     def _init_weights(self, m):
         if isinstance(m, nn.Linear):
@@ -396,6 +452,16 @@ class AST(nn.Module):
         if not x.is_cuda:
             raise RuntimeError("uwr AST runs on CUDA (B200) only; there is no CPU fallback")
         x = x.contiguous().float()
+        pool = self._dp_pool if self.training else None
+        if pool is not None:
+            pool.begin(x.shape[0], x.device)
+        try:
+            return self._forward(x, mask)
+        finally:
+            if pool is not None:
+                pool.end(x.device)
+
+    def _forward(self, x, mask):
         y = self.input_proj(x)
         conv0 = self.encoderlayer_0(y, mask=mask)
         pool0 = self.dowsample_0(conv0)
