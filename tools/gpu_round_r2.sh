@@ -5,6 +5,7 @@
 set -x
 TAG=${1:-r2}
 mkdir -p gpurun_out
+python -m pytest tests -m gpu -x -q > gpurun_out/pytest_gpu_$TAG.log 2>&1; tail -2 gpurun_out/pytest_gpu_$TAG.log
 python bench.py --steps 10 --warmup 3 --profile-out gpurun_out/prof_b16_$TAG.json > gpurun_out/bench_$TAG.log 2>gpurun_out/bench_$TAG.err; cat gpurun_out/bench_$TAG.log
 python bench.py --impl reference --steps 3 --warmup 1 > gpurun_out/bench_ref_$TAG.log 2>&1; tail -1 gpurun_out/bench_ref_$TAG.log
 python bench.py --steps 2 --warmup 3 --no-cpu-baseline --no-gpu-eager --no-graph > gpurun_out/plain_launch_$TAG.log 2>&1 &&
@@ -18,6 +19,12 @@ ncu -i gpurun_out/ncu_top_$TAG.ncu-rep --page raw --csv > gpurun_out/ncu_top_$TA
 cat gpurun_out/plain_kb_$TAG.log
 UWR_EAGER_REF=1 UWR_PROFILE_OUT=gpurun_out/prof_spectral_$TAG.json python tools/train_bench.py SpectralTransformer L1withColor 8 > gpurun_out/train_spectral_$TAG.log 2>&1; tail -1 gpurun_out/train_spectral_$TAG.log | cut -c1-600
 UWR_EAGER_REF=1 UWR_PROFILE_OUT=gpurun_out/prof_newbig_$TAG.json python tools/train_bench.py NewBigFRFNModel fflMix 16 > gpurun_out/train_newbig_$TAG.log 2>&1; tail -1 gpurun_out/train_newbig_$TAG.log | cut -c1-600
+# programmatic dependent launch (opt-in): the launch-bound configs with it, and the headline config with it
+UWR_PDL=1 python tools/train_bench.py SpectralTransformer L1withColor 8 > gpurun_out/train_spectral_pdl_$TAG.log 2>&1; tail -1 gpurun_out/train_spectral_pdl_$TAG.log | cut -c1-330
+UWR_PDL=1 python tools/train_bench.py NewBigFRFNModel fflMix 16 > gpurun_out/train_newbig_pdl_$TAG.log 2>&1; tail -1 gpurun_out/train_newbig_pdl_$TAG.log | cut -c1-330
+UWR_PDL=1 python bench.py --steps 20 --warmup 5 --no-cpu-baseline --no-gpu-eager > gpurun_out/bench_pdl_$TAG.log 2>/dev/null; cut -c1-200 gpurun_out/bench_pdl_$TAG.log
 python tests/tools/infer_sweep.py > gpurun_out/infer_sweep_$TAG.log 2>&1; tail -3 gpurun_out/infer_sweep_$TAG.log
 ls -la gpurun_out | tail -20; du -sh gpurun_out
+# micro-benchmarks behind DESIGN.md §9: HBM ceiling per read:write mix, graph node cost with / without PDL, L2-sized chunks
+(tools/micro/rw_mix; tools/micro/pdl_gap; python tools/micro/l2_chunk_ffn.py) > gpurun_out/micro_$TAG.txt 2>&1; cat gpurun_out/micro_$TAG.txt
 tools/micro/ffma2_bench > gpurun_out/ffma2_$TAG.txt 2>&1; cat gpurun_out/ffma2_$TAG.txt | tail -3

@@ -80,7 +80,11 @@ __device__ __forceinline__ uint32_t pack_half2(float a, float b) {
 // ---------------------------------------------------------------------------------- PTX wrappers
 // -------------------------------------------------------------------------------------- kernel
 template <int BN>
-__host__ __device__ constexpr int t5_stages() { return BN >= 256 ? 3 : 4; }
+// Ring depth: what matters is the BYTES in flight per SM (HBM latency x the SM's share of the bandwidth is ~45 KB).  A stage
+// of a narrow tile carries little -- BN = 32: 16 KB of A + 4 KB of B, and for a thin weight gradient (M = 32) only 4 KB of
+// that A tile is inside the matrix -- so narrow tiles get a deeper ring (same box: SpectralTransformer, whose GEMMs are
+// mostly N, M <= 64, 228 -> 238 img/s; AST +0.4 %; one stage more again changed nothing).
+__host__ __device__ constexpr int t5_stages() { return BN >= 256 ? 3 : (BN >= 128 ? 4 : (BN >= 64 ? 6 : 8)); }
 template <int BN>
 __host__ __device__ constexpr int t5_smem_bytes() {
     return t5_stages<BN>() * (TM * KC * 4 + BN * KC * 4) + 256 + BN * 4 + EPI_WARPS * 32 * EP_STRIDE * 4 + 1024;
