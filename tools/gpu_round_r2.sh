@@ -26,5 +26,6 @@ UWR_PDL=1 python bench.py --steps 20 --warmup 5 --no-cpu-baseline --no-gpu-eager
 python tests/tools/infer_sweep.py > gpurun_out/infer_sweep_$TAG.log 2>&1; tail -3 gpurun_out/infer_sweep_$TAG.log
 ls -la gpurun_out | tail -20; du -sh gpurun_out
 # micro-benchmarks behind DESIGN.md §9: HBM ceiling per read:write mix, graph node cost with / without PDL, L2-sized chunks
+for m in rw_mix pdl_gap ffma2_bench; do [ -x tools/micro/$m ] || nvcc -gencode arch=compute_100a,code=sm_100a -O3 -o tools/micro/$m tools/micro/$m.cu; done
 (tools/micro/rw_mix; tools/micro/pdl_gap; python tools/micro/l2_chunk_ffn.py) > gpurun_out/micro_$TAG.txt 2>&1; cat gpurun_out/micro_$TAG.txt
 tools/micro/ffma2_bench > gpurun_out/ffma2_$TAG.txt 2>&1; cat gpurun_out/ffma2_$TAG.txt | tail -3
