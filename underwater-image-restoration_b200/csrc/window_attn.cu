@@ -106,6 +106,15 @@ __device__ __forceinline__ void stage_tiles(const TileSrc<HD> (&t)[NT], const lo
     }
 }
 
+// ldmatrix.x4 of 32-bit data viewed as pairs of .b16: four 8-row x 16-byte matrices, lanes 8m .. 8m+7 give the row
+// addresses of matrix m, lane l receives the 32-bit word (l % 4) of row (l / 4) of each matrix
+__device__ __forceinline__ void ldsm_x4(uint32_t (&r)[4], uint32_t addr) {
+    asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0, %1, %2, %3}, [%4];"
+                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3])
+                 : "r"(addr)
+                 : "memory");
+}
+
 // 3xTF32 operand split.  The tensor core reads only the upper 19 bits of an fp32 operand (it
 // truncates), so the "hi" part is the raw value itself and "lo" is what the truncation drops:
 // lo = x - trunc(x), exact in fp32 (13 significant bits; the hardware truncating it again loses
@@ -134,21 +143,35 @@ __device__ __forceinline__ void mma_rows_x_rowsT(float (&acc)[8][4], const float
     for (int nt = 0; nt < 8; ++nt)
 #pragma unroll
         for (int c = 0; c < 4; ++c) acc[nt][c] = 0.f;
+    // Fragment loads by ldmatrix: a row of an 8x8 .b16 matrix is 16 bytes = four fp32 words, and lane l receives word
+    // (l % 4) of row (l / 4) -- exactly element (g, t) of the m16n8k8 TF32 fragments when both operands are stored
+    // [row][k] (rows 16-byte aligned, stride HD + 4 floats: the eight row addresses of a matrix fall into distinct bank
+    // groups).  One .x4 = the whole A fragment, or the B fragments of two column tiles: 5 shared-memory instructions per
+    // k step instead of 20 scalar loads (the backward was limited by shared-memory instruction issue).
+    const int lane = g * 4 + t, lm = lane >> 3, lr = lane & 7;
+    const uint32_t a_addr = (uint32_t)__cvta_generic_to_shared(A + (r0 + (lm & 1) * 8 + lr) * ST + (lm >> 1) * 4);
+    const uint32_t b_addr = (uint32_t)__cvta_generic_to_shared(Bm + ((lm >> 1) * 8 + lr) * ST + (lm & 1) * 4);
 #pragma unroll
     for (int ks = 0; ks < HD / 8; ++ks) {
         uint32_t ah[4], al[4];
-        split_tf32(A[(r0 + g) * ST + ks * 8 + t], ah[0], al[0]);
-        split_tf32(A[(r0 + g + 8) * ST + ks * 8 + t], ah[1], al[1]);
-        split_tf32(A[(r0 + g) * ST + ks * 8 + t + 4], ah[2], al[2]);
-        split_tf32(A[(r0 + g + 8) * ST + ks * 8 + t + 4], ah[3], al[3]);
+        {
+            uint32_t r[4];
+            ldsm_x4(r, a_addr + ks * 32);
+#pragma unroll
+            for (int c = 0; c < 4; ++c) split_tf32(__uint_as_float(r[c]), ah[c], al[c]);
+        }
         // the three passes run over all eight column tiles before the next pass touches the same
         // accumulator: eight independent MMAs between dependent ones (back-to-back dependent MMAs
         // left the tensor pipe waiting on its own latency)
         uint32_t bh[8][2], bl[8][2];
 #pragma unroll
-        for (int nt = 0; nt < 8; ++nt) {
-            split_tf32(Bm[(nt * 8 + g) * ST + ks * 8 + t], bh[nt][0], bl[nt][0]);
-            split_tf32(Bm[(nt * 8 + g) * ST + ks * 8 + t + 4], bh[nt][1], bl[nt][1]);
+        for (int np = 0; np < 4; ++np) {
+            uint32_t r[4];
+            ldsm_x4(r, b_addr + (np * 16 * ST + ks * 8) * 4);
+            split_tf32(__uint_as_float(r[0]), bh[2 * np][0], bl[2 * np][0]);
+            split_tf32(__uint_as_float(r[1]), bh[2 * np][1], bl[2 * np][1]);
+            split_tf32(__uint_as_float(r[2]), bh[2 * np + 1][0], bl[2 * np + 1][0]);
+            split_tf32(__uint_as_float(r[3]), bh[2 * np + 1][1], bl[2 * np + 1][1]);
         }
         if (!x3 && !EXACT) {  // single pass: operands rounded to nearest (a raw value would be truncated)
 #pragma unroll
