@@ -376,7 +376,12 @@ def run_ours(args):
                          "arithmetic_intensity": ai,
                          "top_shape": {"shape": top["shape"], "ms_per_launch": top["ms_avg"], "gbs": top["gbs"],
                                        "tflops": top["tflops"], "launches": top["launches"]},
-                         "peak_source": f"MEASURED_PEAKS.json ({src}); tf32 peak = bf16 sustained / 2"})
+                         "peak_source": f"MEASURED_PEAKS.json ({src}); tf32 peak = bf16 sustained / 2",
+                         # context, not the denominator: the copy peak is a 1:1 read:write figure; a plain float4 stream
+                         # kernel on the same GPUs reaches 5.5 TB/s at 1 read : 4 writes (the fp32-C streaming shapes of
+                         # this family) and 5.9 TB/s at 1:1 (tools/micro/rw_mix.cu, profiles/r2_micro_benchmarks.txt)
+                         "mix_ceiling_note": "memory system at 1:4 read:write 5.5 TB/s, 1:1 5.9 TB/s, read-only 7.0 TB/s "
+                                             "(tools/micro/rw_mix.cu); frac is against the copy peak as the contract asks"})
         if args.profile_out:
             os.makedirs(os.path.dirname(os.path.abspath(args.profile_out)), exist_ok=True)
             with open(args.profile_out, "w") as f:
