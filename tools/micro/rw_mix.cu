@@ -4,7 +4,7 @@
 #include <cstdio>
 #include <cuda_runtime.h>
 
-template <int NR, int NW>
+template <int NR, int NW, bool CS = false>
 __global__ void __launch_bounds__(512) mix(const float4* __restrict__ in, float4* __restrict__ out, long long n) {
     // per iteration: NR loads from NR disjoint input streams, NW stores to NW disjoint output streams
     const long long stride = (long long)gridDim.x * blockDim.x;
@@ -16,25 +16,28 @@ __global__ void __launch_bounds__(512) mix(const float4* __restrict__ in, float4
             a.x += v.x; a.y += v.y; a.z += v.z; a.w += v.w;
         }
 #pragma unroll
-        for (int w = 0; w < NW; ++w) out[w * n + i] = a;
+        for (int w = 0; w < NW; ++w) {
+            if (CS) __stcs(out + w * n + i, a);   // streaming (evict-first) stores
+            else out[w * n + i] = a;
+        }
         if (NW == 0 && a.x == 12345.678f) out[0] = a;   // keeps the loads alive
     }
 }
 
-template <int NR, int NW>
+template <int NR, int NW, bool CS = false>
 void run(const float4* in, float4* out, long long total_f4) {
     const long long n = total_f4 / (NR + NW > 0 ? (NR > NW ? NR : NW) : 1) / 4 * 4 / 2;   // keep every stream in range
     cudaEvent_t e0, e1;
     cudaEventCreate(&e0); cudaEventCreate(&e1);
-    for (int rep = 0; rep < 2; ++rep) mix<NR, NW><<<148 * 4, 512>>>(in, out, n);
+    for (int rep = 0; rep < 2; ++rep) mix<NR, NW, CS><<<148 * 4, 512>>>(in, out, n);
     cudaEventRecord(e0);
     const int reps = 5;
-    for (int rep = 0; rep < reps; ++rep) mix<NR, NW><<<148 * 4, 512>>>(in, out, n);
+    for (int rep = 0; rep < reps; ++rep) mix<NR, NW, CS><<<148 * 4, 512>>>(in, out, n);
     cudaEventRecord(e1);
     cudaEventSynchronize(e1);
     float ms; cudaEventElapsedTime(&ms, e0, e1); ms /= reps;
     const double bytes = 16.0 * n * (NR + NW);
-    printf("read:write %d:%d  %8.3f ms  %7.0f GB/s  (%.2f GB per launch)\n", NR, NW, ms, bytes / ms / 1e6, bytes / 1e9);
+    printf("read:write %d:%d%s  %8.3f ms  %7.0f GB/s  (%.2f GB per launch)\n", NR, NW, CS ? " (st.cs)" : "", ms, bytes / ms / 1e6, bytes / 1e9);
 }
 
 int main() {
@@ -49,6 +52,10 @@ int main() {
     run<1, 2>(in, out, total_f4);
     run<1, 4>(in, out, total_f4);
     run<0, 1>(in, out, total_f4);
+    run<1, 1, true>(in, out, total_f4);
+    run<1, 2, true>(in, out, total_f4);
+    run<1, 4, true>(in, out, total_f4);
+    run<0, 1, true>(in, out, total_f4);
     printf("%s\n", cudaGetErrorString(cudaDeviceSynchronize()));
     return 0;
 }
