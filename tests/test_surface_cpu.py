@@ -263,3 +263,47 @@ def test_persistent_grids_fit_one_resident_wave(build_lib):
         assert total <= k * sms and (total > k * sms - heads or per_head == tiles), (heads, hd, per_head, k)
         if not torch.cuda.is_available():
             assert k == 1
+
+
+def test_droppath_pool_hands_out_independent_scaled_bernoulli_rows():
+    """uwr.ast.DropPathPool (host logic, device-agnostic): after the request sequence of one training forward has been
+    learnt, all scale vectors of a forward come from ONE (requests, batch) draw -- every row is 0 or 1 / keep_i for ITS
+    module's keep probability, rows follow the request order, and anything out of sequence falls back to per-call draws."""
+    from uwr.ast import AST, DropPath
+    torch.manual_seed(0)
+    m = AST(img_size=128).train()
+    pool = m._dp_pool
+    dps = [x for x in m.modules() if isinstance(x, DropPath)]
+    assert dps and all(d.pool is pool for d in dps)
+    assert "_dp_pool" not in m.state_dict() and len(m.state_dict()) == 274
+    dev = torch.device("cpu")
+    seq = [d for d in dps for _ in range(2)]                      # attention branch, then FFN branch, per block
+    pool.begin(4, dev)
+    first = [d.scale(4, dev) for d in seq]                        # learning pass: per-call draws
+    pool.end(dev)
+    assert pool.order == [id(d) for d in seq] and pool.keep.shape == (len(seq), 1)
+    pool.begin(4, dev)
+    rows = [d.scale(4, dev) for d in seq]
+    assert pool.i == len(seq) and all(r.data_ptr() == pool.rows[i].data_ptr() for i, r in enumerate(rows))
+    pool.end(dev)
+    for d, r, f in zip(seq, rows, first):
+        keep = 1.0 - d.drop_prob
+        for v in (r, f):
+            assert v.shape == (4,) and bool(((v == 0) | ((v - 1.0 / keep).abs() < 1e-6)).all())
+    # statistics of a large draw: mean of every row ~ 1 (E[bernoulli(keep) / keep] = 1)
+    pool.begin(20000, dev)
+    big = pool.rows.clone()
+    pool.end(dev)
+    assert big.shape == (len(seq), 20000) and float((big.mean(dim=1) - 1.0).abs().max()) < 0.02
+    # out of sequence (another module asks first): the pool steps aside for the rest of that forward
+    pool.begin(4, dev)
+    v = seq[-1].scale(4, dev)
+    assert pool.rows is None and v.shape == (4,)
+    pool.end(dev)
+    # injected masks bypass the pool altogether
+    seq[0].forced = torch.tensor([1.0, 0.0, 1.0, 0.0])
+    pool.begin(4, dev)
+    assert torch.equal(seq[0].scale(4, dev), seq[0].forced)
+    pool.end(dev)
+    m.eval()
+    assert dps[-1].scale(4, dev) is None
